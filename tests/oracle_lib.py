@@ -1,0 +1,256 @@
+"""ctypes binding of oracle/liboracle.so -- the CPU checker.  Imported by tests only
+(and by bench.py's cpu_baseline leg / __graft_entry__.smoke through the same file)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+LIB_PATH = os.path.join(ORACLE_DIR, "liboracle.so")
+
+u8p = C.POINTER(C.c_uint8)
+f32p = C.POINTER(C.c_float)
+f64p = C.POINTER(C.c_double)
+
+
+class ReccResult(C.Structure):
+    _fields_ = [
+        ("dcc", C.c_uint8 * 7), ("dcc_errs", C.c_uint8),
+        ("words", (C.c_uint8 * 240) * 7),
+        ("errs", C.c_uint16 * 7),
+        ("valid", C.c_uint8 * 7), ("valid_repeat", C.c_uint8 * 7),
+        ("F", C.c_uint8), ("NAWC", C.c_uint8), ("T", C.c_uint8), ("S", C.c_uint8), ("E", C.c_uint8),
+        ("ER", C.c_uint8), ("SCM", C.c_uint8),
+        ("MIN1", C.c_uint32),
+        ("B_F", C.c_uint8), ("B_NAWC", C.c_uint8), ("MSG_TYPE", C.c_uint8), ("ORDQ", C.c_uint8),
+        ("ORDER", C.c_uint8), ("LT", C.c_uint8), ("EP", C.c_uint8), ("SCM4", C.c_uint8), ("MPCI", C.c_uint8),
+        ("SDCC1", C.c_uint8), ("SDCC2", C.c_uint8),
+        ("MIN2", C.c_uint16),
+        ("word_c_serial", C.c_uint32),
+        ("kind", C.c_int32),
+        ("esn", C.c_uint32),
+        ("min", C.c_char * 11),
+        ("dialed", C.c_char * 33),
+    ]
+
+
+class Burst(C.Structure):
+    _fields_ = [("d_index", C.c_uint64), ("corr", C.c_float), ("symbols", C.c_uint8 * 3374)]
+
+
+BURST_CB = C.CFUNCTYPE(None, u8p, C.c_void_p)
+
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    if force or not os.path.exists(LIB_PATH):
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "-B" if force else "-s", "liboracle.so"])
+    return LIB_PATH
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    build()
+    L = C.CDLL(LIB_PATH)
+    L.orc_bch_encode_40_28.argtypes = [u8p, u8p]
+    L.orc_bch_encode_48_36.argtypes = [u8p, u8p]
+    L.orc_bch_decode_48.argtypes = [u8p, u8p]
+    L.orc_bch_decode_48.restype = C.c_int
+    L.orc_bch_syndromes63.argtypes = [u8p]
+    L.orc_bch_syndromes63.restype = C.c_uint32
+    L.orc_focc_new.restype = C.c_void_p
+    L.orc_focc_new.argtypes = [C.c_ulong, C.c_int]
+    L.orc_focc_free.argtypes = [C.c_void_p]
+    L.orc_focc_work.argtypes = [C.c_void_p, u8p, C.c_int]
+    L.orc_focc_push_words.argtypes = [C.c_void_p, C.c_long, u8p, C.c_long]
+    L.orc_focc_superframe_frames.argtypes = [C.c_void_p]
+    L.orc_fvc_new.restype = C.c_void_p
+    L.orc_fvc_new.argtypes = [C.c_ulong]
+    L.orc_fvc_free.argtypes = [C.c_void_p]
+    L.orc_fvc_push_words.argtypes = [C.c_void_p, u8p, C.c_long, C.c_int, C.c_uint64]
+    L.orc_fvc_work.argtypes = [C.c_void_p, u8p, C.c_int, C.POINTER(C.c_int)]
+    L.orc_recc_new.restype = C.c_void_p
+    L.orc_recc_free.argtypes = [C.c_void_p]
+    L.orc_recc_trigger.argtypes = [u8p]
+    L.orc_recc_work.argtypes = [C.c_void_p, u8p, C.c_int, BURST_CB, C.c_void_p]
+    L.orc_recc_buflen.argtypes = [C.c_void_p]
+    L.orc_recc_buflen.restype = C.c_size_t
+    L.orc_manchester_decode.argtypes = [u8p, u8p, C.c_size_t]
+    L.orc_manchester_decode.restype = C.c_size_t
+    L.orc_recc_decode.argtypes = [u8p, C.POINTER(ReccResult)]
+    L.orc_firdes_low_pass.argtypes = [C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, f32p, C.c_int]
+    L.orc_nco_fcw.argtypes = [C.c_double, C.c_double]
+    L.orc_nco_fcw.restype = C.c_uint32
+    L.orc_rx_chain_f64.argtypes = [f32p, C.c_size_t, C.c_uint32, f32p, C.c_int, f64p, f64p]
+    L.orc_rx_chain_f32.argtypes = [f32p, C.c_size_t, C.c_uint32, f32p, C.c_int, f32p, f32p]
+    L.orc_rx_detect.argtypes = [f32p, C.c_size_t, C.POINTER(Burst), C.c_int]
+    L.orc_cpu_baseline_run.argtypes = [f32p, C.c_size_t, C.c_uint32, f32p, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    L.orc_cpu_baseline_run.restype = C.c_double
+    for name in ("orc_overhead_word_1", "orc_overhead_word_2", "orc_control_filler_word"):
+        getattr(L, name).restype = None
+    L.orc_extract_min_3.argtypes = [C.c_uint64, C.c_char_p]
+    L.orc_calc_min.argtypes = [C.c_uint64, C.c_uint64, C.c_char_p]
+    L.orc_parse_min.argtypes = [C.c_char_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    _lib = L
+    return L
+
+
+def as_u8(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a, dtype=np.uint8))
+
+
+def ptr(a: np.ndarray, t):
+    return a.ctypes.data_as(t)
+
+
+def bch_encode_40_28(bits28) -> np.ndarray:
+    i = as_u8(bits28)
+    o = np.zeros(40, np.uint8)
+    lib().orc_bch_encode_40_28(ptr(i, u8p), ptr(o, u8p))
+    return o
+
+
+def bch_encode_48_36(bits36) -> np.ndarray:
+    i = as_u8(bits36)
+    o = np.zeros(48, np.uint8)
+    lib().orc_bch_encode_48_36(ptr(i, u8p), ptr(o, u8p))
+    return o
+
+
+def bch_decode_48(bits48):
+    i = as_u8(bits48)
+    o = np.zeros(48, np.uint8)
+    ok = lib().orc_bch_decode_48(ptr(i, u8p), ptr(o, u8p))
+    return bool(ok), o
+
+
+def lpf_taps() -> np.ndarray:
+    """lpf_taps of grc/ampsbs.grc:138-184: firdes.low_pass(3, 400e3, 10e3, 4.5e3, BLACKMAN)."""
+    n = lib().orc_firdes_low_pass(3.0, 400e3, 10e3, 4500.0, 2, None, 0)
+    t = np.zeros(n, np.float32)
+    lib().orc_firdes_low_pass(3.0, 400e3, 10e3, 4500.0, 2, ptr(t, f32p), n)
+    return t
+
+
+def firdes_low_pass(gain, fs, fc, tw, window=0) -> np.ndarray:
+    n = lib().orc_firdes_low_pass(gain, fs, fc, tw, window, None, 0)
+    t = np.zeros(n, np.float32)
+    lib().orc_firdes_low_pass(gain, fs, fc, tw, window, ptr(t, f32p), n)
+    return t
+
+
+def iq_f32(x: np.ndarray) -> np.ndarray:
+    x = np.ascontiguousarray(x.astype(np.complex64, copy=False))
+    return x.view(np.float32)
+
+
+def rx_chain_f32(x: np.ndarray, center=-160e3, fs=10e6, taps=None):
+    iq = iq_f32(x)
+    n = len(x) - len(x) % 50
+    taps = lpf_taps() if taps is None else taps
+    fcw = lib().orc_nco_fcw(center, fs)
+    y = np.zeros(2 * (n // 50), np.float32)
+    d = np.zeros(n // 50, np.float32)
+    lib().orc_rx_chain_f32(ptr(iq, f32p), n, fcw, ptr(taps, f32p), len(taps), ptr(y, f32p), ptr(d, f32p))
+    return y.view(np.complex64), d
+
+
+def rx_chain_f64(x: np.ndarray, center=-160e3, fs=10e6, taps=None):
+    iq = iq_f32(x)
+    n = len(x) - len(x) % 50
+    taps = lpf_taps() if taps is None else taps
+    fcw = lib().orc_nco_fcw(center, fs)
+    y = np.zeros(2 * (n // 50), np.float64)
+    d = np.zeros(n // 50, np.float64)
+    lib().orc_rx_chain_f64(ptr(iq, f32p), n, fcw, ptr(taps, f32p), len(taps), ptr(y, f64p), ptr(d, f64p))
+    return y.view(np.complex128), d
+
+
+def rx_detect(d: np.ndarray, max_bursts=64):
+    d = np.ascontiguousarray(d, dtype=np.float32)
+    arr = (Burst * max_bursts)()
+    n = lib().orc_rx_detect(ptr(d, f32p), len(d), arr, max_bursts)
+    return [(int(arr[i].d_index), float(arr[i].corr), np.frombuffer(bytes(arr[i].symbols), np.uint8).copy()) for i in range(n)]
+
+
+def recc_decode(blob) -> ReccResult:
+    b = as_u8(blob)
+    assert len(b) == 3374
+    r = ReccResult()
+    lib().orc_recc_decode(ptr(b, u8p), C.byref(r))
+    return r
+
+
+class Focc:
+    def __init__(self, symrate=100000, aggressive=False):
+        self.h = lib().orc_focc_new(symrate, int(aggressive))
+
+    def work(self, n):
+        buf = np.zeros(max(n, 1), np.uint8)
+        r = lib().orc_focc_work(self.h, ptr(buf, u8p), n)
+        return r, buf[:max(r, 0)].copy()
+
+    def generate(self, total, chunk=4096):
+        out = bytearray()
+        while len(out) < total:
+            r, b = self.work(min(chunk, total - len(out)))
+            out += b.tobytes()
+        return np.frombuffer(bytes(out), np.uint8)
+
+    def push_words(self, stream, words):
+        w = as_u8(words).reshape(-1)
+        return lib().orc_focc_push_words(self.h, stream, ptr(w, u8p), len(w) // 28)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_focc_free(self.h)
+            self.h = None
+
+
+class Fvc:
+    def __init__(self, symrate=100000):
+        self.h = lib().orc_fvc_new(symrate)
+
+    def push_words(self, words, timer=None):
+        w = as_u8(words).reshape(-1)
+        return lib().orc_fvc_push_words(self.h, ptr(w, u8p), len(w) // 28, int(timer is not None), int(timer or 0))
+
+    def work(self, n, fill=0x55):
+        buf = np.full(max(n, 1), fill, np.uint8)
+        off = C.c_int(0)
+        r = lib().orc_fvc_work(self.h, ptr(buf, u8p), n, C.byref(off))
+        return r, buf[:max(r, 0)].copy(), bool(off.value)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_fvc_free(self.h)
+            self.h = None
+
+
+class Recc:
+    def __init__(self):
+        self.h = lib().orc_recc_new()
+        self.bursts = []
+        self._cb = BURST_CB(self._on)
+
+    def _on(self, p, user):
+        self.bursts.append(np.ctypeslib.as_array(p, shape=(3374,)).copy())
+
+    def work(self, syms):
+        s = as_u8(syms)
+        return lib().orc_recc_work(self.h, ptr(s, u8p), len(s), self._cb, None)
+
+    def buflen(self):
+        return lib().orc_recc_buflen(self.h)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_recc_free(self.h)
+            self.h = None
