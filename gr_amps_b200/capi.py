@@ -1,0 +1,257 @@
+"""ctypes binding of libamps_b200.so (the C ABI declared in include/amps_b200.h).
+
+This is plumbing for tests/ and bench.py: the product is the shared library.  There is no
+fallback of any kind -- if the library is missing or no sm_100 device is usable, loading or
+handle creation raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "libamps_b200.so")
+
+TRIGGER_SYMS = 74
+CAPTURE_SYMS = 3374
+
+u8p = C.POINTER(C.c_uint8)
+f32p = C.POINTER(C.c_float)
+
+
+class AmpsError(RuntimeError):
+    def __init__(self, status: int, detail: str):
+        super().__init__(f"libamps_b200 status {status}: {detail}")
+        self.status = status
+
+
+class ReccWords(C.Structure):
+    _fields_ = [
+        ("dcc", C.c_uint8 * 7), ("dcc_errs", C.c_uint8),
+        ("words", (C.c_uint8 * 240) * 7),
+        ("errs", C.c_uint16 * 7),
+        ("valid", C.c_uint8 * 7), ("valid_repeat", C.c_uint8 * 7),
+        ("F", C.c_uint8), ("NAWC", C.c_uint8), ("T", C.c_uint8), ("S", C.c_uint8), ("E", C.c_uint8),
+        ("ER", C.c_uint8), ("SCM", C.c_uint8), ("pad0", C.c_uint8),
+        ("MIN1", C.c_uint32),
+        ("B_F", C.c_uint8), ("B_NAWC", C.c_uint8), ("MSG_TYPE", C.c_uint8), ("ORDQ", C.c_uint8),
+        ("ORDER", C.c_uint8), ("LT", C.c_uint8), ("EP", C.c_uint8), ("SCM4", C.c_uint8), ("MPCI", C.c_uint8),
+        ("SDCC1", C.c_uint8), ("SDCC2", C.c_uint8), ("pad1", C.c_uint8),
+        ("MIN2", C.c_uint16), ("pad2", C.c_uint16),
+        ("word_c_serial", C.c_uint32),
+        ("kind", C.c_int32),
+        ("esn", C.c_uint32),
+        ("min", C.c_char * 12),
+        ("dialed", C.c_char * 36),
+    ]
+
+
+class Burst(C.Structure):
+    _fields_ = [
+        ("sample_index", C.c_uint64), ("demod_index", C.c_uint64),
+        ("corr", C.c_float), ("run_length", C.c_uint32),
+        ("symbols", C.c_uint8 * CAPTURE_SYMS), ("pad", C.c_uint8 * 2),
+        ("decoded", ReccWords),
+    ]
+
+    def symbols_np(self) -> np.ndarray:
+        return np.frombuffer(bytes(self.symbols), np.uint8).copy()
+
+
+class ReccIqParams(C.Structure):
+    _fields_ = [
+        ("samp_rate", C.c_double), ("center_freq", C.c_double), ("device", C.c_int),
+        ("max_samples", C.c_uint32), ("max_bursts", C.c_uint32), ("flags", C.c_uint32),
+        ("lpf_taps", f32p), ("n_lpf_taps", C.c_uint32),
+    ]
+
+
+class FwdParams(C.Structure):
+    _fields_ = [
+        ("samp_rate", C.c_double), ("symrate", C.c_double), ("max_deviation", C.c_double),
+        ("device", C.c_int), ("ncarriers", C.c_int),
+        ("carrier_freq", C.c_double * 3), ("lpf_transition", C.c_double * 3),
+        ("out_scale", C.c_float), ("max_samples", C.c_uint32),
+    ]
+
+
+BURST_CB = C.CFUNCTYPE(None, C.POINTER(Burst), C.c_void_p)
+BLOB_CB = C.CFUNCTYPE(None, u8p, C.c_void_p)
+
+RX_DUMP_BASEBAND = 1
+
+# every symbol include/amps_b200.h declares
+EXPORTS = [
+    "amps_b200_version", "amps_b200_strerror", "amps_b200_last_error", "amps_b200_device_count",
+    "amps_recc_iq_create", "amps_recc_iq_destroy", "amps_recc_iq_reset", "amps_recc_iq_work",
+    "amps_recc_iq_submit_dev", "amps_recc_iq_collect", "amps_recc_iq_granularity", "amps_recc_iq_read_demod",
+    "amps_recc_iq_read_baseband", "amps_recc_iq_stats", "amps_recc_iq_get_taps",
+    "amps_recc_decode_create", "amps_recc_decode_destroy", "amps_recc_decode_burst", "amps_recc_decode_bursts",
+    "amps_recc_create", "amps_recc_destroy", "amps_recc_work", "amps_recc_work_chunks",
+    "amps_focc_create", "amps_focc_destroy", "amps_focc_work", "amps_focc_generate", "amps_focc_generate_dev",
+    "amps_focc_push_words", "amps_focc_set_busy_idle",
+    "amps_fvc_create", "amps_fvc_destroy", "amps_fvc_push_words", "amps_fvc_work",
+    "amps_fwd_create", "amps_fwd_destroy", "amps_fwd_reset", "amps_fwd_work", "amps_fwd_submit_dev",
+    "amps_fwd_interp", "amps_fwd_get_taps",
+]
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  gr_amps_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    L.amps_b200_strerror.restype = C.c_char_p
+    L.amps_b200_last_error.restype = C.c_char_p
+    L.amps_recc_iq_create.argtypes = [C.POINTER(ReccIqParams), C.POINTER(C.c_void_p)]
+    L.amps_recc_iq_destroy.argtypes = [C.c_void_p]
+    L.amps_recc_iq_reset.argtypes = [C.c_void_p]
+    L.amps_recc_iq_work.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, BURST_CB, C.c_void_p]
+    L.amps_recc_iq_submit_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.amps_recc_iq_collect.argtypes = [C.c_void_p, C.POINTER(Burst), C.c_int, C.POINTER(C.c_int)]
+    L.amps_recc_iq_granularity.argtypes = [C.c_void_p]
+    L.amps_recc_iq_read_demod.argtypes = [C.c_void_p, C.c_uint64, f32p, C.c_size_t]
+    L.amps_recc_iq_read_baseband.argtypes = [C.c_void_p, C.c_uint64, f32p, C.c_size_t]
+    L.amps_recc_iq_stats.argtypes = [C.c_void_p] + [C.POINTER(C.c_uint64)] * 4
+    L.amps_recc_iq_get_taps.argtypes = [C.c_void_p, f32p, C.c_int]
+    L.amps_recc_decode_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    L.amps_recc_decode_destroy.argtypes = [C.c_void_p]
+    L.amps_recc_decode_burst.argtypes = [C.c_void_p, u8p, C.POINTER(ReccWords)]
+    L.amps_recc_decode_bursts.argtypes = [C.c_void_p, u8p, C.c_int, C.POINTER(ReccWords)]
+    if hasattr(L, "amps_recc_create"):
+        L.amps_recc_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.amps_recc_destroy.argtypes = [C.c_void_p]
+        L.amps_recc_work.argtypes = [C.c_void_p, u8p, C.c_int, BLOB_CB, C.c_void_p]
+        L.amps_recc_work_chunks.argtypes = [C.c_void_p, u8p, C.POINTER(C.c_int), C.c_int, BLOB_CB, C.c_void_p]
+    if hasattr(L, "amps_focc_create"):
+        L.amps_focc_create.argtypes = [C.c_ulong, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.amps_focc_destroy.argtypes = [C.c_void_p]
+        L.amps_focc_work.argtypes = [C.c_void_p, u8p, C.c_int, C.POINTER(C.c_int)]
+        L.amps_focc_generate.argtypes = [C.c_void_p, u8p, C.c_size_t]
+        L.amps_focc_generate_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.amps_focc_push_words.argtypes = [C.c_void_p, C.c_long, u8p, C.c_long]
+        L.amps_focc_set_busy_idle.argtypes = [C.c_void_p, C.c_int]
+    if hasattr(L, "amps_fvc_create"):
+        L.amps_fvc_create.argtypes = [C.c_ulong, C.c_int, C.POINTER(C.c_void_p)]
+        L.amps_fvc_destroy.argtypes = [C.c_void_p]
+        L.amps_fvc_push_words.argtypes = [C.c_void_p, u8p, C.c_long, C.c_int, C.c_uint64]
+        L.amps_fvc_work.argtypes = [C.c_void_p, u8p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    if hasattr(L, "amps_fwd_create"):
+        L.amps_fwd_create.argtypes = [C.POINTER(FwdParams), C.POINTER(C.c_void_p)]
+        L.amps_fwd_destroy.argtypes = [C.c_void_p]
+        L.amps_fwd_reset.argtypes = [C.c_void_p]
+        L.amps_fwd_work.argtypes = [C.c_void_p, C.POINTER(u8p), C.c_size_t, f32p]
+        L.amps_fwd_submit_dev.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_size_t, C.c_void_p, C.c_void_p]
+        L.amps_fwd_interp.argtypes = [C.c_void_p]
+        L.amps_fwd_get_taps.argtypes = [C.c_void_p, C.c_int, f32p, C.c_int]
+    _lib = L
+    return L
+
+
+def check(status: int) -> None:
+    if status != 0:
+        raise AmpsError(status, lib().amps_b200_last_error().decode(errors="replace") or lib().amps_b200_strerror(status).decode())
+
+
+class ReccIq:
+    """Fused RECC receive path on IQ (amps_recc_iq_*)."""
+
+    def __init__(self, max_samples: int, center_freq=-160e3, samp_rate=10e6, device=0, max_bursts=256,
+                 dump_baseband=False, lpf_taps: np.ndarray | None = None):
+        self._taps = None if lpf_taps is None else np.ascontiguousarray(lpf_taps, dtype=np.float32)
+        p = ReccIqParams(samp_rate, center_freq, device, max_samples, max_bursts,
+                         RX_DUMP_BASEBAND if dump_baseband else 0,
+                         None if self._taps is None else self._taps.ctypes.data_as(f32p),
+                         0 if self._taps is None else len(self._taps))
+        self.h = C.c_void_p()
+        check(lib().amps_recc_iq_create(C.byref(p), C.byref(self.h)))
+        self.granularity = lib().amps_recc_iq_granularity(self.h)
+        self.max_bursts = max_bursts
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().amps_recc_iq_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def reset(self):
+        check(lib().amps_recc_iq_reset(self.h))
+
+    def work(self, iq: np.ndarray) -> list[Burst]:
+        """Host-buffer call; iq complex64 (or its float32 view).  Returns the bursts published."""
+        iq = np.ascontiguousarray(iq)
+        n = iq.size if iq.dtype == np.complex64 else iq.size // 2
+        got: list[Burst] = []
+
+        def on(bp, _user):
+            b = Burst()
+            C.memmove(C.byref(b), bp, C.sizeof(Burst))
+            got.append(b)
+
+        cb = BURST_CB(on)
+        check(lib().amps_recc_iq_work(self.h, iq.ctypes.data_as(C.c_void_p), n, cb, None))
+        return got
+
+    def work_ptr(self, host_ptr: int, nsamples: int, cb=None):
+        check(lib().amps_recc_iq_work(self.h, C.c_void_p(host_ptr), nsamples, cb or C.cast(None, BURST_CB), None))
+
+    def submit_dev(self, dev_ptr: int, nsamples: int, stream: int = 0):
+        check(lib().amps_recc_iq_submit_dev(self.h, C.c_void_p(dev_ptr), nsamples, C.c_void_p(stream)))
+
+    def collect(self, max_bursts: int | None = None) -> list[Burst]:
+        m = max_bursts or self.max_bursts
+        arr = (Burst * m)()
+        n = C.c_int(0)
+        check(lib().amps_recc_iq_collect(self.h, arr, m, C.byref(n)))
+        return [arr[i] for i in range(n.value)]
+
+    def read_demod(self, first: int, n: int) -> np.ndarray:
+        out = np.zeros(n, np.float32)
+        check(lib().amps_recc_iq_read_demod(self.h, first, out.ctypes.data_as(f32p), n))
+        return out
+
+    def read_baseband(self, first: int, n: int) -> np.ndarray:
+        out = np.zeros(2 * n, np.float32)
+        check(lib().amps_recc_iq_read_baseband(self.h, first, out.ctypes.data_as(f32p), n))
+        return out.view(np.complex64)
+
+    def stats(self) -> dict:
+        v = [C.c_uint64(0) for _ in range(4)]
+        check(lib().amps_recc_iq_stats(self.h, *[C.byref(x) for x in v]))
+        return dict(samples_in=v[0].value, demod_out=v[1].value, bursts=v[2].value, kernel_launches=v[3].value)
+
+    def taps(self) -> np.ndarray:
+        n = lib().amps_recc_iq_get_taps(self.h, None, 0)
+        t = np.zeros(n, np.float32)
+        lib().amps_recc_iq_get_taps(self.h, t.ctypes.data_as(f32p), n)
+        return t
+
+
+class ReccDecode:
+    """Message-only burst decoder (amps_recc_decode_*)."""
+
+    def __init__(self, device=0):
+        self.h = C.c_void_p()
+        check(lib().amps_recc_decode_create(device, C.byref(self.h)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().amps_recc_decode_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def decode(self, blobs: np.ndarray) -> list[ReccWords]:
+        b = np.ascontiguousarray(blobs, dtype=np.uint8).reshape(-1, CAPTURE_SYMS)
+        out = (ReccWords * len(b))()
+        check(lib().amps_recc_decode_bursts(self.h, b.ctypes.data_as(u8p), len(b), out))
+        return list(out)

@@ -1,0 +1,354 @@
+// c_api_rx.cu -- extern "C" entry points of the receive side: amps_recc_iq_* (fused IQ path) and
+// amps_recc_decode_* (message-only burst decoder).  See include/amps_b200.h for the contract and
+// the reference interfaces each entry point replaces.
+#include "common.h"
+#include "design.h"
+#include "rx_kernels.cuh"
+
+#include <cstring>
+#include <new>
+#include <vector>
+
+using namespace amps;
+
+struct amps_recc_iq {
+    int          device = 0;
+    int          sm_count = 0;
+    cudaStream_t stream = nullptr;       // own stream for the host-buffer path
+    uint32_t     max_samples = 0;
+    uint32_t     max_records = 0;
+    uint32_t     flags = 0;
+    std::vector<float> lpf;
+    uint32_t     fcw = 0;
+
+    RxFrontParams fp{};                  // constant part filled at create
+    float2      *d_stage = nullptr;      // host path: [carry | new chunk]
+    float2      *d_tail[2] = {nullptr, nullptr};
+    int          tail_cur = 0;
+    float       *d_dring = nullptr;
+    uint32_t     dmask = 0;
+    float2      *d_ydump = nullptr;
+    size_t       ydump_cap = 0;          // complex samples
+    uint64_t     ydump_first = 0, ydump_count = 0;
+    RxState     *d_state = nullptr;
+    Candidate   *d_cand = nullptr;
+    amps_burst  *d_rec = nullptr;
+    amps_burst  *h_rec = nullptr;        // pinned
+    RxState     *h_state = nullptr;      // pinned
+    cudaStream_t last_stream = nullptr;
+
+    size_t       carry = 0;              // unprocessed samples sitting at the front of d_stage
+    uint64_t     samples_in = 0;         // samples handed to the kernels
+    uint64_t     total_d = 0;            // demod samples produced
+    uint64_t     scan_hi = 0;            // positions below this have been searched
+    uint64_t     bursts = 0, launches = 0;
+};
+
+static int rx_alloc(amps_recc_iq *h) {
+    const size_t max_d = (size_t)h->max_samples / (kD1 * kD2) + kTB;
+    size_t cap = 1;
+    while (cap < max_d + (size_t)kSpan + 4096) cap <<= 1;
+    h->dmask = (uint32_t)(cap - 1);
+    CK(cudaMalloc(&h->d_stage, ((size_t)h->max_samples + kPass) * sizeof(float2)));
+    for (int i = 0; i < 2; ++i) {
+        CK(cudaMalloc(&h->d_tail[i], (size_t)kHist * sizeof(float2)));
+        CK(cudaMemset(h->d_tail[i], 0, (size_t)kHist * sizeof(float2)));
+    }
+    CK(cudaMalloc(&h->d_dring, cap * sizeof(float)));
+    CK(cudaMemset(h->d_dring, 0, cap * sizeof(float)));
+    if (h->flags & AMPS_RX_DUMP_BASEBAND) {
+        h->ydump_cap = max_d;
+        CK(cudaMalloc(&h->d_ydump, h->ydump_cap * sizeof(float2)));
+    }
+    CK(cudaMalloc(&h->d_state, sizeof(RxState)));
+    CK(cudaMemset(h->d_state, 0, sizeof(RxState)));
+    CK(cudaMalloc(&h->d_cand, sizeof(Candidate) * kMaxCand));
+    CK(cudaMalloc(&h->d_rec, sizeof(amps_burst) * h->max_records));
+    CK(cudaMallocHost(&h->h_rec, sizeof(amps_burst) * h->max_records));
+    CK(cudaMallocHost(&h->h_state, sizeof(RxState)));
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    return AMPS_OK;
+}
+
+extern "C" int amps_recc_iq_create(const amps_recc_iq_params *params, amps_recc_iq **out) {
+    if (!params || !out) return set_error(AMPS_E_INVAL, "null argument");
+    *out = nullptr;
+    if (params->samp_rate != 10e6)
+        return set_error(AMPS_E_INVAL, "samp_rate must be 10e6 (25 x the reference's 400 kS/s)");
+    if (params->max_samples == 0) return set_error(AMPS_E_INVAL, "max_samples must be > 0");
+    if (params->lpf_taps && (params->n_lpf_taps == 0 || params->n_lpf_taps > (uint32_t)kMaxLpf))
+        return set_error(AMPS_E_INVAL, "n_lpf_taps must be in 1..299");
+    int st = select_device(params->device);
+    if (st != AMPS_OK) return st;
+    amps_recc_iq *h = new (std::nothrow) amps_recc_iq();
+    if (!h) return set_error(AMPS_E_NOMEM, "out of host memory");
+    h->device = params->device;
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, params->device);
+    h->sm_count = prop.multiProcessorCount;
+    // round the per-call capacity up to whole passes
+    h->max_samples = (uint32_t)(((uint64_t)params->max_samples + kPass - 1) / kPass * kPass);
+    h->max_records = params->max_bursts ? params->max_bursts : 256;
+    h->flags = params->flags;
+    if (params->lpf_taps) h->lpf.assign(params->lpf_taps, params->lpf_taps + params->n_lpf_taps);
+    else h->lpf = firdes_low_pass(3.0, 400e3, 10e3, 4500.0, WIN_BLACKMAN);     // grc/ampsbs.grc:138-184
+    h->fcw = nco_fcw(params->center_freq, params->samp_rate);
+
+    std::memset(&h->fp, 0, sizeof h->fp);
+    h->fp.fcw25 = (uint32_t)(25u * h->fcw);
+    nco_block_table(h->fcw, kD1, reinterpret_cast<float *>(h->fp.w));
+    std::vector<float> cic;
+    cic3_taps(kD1, cic);
+    for (size_t i = 0; i < cic.size(); ++i) h->fp.g[i] = cic[i];
+    for (size_t i = 0; i < h->lpf.size(); ++i) h->fp.h2[i] = h->lpf[i];
+
+    cudaError_t ce = rx_configure_device();
+    if (ce != cudaSuccess) { delete h; return set_cuda_error(ce, "rx_configure_device"); }
+    st = rx_alloc(h);
+    if (st != AMPS_OK) { amps_recc_iq_destroy(h); return st; }
+    *out = h;
+    return AMPS_OK;
+}
+
+extern "C" int amps_recc_iq_destroy(amps_recc_iq *h) {
+    if (!h) return AMPS_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+    cudaFree(h->d_stage); cudaFree(h->d_tail[0]); cudaFree(h->d_tail[1]); cudaFree(h->d_dring);
+    cudaFree(h->d_ydump); cudaFree(h->d_state); cudaFree(h->d_cand); cudaFree(h->d_rec);
+    if (h->h_rec) cudaFreeHost(h->h_rec);
+    if (h->h_state) cudaFreeHost(h->h_state);
+    delete h;
+    return AMPS_OK;
+}
+
+extern "C" int amps_recc_iq_reset(amps_recc_iq *h) {
+    if (!h) return set_error(AMPS_E_INVAL, "null handle");
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    for (int i = 0; i < 2; ++i) CK(cudaMemset(h->d_tail[i], 0, (size_t)kHist * sizeof(float2)));
+    CK(cudaMemset(h->d_state, 0, sizeof(RxState)));
+    CK(cudaMemset(h->d_dring, 0, ((size_t)h->dmask + 1) * sizeof(float)));
+    h->tail_cur = 0; h->carry = 0; h->samples_in = 0; h->total_d = 0; h->scan_hi = 0;
+    h->ydump_first = 0; h->ydump_count = 0;
+    return AMPS_OK;
+}
+
+extern "C" int amps_recc_iq_granularity(const amps_recc_iq *h) { (void)h; return kPass; }
+
+// Enqueue everything for `npass` passes whose samples start at d_chunk.
+static int rx_enqueue(amps_recc_iq *h, const float2 *d_chunk, uint32_t npass, cudaStream_t st) {
+    RxFrontParams p = h->fp;
+    p.chunk = d_chunk;
+    p.tail = h->d_tail[h->tail_cur];
+    p.dring = h->d_dring;
+    p.dmask = h->dmask;
+    p.q_base = h->total_d;
+    p.npass = npass;
+    p.blk_base = (uint32_t)(h->samples_in / kD1);
+    p.ydump = h->d_ydump;
+    int grid = 2 * h->sm_count;
+    if ((uint32_t)grid > npass) grid = (int)npass;
+    CKL(launch_rx_front(p, grid, st));
+    h->launches++;
+    // history for the next call = the last pass of this one
+    CK(cudaMemcpyAsync(h->d_tail[h->tail_cur ^ 1], d_chunk + (size_t)(npass - 1) * kPass, (size_t)kHist * sizeof(float2),
+                       cudaMemcpyDeviceToDevice, st));
+    h->tail_cur ^= 1;
+    h->ydump_first = h->total_d;
+    h->ydump_count = (uint64_t)npass * kTB;
+    h->samples_in += (uint64_t)npass * kPass;
+    h->total_d += (uint64_t)npass * kTB;
+    // search every position whose capture is complete
+    if (h->total_d > (uint64_t)kSpan) {
+        const uint64_t hi = h->total_d - (uint64_t)kSpan;
+        const uint64_t lo = h->scan_hi > 64 ? h->scan_hi - 64 : 0;
+        if (hi > h->scan_hi) {
+            CKL(launch_rx_detect(h->d_dring, h->dmask, h->d_state, h->d_cand, lo, hi, st));
+            CKL(launch_rx_select(h->d_dring, h->dmask, h->d_state, h->d_cand, hi, h->d_rec, h->max_records, st));
+            h->launches += 2;
+            h->scan_hi = hi;
+        }
+    }
+    h->last_stream = st;
+    return AMPS_OK;
+}
+
+extern "C" int amps_recc_iq_submit_dev(amps_recc_iq *h, const void *d_iq, size_t nsamples, void *cuda_stream) {
+    if (!h || (!d_iq && nsamples)) return set_error(AMPS_E_INVAL, "null argument");
+    if (nsamples == 0) return AMPS_OK;
+    if (nsamples % kPass) return set_error(AMPS_E_ALIGN, "nsamples must be a multiple of amps_recc_iq_granularity()");
+    if (reinterpret_cast<uintptr_t>(d_iq) & 15u) return set_error(AMPS_E_ALIGN, "d_iq must be 16-byte aligned");
+    if (nsamples > h->max_samples) return set_error(AMPS_E_OVERFLOW, "nsamples exceeds max_samples");
+    if (h->carry) return set_error(AMPS_E_STATE, "host-path samples are pending; reset() or keep using work()");
+    CK(cudaSetDevice(h->device));
+    return rx_enqueue(h, static_cast<const float2 *>(d_iq), (uint32_t)(nsamples / kPass), static_cast<cudaStream_t>(cuda_stream));
+}
+
+// Wait for the stream, bring the records found since the last fetch into h->h_rec.
+static int rx_fetch(amps_recc_iq *h, unsigned int *n_out) {
+    *n_out = 0;
+    cudaStream_t st = h->last_stream;
+    CK(cudaMemcpyAsync(h->h_state, h->d_state, sizeof(RxState), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (h->h_state->cand_overflow)
+        return set_error(AMPS_E_OVERFLOW, "trigger candidate list overflowed (more than 8192 matches in one call)");
+    unsigned int n = h->h_state->nrec;
+    if (n > h->max_records) n = h->max_records;
+    if (n) {
+        CK(cudaMemcpyAsync(h->h_rec, h->d_rec, sizeof(amps_burst) * n, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemsetAsync(&h->d_state->nrec, 0, sizeof(unsigned int), st));
+        CK(cudaStreamSynchronize(st));
+    }
+    h->bursts += n;
+    *n_out = n;
+    return AMPS_OK;
+}
+
+extern "C" int amps_recc_iq_collect(amps_recc_iq *h, amps_burst *out, int max, int *n_out) {
+    if (!h || !n_out || (max > 0 && !out)) return set_error(AMPS_E_INVAL, "null argument");
+    *n_out = 0;
+    CK(cudaSetDevice(h->device));
+    unsigned int n = 0;
+    int rc = rx_fetch(h, &n);
+    if (rc != AMPS_OK) return rc;
+    const int give = (int)n < max ? (int)n : max;      // records beyond max are dropped
+    for (int i = 0; i < give; ++i) out[i] = h->h_rec[i];
+    *n_out = give;
+    return AMPS_OK;
+}
+
+extern "C" int amps_recc_iq_work(amps_recc_iq *h, const float *iq_host, size_t nsamples, amps_burst_cb cb, void *user) {
+    if (!h || (!iq_host && nsamples)) return set_error(AMPS_E_INVAL, "null argument");
+    if (nsamples > h->max_samples) return set_error(AMPS_E_OVERFLOW, "nsamples exceeds max_samples");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    if (nsamples)
+        CK(cudaMemcpyAsync(h->d_stage + h->carry, iq_host, nsamples * sizeof(float2), cudaMemcpyHostToDevice, st));
+    const size_t avail = h->carry + nsamples;
+    const uint32_t npass = (uint32_t)(avail / kPass);
+    h->last_stream = st;
+    if (npass) {
+        int rc = rx_enqueue(h, h->d_stage, npass, st);
+        if (rc != AMPS_OK) return rc;
+        const size_t left = avail - (size_t)npass * kPass;
+        if (left)
+            CK(cudaMemcpyAsync(h->d_stage, h->d_stage + (size_t)npass * kPass, left * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+        h->carry = left;
+    } else {
+        h->carry = avail;
+    }
+    // deliver bursts in stream order, like message_port_pub("bursts", ...) from work() (lib/recc_impl.cc:126)
+    unsigned int n = 0;
+    int rc = rx_fetch(h, &n);
+    if (rc != AMPS_OK) return rc;
+    if (cb) for (unsigned int i = 0; i < n; ++i) cb(&h->h_rec[i], user);
+    return AMPS_OK;
+}
+
+extern "C" int amps_recc_iq_read_demod(amps_recc_iq *h, uint64_t first, float *out, size_t n) {
+    if (!h || !out) return set_error(AMPS_E_INVAL, "null argument");
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    if (first + n > h->total_d) return set_error(AMPS_E_INVAL, "range beyond the demodulated stream");
+    if (h->total_d - first > (uint64_t)h->dmask + 1) return set_error(AMPS_E_INVAL, "range no longer in the demod ring");
+    size_t done = 0;
+    while (done < n) {
+        const size_t idx = (size_t)((first + done) & h->dmask);
+        size_t run = (size_t)h->dmask + 1 - idx;
+        if (run > n - done) run = n - done;
+        CK(cudaMemcpy(out + done, h->d_dring + idx, run * sizeof(float), cudaMemcpyDeviceToHost));
+        done += run;
+    }
+    return AMPS_OK;
+}
+
+extern "C" int amps_recc_iq_read_baseband(amps_recc_iq *h, uint64_t first, float *out_iq, size_t n) {
+    if (!h || !out_iq) return set_error(AMPS_E_INVAL, "null argument");
+    if (!h->d_ydump) return set_error(AMPS_E_STATE, "handle was not created with AMPS_RX_DUMP_BASEBAND");
+    if (first < h->ydump_first || first + n > h->ydump_first + h->ydump_count)
+        return set_error(AMPS_E_INVAL, "only the last call's baseband is kept");
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out_iq, h->d_ydump + (first - h->ydump_first), n * sizeof(float2), cudaMemcpyDeviceToHost));
+    return AMPS_OK;
+}
+
+extern "C" int amps_recc_iq_stats(const amps_recc_iq *h, uint64_t *samples_in, uint64_t *demod_out, uint64_t *bursts,
+                                  uint64_t *kernel_launches) {
+    if (!h) return set_error(AMPS_E_INVAL, "null handle");
+    if (samples_in) *samples_in = h->samples_in;
+    if (demod_out) *demod_out = h->total_d;
+    if (bursts) *bursts = h->bursts;
+    if (kernel_launches) *kernel_launches = h->launches;
+    return AMPS_OK;
+}
+
+extern "C" int amps_recc_iq_get_taps(const amps_recc_iq *h, float *lpf_out, int cap) {
+    if (!h) return set_error(AMPS_E_INVAL, "null handle");
+    const int n = (int)h->lpf.size();
+    if (lpf_out) for (int i = 0; i < n && i < cap; ++i) lpf_out[i] = h->lpf[i];
+    return n;
+}
+
+// --------------------------------------------------------------------------------------------
+// recc_decode (message-only block)
+// --------------------------------------------------------------------------------------------
+struct amps_recc_decode {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    uint8_t *d_blobs = nullptr;
+    amps_recc_words *d_out = nullptr;
+    int cap = 0;
+};
+
+static int decode_reserve(amps_recc_decode *h, int n) {
+    if (n <= h->cap) return AMPS_OK;
+    cudaFree(h->d_blobs); cudaFree(h->d_out);
+    h->d_blobs = nullptr; h->d_out = nullptr; h->cap = 0;
+    CK(cudaMalloc(&h->d_blobs, (size_t)n * kCapture));
+    CK(cudaMalloc(&h->d_out, (size_t)n * sizeof(amps_recc_words)));
+    h->cap = n;
+    return AMPS_OK;
+}
+
+extern "C" int amps_recc_decode_create(int device, amps_recc_decode **out) {
+    if (!out) return set_error(AMPS_E_INVAL, "null argument");
+    *out = nullptr;
+    int st = select_device(device);
+    if (st != AMPS_OK) return st;
+    amps_recc_decode *h = new (std::nothrow) amps_recc_decode();
+    if (!h) return set_error(AMPS_E_NOMEM, "out of host memory");
+    h->device = device;
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    st = decode_reserve(h, 16);
+    if (st != AMPS_OK) { amps_recc_decode_destroy(h); return st; }
+    *out = h;
+    return AMPS_OK;
+}
+
+extern "C" int amps_recc_decode_destroy(amps_recc_decode *h) {
+    if (!h) return AMPS_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    cudaFree(h->d_blobs); cudaFree(h->d_out);
+    delete h;
+    return AMPS_OK;
+}
+
+extern "C" int amps_recc_decode_bursts(amps_recc_decode *h, const uint8_t *blobs, int nbursts, amps_recc_words *out) {
+    if (!h || !blobs || !out || nbursts < 0) return set_error(AMPS_E_INVAL, "bad argument");
+    if (nbursts == 0) return AMPS_OK;
+    CK(cudaSetDevice(h->device));
+    int st = decode_reserve(h, nbursts);
+    if (st != AMPS_OK) return st;
+    CK(cudaMemcpyAsync(h->d_blobs, blobs, (size_t)nbursts * kCapture, cudaMemcpyHostToDevice, h->stream));
+    CKL(launch_decode_blobs(h->d_blobs, nbursts, h->d_out, h->stream));
+    CK(cudaMemcpyAsync(out, h->d_out, (size_t)nbursts * sizeof(amps_recc_words), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return AMPS_OK;
+}
+
+extern "C" int amps_recc_decode_burst(amps_recc_decode *h, const uint8_t *blob3374, amps_recc_words *out) {
+    return amps_recc_decode_bursts(h, blob3374, 1, out);
+}

@@ -1,0 +1,56 @@
+#include "design.h"
+#include <cmath>
+
+namespace amps {
+
+static const double kPi = 3.14159265358979323846;
+
+std::vector<float> firdes_low_pass(double gain, double fs, double fc, double tw, Window win) {
+    static const double atten[3] = {53.0, 44.0, 74.0};
+    int ntaps = (int)(atten[win] * fs / (22.0 * tw));
+    if ((ntaps & 1) == 0) ntaps++;
+    const int M = (ntaps - 1) / 2;
+    const double fwT0 = 2.0 * kPi * fc / fs;
+    std::vector<float> taps((size_t)ntaps);
+    for (int n = -M; n <= M; n++) {
+        const int k = n + M;
+        double wv;
+        if (win == WIN_HAMMING) wv = 0.54 - 0.46 * std::cos(2.0 * kPi * k / (ntaps - 1));
+        else if (win == WIN_HANN) wv = 0.5 - 0.5 * std::cos(2.0 * kPi * k / (ntaps - 1));
+        else wv = 0.42 - 0.5 * std::cos(2.0 * kPi * k / (ntaps - 1)) + 0.08 * std::cos(4.0 * kPi * k / (ntaps - 1));
+        const float wf = (float)wv;                      // the window is a float vector in GNU Radio
+        if (n == 0) taps[k] = (float)(fwT0 / kPi * wf);
+        else taps[k] = (float)(std::sin(n * fwT0) / (n * kPi) * wf);
+    }
+    double fmax = taps[M];
+    for (int n = 1; n <= M; n++) fmax += 2.0 * taps[n + M];
+    const double g = gain / fmax;
+    for (int i = 0; i < ntaps; i++) taps[i] = (float)(taps[i] * g);
+    return taps;
+}
+
+uint32_t nco_fcw(double center_freq, double samp_rate) {
+    double turns = -center_freq / samp_rate;
+    turns -= std::floor(turns);
+    return (uint32_t)(uint64_t)std::llround(turns * 4294967296.0);
+}
+
+void nco_block_table(uint32_t fcw, int n, float *out) {
+    for (int k = 0; k < n; k++) {
+        const uint32_t psi = (uint32_t)((uint32_t)k * fcw);
+        const double ang = 2.0 * kPi * ((double)psi / 4294967296.0);
+        out[2 * k] = (float)std::cos(ang);
+        out[2 * k + 1] = (float)std::sin(ang);
+    }
+}
+
+void cic3_taps(int decim, std::vector<float> &taps) {
+    std::vector<double> a((size_t)(2 * decim - 1), 0.0), c((size_t)(3 * decim - 2), 0.0);
+    for (int i = 0; i < decim; i++) for (int j = 0; j < decim; j++) a[(size_t)(i + j)] += 1.0;
+    for (int i = 0; i < 2 * decim - 1; i++) for (int j = 0; j < decim; j++) c[(size_t)(i + j)] += a[(size_t)i];
+    const double norm = (double)decim * decim * decim;
+    taps.resize(c.size());
+    for (size_t i = 0; i < c.size(); i++) taps[i] = (float)(c[i] / norm);
+}
+
+}  // namespace amps

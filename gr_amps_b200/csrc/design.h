@@ -1,0 +1,15 @@
+// design.h -- host-side filter / NCO design for libamps_b200 (plain C++, no CUDA).
+// Restates the documented behaviour of gr::filter::firdes::low_pass (GNU Radio 3.7, not in the
+// reference tree; parameters from grc/ampsbs.grc:138-184, 2172, 2227) and defines the 10 MS/s
+// front end.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+namespace amps {
+enum Window { WIN_HAMMING = 0, WIN_HANN = 1, WIN_BLACKMAN = 2 };
+std::vector<float> firdes_low_pass(double gain, double fs, double fc, double tw, Window win);
+uint32_t nco_fcw(double center_freq, double samp_rate);          // phase step for a shift by -center_freq
+void nco_block_table(uint32_t fcw, int n, float *re_im_pairs);   // e^{j 2 pi (k*fcw mod 2^32) / 2^32}, k < n
+void cic3_taps(int decim, std::vector<float> &taps);              // boxcar^3 / decim^3
+}  // namespace amps

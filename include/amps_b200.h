@@ -1,0 +1,228 @@
+/*
+ * amps_b200.h -- C ABI of libamps_b200.so: the B200-native drop-in for gr-amps's per-sample DSP
+ * hot path.  Plain pointers and sizes only; no C++/torch/GNU Radio types cross this boundary.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the gr-amps
+ * tree).  A handle mirrors one GNU Radio block instance: like a block's work()/message handlers
+ * (one scheduler thread per block), a handle must be used by one thread at a time.
+ *
+ * Every function returns an int status: AMPS_OK (0) or a negative AMPS_E_* code; nothing throws.
+ * There is NO CPU fallback: without a usable sm_100 device every create() fails with
+ * AMPS_E_NODEVICE and the library says so loudly on stderr.
+ */
+#ifndef AMPS_B200_H
+#define AMPS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define AMPS_B200_API __attribute__((visibility("default")))
+#else
+#define AMPS_B200_API
+#endif
+
+#define AMPS_OK            0
+#define AMPS_E_INVAL      (-1)   /* bad argument */
+#define AMPS_E_NODEVICE   (-2)   /* no CUDA device / not sm_100 */
+#define AMPS_E_CUDA       (-3)   /* CUDA runtime error (see amps_b200_last_error) */
+#define AMPS_E_NOMEM      (-4)
+#define AMPS_E_ALIGN      (-5)   /* device pointer / length alignment not met */
+#define AMPS_E_OVERFLOW   (-6)   /* more samples than the handle was created for */
+#define AMPS_E_STATE      (-7)
+
+#define AMPS_RECC_TRIGGER_SYMS 74      /* lib/recc_impl.cc:76-77 */
+#define AMPS_RECC_CAPTURE_SYMS 3374    /* lib/recc_impl.cc:70 */
+#define AMPS_WORD_BITS 28              /* FOCC/FVC info word, one byte per bit (lib/amps_packet.cc) */
+
+AMPS_B200_API int         amps_b200_version(void);
+AMPS_B200_API const char *amps_b200_strerror(int status);
+AMPS_B200_API const char *amps_b200_last_error(void);          /* thread-local detail string */
+AMPS_B200_API int         amps_b200_device_count(void);        /* number of sm_100 devices, <0 on error */
+
+/* ------------------------------------------------------------------------------------------
+ * RECC word decode result -- replaces the locals of recc_decode_impl::bursts_message
+ * (lib/recc_decode_impl.cc:81-169) and the parsers of lib/amps_packet.h:103-274.
+ * Fields are parsed from the RAW first repeat of each word, exactly as the reference does.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct amps_recc_words {
+    uint8_t  dcc[7];
+    uint8_t  dcc_errs;
+    uint8_t  words[7][240];      /* Manchester-decoded bits, 5 repeats x 48 */
+    uint16_t errs[7];            /* invalid Manchester pairs per word (lib/utils.cc:36-44) */
+    uint8_t  valid[7];           /* BCH(63,51) validity of the first repeat that decodes */
+    uint8_t  valid_repeat[7];    /* which repeat validated, 5 if none */
+    uint8_t  F, NAWC, T, S, E, ER, SCM;
+    uint8_t  pad0;
+    uint32_t MIN1;
+    uint8_t  B_F, B_NAWC, MSG_TYPE, ORDQ, ORDER, LT, EP, SCM4, MPCI, SDCC1, SDCC2;
+    uint8_t  pad1;
+    uint16_t MIN2;
+    uint16_t pad2;
+    uint32_t word_c_serial;
+    int32_t  kind;               /* AMPS_MSG_* */
+    uint32_t esn;
+    char     min[12];            /* 10 digits + NUL */
+    char     dialed[36];         /* up to 32 digits + NUL */
+} amps_recc_words;
+
+#define AMPS_MSG_INVALID_A     0   /* Word A failed BCH: dropped (recc_decode_impl.cc:108-111) */
+#define AMPS_MSG_E0_DROPPED    1   /* E == 0 (:113-116) */
+#define AMPS_MSG_PAGE_RESPONSE 2   /* :121 */
+#define AMPS_MSG_REGISTRATION  3   /* :123-138 */
+#define AMPS_MSG_ORIGINATION   4   /* :139-165 */
+#define AMPS_MSG_UNKNOWN       5   /* :166-168 */
+#define AMPS_MSG_BAD_NAWC      6   /* :154-157 */
+
+/* One captured burst: what recc_impl::work publishes on message port "bursts"
+ * (lib/recc_impl.cc:126: a 3374-byte blob of 0/1 half-symbols) plus where it was found and its
+ * decode (what recc_decode_impl would compute from that blob). */
+typedef struct amps_burst {
+    uint64_t sample_index;       /* absolute input-sample index of the sampling instant of the first trigger half-symbol */
+    uint64_t demod_index;        /* same, in demodulated samples (200 kS/s) */
+    float    corr;               /* soft correlation of the 74-symbol trigger at the chosen phase */
+    uint32_t run_length;         /* number of adjacent sampling phases that matched 74/74 */
+    uint8_t  symbols[AMPS_RECC_CAPTURE_SYMS];
+    uint8_t  pad[2];
+    amps_recc_words decoded;
+} amps_burst;
+
+/* ------------------------------------------------------------------------------------------
+ * Fused RECC receive path on IQ.  One handle replaces, for one carrier, the chain
+ *   freq_xlating_fir_filter_ccc -> quadrature_demod_cf -> clock_recovery_mm_ff ->
+ *   binary_slicer_fb (grc/ampsbs.grc:1814-1872, 774-816, 1751-1813, 1712-1750)
+ *   -> amps.recc (lib/recc_impl.cc:93-145) -> burst decode (lib/recc_decode_impl.cc:81-169)
+ * at samp_rate = 10 MS/s (25 x the reference's 400 kS/s).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct amps_recc_iq amps_recc_iq;
+
+typedef struct amps_recc_iq_params {
+    double   samp_rate;          /* must be 10e6 */
+    double   center_freq;        /* carrier offset inside the band, Hz (reference: rx_offset = -160e3, grc/ampsbs.grc:212-238) */
+    int      device;             /* CUDA ordinal */
+    uint32_t max_samples;        /* largest nsamples ever passed in one call (sizes device buffers) */
+    uint32_t max_bursts;         /* burst records kept per call before the oldest are dropped (0 -> 256) */
+    uint32_t flags;              /* AMPS_RX_* */
+    const float *lpf_taps;       /* channel filter taps @400 kS/s, NULL -> firdes.low_pass(3,400e3,10e3,4.5e3,BLACKMAN) */
+    uint32_t n_lpf_taps;         /* <= 299 */
+} amps_recc_iq_params;
+
+#define AMPS_RX_DUMP_BASEBAND 1u   /* keep the 200 kS/s complex baseband of the last call for inspection */
+
+typedef void (*amps_burst_cb)(const amps_burst *burst, void *user);
+
+AMPS_B200_API int amps_recc_iq_create(const amps_recc_iq_params *params, amps_recc_iq **out);
+AMPS_B200_API int amps_recc_iq_destroy(amps_recc_iq *h);
+AMPS_B200_API int amps_recc_iq_reset(amps_recc_iq *h);          /* back to stream start (zero history) */
+
+/* Host-buffer streaming call -- what a gr::sync_block::work() does with the scheduler's input
+ * buffer (interleaved float re,im; nsamples complex samples).  Copies H2D, runs the fused kernels,
+ * copies burst records D2H and invokes cb once per burst, in stream order (the equivalent of
+ * message_port_pub("bursts", ...), lib/recc_impl.cc:126).  Any nsamples >= 0 is accepted; samples
+ * that do not fill a processing pass are carried to the next call. */
+AMPS_B200_API int amps_recc_iq_work(amps_recc_iq *h, const float *iq_host, size_t nsamples,
+                                    amps_burst_cb cb, void *user);
+
+/* Device-resident variant: d_iq is a device pointer (16-byte aligned) on the handle's device,
+ * nsamples a multiple of amps_recc_iq_granularity(); kernels are enqueued on cuda_stream
+ * (a cudaStream_t, NULL = default stream) and the call returns without synchronising. */
+AMPS_B200_API int amps_recc_iq_submit_dev(amps_recc_iq *h, const void *d_iq, size_t nsamples, void *cuda_stream);
+/* Waits for the stream, copies out the bursts found since the last collect (at most max). */
+AMPS_B200_API int amps_recc_iq_collect(amps_recc_iq *h, amps_burst *out, int max, int *n_out);
+AMPS_B200_API int amps_recc_iq_granularity(const amps_recc_iq *h);
+/* Inspection (tests / roofline accounting) */
+AMPS_B200_API int amps_recc_iq_read_demod(amps_recc_iq *h, uint64_t first, float *out, size_t n);          /* 200 kS/s FM demod */
+AMPS_B200_API int amps_recc_iq_read_baseband(amps_recc_iq *h, uint64_t first, float *out_iq, size_t n);    /* needs AMPS_RX_DUMP_BASEBAND */
+AMPS_B200_API int amps_recc_iq_stats(const amps_recc_iq *h, uint64_t *samples_in, uint64_t *demod_out,
+                                     uint64_t *bursts, uint64_t *kernel_launches);
+AMPS_B200_API int amps_recc_iq_get_taps(const amps_recc_iq *h, float *lpf_out, int cap);                   /* returns ntaps */
+
+/* ------------------------------------------------------------------------------------------
+ * recc_decode: message-only block (lib/recc_decode_impl.cc:81-169).  blob = 3374 hard half-symbols.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct amps_recc_decode amps_recc_decode;
+AMPS_B200_API int amps_recc_decode_create(int device, amps_recc_decode **out);
+AMPS_B200_API int amps_recc_decode_destroy(amps_recc_decode *h);
+AMPS_B200_API int amps_recc_decode_burst(amps_recc_decode *h, const uint8_t *blob3374, amps_recc_words *out);
+/* batch form: nbursts blobs back to back */
+AMPS_B200_API int amps_recc_decode_bursts(amps_recc_decode *h, const uint8_t *blobs, int nbursts, amps_recc_words *out);
+
+/* ------------------------------------------------------------------------------------------
+ * recc: byte-stream sink, compat mode (lib/recc_impl.cc:93-145 incl. its buffer quirks).
+ * in = n hard half-symbols (0/1).  cb is invoked with each 3374-byte blob.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct amps_recc amps_recc;
+typedef void (*amps_blob_cb)(const uint8_t *blob3374, void *user);
+AMPS_B200_API int amps_recc_create(int device, amps_recc **out);
+AMPS_B200_API int amps_recc_destroy(amps_recc *h);
+/* one work() call; returns AMPS_OK (the reference returns 0 items and consumes n) */
+AMPS_B200_API int amps_recc_work(amps_recc *h, const uint8_t *in, int n, amps_blob_cb cb, void *user);
+/* a whole schedule of work() calls in one launch: chunk_sizes[nchunks], in = concatenated chunks */
+AMPS_B200_API int amps_recc_work_chunks(amps_recc *h, const uint8_t *in, const int *chunk_sizes, int nchunks,
+                                        amps_blob_cb cb, void *user);
+
+/* ------------------------------------------------------------------------------------------
+ * focc: FOCC Manchester half-symbol source (lib/focc_impl.cc:104-136, 486-647).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct amps_focc amps_focc;
+AMPS_B200_API int amps_focc_create(unsigned long symrate, int aggressive_registration, int device, amps_focc **out);
+AMPS_B200_API int amps_focc_destroy(amps_focc *h);
+/* work(): writes up to noutput_items bytes (+1 = 0x01, -1 = 0xFF) to out (host memory) and returns
+ * the number produced in *produced: at most one 23/22-bit burst per call, possibly 0; -1 (WORK_DONE)
+ * when noutput_items < 1 (lib/focc_impl.cc:590-593,630-632). */
+AMPS_B200_API int amps_focc_work(amps_focc *h, uint8_t *out, int noutput_items, int *produced);
+/* bulk form: the concatenation of successive work() outputs until exactly n bytes were produced */
+AMPS_B200_API int amps_focc_generate(amps_focc *h, uint8_t *out, size_t n);
+AMPS_B200_API int amps_focc_generate_dev(amps_focc *h, void *d_out, size_t n, void *cuda_stream);
+/* focc_words message (lib/focc_impl.cc:521-563): stream 1=A 2=B 3=BOTH, words28 = nwords x 28 bytes */
+AMPS_B200_API int amps_focc_push_words(amps_focc *h, long stream, const uint8_t *words28, long nwords);
+AMPS_B200_API int amps_focc_set_busy_idle(amps_focc *h, int idle);      /* lib/amps_common.h:7 */
+
+/* ------------------------------------------------------------------------------------------
+ * fvc: FVC blank-and-burst source (lib/fvc_impl.cc:56-193).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct amps_fvc amps_fvc;
+AMPS_B200_API int amps_fvc_create(unsigned long symrate, int device, amps_fvc **out);
+AMPS_B200_API int amps_fvc_destroy(amps_fvc *h);
+/* fvc_words message (lib/fvc_impl.cc:109-143); has_timer/timer = the optional trailing uint64 */
+AMPS_B200_API int amps_fvc_push_words(amps_fvc *h, const uint8_t *words28, long nwords, int has_timer, uint64_t timer);
+/* work(): *produced = items produced; while no word was ever pushed the reference returns
+ * noutput_items WITHOUT writing (lib/fvc_impl.cc:159-161); this library writes zeros there
+ * (documented deviation).  *fvc_off is set when the "fvc off" PDU is due (:163-171). */
+AMPS_B200_API int amps_fvc_work(amps_fvc *h, uint8_t *out, int noutput_items, int *produced, int *fvc_off);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused forward path: symbols -> char_to_float -> frequency_modulator_fc -> pfb interpolator ->
+ * mix -> sum -> x0.5 (grc/ampsbs.grc:1159-1252, 574-659, 2120-2229, 817-942, 1006-1056, 1355-1405)
+ * at 10 MS/s output.  Up to 3 carriers (FOCC @0 Hz + two FVC legs).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct amps_fwd amps_fwd;
+typedef struct amps_fwd_params {
+    double   samp_rate;          /* output rate, 10e6 */
+    double   symrate;            /* symbol-stream rate feeding the FM modulator, 100e3 (grc/ampsbs.grc:135,317) */
+    double   max_deviation;      /* 8000 (grc/ampsbs.grc:209) */
+    int      device;
+    int      ncarriers;          /* 1..3 */
+    double   carrier_freq[3];    /* 0, 60e3, 90e3 (grc/ampsbs.grc:841,904) */
+    double   lpf_transition[3];  /* firdes.low_pass(1, samp_rate, 10e3, tw): 5e3 FOCC, 3e3 FVC (:2227,:2172) */
+    float    out_scale;          /* 0.5 (:1367) */
+    uint32_t max_samples;
+} amps_fwd_params;
+AMPS_B200_API int amps_fwd_create(const amps_fwd_params *p, amps_fwd **out);
+AMPS_B200_API int amps_fwd_destroy(amps_fwd *h);
+AMPS_B200_API int amps_fwd_reset(amps_fwd *h);
+/* sym[c] = host arrays of nsym +1/-1 (0x01/0xFF, 0 = muted) bytes per carrier; out_iq_host gets
+ * nsym * (samp_rate/symrate) complex samples. */
+AMPS_B200_API int amps_fwd_work(amps_fwd *h, const uint8_t *const *sym, size_t nsym, float *out_iq_host);
+AMPS_B200_API int amps_fwd_submit_dev(amps_fwd *h, const void *const *d_sym, size_t nsym, void *d_out_iq, void *cuda_stream);
+AMPS_B200_API int amps_fwd_interp(const amps_fwd *h);
+AMPS_B200_API int amps_fwd_get_taps(const amps_fwd *h, int carrier, float *out, int cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMPS_B200_H */
