@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of gr_amps_b200: Msamples/s of complex IQ through the fused RECC
+demod + correlate path (BASELINE.json metric), at N GPUs of one node.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+N > 1 is launched by torchrun (one rank per GPU, NCCL only for the barrier / max-over-ranks; there is
+no collective on the sample path: every rank demodulates its own independent carrier -- weak scaling).
+
+One step = one batch of synthetic 10 MS/s baseband (128 config-2 periods = 269 107 200 complex
+samples = 2.15 GB, larger than L2, so every step streams from HBM) through
+amps_recc_iq_submit_dev (device-resident input; `value`) or amps_recc_iq_work (pinned HOST buffer,
+H2D + kernels + D2H of the burst records inside the timed region; `e2e`).
+
+--impl reference times the reference's own CPU path: GNU Radio cannot be built here, so it is the
+oracle port (oracle/, fp32 chain + detect + decode) on all host cores, on a bounded sample.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PASS = 9600
+PERIOD = 219 * PASS              # 2 102 400 samples, one 7-word origination burst
+PERIODS_PER_BATCH = 128
+ALG_BYTES_PER_SAMPLE = 8.0 + 1.0 / 500.0     # 8 B read + 1 B per half-symbol (500 samples)
+BURST_BYTES = 3374.0
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def load_traffic():
+    """dram bytes per front-kernel launch per sample, from the committed ncu summary (or None)."""
+    p = os.path.join(ROOT, "profiles", "rx_front_traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+class ClockSampler(threading.Thread):
+    """Polls NVML for SM clock / throttle reasons of one GPU while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self.power = []
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples),
+                "power_w_max": max(self.power) if self.power else None}
+
+
+def make_clean_period(rank):
+    from gr_amps_b200 import synth
+    # config 4: carrier g sits at -160 kHz + 30 kHz * g, its own MIN
+    center = -160e3 + 30e3 * rank
+    x, hs, _ = synth.config2_period(n_total=PERIOD, snr_db=None, center=center, min10="21255512%02d" % (30 + rank))
+    return x, hs, center
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle port of the chain on all host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    from tests import oracle_lib as O
+    from gr_amps_b200 import synth
+    cores = os.cpu_count() or 1
+    x, _, _ = synth.config2_period(n_total=PERIOD, snr_db=20.0, seed=0xA3B5)
+    reps = 4                                   # per thread per step: 4 periods (8.4 M samples)
+    for _ in range(max(args.warmup, 1)):
+        O.cpu_baseline_run(x, cores, 1)
+    t_total, nb = 0.0, 0
+    for _ in range(args.steps):
+        sec, b = O.cpu_baseline_run(x, cores, reps)
+        t_total += sec
+        nb += b
+    samples = float(args.steps) * cores * reps * len(x)
+    v = samples / t_total / 1e6
+    sample = "%d threads x %d x one config-2 period (%d samples) per step, same chain as the GPU arm (fp32 oracle port + detect + decode)" % (cores, reps, len(x))
+    line = {
+        "impl": "reference", "metric": "Msamples/s complex IQ through RECC demod+correlate", "value": v, "unit": "Msamples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "config2: 10 MS/s synthetic FM RECC bursts, 7-word origination, SNR 20 dB, one channel per host thread",
+                   "period_samples": PERIOD, "samples_per_step": cores * reps * len(x)},
+        "cpu_baseline": {"value": v, "unit": "Msamples/s", "cores": cores, "kind": "port", "sample": sample,
+                         "bursts_decoded": nb},
+        "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--periods", type=int, default=PERIODS_PER_BATCH)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from gr_amps_b200 import capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; gr_amps_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    # ---- synthetic batch: tile one clean period, add fresh AWGN (SNR 20 dB in 30 kHz) on the device
+    clean, hs, center = make_clean_period(rank)
+    nper = args.periods
+    n = nper * PERIOD
+    g = torch.Generator(device=dev)
+    g.manual_seed(0xA3B5 + rank)
+    base = torch.from_numpy(clean.view(np.float32).copy()).to(dev)
+    sigma = float(np.sqrt(0.25 / 100.0 * (10e6 / 30e3) / 2.0))
+    batch = base.repeat(nper)
+    batch.add_(torch.randn(batch.shape, generator=g, device=dev, dtype=torch.float32), alpha=sigma)
+    del base
+    torch.cuda.synchronize()
+
+    steps_total = args.warmup + args.steps
+    rx = capi.ReccIq(max_samples=n, center_freq=center, device=local_rank, max_bursts=nper * (steps_total + 2),
+                     time_kernels=True)
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm ------------------------------------------------------------------
+    for _ in range(args.warmup):
+        rx.submit_dev(batch.data_ptr(), n, stream.cuda_stream)
+    _, _, _, warm_count = rx.peek()
+    rx.consume(warm_count)
+    launches0 = rx.stats()["kernel_launches"]
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        rx.submit_dev(batch.data_ptr(), n, stream.cuda_stream)
+    ring, ring_len, first, count = rx.peek()   # stream sync; the kernels already published every record to the pinned host ring
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    launches = rx.stats()["kernel_launches"] - launches0
+    front_ms = rx.front_times_ms(256)[-args.steps:]
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+
+    # correctness gate: the stream is continuous over the steps, so all but the burst straddling the
+    # last batch's end are captured; every one must decode to this rank's MIN with all words valid
+    expect_min = ("21255512%02d" % (30 + rank)).encode()
+    bursts = [ring[(first + i) % ring_len] for i in range(count)]
+    ok = [b for b in bursts if b.decoded.min == expect_min and list(b.decoded.valid) == [1] * 7 and b.decoded.kind == 4]
+    if len(ok) < args.steps * nper - 2 or len(ok) != len(bursts):
+        raise SystemExit("bench.py: parity gate failed: %d bursts, %d good, expected >= %d" % (len(bursts), len(ok), args.steps * nper - 2))
+    n_bursts = len(bursts)
+    del bursts
+    rx.consume(count)
+
+    # ---- end-to-end arm: pinned host buffer through amps_recc_iq_work ----------------------------
+    host = torch.empty(batch.shape, dtype=torch.float32, pin_memory=True)
+    host.copy_(batch)
+    torch.cuda.synchronize()
+    rx2 = capi.ReccIq(max_samples=n, center_freq=center, device=local_rank, max_bursts=2 * nper + 8)
+    got = []
+    cb = capi.BURST_CB(lambda bp, user: got.append(bp.contents.decoded.min))
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        rx2.work_ptr(host.data_ptr(), n, cb)
+    got.clear()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        rx2.work_ptr(host.data_ptr(), n, cb)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    te = torch.tensor([t1 - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_sec = float(te.item())
+    if len(got) < e2e_steps * nper - 2 or any(m != expect_min for m in got):
+        raise SystemExit("bench.py: e2e parity gate failed (%d bursts)" % len(got))
+    rec_bytes = 24 + (len(got) / e2e_steps) * float(capi.C.sizeof(capi.Burst))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = load_peaks()
+    value = world * args.steps * n / (ms_max * 1e-3) / 1e6
+    fm = float(np.mean(front_ms)) if len(front_ms) else float("nan")
+    alg_bytes = n * ALG_BYTES_PER_SAMPLE + nper * BURST_BYTES
+    achieved = alg_bytes / (fm * 1e-3) / 1e9
+    traffic = load_traffic()
+    roofline = {
+        "bound": "hbm", "kernel": "rx_front_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak, "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": fm,
+        "traffic": (traffic["dram_bytes_per_sample"] * n if traffic else None),
+        "front_share_of_step": fm / (ms_max / args.steps),
+    }
+
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        from tests import oracle_lib as O
+        from gr_amps_b200 import synth
+        cores = os.cpu_count() or 1
+        xs, _, _ = synth.config2_period(n_total=PERIOD, snr_db=20.0, seed=0xA3B5)
+        O.cpu_baseline_run(xs, cores, 1)
+        reps = 8
+        sec, nb = O.cpu_baseline_run(xs, cores, reps)
+        cpu = {"value": cores * reps * len(xs) / sec / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "port",
+               "sample": "%d threads x %d x one config-2 period (%d samples); fp32 oracle chain + detect + decode; %.1f s CPU work"
+                         % (cores, reps, len(xs), sec * cores), "bursts_decoded": nb}
+
+    line = {
+        "metric": "Msamples/s complex IQ through RECC demod+correlate",
+        "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "config2: single RECC chain per GPU, 10 MS/s synthetic FM RECC bursts (7-word origination, SNR 20 dB), demod+correlate+decode, bit-exact word recovery gated",
+                   "samples_per_step_per_gpu": n, "bursts_per_step_per_gpu": nper, "period_samples": PERIOD,
+                   "carriers": "one per GPU at -160 kHz + 30 kHz*rank", "l2": "inputs larger than L2 (2.15 GB per step)",
+                   "timing": "CUDA events on the launching stream, max over ranks"},
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "clocks": clocks,
+        "e2e": {"value": world * e2e_steps * n / e2e_sec / 1e6, "unit": "Msamples/s",
+                "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": int(rec_bytes), "steps": e2e_steps,
+                "api": "amps_recc_iq_work (pinned host buffer, burst callbacks)"},
+        "gpu_launches": int(launches) * world,
+        "bursts_decoded": n_bursts,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

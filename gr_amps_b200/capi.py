@@ -81,13 +81,14 @@ BURST_CB = C.CFUNCTYPE(None, C.POINTER(Burst), C.c_void_p)
 BLOB_CB = C.CFUNCTYPE(None, u8p, C.c_void_p)
 
 RX_DUMP_BASEBAND = 1
+RX_TIME_KERNELS = 2
 
 # every symbol include/amps_b200.h declares
 EXPORTS = [
-    "amps_b200_version", "amps_b200_strerror", "amps_b200_last_error", "amps_b200_device_count",
+    "amps_b200_version", "amps_b200_strerror", "amps_b200_last_error", "amps_b200_device_count", "amps_b200_abi_sizes",
     "amps_recc_iq_create", "amps_recc_iq_destroy", "amps_recc_iq_reset", "amps_recc_iq_work",
-    "amps_recc_iq_submit_dev", "amps_recc_iq_collect", "amps_recc_iq_granularity", "amps_recc_iq_read_demod",
-    "amps_recc_iq_read_baseband", "amps_recc_iq_stats", "amps_recc_iq_get_taps",
+    "amps_recc_iq_submit_dev", "amps_recc_iq_collect", "amps_recc_iq_peek", "amps_recc_iq_consume", "amps_recc_iq_granularity", "amps_recc_iq_read_demod",
+    "amps_recc_iq_read_baseband", "amps_recc_iq_stats", "amps_recc_iq_front_times", "amps_recc_iq_get_taps",
     "amps_recc_decode_create", "amps_recc_decode_destroy", "amps_recc_decode_burst", "amps_recc_decode_bursts",
     "amps_recc_create", "amps_recc_destroy", "amps_recc_work", "amps_recc_work_chunks",
     "amps_focc_create", "amps_focc_destroy", "amps_focc_work", "amps_focc_generate", "amps_focc_generate_dev",
@@ -118,10 +119,19 @@ def lib() -> C.CDLL:
     L.amps_recc_iq_submit_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     L.amps_recc_iq_collect.argtypes = [C.c_void_p, C.POINTER(Burst), C.c_int, C.POINTER(C.c_int)]
     L.amps_recc_iq_granularity.argtypes = [C.c_void_p]
+    L.amps_recc_iq_peek.argtypes = [C.c_void_p, C.POINTER(C.POINTER(Burst)), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.amps_recc_iq_consume.argtypes = [C.c_void_p, C.c_uint64]
+    L.amps_b200_abi_sizes.argtypes = [C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    bs, ws = C.c_size_t(0), C.c_size_t(0)
+    L.amps_b200_abi_sizes(C.byref(bs), C.byref(ws))
+    if bs.value != C.sizeof(Burst) or ws.value != C.sizeof(ReccWords):
+        raise ImportError("gr_amps_b200.capi struct layout (%d, %d) does not match libamps_b200.so (%d, %d)"
+                          % (C.sizeof(Burst), C.sizeof(ReccWords), bs.value, ws.value))
     L.amps_recc_iq_read_demod.argtypes = [C.c_void_p, C.c_uint64, f32p, C.c_size_t]
     L.amps_recc_iq_read_baseband.argtypes = [C.c_void_p, C.c_uint64, f32p, C.c_size_t]
     L.amps_recc_iq_stats.argtypes = [C.c_void_p] + [C.POINTER(C.c_uint64)] * 4
     L.amps_recc_iq_get_taps.argtypes = [C.c_void_p, f32p, C.c_int]
+    L.amps_recc_iq_front_times.argtypes = [C.c_void_p, f32p, C.c_int, C.POINTER(C.c_int)]
     L.amps_recc_decode_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
     L.amps_recc_decode_destroy.argtypes = [C.c_void_p]
     L.amps_recc_decode_burst.argtypes = [C.c_void_p, u8p, C.POINTER(ReccWords)]
@@ -165,10 +175,10 @@ class ReccIq:
     """Fused RECC receive path on IQ (amps_recc_iq_*)."""
 
     def __init__(self, max_samples: int, center_freq=-160e3, samp_rate=10e6, device=0, max_bursts=256,
-                 dump_baseband=False, lpf_taps: np.ndarray | None = None):
+                 dump_baseband=False, lpf_taps: np.ndarray | None = None, time_kernels=False):
         self._taps = None if lpf_taps is None else np.ascontiguousarray(lpf_taps, dtype=np.float32)
         p = ReccIqParams(samp_rate, center_freq, device, max_samples, max_bursts,
-                         RX_DUMP_BASEBAND if dump_baseband else 0,
+                         (RX_DUMP_BASEBAND if dump_baseband else 0) | (RX_TIME_KERNELS if time_kernels else 0),
                          None if self._taps is None else self._taps.ctypes.data_as(f32p),
                          0 if self._taps is None else len(self._taps))
         self.h = C.c_void_p()
@@ -214,6 +224,16 @@ class ReccIq:
         check(lib().amps_recc_iq_collect(self.h, arr, m, C.byref(n)))
         return [arr[i] for i in range(n.value)]
 
+    def peek(self):
+        """Zero-copy view of the published bursts: (ring pointer, ring_len, first, count); call consume(count) after."""
+        ring = C.POINTER(Burst)()
+        rl, first, count = C.c_uint32(0), C.c_uint64(0), C.c_uint64(0)
+        check(lib().amps_recc_iq_peek(self.h, C.byref(ring), C.byref(rl), C.byref(first), C.byref(count)))
+        return ring, rl.value, first.value, count.value
+
+    def consume(self, count: int):
+        check(lib().amps_recc_iq_consume(self.h, count))
+
     def read_demod(self, first: int, n: int) -> np.ndarray:
         out = np.zeros(n, np.float32)
         check(lib().amps_recc_iq_read_demod(self.h, first, out.ctypes.data_as(f32p), n))
@@ -228,6 +248,12 @@ class ReccIq:
         v = [C.c_uint64(0) for _ in range(4)]
         check(lib().amps_recc_iq_stats(self.h, *[C.byref(x) for x in v]))
         return dict(samples_in=v[0].value, demod_out=v[1].value, bursts=v[2].value, kernel_launches=v[3].value)
+
+    def front_times_ms(self, cap: int = 256) -> np.ndarray:
+        out = np.zeros(cap, np.float32)
+        n = C.c_int(0)
+        check(lib().amps_recc_iq_front_times(self.h, out.ctypes.data_as(f32p), cap, C.byref(n)))
+        return out[:n.value].copy()
 
     def taps(self) -> np.ndarray:
         n = lib().amps_recc_iq_get_taps(self.h, None, 0)

@@ -32,9 +32,11 @@ struct amps_recc_iq {
     uint64_t     ydump_first = 0, ydump_count = 0;
     RxState     *d_state = nullptr;
     Candidate   *d_cand = nullptr;
-    amps_burst  *d_rec = nullptr;
-    amps_burst  *h_rec = nullptr;        // pinned
-    RxState     *h_state = nullptr;      // pinned
+    amps_burst  *d_scratch = nullptr;    // record assembly area (kMaxAccept entries)
+    amps_burst  *h_ring = nullptr;       // mapped pinned host ring the select kernel publishes into
+    RxPublished *h_pub = nullptr;        // mapped pinned counters
+    uint64_t     consumed = 0;           // bursts already handed to the caller
+    uint64_t     lost = 0;               // bursts overwritten in the ring before they were collected
     cudaStream_t last_stream = nullptr;
 
     size_t       carry = 0;              // unprocessed samples sitting at the front of d_stage
@@ -42,6 +44,10 @@ struct amps_recc_iq {
     uint64_t     total_d = 0;            // demod samples produced
     uint64_t     scan_hi = 0;            // positions below this have been searched
     uint64_t     bursts = 0, launches = 0;
+    // AMPS_RX_TIME_KERNELS: ring of event pairs around the front-end kernel
+    static constexpr int kEv = 256;
+    cudaEvent_t  ev0[kEv] = {}, ev1[kEv] = {};
+    uint64_t     ev_count = 0;
 };
 
 static int rx_alloc(amps_recc_iq *h) {
@@ -63,10 +69,13 @@ static int rx_alloc(amps_recc_iq *h) {
     CK(cudaMalloc(&h->d_state, sizeof(RxState)));
     CK(cudaMemset(h->d_state, 0, sizeof(RxState)));
     CK(cudaMalloc(&h->d_cand, sizeof(Candidate) * kMaxCand));
-    CK(cudaMalloc(&h->d_rec, sizeof(amps_burst) * h->max_records));
-    CK(cudaMallocHost(&h->h_rec, sizeof(amps_burst) * h->max_records));
-    CK(cudaMallocHost(&h->h_state, sizeof(RxState)));
+    CK(cudaMalloc(&h->d_scratch, sizeof(amps_burst) * kMaxAccept));
+    CK(cudaHostAlloc(&h->h_ring, sizeof(amps_burst) * h->max_records, cudaHostAllocMapped));
+    CK(cudaHostAlloc(&h->h_pub, sizeof(RxPublished), cudaHostAllocMapped));
+    std::memset(h->h_pub, 0, sizeof(RxPublished));
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    if (h->flags & AMPS_RX_TIME_KERNELS)
+        for (int i = 0; i < amps_recc_iq::kEv; ++i) { CK(cudaEventCreate(&h->ev0[i])); CK(cudaEventCreate(&h->ev1[i])); }
     return AMPS_OK;
 }
 
@@ -113,11 +122,13 @@ extern "C" int amps_recc_iq_create(const amps_recc_iq_params *params, amps_recc_
 extern "C" int amps_recc_iq_destroy(amps_recc_iq *h) {
     if (!h) return AMPS_OK;
     cudaSetDevice(h->device);
-    if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+    cudaDeviceSynchronize();
+    if (h->stream) cudaStreamDestroy(h->stream);
+    for (int i = 0; i < amps_recc_iq::kEv; ++i) { if (h->ev0[i]) cudaEventDestroy(h->ev0[i]); if (h->ev1[i]) cudaEventDestroy(h->ev1[i]); }
     cudaFree(h->d_stage); cudaFree(h->d_tail[0]); cudaFree(h->d_tail[1]); cudaFree(h->d_dring);
-    cudaFree(h->d_ydump); cudaFree(h->d_state); cudaFree(h->d_cand); cudaFree(h->d_rec);
-    if (h->h_rec) cudaFreeHost(h->h_rec);
-    if (h->h_state) cudaFreeHost(h->h_state);
+    cudaFree(h->d_ydump); cudaFree(h->d_state); cudaFree(h->d_cand); cudaFree(h->d_scratch);
+    if (h->h_ring) cudaFreeHost(h->h_ring);
+    if (h->h_pub) cudaFreeHost(h->h_pub);
     delete h;
     return AMPS_OK;
 }
@@ -129,6 +140,8 @@ extern "C" int amps_recc_iq_reset(amps_recc_iq *h) {
     for (int i = 0; i < 2; ++i) CK(cudaMemset(h->d_tail[i], 0, (size_t)kHist * sizeof(float2)));
     CK(cudaMemset(h->d_state, 0, sizeof(RxState)));
     CK(cudaMemset(h->d_dring, 0, ((size_t)h->dmask + 1) * sizeof(float)));
+    std::memset(h->h_pub, 0, sizeof(RxPublished));
+    h->consumed = 0;
     h->tail_cur = 0; h->carry = 0; h->samples_in = 0; h->total_d = 0; h->scan_hi = 0;
     h->ydump_first = 0; h->ydump_count = 0;
     return AMPS_OK;
@@ -149,7 +162,11 @@ static int rx_enqueue(amps_recc_iq *h, const float2 *d_chunk, uint32_t npass, cu
     p.ydump = h->d_ydump;
     int grid = 2 * h->sm_count;
     if ((uint32_t)grid > npass) grid = (int)npass;
+    const bool timed = (h->flags & AMPS_RX_TIME_KERNELS) != 0;
+    const int  evi = (int)(h->ev_count % amps_recc_iq::kEv);
+    if (timed) CK(cudaEventRecord(h->ev0[evi], st));
     CKL(launch_rx_front(p, grid, st));
+    if (timed) { CK(cudaEventRecord(h->ev1[evi], st)); h->ev_count++; }
     h->launches++;
     // history for the next call = the last pass of this one
     CK(cudaMemcpyAsync(h->d_tail[h->tail_cur ^ 1], d_chunk + (size_t)(npass - 1) * kPass, (size_t)kHist * sizeof(float2),
@@ -165,7 +182,8 @@ static int rx_enqueue(amps_recc_iq *h, const float2 *d_chunk, uint32_t npass, cu
         const uint64_t lo = h->scan_hi > 64 ? h->scan_hi - 64 : 0;
         if (hi > h->scan_hi) {
             CKL(launch_rx_detect(h->d_dring, h->dmask, h->d_state, h->d_cand, lo, hi, st));
-            CKL(launch_rx_select(h->d_dring, h->dmask, h->d_state, h->d_cand, hi, h->d_rec, h->max_records, st));
+            CKL(launch_rx_select(h->d_dring, h->dmask, h->d_state, h->d_cand, hi, h->d_scratch, h->h_ring, h->max_records,
+                                 h->h_pub, st));
             h->launches += 2;
             h->scan_hi = hi;
         }
@@ -185,23 +203,18 @@ extern "C" int amps_recc_iq_submit_dev(amps_recc_iq *h, const void *d_iq, size_t
     return rx_enqueue(h, static_cast<const float2 *>(d_iq), (uint32_t)(nsamples / kPass), static_cast<cudaStream_t>(cuda_stream));
 }
 
-// Wait for the stream, bring the records found since the last fetch into h->h_rec.
-static int rx_fetch(amps_recc_iq *h, unsigned int *n_out) {
+// Wait for the stream; afterwards records [h->consumed, h->consumed + *n_out) sit in the host ring.
+static int rx_fetch(amps_recc_iq *h, uint64_t *n_out) {
     *n_out = 0;
-    cudaStream_t st = h->last_stream;
-    CK(cudaMemcpyAsync(h->h_state, h->d_state, sizeof(RxState), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    if (h->h_state->cand_overflow)
+    CK(cudaStreamSynchronize(h->last_stream));
+    if (h->h_pub->cand_overflow)
         return set_error(AMPS_E_OVERFLOW, "trigger candidate list overflowed (more than 8192 matches in one call)");
-    unsigned int n = h->h_state->nrec;
-    if (n > h->max_records) n = h->max_records;
-    if (n) {
-        CK(cudaMemcpyAsync(h->h_rec, h->d_rec, sizeof(amps_burst) * n, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemsetAsync(&h->d_state->nrec, 0, sizeof(unsigned int), st));
-        CK(cudaStreamSynchronize(st));
+    const uint64_t total = h->h_pub->nrec_total;
+    if (total - h->consumed > h->max_records) {           // the ring wrapped over uncollected records
+        h->lost += total - h->consumed - h->max_records;
+        h->consumed = total - h->max_records;
     }
-    h->bursts += n;
-    *n_out = n;
+    *n_out = total - h->consumed;
     return AMPS_OK;
 }
 
@@ -209,12 +222,32 @@ extern "C" int amps_recc_iq_collect(amps_recc_iq *h, amps_burst *out, int max, i
     if (!h || !n_out || (max > 0 && !out)) return set_error(AMPS_E_INVAL, "null argument");
     *n_out = 0;
     CK(cudaSetDevice(h->device));
-    unsigned int n = 0;
+    uint64_t n = 0;
     int rc = rx_fetch(h, &n);
     if (rc != AMPS_OK) return rc;
-    const int give = (int)n < max ? (int)n : max;      // records beyond max are dropped
-    for (int i = 0; i < give; ++i) out[i] = h->h_rec[i];
-    *n_out = give;
+    const uint64_t give = n < (uint64_t)max ? n : (uint64_t)max;     // the rest stays for the next collect
+    for (uint64_t i = 0; i < give; ++i) out[i] = h->h_ring[(h->consumed + i) % h->max_records];
+    h->consumed += give;
+    h->bursts += give;
+    *n_out = (int)give;
+    return AMPS_OK;
+}
+
+extern "C" int amps_recc_iq_peek(amps_recc_iq *h, const amps_burst **ring, uint32_t *ring_len, uint64_t *first, uint64_t *count) {
+    if (!h || !ring || !ring_len || !first || !count) return set_error(AMPS_E_INVAL, "null argument");
+    CK(cudaSetDevice(h->device));
+    uint64_t n = 0;
+    int rc = rx_fetch(h, &n);
+    if (rc != AMPS_OK) return rc;
+    *ring = h->h_ring; *ring_len = h->max_records; *first = h->consumed; *count = n;
+    return AMPS_OK;
+}
+
+extern "C" int amps_recc_iq_consume(amps_recc_iq *h, uint64_t count) {
+    if (!h) return set_error(AMPS_E_INVAL, "null handle");
+    if (h->consumed + count > h->h_pub->nrec_total) return set_error(AMPS_E_INVAL, "consuming more bursts than were published");
+    h->consumed += count;
+    h->bursts += count;
     return AMPS_OK;
 }
 
@@ -238,11 +271,14 @@ extern "C" int amps_recc_iq_work(amps_recc_iq *h, const float *iq_host, size_t n
     } else {
         h->carry = avail;
     }
-    // deliver bursts in stream order, like message_port_pub("bursts", ...) from work() (lib/recc_impl.cc:126)
-    unsigned int n = 0;
+    // deliver bursts in stream order, like message_port_pub("bursts", ...) from work() (lib/recc_impl.cc:126);
+    // the callback sees the record in place in the pinned ring
+    uint64_t n = 0;
     int rc = rx_fetch(h, &n);
     if (rc != AMPS_OK) return rc;
-    if (cb) for (unsigned int i = 0; i < n; ++i) cb(&h->h_rec[i], user);
+    if (cb) for (uint64_t i = 0; i < n; ++i) cb(&h->h_ring[(h->consumed + i) % h->max_records], user);
+    h->consumed += n;
+    h->bursts += n;
     return AMPS_OK;
 }
 
@@ -281,6 +317,22 @@ extern "C" int amps_recc_iq_stats(const amps_recc_iq *h, uint64_t *samples_in, u
     if (demod_out) *demod_out = h->total_d;
     if (bursts) *bursts = h->bursts;
     if (kernel_launches) *kernel_launches = h->launches;
+    return AMPS_OK;
+}
+
+extern "C" int amps_recc_iq_front_times(amps_recc_iq *h, float *ms_out, int cap, int *n_out) {
+    if (!h || !n_out || (cap > 0 && !ms_out)) return set_error(AMPS_E_INVAL, "null argument");
+    *n_out = 0;
+    if (!(h->flags & AMPS_RX_TIME_KERNELS)) return set_error(AMPS_E_STATE, "handle was not created with AMPS_RX_TIME_KERNELS");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->last_stream));
+    uint64_t have = h->ev_count < (uint64_t)amps_recc_iq::kEv ? h->ev_count : (uint64_t)amps_recc_iq::kEv;
+    if (have > (uint64_t)cap) have = (uint64_t)cap;
+    for (uint64_t k = 0; k < have; ++k) {
+        const int i = (int)((h->ev_count - have + k) % amps_recc_iq::kEv);
+        CK(cudaEventElapsedTime(&ms_out[k], h->ev0[i], h->ev1[i]));
+    }
+    *n_out = (int)have;
     return AMPS_OK;
 }
 

@@ -44,6 +44,12 @@ int select_device(int device) {
 
 extern "C" int amps_b200_version(void) { return 100; }
 
+extern "C" int amps_b200_abi_sizes(size_t *burst_bytes, size_t *words_bytes) {
+    if (burst_bytes) *burst_bytes = sizeof(amps_burst);
+    if (words_bytes) *words_bytes = sizeof(amps_recc_words);
+    return AMPS_OK;
+}
+
 extern "C" const char *amps_b200_last_error(void) { return amps::g_err; }
 
 extern "C" const char *amps_b200_strerror(int status) {

@@ -18,6 +18,8 @@
 
 namespace amps {
 
+static_assert(sizeof(amps_burst) % 8 == 0, "burst records are streamed to the host ring in 8-byte words");
+
 // ============================================================================================
 // front end
 // ============================================================================================
@@ -365,11 +367,9 @@ cudaError_t launch_decode_blobs(const uint8_t *blobs, int nbursts, amps_recc_wor
 // ============================================================================================
 // candidate selection + capture + decode (single CTA; candidates are rare)
 // ============================================================================================
-constexpr int kMaxAccept = 512;
-
 __global__ void __launch_bounds__(256) rx_select_kernel(const float *__restrict__ dring, uint32_t dmask, RxState *state,
-                                                       Candidate *cand, unsigned long long scan_hi, amps_burst *records,
-                                                       unsigned int max_records) {
+                                                       Candidate *cand, unsigned long long scan_hi, amps_burst *scratch,
+                                                       amps_burst *host_ring, unsigned int ring_len, RxPublished *host_pub) {
     extern __shared__ unsigned char sel_raw[];
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(sel_raw);          // kMaxCand
     float *corr = reinterpret_cast<float *>(keys + kMaxCand);                            // kMaxCand
@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(256) rx_select_kernel(const float *__restrict_
     __shared__ unsigned int n_acc;
     __shared__ uint8_t s_valid[40];
     __shared__ unsigned int s_errs[8];
-    __shared__ unsigned int rec_base;
+    __shared__ unsigned long long rec_base;
 
     const int t = threadIdx.x, nt = blockDim.x;
     unsigned int n = state->ncand;
@@ -439,16 +439,11 @@ __global__ void __launch_bounds__(256) rx_select_kernel(const float *__restrict_
         state->resume_at = resume;
         state->ncand = 0;
         n_acc = na;
-        rec_base = state->nrec;
+        rec_base = state->nrec_total;
     }
     __syncthreads();
     for (unsigned int a = 0; a < n_acc; ++a) {
-        const unsigned int slot = rec_base + a;
-        if (slot >= max_records) {
-            if (t == 0) atomicAdd(&state->dropped, 1u);
-            continue;
-        }
-        amps_burst *rec = &records[slot];
+        amps_burst *rec = &scratch[a];
         const unsigned long long pos = acc_pos[a];
         for (int s = t; s < kCapture; s += nt) {
             const float v = dring[(pos + (unsigned long long)(kOS * (kTrig + s))) & dmask];
@@ -463,18 +458,25 @@ __global__ void __launch_bounds__(256) rx_select_kernel(const float *__restrict_
         }
         __syncthreads();
         decode_burst_block(rec->symbols, &rec->decoded, s_valid, s_errs);
+        // publish: stream the finished record into the host-visible ring (posted PCIe writes)
+        const unsigned long long *src = reinterpret_cast<const unsigned long long *>(rec);
+        unsigned long long *dst = reinterpret_cast<unsigned long long *>(&host_ring[(rec_base + a) % ring_len]);
+        for (int w = t; w < (int)(sizeof(amps_burst) / 8); w += nt) dst[w] = src[w];
     }
+    __syncthreads();
     if (t == 0) {
-        unsigned int kept = n_acc;
-        if (rec_base + kept > max_records) kept = max_records > rec_base ? max_records - rec_base : 0;
-        state->nrec = rec_base + kept;
+        state->nrec_total = rec_base + n_acc;
+        __threadfence_system();
+        host_pub->cand_overflow = state->cand_overflow;
+        host_pub->nrec_total = rec_base + n_acc;
     }
 }
 
 cudaError_t launch_rx_select(const float *dring, uint32_t dmask, RxState *state, Candidate *cand,
-                             unsigned long long scan_hi, amps_burst *records, unsigned int max_records, cudaStream_t st) {
+                             unsigned long long scan_hi, amps_burst *scratch, amps_burst *host_ring, unsigned int ring_len,
+                             RxPublished *host_pub, cudaStream_t st) {
     const size_t smem = (size_t)kMaxCand * (sizeof(unsigned long long) + sizeof(float));
-    rx_select_kernel<<<1, 256, smem, st>>>(dring, dmask, state, cand, scan_hi, records, max_records);
+    rx_select_kernel<<<1, 256, smem, st>>>(dring, dmask, state, cand, scan_hi, scratch, host_ring, ring_len, host_pub);
     return cudaGetLastError();
 }
 

@@ -33,24 +33,32 @@ struct RxFrontParams {
 struct RxState {             // device-resident stream state
     unsigned long long lo;          // next demod position to search
     unsigned long long resume_at;   // positions below this are inside an already captured burst
+    unsigned long long nrec_total;  // bursts published since stream start (monotonic)
     unsigned int       ncand;       // candidates found by the detect kernel (reset by select)
-    unsigned int       nrec;        // records written since the last collect
-    unsigned int       dropped;     // records lost to a full record buffer
     unsigned int       cand_overflow;
+};
+
+struct RxPublished {         // mirror of the counters in mapped pinned host memory, written by the select kernel
+    unsigned long long nrec_total;
+    unsigned int       cand_overflow;
+    unsigned int       pad;
 };
 
 struct Candidate { unsigned long long pos; float corr; unsigned int pad; };
 
 constexpr int kMaxCand = 8192;
+constexpr int kMaxAccept = 512;    // bursts one call can publish
 
 size_t rx_front_smem_bytes();
 cudaError_t rx_configure_device();
 cudaError_t launch_rx_front(const RxFrontParams &p, int grid, cudaStream_t st);
 cudaError_t launch_rx_detect(const float *dring, uint32_t dmask, RxState *state, Candidate *cand,
                              unsigned long long scan_lo, unsigned long long scan_hi, cudaStream_t st);
+// records are assembled in `scratch` (device memory, kMaxAccept entries) and then streamed into
+// host_ring[(nrec_total + a) % ring_len] (mapped pinned host memory, device-visible alias)
 cudaError_t launch_rx_select(const float *dring, uint32_t dmask, RxState *state, Candidate *cand,
-                             unsigned long long scan_hi, amps_burst *records, unsigned int max_records,
-                             cudaStream_t st);
+                             unsigned long long scan_hi, amps_burst *scratch, amps_burst *host_ring,
+                             unsigned int ring_len, RxPublished *host_pub, cudaStream_t st);
 cudaError_t launch_decode_blobs(const uint8_t *blobs, int nbursts, amps_recc_words *out, cudaStream_t st);
 
 }  // namespace amps

@@ -91,6 +91,10 @@ typedef struct amps_burst {
     amps_recc_words decoded;
 } amps_burst;
 
+/* sizeof(amps_burst) / sizeof(amps_recc_words) as this library was built: lets a binding check its
+ * struct layout before trusting it. */
+AMPS_B200_API int amps_b200_abi_sizes(size_t *burst_bytes, size_t *words_bytes);
+
 /* ------------------------------------------------------------------------------------------
  * Fused RECC receive path on IQ.  One handle replaces, for one carrier, the chain
  *   freq_xlating_fir_filter_ccc -> quadrature_demod_cf -> clock_recovery_mm_ff ->
@@ -105,13 +109,14 @@ typedef struct amps_recc_iq_params {
     double   center_freq;        /* carrier offset inside the band, Hz (reference: rx_offset = -160e3, grc/ampsbs.grc:212-238) */
     int      device;             /* CUDA ordinal */
     uint32_t max_samples;        /* largest nsamples ever passed in one call (sizes device buffers) */
-    uint32_t max_bursts;         /* burst records kept per call before the oldest are dropped (0 -> 256) */
+    uint32_t max_bursts;         /* length of the pinned host ring of burst records; uncollected bursts beyond it are overwritten (0 -> 256) */
     uint32_t flags;              /* AMPS_RX_* */
     const float *lpf_taps;       /* channel filter taps @400 kS/s, NULL -> firdes.low_pass(3,400e3,10e3,4.5e3,BLACKMAN) */
     uint32_t n_lpf_taps;         /* <= 299 */
 } amps_recc_iq_params;
 
 #define AMPS_RX_DUMP_BASEBAND 1u   /* keep the 200 kS/s complex baseband of the last call for inspection */
+#define AMPS_RX_TIME_KERNELS  2u   /* bracket every front-end kernel launch with CUDA events (roofline accounting) */
 
 typedef void (*amps_burst_cb)(const amps_burst *burst, void *user);
 
@@ -131,14 +136,23 @@ AMPS_B200_API int amps_recc_iq_work(amps_recc_iq *h, const float *iq_host, size_
  * nsamples a multiple of amps_recc_iq_granularity(); kernels are enqueued on cuda_stream
  * (a cudaStream_t, NULL = default stream) and the call returns without synchronising. */
 AMPS_B200_API int amps_recc_iq_submit_dev(amps_recc_iq *h, const void *d_iq, size_t nsamples, void *cuda_stream);
-/* Waits for the stream, copies out the bursts found since the last collect (at most max). */
+/* Waits for the stream, copies out the bursts published since the last collect (at most max; the
+ * rest stays queued). */
 AMPS_B200_API int amps_recc_iq_collect(amps_recc_iq *h, amps_burst *out, int max, int *n_out);
+/* Zero-copy form: waits for the stream and exposes the pinned host ring the kernels publish into.
+ * Bursts number first .. first+count-1 are at ring[(first + i) % ring_len]; call consume() when done. */
+AMPS_B200_API int amps_recc_iq_peek(amps_recc_iq *h, const amps_burst **ring, uint32_t *ring_len,
+                                    uint64_t *first, uint64_t *count);
+AMPS_B200_API int amps_recc_iq_consume(amps_recc_iq *h, uint64_t count);
 AMPS_B200_API int amps_recc_iq_granularity(const amps_recc_iq *h);
 /* Inspection (tests / roofline accounting) */
 AMPS_B200_API int amps_recc_iq_read_demod(amps_recc_iq *h, uint64_t first, float *out, size_t n);          /* 200 kS/s FM demod */
 AMPS_B200_API int amps_recc_iq_read_baseband(amps_recc_iq *h, uint64_t first, float *out_iq, size_t n);    /* needs AMPS_RX_DUMP_BASEBAND */
 AMPS_B200_API int amps_recc_iq_stats(const amps_recc_iq *h, uint64_t *samples_in, uint64_t *demod_out,
                                      uint64_t *bursts, uint64_t *kernel_launches);
+/* Needs AMPS_RX_TIME_KERNELS: device time (ms) of the most recent front-end kernel launches, oldest
+ * first, at most cap (the handle keeps the last 256).  Synchronises the stream. */
+AMPS_B200_API int amps_recc_iq_front_times(amps_recc_iq *h, float *ms_out, int cap, int *n_out);
 AMPS_B200_API int amps_recc_iq_get_taps(const amps_recc_iq *h, float *lpf_out, int cap);                   /* returns ntaps */
 
 /* ------------------------------------------------------------------------------------------

@@ -91,7 +91,7 @@ def lib() -> C.CDLL:
     L.orc_rx_chain_f64.argtypes = [f32p, C.c_size_t, C.c_uint32, f32p, C.c_int, f64p, f64p]
     L.orc_rx_chain_f32.argtypes = [f32p, C.c_size_t, C.c_uint32, f32p, C.c_int, f32p, f32p]
     L.orc_rx_detect.argtypes = [f32p, C.c_size_t, C.POINTER(Burst), C.c_int]
-    L.orc_cpu_baseline_run.argtypes = [f32p, C.c_size_t, C.c_uint32, f32p, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    L.orc_cpu_baseline_run.argtypes = [f32p, C.c_size_t, C.c_uint32, f32p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
     L.orc_cpu_baseline_run.restype = C.c_double
     for name in ("orc_overhead_word_1", "orc_overhead_word_2", "orc_control_filler_word"):
         getattr(L, name).restype = None
@@ -178,6 +178,17 @@ def rx_detect(d: np.ndarray, max_bursts=64):
     arr = (Burst * max_bursts)()
     n = lib().orc_rx_detect(ptr(d, f32p), len(d), arr, max_bursts)
     return [(int(arr[i].d_index), float(arr[i].corr), np.frombuffer(bytes(arr[i].symbols), np.uint8).copy()) for i in range(n)]
+
+
+def cpu_baseline_run(x: np.ndarray, threads: int, reps: int, center=-160e3, fs=10e6):
+    """Time the fp32 oracle chain (+detect+decode) on `threads` host threads; returns (seconds, bursts)."""
+    iq = iq_f32(x)
+    n = len(x) - len(x) % 50
+    taps = lpf_taps()
+    fcw = lib().orc_nco_fcw(center, fs)
+    nb = C.c_int(0)
+    sec = lib().orc_cpu_baseline_run(ptr(iq, f32p), n, fcw, ptr(taps, f32p), len(taps), threads, reps, C.byref(nb))
+    return sec, nb.value
 
 
 def recc_decode(blob) -> ReccResult:
