@@ -7,8 +7,8 @@ demod + correlate path (BASELINE.json metric), at N GPUs of one node.
 N > 1 is launched by torchrun (one rank per GPU, NCCL only for the barrier / max-over-ranks; there is
 no collective on the sample path: every rank demodulates its own independent carrier -- weak scaling).
 
-One step = one batch of synthetic 10 MS/s baseband (128 config-2 periods = 269 107 200 complex
-samples = 2.15 GB, larger than L2, so every step streams from HBM) through
+One step = one batch of synthetic 10 MS/s baseband (128 config-2 periods = 270 336 000 complex
+samples = 2.16 GB, larger than L2, so every step streams from HBM) through
 amps_recc_iq_submit_dev (device-resident input; `value`) or amps_recc_iq_work (pinned HOST buffer,
 H2D + kernels + D2H of the burst records inside the timed region; `e2e`).
 
@@ -27,8 +27,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-PASS = 9600
-PERIOD = 219 * PASS              # 2 102 400 samples, one 7-word origination burst
+PASS = 38400                     # amps_recc_iq_granularity()
+PERIOD = 55 * PASS               # 2 112 000 samples, one 7-word origination burst
 PERIODS_PER_BATCH = 128
 ALG_BYTES_PER_SAMPLE = 8.0 + 1.0 / 500.0     # 8 B read + 1 B per half-symbol (500 samples)
 BURST_BYTES = 3374.0
@@ -305,7 +305,7 @@ def main():
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "config2: single RECC chain per GPU, 10 MS/s synthetic FM RECC bursts (7-word origination, SNR 20 dB), demod+correlate+decode, bit-exact word recovery gated",
                    "samples_per_step_per_gpu": n, "bursts_per_step_per_gpu": nper, "period_samples": PERIOD,
-                   "carriers": "one per GPU at -160 kHz + 30 kHz*rank", "l2": "inputs larger than L2 (2.15 GB per step)",
+                   "carriers": "one per GPU at -160 kHz + 30 kHz*rank", "l2": "inputs larger than L2 (2.16 GB per step at the default 128 periods)",
                    "timing": "CUDA events on the launching stream, max over ranks"},
         "roofline": roofline,
         "cpu_baseline": cpu,

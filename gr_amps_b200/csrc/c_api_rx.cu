@@ -5,6 +5,7 @@
 #include "design.h"
 #include "rx_kernels.cuh"
 
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -26,18 +27,24 @@ struct amps_recc_iq {
     float2      *d_tail[2] = {nullptr, nullptr};
     int          tail_cur = 0;
     float       *d_dring = nullptr;
+    uint32_t    *d_hring = nullptr;      // hard decisions (d >= 0), 1 bit per demod sample, same ring indexing
     uint32_t     dmask = 0;
     float2      *d_ydump = nullptr;
     size_t       ydump_cap = 0;          // complex samples
     uint64_t     ydump_first = 0, ydump_count = 0;
     RxState     *d_state = nullptr;
     Candidate   *d_cand = nullptr;
-    amps_burst  *d_scratch = nullptr;    // record assembly area (kMaxAccept entries)
+    Accepted    *d_acc = nullptr;        // bursts accepted by the last select (kMaxAccept entries)
     amps_burst  *h_ring = nullptr;       // mapped pinned host ring the select kernel publishes into
     RxPublished *h_pub = nullptr;        // mapped pinned counters
     uint64_t     consumed = 0;           // bursts already handed to the caller
     uint64_t     lost = 0;               // bursts overwritten in the ring before they were collected
     cudaStream_t last_stream = nullptr;
+    cudaStream_t side = nullptr;         // detect / select / capture run here, overlapped with the next front kernel
+    cudaEvent_t  ev_front = nullptr;     // front kernel of the current call finished
+    cudaEvent_t  ev_side[2] = {nullptr, nullptr};   // detection of call k finished (k & 1)
+    uint64_t     call_no = 0;
+    bool         serial = false;         // AMPS_RX_SERIAL=1: no overlap (profiling / A-B measurements)
 
     size_t       carry = 0;              // unprocessed samples sitting at the front of d_stage
     uint64_t     samples_in = 0;         // samples handed to the kernels
@@ -51,9 +58,10 @@ struct amps_recc_iq {
 };
 
 static int rx_alloc(amps_recc_iq *h) {
-    const size_t max_d = (size_t)h->max_samples / (kD1 * kD2) + kTB;
+    const size_t max_d = (size_t)h->max_samples / (kD1 * kD2) + kPassOut;
     size_t cap = 1;
-    while (cap < max_d + (size_t)kSpan + 4096) cap <<= 1;
+    // two calls' worth: the detection of call k overlaps the front kernel of call k+1
+    while (cap < 2 * max_d + (size_t)kSpan + 4096) cap <<= 1;
     h->dmask = (uint32_t)(cap - 1);
     CK(cudaMalloc(&h->d_stage, ((size_t)h->max_samples + kPass) * sizeof(float2)));
     for (int i = 0; i < 2; ++i) {
@@ -62,6 +70,8 @@ static int rx_alloc(amps_recc_iq *h) {
     }
     CK(cudaMalloc(&h->d_dring, cap * sizeof(float)));
     CK(cudaMemset(h->d_dring, 0, cap * sizeof(float)));
+    CK(cudaMalloc(&h->d_hring, cap / 8));
+    CK(cudaMemset(h->d_hring, 0, cap / 8));
     if (h->flags & AMPS_RX_DUMP_BASEBAND) {
         h->ydump_cap = max_d;
         CK(cudaMalloc(&h->d_ydump, h->ydump_cap * sizeof(float2)));
@@ -69,11 +79,14 @@ static int rx_alloc(amps_recc_iq *h) {
     CK(cudaMalloc(&h->d_state, sizeof(RxState)));
     CK(cudaMemset(h->d_state, 0, sizeof(RxState)));
     CK(cudaMalloc(&h->d_cand, sizeof(Candidate) * kMaxCand));
-    CK(cudaMalloc(&h->d_scratch, sizeof(amps_burst) * kMaxAccept));
+    CK(cudaMalloc(&h->d_acc, sizeof(Accepted) * kMaxAccept));
     CK(cudaHostAlloc(&h->h_ring, sizeof(amps_burst) * h->max_records, cudaHostAllocMapped));
     CK(cudaHostAlloc(&h->h_pub, sizeof(RxPublished), cudaHostAllocMapped));
     std::memset(h->h_pub, 0, sizeof(RxPublished));
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_front, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) CK(cudaEventCreateWithFlags(&h->ev_side[i], cudaEventDisableTiming));
     if (h->flags & AMPS_RX_TIME_KERNELS)
         for (int i = 0; i < amps_recc_iq::kEv; ++i) { CK(cudaEventCreate(&h->ev0[i])); CK(cudaEventCreate(&h->ev1[i])); }
     return AMPS_OK;
@@ -99,6 +112,7 @@ extern "C" int amps_recc_iq_create(const amps_recc_iq_params *params, amps_recc_
     h->max_samples = (uint32_t)(((uint64_t)params->max_samples + kPass - 1) / kPass * kPass);
     h->max_records = params->max_bursts ? params->max_bursts : 256;
     h->flags = params->flags;
+    { const char *e = std::getenv("AMPS_RX_SERIAL"); h->serial = e && e[0] == '1'; }
     if (params->lpf_taps) h->lpf.assign(params->lpf_taps, params->lpf_taps + params->n_lpf_taps);
     else h->lpf = firdes_low_pass(3.0, 400e3, 10e3, 4500.0, WIN_BLACKMAN);     // grc/ampsbs.grc:138-184
     h->fcw = nco_fcw(params->center_freq, params->samp_rate);
@@ -124,9 +138,12 @@ extern "C" int amps_recc_iq_destroy(amps_recc_iq *h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->side) cudaStreamDestroy(h->side);
+    if (h->ev_front) cudaEventDestroy(h->ev_front);
+    for (int i = 0; i < 2; ++i) if (h->ev_side[i]) cudaEventDestroy(h->ev_side[i]);
     for (int i = 0; i < amps_recc_iq::kEv; ++i) { if (h->ev0[i]) cudaEventDestroy(h->ev0[i]); if (h->ev1[i]) cudaEventDestroy(h->ev1[i]); }
-    cudaFree(h->d_stage); cudaFree(h->d_tail[0]); cudaFree(h->d_tail[1]); cudaFree(h->d_dring);
-    cudaFree(h->d_ydump); cudaFree(h->d_state); cudaFree(h->d_cand); cudaFree(h->d_scratch);
+    cudaFree(h->d_stage); cudaFree(h->d_tail[0]); cudaFree(h->d_tail[1]); cudaFree(h->d_dring); cudaFree(h->d_hring);
+    cudaFree(h->d_ydump); cudaFree(h->d_state); cudaFree(h->d_cand); cudaFree(h->d_acc);
     if (h->h_ring) cudaFreeHost(h->h_ring);
     if (h->h_pub) cudaFreeHost(h->h_pub);
     delete h;
@@ -141,7 +158,7 @@ extern "C" int amps_recc_iq_reset(amps_recc_iq *h) {
     CK(cudaMemset(h->d_state, 0, sizeof(RxState)));
     CK(cudaMemset(h->d_dring, 0, ((size_t)h->dmask + 1) * sizeof(float)));
     std::memset(h->h_pub, 0, sizeof(RxPublished));
-    h->consumed = 0;
+    h->consumed = 0; h->call_no = 0;
     h->tail_cur = 0; h->carry = 0; h->samples_in = 0; h->total_d = 0; h->scan_hi = 0;
     h->ydump_first = 0; h->ydump_count = 0;
     return AMPS_OK;
@@ -155,13 +172,18 @@ static int rx_enqueue(amps_recc_iq *h, const float2 *d_chunk, uint32_t npass, cu
     p.chunk = d_chunk;
     p.tail = h->d_tail[h->tail_cur];
     p.dring = h->d_dring;
+    p.hring = h->d_hring;
     p.dmask = h->dmask;
     p.q_base = h->total_d;
     p.npass = npass;
     p.blk_base = (uint32_t)(h->samples_in / kD1);
     p.ydump = h->d_ydump;
-    int grid = 2 * h->sm_count;
-    if ((uint32_t)grid > npass) grid = (int)npass;
+    // whole passes per CTA, grid sized so that (nearly) every CTA gets the same count within one wave
+    p.pass_per_cta = (npass + 2u * (uint32_t)h->sm_count - 1u) / (2u * (uint32_t)h->sm_count);
+    const int grid = (int)((npass + p.pass_per_cta - 1u) / p.pass_per_cta);
+    // the demod ring holds two calls: do not overwrite what the detection of call k-2 may still read
+    const int par = (int)(h->call_no & 1u);
+    if (h->call_no >= 2) CK(cudaStreamWaitEvent(st, h->ev_side[par], 0));
     const bool timed = (h->flags & AMPS_RX_TIME_KERNELS) != 0;
     const int  evi = (int)(h->ev_count % amps_recc_iq::kEv);
     if (timed) CK(cudaEventRecord(h->ev0[evi], st));
@@ -169,25 +191,33 @@ static int rx_enqueue(amps_recc_iq *h, const float2 *d_chunk, uint32_t npass, cu
     if (timed) { CK(cudaEventRecord(h->ev1[evi], st)); h->ev_count++; }
     h->launches++;
     // history for the next call = the last pass of this one
-    CK(cudaMemcpyAsync(h->d_tail[h->tail_cur ^ 1], d_chunk + (size_t)(npass - 1) * kPass, (size_t)kHist * sizeof(float2),
+    CK(cudaMemcpyAsync(h->d_tail[h->tail_cur ^ 1], d_chunk + ((size_t)npass * kPass - kHist), (size_t)kHist * sizeof(float2),
                        cudaMemcpyDeviceToDevice, st));
     h->tail_cur ^= 1;
     h->ydump_first = h->total_d;
-    h->ydump_count = (uint64_t)npass * kTB;
+    h->ydump_count = (uint64_t)npass * kPassOut;
     h->samples_in += (uint64_t)npass * kPass;
-    h->total_d += (uint64_t)npass * kTB;
-    // search every position whose capture is complete
+    h->total_d += (uint64_t)npass * kPassOut;
+    // search every position whose capture is complete -- on the side stream, so that the next call's
+    // front kernel (HBM-bound, 2 CTAs/SM) overlaps these small latency-bound kernels
+    CK(cudaEventRecord(h->ev_front, st));
+    cudaStream_t sd = h->serial ? st : h->side;
+    if (!h->serial) CK(cudaStreamWaitEvent(sd, h->ev_front, 0));
     if (h->total_d > (uint64_t)kSpan) {
         const uint64_t hi = h->total_d - (uint64_t)kSpan;
         const uint64_t lo = h->scan_hi > 64 ? h->scan_hi - 64 : 0;
         if (hi > h->scan_hi) {
-            CKL(launch_rx_detect(h->d_dring, h->dmask, h->d_state, h->d_cand, lo, hi, st));
-            CKL(launch_rx_select(h->d_dring, h->dmask, h->d_state, h->d_cand, hi, h->d_scratch, h->h_ring, h->max_records,
-                                 h->h_pub, st));
-            h->launches += 2;
+            CKL(launch_rx_detect(h->d_dring, h->d_hring, h->dmask, h->d_state, h->d_cand, lo, hi, sd));
+            CKL(launch_rx_select(h->d_state, h->d_cand, h->d_acc, hi, h->h_pub, sd));
+            // at most one burst per kBurstLen searched positions (+1 for a run deferred from the last call)
+            const int max_new = (int)((hi - lo) / (uint64_t)kBurstLen) + 2;
+            CKL(launch_rx_capture(h->d_dring, h->dmask, h->d_state, h->d_acc, max_new, h->h_ring, h->max_records, h->h_pub, sd));
+            h->launches += 3;
             h->scan_hi = hi;
         }
     }
+    CK(cudaEventRecord(h->ev_side[par], sd));
+    h->call_no++;
     h->last_stream = st;
     return AMPS_OK;
 }
@@ -206,6 +236,7 @@ extern "C" int amps_recc_iq_submit_dev(amps_recc_iq *h, const void *d_iq, size_t
 // Wait for the stream; afterwards records [h->consumed, h->consumed + *n_out) sit in the host ring.
 static int rx_fetch(amps_recc_iq *h, uint64_t *n_out) {
     *n_out = 0;
+    CK(cudaStreamSynchronize(h->side));
     CK(cudaStreamSynchronize(h->last_stream));
     if (h->h_pub->cand_overflow)
         return set_error(AMPS_E_OVERFLOW, "trigger candidate list overflowed (more than 8192 matches in one call)");

@@ -23,34 +23,51 @@ static_assert(sizeof(amps_burst) % 8 == 0, "burst records are streamed to the ho
 // ============================================================================================
 // front end
 // ============================================================================================
+// 400 kS/s samples are kept as PAIRS (v[2P], v[2P+1]) = one float4, de-interleaved over kR rows by
+// P mod kR: a thread that produces outputs R*c .. R*c+R-1 then walks pairs whose row is a
+// compile-time constant and whose column is c + const, so consecutive lanes read consecutive
+// 16-byte slots (conflict-free LDS.128) and every load feeds up to 2*kR FFMA2.
 struct FrontSmem {
     float2   in[kStages][kTile];          // TMA landing ring
-    float2   v[kPorch + kVRing];          // 400 kS/s samples: porch mirrors the ring tail
+    float4   v[kR][kRowLen];              // row r, column c (c >= -kPorchCols) at v[r][c + kPorchCols]
     float2   pb[2][2][kTB];               // [tile parity][P1|P2][block] rotated CIC partial sums
-    float2   y[2][kTB + 1];               // [pass parity][1 + thread] 200 kS/s baseband
+    float2   ylast[kTB];                  // each thread's last output of the current pass
+    float2   ycarry[2];                   // last output of a pass, by pass parity
     uint64_t full[kStages];
 };
 
 size_t rx_front_smem_bytes() { return sizeof(FrontSmem); }
 
 __device__ __forceinline__ void issue_tile(const RxFrontParams &p, FrontSmem *sm, long tile, int stage) {
-    // tiles with a negative index come from the history buffer (one pass = 2 tiles long)
+    // tiles with a negative index come from the history buffer (kWarmTiles tiles long)
     const float2 *src = tile < 0 ? p.tail + (long)kHist + tile * (long)kTile : p.chunk + tile * (long)kTile;
     mbar_expect_tx(&sm->full[stage], kTile * (uint32_t)sizeof(float2));
     tma_load_1d(sm->in[stage], src, kTile * (uint32_t)sizeof(float2), &sm->full[stage]);
 }
 
-// y[q] = sum_k h2[k] v[2q-k] as two interleaved FFMA2 chains (even taps, odd taps), k ascending.
-// vq points at v[2q]; pairs (v[2q-2j], v[2q-2j+1]) are fetched with one 128-bit shared load.
-__device__ __forceinline__ float2 channel_filter(const RxFrontParams &p, const float2 *vq) {
-    float2 E = make_float2(0.f, 0.f), O = make_float2(0.f, 0.f);
+__host__ __device__ constexpr int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+// y[q] = sum_k h2[k] v[2q-k] for the kR outputs q = kR*c0 + r, each as two FFMA2 chains (even taps,
+// odd taps), k ascending -- the order the oracle uses.  vcol points at column c0 of row 0.
+__device__ __forceinline__ void channel_filter(const RxFrontParams &p, const float4 *vcol, float2 (&y)[kR]) {
+    float2 E[kR], O[kR];
 #pragma unroll
-    for (int j = 0; j < 150; ++j) {
-        float4 pr = *reinterpret_cast<const float4 *>(vq - 2 * j);
-        E = fma2(splat(p.h2[2 * j]), make_float2(pr.x, pr.y), E);
-        if (j >= 1) O = fma2(splat(p.h2[2 * j - 1]), make_float2(pr.z, pr.w), O);
+    for (int r = 0; r < kR; ++r) { E[r] = make_float2(0.f, 0.f); O[r] = make_float2(0.f, 0.f); }
+#pragma unroll
+    for (int s = 0; s < 150 + kR - 1; ++s) {
+        // pair P = kR*c0 + (kR-1) - s : row and column offset are compile-time
+        const int row = (kR - 1 - s) & (kR - 1);
+        const int cs  = floor_div(kR - 1 - s, kR);
+        const float4 pr = vcol[row * kRowLen + cs];
+#pragma unroll
+        for (int r = 0; r < kR; ++r) {
+            const int j = r - (kR - 1) + s;           // tap pair index for output r
+            if (j >= 0 && j <= 149) E[r] = fma2(splat(p.h2[2 * j]), make_float2(pr.x, pr.y), E[r]);
+            if (j >= 1 && j <= 149) O[r] = fma2(splat(p.h2[2 * j - 1]), make_float2(pr.z, pr.w), O[r]);
+        }
     }
-    return add2(E, O);
+#pragma unroll
+    for (int r = 0; r < kR; ++r) y[r] = add2(E[r], O[r]);
 }
 
 __global__ void __launch_bounds__(kTB, 2) rx_front_kernel(const __grid_constant__ RxFrontParams p) {
@@ -58,25 +75,24 @@ __global__ void __launch_bounds__(kTB, 2) rx_front_kernel(const __grid_constant_
     FrontSmem *sm = reinterpret_cast<FrontSmem *>(smem_raw);
     const int t = threadIdx.x;
 
-    const uint32_t pa = (uint32_t)(((uint64_t)p.npass * blockIdx.x) / gridDim.x);
-    const uint32_t pb = (uint32_t)(((uint64_t)p.npass * (blockIdx.x + 1)) / gridDim.x);
-    if (pa == pb) return;
-    const int  ntiles = 2 * (int)(pb - pa) + 2;          // one warm-up pass + the CTA's own passes
-    const long tile0  = 2 * (long)pa - 2;
+    uint32_t pa = blockIdx.x * p.pass_per_cta;
+    if (pa >= p.npass) return;
+    uint32_t pb = pa + p.pass_per_cta;
+    if (pb > p.npass) pb = p.npass;
+    const int  ntiles = kPassTiles * (int)(pb - pa) + kWarmTiles;     // warm-up tiles + the CTA's own passes
+    const long tile0  = (long)kPassTiles * pa - kWarmTiles;
 
     if (t == 0) {
         for (int s = 0; s < kStages; ++s) mbar_init(&sm->full[s], 1);
         mbar_fence_init();
     }
-    // partial sums "before the first tile": only ever feed warm-up outputs that are discarded
+    // partial sums "before the first tile": they only reach samples the warm-up never uses
     sm->pb[1][0][t] = make_float2(0.f, 0.f);
     sm->pb[1][1][t] = make_float2(0.f, 0.f);
     __syncthreads();
     if (t == 0) {
         for (int s = 0; s < kStages && s < ntiles; ++s) issue_tile(p, sm, tile0 + s, s);
     }
-
-    float2 *vorg = sm->v + kPorch;
 
     for (int i = 0; i < ntiles; ++i) {
         const int s = i % kStages;
@@ -104,38 +120,68 @@ __global__ void __launch_bounds__(kTB, 2) rx_front_kernel(const __grid_constant_
         __syncthreads();                                   // partials visible; in[s] fully consumed
         if (t == 0 && i + kStages < ntiles) issue_tile(p, sm, tile0 + i + kStages, s);
 
-        // ---- v[m] = (P0[m] + P1[m-1]) + P2[m-2]
+        // ---- v[m] = (P0[m] + P1[m-1]) + P2[m-2], stored into the pair/row layout
         const float2 q1 = t >= 1 ? sm->pb[par][0][t - 1] : sm->pb[par ^ 1][0][kTB - 1];
         const float2 q2 = t >= 2 ? sm->pb[par][1][t - 2] : sm->pb[par ^ 1][1][kTB - 2 + t];
         const float2 v  = add2(add2(P0, q1), q2);
-        const int base = ((i >> 1) & 1) * 2 * kTB;
-        const int r    = base + (i & 1) * kTB + t;
-        vorg[r] = v;
-        if (r >= kVRing - kPorch) vorg[r - kVRing] = v;
+        const bool warm = i < kWarmTiles;
+        const int  u    = warm ? 0 : (i - kWarmTiles) % kPassTiles;          // tile index inside the pass
+        const int  mrel = warm ? (i - kWarmTiles) * kTB + t : u * kTB + t;   // 400 kS/s index relative to the pass start
+        const int  P    = mrel >> 1;                                         // pair index (floor)
+        const int  col  = P >> kLogR;
+        if (col >= -kPorchCols)
+            reinterpret_cast<float2 *>(&sm->v[P & (kR - 1)][col + kPorchCols])[mrel & 1] = v;
 
-        if (i & 1) {
-            // End of a pass.  The warm-up pass (i == 1) only produces y[q0-1], the predecessor the
+        const bool pass_end = !warm && u == kPassTiles - 1;
+        if (pass_end || i == kWarmTiles - 1) {
+            // End of a pass.  The end of the warm-up only produces y[q0-1], the predecessor the
             // quadrature demod of the CTA's first real output needs; nothing is written for it.
-            const bool warm = (i == 1);
-            __syncthreads();                               // the pass's 2*TB new v samples are in place
-            // ---- stage 2: 299-tap channel filter /2, one output per thread
-            const int yb = (i >> 1) & 1;
-            float2 y = make_float2(0.f, 0.f);
-            if (!warm || t == kTB - 1) {
-                y = channel_filter(p, vorg + base + 2 * t);
-                sm->y[yb][t + 1] = y;
+            const int pc = warm ? -1 : (i - kWarmTiles) / kPassTiles;        // CTA-local pass counter
+            __syncthreads();                               // the pass's new v samples are in place
+            // ---- stage 2: 299-tap channel filter /2, kR outputs per thread
+            float2 y[kR];
+#pragma unroll
+            for (int r = 0; r < kR; ++r) y[r] = make_float2(0.f, 0.f);
+            if (!warm || t == 0) {
+                const int c0 = warm ? -1 : t;
+                channel_filter(p, &sm->v[0][c0 + kPorchCols], y);
+                if (!warm) sm->ylast[t] = y[kR - 1];
+                if (warm || t == kTB - 1) sm->ycarry[pc & 1] = y[kR - 1];
             }
             __syncthreads();
             if (!warm) {
+                // the last kPorchCols columns become the history of the next pass
+                if (t < kR * kPorchCols) {
+                    const int r = t / kPorchCols, c = t % kPorchCols;
+                    sm->v[r][c] = sm->v[r][kTB + c];
+                }
                 // ---- quadrature demod: arg(y[q] * conj(y[q-1]))
-                const float2 yp = t == 0 ? sm->y[yb ^ 1][kTB] : sm->y[yb][t];
-                const float zr = __fmaf_rn(y.y, yp.y, __fmul_rn(y.x, yp.x));
-                const float zi = __fmaf_rn(y.y, yp.x, -__fmul_rn(y.x, yp.y));
-                const float d  = atan2_spec(zi, zr);
-                const uint32_t    lp = pa + (uint32_t)(i >> 1) - 1u;          // pass index within this call
-                const unsigned long long ql = (unsigned long long)lp * kTB + t;
-                p.dring[(p.q_base + ql) & p.dmask] = d;
-                if (p.ydump) p.ydump[ql] = y;
+                float2 yp = t == 0 ? sm->ycarry[(pc + 1) & 1] : sm->ylast[t - 1];
+                float d[kR];
+#pragma unroll
+                for (int r = 0; r < kR; ++r) {
+                    const float zr = __fmaf_rn(y[r].y, yp.y, __fmul_rn(y[r].x, yp.x));
+                    const float zi = __fmaf_rn(y[r].y, yp.x, -__fmul_rn(y[r].x, yp.y));
+                    d[r] = atan2_spec(zi, zr);
+                    yp = y[r];
+                }
+                const unsigned long long ql = (unsigned long long)(pa + (uint32_t)pc) * kPassOut + (unsigned long long)kR * t;
+                const unsigned long long qabs = p.q_base + ql;
+                float4 *dst = reinterpret_cast<float4 *>(&p.dring[qabs & p.dmask]);
+                *dst = make_float4(d[0], d[1], d[2], d[3]);
+                // hard decisions (binary_slicer_fb: x >= 0 -> 1), 32 per word: 8 lanes x 4 outputs
+                unsigned int hb = 0;
+#pragma unroll
+                for (int r = 0; r < kR; ++r) hb |= (d[r] >= 0.0f ? 1u : 0u) << r;
+                hb <<= 4 * (t & 7);
+                hb |= __shfl_xor_sync(0xffffffffu, hb, 1);
+                hb |= __shfl_xor_sync(0xffffffffu, hb, 2);
+                hb |= __shfl_xor_sync(0xffffffffu, hb, 4);
+                if ((t & 7) == 0) p.hring[(qabs & p.dmask) >> 5] = hb;
+                if (p.ydump) {
+#pragma unroll
+                    for (int r = 0; r < kR; ++r) p.ydump[ql + r] = y[r];
+                }
             }
         }
     }
@@ -155,38 +201,88 @@ __device__ __constant__ uint8_t c_trig[kTrig] = {
     0,1,1,0,0,1,1,0,0,1,1,0,0,1,1,0,0,1,1,0,0,1,1,0,0,1,1,0,0,1,1,0,0,1,1,0,0,1,1,0,0,1,1,0,0,1,1,0,0,1,1,0,
     0,1,0,1,0,1,1,0,1,0,1,0,0,1,1,0,1,0,0,1,1,0};
 
-__global__ void __launch_bounds__(256) rx_detect_kernel(const float *__restrict__ dring, uint32_t dmask, RxState *state,
-                                                       Candidate *cand, unsigned long long scan_lo, unsigned long long scan_hi) {
-    const unsigned long long i = scan_lo + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= scan_hi) return;
-    if (i < state->lo || i < state->resume_at) return;
-    // early-out hard match: after k compares a random position survives with probability 2^-k
+// 74-symbol trigger packed LSB-first (symbol k = bit k)
+__device__ __constant__ uint32_t c_trig_bits[3] = {0x66666666u, 0x56A66666u, 0x00000196u};
+
+// Exact 74/74 hard match for the 32 adjacent sampling positions i0 .. i0+31 (i0 a multiple of 32):
+// for half-symbol k the 32 hard decisions at positions i0+10k .. i0+10k+31 are one 32-bit window of
+// the bit ring, so one AND per symbol tests all 32 positions; a random group dies after ~6 symbols.
+__device__ __forceinline__ uint32_t group_match(const uint32_t *__restrict__ hring, uint32_t wmask, unsigned long long i0) {
+    uint32_t m = 0xffffffffu;
 #pragma unroll 1
-    for (int k = 0; k < kTrig; ++k) {
-        const float v = dring[(i + (unsigned long long)(kOS * k)) & dmask];
-        if ((v >= 0.0f) != (c_trig[k] != 0)) return;
+    for (int k = 0; k < kTrig && m; ++k) {
+        const unsigned long long b = i0 + (unsigned long long)(kOS * k);
+        const uint32_t wi = (uint32_t)(b >> 5);
+        const uint32_t w0 = hring[wi & wmask], w1 = hring[(wi + 1) & wmask];
+        const uint32_t win = __funnelshift_r(w0, w1, (uint32_t)b & 31u);
+        m &= ((c_trig_bits[k >> 5] >> (k & 31)) & 1u) ? win : ~win;
     }
+    return m;
+}
+
+// soft correlation of the trigger at sampling position i: sum_k (+/-) d[i + 10k], k ascending
+__device__ __forceinline__ float trig_corr(const float *__restrict__ dring, uint32_t dmask, unsigned long long i) {
+    float v[kTrig];
+#pragma unroll
+    for (int k = 0; k < kTrig; ++k) v[k] = dring[(i + (unsigned long long)(kOS * k)) & dmask];
     float c = 0.0f;
-#pragma unroll 1
-    for (int k = 0; k < kTrig; ++k) {
-        const float v = dring[(i + (unsigned long long)(kOS * k)) & dmask];
-        c = __fadd_rn(c, c_trig[k] ? v : -v);
-    }
-    const unsigned int slot = atomicAdd(&state->ncand, 1u);
-    if (slot < (unsigned)kMaxCand) {
-        cand[slot].pos = i;
-        cand[slot].corr = c;
-    } else {
-        atomicAdd(&state->cand_overflow, 1u);
+#pragma unroll
+    for (int k = 0; k < kTrig; ++k) c = __fadd_rn(c, c_trig[k] ? v[k] : -v[k]);
+    return c;
+}
+
+// One thread per group of 32 sampling positions.  The thread owning the FIRST position of a run of
+// matches (at most 10 long: the pattern cannot match one half-symbol later) emits one candidate for
+// the whole run: its soft-correlation peak (first maximum) is the sampling phase.
+__global__ void __launch_bounds__(256) rx_detect_kernel(const float *__restrict__ dring, const uint32_t *__restrict__ hring,
+                                                       uint32_t dmask, RxState *state, Candidate *cand,
+                                                       unsigned long long scan_lo, unsigned long long scan_hi) {
+    const unsigned long long i0 = (scan_lo & ~31ull) + 32ull * ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x);
+    if (i0 >= scan_hi) return;
+    const uint32_t wmask = dmask >> 5;
+    const uint32_t m0 = group_match(hring, wmask, i0);
+    if (!m0) return;
+    // rare path: neighbours' match bits decide where runs start and end
+    const uint32_t mprev = i0 >= 32 ? group_match(hring, wmask, i0 - 32) : 0u;
+    const uint32_t mnext = group_match(hring, wmask, i0 + 32);
+    const unsigned long long M = (unsigned long long)m0 | ((unsigned long long)mnext << 32);
+    uint32_t starts = m0 & ~((m0 << 1) | (mprev >> 31));
+    const unsigned long long lo = state->lo > scan_lo ? state->lo : scan_lo;
+    while (starts) {
+        const int bit = __ffs(starts) - 1;
+        starts &= starts - 1;
+        const unsigned long long i = i0 + (unsigned long long)bit;
+        if (i < lo || i >= scan_hi) continue;
+        unsigned long long best = i;
+        float bestc = trig_corr(dring, dmask, i);
+        unsigned int run = 1;
+        bool open = false;
+        for (;;) {
+            const unsigned long long j = i + run;
+            if (j >= scan_hi) { open = true; break; }                 // the run may go on in data not searched yet
+            if (!((M >> (bit + run)) & 1ull)) break;
+            const float c = trig_corr(dring, dmask, j);
+            if (c > bestc) { bestc = c; best = j; }
+            ++run;
+        }
+        const unsigned int slot = atomicAdd(&state->ncand, 1u);
+        if (slot < (unsigned)kMaxCand) {
+            cand[slot].start = i;
+            cand[slot].best = best;
+            cand[slot].corr = bestc;
+            cand[slot].run = run | (open ? 0x80000000u : 0u);
+        } else {
+            atomicAdd(&state->cand_overflow, 1u);
+        }
     }
 }
 
-cudaError_t launch_rx_detect(const float *dring, uint32_t dmask, RxState *state, Candidate *cand,
+cudaError_t launch_rx_detect(const float *dring, const uint32_t *hring, uint32_t dmask, RxState *state, Candidate *cand,
                              unsigned long long scan_lo, unsigned long long scan_hi, cudaStream_t st) {
     if (scan_hi <= scan_lo) return cudaSuccess;
-    unsigned long long n = scan_hi - scan_lo;
-    unsigned int grid = (unsigned int)((n + 255) / 256);
-    rx_detect_kernel<<<grid, 256, 0, st>>>(dring, dmask, state, cand, scan_lo, scan_hi);
+    const unsigned long long groups = (scan_hi - (scan_lo & ~31ull) + 31ull) / 32ull;
+    const unsigned int grid = (unsigned int)((groups + 255) / 256);
+    rx_detect_kernel<<<grid, 256, 0, st>>>(dring, hring, dmask, state, cand, scan_lo, scan_hi);
     return cudaGetLastError();
 }
 
@@ -214,34 +310,36 @@ static constexpr Gf64 make_gf() {
 }
 __device__ __constant__ Gf64 c_gf = make_gf();
 
-__device__ __forceinline__ unsigned gf_mul(unsigned a, unsigned b) {
-    return (a && b) ? c_gf.exp[c_gf.log[a] + c_gf.log[b]] : 0u;
+// The tables are copied to shared memory by the decode routine: lanes index them with different
+// values, which the constant cache would serialise.
+__device__ __forceinline__ unsigned gf_mul(const Gf64 &gf, unsigned a, unsigned b) {
+    return (a && b) ? gf.exp[gf.log[a] + gf.log[b]] : 0u;
 }
 
 // Validity of one 48-bit RECC word repeat as itpp::BCH(63,2,true)::decode reports it for
 // (15 zeros || 48 bits) (lib/recc_decode_impl.cc:53-79): <=2 errors anywhere in the 63 bits, plus
 // the S1 == 0, S3 a non-zero cube case that Berlekamp's 2-step iteration turns into a degree-3
 // locator with three roots.
-__device__ bool bch48_valid(const uint8_t *bits48) {
+__device__ bool bch48_valid(const Gf64 &gf, const uint8_t *bits48) {
     unsigned s1 = 0, s3 = 0;
     for (int b = 0; b < 48; ++b) {
         if (bits48[b] & 1u) {
             const int e = 47 - b;                       // exponent of x carried by this bit
-            s1 ^= c_gf.exp[e];
-            s3 ^= c_gf.exp[(3 * e) % 63];
+            s1 ^= gf.exp[e];
+            s3 ^= gf.exp[(3 * e) % 63];
         }
     }
-    if (s1 == 0) return s3 == 0 || (c_gf.log[s3] % 3u) == 0;
-    const unsigned s1c = gf_mul(gf_mul(s1, s1), s1);
+    if (s1 == 0) return s3 == 0 || (gf.log[s3] % 3u) == 0;
+    const unsigned s1c = gf_mul(gf, gf_mul(gf, s1, s1), s1);
     if (s3 == s1c) return true;                         // single error
     // Lambda(x) = 1 + s1 x + ((s3 + s1^3)/s1) x^2 must have two roots among alpha^0..alpha^62
     const unsigned num = s3 ^ s1c;
-    const unsigned c2  = c_gf.exp[c_gf.log[num] + 63 - c_gf.log[s1]];
+    const unsigned c2  = gf.exp[gf.log[num] + 63 - gf.log[s1]];
     int roots = 0;
     for (int j = 0; j < 63; ++j) {
-        const unsigned x  = c_gf.exp[j];
-        const unsigned x2 = c_gf.exp[(2 * j) % 63];
-        if ((1u ^ gf_mul(s1, x) ^ gf_mul(c2, x2)) == 0u) ++roots;
+        const unsigned x  = gf.exp[j];
+        const unsigned x2 = gf.exp[(2 * j) % 63];
+        if ((1u ^ gf_mul(gf, s1, x) ^ gf_mul(gf, c2, x2)) == 0u) ++roots;
     }
     return roots == 2;
 }
@@ -270,7 +368,9 @@ __device__ void extract_min_3(unsigned val, char *out3) {
 // `scratch` is shared memory: 7*5 validity bytes.
 __device__ void decode_burst_block(const uint8_t *symbols, amps_recc_words *out, uint8_t *scratch_valid,
                                    unsigned int *scratch_errs) {
+    __shared__ Gf64 gf;
     const int t = threadIdx.x, nt = blockDim.x;
+    for (int i = t; i < (int)sizeof(Gf64); i += nt) reinterpret_cast<uint8_t *>(&gf)[i] = reinterpret_cast<const uint8_t *>(&c_gf)[i];
     if (t < 8) scratch_errs[t] = 0;
     __syncthreads();
     // Manchester pairs: (1,0)->0 (0,1)->1 (1,1)->0+err (0,0)->1+err   (lib/utils.cc:36-50)
@@ -284,7 +384,7 @@ __device__ void decode_burst_block(const uint8_t *symbols, amps_recc_words *out,
         if (a == b) atomicAdd(&scratch_errs[w], 1u);
     }
     __syncthreads();
-    if (t < 35) scratch_valid[t] = bch48_valid(&out->words[t / 5][48 * (t % 5)]) ? 1 : 0;
+    if (t < 35) scratch_valid[t] = bch48_valid(gf, &out->words[t / 5][48 * (t % 5)]) ? 1 : 0;
     __syncthreads();
     if (t == 0) {
         out->dcc_errs = (uint8_t)scratch_errs[7];
@@ -365,118 +465,112 @@ cudaError_t launch_decode_blobs(const uint8_t *blobs, int nbursts, amps_recc_wor
 }
 
 // ============================================================================================
-// candidate selection + capture + decode (single CTA; candidates are rare)
+// candidate selection (single CTA; candidates are rare) and burst capture (one CTA per burst)
 // ============================================================================================
-__global__ void __launch_bounds__(256) rx_select_kernel(const float *__restrict__ dring, uint32_t dmask, RxState *state,
-                                                       Candidate *cand, unsigned long long scan_hi, amps_burst *scratch,
-                                                       amps_burst *host_ring, unsigned int ring_len, RxPublished *host_pub) {
+__global__ void __launch_bounds__(256) rx_select_kernel(RxState *state, Candidate *cand, Accepted *acc,
+                                                       unsigned long long scan_hi, RxPublished *host_pub) {
     extern __shared__ unsigned char sel_raw[];
-    unsigned long long *keys = reinterpret_cast<unsigned long long *>(sel_raw);          // kMaxCand
-    float *corr = reinterpret_cast<float *>(keys + kMaxCand);                            // kMaxCand
-    __shared__ unsigned long long acc_pos[kMaxAccept];
-    __shared__ float acc_corr[kMaxAccept];
-    __shared__ unsigned int acc_run[kMaxAccept];
-    __shared__ unsigned int n_acc;
-    __shared__ uint8_t s_valid[40];
-    __shared__ unsigned int s_errs[8];
-    __shared__ unsigned long long rec_base;
-
+    Candidate *sorted = reinterpret_cast<Candidate *>(sel_raw);                          // kMaxCand
     const int t = threadIdx.x, nt = blockDim.x;
     unsigned int n = state->ncand;
     if (n > (unsigned)kMaxCand) n = kMaxCand;
-    // pad to a power of two and bitonic-sort by position (atomics made the order arbitrary)
-    unsigned int np = 1;
-    while (np < n) np <<= 1;
-    for (unsigned int i = t; i < np; i += nt) {
-        keys[i] = i < n ? cand[i].pos : ~0ull;
-        corr[i] = i < n ? cand[i].corr : 0.0f;
+    // rank sort by run start (the atomics made the order arbitrary; run starts are distinct)
+    for (unsigned int i = t; i < n; i += nt) {
+        const Candidate c = cand[i];
+        unsigned int rank = 0;
+        for (unsigned int j = 0; j < n; ++j) rank += cand[j].start < c.start ? 1u : 0u;
+        sorted[rank] = c;
     }
     __syncthreads();
-    for (unsigned int k = 2; k <= np; k <<= 1) {
-        for (unsigned int j = k >> 1; j > 0; j >>= 1) {
-            for (unsigned int i = t; i < np; i += nt) {
-                const unsigned int ixj = i ^ j;
-                if (ixj > i) {
-                    const bool up = (i & k) == 0;
-                    const unsigned long long a = keys[i], b = keys[ixj];
-                    if ((a > b) == up) {
-                        keys[i] = b; keys[ixj] = a;
-                        const float ca = corr[i]; corr[i] = corr[ixj]; corr[ixj] = ca;
-                    }
-                }
-            }
-            __syncthreads();
-        }
-    }
     if (t == 0) {
-        unsigned long long lo = state->lo, resume = state->resume_at;
+        const unsigned long long lo = state->lo;
+        unsigned long long resume = state->resume_at;
         unsigned long long new_lo = scan_hi > lo ? scan_hi : lo;
         unsigned int na = 0;
-        unsigned int i = 0;
-        while (i < n) {
-            if (keys[i] < lo || keys[i] < resume) { ++i; continue; }
-            // run of adjacent sampling phases that all matched
-            unsigned int j = i;
-            unsigned int best = i;
-            while (j + 1 < n && keys[j + 1] == keys[j] + 1) {
-                ++j;
-                if (corr[j] > corr[best]) best = j;
-            }
-            if (keys[j] + 1 >= scan_hi) {                  // run may continue past the searched range: decide next call
-                new_lo = keys[i];
+        for (unsigned int i = 0; i < n; ++i) {
+            const Candidate c = sorted[i];
+            if (c.start < lo) continue;                    // handled by an earlier call
+            if (c.run & 0x80000000u) {                     // run reaches the end of the searched range: decide next call
+                new_lo = c.start;
                 break;
             }
+            if (c.start < resume) continue;                // begins inside a burst that was already captured
             if (na < (unsigned)kMaxAccept) {
-                acc_pos[na] = keys[best];
-                acc_corr[na] = corr[best];
-                acc_run[na] = j - i + 1;
+                acc[na].pos = c.best;
+                acc[na].corr = c.corr;
+                acc[na].run = c.run;
                 ++na;
             }
-            resume = keys[best] + (unsigned long long)kBurstLen;
-            i = j + 1;
+            resume = c.best + (unsigned long long)kBurstLen;
         }
         state->lo = new_lo;
         state->resume_at = resume;
         state->ncand = 0;
-        n_acc = na;
-        rec_base = state->nrec_total;
-    }
-    __syncthreads();
-    for (unsigned int a = 0; a < n_acc; ++a) {
-        amps_burst *rec = &scratch[a];
-        const unsigned long long pos = acc_pos[a];
-        for (int s = t; s < kCapture; s += nt) {
-            const float v = dring[(pos + (unsigned long long)(kOS * (kTrig + s))) & dmask];
-            rec->symbols[s] = v >= 0.0f ? 1 : 0;
+        state->n_acc = na;
+        state->done = 0;
+        state->rec_base = state->nrec_total;
+        state->nrec_total += na;
+        if (na == 0) {                                    // nothing for the capture kernel to publish
+            __threadfence_system();
+            host_pub->cand_overflow = state->cand_overflow;
         }
-        if (t == 0) {
-            rec->demod_index = pos;
-            rec->sample_index = pos * (unsigned long long)(kD1 * kD2);
-            rec->corr = acc_corr[a];
-            rec->run_length = acc_run[a];
-            rec->pad[0] = 0; rec->pad[1] = 0;
-        }
-        __syncthreads();
-        decode_burst_block(rec->symbols, &rec->decoded, s_valid, s_errs);
-        // publish: stream the finished record into the host-visible ring (posted PCIe writes)
-        const unsigned long long *src = reinterpret_cast<const unsigned long long *>(rec);
-        unsigned long long *dst = reinterpret_cast<unsigned long long *>(&host_ring[(rec_base + a) % ring_len]);
-        for (int w = t; w < (int)(sizeof(amps_burst) / 8); w += nt) dst[w] = src[w];
-    }
-    __syncthreads();
-    if (t == 0) {
-        state->nrec_total = rec_base + n_acc;
-        __threadfence_system();
-        host_pub->cand_overflow = state->cand_overflow;
-        host_pub->nrec_total = rec_base + n_acc;
     }
 }
 
-cudaError_t launch_rx_select(const float *dring, uint32_t dmask, RxState *state, Candidate *cand,
-                             unsigned long long scan_hi, amps_burst *scratch, amps_burst *host_ring, unsigned int ring_len,
+cudaError_t launch_rx_select(RxState *state, Candidate *cand, Accepted *acc, unsigned long long scan_hi,
                              RxPublished *host_pub, cudaStream_t st) {
-    const size_t smem = (size_t)kMaxCand * (sizeof(unsigned long long) + sizeof(float));
-    rx_select_kernel<<<1, 256, smem, st>>>(dring, dmask, state, cand, scan_hi, scratch, host_ring, ring_len, host_pub);
+    const size_t smem = (size_t)kMaxCand * sizeof(Candidate);
+    rx_select_kernel<<<1, 256, smem, st>>>(state, cand, acc, scan_hi, host_pub);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) rx_capture_kernel(const float *__restrict__ dring, uint32_t dmask, RxState *state,
+                                                        const Accepted *acc, amps_burst *host_ring, unsigned int ring_len,
+                                                        RxPublished *host_pub) {
+    __shared__ __align__(16) unsigned char rec_raw[sizeof(amps_burst)];
+    __shared__ uint8_t s_valid[40];
+    __shared__ unsigned int s_errs[8];
+    const unsigned int n_acc = state->n_acc;
+    if (blockIdx.x >= n_acc) return;
+    const int t = threadIdx.x, nt = blockDim.x;
+    amps_burst *rec = reinterpret_cast<amps_burst *>(rec_raw);
+    const Accepted a = acc[blockIdx.x];
+    // the 3374 half-symbols after the trigger, sliced at the chosen sampling phase (recc_impl.cc:124-126)
+    for (int s = t; s < kCapture; s += nt) {
+        const float v = dring[(a.pos + (unsigned long long)(kOS * (kTrig + s))) & dmask];
+        rec->symbols[s] = v >= 0.0f ? 1 : 0;
+    }
+    if (t == 0) {
+        rec->demod_index = a.pos;
+        rec->sample_index = a.pos * (unsigned long long)(kD1 * kD2);
+        rec->corr = a.corr;
+        rec->run_length = a.run;
+        rec->pad[0] = 0; rec->pad[1] = 0;
+    }
+    __syncthreads();
+    decode_burst_block(rec->symbols, &rec->decoded, s_valid, s_errs);
+    // publish: stream the finished record into the host-visible ring (posted PCIe writes)
+    const unsigned long long rec_base = state->rec_base;
+    const unsigned long long *src = reinterpret_cast<const unsigned long long *>(rec);
+    unsigned long long *dst = reinterpret_cast<unsigned long long *>(&host_ring[(rec_base + blockIdx.x) % ring_len]);
+    for (int w = t; w < (int)(sizeof(amps_burst) / 8); w += nt) dst[w] = src[w];
+    __threadfence_system();
+    __syncthreads();
+    if (t == 0) {
+        const unsigned int prev = atomicAdd(&state->done, 1u);
+        if (prev + 1 == n_acc) {                          // last CTA: every record is on its way, publish the count
+            __threadfence_system();
+            host_pub->cand_overflow = state->cand_overflow;
+            host_pub->nrec_total = rec_base + n_acc;
+        }
+    }
+}
+
+cudaError_t launch_rx_capture(const float *dring, uint32_t dmask, RxState *state, const Accepted *acc, int grid,
+                              amps_burst *host_ring, unsigned int ring_len, RxPublished *host_pub, cudaStream_t st) {
+    if (grid <= 0) return cudaSuccess;
+    if (grid > kMaxAccept) grid = kMaxAccept;
+    rx_capture_kernel<<<grid, 256, 0, st>>>(dring, dmask, state, acc, host_ring, ring_len, host_pub);
     return cudaGetLastError();
 }
 
@@ -485,7 +579,7 @@ cudaError_t rx_configure_device() {
     cudaError_t e = cudaFuncSetAttribute(rx_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rx_front_smem_bytes());
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(rx_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)((size_t)kMaxCand * (sizeof(unsigned long long) + sizeof(float))));
+                                (int)((size_t)kMaxCand * sizeof(Candidate)));
 }
 
 }  // namespace amps

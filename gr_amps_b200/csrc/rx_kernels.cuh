@@ -5,24 +5,33 @@
 
 namespace amps {
 
-// Geometry of the front-end kernel.  One "pass" = kS2Tiles tiles = 2*TB blocks of 25 samples
-// -> TB demodulated outputs (one per thread).
-constexpr int kTB      = 192;              // threads per CTA == 25-sample blocks per tile
-constexpr int kStages  = 2;                // TMA ring depth
-constexpr int kTile    = kTB * kD1;        // 4800 input samples, 38400 bytes
-constexpr int kPass    = 2 * kTile;        // 9600 input samples per stage-2 pass
-constexpr int kHist    = kPass;            // input history carried between calls (one pass)
-constexpr int kPorch   = 304;              // v history mirrored in front of the ring
-constexpr int kVRing   = 4 * kTB;          // two passes of 400 kS/s samples
+// Geometry of the front-end kernel.
+//   tile  = kTB blocks of 25 samples, one block per thread (stage 1: NCO + CIC^3 /25);
+//   pass  = kPassTiles tiles -> 2*kR*kTB samples @400 kS/s -> kR*kTB demodulated outputs, kR per thread
+//           (stage 2: channel filter /2 with kR-fold register reuse of every shared-memory load).
+constexpr int kTB        = 192;              // threads per CTA == 25-sample blocks per tile
+constexpr int kStages    = 2;                // TMA ring depth
+constexpr int kR         = 4;                // outputs per thread per pass (power of two)
+constexpr int kLogR      = 2;
+constexpr int kTile      = kTB * kD1;        // 4800 input samples, 38400 bytes
+constexpr int kPassTiles = 2 * kR;
+constexpr int kPass      = kPassTiles * kTile;   // 38400 input samples per pass (API granularity)
+constexpr int kPassOut   = kR * kTB;         // 768 demodulated samples per pass
+constexpr int kWarmTiles = 2;                // history a CTA re-reads before its first pass (>= 306 blocks)
+constexpr int kHist      = kWarmTiles * kTile;   // input history carried between calls
+constexpr int kPorchCols = 40;               // columns of v history kept in front of each row (>= (150 + 2R)/R)
+constexpr int kRowLen    = kPorchCols + kTB + 2; // pairs per row (+2: rows land 32 B apart in bank space)
 
 struct RxFrontParams {
     const float2 *chunk;     // logical samples [0, npass*kPass)
     const float2 *tail;      // logical samples [-kHist, 0)
     float        *dring;     // demod ring, indexed by (absolute demod index & dmask)
-    float2       *ydump;     // optional: complex baseband of this call (npass*kTB entries) or nullptr
+    uint32_t     *hring;     // hard decisions d >= 0, bit (i & 31) of word ((i & dmask) >> 5)
+    float2       *ydump;     // optional: complex baseband of this call (npass*kPassOut entries) or nullptr
     uint64_t      q_base;    // absolute demod index of this call's first output
     uint32_t      dmask;
     uint32_t      npass;
+    uint32_t      pass_per_cta;
     uint32_t      blk_base;  // absolute 25-sample block index (mod 2^32) of logical sample 0
     uint32_t      fcw25;     // NCO phase step per block (25 * fcw mod 2^32)
     float2        w[kD1];    // NCO phasors inside a block
@@ -34,9 +43,14 @@ struct RxState {             // device-resident stream state
     unsigned long long lo;          // next demod position to search
     unsigned long long resume_at;   // positions below this are inside an already captured burst
     unsigned long long nrec_total;  // bursts published since stream start (monotonic)
+    unsigned long long rec_base;    // nrec_total before the bursts accepted by the last select
     unsigned int       ncand;       // candidates found by the detect kernel (reset by select)
     unsigned int       cand_overflow;
+    unsigned int       n_acc;       // bursts accepted by the last select, captured by the capture kernel
+    unsigned int       done;        // capture CTAs finished
 };
+
+struct Accepted { unsigned long long pos; float corr; unsigned int run; };
 
 struct RxPublished {         // mirror of the counters in mapped pinned host memory, written by the select kernel
     unsigned long long nrec_total;
@@ -44,7 +58,13 @@ struct RxPublished {         // mirror of the counters in mapped pinned host mem
     unsigned int       pad;
 };
 
-struct Candidate { unsigned long long pos; float corr; unsigned int pad; };
+// one run of adjacent sampling phases that all match the trigger 74/74, found by the detect kernel
+struct Candidate {
+    unsigned long long start;   // first matching position of the run
+    unsigned long long best;    // position of the soft-correlation peak inside the run (first maximum)
+    float              corr;
+    unsigned int       run;     // run length; bit 31 set = the run reaches the end of the searched range
+};
 
 constexpr int kMaxCand = 8192;
 constexpr int kMaxAccept = 512;    // bursts one call can publish
@@ -52,13 +72,15 @@ constexpr int kMaxAccept = 512;    // bursts one call can publish
 size_t rx_front_smem_bytes();
 cudaError_t rx_configure_device();
 cudaError_t launch_rx_front(const RxFrontParams &p, int grid, cudaStream_t st);
-cudaError_t launch_rx_detect(const float *dring, uint32_t dmask, RxState *state, Candidate *cand,
+cudaError_t launch_rx_detect(const float *dring, const uint32_t *hring, uint32_t dmask, RxState *state, Candidate *cand,
                              unsigned long long scan_lo, unsigned long long scan_hi, cudaStream_t st);
-// records are assembled in `scratch` (device memory, kMaxAccept entries) and then streamed into
-// host_ring[(nrec_total + a) % ring_len] (mapped pinned host memory, device-visible alias)
-cudaError_t launch_rx_select(const float *dring, uint32_t dmask, RxState *state, Candidate *cand,
-                             unsigned long long scan_hi, amps_burst *scratch, amps_burst *host_ring,
-                             unsigned int ring_len, RxPublished *host_pub, cudaStream_t st);
+// select: sorts the candidates, groups runs, picks sampling phases -> acc[0 .. state->n_acc)
+cudaError_t launch_rx_select(RxState *state, Candidate *cand, Accepted *acc, unsigned long long scan_hi,
+                             RxPublished *host_pub, cudaStream_t st);
+// capture: one CTA per accepted burst (grid = upper bound, surplus CTAs exit): gathers the 3374 half-symbols,
+// decodes, and streams the record into host_ring[(rec_base + b) % ring_len] (mapped pinned host memory)
+cudaError_t launch_rx_capture(const float *dring, uint32_t dmask, RxState *state, const Accepted *acc, int grid,
+                              amps_burst *host_ring, unsigned int ring_len, RxPublished *host_pub, cudaStream_t st);
 cudaError_t launch_decode_blobs(const uint8_t *blobs, int nbursts, amps_recc_words *out, cudaStream_t st);
 
 }  // namespace amps

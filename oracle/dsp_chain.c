@@ -225,32 +225,35 @@ void orc_rx_chain_f32(const float *iq, size_t n, uint32_t fcw, const float *h2, 
 
 /* ------------------------------------------------------------------ detection on d */
 #define OS 10   /* demod samples per half-symbol */
+static int trig_match(const float *d, size_t i, const uint8_t *trig) {
+    for (int k = 0; k < ORC_RECC_TRIGGER_LEN; k++) {
+        int hard = d[i + (size_t)OS * k] >= 0.0f;
+        if (hard != trig[k]) return 0;
+    }
+    return 1;
+}
+/* A "run" is a maximal set of adjacent sampling positions that all match the trigger 74/74 (exact
+ * hard match, as the memmem of recc_impl.cc:118).  One burst per run whose FIRST position is not
+ * inside an already captured burst; the sampling position is the soft-correlation peak of the run
+ * (first maximum); the search resumes (74+3374)*10 positions after it. */
 int orc_rx_detect(const float *d, size_t nd, orc_burst *out, int max) {
     uint8_t trig[ORC_RECC_TRIGGER_LEN];
     orc_recc_trigger(trig);
     const size_t span = (size_t)OS * (ORC_RECC_TRIGGER_LEN + ORC_RECC_CAPTURE_LEN - 1);  /* last needed offset */
     if (nd <= span) return 0;
     size_t limit = nd - span;          /* candidate positions i in [0, limit) have a complete capture */
+    size_t resume = 0;
     int count = 0;
     size_t i = 0;
     while (i < limit && count < max) {
-        /* exact 74/74 hard match at sampling phase i */
-        int match = 1;
-        for (int k = 0; k < ORC_RECC_TRIGGER_LEN; k++) {
-            int hard = d[i + (size_t)OS * k] >= 0.0f;
-            if (hard != trig[k]) { match = 0; break; }
-        }
-        if (!match) { i++; continue; }
-        /* run of consecutive matching phases: pick the soft-correlation peak (first maximum) */
-        size_t best = i; float bestc = 0; int first = 1;
-        size_t j = i;
-        for (; j < limit; j++) {
-            int m2 = 1;
-            for (int k = 0; k < ORC_RECC_TRIGGER_LEN; k++) {
-                int hard = d[j + (size_t)OS * k] >= 0.0f;
-                if (hard != trig[k]) { m2 = 0; break; }
-            }
-            if (!m2) break;
+        if (!trig_match(d, i, trig) || (i > 0 && trig_match(d, i - 1, trig))) { i++; continue; }
+        /* i starts a run */
+        size_t best = i, j = i;
+        float bestc = 0;
+        int first = 1, open = 0;
+        for (;; j++) {
+            if (j >= limit) { open = 1; break; }          /* run reaches the end of the searchable range: not decided */
+            if (!trig_match(d, j, trig)) break;
             float c = 0.0f;
             for (int k = 0; k < ORC_RECC_TRIGGER_LEN; k++) {
                 float v = d[j + (size_t)OS * k];
@@ -258,12 +261,16 @@ int orc_rx_detect(const float *d, size_t nd, orc_burst *out, int max) {
             }
             if (first || c > bestc) { best = j; bestc = c; first = 0; }
         }
-        orc_burst *b = &out[count++];
-        b->d_index = best;
-        b->corr = bestc;
-        for (int s = 0; s < ORC_RECC_CAPTURE_LEN; s++)
-            b->symbols[s] = d[best + (size_t)OS * (ORC_RECC_TRIGGER_LEN + s)] >= 0.0f ? 1 : 0;
-        i = best + (size_t)OS * (ORC_RECC_TRIGGER_LEN + ORC_RECC_CAPTURE_LEN);   /* resume after the capture */
+        if (open) break;
+        if (i >= resume) {
+            orc_burst *b = &out[count++];
+            b->d_index = best;
+            b->corr = bestc;
+            for (int s = 0; s < ORC_RECC_CAPTURE_LEN; s++)
+                b->symbols[s] = d[best + (size_t)OS * (ORC_RECC_TRIGGER_LEN + s)] >= 0.0f ? 1 : 0;
+            resume = best + (size_t)OS * (ORC_RECC_TRIGGER_LEN + ORC_RECC_CAPTURE_LEN);
+        }
+        i = j;
     }
     return count;
 }

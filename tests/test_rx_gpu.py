@@ -8,8 +8,8 @@ from tests.helpers import bits_equal_f32, words_equal
 
 pytestmark = pytest.mark.gpu
 
-PASS = 9600
-N1 = 219 * PASS          # one config-2 period rounded to whole passes (2 102 400 samples)
+PASS = 38400             # amps_recc_iq_granularity()
+N1 = 55 * PASS           # one config-2 period rounded to whole passes (2 112 000 samples)
 
 
 @pytest.fixture(scope="module")
@@ -70,7 +70,7 @@ def test_chunked_stream_equals_one_shot(capi, oracle):
         n = int(rng.integers(1, 400000))
         got += st.work(x[pos:pos + n])
         pos += n
-    assert st.stats()["demod_out"] == len(x) // PASS * 192
+    assert st.granularity == PASS and st.stats()["demod_out"] == len(x) // PASS * (PASS // 50)
     assert len(b1) == 2 and len(got) == 2
     for a, b in zip(b1, got):
         assert a.demod_index == b.demod_index and bytes(a.symbols) == bytes(b.symbols)
