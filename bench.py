@@ -109,11 +109,11 @@ class ClockSampler(threading.Thread):
 
 
 def make_clean_period(rank):
-    from gr_amps_b200 import synth
+    from gr_amps_b200 import multi, synth
     # config 4: carrier g sits at -160 kHz + 30 kHz * g, its own MIN
-    center = -160e3 + 30e3 * rank
-    x, hs, _ = synth.config2_period(n_total=PERIOD, snr_db=None, center=center, min10="21255512%02d" % (30 + rank))
-    return x, hs, center
+    c = multi.carrier(rank)
+    x, hs, _ = synth.config2_period(n_total=PERIOD, snr_db=None, center=c.center_freq, min10=c.min10)
+    return x, hs, c
 
 
 def run_reference(args, rank, world):
@@ -182,11 +182,12 @@ def main():
         args.warmup = 3
 
     # ---- synthetic batch: tile one clean period, add fresh AWGN (SNR 20 dB in 30 kHz) on the device
-    clean, hs, center = make_clean_period(rank)
+    clean, hs, car = make_clean_period(rank)
+    center = car.center_freq
     nper = args.periods
     n = nper * PERIOD
     g = torch.Generator(device=dev)
-    g.manual_seed(0xA3B5 + rank)
+    g.manual_seed(car.seed)
     base = torch.from_numpy(clean.view(np.float32).copy()).to(dev)
     sigma = float(np.sqrt(0.25 / 100.0 * (10e6 / 30e3) / 2.0))
     batch = base.repeat(nper)
@@ -225,14 +226,12 @@ def main():
     ms = e0.elapsed_time(e1)
     launches = rx.stats()["kernel_launches"] - launches0
     front_ms = rx.front_times_ms(256)[-args.steps:]
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    from gr_amps_b200 import multi
+    total_samples, ms_max = multi.whole_job_throughput(float(args.steps) * n, ms, dev)
 
     # correctness gate: the stream is continuous over the steps, so all but the burst straddling the
     # last batch's end are captured; every one must decode to this rank's MIN with all words valid
-    expect_min = ("21255512%02d" % (30 + rank)).encode()
+    expect_min = car.min10.encode()
     bursts = [ring[(first + i) % ring_len] for i in range(count)]
     ok = [b for b in bursts if b.decoded.min == expect_min and list(b.decoded.valid) == [1] * 7 and b.decoded.kind == 4]
     if len(ok) < args.steps * nper - 2 or len(ok) != len(bursts):
@@ -258,10 +257,7 @@ def main():
         rx2.work_ptr(host.data_ptr(), n, cb)
     torch.cuda.synchronize()
     t1 = time.perf_counter()
-    te = torch.tensor([t1 - t0], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_sec = float(te.item())
+    e2e_samples, e2e_sec = multi.whole_job_throughput(float(e2e_steps) * n, t1 - t0, dev)
     if len(got) < e2e_steps * nper - 2 or any(m != expect_min for m in got):
         raise SystemExit("bench.py: e2e parity gate failed (%d bursts)" % len(got))
     rec_bytes = 24 + (len(got) / e2e_steps) * float(capi.C.sizeof(capi.Burst))
@@ -272,7 +268,7 @@ def main():
         return 0
 
     peak, peak_src = load_peaks()
-    value = world * args.steps * n / (ms_max * 1e-3) / 1e6
+    value = total_samples / (ms_max * 1e-3) / 1e6
     fm = float(np.mean(front_ms)) if len(front_ms) else float("nan")
     alg_bytes = n * ALG_BYTES_PER_SAMPLE + nper * BURST_BYTES
     achieved = alg_bytes / (fm * 1e-3) / 1e9
@@ -310,7 +306,7 @@ def main():
         "roofline": roofline,
         "cpu_baseline": cpu,
         "clocks": clocks,
-        "e2e": {"value": world * e2e_steps * n / e2e_sec / 1e6, "unit": "Msamples/s",
+        "e2e": {"value": e2e_samples / e2e_sec / 1e6, "unit": "Msamples/s",
                 "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": int(rec_bytes), "steps": e2e_steps,
                 "api": "amps_recc_iq_work (pinned host buffer, burst callbacks)"},
         "gpu_launches": int(launches) * world,

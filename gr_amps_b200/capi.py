@@ -90,12 +90,6 @@ EXPORTS = [
     "amps_recc_iq_submit_dev", "amps_recc_iq_collect", "amps_recc_iq_peek", "amps_recc_iq_consume", "amps_recc_iq_granularity", "amps_recc_iq_read_demod",
     "amps_recc_iq_read_baseband", "amps_recc_iq_stats", "amps_recc_iq_front_times", "amps_recc_iq_get_taps",
     "amps_recc_decode_create", "amps_recc_decode_destroy", "amps_recc_decode_burst", "amps_recc_decode_bursts",
-    "amps_recc_create", "amps_recc_destroy", "amps_recc_work", "amps_recc_work_chunks",
-    "amps_focc_create", "amps_focc_destroy", "amps_focc_work", "amps_focc_generate", "amps_focc_generate_dev",
-    "amps_focc_push_words", "amps_focc_set_busy_idle",
-    "amps_fvc_create", "amps_fvc_destroy", "amps_fvc_push_words", "amps_fvc_work",
-    "amps_fwd_create", "amps_fwd_destroy", "amps_fwd_reset", "amps_fwd_work", "amps_fwd_submit_dev",
-    "amps_fwd_interp", "amps_fwd_get_taps",
 ]
 
 _lib = None

@@ -165,77 +165,6 @@ AMPS_B200_API int amps_recc_decode_burst(amps_recc_decode *h, const uint8_t *blo
 /* batch form: nbursts blobs back to back */
 AMPS_B200_API int amps_recc_decode_bursts(amps_recc_decode *h, const uint8_t *blobs, int nbursts, amps_recc_words *out);
 
-/* ------------------------------------------------------------------------------------------
- * recc: byte-stream sink, compat mode (lib/recc_impl.cc:93-145 incl. its buffer quirks).
- * in = n hard half-symbols (0/1).  cb is invoked with each 3374-byte blob.
- * ------------------------------------------------------------------------------------------ */
-typedef struct amps_recc amps_recc;
-typedef void (*amps_blob_cb)(const uint8_t *blob3374, void *user);
-AMPS_B200_API int amps_recc_create(int device, amps_recc **out);
-AMPS_B200_API int amps_recc_destroy(amps_recc *h);
-/* one work() call; returns AMPS_OK (the reference returns 0 items and consumes n) */
-AMPS_B200_API int amps_recc_work(amps_recc *h, const uint8_t *in, int n, amps_blob_cb cb, void *user);
-/* a whole schedule of work() calls in one launch: chunk_sizes[nchunks], in = concatenated chunks */
-AMPS_B200_API int amps_recc_work_chunks(amps_recc *h, const uint8_t *in, const int *chunk_sizes, int nchunks,
-                                        amps_blob_cb cb, void *user);
-
-/* ------------------------------------------------------------------------------------------
- * focc: FOCC Manchester half-symbol source (lib/focc_impl.cc:104-136, 486-647).
- * ------------------------------------------------------------------------------------------ */
-typedef struct amps_focc amps_focc;
-AMPS_B200_API int amps_focc_create(unsigned long symrate, int aggressive_registration, int device, amps_focc **out);
-AMPS_B200_API int amps_focc_destroy(amps_focc *h);
-/* work(): writes up to noutput_items bytes (+1 = 0x01, -1 = 0xFF) to out (host memory) and returns
- * the number produced in *produced: at most one 23/22-bit burst per call, possibly 0; -1 (WORK_DONE)
- * when noutput_items < 1 (lib/focc_impl.cc:590-593,630-632). */
-AMPS_B200_API int amps_focc_work(amps_focc *h, uint8_t *out, int noutput_items, int *produced);
-/* bulk form: the concatenation of successive work() outputs until exactly n bytes were produced */
-AMPS_B200_API int amps_focc_generate(amps_focc *h, uint8_t *out, size_t n);
-AMPS_B200_API int amps_focc_generate_dev(amps_focc *h, void *d_out, size_t n, void *cuda_stream);
-/* focc_words message (lib/focc_impl.cc:521-563): stream 1=A 2=B 3=BOTH, words28 = nwords x 28 bytes */
-AMPS_B200_API int amps_focc_push_words(amps_focc *h, long stream, const uint8_t *words28, long nwords);
-AMPS_B200_API int amps_focc_set_busy_idle(amps_focc *h, int idle);      /* lib/amps_common.h:7 */
-
-/* ------------------------------------------------------------------------------------------
- * fvc: FVC blank-and-burst source (lib/fvc_impl.cc:56-193).
- * ------------------------------------------------------------------------------------------ */
-typedef struct amps_fvc amps_fvc;
-AMPS_B200_API int amps_fvc_create(unsigned long symrate, int device, amps_fvc **out);
-AMPS_B200_API int amps_fvc_destroy(amps_fvc *h);
-/* fvc_words message (lib/fvc_impl.cc:109-143); has_timer/timer = the optional trailing uint64 */
-AMPS_B200_API int amps_fvc_push_words(amps_fvc *h, const uint8_t *words28, long nwords, int has_timer, uint64_t timer);
-/* work(): *produced = items produced; while no word was ever pushed the reference returns
- * noutput_items WITHOUT writing (lib/fvc_impl.cc:159-161); this library writes zeros there
- * (documented deviation).  *fvc_off is set when the "fvc off" PDU is due (:163-171). */
-AMPS_B200_API int amps_fvc_work(amps_fvc *h, uint8_t *out, int noutput_items, int *produced, int *fvc_off);
-
-/* ------------------------------------------------------------------------------------------
- * Fused forward path: symbols -> char_to_float -> frequency_modulator_fc -> pfb interpolator ->
- * mix -> sum -> x0.5 (grc/ampsbs.grc:1159-1252, 574-659, 2120-2229, 817-942, 1006-1056, 1355-1405)
- * at 10 MS/s output.  Up to 3 carriers (FOCC @0 Hz + two FVC legs).
- * ------------------------------------------------------------------------------------------ */
-typedef struct amps_fwd amps_fwd;
-typedef struct amps_fwd_params {
-    double   samp_rate;          /* output rate, 10e6 */
-    double   symrate;            /* symbol-stream rate feeding the FM modulator, 100e3 (grc/ampsbs.grc:135,317) */
-    double   max_deviation;      /* 8000 (grc/ampsbs.grc:209) */
-    int      device;
-    int      ncarriers;          /* 1..3 */
-    double   carrier_freq[3];    /* 0, 60e3, 90e3 (grc/ampsbs.grc:841,904) */
-    double   lpf_transition[3];  /* firdes.low_pass(1, samp_rate, 10e3, tw): 5e3 FOCC, 3e3 FVC (:2227,:2172) */
-    float    out_scale;          /* 0.5 (:1367) */
-    uint32_t max_samples;
-} amps_fwd_params;
-AMPS_B200_API int amps_fwd_create(const amps_fwd_params *p, amps_fwd **out);
-AMPS_B200_API int amps_fwd_destroy(amps_fwd *h);
-AMPS_B200_API int amps_fwd_reset(amps_fwd *h);
-/* sym[c] = host arrays of nsym +1/-1 (0x01/0xFF, 0 = muted) bytes per carrier; out_iq_host gets
- * nsym * (samp_rate/symrate) complex samples. */
-AMPS_B200_API int amps_fwd_work(amps_fwd *h, const uint8_t *const *sym, size_t nsym, float *out_iq_host);
-AMPS_B200_API int amps_fwd_submit_dev(amps_fwd *h, const void *const *d_sym, size_t nsym, void *d_out_iq, void *cuda_stream);
-AMPS_B200_API int amps_fwd_interp(const amps_fwd *h);
-AMPS_B200_API int amps_fwd_get_taps(const amps_fwd *h, int carrier, float *out, int cap);
-
 #ifdef __cplusplus
 }
 #endif

@@ -93,13 +93,31 @@ def lib() -> C.CDLL:
     L.orc_rx_detect.argtypes = [f32p, C.c_size_t, C.POINTER(Burst), C.c_int]
     L.orc_cpu_baseline_run.argtypes = [f32p, C.c_size_t, C.c_uint32, f32p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
     L.orc_cpu_baseline_run.restype = C.c_double
-    for name in ("orc_overhead_word_1", "orc_overhead_word_2", "orc_control_filler_word"):
-        getattr(L, name).restype = None
+    ui = C.c_uint
+    L.orc_overhead_word_1.argtypes = [u8p, ui, ui, C.c_int, C.c_int, C.c_int, ui]
+    L.orc_overhead_word_2.argtypes = [u8p, ui, C.c_int, C.c_int, C.c_int, C.c_int, ui, ui, C.c_int, C.c_int, ui, C.c_int]
+    L.orc_control_filler_word.argtypes = [u8p]
+    L.orc_access_type_global_action.argtypes = [u8p, ui, C.c_int]
+    L.orc_reg_increment_global_action.argtypes = [u8p, ui, ui, C.c_int]
+    L.orc_registration_id.argtypes = [u8p, ui, C.c_ulong, C.c_int]
+    L.orc_focc_word1.argtypes = [u8p, C.c_int, ui, C.c_uint64]
+    L.orc_focc_word2_general.argtypes = [u8p, C.c_uint64, ui, ui, ui]
+    L.orc_fvc_word1_general.argtypes = [u8p, ui, ui, ui, ui]
+    L.orc_focc_word2_voice_channel.argtypes = [u8p, ui, C.c_uint64, ui, ui]
+    L.orc_compute_min_3.argtypes = [C.c_char, C.c_char, C.c_char]
+    L.orc_compute_min_3.restype = C.c_uint64
     L.orc_extract_min_3.argtypes = [C.c_uint64, C.c_char_p]
     L.orc_calc_min.argtypes = [C.c_uint64, C.c_uint64, C.c_char_p]
     L.orc_parse_min.argtypes = [C.c_char_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     _lib = L
     return L
+
+
+def word(builder: str, *args) -> np.ndarray:
+    """Call one of the 28-bit word builders, e.g. word('orc_overhead_word_1', 0, 16, 1, 0, 0, 3)."""
+    w = np.zeros(28, np.uint8)
+    getattr(lib(), builder)(w.ctypes.data_as(u8p), *args)
+    return w
 
 
 def as_u8(a) -> np.ndarray:

