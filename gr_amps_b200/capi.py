@@ -90,6 +90,10 @@ EXPORTS = [
     "amps_recc_iq_submit_dev", "amps_recc_iq_collect", "amps_recc_iq_peek", "amps_recc_iq_consume", "amps_recc_iq_granularity", "amps_recc_iq_read_demod",
     "amps_recc_iq_read_baseband", "amps_recc_iq_stats", "amps_recc_iq_front_times", "amps_recc_iq_get_taps",
     "amps_recc_decode_create", "amps_recc_decode_destroy", "amps_recc_decode_burst", "amps_recc_decode_bursts",
+    "amps_recc_create", "amps_recc_destroy", "amps_recc_work", "amps_recc_work_chunks",
+    "amps_focc_create", "amps_focc_destroy", "amps_focc_work", "amps_focc_generate", "amps_focc_generate_dev",
+    "amps_focc_push_words", "amps_focc_set_busy_idle",
+    "amps_fvc_create", "amps_fvc_destroy", "amps_fvc_push_words", "amps_fvc_work",
 ]
 
 _lib = None
@@ -275,3 +279,90 @@ class ReccDecode:
         out = (ReccWords * len(b))()
         check(lib().amps_recc_decode_bursts(self.h, b.ctypes.data_as(u8p), len(b), out))
         return list(out)
+
+
+class Recc:
+    """amps.recc byte-stream sink, compat mode (amps_recc_*)."""
+
+    def __init__(self, device=0):
+        self.h = C.c_void_p()
+        check(lib().amps_recc_create(device, C.byref(self.h)))
+        self.bursts: list[np.ndarray] = []
+        self._cb = BLOB_CB(lambda p, u: self.bursts.append(np.ctypeslib.as_array(p, shape=(CAPTURE_SYMS,)).copy()))
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().amps_recc_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def work(self, syms) -> None:
+        s = np.ascontiguousarray(syms, dtype=np.uint8)
+        check(lib().amps_recc_work(self.h, s.ctypes.data_as(u8p), len(s), self._cb, None))
+
+    def work_chunks(self, syms, sizes) -> None:
+        s = np.ascontiguousarray(syms, dtype=np.uint8)
+        z = (C.c_int * len(sizes))(*[int(v) for v in sizes])
+        check(lib().amps_recc_work_chunks(self.h, s.ctypes.data_as(u8p), z, len(sizes), self._cb, None))
+
+
+class Focc:
+    """amps.focc half-symbol source (amps_focc_*)."""
+
+    def __init__(self, symrate=100000, aggressive=False, device=0):
+        self.h = C.c_void_p()
+        check(lib().amps_focc_create(symrate, int(aggressive), device, C.byref(self.h)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().amps_focc_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def work(self, n: int):
+        buf = np.zeros(max(n, 1), np.uint8)
+        produced = C.c_int(0)
+        check(lib().amps_focc_work(self.h, buf.ctypes.data_as(u8p), n, C.byref(produced)))
+        return produced.value, buf[:max(produced.value, 0)].copy()
+
+    def generate(self, n: int) -> np.ndarray:
+        buf = np.zeros(n, np.uint8)
+        check(lib().amps_focc_generate(self.h, buf.ctypes.data_as(u8p), n))
+        return buf
+
+    def generate_dev(self, dev_ptr: int, n: int, stream: int = 0):
+        check(lib().amps_focc_generate_dev(self.h, C.c_void_p(dev_ptr), n, C.c_void_p(stream)))
+
+    def push_words(self, stream: int, words):
+        w = np.ascontiguousarray(words, dtype=np.uint8).reshape(-1)
+        check(lib().amps_focc_push_words(self.h, stream, w.ctypes.data_as(u8p), len(w) // 28))
+
+    def set_busy_idle(self, idle: bool):
+        check(lib().amps_focc_set_busy_idle(self.h, int(idle)))
+
+
+class Fvc:
+    """amps.fvc half-symbol source (amps_fvc_*)."""
+
+    def __init__(self, symrate=100000, device=0):
+        self.h = C.c_void_p()
+        check(lib().amps_fvc_create(symrate, device, C.byref(self.h)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().amps_fvc_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def push_words(self, words, timer=None):
+        w = np.ascontiguousarray(words, dtype=np.uint8).reshape(-1)
+        check(lib().amps_fvc_push_words(self.h, w.ctypes.data_as(u8p), len(w) // 28, int(timer is not None), int(timer or 0)))
+
+    def work(self, n: int, fill=0x55):
+        buf = np.full(max(n, 1), fill, np.uint8)
+        produced, off = C.c_int(0), C.c_int(0)
+        check(lib().amps_fvc_work(self.h, buf.ctypes.data_as(u8p), n, C.byref(produced), C.byref(off)))
+        return produced.value, buf[:max(produced.value, 0)].copy(), bool(off.value)

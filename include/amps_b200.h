@@ -165,6 +165,50 @@ AMPS_B200_API int amps_recc_decode_burst(amps_recc_decode *h, const uint8_t *blo
 /* batch form: nbursts blobs back to back */
 AMPS_B200_API int amps_recc_decode_bursts(amps_recc_decode *h, const uint8_t *blobs, int nbursts, amps_recc_words *out);
 
+/* ------------------------------------------------------------------------------------------
+ * recc: byte-stream sink, compat mode (lib/recc_impl.cc:93-145 incl. its buffer quirks).
+ * in = n hard half-symbols (0/1).  cb is invoked with each 3374-byte blob.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct amps_recc amps_recc;
+typedef void (*amps_blob_cb)(const uint8_t *blob3374, void *user);
+AMPS_B200_API int amps_recc_create(int device, amps_recc **out);
+AMPS_B200_API int amps_recc_destroy(amps_recc *h);
+/* one work() call; returns AMPS_OK (the reference returns 0 items and consumes n) */
+AMPS_B200_API int amps_recc_work(amps_recc *h, const uint8_t *in, int n, amps_blob_cb cb, void *user);
+/* a whole schedule of work() calls in one launch: chunk_sizes[nchunks], in = concatenated chunks */
+AMPS_B200_API int amps_recc_work_chunks(amps_recc *h, const uint8_t *in, const int *chunk_sizes, int nchunks,
+                                        amps_blob_cb cb, void *user);
+
+/* ------------------------------------------------------------------------------------------
+ * focc: FOCC Manchester half-symbol source (lib/focc_impl.cc:104-136, 486-647).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct amps_focc amps_focc;
+AMPS_B200_API int amps_focc_create(unsigned long symrate, int aggressive_registration, int device, amps_focc **out);
+AMPS_B200_API int amps_focc_destroy(amps_focc *h);
+/* work(): writes up to noutput_items bytes (+1 = 0x01, -1 = 0xFF) to out (host memory) and returns
+ * the number produced in *produced: at most one 23/22-bit burst per call, possibly 0; -1 (WORK_DONE)
+ * when noutput_items < 1 (lib/focc_impl.cc:590-593,630-632). */
+AMPS_B200_API int amps_focc_work(amps_focc *h, uint8_t *out, int noutput_items, int *produced);
+/* bulk form: the concatenation of successive work() outputs until exactly n bytes were produced */
+AMPS_B200_API int amps_focc_generate(amps_focc *h, uint8_t *out, size_t n);
+AMPS_B200_API int amps_focc_generate_dev(amps_focc *h, void *d_out, size_t n, void *cuda_stream);
+/* focc_words message (lib/focc_impl.cc:521-563): stream 1=A 2=B 3=BOTH, words28 = nwords x 28 bytes */
+AMPS_B200_API int amps_focc_push_words(amps_focc *h, long stream, const uint8_t *words28, long nwords);
+AMPS_B200_API int amps_focc_set_busy_idle(amps_focc *h, int idle);      /* lib/amps_common.h:7 */
+
+/* ------------------------------------------------------------------------------------------
+ * fvc: FVC blank-and-burst source (lib/fvc_impl.cc:56-193).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct amps_fvc amps_fvc;
+AMPS_B200_API int amps_fvc_create(unsigned long symrate, int device, amps_fvc **out);
+AMPS_B200_API int amps_fvc_destroy(amps_fvc *h);
+/* fvc_words message (lib/fvc_impl.cc:109-143); has_timer/timer = the optional trailing uint64 */
+AMPS_B200_API int amps_fvc_push_words(amps_fvc *h, const uint8_t *words28, long nwords, int has_timer, uint64_t timer);
+/* work(): *produced = items produced; while no word was ever pushed the reference returns
+ * noutput_items WITHOUT writing (lib/fvc_impl.cc:159-161); this library writes zeros there
+ * (documented deviation).  *fvc_off is set when the "fvc off" PDU is due (:163-171). */
+AMPS_B200_API int amps_fvc_work(amps_fvc *h, uint8_t *out, int noutput_items, int *produced, int *fvc_off);
+
 #ifdef __cplusplus
 }
 #endif
