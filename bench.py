@@ -96,7 +96,7 @@ class ClockSampler(threading.Thread):
                 self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(0.0005)
 
     def stop(self):
         self._stop_evt.set()
@@ -124,7 +124,7 @@ def run_reference(args, rank, world):
     from gr_amps_b200 import synth
     cores = os.cpu_count() or 1
     x, _, _ = synth.config2_period(n_total=PERIOD, snr_db=20.0, seed=0xA3B5)
-    reps = 4                                   # per thread per step: 4 periods (8.4 M samples)
+    reps = 1                                   # per thread per step: one period (2.1 M samples)
     for _ in range(max(args.warmup, 1)):
         O.cpu_baseline_run(x, cores, 1)
     t_total, nb = 0.0, 0
@@ -152,7 +152,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--periods", type=int, default=PERIODS_PER_BATCH)
@@ -287,8 +287,8 @@ def main():
         from gr_amps_b200 import synth
         cores = os.cpu_count() or 1
         xs, _, _ = synth.config2_period(n_total=PERIOD, snr_db=20.0, seed=0xA3B5)
-        O.cpu_baseline_run(xs, cores, 1)
-        reps = 8
+        O.cpu_baseline_run(xs, min(cores, 8), 1)      # warm the code and the page cache
+        reps = 1
         sec, nb = O.cpu_baseline_run(xs, cores, reps)
         cpu = {"value": cores * reps * len(xs) / sec / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "port",
                "sample": "%d threads x %d x one config-2 period (%d samples); fp32 oracle chain + detect + decode; %.1f s CPU work"
