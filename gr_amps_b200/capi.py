@@ -94,6 +94,8 @@ EXPORTS = [
     "amps_focc_create", "amps_focc_destroy", "amps_focc_work", "amps_focc_generate", "amps_focc_generate_dev",
     "amps_focc_push_words", "amps_focc_set_busy_idle",
     "amps_fvc_create", "amps_fvc_destroy", "amps_fvc_push_words", "amps_fvc_work",
+    "amps_fwd_create", "amps_fwd_destroy", "amps_fwd_reset", "amps_fwd_work", "amps_fwd_submit_dev",
+    "amps_fwd_interp", "amps_fwd_get_taps",
 ]
 
 _lib = None
@@ -156,7 +158,7 @@ def lib() -> C.CDLL:
         L.amps_fwd_create.argtypes = [C.POINTER(FwdParams), C.POINTER(C.c_void_p)]
         L.amps_fwd_destroy.argtypes = [C.c_void_p]
         L.amps_fwd_reset.argtypes = [C.c_void_p]
-        L.amps_fwd_work.argtypes = [C.c_void_p, C.POINTER(u8p), C.c_size_t, f32p]
+        L.amps_fwd_work.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_size_t, f32p]
         L.amps_fwd_submit_dev.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_size_t, C.c_void_p, C.c_void_p]
         L.amps_fwd_interp.argtypes = [C.c_void_p]
         L.amps_fwd_get_taps.argtypes = [C.c_void_p, C.c_int, f32p, C.c_int]
@@ -366,3 +368,45 @@ class Fvc:
         produced, off = C.c_int(0), C.c_int(0)
         check(lib().amps_fvc_work(self.h, buf.ctypes.data_as(u8p), n, C.byref(produced), C.byref(off)))
         return produced.value, buf[:max(produced.value, 0)].copy(), bool(off.value)
+
+
+class Fwd:
+    """Fused forward path (amps_fwd_*): half-symbol bytes of up to 3 carriers -> complex baseband @10 MS/s."""
+
+    def __init__(self, max_samples: int, carrier_freq=(0.0, 60e3, 90e3), lpf_transition=(5e3, 3e3, 3e3),
+                 out_scale=0.5, device=0, max_deviation=8000.0):
+        n = len(carrier_freq)
+        p = FwdParams(10e6, 100e3, max_deviation, device, n, (C.c_double * 3)(*(list(carrier_freq) + [0.0] * (3 - n))),
+                      (C.c_double * 3)(*(list(lpf_transition)[:n] + [5e3] * (3 - n))), out_scale, max_samples)
+        self.h = C.c_void_p()
+        self.ncar = n
+        check(lib().amps_fwd_create(C.byref(p), C.byref(self.h)))
+        self.interp = lib().amps_fwd_interp(self.h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().amps_fwd_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def reset(self):
+        check(lib().amps_fwd_reset(self.h))
+
+    def taps(self, carrier: int) -> np.ndarray:
+        n = lib().amps_fwd_get_taps(self.h, carrier, None, 0)
+        t = np.zeros(n, np.float32)
+        lib().amps_fwd_get_taps(self.h, carrier, t.ctypes.data_as(f32p), n)
+        return t
+
+    def work(self, syms) -> np.ndarray:
+        arrs = [np.ascontiguousarray(s, dtype=np.uint8) for s in syms]
+        nsym = len(arrs[0])
+        ptrs = (C.c_void_p * 3)(*[a.ctypes.data for a in arrs] + [None] * (3 - len(arrs)))
+        out = np.zeros(2 * nsym * self.interp, np.float32)
+        check(lib().amps_fwd_work(self.h, ptrs, nsym, out.ctypes.data_as(f32p)))
+        return out.view(np.complex64)
+
+    def submit_dev(self, dev_ptrs, nsym: int, out_ptr: int, stream: int = 0):
+        ptrs = (C.c_void_p * 3)(*list(dev_ptrs) + [None] * (3 - len(dev_ptrs)))
+        check(lib().amps_fwd_submit_dev(self.h, ptrs, nsym, C.c_void_p(out_ptr), C.c_void_p(stream)))

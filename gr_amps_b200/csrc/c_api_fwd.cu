@@ -1,0 +1,180 @@
+// c_api_fwd.cu -- extern "C" entry points of the fused forward path (amps_fwd_*), see include/amps_b200.h.
+#include "common.h"
+#include "design.h"
+#include "fwd_kernels.cuh"
+
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <vector>
+
+using namespace amps;
+
+struct amps_fwd {
+    int device = 0, sm_count = 0, ncar = 0;
+    cudaStream_t stream = nullptr;
+    uint32_t max_sym = 0;
+    FwdParams fp{};
+    std::vector<float> taps[kFwdMaxCar];
+    uint8_t *d_sym[kFwdMaxCar] = {};          // host-path staging
+    int32_t *d_sloc[kFwdMaxCar] = {}, *d_btot[kFwdMaxCar] = {}, *d_boff[kFwdMaxCar] = {};
+    uint8_t *d_hsym[2][kFwdMaxCar] = {};
+    int32_t *d_hS[2][kFwdMaxCar] = {};
+    int32_t *d_carry = nullptr;
+    int hist_cur = 0;
+    float2 *d_out = nullptr;                  // host-path staging
+    uint64_t sym_total = 0;
+};
+
+static int fwd_reset_state(amps_fwd *h) {
+    for (int b = 0; b < 2; ++b)
+        for (int c = 0; c < kFwdMaxCar; ++c) {
+            CK(cudaMemset(h->d_hsym[b][c], 0, kFwdHistLen));
+            CK(cudaMemset(h->d_hS[b][c], 0, sizeof(int32_t) * kFwdHistLen));
+        }
+    CK(cudaMemset(h->d_carry, 0, sizeof(int32_t) * kFwdMaxCar));
+    h->hist_cur = 0;
+    h->sym_total = 0;
+    return AMPS_OK;
+}
+
+extern "C" int amps_fwd_create(const amps_fwd_params *p, amps_fwd **out) {
+    if (!p || !out) return set_error(AMPS_E_INVAL, "null argument");
+    *out = nullptr;
+    if (p->samp_rate != 10e6 || p->symrate != 100e3)
+        return set_error(AMPS_E_INVAL, "samp_rate must be 10e6 and symrate 100e3 (x4 reference interpolator, x25 CIC)");
+    if (p->ncarriers < 1 || p->ncarriers > kFwdMaxCar) return set_error(AMPS_E_INVAL, "ncarriers must be 1..3");
+    if (p->max_samples == 0) return set_error(AMPS_E_INVAL, "max_samples must be > 0");
+    int st = select_device(p->device);
+    if (st != AMPS_OK) return st;
+    amps_fwd *h = new (std::nothrow) amps_fwd();
+    if (!h) return set_error(AMPS_E_NOMEM, "out of host memory");
+    h->device = p->device;
+    h->ncar = p->ncarriers;
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, p->device);
+    h->sm_count = prop.multiProcessorCount;
+    h->max_sym = (p->max_samples + kFwdInterp - 1) / kFwdInterp;
+    std::memset(&h->fp, 0, sizeof h->fp);
+    h->fp.ncar = h->ncar;
+    h->fp.scale = p->out_scale;
+    // frequency_modulator_fc sensitivity 2 pi max_deviation / symrate (grc/ampsbs.grc:614) as a 32-bit phase step
+    h->fp.fcw_fm = (uint32_t)(uint64_t)std::llround(p->max_deviation / p->symrate * 4294967296.0);
+    std::vector<float> cic;
+    cic3_taps(kD1, cic);
+    for (size_t i = 0; i < cic.size(); ++i) h->fp.G[i] = 25.0f * cic[i];
+    for (int c = 0; c < h->ncar; ++c) {
+        // pfb interpolator taps at the reference's 400 kS/s: firdes.low_pass(1, 400e3, 10e3, tw) (Hamming), :2172,:2227
+        h->taps[c] = firdes_low_pass(1.0, 400e3, 10e3, p->lpf_transition[c], WIN_HAMMING);
+        const int n = (int)h->taps[c].size();
+        if (n > 4 * kFwdMaxTap4) { delete h; return set_error(AMPS_E_INVAL, "interpolator has more than 324 taps (transition too narrow)"); }
+        h->fp.ntap4[c] = (n + 3) / 4;
+        for (int i = 0; i < n; ++i) h->fp.taps[c][i] = h->taps[c][(size_t)i];
+        const uint32_t fcw = nco_fcw(-p->carrier_freq[c], p->samp_rate);      // shift UP by carrier_freq
+        h->fp.fcw_mix25[c] = (uint32_t)(25u * fcw);
+        nco_block_table(fcw, kD1, reinterpret_cast<float *>(h->fp.w[c]));
+    }
+    cudaError_t ce = fwd_configure_device();
+    if (ce != cudaSuccess) { delete h; return set_cuda_error(ce, "fwd_configure_device"); }
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    const size_t nblk = ((size_t)h->max_sym + kFwdScanBlock - 1) / kFwdScanBlock;
+    for (int c = 0; c < kFwdMaxCar; ++c) {
+        CK(cudaMalloc(&h->d_sym[c], h->max_sym));
+        CK(cudaMalloc(&h->d_sloc[c], sizeof(int32_t) * h->max_sym));
+        CK(cudaMalloc(&h->d_btot[c], sizeof(int32_t) * nblk));
+        CK(cudaMalloc(&h->d_boff[c], sizeof(int32_t) * nblk));
+        for (int b = 0; b < 2; ++b) {
+            CK(cudaMalloc(&h->d_hsym[b][c], kFwdHistLen));
+            CK(cudaMalloc(&h->d_hS[b][c], sizeof(int32_t) * kFwdHistLen));
+        }
+    }
+    CK(cudaMalloc(&h->d_carry, sizeof(int32_t) * kFwdMaxCar));
+    CK(cudaMalloc(&h->d_out, sizeof(float2) * (size_t)h->max_sym * kFwdInterp));
+    st = fwd_reset_state(h);
+    if (st != AMPS_OK) { amps_fwd_destroy(h); return st; }
+    *out = h;
+    return AMPS_OK;
+}
+
+extern "C" int amps_fwd_destroy(amps_fwd *h) {
+    if (!h) return AMPS_OK;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    if (h->stream) cudaStreamDestroy(h->stream);
+    for (int c = 0; c < kFwdMaxCar; ++c) {
+        cudaFree(h->d_sym[c]); cudaFree(h->d_sloc[c]); cudaFree(h->d_btot[c]); cudaFree(h->d_boff[c]);
+        for (int b = 0; b < 2; ++b) { cudaFree(h->d_hsym[b][c]); cudaFree(h->d_hS[b][c]); }
+    }
+    cudaFree(h->d_carry); cudaFree(h->d_out);
+    delete h;
+    return AMPS_OK;
+}
+
+extern "C" int amps_fwd_reset(amps_fwd *h) {
+    if (!h) return set_error(AMPS_E_INVAL, "null handle");
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    return fwd_reset_state(h);
+}
+
+extern "C" int amps_fwd_interp(const amps_fwd *h) { (void)h; return kFwdInterp; }
+
+extern "C" int amps_fwd_get_taps(const amps_fwd *h, int carrier, float *out, int cap) {
+    if (!h || carrier < 0 || carrier >= h->ncar) return set_error(AMPS_E_INVAL, "bad argument");
+    const int n = (int)h->taps[carrier].size();
+    if (out) for (int i = 0; i < n && i < cap; ++i) out[i] = h->taps[carrier][(size_t)i];
+    return n;
+}
+
+extern "C" int amps_fwd_submit_dev(amps_fwd *h, const void *const *d_sym, size_t nsym, void *d_out_iq, void *cuda_stream) {
+    if (!h || !d_sym || (nsym && !d_out_iq)) return set_error(AMPS_E_INVAL, "null argument");
+    if (nsym == 0) return AMPS_OK;
+    if (nsym > h->max_sym) return set_error(AMPS_E_OVERFLOW, "nsym exceeds max_samples / 100");
+    if (reinterpret_cast<uintptr_t>(d_out_iq) & 15u) return set_error(AMPS_E_ALIGN, "d_out_iq must be 16-byte aligned");
+    for (int c = 0; c < h->ncar; ++c) if (!d_sym[c]) return set_error(AMPS_E_INVAL, "null symbol stream");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    const int cur = h->hist_cur, nxt = cur ^ 1;
+    FwdScanParams sp{};
+    FwdParams p = h->fp;
+    for (int c = 0; c < kFwdMaxCar; ++c) {
+        const int cc = c < h->ncar ? c : 0;
+        sp.sym[c] = static_cast<const uint8_t *>(d_sym[cc]);
+        sp.sloc[c] = h->d_sloc[c]; sp.btot[c] = h->d_btot[c]; sp.boff[c] = h->d_boff[c];
+        sp.hsym_old[c] = h->d_hsym[cur][c]; sp.hS_old[c] = h->d_hS[cur][c];
+        sp.hsym_new[c] = h->d_hsym[nxt][c]; sp.hS_new[c] = h->d_hS[nxt][c];
+        p.sym[c] = sp.sym[c]; p.sloc[c] = h->d_sloc[c]; p.boff[c] = h->d_boff[c];
+        p.hsym[c] = h->d_hsym[cur][c]; p.hS[c] = h->d_hS[cur][c];
+    }
+    sp.carry = h->d_carry;
+    sp.nsym = (uint32_t)nsym;
+    CKL(launch_fwd_scan(sp, h->ncar, st));
+    p.out = static_cast<float2 *>(d_out_iq);
+    p.nsym = (uint32_t)nsym;
+    p.m_base = (uint32_t)(h->sym_total * 4u);
+    const uint32_t ntiles = ((uint32_t)nsym + kFwdTileSym - 1) / kFwdTileSym;
+    uint32_t grid = 2u * (uint32_t)h->sm_count;
+    if (grid > ntiles) grid = ntiles;
+    CKL(launch_fwd_fused(p, (int)grid, st));
+    h->hist_cur = nxt;
+    h->sym_total += nsym;
+    return AMPS_OK;
+}
+
+extern "C" int amps_fwd_work(amps_fwd *h, const uint8_t *const *sym, size_t nsym, float *out_iq_host) {
+    if (!h || !sym || (nsym && !out_iq_host)) return set_error(AMPS_E_INVAL, "null argument");
+    if (nsym == 0) return AMPS_OK;
+    if (nsym > h->max_sym) return set_error(AMPS_E_OVERFLOW, "nsym exceeds max_samples / 100");
+    CK(cudaSetDevice(h->device));
+    const void *dptr[kFwdMaxCar] = {};
+    for (int c = 0; c < h->ncar; ++c) {
+        if (!sym[c]) return set_error(AMPS_E_INVAL, "null symbol stream");
+        CK(cudaMemcpyAsync(h->d_sym[c], sym[c], nsym, cudaMemcpyHostToDevice, h->stream));
+        dptr[c] = h->d_sym[c];
+    }
+    int rc = amps_fwd_submit_dev(h, dptr, nsym, h->d_out, h->stream);
+    if (rc != AMPS_OK) return rc;
+    CK(cudaMemcpyAsync(out_iq_host, h->d_out, sizeof(float2) * nsym * kFwdInterp, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return AMPS_OK;
+}

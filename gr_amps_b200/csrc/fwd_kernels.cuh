@@ -1,0 +1,52 @@
+// fwd_kernels.cuh -- launch interface of the fused forward (transmit) path (fwd_kernels.cu)
+#pragma once
+#include "spec.cuh"
+
+namespace amps {
+
+constexpr int kFwdMaxCar   = 3;
+constexpr int kFwdTileSym  = 63;                 // new 100 kS/s symbols per tile -> 6300 output samples
+constexpr int kFwdMaxTap4  = 81;                 // taps per polyphase arm (321 padded to 324)
+constexpr int kFwdHistLen  = kFwdMaxTap4 + 1;    // symbols of history a call needs from the previous one
+constexpr int kFwdThreads  = 256;
+constexpr int kFwdScanBlock = 4096;              // symbols per block of the prefix-sum kernels
+constexpr int kFwdInterp   = 100;                // 10 MS/s / 100 kS/s = 4 (reference) x 25 (CIC)
+
+struct FwdScanParams {
+    const uint8_t *sym[kFwdMaxCar];
+    int32_t       *sloc[kFwdMaxCar];             // inclusive scan inside each 4096-symbol block
+    int32_t       *btot[kFwdMaxCar];             // block totals
+    int32_t       *boff[kFwdMaxCar];             // exclusive scan of the block totals + carry
+    int32_t       *carry;                        // [kFwdMaxCar] running sum across calls
+    const uint8_t *hsym_old[kFwdMaxCar];
+    const int32_t *hS_old[kFwdMaxCar];
+    uint8_t       *hsym_new[kFwdMaxCar];
+    int32_t       *hS_new[kFwdMaxCar];
+    uint32_t       nsym;
+};
+
+struct FwdParams {
+    const uint8_t *sym[kFwdMaxCar];
+    const int32_t *sloc[kFwdMaxCar];
+    const int32_t *boff[kFwdMaxCar];
+    const uint8_t *hsym[kFwdMaxCar];             // previous call's last kFwdHistLen symbols
+    const int32_t *hS[kFwdMaxCar];               // and their absolute phase sums
+    float2        *out;
+    uint32_t       nsym;
+    int            ncar;
+    uint32_t       fcw_fm;                       // FM phase step per unit symbol (2^32 = one turn)
+    uint32_t       m_base;                       // absolute 400 kS/s index of this call's first sample (mod 2^32)
+    uint32_t       fcw_mix25[kFwdMaxCar];        // mixer phase step per 400 kS/s sample (25 * fcw)
+    float          scale;
+    int            ntap4[kFwdMaxCar];
+    float2         w[kFwdMaxCar][kD1];           // mixer phasors inside a 25-sample block
+    float          G[75];                        // 25 * CIC^3 taps
+    float          taps[kFwdMaxCar][4 * kFwdMaxTap4];
+};
+
+size_t fwd_smem_bytes();
+cudaError_t fwd_configure_device();
+cudaError_t launch_fwd_scan(const FwdScanParams &p, int ncar, cudaStream_t st);
+cudaError_t launch_fwd_fused(const FwdParams &p, int grid, cudaStream_t st);
+
+}  // namespace amps

@@ -209,6 +209,34 @@ AMPS_B200_API int amps_fvc_push_words(amps_fvc *h, const uint8_t *words28, long 
  * (documented deviation).  *fvc_off is set when the "fvc off" PDU is due (:163-171). */
 AMPS_B200_API int amps_fvc_work(amps_fvc *h, uint8_t *out, int noutput_items, int *produced, int *fvc_off);
 
+/* ------------------------------------------------------------------------------------------
+ * Fused forward path: symbols -> char_to_float -> frequency_modulator_fc -> pfb interpolator (x4, the
+ * reference's taps @400 kS/s) -> CIC^3 x25 -> mix -> sum -> x0.5 (grc/ampsbs.grc:1159-1252, 574-659,
+ * 2120-2229, 817-942, 1006-1056, 1355-1405) at 10 MS/s output.  Up to 3 carriers (FOCC @0 Hz + two
+ * FVC legs).  A symbol byte of 0 mutes that symbol (mute_xx, :1508-1601).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct amps_fwd amps_fwd;
+typedef struct amps_fwd_params {
+    double   samp_rate;          /* output rate, 10e6 */
+    double   symrate;            /* symbol-stream rate feeding the FM modulator, 100e3 (grc/ampsbs.grc:135,317) */
+    double   max_deviation;      /* 8000 (grc/ampsbs.grc:209) */
+    int      device;
+    int      ncarriers;          /* 1..3 */
+    double   carrier_freq[3];    /* 0, 60e3, 90e3 (grc/ampsbs.grc:841,904) */
+    double   lpf_transition[3];  /* x4 pfb interpolator taps firdes.low_pass(1, 400e3, 10e3, tw): 5e3 FOCC, 3e3 FVC (:2227,:2172) */
+    float    out_scale;          /* 0.5 (:1367) */
+    uint32_t max_samples;
+} amps_fwd_params;
+AMPS_B200_API int amps_fwd_create(const amps_fwd_params *p, amps_fwd **out);
+AMPS_B200_API int amps_fwd_destroy(amps_fwd *h);
+AMPS_B200_API int amps_fwd_reset(amps_fwd *h);
+/* sym[c] = host arrays of nsym +1/-1 (0x01/0xFF, 0 = muted) bytes per carrier; out_iq_host gets
+ * nsym * (samp_rate/symrate) complex samples. */
+AMPS_B200_API int amps_fwd_work(amps_fwd *h, const uint8_t *const *sym, size_t nsym, float *out_iq_host);
+AMPS_B200_API int amps_fwd_submit_dev(amps_fwd *h, const void *const *d_sym, size_t nsym, void *d_out_iq, void *cuda_stream);
+AMPS_B200_API int amps_fwd_interp(const amps_fwd *h);
+AMPS_B200_API int amps_fwd_get_taps(const amps_fwd *h, int carrier, float *out, int cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -135,9 +135,10 @@ typedef struct {
 } orc_burst;
 int  orc_rx_detect(const float *d, size_t nd, orc_burst *out, int max);
 
-/* TX chain (config 3): symbols(+1/-1 bytes) -> FM -> interpolating FIR -> mix; see dsp_chain.c */
-void orc_tx_chain_f64(const int8_t *sym, size_t nsym, double sens, int interp, const float *taps, int ntaps,
-                      double mix_cycles_per_sample, double *out /* nsym*interp complex */);
+/* Forward (TX) chain, f64 "ideal" (config 3); see dsp_chain.c for the definition. */
+void orc_fwd_chain_f64(const int8_t *const *sym, int ncarriers, size_t nsym, uint32_t fcw_fm,
+                       const float *const *taps, const int *ntaps, const uint32_t *fcw_mix, double scale,
+                       double *out /* nsym*100 complex */);
 
 #ifdef __cplusplus
 }

@@ -275,31 +275,65 @@ int orc_rx_detect(const float *d, size_t nd, orc_burst *out, int max) {
     return count;
 }
 
-/* ------------------------------------------------------------------ TX chain, f64 */
-/* char_to_float -> frequency_modulator_fc(sens) -> pfb interpolator (taps, interp) -> x e^{j 2 pi f n}
- * (grc/ampsbs.grc:1159-1252, 574-659, 2120-2229, 817-942).  out has nsym*interp complex doubles. */
-void orc_tx_chain_f64(const int8_t *sym, size_t nsym, double sens, int interp, const float *taps, int ntaps,
-                      double mix, double *out) {
+/* ------------------------------------------------------------------ forward (TX) chain, f64 */
+/* What the reference does @400 kS/s (grc/ampsbs.grc): char_to_float (:1159-1252) ->
+ * frequency_modulator_fc(2 pi 8000 / symrate) (:574-659) -> pfb.interpolator_ccf(4, firdes.low_pass(1,
+ * 400e3, 10e3, tw)) (:2120-2229) -> [mute] -> multiply by e^{j 2 pi f n / fs} (:817-942) -> add (:1006-1056)
+ * -> x 0.5 (:1355-1405).  The 10 MS/s extrapolation keeps all of that at the reference's 400 kS/s and
+ * appends a CIC^3 x25 interpolator per carrier before the mixers:
+ *
+ *   s[i] in {+1,-1,0}  ->  S[i] = sum s  ->  fm[i] = (s[i] != 0) * exp(j 2 pi frac(S[i] * fcw_fm / 2^32))
+ *   a[4i+j] = sum_k T[j+4k] fm[i-k]                         (pfb interpolator, zero history)
+ *   b[25m+r] = sum_{t=0..2} G[r+25t] a[m-t],  G = 25 * cic3   (zero-stuff by 25, CIC^3)
+ *   out[n]  = scale * sum_c b_c[n] * exp(j 2 pi frac(n * fcw_c / 2^32))
+ *
+ * A symbol byte of 0 mutes that symbol (the reference's mute_xx, :1508-1601, gates the interpolator output;
+ * gating its input differs only in the 0.8 ms filter transient).
+ */
+void orc_fwd_chain_f64(const int8_t *const *sym, int ncarriers, size_t nsym, uint32_t fcw_fm,
+                       const float *const *taps, const int *ntaps, const uint32_t *fcw_mix, double scale,
+                       double *out /* nsym*100 complex */) {
+    const size_t nm = nsym * 4, nout = nsym * 100;
+    double c3[NCIC];
+    cic_coeffs(c3);
+    memset(out, 0, sizeof(double) * 2 * nout);
     double *fr = (double *)malloc(sizeof(double) * nsym), *fi = (double *)malloc(sizeof(double) * nsym);
-    double phi = 0;
-    for (size_t i = 0; i < nsym; i++) {
-        phi += sens * (double)sym[i];
-        fr[i] = cos(phi); fi[i] = sin(phi);
-    }
-    for (size_t i = 0; i < nsym; i++) {
-        for (int j = 0; j < interp; j++) {
-            double ar = 0, ai = 0;
-            for (int k = 0; j + k * interp < ntaps; k++) {
-                if (i < (size_t)k) break;
-                double t = taps[j + k * interp];
-                ar += t * fr[i - k]; ai += t * fi[i - k];
-            }
-            size_t n = i * (size_t)interp + (size_t)j;
-            double ang = 2.0 * M_PI * fmod(mix * (double)n, 1.0);
-            double cr = cos(ang), ci = sin(ang);
-            out[2 * n] = ar * cr - ai * ci;
-            out[2 * n + 1] = ar * ci + ai * cr;
+    double *ar = (double *)malloc(sizeof(double) * nm), *ai = (double *)malloc(sizeof(double) * nm);
+    for (int c = 0; c < ncarriers; c++) {
+        int32_t S = 0;
+        for (size_t i = 0; i < nsym; i++) {
+            S += sym[c][i];
+            uint32_t psi = (uint32_t)S * fcw_fm;
+            double ang = 2.0 * M_PI * ((double)psi / 4294967296.0);
+            double g = sym[c][i] != 0 ? 1.0 : 0.0;
+            fr[i] = g * cos(ang); fi[i] = g * sin(ang);
         }
+        for (size_t i = 0; i < nsym; i++)
+            for (int j = 0; j < 4; j++) {
+                double sr = 0, si = 0;
+                for (int k = 0; j + 4 * k < ntaps[c]; k++) {
+                    if (i < (size_t)k) break;
+                    double t = taps[c][j + 4 * k];
+                    sr += t * fr[i - k]; si += t * fi[i - k];
+                }
+                ar[4 * i + j] = sr; ai[4 * i + j] = si;
+            }
+        for (size_t m = 0; m < nm; m++)
+            for (int r = 0; r < 25; r++) {
+                double br = 0, bi = 0;
+                for (int t = 0; t < 3; t++) {
+                    int gi = r + 25 * t;
+                    if (gi >= NCIC || m < (size_t)t) continue;
+                    double g = 25.0 * c3[gi];
+                    br += g * ar[m - t]; bi += g * ai[m - t];
+                }
+                size_t n = 25 * m + (size_t)r;
+                uint32_t psi = (uint32_t)((uint64_t)n * fcw_mix[c]);
+                double ang = 2.0 * M_PI * ((double)psi / 4294967296.0);
+                double cr = cos(ang), ci = sin(ang);
+                out[2 * n] += scale * (br * cr - bi * ci);
+                out[2 * n + 1] += scale * (br * ci + bi * cr);
+            }
     }
-    free(fr); free(fi);
+    free(fr); free(fi); free(ar); free(ai);
 }

@@ -93,6 +93,8 @@ def lib() -> C.CDLL:
     L.orc_rx_detect.argtypes = [f32p, C.c_size_t, C.POINTER(Burst), C.c_int]
     L.orc_cpu_baseline_run.argtypes = [f32p, C.c_size_t, C.c_uint32, f32p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
     L.orc_cpu_baseline_run.restype = C.c_double
+    L.orc_fwd_chain_f64.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_size_t, C.c_uint32, C.POINTER(C.c_void_p),
+                                    C.POINTER(C.c_int), C.POINTER(C.c_uint32), C.c_double, f64p]
     ui = C.c_uint
     L.orc_overhead_word_1.argtypes = [u8p, ui, ui, C.c_int, C.c_int, C.c_int, ui]
     L.orc_overhead_word_2.argtypes = [u8p, ui, C.c_int, C.c_int, C.c_int, C.c_int, ui, ui, C.c_int, C.c_int, ui, C.c_int]
@@ -207,6 +209,23 @@ def cpu_baseline_run(x: np.ndarray, threads: int, reps: int, center=-160e3, fs=1
     nb = C.c_int(0)
     sec = lib().orc_cpu_baseline_run(ptr(iq, f32p), n, fcw, ptr(taps, f32p), len(taps), threads, reps, C.byref(nb))
     return sec, nb.value
+
+
+def fwd_chain_f64(syms, carrier_freq=(0.0, 60e3, 90e3), lpf_transition=(5e3, 3e3, 3e3), scale=0.5,
+                  max_deviation=8000.0, symrate=100e3, fs=10e6) -> np.ndarray:
+    """float64 forward chain of BASELINE config 3 (see oracle/dsp_chain.c); syms = list of +-1/0 byte arrays."""
+    n = len(syms)
+    arrs = [np.ascontiguousarray(s, dtype=np.uint8) for s in syms]
+    nsym = len(arrs[0])
+    taps = [firdes_low_pass(1.0, 400e3, 10e3, lpf_transition[c], 0) for c in range(n)]
+    symp = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+    tapp = (C.c_void_p * n)(*[t.ctypes.data for t in taps])
+    nt = (C.c_int * n)(*[len(t) for t in taps])
+    fcw = (C.c_uint32 * n)(*[lib().orc_nco_fcw(-carrier_freq[c], fs) for c in range(n)])
+    fcw_fm = int(round(max_deviation / symrate * 4294967296.0)) & 0xffffffff
+    out = np.zeros(2 * nsym * 100, np.float64)
+    lib().orc_fwd_chain_f64(symp, n, nsym, fcw_fm, tapp, nt, fcw, scale, ptr(out, f64p))
+    return out.view(np.complex128)
 
 
 def recc_decode(blob) -> ReccResult:
