@@ -62,7 +62,6 @@ extern "C" int amps_fwd_create(const amps_fwd_params *p, amps_fwd **out) {
     h->fp.fcw_fm = (uint32_t)(uint64_t)std::llround(p->max_deviation / p->symrate * 4294967296.0);
     std::vector<float> cic;
     cic3_taps(kD1, cic);
-    for (size_t i = 0; i < cic.size(); ++i) h->fp.G[i] = 25.0f * cic[i];
     for (int c = 0; c < h->ncar; ++c) {
         // pfb interpolator taps at the reference's 400 kS/s: firdes.low_pass(1, 400e3, 10e3, tw) (Hamming), :2172,:2227
         h->taps[c] = firdes_low_pass(1.0, 400e3, 10e3, p->lpf_transition[c], WIN_HAMMING);
@@ -72,7 +71,13 @@ extern "C" int amps_fwd_create(const amps_fwd_params *p, amps_fwd **out) {
         for (int i = 0; i < n; ++i) h->fp.taps[c][i] = h->taps[c][(size_t)i];
         const uint32_t fcw = nco_fcw(-p->carrier_freq[c], p->samp_rate);      // shift UP by carrier_freq
         h->fp.fcw_mix25[c] = (uint32_t)(25u * fcw);
-        nco_block_table(fcw, kD1, reinterpret_cast<float *>(h->fp.w[c]));
+        std::vector<float> ph(2 * 75);
+        nco_block_table(fcw, 75, ph.data());                       // e^{j phi_c(u)}, u < 75
+        for (int u = 0; u < 75; ++u) {
+            const float g = u < (int)cic.size() ? 25.0f * cic[(size_t)u] : 0.0f;
+            h->fp.C[c][u] = make_float2(g * ph[2 * (size_t)u], g * ph[2 * (size_t)u + 1]);
+        }
+        h->fp.w25[c] = make_float2(ph[50], ph[51]);
     }
     cudaError_t ce = fwd_configure_device();
     if (ce != cudaSuccess) { delete h; return set_cuda_error(ce, "fwd_configure_device"); }

@@ -115,7 +115,7 @@ cudaError_t launch_fwd_scan(const FwdScanParams &p, int ncar, cudaStream_t st) {
 struct FwdSmem {
     float2 out[2][kFwdTileSym * 100];          // two output tiles (TMA store sources)
     float2 fm[kFwdMaxCar][kFwdTileSym + 1 + kFwdMaxTap4];     // FM samples for symbols i0-1-81 .. i0+62
-    float2 a[kFwdMaxCar][4 * (kFwdTileSym + 1)];              // 400 kS/s samples for symbols i0-1 .. i0+62
+    float2 a[kFwdMaxCar][4 * (kFwdTileSym + 1) + 16];         // 400 kS/s samples for symbols i0-1 .. i0+62 (+ slack for unrolled reads)
 };
 
 size_t fwd_smem_bytes() { return sizeof(FwdSmem); }
@@ -127,6 +127,11 @@ __device__ __forceinline__ void tma_store_1d(void *gdst, const void *smem_src, u
 __device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// acc += x * c for complex x, c (cr = (-c.im, c.re)): two packed FMAs
+__device__ __forceinline__ float2 cmac(float2 x, float2 c, float2 cr, float2 acc) {
+    return fma2(splat(x.y), cr, fma2(splat(x.x), c, acc));
+}
 
 __global__ void __launch_bounds__(kFwdThreads, 2) fwd_fused_kernel(const __grid_constant__ FwdParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -155,58 +160,72 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fwd_fused_kernel(const __grid_
         }
         __syncthreads();
 
-        // ---- phase 2: x4 polyphase interpolation, one symbol (4 outputs) per thread, 64 threads per carrier
+        // ---- phase 2: x4 polyphase interpolation, one symbol (4 outputs) per thread, 64 threads per carrier;
+        //      the 400 kS/s samples are stored already rotated by the carrier's NCO: at[m] = a[m] e^{j phi_c(25 m)}
         if (t < 64 * p.ncar) {
-            const int c = t >> 6, il = t & 63;                      // symbol i0 - 1 + il
+            const int c = t >> 6, il = t & 63;                      // symbol i0 - 1 + il  (c is warp-uniform)
             const float2 *f = &sm->fm[c][il + kFwdMaxTap4];
-            const float *T = p.taps[c];
-            const int n4 = p.ntap4[c];
             float2 acc0 = make_float2(0.f, 0.f), acc1 = acc0, acc2 = acc0, acc3 = acc0;
-#pragma unroll 4
-            for (int k = 0; k < n4; ++k) {
-                const float2 x = f[-k];
-                acc0 = fma2(splat(T[4 * k + 0]), x, acc0);
-                acc1 = fma2(splat(T[4 * k + 1]), x, acc1);
-                acc2 = fma2(splat(T[4 * k + 2]), x, acc2);
-                acc3 = fma2(splat(T[4 * k + 3]), x, acc3);
-            }
+            auto arm = [&](const float *T, int n4) {
+#pragma unroll 3
+                for (int k = 0; k < n4; ++k) {
+                    const float2 x = f[-k];
+                    const float4 tk = *reinterpret_cast<const float4 *>(T + 4 * k);     // uniform: LDCU.128
+                    acc0 = fma2(splat(tk.x), x, acc0);
+                    acc1 = fma2(splat(tk.y), x, acc1);
+                    acc2 = fma2(splat(tk.z), x, acc2);
+                    acc3 = fma2(splat(tk.w), x, acc3);
+                }
+            };
+            if (c == 0) arm(p.taps[0], p.ntap4[0]);
+            else if (c == 1) arm(p.taps[1], p.ntap4[1]);
+            else arm(p.taps[2], p.ntap4[2]);
+            const uint32_t m4 = p.m_base + (uint32_t)(4 * (i0 - 1 + il));
+            const float2 W0 = sincos_phase(m4 * p.fcw_mix25[c]);
+            const float2 w25 = p.w25[c];
+            const float2 W1 = cmul(W0, w25), W2 = cmul(W1, w25), W3 = cmul(W2, w25);
             float2 *a = &sm->a[c][4 * il];
-            a[0] = acc0; a[1] = acc1; a[2] = acc2; a[3] = acc3;
+            a[0] = cmul(acc0, W0); a[1] = cmul(acc1, W1); a[2] = cmul(acc2, W2); a[3] = cmul(acc3, W3);
         }
         // the output tile we are about to fill must have left the SM (its bulk store has read it)
         if (t == 0) tma_store_wait_read1();
         __syncthreads();
 
-        // ---- phase 3: x25 CIC^3 interpolation + mixers + sum, 25 outputs per thread
-        if (t < 4 * nvalid) {
-            const int ai = t + 4;                                   // index of a[m], m = 4*i0 + t
-            const uint32_t mabs = p.m_base + (uint32_t)(4 * i0) + (uint32_t)t;
-            float2 a0[kFwdMaxCar], a1[kFwdMaxCar], a2[kFwdMaxCar];
+        // ---- phase 3: x25 CIC^3 interpolation + mixing + sum.  out[25 m + r] = scale * sum_c sum_j C_c[r + 25 j] at_c[m - j]
+        //      with C_c[u] = 25 cic[u] e^{j phi_c(u)}: thread = (output phase r, chunk of m), so the 9 complex taps sit in
+        //      registers, the three new at_c[m] are broadcast loads and the 25 lanes of a chunk store 25 adjacent samples.
+        if (t < 25 * kFwdChunks) {
+            const int r = t % 25, chunk = t / 25;
+            float2 C[kFwdMaxCar][3];
 #pragma unroll
-            for (int c = 0; c < kFwdMaxCar; ++c) {
-                if (c < p.ncar) {
-                    const float2 W = sincos_phase(mabs * p.fcw_mix25[c]);
-                    a0[c] = cmul(sm->a[c][ai], W);
-                    a1[c] = cmul(sm->a[c][ai - 1], W);
-                    a2[c] = cmul(sm->a[c][ai - 2], W);
-                } else {
-                    a0[c] = a1[c] = a2[c] = make_float2(0.f, 0.f);
-                }
-            }
-            float2 *o = &sm->out[buf][25 * t];
+            for (int c = 0; c < kFwdMaxCar; ++c)
 #pragma unroll
-            for (int r = 0; r < 25; ++r) {
+                for (int j = 0; j < 3; ++j) C[c][j] = (c < p.ncar && r + 25 * j < kNCic) ? p.C[c][r + 25 * j] : make_float2(0.f, 0.f);
+            float2 Cr[kFwdMaxCar][3];                               // (-Im, Re) of each tap: the second half of a complex MAC
+#pragma unroll
+            for (int c = 0; c < kFwdMaxCar; ++c)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) Cr[c][j] = make_float2(-C[c][j].y, C[c][j].x);
+            const int mlo = chunk * kFwdChunkLen;
+            int mhi = mlo + kFwdChunkLen;
+            if (mhi > 4 * nvalid) mhi = 4 * nvalid;
+            float2 x1[kFwdMaxCar], x2[kFwdMaxCar];
+#pragma unroll
+            for (int c = 0; c < kFwdMaxCar; ++c) { x1[c] = sm->a[c][mlo + 3]; x2[c] = sm->a[c][mlo + 2]; }
+            float2 *o = &sm->out[buf][r];
+#pragma unroll
+            for (int mm = 0; mm < kFwdChunkLen; ++mm) {
+                const int m = mlo + mm;
                 float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int c = 0; c < kFwdMaxCar; ++c) {
-                    if (c < p.ncar) {
-                        float2 b = mul2(splat(p.G[r]), a0[c]);
-                        b = fma2(splat(p.G[r + 25]), a1[c], b);
-                        if (r + 50 < kNCic) b = fma2(splat(p.G[r + 50]), a2[c], b);
-                        acc = add2(acc, cmul(b, p.w[c][r]));
-                    }
+                    const float2 x0 = sm->a[c][m + 4];
+                    acc = cmac(x0, C[c][0], Cr[c][0], acc);
+                    acc = cmac(x1[c], C[c][1], Cr[c][1], acc);
+                    acc = cmac(x2[c], C[c][2], Cr[c][2], acc);
+                    x2[c] = x1[c]; x1[c] = x0;
                 }
-                o[r] = mul2(splat(p.scale), acc);
+                if (m < mhi) o[25 * m] = mul2(splat(p.scale), acc);
             }
         }
         fence_async_smem();

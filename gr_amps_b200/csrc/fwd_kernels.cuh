@@ -9,6 +9,8 @@ constexpr int kFwdTileSym  = 63;                 // new 100 kS/s symbols per til
 constexpr int kFwdMaxTap4  = 81;                 // taps per polyphase arm (321 padded to 324)
 constexpr int kFwdHistLen  = kFwdMaxTap4 + 1;    // symbols of history a call needs from the previous one
 constexpr int kFwdThreads  = 256;
+constexpr int kFwdChunks   = 10;                 // phase 3: 25 output phases x 10 chunks of 400 kS/s samples
+constexpr int kFwdChunkLen = 26;                 // 10 x 26 >= 252
 constexpr int kFwdScanBlock = 4096;              // symbols per block of the prefix-sum kernels
 constexpr int kFwdInterp   = 100;                // 10 MS/s / 100 kS/s = 4 (reference) x 25 (CIC)
 
@@ -39,8 +41,8 @@ struct FwdParams {
     uint32_t       fcw_mix25[kFwdMaxCar];        // mixer phase step per 400 kS/s sample (25 * fcw)
     float          scale;
     int            ntap4[kFwdMaxCar];
-    float2         w[kFwdMaxCar][kD1];           // mixer phasors inside a 25-sample block
-    float          G[75];                        // 25 * CIC^3 taps
+    float2         w25[kFwdMaxCar];              // mixer phasor of one 400 kS/s step
+    float2         C[kFwdMaxCar][75];            // 25 cic[u] e^{j phi_c(u)}: CIC^3 taps carrying the mixer
     float          taps[kFwdMaxCar][4 * kFwdMaxTap4];
 };
 
