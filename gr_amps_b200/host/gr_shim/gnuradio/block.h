@@ -1,0 +1,2 @@
+#pragma once
+#include <gnuradio/sync_block.h>

@@ -1,0 +1,11 @@
+// focc.h -- same public surface as the reference's include/amps/focc.h:34
+#pragma once
+#include <amps/api.h>
+#include <gnuradio/sync_block.h>
+namespace gr { namespace amps {
+class AMPS_API focc : virtual public gr::sync_block {
+public:
+    typedef std::shared_ptr<focc> sptr;
+    static sptr make(unsigned long symrate, bool aggressive_registration);
+};
+}}

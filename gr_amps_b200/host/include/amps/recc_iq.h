@@ -1,0 +1,15 @@
+// recc_iq.h -- NEW sibling of amps.recc: complex IQ in (10 MS/s), "bursts" message port out.  It replaces
+// freq_xlating_fir_filter_ccc -> quadrature_demod_cf -> clock_recovery_mm_ff -> binary_slicer_fb -> amps.recc
+// (grc/ampsbs.grc:4656,4620,4506,4614,4602) with the fused B200 path; the blob it publishes has the same
+// layout as the one recc_impl::work publishes (lib/recc_impl.cc:126).
+#pragma once
+#include <amps/api.h>
+#include <gnuradio/sync_block.h>
+#include <complex>
+namespace gr { namespace amps {
+class AMPS_API recc_iq : virtual public gr::sync_block {
+public:
+    typedef std::shared_ptr<recc_iq> sptr;
+    static sptr make(double samp_rate, double center_freq, int device = 0);
+};
+}}

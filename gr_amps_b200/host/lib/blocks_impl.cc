@@ -1,0 +1,184 @@
+// blocks_impl.cc -- gr::amps::{focc,fvc,recc,recc_iq,recc_decode} on top of libamps_b200.
+// Same names, make() signatures, stream signatures, message ports and work() return conventions as the
+// reference (lib/*_impl.cc); the bodies are calls into the C ABI.  Errors follow the reference's style:
+// construction failures throw std::runtime_error (a flowgraph cannot start), run-time failures are logged.
+#include "blocks_impl.h"
+#include "../../csrc/proto.h"
+
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <vector>
+
+namespace gr { namespace amps {
+
+static void must(int status, const char *what) {
+    if (status != AMPS_OK) throw std::runtime_error(std::string(what) + ": " + amps_b200_last_error());
+}
+static void warn(int status, const char *what) {
+    if (status != AMPS_OK) std::fprintf(stderr, "gr-amps(b200) %s: %s\n", what, amps_b200_last_error());
+}
+
+// ------------------------------------------------------------------ focc (lib/focc_impl.cc)
+focc::sptr focc::make(unsigned long symrate, bool aggressive_registration) {
+    return gnuradio::get_initial_sptr(new focc_impl(symrate, aggressive_registration));
+}
+focc_impl::focc_impl(unsigned long symrate, bool aggressive_registration)
+    : gr::sync_block("focc", gr::io_signature::make(0, 0, 0), gr::io_signature::make(1, 1, sizeof(unsigned char))), d_h(NULL) {
+    must(amps_focc_create(symrate, aggressive_registration ? 1 : 0, 0, &d_h), "focc");
+    message_port_register_in(pmt::mp("focc_words"));                                   // lib/focc_impl.cc:127-130
+    set_msg_handler(pmt::mp("focc_words"), [this](pmt::pmt_t m) { this->focc_words_message(m); });
+}
+focc_impl::~focc_impl() { amps_focc_destroy(d_h); }
+void focc_impl::focc_words_message(pmt::pmt_t msg) {                                   // lib/focc_impl.cc:521-563
+    if (!pmt::is_tuple(msg) || pmt::length(msg) < 3) return;
+    const long stream = pmt::to_long(pmt::tuple_ref(msg, 0));
+    const long nwords = pmt::to_long(pmt::tuple_ref(msg, 1));
+    std::vector<uint8_t> w((size_t)28 * (size_t)nwords);
+    for (long i = 0; i < nwords; i++) {
+        pmt::pmt_t blob = pmt::tuple_ref(msg, 2 + (size_t)i);
+        if (pmt::blob_length(blob) != 28) return;
+        std::memcpy(&w[(size_t)28 * (size_t)i], pmt::blob_data(blob), 28);
+    }
+    warn(amps_focc_push_words(d_h, stream, w.data(), nwords), "focc_words");
+}
+int focc_impl::work(int noutput_items, gr_vector_const_void_star &, gr_vector_void_star &output_items) {
+    int produced = 0;
+    warn(amps_focc_work(d_h, static_cast<uint8_t *>(output_items[0]), noutput_items, &produced), "focc work");
+    return produced;      // <= one burst, possibly 0, -1 (WORK_DONE) when noutput_items < 1 (lib/focc_impl.cc:590-593,630-632)
+}
+
+// ------------------------------------------------------------------ fvc (lib/fvc_impl.cc)
+fvc::sptr fvc::make(unsigned long symrate) { return gnuradio::get_initial_sptr(new fvc_impl(symrate)); }
+fvc_impl::fvc_impl(unsigned long symrate)
+    : gr::sync_block("fvc", gr::io_signature::make(0, 0, 0), gr::io_signature::make(1, 1, sizeof(unsigned char))), d_h(NULL) {
+    must(amps_fvc_create(symrate, 0, &d_h), "fvc");
+    message_port_register_in(pmt::mp("fvc_words"));                                    // lib/fvc_impl.cc:62-66
+    set_msg_handler(pmt::mp("fvc_words"), [this](pmt::pmt_t m) { this->fvc_words_message(m); });
+    message_port_register_out(pmt::mp("command_out"));
+}
+fvc_impl::~fvc_impl() { amps_fvc_destroy(d_h); }
+void fvc_impl::fvc_words_message(pmt::pmt_t msg) {                                     // lib/fvc_impl.cc:109-143
+    if (!pmt::is_tuple(msg) || pmt::length(msg) < 2) return;
+    const size_t len = pmt::length(msg);
+    const long nwords = pmt::to_long(pmt::tuple_ref(msg, 0));
+    std::vector<uint8_t> w((size_t)28 * (size_t)nwords);
+    for (long i = 0; i < nwords; i++) std::memcpy(&w[(size_t)28 * (size_t)i], pmt::blob_data(pmt::tuple_ref(msg, 1 + (size_t)i)), 28);
+    const bool has_timer = len > (size_t)(1 + nwords);
+    const uint64_t timer = has_timer ? pmt::to_uint64(pmt::tuple_ref(msg, 1 + (size_t)nwords)) : 0;
+    warn(amps_fvc_push_words(d_h, w.data(), nwords, has_timer ? 1 : 0, timer), "fvc_words");
+}
+int fvc_impl::work(int noutput_items, gr_vector_const_void_star &, gr_vector_void_star &output_items) {
+    int produced = 0, off = 0;
+    warn(amps_fvc_work(d_h, static_cast<uint8_t *>(output_items[0]), noutput_items, &produced, &off), "fvc work");
+    if (off) {                                                                          // lib/fvc_impl.cc:163-171
+        const char *m = "fvc off";
+        message_port_pub(pmt::mp("command_out"), pmt::cons(pmt::make_dict(), pmt::init_u8vector(std::strlen(m), (const uint8_t *)m)));
+    }
+    return produced;
+}
+
+// ------------------------------------------------------------------ recc (lib/recc_impl.cc)
+recc::sptr recc::make() { return gnuradio::get_initial_sptr(new recc_impl()); }
+recc_impl::recc_impl()
+    : gr::sync_block("recc", gr::io_signature::make(1, 1, sizeof(unsigned char)), gr::io_signature::make(0, 0, 0)), d_h(NULL) {
+    must(amps_recc_create(0, &d_h), "recc");
+    message_port_register_out(pmt::mp("bursts"));                                      // lib/recc_impl.cc:82
+}
+recc_impl::~recc_impl() { amps_recc_destroy(d_h); }
+void recc_impl::on_blob(const uint8_t *blob, void *self) {
+    static_cast<recc_impl *>(self)->message_port_pub(pmt::mp("bursts"), pmt::mp(blob, AMPS_RECC_CAPTURE_SYMS));   // :126
+}
+int recc_impl::work(int noutput_items, gr_vector_const_void_star &input_items, gr_vector_void_star &) {
+    if (noutput_items < 1) return 0;                                                   // :98-101
+    warn(amps_recc_work(d_h, static_cast<const uint8_t *>(input_items[0]), noutput_items, &recc_impl::on_blob, this), "recc work");
+    consume_each(noutput_items);                                                       // :113
+    return 0;                                                                          // :144
+}
+
+// ------------------------------------------------------------------ recc_iq (new sibling block)
+recc_iq::sptr recc_iq::make(double samp_rate, double center_freq, int device) {
+    return gnuradio::get_initial_sptr(new recc_iq_impl(samp_rate, center_freq, device));
+}
+recc_iq_impl::recc_iq_impl(double samp_rate, double center_freq, int device)
+    : gr::sync_block("recc_iq", gr::io_signature::make(1, 1, sizeof(std::complex<float>)), gr::io_signature::make(0, 0, 0)), d_h(NULL) {
+    amps_recc_iq_params p;
+    std::memset(&p, 0, sizeof p);
+    p.samp_rate = samp_rate; p.center_freq = center_freq; p.device = device;
+    p.max_samples = 1u << 22;                      // the scheduler never hands a block more than this at once
+    must(amps_recc_iq_create(&p, &d_h), "recc_iq");
+    message_port_register_out(pmt::mp("bursts"));
+}
+recc_iq_impl::~recc_iq_impl() { amps_recc_iq_destroy(d_h); }
+void recc_iq_impl::on_burst(const amps_burst *b, void *self) {
+    static_cast<recc_iq_impl *>(self)->message_port_pub(pmt::mp("bursts"), pmt::mp(b->symbols, AMPS_RECC_CAPTURE_SYMS));
+}
+int recc_iq_impl::work(int noutput_items, gr_vector_const_void_star &input_items, gr_vector_void_star &) {
+    if (noutput_items < 1) return 0;
+    // gr_complex is std::complex<float>: interleaved re, im -- exactly what the ABI takes
+    warn(amps_recc_iq_work(d_h, static_cast<const float *>(input_items[0]), (size_t)noutput_items, &recc_iq_impl::on_burst, this), "recc_iq work");
+    return noutput_items;
+}
+
+// ------------------------------------------------------------------ recc_decode (lib/recc_decode_impl.cc)
+recc_decode::sptr recc_decode::make() { return gnuradio::get_initial_sptr(new recc_decode_impl()); }
+recc_decode_impl::recc_decode_impl()
+    : gr::block("recc_decode", gr::io_signature::make(0, 0, 0), gr::io_signature::make(0, 0, 0)), d_h(NULL) {
+    must(amps_recc_decode_create(0, &d_h), "recc_decode");
+    message_port_register_in(pmt::mp("bursts"));                                       // lib/recc_decode_impl.cc:38-46
+    set_msg_handler(pmt::mp("bursts"), [this](pmt::pmt_t m) { this->bursts_message(m); });
+    message_port_register_out(pmt::mp("focc_words"));
+    message_port_register_out(pmt::mp("fvc_words"));
+    message_port_register_out(pmt::mp("audio_mute"));
+    message_port_register_out(pmt::mp("fvc_mute"));
+    message_port_register_out(pmt::mp("command_out"));
+}
+recc_decode_impl::~recc_decode_impl() { amps_recc_decode_destroy(d_h); }
+
+void recc_decode_impl::bursts_message(pmt::pmt_t msg) {                                // lib/recc_decode_impl.cc:81-169
+    if (!pmt::is_blob(msg) || pmt::blob_length(msg) < AMPS_RECC_CAPTURE_SYMS) return;
+    amps_recc_words w;
+    if (amps_recc_decode_burst(d_h, static_cast<const uint8_t *>(pmt::blob_data(msg)), &w) != AMPS_OK) {
+        warn(AMPS_E_CUDA, "recc_decode");
+        return;
+    }
+    switch (w.kind) {
+        case AMPS_MSG_INVALID_A: return;                                               // :108-111
+        case AMPS_MSG_E0_DROPPED: return;                                              // :113-116
+        case AMPS_MSG_PAGE_RESPONSE: handle_response(w); return;                       // :121
+        case AMPS_MSG_REGISTRATION: handle_registration(w); return;                    // :123-138
+        case AMPS_MSG_ORIGINATION: handle_origination(w); return;                      // :139-165
+        default: return;                                                               // unknown / bad NAWC: logged and dropped
+    }
+}
+
+static pmt::pmt_t word_blob(const ::amps::Word28 &w) { return pmt::mp(w.data(), 28); }
+
+void recc_decode_impl::handle_registration(const amps_recc_words &w) {                 // :181-190: order confirmation (audit, order 7)
+    const ::amps::Word28 w1 = ::amps::focc_word1(true, GLOBAL_DCC_SHORT, w.MIN1);
+    const ::amps::Word28 w2 = ::amps::focc_word2_general(w.MIN2, 0, 0, 7);
+    message_port_pub(pmt::mp("focc_words"), pmt::make_tuple(pmt::from_long(STREAM_BOTH), pmt::from_long(2), word_blob(w1), word_blob(w2)));
+}
+
+void recc_decode_impl::handle_response(const amps_recc_words &w) {                     // :195-220: page response -> voice channel 355 + alert
+    const ::amps::Word28 w1 = ::amps::focc_word1(true, GLOBAL_DCC_SHORT, w.MIN1);
+    const ::amps::Word28 w2 = ::amps::focc_word2_voice_channel(GLOBAL_SCC, w.MIN2, 0, 355);
+    message_port_pub(pmt::mp("focc_words"), pmt::make_tuple(pmt::from_long(STREAM_BOTH), pmt::from_long(2), word_blob(w1), word_blob(w2)));
+    const ::amps::Word28 fv = ::amps::fvc_word1_general(GLOBAL_SCC, 0, 0, 1);
+    message_port_pub(pmt::mp("fvc_words"), pmt::make_tuple(pmt::from_long(1), word_blob(fv), pmt::from_uint64(35)));
+    message_port_pub(pmt::mp("fvc_mute"), pmt::from_bool(false));
+    message_port_pub(pmt::mp("audio_mute"), pmt::from_bool(true));
+}
+
+void recc_decode_impl::handle_origination(const amps_recc_words &w) {                  // :234-272: initial voice designation, channel 356
+    const ::amps::Word28 w1 = ::amps::focc_word1(true, GLOBAL_DCC_SHORT, w.MIN1);
+    const ::amps::Word28 w2 = (w.dialed[0] == '0') ? ::amps::focc_word2_general(w.MIN2, 0, 0, 9)
+                                                    : ::amps::focc_word2_voice_channel(GLOBAL_SCC, w.MIN2, 0, 356);
+    message_port_pub(pmt::mp("focc_words"), pmt::make_tuple(pmt::from_long(STREAM_BOTH), pmt::from_long(2), word_blob(w1), word_blob(w2)));
+    message_port_pub(pmt::mp("fvc_mute"), pmt::from_bool(true));
+    message_port_pub(pmt::mp("audio_mute"), pmt::from_bool(false));
+    const std::string m = std::string("page ") + w.dialed;
+    message_port_pub(pmt::mp("command_out"), pmt::cons(pmt::make_dict(), pmt::init_u8vector(m.size(), (const uint8_t *)m.data())));
+}
+
+}}  // namespace gr::amps

@@ -1,0 +1,164 @@
+// qa_blocks.cc -- C++ QA driver for the gr::amps blocks built on libamps_b200 (the reference's own
+// lib/qa_amps.cc is an empty CppUnit suite; apps/testalloc.cc is its only harness and is the model here).
+// It wires the blocks exactly as grc/ampsbs.grc:4404-4470 does (msg_connect) and drives work() the way the
+// GNU Radio scheduler would.  Results go to files / JSON lines that tests/test_host_gpu.py compares with the oracle.
+//
+//   qa_blocks focc <symrate> <aggr 0|1> <total_bytes> <seed> <out.bin>
+//   qa_blocks loop <iq.bin> <nsamples> <chunk> <focc_bytes> <out_prefix>
+#include <amps/focc.h>
+#include <amps/fvc.h>
+#include <amps/recc.h>
+#include <amps/recc_decode.h>
+#include <amps/recc_iq.h>
+
+#include <complex>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <string>
+#include <vector>
+
+using namespace gr::amps;
+
+static std::string bits28(const void *p) {
+    std::string s;
+    for (int i = 0; i < 28; i++) s += static_cast<const char *>(p)[i] ? '1' : '0';
+    return s;
+}
+
+// message sink that records everything recc_decode / fvc publish, as JSON lines
+class probe : public gr::block {
+public:
+    std::vector<std::string> lines;
+    probe() : gr::block("probe", gr::io_signature::make(0, 0, 0), gr::io_signature::make(0, 0, 0)) {
+        const char *ports[] = {"focc_words", "fvc_words", "audio_mute", "fvc_mute", "command_out", "bursts"};
+        for (size_t i = 0; i < sizeof(ports) / sizeof(ports[0]); i++) {
+            const std::string port = ports[i];
+            message_port_register_in(pmt::mp(port));
+            set_msg_handler(pmt::mp(port), [this, port](pmt::pmt_t m) { this->on(port, m); });
+        }
+    }
+    void on(const std::string &port, pmt::pmt_t m) {
+        char buf[256];
+        std::string js = "{\"port\": \"" + port + "\"";
+        if (port == "focc_words") {
+            const long n = pmt::to_long(pmt::tuple_ref(m, 1));
+            std::snprintf(buf, sizeof buf, ", \"stream\": %ld, \"n\": %ld, \"words\": [", pmt::to_long(pmt::tuple_ref(m, 0)), n);
+            js += buf;
+            for (long i = 0; i < n; i++) js += std::string(i ? ", " : "") + "\"" + bits28(pmt::blob_data(pmt::tuple_ref(m, 2 + (size_t)i))) + "\"";
+            js += "]";
+        } else if (port == "fvc_words") {
+            const long n = pmt::to_long(pmt::tuple_ref(m, 0));
+            js += ", \"words\": [";
+            for (long i = 0; i < n; i++) js += std::string(i ? ", " : "") + "\"" + bits28(pmt::blob_data(pmt::tuple_ref(m, 1 + (size_t)i))) + "\"";
+            js += "]";
+            if (pmt::length(m) > (size_t)(1 + n)) {
+                std::snprintf(buf, sizeof buf, ", \"timer\": %llu", (unsigned long long)pmt::to_uint64(pmt::tuple_ref(m, 1 + (size_t)n)));
+                js += buf;
+            }
+        } else if (port == "audio_mute" || port == "fvc_mute") {
+            js += std::string(", \"value\": ") + (pmt::to_bool(m) ? "true" : "false");
+        } else if (port == "command_out") {
+            size_t n = 0;
+            const uint8_t *d = pmt::u8vector_elements(pmt::cdr(m), n);
+            js += ", \"text\": \"" + std::string(reinterpret_cast<const char *>(d), n) + "\"";
+        } else if (port == "bursts") {
+            std::snprintf(buf, sizeof buf, ", \"len\": %zu", pmt::blob_length(m));
+            js += buf;
+        }
+        lines.push_back(js + "}");
+    }
+};
+
+static int run_focc(int argc, char **argv) {
+    if (argc < 7) return 2;
+    const unsigned long symrate = std::strtoul(argv[2], NULL, 10);
+    const bool aggr = std::atoi(argv[3]) != 0;
+    const size_t total = std::strtoull(argv[4], NULL, 10);
+    unsigned long long lcg = std::strtoull(argv[5], NULL, 10);
+    focc::sptr blk = focc::make(symrate, aggr);
+    std::vector<unsigned char> out, buf(1 << 16);
+    gr_vector_const_void_star in;
+    gr_vector_void_star outs(1);
+    while (out.size() < total) {
+        lcg = lcg * 6364136223846793005ull + 1442695040888963407ull;
+        int n = 1 + (int)((lcg >> 33) % 9000);
+        if ((size_t)n > total - out.size()) n = (int)(total - out.size());
+        outs[0] = buf.data();
+        const int r = blk->work(n, in, outs);              // apps/testalloc.cc:57: retval may be short
+        if (r < 0) return 3;
+        out.insert(out.end(), buf.begin(), buf.begin() + r);
+    }
+    std::ofstream(argv[6], std::ios::binary).write(reinterpret_cast<const char *>(out.data()), (std::streamsize)out.size());
+    std::printf("{\"bytes\": %zu}\n", out.size());
+    return 0;
+}
+
+static int run_loop(int argc, char **argv) {
+    if (argc < 7) return 2;
+    const size_t nsamples = std::strtoull(argv[3], NULL, 10);
+    const size_t chunk = std::strtoull(argv[4], NULL, 10);
+    const size_t focc_bytes = std::strtoull(argv[5], NULL, 10);
+    const std::string prefix = argv[6];
+    std::vector<std::complex<float>> iq(nsamples);
+    std::ifstream f(argv[2], std::ios::binary);
+    f.read(reinterpret_cast<char *>(iq.data()), (std::streamsize)(nsamples * sizeof(std::complex<float>)));
+    if (!f) { std::fprintf(stderr, "short read of %s\n", argv[2]); return 4; }
+
+    // the message wiring of grc/ampsbs.grc:4404-4470 around the RECC/FOCC/FVC blocks
+    recc_iq::sptr rx = recc_iq::make(10e6, -160e3, 0);
+    recc_decode::sptr dec = recc_decode::make();
+    focc::sptr fo = focc::make(100000, false);
+    fvc::sptr fv = fvc::make(100000);
+    probe pr;
+    gr::msg_connect(*rx, "bursts", *dec, "bursts");
+    gr::msg_connect(*rx, "bursts", pr, "bursts");
+    gr::msg_connect(*dec, "focc_words", *fo, "focc_words");
+    gr::msg_connect(*dec, "fvc_words", *fv, "fvc_words");
+    const char *ports[] = {"focc_words", "fvc_words", "audio_mute", "fvc_mute", "command_out"};
+    for (size_t i = 0; i < 5; i++) gr::msg_connect(*dec, ports[i], pr, ports[i]);
+    gr::msg_connect(*fv, "command_out", pr, "command_out");
+
+    gr_vector_const_void_star in(1);
+    gr_vector_void_star none;
+    for (size_t pos = 0; pos < nsamples; pos += chunk) {
+        const size_t n = nsamples - pos < chunk ? nsamples - pos : chunk;
+        in[0] = &iq[pos];
+        if (rx->work((int)n, in, none) != (int)n) return 5;
+    }
+    // then let the sources run, as the scheduler would
+    std::vector<unsigned char> out, buf(1 << 16);
+    gr_vector_const_void_star noin;
+    gr_vector_void_star outs(1);
+    while (out.size() < focc_bytes) {
+        outs[0] = buf.data();
+        int want = (int)(focc_bytes - out.size() < buf.size() ? focc_bytes - out.size() : buf.size());
+        const int r = fo->work(want, noin, outs);
+        if (r < 0) return 6;
+        out.insert(out.end(), buf.begin(), buf.begin() + r);
+    }
+    std::ofstream((prefix + ".focc.bin").c_str(), std::ios::binary).write(reinterpret_cast<const char *>(out.data()), (std::streamsize)out.size());
+    std::vector<unsigned char> vout;
+    while (vout.size() < 30000) {
+        outs[0] = buf.data();
+        const int r = fv->work(4096, noin, outs);
+        if (r < 0) return 7;
+        vout.insert(vout.end(), buf.begin(), buf.begin() + r);
+    }
+    std::ofstream((prefix + ".fvc.bin").c_str(), std::ios::binary).write(reinterpret_cast<const char *>(vout.data()), (std::streamsize)vout.size());
+    for (size_t i = 0; i < pr.lines.size(); i++) std::printf("%s\n", pr.lines[i].c_str());
+    return 0;
+}
+
+int main(int argc, char **argv) {
+    if (argc < 2) { std::fprintf(stderr, "usage: qa_blocks focc|loop ...\n"); return 2; }
+    try {
+        if (!std::strcmp(argv[1], "focc")) return run_focc(argc, argv);
+        if (!std::strcmp(argv[1], "loop")) return run_loop(argc, argv);
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "qa_blocks: %s\n", e.what());
+        return 10;
+    }
+    return 2;
+}

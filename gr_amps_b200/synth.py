@@ -91,6 +91,28 @@ def origination_words(min10="2125551234", esn=0x82ABCDEF, dialed="18005551212", 
     return words
 
 
+def pad_words(words, n=7) -> list[list[int]]:
+    """A RECC capture is always 7 words long (lib/recc_impl.cc:70); shorter messages are followed by idle (all-zero) words."""
+    return list(words) + [[0] * 36 for _ in range(n - len(words))]
+
+
+def page_response_words(min10="2125551234", scm=0b0010) -> list[list[int]]:
+    """T=0 response with all-zero order fields -> recc_decode treats it as a page response (lib/recc_decode_impl.cc:121)."""
+    min1, min2 = min_to_fields(min10)
+    wa = [1] + bits_msb(1, 3) + [0, 0, 1, 0] + bits_msb(scm, 4) + bits_msb(min1, 24)
+    wb = [0] + bits_msb(0, 3) + bits_msb(0, 5) + bits_msb(0, 3) + bits_msb(0, 5) + [0, 0, 0] + bits_msb(0, 6) + bits_msb(min2, 10)
+    return pad_words([wa, wb])
+
+
+def registration_words(min10="2125551234", esn=0x82ABCDEF, scm=0b0010) -> list[list[int]]:
+    """T=1, ORDER=01101: word-C-included registration order (lib/recc_decode_impl.cc:123-138)."""
+    min1, min2 = min_to_fields(min10)
+    wa = [1] + bits_msb(2, 3) + [1, 1, 1, 0] + bits_msb(scm, 4) + bits_msb(min1, 24)
+    wb = [0] + bits_msb(1, 3) + bits_msb(0, 5) + bits_msb(0, 3) + bits_msb(0xd, 5) + [0, 0, 0] + bits_msb(0, 6) + bits_msb(min2, 10)
+    wc = [0] + bits_msb(0, 3) + bits_msb(esn, 32)
+    return pad_words([wa, wb, wc])
+
+
 def recc_message_bits(words36, dcc7=(0, 0, 0, 0, 0, 0, 0)) -> np.ndarray:
     bits = [1, 0] * 15 + WORD_SYNC + list(dcc7)
     for w in words36:
@@ -131,6 +153,12 @@ def fm_burst(halfsyms: np.ndarray, n_total: int, lead: int, samp_rate=10e6, cent
         x.real += s * rng.standard_normal(n_total, dtype=np.float32)
         x.imag += s * rng.standard_normal(n_total, dtype=np.float32)
     return x
+
+
+def burst_period(words36, n_total=55 * 38400, lead=20000, snr_db=None, seed=0xA3B5, center=-160e3):
+    """One period carrying an arbitrary 7-word RECC message."""
+    hs = manchester(recc_message_bits(words36))
+    return fm_burst(hs, n_total, lead, center=center, snr_db=snr_db, seed=seed), hs
 
 
 def config2_period(n_total=1 << 21, lead=20000, snr_db=None, seed=0xA3B5, center=-160e3, **kw):

@@ -109,6 +109,17 @@ typedef struct {
 } orc_recc_result;
 size_t orc_manchester_decode(const uint8_t *src, uint8_t *dst, size_t dstlen); /* lib/utils.cc:27-59 */
 void   orc_recc_decode(const uint8_t blob[3374], orc_recc_result *out);        /* lib/recc_decode_impl.cc:81-169 */
+typedef struct {
+    int32_t  n_focc;             /* words in the focc_words tuple (0 = none published) */
+    int64_t  focc_stream;
+    uint8_t  focc_words[2][28];
+    int32_t  has_fvc;            /* fvc_words tuple published */
+    uint8_t  fvc_word[28];
+    uint64_t fvc_timer;
+    int32_t  fvc_mute, audio_mute;   /* -1 = not published, else the bool */
+    char     command[48];        /* command_out PDU text, "" = none */
+} orc_recc_actions;
+void   orc_recc_actions_for(const orc_recc_result *r, orc_recc_actions *a);     /* lib/recc_decode_impl.cc:181-272 */
 
 /* ---------------------------------------------------------------- DSP chain (dsp_chain.c) */
 /* gr::filter::firdes::low_pass (EXTERNAL). window: 0 hamming, 1 hann, 2 blackman.

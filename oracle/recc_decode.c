@@ -92,3 +92,31 @@ void orc_recc_decode(const uint8_t blob[3374], orc_recc_result *r) {
         r->kind = 5;
     }
 }
+
+/* What recc_decode_impl publishes for a decoded burst: restates handle_registration (:181-190),
+ * handle_response (:195-220) and handle_origination (:234-272) of lib/recc_decode_impl.cc.  stream is always
+ * STREAM_BOTH (the reference overrides its own A/B choice, :247). */
+void orc_recc_actions_for(const orc_recc_result *r, orc_recc_actions *a) {
+    memset(a, 0, sizeof *a);
+    a->fvc_mute = -1; a->audio_mute = -1;
+    if (r->kind == 3) {
+        a->n_focc = 2; a->focc_stream = 3;
+        orc_focc_word1(a->focc_words[0], 1, 0, r->MIN1);
+        orc_focc_word2_general(a->focc_words[1], r->MIN2, 0, 0, 7);
+    } else if (r->kind == 2) {
+        a->n_focc = 2; a->focc_stream = 3;
+        orc_focc_word1(a->focc_words[0], 1, 0, r->MIN1);
+        orc_focc_word2_voice_channel(a->focc_words[1], 1, r->MIN2, 0, 355);
+        a->has_fvc = 1; a->fvc_timer = 35;
+        orc_fvc_word1_general(a->fvc_word, 1, 0, 0, 1);
+        a->fvc_mute = 0; a->audio_mute = 1;
+    } else if (r->kind == 4) {
+        a->n_focc = 2; a->focc_stream = 3;
+        orc_focc_word1(a->focc_words[0], 1, 0, r->MIN1);
+        if (r->dialed[0] == '0') orc_focc_word2_general(a->focc_words[1], r->MIN2, 0, 0, 9);
+        else orc_focc_word2_voice_channel(a->focc_words[1], 1, r->MIN2, 0, 356);
+        a->fvc_mute = 1; a->audio_mute = 0;
+        strcpy(a->command, "page ");
+        strncat(a->command, r->dialed, sizeof a->command - 6);
+    }
+}

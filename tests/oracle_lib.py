@@ -38,6 +38,12 @@ class ReccResult(C.Structure):
     ]
 
 
+class ReccActions(C.Structure):
+    _fields_ = [("n_focc", C.c_int32), ("focc_stream", C.c_int64), ("focc_words", (C.c_uint8 * 28) * 2),
+                ("has_fvc", C.c_int32), ("fvc_word", C.c_uint8 * 28), ("fvc_timer", C.c_uint64),
+                ("fvc_mute", C.c_int32), ("audio_mute", C.c_int32), ("command", C.c_char * 48)]
+
+
 class Burst(C.Structure):
     _fields_ = [("d_index", C.c_uint64), ("corr", C.c_float), ("symbols", C.c_uint8 * 3374)]
 
@@ -85,6 +91,7 @@ def lib() -> C.CDLL:
     L.orc_manchester_decode.argtypes = [u8p, u8p, C.c_size_t]
     L.orc_manchester_decode.restype = C.c_size_t
     L.orc_recc_decode.argtypes = [u8p, C.POINTER(ReccResult)]
+    L.orc_recc_actions_for.argtypes = [C.POINTER(ReccResult), C.POINTER(ReccActions)]
     L.orc_firdes_low_pass.argtypes = [C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, f32p, C.c_int]
     L.orc_nco_fcw.argtypes = [C.c_double, C.c_double]
     L.orc_nco_fcw.restype = C.c_uint32
@@ -209,6 +216,12 @@ def cpu_baseline_run(x: np.ndarray, threads: int, reps: int, center=-160e3, fs=1
     nb = C.c_int(0)
     sec = lib().orc_cpu_baseline_run(ptr(iq, f32p), n, fcw, ptr(taps, f32p), len(taps), threads, reps, C.byref(nb))
     return sec, nb.value
+
+
+def recc_actions(result: ReccResult) -> ReccActions:
+    a = ReccActions()
+    lib().orc_recc_actions_for(C.byref(result), C.byref(a))
+    return a
 
 
 def fwd_chain_f64(syms, carrier_freq=(0.0, 60e3, 90e3), lpf_transition=(5e3, 3e3, 3e3), scale=0.5,

@@ -1,0 +1,93 @@
+"""The C++ host layer (gr::amps::{focc,fvc,recc_iq,recc_decode} over the C ABI, gr_amps_b200/host/) driven by
+its C++ QA program, compared with the oracle.  The `loop` scenario is the reference's closed loop
+(grc/ampsbs.grc:4404-4470): IQ -> recc_iq -> bursts -> recc_decode -> focc_words / fvc_words -> focc / fvc."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from gr_amps_b200 import synth
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+QA = os.path.join(ROOT, "gr_amps_b200", "host", "qa_blocks")
+
+
+def run(args, cwd):
+    return subprocess.run([QA] + [str(a) for a in args], cwd=cwd, check=True, capture_output=True, text=True, timeout=600).stdout
+
+
+@pytest.mark.parametrize("symrate,aggr,seed", [(100000, 0, 1), (200000, 1, 7)])
+def test_focc_block_work_schedule(oracle, tmp_path, symrate, aggr, seed):
+    total = 500_000
+    out = tmp_path / "focc.bin"
+    run(["focc", symrate, aggr, total, seed, out], tmp_path)
+    got = np.fromfile(out, np.uint8)
+    # same LCG request schedule against the oracle block
+    o = oracle.Focc(symrate, bool(aggr))
+    lcg, ref = seed, bytearray()
+    while len(ref) < total:
+        lcg = (lcg * 6364136223846793005 + 1442695040888963407) % (1 << 64)
+        n = min(1 + (lcg >> 33) % 9000, total - len(ref))
+        r, b = o.work(n)
+        ref += b.tobytes()
+    assert np.array_equal(got, np.frombuffer(bytes(ref), np.uint8))
+
+
+def test_closed_loop_flowgraph(oracle, tmp_path):
+    period = 55 * 38400
+    msgs = [synth.origination_words(min10="2125550101", dialed="4155551212"),
+            synth.page_response_words(min10="2125550102"),
+            synth.registration_words(min10="2125550103"),
+            synth.origination_words(min10="2125550104", dialed="0")]
+    parts = [synth.burst_period(w, n_total=period, snr_db=20.0, seed=40 + i)[0] for i, w in enumerate(msgs)]
+    x = np.concatenate(parts + [np.zeros(38400, np.complex64)])
+    iq = tmp_path / "iq.bin"
+    x.tofile(iq)
+    focc_bytes = 3 * 19 * 4630
+    out = run(["loop", iq, len(x), 262144, focc_bytes, tmp_path / "loop"], tmp_path)
+    lines = [json.loads(l) for l in out.splitlines() if l.startswith("{")]
+
+    # oracle side of the same loop
+    _, d = oracle.rx_chain_f32(x)
+    bursts = oracle.rx_detect(d)
+    assert len(bursts) == 4
+    expect, ofocc, ofvc = [], oracle.Focc(100000, False), oracle.Fvc(100000)
+    bits = lambda w: "".join(str(int(v)) for v in w)
+    for _, _, blob in bursts:
+        r = oracle.recc_decode(blob)
+        a = oracle.recc_actions(r)
+        if a.n_focc:
+            words = [bits(a.focc_words[i]) for i in range(a.n_focc)]
+            expect.append({"port": "focc_words", "stream": a.focc_stream, "n": a.n_focc, "words": words})
+            ofocc.push_words(a.focc_stream, np.array([[int(c) for c in w] for w in words], np.uint8))
+        if a.has_fvc:
+            expect.append({"port": "fvc_words", "words": [bits(a.fvc_word)], "timer": a.fvc_timer})
+            ofvc.push_words(np.array(list(a.fvc_word), np.uint8), timer=a.fvc_timer)
+        if a.fvc_mute >= 0:
+            expect.append({"port": "fvc_mute", "value": bool(a.fvc_mute)})
+        if a.audio_mute >= 0:
+            expect.append({"port": "audio_mute", "value": bool(a.audio_mute)})
+        if a.command:
+            expect.append({"port": "command_out", "text": a.command.decode()})
+        expect.append({"port": "bursts", "len": 3374})
+    assert lines == expect
+    kinds = [oracle.recc_decode(b[2]).kind for b in bursts]
+    assert kinds == [4, 2, 3, 4]
+    assert [l["text"] for l in lines if l["port"] == "command_out"] == ["page 4155551212", "page 0"]
+
+    got = np.fromfile(str(tmp_path / "loop.focc.bin"), np.uint8)
+    assert np.array_equal(got, ofocc.generate(focc_bytes, chunk=65536))
+    # the four injected word pairs occupy the first filler slots of the superframe, two frames each
+    plain = oracle.Focc(100000, False).generate(focc_bytes, chunk=65536)
+    fb = 4630
+    changed = sorted(set(np.nonzero(got != plain)[0] // fb))
+    assert changed == [4, 5, 6, 7, 8, 9, 10, 11]
+    gv = np.fromfile(str(tmp_path / "loop.fvc.bin"), np.uint8)
+    ref = bytearray()
+    while len(ref) < 30000:
+        r, b, _ = ofvc.work(4096)
+        ref += b.tobytes()
+    assert np.array_equal(gv, np.frombuffer(bytes(ref), np.uint8)[:len(gv)])
