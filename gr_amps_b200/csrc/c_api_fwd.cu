@@ -60,8 +60,9 @@ extern "C" int amps_fwd_create(const amps_fwd_params *p, amps_fwd **out) {
     h->fp.scale = p->out_scale;
     // frequency_modulator_fc sensitivity 2 pi max_deviation / symrate (grc/ampsbs.grc:614) as a 32-bit phase step
     h->fp.fcw_fm = (uint32_t)(uint64_t)std::llround(p->max_deviation / p->symrate * 4294967296.0);
-    std::vector<float> cic;
-    cic3_taps(kD1, cic);
+    std::vector<float> cic5;                                       // boxcar5^3 / 125, 13 taps
+    cic3_taps(5, cic5);
+    for (int u = 0; u < 15; ++u) h->fp.G2[u] = u < (int)cic5.size() ? p->out_scale * 5.0f * cic5[(size_t)u] : 0.0f;
     for (int c = 0; c < h->ncar; ++c) {
         // pfb interpolator taps at the reference's 400 kS/s: firdes.low_pass(1, 400e3, 10e3, tw) (Hamming), :2172,:2227
         h->taps[c] = firdes_low_pass(1.0, 400e3, 10e3, p->lpf_transition[c], WIN_HAMMING);
@@ -73,9 +74,9 @@ extern "C" int amps_fwd_create(const amps_fwd_params *p, amps_fwd **out) {
         h->fp.fcw_mix25[c] = (uint32_t)(25u * fcw);
         std::vector<float> ph(2 * 75);
         nco_block_table(fcw, 75, ph.data());                       // e^{j phi_c(u)}, u < 75
-        for (int u = 0; u < 75; ++u) {
-            const float g = u < (int)cic.size() ? 25.0f * cic[(size_t)u] : 0.0f;
-            h->fp.C[c][u] = make_float2(g * ph[2 * (size_t)u], g * ph[2 * (size_t)u + 1]);
+        for (int u = 0; u < 15; ++u) {                              // tap u of the 2 MS/s stage sits 5 u output samples later
+            const float g = u < (int)cic5.size() ? 5.0f * cic5[(size_t)u] : 0.0f;
+            h->fp.C1[c][u] = make_float2(g * ph[2 * (size_t)(5 * u)], g * ph[2 * (size_t)(5 * u) + 1]);
         }
         h->fp.w25[c] = make_float2(ph[50], ph[51]);
     }
@@ -158,7 +159,7 @@ extern "C" int amps_fwd_submit_dev(amps_fwd *h, const void *const *d_sym, size_t
     p.nsym = (uint32_t)nsym;
     p.m_base = (uint32_t)(h->sym_total * 4u);
     const uint32_t ntiles = ((uint32_t)nsym + kFwdTileSym - 1) / kFwdTileSym;
-    uint32_t grid = 2u * (uint32_t)h->sm_count;
+    uint32_t grid = 3u * (uint32_t)h->sm_count;                  // 70 KB smem, 60 registers: 3 CTAs per SM
     if (grid > ntiles) grid = ntiles;
     CKL(launch_fwd_fused(p, (int)grid, st));
     h->hist_cur = nxt;

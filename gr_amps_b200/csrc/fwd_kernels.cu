@@ -4,8 +4,8 @@
 //   half-symbol bytes (+1/-1/0) @100 kS/s        char_to_float                 (:1159-1252)
 //   -> S[i] = running sum, fm[i] = e^{j 2 pi S[i] fcw_fm / 2^32}   frequency_modulator_fc  (:574-659)
 //   -> x4 polyphase interpolation, the reference's own firdes taps (193 / 321) @400 kS/s  (:2120-2229)
-//   -> x25 CIC^3 interpolation to 10 MS/s (ours: the reference stops at 400 kS/s)
-//   -> mix to the carrier offset, sum the carriers, x0.5                     (:817-942,1006-1056,1355-1405)
+//   -> x5 CIC^3 to 2 MS/s with the mixer folded in, carriers summed          (:817-942,1006-1056; the x25 is ours:
+//   -> x5 CIC^3 to 10 MS/s (shared), x0.5                                     the reference stops at 400 kS/s) (:1355-1405)
 // One fused kernel writes 8 bytes per output sample and reads ~0.05: it is HBM-WRITE bound.  Output tiles
 // are assembled in shared memory and leave through TMA bulk stores (cp.async.bulk.global.shared::cta).
 //
@@ -27,10 +27,18 @@ __global__ void __launch_bounds__(256) fwd_scan_local_kernel(FwdScanParams p) {
     const uint32_t base = b * (uint32_t)kFwdScanBlock + (uint32_t)t * 16u;
     int v[16];
     int run = 0;
+    // 16 symbols per thread: one 128-bit load when the run is fully inside the stream (base is 16-byte aligned)
+    uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+    if (base + 16u <= p.nsym && (reinterpret_cast<uintptr_t>(sym) & 15u) == 0) {
+        raw = *reinterpret_cast<const uint4 *>(sym + base);
+    } else {
+        uint8_t *rb = reinterpret_cast<uint8_t *>(&raw);
+        for (int k = 0; k < 16; ++k) rb[k] = base + k < p.nsym ? sym[base + k] : 0;
+    }
+    const uint32_t words[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-        const uint32_t i = base + k;
-        const int s = i < p.nsym ? (int)(int8_t)sym[i] : 0;      // bytes are signed: 0x01 = +1, 0xFF = -1
+        const int s = (int)(int8_t)((words[k >> 2] >> (8 * (k & 3))) & 0xffu);      // bytes are signed: 0x01 = +1, 0xFF = -1
         run += s;
         v[k] = run;
     }
@@ -45,10 +53,16 @@ __global__ void __launch_bounds__(256) fwd_scan_local_kernel(FwdScanParams p) {
     int woff = 0;
     for (int w = 0; w < (t >> 5); ++w) woff += warp_tot[w];
     const int excl = woff + incl - run;
+    if (base + 16u <= p.nsym) {
+        int4 *dst = reinterpret_cast<int4 *>(p.sloc[c] + base);      // cudaMalloc'ed, base multiple of 16: aligned
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        const uint32_t i = base + k;
-        if (i < p.nsym) p.sloc[c][i] = excl + v[k];
+        for (int k = 0; k < 4; ++k) dst[k] = make_int4(excl + v[4 * k], excl + v[4 * k + 1], excl + v[4 * k + 2], excl + v[4 * k + 3]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const uint32_t i = base + k;
+            if (i < p.nsym) p.sloc[c][i] = excl + v[k];
+        }
     }
     if (t == 255) p.btot[c][b] = woff + incl;
 }
@@ -113,7 +127,8 @@ cudaError_t launch_fwd_scan(const FwdScanParams &p, int ncar, cudaStream_t st) {
 // fused modulator
 // ---------------------------------------------------------------------------------------------
 struct FwdSmem {
-    float2 out[2][kFwdTileSym * 100];          // two output tiles (TMA store sources)
+    float2 out[kFwdTileSym * 100];             // output tile (TMA store source); its store overlaps phases 1-3a of the next tile
+    float2 B[5 * (4 * kFwdTileSym + 1) + 3];   // 2 MS/s samples (carriers mixed and summed) for m = m0-1 .. m0+251
     float2 fm[kFwdMaxCar][kFwdTileSym + 1 + kFwdMaxTap4];     // FM samples for symbols i0-1-81 .. i0+62
     float2 a[kFwdMaxCar][4 * (kFwdTileSym + 1) + 16];         // 400 kS/s samples for symbols i0-1 .. i0+62 (+ slack for unrolled reads)
 };
@@ -124,7 +139,7 @@ __device__ __forceinline__ void tma_store_1d(void *gdst, const void *smem_src, u
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
-__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -133,15 +148,14 @@ __device__ __forceinline__ float2 cmac(float2 x, float2 c, float2 cr, float2 acc
     return fma2(splat(x.y), cr, fma2(splat(x.x), c, acc));
 }
 
-__global__ void __launch_bounds__(kFwdThreads, 2) fwd_fused_kernel(const __grid_constant__ FwdParams p) {
+__global__ void __launch_bounds__(kFwdThreads, 3) fwd_fused_kernel(const __grid_constant__ FwdParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     FwdSmem *sm = reinterpret_cast<FwdSmem *>(smem_raw);
     const int t = threadIdx.x;
     const uint32_t ntiles = (p.nsym + kFwdTileSym - 1) / kFwdTileSym;
     constexpr int kFmLen = kFwdTileSym + 1 + kFwdMaxTap4;          // 145
 
-    int buf = 0;
-    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long i0 = (long)tile * kFwdTileSym;                  // first new symbol of the tile
         const int nvalid = (int)((long)p.nsym - i0 < kFwdTileSym ? (long)p.nsym - i0 : kFwdTileSym);
 
@@ -187,50 +201,59 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fwd_fused_kernel(const __grid_
             float2 *a = &sm->a[c][4 * il];
             a[0] = cmul(acc0, W0); a[1] = cmul(acc1, W1); a[2] = cmul(acc2, W2); a[3] = cmul(acc3, W3);
         }
-        // the output tile we are about to fill must have left the SM (its bulk store has read it)
-        if (t == 0) tma_store_wait_read1();
         __syncthreads();
 
-        // ---- phase 3: x25 CIC^3 interpolation + mixing + sum.  out[25 m + r] = scale * sum_c sum_j C_c[r + 25 j] at_c[m - j]
-        //      with C_c[u] = 25 cic[u] e^{j phi_c(u)}: thread = (output phase r, chunk of m), so the 9 complex taps sit in
-        //      registers, the three new at_c[m] are broadcast loads and the 25 lanes of a chunk store 25 adjacent samples.
-        if (t < 25 * kFwdChunks) {
-            const int r = t % 25, chunk = t / 25;
-            float2 C[kFwdMaxCar][3];
+        // ---- phase 3a: x5 CIC^3 interpolation to 2 MS/s with the mixer folded into complex taps, carriers summed.
+        //      B[5 m + r] = sum_c sum_j C1_c[r + 5 j] at_c[m - j];  thread = one 400 kS/s sample -> 5 outputs
+        if (t < 4 * kFwdTileSym + 1) {
+            float2 acc[5];
 #pragma unroll
-            for (int c = 0; c < kFwdMaxCar; ++c)
+            for (int r = 0; r < 5; ++r) acc[r] = make_float2(0.f, 0.f);
 #pragma unroll
-                for (int j = 0; j < 3; ++j) C[c][j] = (c < p.ncar && r + 25 * j < kNCic) ? p.C[c][r + 25 * j] : make_float2(0.f, 0.f);
-            float2 Cr[kFwdMaxCar][3];                               // (-Im, Re) of each tap: the second half of a complex MAC
+            for (int c = 0; c < kFwdMaxCar; ++c) {
+                if (c < p.ncar) {
 #pragma unroll
-            for (int c = 0; c < kFwdMaxCar; ++c)
+                    for (int j = 0; j < 3; ++j) {
+                        const float2 x = sm->a[c][t + 3 - j];
+                        const float2 xr = splat(x.x), xi = splat(x.y);
 #pragma unroll
-                for (int j = 0; j < 3; ++j) Cr[c][j] = make_float2(-C[c][j].y, C[c][j].x);
-            const int mlo = chunk * kFwdChunkLen;
-            int mhi = mlo + kFwdChunkLen;
-            if (mhi > 4 * nvalid) mhi = 4 * nvalid;
-            float2 x1[kFwdMaxCar], x2[kFwdMaxCar];
-#pragma unroll
-            for (int c = 0; c < kFwdMaxCar; ++c) { x1[c] = sm->a[c][mlo + 3]; x2[c] = sm->a[c][mlo + 2]; }
-            float2 *o = &sm->out[buf][r];
-#pragma unroll
-            for (int mm = 0; mm < kFwdChunkLen; ++mm) {
-                const int m = mlo + mm;
-                float2 acc = make_float2(0.f, 0.f);
-#pragma unroll
-                for (int c = 0; c < kFwdMaxCar; ++c) {
-                    const float2 x0 = sm->a[c][m + 4];
-                    acc = cmac(x0, C[c][0], Cr[c][0], acc);
-                    acc = cmac(x1[c], C[c][1], Cr[c][1], acc);
-                    acc = cmac(x2[c], C[c][2], Cr[c][2], acc);
-                    x2[c] = x1[c]; x1[c] = x0;
+                        for (int r = 0; r < 5; ++r) {
+                            if (r + 5 * j < 13) {
+                                const float2 C = p.C1[c][r + 5 * j];
+                                acc[r] = fma2(xi, make_float2(-C.y, C.x), fma2(xr, C, acc[r]));
+                            }
+                        }
+                    }
                 }
-                if (m < mhi) o[25 * m] = mul2(splat(p.scale), acc);
             }
+            float2 *Bo = &sm->B[5 * t];
+#pragma unroll
+            for (int r = 0; r < 5; ++r) Bo[r] = acc[r];
+        }
+        // the output tile we are about to refill must have left the SM (its bulk store has read it)
+        if (t == 0) tma_store_wait_read0();
+        __syncthreads();
+
+        // ---- phase 3b: shared x5 CIC^3 interpolation to 10 MS/s (real taps, x out_scale folded in): 25 outputs per thread
+        if (t < 4 * nvalid) {
+            const float2 *Bi = &sm->B[5 * (t + 1)];                 // B[q], q = 5 t (tile-local)
+            float2 b[7];
+#pragma unroll
+            for (int k = 0; k < 7; ++k) b[k] = Bi[k - 2];
+            float2 *o = &sm->out[25 * t];
+#pragma unroll
+            for (int qq = 0; qq < 5; ++qq)
+#pragma unroll
+                for (int r = 0; r < 5; ++r) {
+                    float2 v = mul2(splat(p.G2[r]), b[qq + 2]);
+                    v = fma2(splat(p.G2[r + 5]), b[qq + 1], v);
+                    if (r + 10 < 13) v = fma2(splat(p.G2[r + 10]), b[qq], v);
+                    o[5 * qq + r] = v;
+                }
         }
         fence_async_smem();
         __syncthreads();
-        if (t == 0) tma_store_1d(p.out + (size_t)i0 * 100, sm->out[buf], (uint32_t)nvalid * 100u * (uint32_t)sizeof(float2));
+        if (t == 0) tma_store_1d(p.out + (size_t)i0 * 100, sm->out, (uint32_t)nvalid * 100u * (uint32_t)sizeof(float2));
     }
     if (t == 0) tma_store_wait_all();
 }

@@ -9,8 +9,6 @@ constexpr int kFwdTileSym  = 63;                 // new 100 kS/s symbols per til
 constexpr int kFwdMaxTap4  = 81;                 // taps per polyphase arm (321 padded to 324)
 constexpr int kFwdHistLen  = kFwdMaxTap4 + 1;    // symbols of history a call needs from the previous one
 constexpr int kFwdThreads  = 256;
-constexpr int kFwdChunks   = 10;                 // phase 3: 25 output phases x 10 chunks of 400 kS/s samples
-constexpr int kFwdChunkLen = 26;                 // 10 x 26 >= 252
 constexpr int kFwdScanBlock = 4096;              // symbols per block of the prefix-sum kernels
 constexpr int kFwdInterp   = 100;                // 10 MS/s / 100 kS/s = 4 (reference) x 25 (CIC)
 
@@ -42,7 +40,8 @@ struct FwdParams {
     float          scale;
     int            ntap4[kFwdMaxCar];
     float2         w25[kFwdMaxCar];              // mixer phasor of one 400 kS/s step
-    float2         C[kFwdMaxCar][75];            // 25 cic[u] e^{j phi_c(u)}: CIC^3 taps carrying the mixer
+    float2         C1[kFwdMaxCar][15];           // 5 cic5[u] e^{j phi_c(5 u)}: first x5 CIC^3 stage carrying the mixer
+    float          G2[15];                       // out_scale * 5 cic5[u]: second (shared) x5 CIC^3 stage
     float          taps[kFwdMaxCar][4 * kFwdMaxTap4];
 };
 

@@ -283,9 +283,10 @@ int orc_rx_detect(const float *d, size_t nd, orc_burst *out, int max) {
  * appends a CIC^3 x25 interpolator per carrier before the mixers:
  *
  *   s[i] in {+1,-1,0}  ->  S[i] = sum s  ->  fm[i] = (s[i] != 0) * exp(j 2 pi frac(S[i] * fcw_fm / 2^32))
- *   a[4i+j] = sum_k T[j+4k] fm[i-k]                         (pfb interpolator, zero history)
- *   b[25m+r] = sum_{t=0..2} G[r+25t] a[m-t],  G = 25 * cic3   (zero-stuff by 25, CIC^3)
- *   out[n]  = scale * sum_c b_c[n] * exp(j 2 pi frac(n * fcw_c / 2^32))
+ *   a[4i+j] = sum_k T[j+4k] fm[i-k]                         (pfb interpolator, zero history)        @400 kS/s
+ *   b[5m+r]  = sum_{t=0..2} G5[r+5t] a[m-t],  G5 = 5 * boxcar5^3 / 125   (x5 CIC^3)                  @2 MS/s
+ *   B[q]     = sum_c b_c[q] * exp(j 2 pi frac(5 q * fcw_c / 2^32))       (mixers, carriers summed)   @2 MS/s
+ *   out[5q+r] = scale * sum_{t=0..2} G5[r+5t] B[q-t]                       (x5 CIC^3, shared)          @10 MS/s
  *
  * A symbol byte of 0 mutes that symbol (the reference's mute_xx, :1508-1601, gates the interpolator output;
  * gating its input differs only in the 0.8 ms filter transient).
@@ -293,12 +294,17 @@ int orc_rx_detect(const float *d, size_t nd, orc_burst *out, int max) {
 void orc_fwd_chain_f64(const int8_t *const *sym, int ncarriers, size_t nsym, uint32_t fcw_fm,
                        const float *const *taps, const int *ntaps, const uint32_t *fcw_mix, double scale,
                        double *out /* nsym*100 complex */) {
-    const size_t nm = nsym * 4, nout = nsym * 100;
-    double c3[NCIC];
-    cic_coeffs(c3);
-    memset(out, 0, sizeof(double) * 2 * nout);
+    const size_t nm = nsym * 4, nq = nsym * 20, nout = nsym * 100;
+    double g5[15];
+    {   /* 5 * (boxcar5 * boxcar5 * boxcar5) / 125, 13 taps */
+        double a[9] = {0}, c[13] = {0};
+        for (int i = 0; i < 5; i++) for (int j = 0; j < 5; j++) a[i + j] += 1.0;
+        for (int i = 0; i < 9; i++) for (int j = 0; j < 5; j++) c[i + j] += a[i];
+        for (int i = 0; i < 15; i++) g5[i] = i < 13 ? 5.0 * c[i] / 125.0 : 0.0;
+    }
     double *fr = (double *)malloc(sizeof(double) * nsym), *fi = (double *)malloc(sizeof(double) * nsym);
     double *ar = (double *)malloc(sizeof(double) * nm), *ai = (double *)malloc(sizeof(double) * nm);
+    double *Br = (double *)calloc(nq, sizeof(double)), *Bi = (double *)calloc(nq, sizeof(double));
     for (int c = 0; c < ncarriers; c++) {
         int32_t S = 0;
         for (size_t i = 0; i < nsym; i++) {
@@ -319,21 +325,30 @@ void orc_fwd_chain_f64(const int8_t *const *sym, int ncarriers, size_t nsym, uin
                 ar[4 * i + j] = sr; ai[4 * i + j] = si;
             }
         for (size_t m = 0; m < nm; m++)
-            for (int r = 0; r < 25; r++) {
+            for (int r = 0; r < 5; r++) {
                 double br = 0, bi = 0;
                 for (int t = 0; t < 3; t++) {
-                    int gi = r + 25 * t;
-                    if (gi >= NCIC || m < (size_t)t) continue;
-                    double g = 25.0 * c3[gi];
-                    br += g * ar[m - t]; bi += g * ai[m - t];
+                    if (m < (size_t)t) continue;
+                    br += g5[r + 5 * t] * ar[m - t]; bi += g5[r + 5 * t] * ai[m - t];
                 }
-                size_t n = 25 * m + (size_t)r;
-                uint32_t psi = (uint32_t)((uint64_t)n * fcw_mix[c]);
+                size_t q = 5 * m + (size_t)r;
+                uint32_t psi = (uint32_t)((uint64_t)(5 * q) * fcw_mix[c]);
                 double ang = 2.0 * M_PI * ((double)psi / 4294967296.0);
                 double cr = cos(ang), ci = sin(ang);
-                out[2 * n] += scale * (br * cr - bi * ci);
-                out[2 * n + 1] += scale * (br * ci + bi * cr);
+                Br[q] += br * cr - bi * ci;
+                Bi[q] += br * ci + bi * cr;
             }
     }
-    free(fr); free(fi); free(ar); free(ai);
+    for (size_t q = 0; q < nq; q++)
+        for (int r = 0; r < 5; r++) {
+            double orr = 0, oi = 0;
+            for (int t = 0; t < 3; t++) {
+                if (q < (size_t)t) continue;
+                orr += g5[r + 5 * t] * Br[q - t]; oi += g5[r + 5 * t] * Bi[q - t];
+            }
+            out[2 * (5 * q + r)] = scale * orr;
+            out[2 * (5 * q + r) + 1] = scale * oi;
+        }
+    (void)nout;
+    free(fr); free(fi); free(ar); free(ai); free(Br); free(Bi);
 }
