@@ -174,32 +174,44 @@ __global__ void __launch_bounds__(kFwdThreads, 3) fwd_fused_kernel(const __grid_
         }
         __syncthreads();
 
-        // ---- phase 2: x4 polyphase interpolation, one symbol (4 outputs) per thread, 64 threads per carrier;
-        //      the 400 kS/s samples are stored already rotated by the carrier's NCO: at[m] = a[m] e^{j phi_c(25 m)}
-        if (t < 64 * p.ncar) {
-            const int c = t >> 6, il = t & 63;                      // symbol i0 - 1 + il  (c is warp-uniform)
-            const float2 *f = &sm->fm[c][il + kFwdMaxTap4];
-            float2 acc0 = make_float2(0.f, 0.f), acc1 = acc0, acc2 = acc0, acc3 = acc0;
+        // ---- phase 2: x4 polyphase interpolation.  One thread = two adjacent symbols (8 outputs) of one carrier: the
+        //      FM sample loaded for symbol i at tap k is symbol i+1's sample at tap k+1, so each shared-memory load and
+        //      each uniform 4-tap load feeds 8 FFMA2.  One warp per carrier.  The 400 kS/s samples are stored already
+        //      rotated by the carrier's NCO: at[m] = a[m] e^{j phi_c(25 m)}.
+        if (t < 32 * p.ncar) {
+            const int c = t >> 5, ip = t & 31;                      // symbols i0 - 1 + 2 ip, i0 + 2 ip   (c is warp-uniform)
+            const float2 *f = &sm->fm[c][2 * ip + kFwdMaxTap4];     // fm of the first symbol of the pair
+            float2 lo0 = make_float2(0.f, 0.f), lo1 = lo0, lo2 = lo0, lo3 = lo0, hi0 = lo0, hi1 = lo0, hi2 = lo0, hi3 = lo0;
             auto arm = [&](const float *T, int n4) {
+                float2 xh = f[1];                                   // fm[i+1 - 0]
 #pragma unroll 3
                 for (int k = 0; k < n4; ++k) {
-                    const float2 x = f[-k];
+                    const float2 xl = f[-k];                        // fm[i - k] == fm[(i+1) - (k+1)]
                     const float4 tk = *reinterpret_cast<const float4 *>(T + 4 * k);     // uniform: LDCU.128
-                    acc0 = fma2(splat(tk.x), x, acc0);
-                    acc1 = fma2(splat(tk.y), x, acc1);
-                    acc2 = fma2(splat(tk.z), x, acc2);
-                    acc3 = fma2(splat(tk.w), x, acc3);
+                    lo0 = fma2(splat(tk.x), xl, lo0); hi0 = fma2(splat(tk.x), xh, hi0);
+                    lo1 = fma2(splat(tk.y), xl, lo1); hi1 = fma2(splat(tk.y), xh, hi1);
+                    lo2 = fma2(splat(tk.z), xl, lo2); hi2 = fma2(splat(tk.z), xh, hi2);
+                    lo3 = fma2(splat(tk.w), xl, lo3); hi3 = fma2(splat(tk.w), xh, hi3);
+                    xh = xl;
                 }
             };
             if (c == 0) arm(p.taps[0], p.ntap4[0]);
             else if (c == 1) arm(p.taps[1], p.ntap4[1]);
             else arm(p.taps[2], p.ntap4[2]);
-            const uint32_t m4 = p.m_base + (uint32_t)(4 * (i0 - 1 + il));
-            const float2 W0 = sincos_phase(m4 * p.fcw_mix25[c]);
+            const uint32_t m8 = p.m_base + (uint32_t)(4 * (i0 - 1 + 2 * ip));
             const float2 w25 = p.w25[c];
-            const float2 W1 = cmul(W0, w25), W2 = cmul(W1, w25), W3 = cmul(W2, w25);
-            float2 *a = &sm->a[c][4 * il];
-            a[0] = cmul(acc0, W0); a[1] = cmul(acc1, W1); a[2] = cmul(acc2, W2); a[3] = cmul(acc3, W3);
+            // each symbol starts its own phasor recurrence, so a sample's value does not depend on how symbols pair up
+            float2 W = sincos_phase(m8 * p.fcw_mix25[c]);
+            float2 *a = &sm->a[c][8 * ip];
+            a[0] = cmul(lo0, W); W = cmul(W, w25);
+            a[1] = cmul(lo1, W); W = cmul(W, w25);
+            a[2] = cmul(lo2, W); W = cmul(W, w25);
+            a[3] = cmul(lo3, W);
+            W = sincos_phase((m8 + 4u) * p.fcw_mix25[c]);
+            a[4] = cmul(hi0, W); W = cmul(W, w25);
+            a[5] = cmul(hi1, W); W = cmul(W, w25);
+            a[6] = cmul(hi2, W); W = cmul(W, w25);
+            a[7] = cmul(hi3, W);
         }
         __syncthreads();
 
