@@ -87,7 +87,7 @@ RX_TIME_KERNELS = 2
 EXPORTS = [
     "amps_b200_version", "amps_b200_strerror", "amps_b200_last_error", "amps_b200_device_count", "amps_b200_abi_sizes",
     "amps_recc_iq_create", "amps_recc_iq_destroy", "amps_recc_iq_reset", "amps_recc_iq_work",
-    "amps_recc_iq_submit_dev", "amps_recc_iq_collect", "amps_recc_iq_peek", "amps_recc_iq_consume", "amps_recc_iq_granularity", "amps_recc_iq_read_demod",
+    "amps_recc_iq_submit_dev", "amps_recc_iq_collect", "amps_recc_iq_peek", "amps_recc_iq_consume", "amps_recc_iq_poll", "amps_recc_iq_granularity", "amps_recc_iq_read_demod",
     "amps_recc_iq_read_baseband", "amps_recc_iq_stats", "amps_recc_iq_front_times", "amps_recc_iq_get_taps",
     "amps_recc_decode_create", "amps_recc_decode_destroy", "amps_recc_decode_burst", "amps_recc_decode_bursts",
     "amps_recc_create", "amps_recc_destroy", "amps_recc_work", "amps_recc_work_chunks",
@@ -121,6 +121,7 @@ def lib() -> C.CDLL:
     L.amps_recc_iq_granularity.argtypes = [C.c_void_p]
     L.amps_recc_iq_peek.argtypes = [C.c_void_p, C.POINTER(C.POINTER(Burst)), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.amps_recc_iq_consume.argtypes = [C.c_void_p, C.c_uint64]
+    L.amps_recc_iq_poll.argtypes = L.amps_recc_iq_peek.argtypes
     L.amps_b200_abi_sizes.argtypes = [C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     bs, ws = C.c_size_t(0), C.c_size_t(0)
     L.amps_b200_abi_sizes(C.byref(bs), C.byref(ws))
@@ -229,6 +230,13 @@ class ReccIq:
         ring = C.POINTER(Burst)()
         rl, first, count = C.c_uint32(0), C.c_uint64(0), C.c_uint64(0)
         check(lib().amps_recc_iq_peek(self.h, C.byref(ring), C.byref(rl), C.byref(first), C.byref(count)))
+        return ring, rl.value, first.value, count.value
+
+    def poll(self):
+        """Like peek() but without synchronising the stream: what has been published so far."""
+        ring = C.POINTER(Burst)()
+        rl, first, count = C.c_uint32(0), C.c_uint64(0), C.c_uint64(0)
+        check(lib().amps_recc_iq_poll(self.h, C.byref(ring), C.byref(rl), C.byref(first), C.byref(count)))
         return ring, rl.value, first.value, count.value
 
     def consume(self, count: int):

@@ -274,6 +274,17 @@ extern "C" int amps_recc_iq_peek(amps_recc_iq *h, const amps_burst **ring, uint3
     return AMPS_OK;
 }
 
+extern "C" int amps_recc_iq_poll(amps_recc_iq *h, const amps_burst **ring, uint32_t *ring_len, uint64_t *first, uint64_t *count) {
+    if (!h || !ring || !ring_len || !first || !count) return set_error(AMPS_E_INVAL, "null argument");
+    const uint64_t total = *reinterpret_cast<volatile unsigned long long *>(&h->h_pub->nrec_total);
+    if (total - h->consumed > h->max_records) {           // the ring wrapped over uncollected records
+        h->lost += total - h->consumed - h->max_records;
+        h->consumed = total - h->max_records;
+    }
+    *ring = h->h_ring; *ring_len = h->max_records; *first = h->consumed; *count = total - h->consumed;
+    return AMPS_OK;
+}
+
 extern "C" int amps_recc_iq_consume(amps_recc_iq *h, uint64_t count) {
     if (!h) return set_error(AMPS_E_INVAL, "null handle");
     if (h->consumed + count > h->h_pub->nrec_total) return set_error(AMPS_E_INVAL, "consuming more bursts than were published");

@@ -143,11 +143,6 @@ __device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// acc += x * c for complex x, c (cr = (-c.im, c.re)): two packed FMAs
-__device__ __forceinline__ float2 cmac(float2 x, float2 c, float2 cr, float2 acc) {
-    return fma2(splat(x.y), cr, fma2(splat(x.x), c, acc));
-}
-
 __global__ void __launch_bounds__(kFwdThreads, 3) fwd_fused_kernel(const __grid_constant__ FwdParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     FwdSmem *sm = reinterpret_cast<FwdSmem *>(smem_raw);

@@ -144,6 +144,10 @@ AMPS_B200_API int amps_recc_iq_collect(amps_recc_iq *h, amps_burst *out, int max
 AMPS_B200_API int amps_recc_iq_peek(amps_recc_iq *h, const amps_burst **ring, uint32_t *ring_len,
                                     uint64_t *first, uint64_t *count);
 AMPS_B200_API int amps_recc_iq_consume(amps_recc_iq *h, uint64_t count);
+/* Non-blocking form of peek(): no stream synchronisation, reports the bursts the kernels have published so far
+ * (a record is complete in host memory before the counter that covers it is written). */
+AMPS_B200_API int amps_recc_iq_poll(amps_recc_iq *h, const amps_burst **ring, uint32_t *ring_len,
+                                    uint64_t *first, uint64_t *count);
 AMPS_B200_API int amps_recc_iq_granularity(const amps_recc_iq *h);
 /* Inspection (tests / roofline accounting) */
 AMPS_B200_API int amps_recc_iq_read_demod(amps_recc_iq *h, uint64_t first, float *out, size_t n);          /* 200 kS/s FM demod */
