@@ -149,12 +149,12 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def run_fwd(args, rank, local_rank, world):
-    """Secondary line: BASELINE config 3, FOCC @0 Hz + FVC @+60 kHz + FVC @+90 kHz -> 10 MS/s complex, device resident.
-    Algorithmic bytes: 8 B written per output sample (+ 3 symbol bytes per 100 samples read)."""
+def measure_fwd(local_rank, steps, warmup):
+    """BASELINE config 3 on this rank's GPU: FOCC @0 Hz + FVC @+60 kHz + FVC @+90 kHz, x0.5 -> 10 MS/s complex,
+    device resident.  Algorithmic bytes: 8 B written per output sample (+ 3 symbol bytes per 100 samples read).
+    Returns (samples per step, ms per step)."""
     import torch
     from gr_amps_b200 import capi
-    torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     nsym = 2_703_360                                  # 270 336 000 output samples, 2.16 GB
     focc = capi.Focc(100000, False, device=local_rank)
@@ -163,7 +163,6 @@ def run_fwd(args, rank, local_rank, world):
     focc.generate_dev(t.data_ptr(), nsym, torch.cuda.current_stream().cuda_stream)
     syms.append(t)
     fvc = capi.Fvc(100000, device=local_rank)
-    from gr_amps_b200.capi import C  # noqa: F401
     alert = np.array([int(c) for c in "1011010000000000000000000001"], np.uint8)
     fvc.push_words(alert)
     train = bytearray()
@@ -177,22 +176,32 @@ def run_fwd(args, rank, local_rank, world):
     fw = capi.Fwd(max_samples=nsym * 100, device=local_rank)
     stream = torch.cuda.current_stream()
     ptrs = [s.data_ptr() for s in syms]
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         fw.submit_dev(ptrs, nsym, out.data_ptr(), stream.cuda_stream)
     torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(steps):
         fw.submit_dev(ptrs, nsym, out.data_ptr(), stream.cuda_stream)
     e1.record(stream)
     torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    fw.close()
+    del out, syms
+    torch.cuda.empty_cache()
+    return nsym * 100, ms
+
+
+def run_fwd(args, rank, local_rank, world):
+    """Secondary line: the forward path alone (single GPU)."""
+    import torch
+    torch.cuda.set_device(local_rank)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    n, ms = measure_fwd(local_rank, args.steps, args.warmup)
     clocks = sampler.stop()
-    ms = e0.elapsed_time(e1) / args.steps
     peak, peak_src = load_peaks()
-    n = nsym * 100
-    achieved = (8.0 * n + 3.0 * nsym) / (ms * 1e-3) / 1e9
+    achieved = (8.0 * n + 0.03 * n) / (ms * 1e-3) / 1e9
     print(json.dumps({
         "metric": "Msamples/s complex baseband out of the fused forward path (config 3)", "value": n / (ms * 1e-3) / 1e6,
         "unit": "Msamples/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
@@ -328,6 +337,14 @@ def main():
         raise SystemExit("bench.py: e2e parity gate failed (%d bursts)" % len(got))
     rec_bytes = 24 + (len(got) / e2e_steps) * float(capi.C.sizeof(capi.Burst))
 
+    # ---- secondary: the forward path (config 3 / the FOCC half of config 4) on every rank's GPU
+    del host, batch
+    rx.close(); rx2.close()
+    torch.cuda.empty_cache()
+    barrier()
+    fwd_n, fwd_ms = measure_fwd(local_rank, 20, 3)
+    fwd_total, fwd_ms_max = multi.whole_job_throughput(float(fwd_n), fwd_ms, dev)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -356,7 +373,9 @@ def main():
         O.cpu_baseline_run(xs, min(cores, 8), 1)      # warm the code and the page cache
         reps = 1
         sec, nb = O.cpu_baseline_run(xs, cores, reps)
+        sec1, _ = O.cpu_baseline_run(xs, 1, 2)
         cpu = {"value": cores * reps * len(xs) / sec / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "port",
+               "value_1_thread": 2 * len(xs) / sec1 / 1e6,
                "sample": "%d threads x %d x one config-2 period (%d samples); fp32 oracle chain + detect + decode; %.1f s CPU work"
                          % (cores, reps, len(xs), sec * cores), "bursts_decoded": nb}
 
@@ -375,6 +394,9 @@ def main():
         "e2e": {"value": e2e_samples / e2e_sec / 1e6, "unit": "Msamples/s",
                 "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": int(rec_bytes), "steps": e2e_steps,
                 "api": "amps_recc_iq_work (pinned host buffer, burst callbacks)"},
+        "forward": {"metric": "Msamples/s out of the fused forward path (config 3: FOCC + 2 FVC carriers per GPU)",
+                    "value": fwd_total / (fwd_ms_max * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": fwd_ms_max,
+                    "hbm_frac": 8.03 * fwd_n / (fwd_ms * 1e-3) / 1e9 / peak},
         "gpu_launches": int(launches) * world,
         "bursts_decoded": n_bursts,
     }
