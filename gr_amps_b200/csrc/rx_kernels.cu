@@ -551,9 +551,13 @@ __global__ void __launch_bounds__(256) rx_capture_kernel(const float *__restrict
     decode_burst_block(rec->symbols, &rec->decoded, s_valid, s_errs);
     // publish: stream the finished record into the host-visible ring (posted PCIe writes)
     const unsigned long long rec_base = state->rec_base;
-    const unsigned long long *src = reinterpret_cast<const unsigned long long *>(rec);
-    unsigned long long *dst = reinterpret_cast<unsigned long long *>(&host_ring[(rec_base + blockIdx.x) % ring_len]);
-    for (int w = t; w < (int)(sizeof(amps_burst) / 8); w += nt) dst[w] = src[w];
+    // (when one call accepts more bursts than the ring holds, only the newest ring_len are written: two CTAs must
+    // never race for the same slot)
+    if (n_acc - blockIdx.x <= ring_len) {
+        const unsigned long long *src = reinterpret_cast<const unsigned long long *>(rec);
+        unsigned long long *dst = reinterpret_cast<unsigned long long *>(&host_ring[(rec_base + blockIdx.x) % ring_len]);
+        for (int w = t; w < (int)(sizeof(amps_burst) / 8); w += nt) dst[w] = src[w];
+    }
     __threadfence_system();
     __syncthreads();
     if (t == 0) {

@@ -97,3 +97,95 @@ def test_device_resident_many_bursts(capi, oracle):
         assert words_equal(b.decoded, oracle.recc_decode(o[2])) == []
         assert b.decoded.min == ("2125550%03d" % i).encode()
     rx.close()
+
+
+# ------------------------------------------------------------------ edge cases
+def test_empty_and_tiny_calls(capi):
+    rx = capi.ReccIq(max_samples=PASS * 4)
+    assert rx.work(np.zeros(0, np.complex64)) == []
+    for n in (1, 7, 49, 50, 38399):                      # less than one pass: carried, nothing produced yet
+        assert rx.work(np.zeros(n, np.complex64)) == []
+    st = rx.stats()
+    assert st["demod_out"] == (1 + 7 + 49 + 50 + 38399) // PASS * (PASS // 50)
+    with pytest.raises(capi.AmpsError):
+        rx.work(np.zeros(PASS * 4 + PASS + 1, np.complex64))     # more than max_samples
+    import torch
+    t = torch.zeros(2 * PASS + 2, dtype=torch.float32, device="cuda")
+    rx2 = capi.ReccIq(max_samples=PASS * 4)
+    with pytest.raises(capi.AmpsError):
+        rx2.submit_dev(t.data_ptr(), PASS + 1, 0)        # not a multiple of the granularity
+    with pytest.raises(capi.AmpsError):
+        rx2.submit_dev(t.data_ptr() + 8, PASS, 0)        # not 16-byte aligned
+    rx.close(); rx2.close()
+
+
+def test_noise_only_and_silence_give_no_bursts(capi, oracle):
+    rng = np.random.default_rng(5)
+    n = 20 * PASS
+    noise = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+    for x in (noise, np.zeros(n, np.complex64)):
+        rx = capi.ReccIq(max_samples=n)
+        assert rx.work(x) == []
+        _, d = oracle.rx_chain_f32(x)
+        assert bits_equal_f32(rx.read_demod(0, n // 50), d)
+        assert oracle.rx_detect(d) == []
+        rx.close()
+
+
+def test_truncated_burst_and_overlapping_triggers(capi, oracle):
+    """(a) a burst cut off before its 3374 symbols are in: not reported (and reported once the rest arrives);
+    (b) a second seizure precursor inside an already captured burst is ignored, a later one is captured."""
+    x, hs, _ = synth.config2_period(n_total=N1, snr_db=25.0, seed=21)
+    cut = 30 * PASS                                       # 1 152 000 samples: trigger in, capture incomplete
+    rx = capi.ReccIq(max_samples=N1)
+    assert rx.work(x[:cut]) == []
+    got = rx.work(x[cut:])
+    one = capi.ReccIq(max_samples=N1)
+    ref = one.work(x)
+    assert len(got) == len(ref) == 1 and got[0].demod_index == ref[0].demod_index and bytes(got[0].symbols) == bytes(ref[0].symbols)
+    rx.close(); one.close()
+    # (b): inject the 37-bit trigger pattern again 600 half-symbols into the message (inside the capture window)
+    words = synth.origination_words()
+    bits = synth.recc_message_bits(words).copy()
+    trig_bits = np.array([1, 0] * 13 + synth.WORD_SYNC, np.uint8)
+    bits[300:337] = trig_bits
+    hs2 = synth.manchester(bits)
+    xa = synth.fm_burst(hs2, N1, 20000, snr_db=25.0, seed=22)
+    xb, _, _ = synth.config2_period(n_total=N1, snr_db=25.0, seed=23)
+    xx = np.concatenate([xa, xb])
+    rx = capi.ReccIq(max_samples=len(xx))
+    b = rx.work(xx)
+    _, d = oracle.rx_chain_f32(xx)
+    ob = oracle.rx_detect(d)
+    assert len(b) == len(ob) == 2                         # the embedded trigger did not produce a third record
+    for g, o in zip(b, ob):
+        assert g.demod_index == o[0] and np.array_equal(g.symbols_np(), o[2])
+        assert words_equal(g.decoded, oracle.recc_decode(o[2])) == []
+    assert b[1].decoded.min == b"2125551234" and list(b[1].decoded.valid) == [1] * 7
+    rx.close()
+
+
+def test_reset_restarts_the_stream(capi):
+    x, _, _ = synth.config2_period(n_total=N1, snr_db=22.0, seed=31)
+    rx = capi.ReccIq(max_samples=N1)
+    a = rx.work(x)
+    rx.reset()
+    b = rx.work(x)
+    assert len(a) == len(b) == 1 and a[0].demod_index == b[0].demod_index and bytes(a[0].symbols) == bytes(b[0].symbols)
+    assert np.float32(a[0].corr) == np.float32(b[0].corr)
+    rx.close()
+
+
+def test_ring_overflow_is_reported_not_corrupting(capi):
+    """More bursts than the host ring holds between collects: the newest max_bursts survive, in order."""
+    torch = pytest.importorskip("torch")
+    x, _, _ = synth.config2_period(n_total=N1, snr_db=None)
+    xs = np.tile(x, 6)
+    t = torch.from_numpy(xs.view(np.float32).copy()).cuda()
+    rx = capi.ReccIq(max_samples=len(xs), max_bursts=4)
+    rx.submit_dev(t.data_ptr(), len(xs), torch.cuda.current_stream().cuda_stream)
+    got = rx.collect()
+    assert len(got) == 4
+    idx = [g.demod_index for g in got]
+    assert idx == sorted(idx) and idx[-1] // (N1 // 50) == 5
+    rx.close()
