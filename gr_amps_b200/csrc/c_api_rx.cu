@@ -21,6 +21,10 @@ struct amps_recc_iq {
     uint32_t     flags = 0;
     std::vector<float> lpf;
     uint32_t     fcw = 0;
+    bool         native400 = false;      // samp_rate == 400e3: the reference's own rate, no CIC stage
+    uint32_t     pass_in = kPass;        // input samples per pass (API granularity)
+    uint32_t     hist = kHist;           // input samples of history carried between calls
+    uint32_t     decim = kD1 * kD2;      // input samples per demodulated sample
 
     RxFrontParams fp{};                  // constant part filled at create
     float2      *d_stage = nullptr;      // host path: [carry | new chunk]
@@ -58,15 +62,15 @@ struct amps_recc_iq {
 };
 
 static int rx_alloc(amps_recc_iq *h) {
-    const size_t max_d = (size_t)h->max_samples / (kD1 * kD2) + kPassOut;
+    const size_t max_d = (size_t)h->max_samples / h->decim + kPassOut;
     size_t cap = 1;
     // two calls' worth: the detection of call k overlaps the front kernel of call k+1
     while (cap < 2 * max_d + (size_t)kSpan + 4096) cap <<= 1;
     h->dmask = (uint32_t)(cap - 1);
-    CK(cudaMalloc(&h->d_stage, ((size_t)h->max_samples + kPass) * sizeof(float2)));
+    CK(cudaMalloc(&h->d_stage, ((size_t)h->max_samples + h->pass_in) * sizeof(float2)));
     for (int i = 0; i < 2; ++i) {
-        CK(cudaMalloc(&h->d_tail[i], (size_t)kHist * sizeof(float2)));
-        CK(cudaMemset(h->d_tail[i], 0, (size_t)kHist * sizeof(float2)));
+        CK(cudaMalloc(&h->d_tail[i], (size_t)h->hist * sizeof(float2)));
+        CK(cudaMemset(h->d_tail[i], 0, (size_t)h->hist * sizeof(float2)));
     }
     CK(cudaMalloc(&h->d_dring, cap * sizeof(float)));
     CK(cudaMemset(h->d_dring, 0, cap * sizeof(float)));
@@ -95,8 +99,8 @@ static int rx_alloc(amps_recc_iq *h) {
 extern "C" int amps_recc_iq_create(const amps_recc_iq_params *params, amps_recc_iq **out) {
     if (!params || !out) return set_error(AMPS_E_INVAL, "null argument");
     *out = nullptr;
-    if (params->samp_rate != 10e6)
-        return set_error(AMPS_E_INVAL, "samp_rate must be 10e6 (25 x the reference's 400 kS/s)");
+    if (params->samp_rate != 10e6 && params->samp_rate != 400e3)
+        return set_error(AMPS_E_INVAL, "samp_rate must be 10e6 (25 x the reference's rate) or 400e3 (the reference's own rate)");
     if (params->max_samples == 0) return set_error(AMPS_E_INVAL, "max_samples must be > 0");
     if (params->lpf_taps && (params->n_lpf_taps == 0 || params->n_lpf_taps > (uint32_t)kMaxLpf))
         return set_error(AMPS_E_INVAL, "n_lpf_taps must be in 1..299");
@@ -109,7 +113,9 @@ extern "C" int amps_recc_iq_create(const amps_recc_iq_params *params, amps_recc_
     cudaGetDeviceProperties(&prop, params->device);
     h->sm_count = prop.multiProcessorCount;
     // round the per-call capacity up to whole passes
-    h->max_samples = (uint32_t)(((uint64_t)params->max_samples + kPass - 1) / kPass * kPass);
+    h->native400 = params->samp_rate == 400e3;
+    if (h->native400) { h->pass_in = kPass400; h->hist = kPass400; h->decim = kD2; }
+    h->max_samples = (uint32_t)(((uint64_t)params->max_samples + h->pass_in - 1) / h->pass_in * h->pass_in);
     h->max_records = params->max_bursts ? params->max_bursts : 256;
     h->flags = params->flags;
     { const char *e = std::getenv("AMPS_RX_SERIAL"); h->serial = e && e[0] == '1'; }
@@ -154,7 +160,7 @@ extern "C" int amps_recc_iq_reset(amps_recc_iq *h) {
     if (!h) return set_error(AMPS_E_INVAL, "null handle");
     CK(cudaSetDevice(h->device));
     CK(cudaDeviceSynchronize());
-    for (int i = 0; i < 2; ++i) CK(cudaMemset(h->d_tail[i], 0, (size_t)kHist * sizeof(float2)));
+    for (int i = 0; i < 2; ++i) CK(cudaMemset(h->d_tail[i], 0, (size_t)h->hist * sizeof(float2)));
     CK(cudaMemset(h->d_state, 0, sizeof(RxState)));
     CK(cudaMemset(h->d_dring, 0, ((size_t)h->dmask + 1) * sizeof(float)));
     std::memset(h->h_pub, 0, sizeof(RxPublished));
@@ -164,7 +170,7 @@ extern "C" int amps_recc_iq_reset(amps_recc_iq *h) {
     return AMPS_OK;
 }
 
-extern "C" int amps_recc_iq_granularity(const amps_recc_iq *h) { (void)h; return kPass; }
+extern "C" int amps_recc_iq_granularity(const amps_recc_iq *h) { return h ? (int)h->pass_in : kPass; }
 
 // Enqueue everything for `npass` passes whose samples start at d_chunk.
 static int rx_enqueue(amps_recc_iq *h, const float2 *d_chunk, uint32_t npass, cudaStream_t st) {
@@ -177,6 +183,7 @@ static int rx_enqueue(amps_recc_iq *h, const float2 *d_chunk, uint32_t npass, cu
     p.q_base = h->total_d;
     p.npass = npass;
     p.blk_base = (uint32_t)(h->samples_in / kD1);
+    p.n_base = h->samples_in;
     p.ydump = h->d_ydump;
     // whole passes per CTA, grid sized so that (nearly) every CTA gets the same count within one wave
     p.pass_per_cta = (npass + 2u * (uint32_t)h->sm_count - 1u) / (2u * (uint32_t)h->sm_count);
@@ -187,16 +194,17 @@ static int rx_enqueue(amps_recc_iq *h, const float2 *d_chunk, uint32_t npass, cu
     const bool timed = (h->flags & AMPS_RX_TIME_KERNELS) != 0;
     const int  evi = (int)(h->ev_count % amps_recc_iq::kEv);
     if (timed) CK(cudaEventRecord(h->ev0[evi], st));
-    CKL(launch_rx_front(p, grid, st));
+    if (h->native400) CKL(launch_rx_front400(p, grid, st));
+    else CKL(launch_rx_front(p, grid, st));
     if (timed) { CK(cudaEventRecord(h->ev1[evi], st)); h->ev_count++; }
     h->launches++;
     // history for the next call = the last pass of this one
-    CK(cudaMemcpyAsync(h->d_tail[h->tail_cur ^ 1], d_chunk + ((size_t)npass * kPass - kHist), (size_t)kHist * sizeof(float2),
+    CK(cudaMemcpyAsync(h->d_tail[h->tail_cur ^ 1], d_chunk + ((size_t)npass * h->pass_in - h->hist), (size_t)h->hist * sizeof(float2),
                        cudaMemcpyDeviceToDevice, st));
     h->tail_cur ^= 1;
     h->ydump_first = h->total_d;
     h->ydump_count = (uint64_t)npass * kPassOut;
-    h->samples_in += (uint64_t)npass * kPass;
+    h->samples_in += (uint64_t)npass * h->pass_in;
     h->total_d += (uint64_t)npass * kPassOut;
     // search every position whose capture is complete -- on the side stream, so that the next call's
     // front kernel (HBM-bound, 2 CTAs/SM) overlaps these small latency-bound kernels
@@ -211,7 +219,7 @@ static int rx_enqueue(amps_recc_iq *h, const float2 *d_chunk, uint32_t npass, cu
             CKL(launch_rx_select(h->d_state, h->d_cand, h->d_acc, hi, h->h_pub, sd));
             // at most one burst per kBurstLen searched positions (+1 for a run deferred from the last call)
             const int max_new = (int)((hi - lo) / (uint64_t)kBurstLen) + 2;
-            CKL(launch_rx_capture(h->d_dring, h->dmask, h->d_state, h->d_acc, max_new, h->h_ring, h->max_records, h->h_pub, sd));
+            CKL(launch_rx_capture(h->d_dring, h->dmask, h->d_state, h->d_acc, max_new, h->h_ring, h->max_records, h->h_pub, h->decim, sd));
             h->launches += 3;
             h->scan_hi = hi;
         }
@@ -225,12 +233,12 @@ static int rx_enqueue(amps_recc_iq *h, const float2 *d_chunk, uint32_t npass, cu
 extern "C" int amps_recc_iq_submit_dev(amps_recc_iq *h, const void *d_iq, size_t nsamples, void *cuda_stream) {
     if (!h || (!d_iq && nsamples)) return set_error(AMPS_E_INVAL, "null argument");
     if (nsamples == 0) return AMPS_OK;
-    if (nsamples % kPass) return set_error(AMPS_E_ALIGN, "nsamples must be a multiple of amps_recc_iq_granularity()");
+    if (nsamples % h->pass_in) return set_error(AMPS_E_ALIGN, "nsamples must be a multiple of amps_recc_iq_granularity()");
     if (reinterpret_cast<uintptr_t>(d_iq) & 15u) return set_error(AMPS_E_ALIGN, "d_iq must be 16-byte aligned");
     if (nsamples > h->max_samples) return set_error(AMPS_E_OVERFLOW, "nsamples exceeds max_samples");
     if (h->carry) return set_error(AMPS_E_STATE, "host-path samples are pending; reset() or keep using work()");
     CK(cudaSetDevice(h->device));
-    return rx_enqueue(h, static_cast<const float2 *>(d_iq), (uint32_t)(nsamples / kPass), static_cast<cudaStream_t>(cuda_stream));
+    return rx_enqueue(h, static_cast<const float2 *>(d_iq), (uint32_t)(nsamples / h->pass_in), static_cast<cudaStream_t>(cuda_stream));
 }
 
 // Wait for the stream; afterwards records [h->consumed, h->consumed + *n_out) sit in the host ring.
@@ -301,14 +309,14 @@ extern "C" int amps_recc_iq_work(amps_recc_iq *h, const float *iq_host, size_t n
     if (nsamples)
         CK(cudaMemcpyAsync(h->d_stage + h->carry, iq_host, nsamples * sizeof(float2), cudaMemcpyHostToDevice, st));
     const size_t avail = h->carry + nsamples;
-    const uint32_t npass = (uint32_t)(avail / kPass);
+    const uint32_t npass = (uint32_t)(avail / h->pass_in);
     h->last_stream = st;
     if (npass) {
         int rc = rx_enqueue(h, h->d_stage, npass, st);
         if (rc != AMPS_OK) return rc;
-        const size_t left = avail - (size_t)npass * kPass;
+        const size_t left = avail - (size_t)npass * h->pass_in;
         if (left)
-            CK(cudaMemcpyAsync(h->d_stage, h->d_stage + (size_t)npass * kPass, left * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+            CK(cudaMemcpyAsync(h->d_stage, h->d_stage + (size_t)npass * h->pass_in, left * sizeof(float2), cudaMemcpyDeviceToDevice, st));
         h->carry = left;
     } else {
         h->carry = avail;

@@ -27,12 +27,15 @@ static_assert(sizeof(amps_burst) % 8 == 0, "burst records are streamed to the ho
 // P mod kR: a thread that produces outputs R*c .. R*c+R-1 then walks pairs whose row is a
 // compile-time constant and whose column is c + const, so consecutive lanes read consecutive
 // 16-byte slots (conflict-free LDS.128) and every load feeds up to 2*kR FFMA2.
-struct FrontSmem {
-    float2   in[kStages][kTile];          // TMA landing ring
+struct PassSmem {                         // what stage 2 + demod work on (shared by the 10 MS/s and the 400 kS/s front ends)
     float4   v[kR][kRowLen];              // row r, column c (c >= -kPorchCols) at v[r][c + kPorchCols]
-    float2   pb[2][2][kTB];               // [tile parity][P1|P2][block] rotated CIC partial sums
     float2   ylast[kTB];                  // each thread's last output of the current pass
     float2   ycarry[2];                   // last output of a pass, by pass parity
+};
+struct FrontSmem {
+    float2   in[kStages][kTile];          // TMA landing ring
+    PassSmem ps;
+    float2   pb[2][2][kTB];               // [tile parity][P1|P2][block] rotated CIC partial sums
     uint64_t full[kStages];
 };
 
@@ -68,6 +71,64 @@ __device__ __forceinline__ void channel_filter(const RxFrontParams &p, const flo
     }
 #pragma unroll
     for (int r = 0; r < kR; ++r) y[r] = add2(E[r], O[r]);
+}
+
+// store one 400 kS/s sample (index relative to the start of the current pass, negative = history) into the pair/row layout
+__device__ __forceinline__ void store_v(PassSmem *ps, int mrel, float2 v) {
+    const int P   = mrel >> 1;                                   // pair index (floor)
+    const int col = P >> kLogR;
+    if (col >= -kPorchCols) reinterpret_cast<float2 *>(&ps->v[P & (kR - 1)][col + kPorchCols])[mrel & 1] = v;
+}
+
+// End of a pass (all threads call it): stage 2 (299-tap channel filter /2, kR outputs per thread), quadrature demod,
+// hard decisions, and the history shuffle for the next pass.  With warm == true it only produces y[q0-1], the
+// predecessor the demod of the CTA's first real output needs; nothing is written for it.
+__device__ __forceinline__ void finish_pass(const RxFrontParams &p, PassSmem *ps, bool warm, int pc, uint32_t pa, int t) {
+    __syncthreads();                                   // the pass's new v samples are in place
+    float2 y[kR];
+#pragma unroll
+    for (int r = 0; r < kR; ++r) y[r] = make_float2(0.f, 0.f);
+    if (!warm || t == 0) {
+        const int c0 = warm ? -1 : t;
+        channel_filter(p, &ps->v[0][c0 + kPorchCols], y);
+        if (!warm) ps->ylast[t] = y[kR - 1];
+        if (warm || t == kTB - 1) ps->ycarry[pc & 1] = y[kR - 1];
+    }
+    __syncthreads();
+    if (!warm) {
+        // the last kPorchCols columns become the history of the next pass
+        if (t < kR * kPorchCols) {
+            const int r = t / kPorchCols, c = t % kPorchCols;
+            ps->v[r][c] = ps->v[r][kTB + c];
+        }
+        // ---- quadrature demod: arg(y[q] * conj(y[q-1]))
+        float2 yp = t == 0 ? ps->ycarry[(pc + 1) & 1] : ps->ylast[t - 1];
+        float d[kR];
+#pragma unroll
+        for (int r = 0; r < kR; ++r) {
+            const float zr = __fmaf_rn(y[r].y, yp.y, __fmul_rn(y[r].x, yp.x));
+            const float zi = __fmaf_rn(y[r].y, yp.x, -__fmul_rn(y[r].x, yp.y));
+            d[r] = atan2_spec(zi, zr);
+            yp = y[r];
+        }
+        const unsigned long long ql = (unsigned long long)(pa + (uint32_t)pc) * kPassOut + (unsigned long long)kR * t;
+        const unsigned long long qabs = p.q_base + ql;
+        float4 *dst = reinterpret_cast<float4 *>(&p.dring[qabs & p.dmask]);
+        *dst = make_float4(d[0], d[1], d[2], d[3]);
+        // hard decisions (binary_slicer_fb: x >= 0 -> 1), 32 per word: 8 lanes x 4 outputs
+        unsigned int hb = 0;
+#pragma unroll
+        for (int r = 0; r < kR; ++r) hb |= (d[r] >= 0.0f ? 1u : 0u) << r;
+        hb <<= 4 * (t & 7);
+        hb |= __shfl_xor_sync(0xffffffffu, hb, 1);
+        hb |= __shfl_xor_sync(0xffffffffu, hb, 2);
+        hb |= __shfl_xor_sync(0xffffffffu, hb, 4);
+        if ((t & 7) == 0) p.hring[(qabs & p.dmask) >> 5] = hb;
+        if (p.ydump) {
+#pragma unroll
+            for (int r = 0; r < kR; ++r) p.ydump[ql + r] = y[r];
+        }
+    }
 }
 
 __global__ void __launch_bounds__(kTB, 2) rx_front_kernel(const __grid_constant__ RxFrontParams p) {
@@ -126,65 +187,52 @@ __global__ void __launch_bounds__(kTB, 2) rx_front_kernel(const __grid_constant_
         const float2 v  = add2(add2(P0, q1), q2);
         const bool warm = i < kWarmTiles;
         const int  u    = warm ? 0 : (i - kWarmTiles) % kPassTiles;          // tile index inside the pass
-        const int  mrel = warm ? (i - kWarmTiles) * kTB + t : u * kTB + t;   // 400 kS/s index relative to the pass start
-        const int  P    = mrel >> 1;                                         // pair index (floor)
-        const int  col  = P >> kLogR;
-        if (col >= -kPorchCols)
-            reinterpret_cast<float2 *>(&sm->v[P & (kR - 1)][col + kPorchCols])[mrel & 1] = v;
+        store_v(&sm->ps, warm ? (i - kWarmTiles) * kTB + t : u * kTB + t, v);
 
         const bool pass_end = !warm && u == kPassTiles - 1;
-        if (pass_end || i == kWarmTiles - 1) {
-            // End of a pass.  The end of the warm-up only produces y[q0-1], the predecessor the
-            // quadrature demod of the CTA's first real output needs; nothing is written for it.
-            const int pc = warm ? -1 : (i - kWarmTiles) / kPassTiles;        // CTA-local pass counter
-            __syncthreads();                               // the pass's new v samples are in place
-            // ---- stage 2: 299-tap channel filter /2, kR outputs per thread
-            float2 y[kR];
-#pragma unroll
-            for (int r = 0; r < kR; ++r) y[r] = make_float2(0.f, 0.f);
-            if (!warm || t == 0) {
-                const int c0 = warm ? -1 : t;
-                channel_filter(p, &sm->v[0][c0 + kPorchCols], y);
-                if (!warm) sm->ylast[t] = y[kR - 1];
-                if (warm || t == kTB - 1) sm->ycarry[pc & 1] = y[kR - 1];
-            }
-            __syncthreads();
-            if (!warm) {
-                // the last kPorchCols columns become the history of the next pass
-                if (t < kR * kPorchCols) {
-                    const int r = t / kPorchCols, c = t % kPorchCols;
-                    sm->v[r][c] = sm->v[r][kTB + c];
-                }
-                // ---- quadrature demod: arg(y[q] * conj(y[q-1]))
-                float2 yp = t == 0 ? sm->ycarry[(pc + 1) & 1] : sm->ylast[t - 1];
-                float d[kR];
-#pragma unroll
-                for (int r = 0; r < kR; ++r) {
-                    const float zr = __fmaf_rn(y[r].y, yp.y, __fmul_rn(y[r].x, yp.x));
-                    const float zi = __fmaf_rn(y[r].y, yp.x, -__fmul_rn(y[r].x, yp.y));
-                    d[r] = atan2_spec(zi, zr);
-                    yp = y[r];
-                }
-                const unsigned long long ql = (unsigned long long)(pa + (uint32_t)pc) * kPassOut + (unsigned long long)kR * t;
-                const unsigned long long qabs = p.q_base + ql;
-                float4 *dst = reinterpret_cast<float4 *>(&p.dring[qabs & p.dmask]);
-                *dst = make_float4(d[0], d[1], d[2], d[3]);
-                // hard decisions (binary_slicer_fb: x >= 0 -> 1), 32 per word: 8 lanes x 4 outputs
-                unsigned int hb = 0;
-#pragma unroll
-                for (int r = 0; r < kR; ++r) hb |= (d[r] >= 0.0f ? 1u : 0u) << r;
-                hb <<= 4 * (t & 7);
-                hb |= __shfl_xor_sync(0xffffffffu, hb, 1);
-                hb |= __shfl_xor_sync(0xffffffffu, hb, 2);
-                hb |= __shfl_xor_sync(0xffffffffu, hb, 4);
-                if ((t & 7) == 0) p.hring[(qabs & p.dmask) >> 5] = hb;
-                if (p.ydump) {
-#pragma unroll
-                    for (int r = 0; r < kR; ++r) p.ydump[ql + r] = y[r];
-                }
-            }
-        }
+        if (pass_end || i == kWarmTiles - 1)
+            finish_pass(p, &sm->ps, warm, warm ? -1 : (i - kWarmTiles) / kPassTiles, pa, t);
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// native-rate front end: complex IQ @400 kS/s (the reference's own operating point, grc/ampsbs.grc:263).
+// No decimating first stage: v[m] = x[m] e^{-j theta m}, then exactly freq_xlating_fir_filter_ccc's filter /2 and
+// quadrature_demod_cf.  At 0.4 MS/s real time this kernel is never a bottleneck (it is FFMA-bound: 150 FFMA2 per
+// 8-byte sample); it exists so that recc_iq drops into the reference flowgraph at its native rate.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTB, 4) rx_front400_kernel(const __grid_constant__ RxFrontParams p) {
+    __shared__ PassSmem ps;
+    const int t = threadIdx.x;
+    uint32_t pa = blockIdx.x * p.pass_per_cta;
+    if (pa >= p.npass) return;
+    uint32_t pb = pa + p.pass_per_cta;
+    if (pb > p.npass) pb = p.npass;
+    auto load = [&](long L) -> float2 {                   // logical sample L of this call; L < 0 = history
+        const float2 x = L < 0 ? p.tail[(long)kPass400 + L] : p.chunk[L];
+        const unsigned long long nabs = p.n_base + (unsigned long long)(long long)L;    // (x is 0 where this wraps: stream start)
+        const uint32_t b = (uint32_t)(nabs / kD1), k = (uint32_t)(nabs % kD1);
+        return cmul(cmul(x, p.w[k]), sincos_phase(b * p.fcw25));
+    };
+    const long first = (long)pa * kPass400;
+    // warm-up: the kPorchCols columns of history in front of the first pass
+    for (int idx = t; idx < 2 * kR * kPorchCols; idx += kTB) {
+        const int mrel = idx - 2 * kR * kPorchCols;
+        store_v(&ps, mrel, load(first + mrel));
+    }
+    finish_pass(p, &ps, true, -1, pa, t);
+    for (uint32_t pc = 0; pc < pb - pa; ++pc) {
+        const long base = first + (long)pc * kPass400;
+        __syncthreads();                                   // the history shuffle of the previous pass is done
+#pragma unroll
+        for (int u = 0; u < kPassTiles; ++u) store_v(&ps, u * kTB + t, load(base + u * kTB + t));
+        finish_pass(p, &ps, false, (int)pc, pa, t);
+    }
+}
+
+cudaError_t launch_rx_front400(const RxFrontParams &p, int grid, cudaStream_t st) {
+    rx_front400_kernel<<<grid, kTB, 0, st>>>(p);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_rx_front(const RxFrontParams &p, int grid, cudaStream_t st) {
@@ -526,7 +574,7 @@ cudaError_t launch_rx_select(RxState *state, Candidate *cand, Accepted *acc, uns
 
 __global__ void __launch_bounds__(256) rx_capture_kernel(const float *__restrict__ dring, uint32_t dmask, RxState *state,
                                                         const Accepted *acc, amps_burst *host_ring, unsigned int ring_len,
-                                                        RxPublished *host_pub) {
+                                                        RxPublished *host_pub, unsigned int decim) {
     __shared__ __align__(16) unsigned char rec_raw[sizeof(amps_burst)];
     __shared__ uint8_t s_valid[40];
     __shared__ unsigned int s_errs[8];
@@ -542,7 +590,7 @@ __global__ void __launch_bounds__(256) rx_capture_kernel(const float *__restrict
     }
     if (t == 0) {
         rec->demod_index = a.pos;
-        rec->sample_index = a.pos * (unsigned long long)(kD1 * kD2);
+        rec->sample_index = a.pos * (unsigned long long)decim;
         rec->corr = a.corr;
         rec->run_length = a.run;
         rec->pad[0] = 0; rec->pad[1] = 0;
@@ -571,10 +619,11 @@ __global__ void __launch_bounds__(256) rx_capture_kernel(const float *__restrict
 }
 
 cudaError_t launch_rx_capture(const float *dring, uint32_t dmask, RxState *state, const Accepted *acc, int grid,
-                              amps_burst *host_ring, unsigned int ring_len, RxPublished *host_pub, cudaStream_t st) {
+                              amps_burst *host_ring, unsigned int ring_len, RxPublished *host_pub, unsigned int decim,
+                              cudaStream_t st) {
     if (grid <= 0) return cudaSuccess;
     if (grid > kMaxAccept) grid = kMaxAccept;
-    rx_capture_kernel<<<grid, 256, 0, st>>>(dring, dmask, state, acc, host_ring, ring_len, host_pub);
+    rx_capture_kernel<<<grid, 256, 0, st>>>(dring, dmask, state, acc, host_ring, ring_len, host_pub, decim);
     return cudaGetLastError();
 }
 

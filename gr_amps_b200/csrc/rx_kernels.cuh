@@ -21,6 +21,7 @@ constexpr int kWarmTiles = 2;                // history a CTA re-reads before it
 constexpr int kHist      = kWarmTiles * kTile;   // input history carried between calls
 constexpr int kPorchCols = 40;               // columns of v history kept in front of each row (>= (150 + 2R)/R)
 constexpr int kRowLen    = kPorchCols + kTB + 2; // pairs per row (+2: rows land 32 B apart in bank space)
+constexpr int kPass400   = kPassTiles * kTB;     // native 400 kS/s front end: 1536 input samples per pass (no CIC stage)
 
 struct RxFrontParams {
     const float2 *chunk;     // logical samples [0, npass*kPass)
@@ -32,6 +33,7 @@ struct RxFrontParams {
     uint32_t      dmask;
     uint32_t      npass;
     uint32_t      pass_per_cta;
+    unsigned long long n_base;  // 400 kS/s front end: absolute index of logical sample 0
     uint32_t      blk_base;  // absolute 25-sample block index (mod 2^32) of logical sample 0
     uint32_t      fcw25;     // NCO phase step per block (25 * fcw mod 2^32)
     float2        w[kD1];    // NCO phasors inside a block
@@ -72,6 +74,7 @@ constexpr int kMaxAccept = 512;    // bursts one call can publish
 size_t rx_front_smem_bytes();
 cudaError_t rx_configure_device();
 cudaError_t launch_rx_front(const RxFrontParams &p, int grid, cudaStream_t st);
+cudaError_t launch_rx_front400(const RxFrontParams &p, int grid, cudaStream_t st);
 cudaError_t launch_rx_detect(const float *dring, const uint32_t *hring, uint32_t dmask, RxState *state, Candidate *cand,
                              unsigned long long scan_lo, unsigned long long scan_hi, cudaStream_t st);
 // select: sorts the candidates, groups runs, picks sampling phases -> acc[0 .. state->n_acc)
@@ -80,7 +83,8 @@ cudaError_t launch_rx_select(RxState *state, Candidate *cand, Accepted *acc, uns
 // capture: one CTA per accepted burst (grid = upper bound, surplus CTAs exit): gathers the 3374 half-symbols,
 // decodes, and streams the record into host_ring[(rec_base + b) % ring_len] (mapped pinned host memory)
 cudaError_t launch_rx_capture(const float *dring, uint32_t dmask, RxState *state, const Accepted *acc, int grid,
-                              amps_burst *host_ring, unsigned int ring_len, RxPublished *host_pub, cudaStream_t st);
+                              amps_burst *host_ring, unsigned int ring_len, RxPublished *host_pub, unsigned int decim,
+                              cudaStream_t st);
 cudaError_t launch_decode_blobs(const uint8_t *blobs, int nbursts, amps_recc_words *out, cudaStream_t st);
 
 }  // namespace amps

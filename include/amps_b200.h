@@ -100,12 +100,13 @@ AMPS_B200_API int amps_b200_abi_sizes(size_t *burst_bytes, size_t *words_bytes);
  *   freq_xlating_fir_filter_ccc -> quadrature_demod_cf -> clock_recovery_mm_ff ->
  *   binary_slicer_fb (grc/ampsbs.grc:1814-1872, 774-816, 1751-1813, 1712-1750)
  *   -> amps.recc (lib/recc_impl.cc:93-145) -> burst decode (lib/recc_decode_impl.cc:81-169)
- * at samp_rate = 10 MS/s (25 x the reference's 400 kS/s).
+ * at samp_rate = 10 MS/s (25 x the reference's 400 kS/s) or at the reference's own
+ * 400 kS/s (no extrapolation stage: NCO + lpf_taps /2 + quadrature demod are then exactly the reference's blocks).
  * ------------------------------------------------------------------------------------------ */
 typedef struct amps_recc_iq amps_recc_iq;
 
 typedef struct amps_recc_iq_params {
-    double   samp_rate;          /* must be 10e6 */
+    double   samp_rate;          /* 10e6 (25 x the reference's rate; CIC^3 /25 first stage) or 400e3 (the reference's own rate, grc/ampsbs.grc:263) */
     double   center_freq;        /* carrier offset inside the band, Hz (reference: rx_offset = -160e3, grc/ampsbs.grc:212-238) */
     int      device;             /* CUDA ordinal */
     uint32_t max_samples;        /* largest nsamples ever passed in one call (sizes device buffers) */

@@ -137,6 +137,9 @@ void orc_rx_chain_f64(const float *iq, size_t n, uint32_t fcw, const float *h2, 
                       double *y_out, double *d_out);
 void orc_rx_chain_f32(const float *iq, size_t n, uint32_t fcw, const float *h2, int nh2,
                       float *y_out, float *d_out);
+/* native 400 kS/s front end (the reference's own rate): NCO -> lpf_taps /2 -> quadrature demod */
+void orc_rx_chain400_f64(const float *iq, size_t n, uint32_t fcw, const float *h2, int nh2, double *y_out, double *d_out);
+void orc_rx_chain400_f32(const float *iq, size_t n, uint32_t fcw, const float *h2, int nh2, float *y_out, float *d_out);
 /* Trigger search + soft-peak timing + capture on the demod stream d (200 kS/s, 10 samples/half-symbol).
  * Fixed-mode semantics.  Writes up to max records; returns count. */
 typedef struct {

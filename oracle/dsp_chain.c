@@ -154,6 +154,31 @@ static float spec_atan2(float y, float x) {
     return a;
 }
 
+/* stage 2 + demod of the fp32 kernel-spec chain: y[q] = E + O (FMA chains over even / odd taps, k ascending),
+ * d[q] = atan2_spec(Im, Re) of y[q] conj(y[q-1]); shared by the 10 MS/s and the native 400 kS/s front ends */
+static void spec_stage2_demod(const float *vr, const float *vi, size_t nq, const float *h2, int nh2, float *y_out, float *d_out) {
+    float pr = 0, pi_ = 0;
+    for (size_t q = 0; q < nq; q++) {
+        float er = 0, ei = 0, orr = 0, oi = 0;
+        for (int k = 0; k < nh2; k += 2) {
+            long idx = (long)(2 * q) - k;
+            float a = idx >= 0 ? vr[idx] : 0.0f, b = idx >= 0 ? vi[idx] : 0.0f;
+            er = fmaf(h2[k], a, er); ei = fmaf(h2[k], b, ei);
+        }
+        for (int k = 1; k < nh2; k += 2) {
+            long idx = (long)(2 * q) - k;
+            float a = idx >= 0 ? vr[idx] : 0.0f, b = idx >= 0 ? vi[idx] : 0.0f;
+            orr = fmaf(h2[k], a, orr); oi = fmaf(h2[k], b, oi);
+        }
+        float yr = er + orr, yi = ei + oi;
+        if (y_out) { y_out[2 * q] = yr; y_out[2 * q + 1] = yi; }
+        float zr = fmaf(yi, pi_, yr * pr);
+        float zi = fmaf(yi, pr, -(yr * pi_));
+        if (d_out) d_out[q] = spec_atan2(zi, zr);
+        pr = yr; pi_ = yi;
+    }
+}
+
 void orc_rx_chain_f32(const float *iq, size_t n, uint32_t fcw, const float *h2, int nh2,
                       float *y_out, float *d_out) {
     size_t nv = n / D1, nq = nv / 2;
@@ -200,27 +225,64 @@ void orc_rx_chain_f32(const float *iq, size_t n, uint32_t fcw, const float *h2, 
         vr[m] = (r + r1) + r2;
         vi[m] = (i + i1) + i2;
     }
-    float pr = 0, pi_ = 0;
-    for (size_t q = 0; q < nq; q++) {
-        float er = 0, ei = 0, orr = 0, oi = 0;
-        for (int k = 0; k < nh2; k += 2) {
-            long idx = (long)(2 * q) - k;
-            float a = idx >= 0 ? vr[idx] : 0.0f, b = idx >= 0 ? vi[idx] : 0.0f;
-            er = fmaf(h2[k], a, er); ei = fmaf(h2[k], b, ei);
-        }
-        for (int k = 1; k < nh2; k += 2) {
-            long idx = (long)(2 * q) - k;
-            float a = idx >= 0 ? vr[idx] : 0.0f, b = idx >= 0 ? vi[idx] : 0.0f;
-            orr = fmaf(h2[k], a, orr); oi = fmaf(h2[k], b, oi);
-        }
-        float yr = er + orr, yi = ei + oi;
-        if (y_out) { y_out[2 * q] = yr; y_out[2 * q + 1] = yi; }
-        float zr = fmaf(yi, pi_, yr * pr);
-        float zi = fmaf(yi, pr, -(yr * pi_));
-        if (d_out) d_out[q] = spec_atan2(zi, zr);
-        pr = yr; pi_ = yi;
-    }
+    spec_stage2_demod(vr, vi, nq, h2, nh2, y_out, d_out);
     free(P); free(vr); free(vi);
+}
+
+/* ------------------------------------------------------------------ native 400 kS/s front end */
+/* The reference's own operating point (grc/ampsbs.grc:263): x[m] @400 kS/s -> NCO -> lpf_taps /2 -> quadrature
+ * demod.  This IS freq_xlating_fir_filter_ccc + quadrature_demod_cf; no extrapolation stage. */
+void orc_rx_chain400_f64(const float *iq, size_t n, uint32_t fcw, const float *h2, int nh2, double *y_out, double *d_out) {
+    size_t nq = n / 2;
+    double *vr = (double *)malloc(sizeof(double) * (n ? n : 1)), *vi = (double *)malloc(sizeof(double) * (n ? n : 1));
+    for (size_t i = 0; i < n; i++) {
+        uint32_t psi = (uint32_t)((uint64_t)i * fcw);
+        double ang = 2.0 * M_PI * ((double)psi / 4294967296.0);
+        double cr = cos(ang), ci = sin(ang);
+        double xr = iq[2 * i], xi = iq[2 * i + 1];
+        vr[i] = xr * cr - xi * ci;
+        vi[i] = xr * ci + xi * cr;
+    }
+    double pr = 0, pi_ = 0;
+    for (size_t q = 0; q < nq; q++) {
+        double ar = 0, ai = 0;
+        for (int k = 0; k < nh2; k++) {
+            long idx = (long)(2 * q) - k;
+            if (idx < 0) break;
+            ar += (double)h2[k] * vr[idx];
+            ai += (double)h2[k] * vi[idx];
+        }
+        if (y_out) { y_out[2 * q] = ar; y_out[2 * q + 1] = ai; }
+        double zr = ar * pr + ai * pi_, zi = ai * pr - ar * pi_;
+        if (d_out) d_out[q] = (zr == 0.0 && zi == 0.0) ? 0.0 : atan2(zi, zr);
+        pr = ar; pi_ = ai;
+    }
+    free(vr); free(vi);
+}
+
+void orc_rx_chain400_f32(const float *iq, size_t n, uint32_t fcw, const float *h2, int nh2, float *y_out, float *d_out) {
+    size_t nq = n / 2;
+    float wr[D1], wi[D1];
+    for (int k = 0; k < D1; k++) {
+        uint32_t psi = (uint32_t)((uint32_t)k * fcw);
+        double ang = 2.0 * M_PI * ((double)psi / 4294967296.0);
+        wr[k] = (float)cos(ang); wi[k] = (float)sin(ang);
+    }
+    uint32_t fcw25 = (uint32_t)(25u * fcw);
+    float *vr = (float *)malloc(sizeof(float) * (n ? n : 1)), *vi = (float *)malloc(sizeof(float) * (n ? n : 1));
+    for (size_t i = 0; i < n; i++) {
+        /* v = (x (*) w[i mod 25]) (*) W(i div 25), each product as t = (x.re*w.re, x.re*w.im); fma(x.im, (-w.im, w.re), t) */
+        int k = (int)(i % D1);
+        float xr = iq[2 * i], xi = iq[2 * i + 1];
+        float ur = fmaf(-xi, wi[k], xr * wr[k]);
+        float ui = fmaf(xi, wr[k], xr * wi[k]);
+        float Wc, Ws;
+        spec_sincos((uint32_t)((uint32_t)(i / D1) * fcw25), &Wc, &Ws);
+        vr[i] = fmaf(-ui, Ws, ur * Wc);
+        vi[i] = fmaf(ui, Wc, ur * Ws);
+    }
+    spec_stage2_demod(vr, vi, nq, h2, nh2, y_out, d_out);
+    free(vr); free(vi);
 }
 
 /* ------------------------------------------------------------------ detection on d */

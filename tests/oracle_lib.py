@@ -97,6 +97,8 @@ def lib() -> C.CDLL:
     L.orc_nco_fcw.restype = C.c_uint32
     L.orc_rx_chain_f64.argtypes = [f32p, C.c_size_t, C.c_uint32, f32p, C.c_int, f64p, f64p]
     L.orc_rx_chain_f32.argtypes = [f32p, C.c_size_t, C.c_uint32, f32p, C.c_int, f32p, f32p]
+    L.orc_rx_chain400_f64.argtypes = [f32p, C.c_size_t, C.c_uint32, f32p, C.c_int, f64p, f64p]
+    L.orc_rx_chain400_f32.argtypes = [f32p, C.c_size_t, C.c_uint32, f32p, C.c_int, f32p, f32p]
     L.orc_rx_detect.argtypes = [f32p, C.c_size_t, C.POINTER(Burst), C.c_int]
     L.orc_cpu_baseline_run.argtypes = [f32p, C.c_size_t, C.c_uint32, f32p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
     L.orc_cpu_baseline_run.restype = C.c_double
@@ -197,6 +199,28 @@ def rx_chain_f64(x: np.ndarray, center=-160e3, fs=10e6, taps=None):
     y = np.zeros(2 * (n // 50), np.float64)
     d = np.zeros(n // 50, np.float64)
     lib().orc_rx_chain_f64(ptr(iq, f32p), n, fcw, ptr(taps, f32p), len(taps), ptr(y, f64p), ptr(d, f64p))
+    return y.view(np.complex128), d
+
+
+def rx_chain400_f32(x: np.ndarray, center=-160e3, fs=400e3, taps=None):
+    iq = iq_f32(x)
+    n = len(x) - len(x) % 2
+    taps = lpf_taps() if taps is None else taps
+    fcw = lib().orc_nco_fcw(center, fs)
+    y = np.zeros(2 * (n // 2), np.float32)
+    d = np.zeros(n // 2, np.float32)
+    lib().orc_rx_chain400_f32(ptr(iq, f32p), n, fcw, ptr(taps, f32p), len(taps), ptr(y, f32p), ptr(d, f32p))
+    return y.view(np.complex64), d
+
+
+def rx_chain400_f64(x: np.ndarray, center=-160e3, fs=400e3, taps=None):
+    iq = iq_f32(x)
+    n = len(x) - len(x) % 2
+    taps = lpf_taps() if taps is None else taps
+    fcw = lib().orc_nco_fcw(center, fs)
+    y = np.zeros(2 * (n // 2), np.float64)
+    d = np.zeros(n // 2, np.float64)
+    lib().orc_rx_chain400_f64(ptr(iq, f32p), n, fcw, ptr(taps, f32p), len(taps), ptr(y, f64p), ptr(d, f64p))
     return y.view(np.complex128), d
 
 

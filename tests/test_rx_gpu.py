@@ -189,3 +189,56 @@ def test_ring_overflow_is_reported_not_corrupting(capi):
     idx = [g.demod_index for g in got]
     assert idx == sorted(idx) and idx[-1] // (N1 // 50) == 5
     rx.close()
+
+
+# ------------------------------------------------------------------ the reference's own rate: 400 kS/s
+def burst_400k(seed, snr, words=None, n_total=55 * 1536, lead=800):
+    words = words or synth.origination_words()
+    hs = synth.manchester(synth.recc_message_bits(words))
+    return synth.fm_burst(hs, n_total, lead, samp_rate=400e3, snr_db=snr, seed=seed), hs
+
+
+@pytest.mark.parametrize("snr", [None, 20.0])
+def test_native_400k_rate_bit_exact(capi, oracle, snr):
+    """recc_iq at the reference's operating point (grc/ampsbs.grc:263): NCO + lpf_taps /2 + quadrature demod are then
+    exactly freq_xlating_fir_filter_ccc + quadrature_demod_cf; bit-exact vs the fp32 oracle, 1e-6 RMS vs float64."""
+    x, hs = burst_400k(5, snr)
+    n = len(x)
+    rx = capi.ReccIq(max_samples=n, samp_rate=400e3, dump_baseband=True)
+    assert rx.granularity == 1536
+    bursts = rx.work(x)
+    y_orc, d_orc = oracle.rx_chain400_f32(x)
+    assert bits_equal_f32(rx.read_demod(0, n // 2), d_orc)
+    y_gpu = rx.read_baseband(0, n // 2)
+    assert bits_equal_f32(y_gpu.view(np.float32), y_orc.view(np.float32))
+    y64, _ = oracle.rx_chain400_f64(x)
+    assert np.sqrt(np.mean(np.abs(y_gpu.astype(np.complex128) - y64) ** 2)) <= 1e-6
+    ob = oracle.rx_detect(d_orc)
+    assert len(bursts) == len(ob) == 1
+    b = bursts[0]
+    assert b.demod_index == ob[0][0] and b.sample_index == 2 * ob[0][0]
+    assert np.array_equal(b.symbols_np(), ob[0][2]) and np.array_equal(b.symbols_np(), hs[82:82 + 3374])
+    assert words_equal(b.decoded, oracle.recc_decode(ob[0][2])) == []
+    rx.close()
+
+
+def test_native_400k_streaming_small_chunks(capi, oracle):
+    """The real-time shape of the reference graph: small scheduler buffers (here 1..4096 samples) at 400 kS/s."""
+    parts = [burst_400k(60 + i, 18.0, w)[0] for i, w in enumerate(
+        [synth.origination_words(min10="2125550111"), synth.page_response_words(min10="2125550112"), synth.registration_words(min10="2125550113")])]
+    x = np.concatenate(parts + [np.zeros(1536, np.complex64)])
+    rx = capi.ReccIq(max_samples=8192, samp_rate=400e3)
+    rng = np.random.default_rng(4)
+    got, pos = [], 0
+    while pos < len(x):
+        n = int(rng.integers(1, 4097))
+        got += rx.work(x[pos:pos + n])
+        pos += n
+    _, d = oracle.rx_chain400_f32(x)
+    ob = oracle.rx_detect(d)
+    assert len(got) == len(ob) == 3
+    for g, o in zip(got, ob):
+        assert g.demod_index == o[0] and np.array_equal(g.symbols_np(), o[2])
+    assert [g.decoded.kind for g in got] == [4, 2, 3]
+    assert [g.decoded.min for g in got] == [b"2125550111", b"2125550112", b"2125550113"]
+    rx.close()
