@@ -130,6 +130,7 @@ struct FwdSmem {
     float2 out[kFwdTileSym * 100];             // output tile (TMA store source); its store overlaps phases 1-3a of the next tile
     float2 B[5 * (4 * kFwdTileSym + 1) + 3];   // 2 MS/s samples (carriers mixed and summed) for m = m0-1 .. m0+251
     float2 fm[kFwdMaxCar][kFwdTileSym + 1 + kFwdMaxTap4];     // FM samples for symbols i0-1-81 .. i0+62
+    alignas(16) float taps[kFwdMaxCar][4 * kFwdMaxTap4];       // polyphase taps (broadcast LDS.128 instead of constant loads)
     float2 a[kFwdMaxCar][4 * (kFwdTileSym + 1) + 16];         // 400 kS/s samples for symbols i0-1 .. i0+62 (+ slack for unrolled reads)
 };
 
@@ -149,6 +150,7 @@ __global__ void __launch_bounds__(kFwdThreads, 3) fwd_fused_kernel(const __grid_
     const int t = threadIdx.x;
     const uint32_t ntiles = (p.nsym + kFwdTileSym - 1) / kFwdTileSym;
     constexpr int kFmLen = kFwdTileSym + 1 + kFwdMaxTap4;          // 145
+    for (int i = t; i < kFwdMaxCar * 4 * kFwdMaxTap4; i += kFwdThreads) (&sm->taps[0][0])[i] = (&p.taps[0][0])[i];
 
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long i0 = (long)tile * kFwdTileSym;                  // first new symbol of the tile
@@ -182,7 +184,7 @@ __global__ void __launch_bounds__(kFwdThreads, 3) fwd_fused_kernel(const __grid_
 #pragma unroll 3
                 for (int k = 0; k < n4; ++k) {
                     const float2 xl = f[-k];                        // fm[i - k] == fm[(i+1) - (k+1)]
-                    const float4 tk = *reinterpret_cast<const float4 *>(T + 4 * k);     // uniform: LDCU.128
+                    const float4 tk = *reinterpret_cast<const float4 *>(T + 4 * k);     // same address in every lane: broadcast LDS.128
                     lo0 = fma2(splat(tk.x), xl, lo0); hi0 = fma2(splat(tk.x), xh, hi0);
                     lo1 = fma2(splat(tk.y), xl, lo1); hi1 = fma2(splat(tk.y), xh, hi1);
                     lo2 = fma2(splat(tk.z), xl, lo2); hi2 = fma2(splat(tk.z), xh, hi2);
@@ -190,9 +192,7 @@ __global__ void __launch_bounds__(kFwdThreads, 3) fwd_fused_kernel(const __grid_
                     xh = xl;
                 }
             };
-            if (c == 0) arm(p.taps[0], p.ntap4[0]);
-            else if (c == 1) arm(p.taps[1], p.ntap4[1]);
-            else arm(p.taps[2], p.ntap4[2]);
+            arm(sm->taps[c], p.ntap4[c]);
             const uint32_t m8 = p.m_base + (uint32_t)(4 * (i0 - 1 + 2 * ip));
             const float2 w25 = p.w25[c];
             // each symbol starts its own phasor recurrence, so a sample's value does not depend on how symbols pair up
