@@ -35,7 +35,8 @@ struct PassSmem {                         // what stage 2 + demod work on (share
 struct FrontSmem {
     float2   in[kStages][kTile];          // TMA landing ring
     PassSmem ps;
-    float2   pb[2][2][kTB];               // [tile parity][P1|P2][block] rotated CIC partial sums
+    float2   pb[3][2][kTB];               // [tile % 3][P1|P2][block] rotated CIC partial sums (3 buffers: a tile reads its
+                                          // own and the previous tile's, the next tile may already be writing)
     uint64_t full[kStages];
 };
 
@@ -148,8 +149,8 @@ __global__ void __launch_bounds__(kTB, 2) rx_front_kernel(const __grid_constant_
         mbar_fence_init();
     }
     // partial sums "before the first tile": they only reach samples the warm-up never uses
-    sm->pb[1][0][t] = make_float2(0.f, 0.f);
-    sm->pb[1][1][t] = make_float2(0.f, 0.f);
+    sm->pb[2][0][t] = make_float2(0.f, 0.f);
+    sm->pb[2][1][t] = make_float2(0.f, 0.f);
     __syncthreads();
     if (t == 0) {
         for (int s = 0; s < kStages && s < ntiles; ++s) issue_tile(p, sm, tile0 + s, s);
@@ -175,15 +176,15 @@ __global__ void __launch_bounds__(kTB, 2) rx_front_kernel(const __grid_constant_
         P0 = cmul(P0, W);
         P1 = cmul(P1, W);
         P2 = cmul(P2, W);
-        const int par = i & 1;
+        const int par = i % 3, prv = (i + 2) % 3;
         sm->pb[par][0][t] = P1;
         sm->pb[par][1][t] = P2;
         __syncthreads();                                   // partials visible; in[s] fully consumed
         if (t == 0 && i + kStages < ntiles) issue_tile(p, sm, tile0 + i + kStages, s);
 
         // ---- v[m] = (P0[m] + P1[m-1]) + P2[m-2], stored into the pair/row layout
-        const float2 q1 = t >= 1 ? sm->pb[par][0][t - 1] : sm->pb[par ^ 1][0][kTB - 1];
-        const float2 q2 = t >= 2 ? sm->pb[par][1][t - 2] : sm->pb[par ^ 1][1][kTB - 2 + t];
+        const float2 q1 = t >= 1 ? sm->pb[par][0][t - 1] : sm->pb[prv][0][kTB - 1];
+        const float2 q2 = t >= 2 ? sm->pb[par][1][t - 2] : sm->pb[prv][1][kTB - 2 + t];
         const float2 v  = add2(add2(P0, q1), q2);
         const bool warm = i < kWarmTiles;
         const int  u    = warm ? 0 : (i - kWarmTiles) % kPassTiles;          // tile index inside the pass

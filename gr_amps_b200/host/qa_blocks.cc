@@ -5,11 +5,13 @@
 //
 //   qa_blocks focc <symrate> <aggr 0|1> <total_bytes> <seed> <out.bin>
 //   qa_blocks loop <iq.bin> <nsamples> <chunk> <focc_bytes> <out_prefix>
+//   qa_blocks fwd <nsym> <out.bin>
 #include <amps/focc.h>
 #include <amps/fvc.h>
 #include <amps/recc.h>
 #include <amps/recc_decode.h>
 #include <amps/recc_iq.h>
+#include <amps_b200.h>
 
 #include <complex>
 #include <cstdio>
@@ -151,11 +153,48 @@ static int run_loop(int argc, char **argv) {
     return 0;
 }
 
+// forward path straight through the C ABI: FOCC block bytes + two FVC alert trains -> amps_fwd_work -> file
+static int run_fwd(int argc, char **argv) {
+    if (argc < 4) return 2;
+    const size_t nsym = std::strtoull(argv[2], NULL, 10);
+    focc::sptr fo = focc::make(100000, false);
+    std::vector<unsigned char> s0, buf(1 << 16);
+    gr_vector_const_void_star noin;
+    gr_vector_void_star outs(1);
+    while (s0.size() < nsym) {
+        outs[0] = buf.data();
+        const int r = fo->work((int)(nsym - s0.size() < buf.size() ? nsym - s0.size() : buf.size()), noin, outs);
+        if (r < 0) return 3;
+        s0.insert(s0.end(), buf.begin(), buf.begin() + r);
+    }
+    std::vector<unsigned char> s1(nsym), s2(nsym, 0);
+    for (size_t i = 0; i < nsym; i++) s1[i] = ((i / 5) & 1) ? 0x01 : 0xFF;          // dotting on the second carrier, third muted
+    amps_fwd_params p;
+    std::memset(&p, 0, sizeof p);
+    p.samp_rate = 10e6; p.symrate = 100e3; p.max_deviation = 8000; p.device = 0; p.ncarriers = 3;
+    p.carrier_freq[0] = 0; p.carrier_freq[1] = 60e3; p.carrier_freq[2] = 90e3;
+    p.lpf_transition[0] = 5e3; p.lpf_transition[1] = 3e3; p.lpf_transition[2] = 3e3;
+    p.out_scale = 0.5f; p.max_samples = (uint32_t)(nsym * 100);
+    amps_fwd *h = NULL;
+    if (amps_fwd_create(&p, &h) != AMPS_OK) { std::fprintf(stderr, "%s\n", amps_b200_last_error()); return 4; }
+    std::vector<float> out(2 * nsym * 100);
+    const uint8_t *syms[3] = {s0.data(), s1.data(), s2.data()};
+    size_t half = nsym / 2;                                                         // two calls: exercises the carried history
+    if (amps_fwd_work(h, syms, half, out.data()) != AMPS_OK) return 5;
+    const uint8_t *syms2[3] = {s0.data() + half, s1.data() + half, s2.data() + half};
+    if (amps_fwd_work(h, syms2, nsym - half, out.data() + 2 * half * 100) != AMPS_OK) return 6;
+    amps_fwd_destroy(h);
+    std::ofstream(argv[3], std::ios::binary).write(reinterpret_cast<const char *>(out.data()), (std::streamsize)(out.size() * sizeof(float)));
+    std::printf("{\"samples\": %zu}\n", nsym * 100);
+    return 0;
+}
+
 int main(int argc, char **argv) {
-    if (argc < 2) { std::fprintf(stderr, "usage: qa_blocks focc|loop ...\n"); return 2; }
+    if (argc < 2) { std::fprintf(stderr, "usage: qa_blocks focc|loop|fwd ...\n"); return 2; }
     try {
         if (!std::strcmp(argv[1], "focc")) return run_focc(argc, argv);
         if (!std::strcmp(argv[1], "loop")) return run_loop(argc, argv);
+        if (!std::strcmp(argv[1], "fwd")) return run_fwd(argc, argv);
     } catch (const std::exception &e) {
         std::fprintf(stderr, "qa_blocks: %s\n", e.what());
         return 10;

@@ -1,0 +1,26 @@
+#!/bin/bash
+# compute-sanitizer passes over the C++ QA driver (no Python / torch in the process): memcheck, racecheck, synccheck
+# on the closed-loop scenario (recc_iq front/detect/select/capture kernels, decode, focc/fvc byte kernels).
+# usage (GPU box): bash tools/sanitize.sh  -> writes gpurun_out/sanitize_*.log
+set -u
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out /tmp/san
+python - <<'PY'
+import sys, numpy as np
+sys.path.insert(0, '.')
+from gr_amps_b200 import synth
+period = 55 * 38400
+msgs = [synth.origination_words(min10="2125550101"), synth.page_response_words(min10="2125550102")]
+parts = [synth.burst_period(w, n_total=period, snr_db=20.0, seed=40 + i)[0] for i, w in enumerate(msgs)]
+x = np.concatenate(parts + [np.zeros(38400, np.complex64)])
+x.tofile('/tmp/san/iq.bin')
+open('/tmp/san/n.txt', 'w').write(str(len(x)))
+PY
+N=$(cat /tmp/san/n.txt)
+QA=gr_amps_b200/host/qa_blocks
+for tool in memcheck racecheck synccheck; do
+  timeout 1200 compute-sanitizer --tool $tool --error-exitcode 9 $QA loop /tmp/san/iq.bin $N 262144 87970 /tmp/san/out > gpurun_out/sanitize_$tool.log 2>&1
+  echo "loop $tool rc=$? $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' gpurun_out/sanitize_$tool.log | tail -1)"
+  timeout 1200 compute-sanitizer --tool $tool --error-exitcode 9 $QA fwd 20000 /tmp/san/fwd.bin > gpurun_out/sanitize_fwd_$tool.log 2>&1
+  echo "fwd  $tool rc=$? $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' gpurun_out/sanitize_fwd_$tool.log | tail -1)"
+done
