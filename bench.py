@@ -149,10 +149,11 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def measure_fwd(local_rank, steps, warmup):
+def measure_fwd(local_rank, steps, warmup, bits=False):
     """BASELINE config 3 on this rank's GPU: FOCC @0 Hz + FVC @+60 kHz + FVC @+90 kHz, x0.5 -> 10 MS/s complex,
     device resident.  Algorithmic bytes: 8 B written per output sample (+ 3 symbol bytes per 100 samples read).
-    Returns (samples per step, ms per step)."""
+    bits=False: half-symbol input (amps_fwd_submit_dev); bits=True: data-bit input, the Manchester fast path
+    (amps_fwd_submit_bits_dev).  Returns (samples per step, ms per step)."""
     import torch
     from gr_amps_b200 import capi
     dev = torch.device("cuda", local_rank)
@@ -175,14 +176,21 @@ def measure_fwd(local_rank, steps, warmup):
     out = torch.empty(2 * nsym * 100, dtype=torch.float32, device=dev)
     fw = capi.Fwd(max_samples=nsym * 100, device=local_rank)
     stream = torch.cuda.current_stream()
-    ptrs = [s.data_ptr() for s in syms]
+    if bits:
+        # one byte per data bit: the second half-symbol of a bit is high for a 1 (lib/amps_packet.h:52-70)
+        syms = [(s.view(-1, 10)[:, 5] == 1).to(torch.uint8).contiguous() for s in syms]
+        nunits = nsym // 10
+        submit = lambda: fw.submit_bits_dev([s.data_ptr() for s in syms], nunits, out.data_ptr(), stream.cuda_stream)
+    else:
+        ptrs = [s.data_ptr() for s in syms]
+        submit = lambda: fw.submit_dev(ptrs, nsym, out.data_ptr(), stream.cuda_stream)
     for _ in range(max(warmup, 3)):
-        fw.submit_dev(ptrs, nsym, out.data_ptr(), stream.cuda_stream)
+        submit()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(steps):
-        fw.submit_dev(ptrs, nsym, out.data_ptr(), stream.cuda_stream)
+        submit()
     e1.record(stream)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
@@ -198,7 +206,8 @@ def run_fwd(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    n, ms = measure_fwd(local_rank, args.steps, args.warmup)
+    n, ms = measure_fwd(local_rank, args.steps, args.warmup, bits=True)
+    _, ms_general = measure_fwd(local_rank, args.steps, args.warmup, bits=False)
     clocks = sampler.stop()
     peak, peak_src = load_peaks()
     achieved = (8.0 * n + 0.03 * n) / (ms * 1e-3) / 1e9
@@ -207,8 +216,10 @@ def run_fwd(args, rank, local_rank, world):
         "unit": "Msamples/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
         "higher_is_better": True, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "config3: FOCC@0 + FVC@+60k + FVC@+90k, x0.5, 10 MS/s out, device resident", "samples_per_step": n},
-        "roofline": {"bound": "hbm", "kernel": "fwd_fused_kernel (+2 scan kernels)", "achieved": achieved, "peak": peak,
+        "roofline": {"bound": "hbm", "kernel": "fwd_bits_kernel (data-bit input, Manchester fast path)", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": None},
+        "general_path": {"kernel": "fwd_fused_kernel (+2 scan kernels), half-symbol input", "ms_per_step": ms_general,
+                         "value": n / (ms_general * 1e-3) / 1e6, "frac": 8.03 * n / (ms_general * 1e-3) / 1e9 / peak},
         "clocks": clocks}), flush=True)
     return 0
 
@@ -342,7 +353,7 @@ def main():
     rx.close(); rx2.close()
     torch.cuda.empty_cache()
     barrier()
-    fwd_n, fwd_ms = measure_fwd(local_rank, 20, 3)
+    fwd_n, fwd_ms = measure_fwd(local_rank, 20, 3, bits=True)
     fwd_total, fwd_ms_max = multi.whole_job_throughput(float(fwd_n), fwd_ms, dev)
 
     if rank != 0:
@@ -394,7 +405,7 @@ def main():
         "e2e": {"value": e2e_samples / e2e_sec / 1e6, "unit": "Msamples/s",
                 "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": int(rec_bytes), "steps": e2e_steps,
                 "api": "amps_recc_iq_work (pinned host buffer, burst callbacks)"},
-        "forward": {"metric": "Msamples/s out of the fused forward path (config 3: FOCC + 2 FVC carriers per GPU)",
+        "forward": {"metric": "Msamples/s out of the fused forward path (config 3: FOCC + 2 FVC carriers per GPU, data-bit input)",
                     "value": fwd_total / (fwd_ms_max * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": fwd_ms_max,
                     "hbm_frac": 8.03 * fwd_n / (fwd_ms * 1e-3) / 1e9 / peak},
         "gpu_launches": int(launches) * world,

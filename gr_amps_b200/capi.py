@@ -95,7 +95,7 @@ EXPORTS = [
     "amps_focc_push_words", "amps_focc_set_busy_idle",
     "amps_fvc_create", "amps_fvc_destroy", "amps_fvc_push_words", "amps_fvc_work",
     "amps_fwd_create", "amps_fwd_destroy", "amps_fwd_reset", "amps_fwd_work", "amps_fwd_submit_dev",
-    "amps_fwd_interp", "amps_fwd_get_taps",
+    "amps_fwd_interp", "amps_fwd_get_taps", "amps_fwd_work_bits", "amps_fwd_submit_bits_dev",
 ]
 
 _lib = None
@@ -162,6 +162,8 @@ def lib() -> C.CDLL:
         L.amps_fwd_work.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_size_t, f32p]
         L.amps_fwd_submit_dev.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_size_t, C.c_void_p, C.c_void_p]
         L.amps_fwd_interp.argtypes = [C.c_void_p]
+        L.amps_fwd_work_bits.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_size_t, f32p]
+        L.amps_fwd_submit_bits_dev.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_size_t, C.c_void_p, C.c_void_p]
         L.amps_fwd_get_taps.argtypes = [C.c_void_p, C.c_int, f32p, C.c_int]
     _lib = L
     return L
@@ -418,3 +420,16 @@ class Fwd:
     def submit_dev(self, dev_ptrs, nsym: int, out_ptr: int, stream: int = 0):
         ptrs = (C.c_void_p * 3)(*list(dev_ptrs) + [None] * (3 - len(dev_ptrs)))
         check(lib().amps_fwd_submit_dev(self.h, ptrs, nsym, C.c_void_p(out_ptr), C.c_void_p(stream)))
+
+    def work_bits(self, bits) -> np.ndarray:
+        """Manchester-bit fast path: bits = list of uint8 arrays (0, 1, 0xFF = muted); 1000 output samples per bit."""
+        arrs = [np.ascontiguousarray(b, dtype=np.uint8) for b in bits]
+        nbits = len(arrs[0])
+        ptrs = (C.c_void_p * 3)(*[a.ctypes.data for a in arrs] + [None] * (3 - len(arrs)))
+        out = np.zeros(2 * nbits * 1000, np.float32)
+        check(lib().amps_fwd_work_bits(self.h, ptrs, nbits, out.ctypes.data_as(f32p)))
+        return out.view(np.complex64)
+
+    def submit_bits_dev(self, dev_ptrs, nbits: int, out_ptr: int, stream: int = 0):
+        ptrs = (C.c_void_p * 3)(*list(dev_ptrs) + [None] * (3 - len(dev_ptrs)))
+        check(lib().amps_fwd_submit_bits_dev(self.h, ptrs, nbits, C.c_void_p(out_ptr), C.c_void_p(stream)))

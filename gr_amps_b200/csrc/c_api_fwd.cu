@@ -24,6 +24,14 @@ struct amps_fwd {
     int hist_cur = 0;
     float2 *d_out = nullptr;                  // host-path staging
     uint64_t sym_total = 0;
+    // Manchester-bit fast path
+    FwdBitsParams bp{};
+    float2 *d_resp = nullptr;                 // [ncar][2][360] per-bit responses of the x4 interpolator
+    uint8_t *d_bits[kFwdMaxCar] = {};         // host-path staging
+    uint8_t *d_hbits[2][kFwdMaxCar] = {};
+    int hbits_cur = 0;
+    uint64_t bit_total = 0;
+    int mode = 0;                             // 0 unset, 1 symbol stream, 2 bit stream (no mixing without reset)
 };
 
 static int fwd_reset_state(amps_fwd *h) {
@@ -33,8 +41,10 @@ static int fwd_reset_state(amps_fwd *h) {
             CK(cudaMemset(h->d_hS[b][c], 0, sizeof(int32_t) * kFwdHistLen));
         }
     CK(cudaMemset(h->d_carry, 0, sizeof(int32_t) * kFwdMaxCar));
-    h->hist_cur = 0;
-    h->sym_total = 0;
+    for (int b = 0; b < 2; ++b)
+        for (int c = 0; c < kFwdMaxCar; ++c) CK(cudaMemset(h->d_hbits[b][c], 0xFF, 16));    // "muted" before the stream starts
+    h->hist_cur = 0; h->hbits_cur = 0;
+    h->sym_total = 0; h->bit_total = 0; h->mode = 0;
     return AMPS_OK;
 }
 
@@ -80,6 +90,44 @@ extern "C" int amps_fwd_create(const amps_fwd_params *p, amps_fwd **out) {
         }
         h->fp.w25[c] = make_float2(ph[50], ph[51]);
     }
+    // ---- Manchester-bit fast path tables: response of the x4 interpolator to one bit's 10 FM samples
+    {
+        std::memset(&h->bp, 0, sizeof h->bp);
+        h->bp.ncar = h->ncar;
+        std::vector<float> resp((size_t)h->ncar * 2 * kFbRespLen * 2, 0.0f);
+        const double kTwoPi = 6.283185307179586476925286766559;
+        for (int c = 0; c < h->ncar; ++c) {
+            const int nt = (int)h->taps[c].size();
+            for (int b = 0; b < 2; ++b) {
+                for (int u = 0; u < kFbRespLen; ++u) {
+                    double re = 0, im = 0;
+                    int S = 0;
+                    for (int i = 0; i < kFbSymPerBit; ++i) {
+                        const int half_sym = i < 5 ? (b ? -1 : +1) : (b ? +1 : -1);     // bit 1 -> (low, high), bit 0 -> (high, low)
+                        S += half_sym;
+                        const int k = u - 4 * i;
+                        if (k < 0 || k >= nt) continue;
+                        const uint32_t psi = (uint32_t)S * h->fp.fcw_fm;
+                        const double ang = kTwoPi * ((double)psi / 4294967296.0);
+                        re += (double)h->taps[c][(size_t)k] * std::cos(ang);
+                        im += (double)h->taps[c][(size_t)k] * std::sin(ang);
+                    }
+                    const size_t o = (((size_t)c * 2 + (size_t)b) * kFbRespLen + (size_t)u) * 2;
+                    resp[o] = (float)re; resp[o + 1] = (float)im;
+                }
+            }
+            const uint32_t fcw = nco_fcw(-p->carrier_freq[c], p->samp_rate);
+            h->bp.fcw_mix1000[c] = (uint32_t)(1000u * fcw);
+            std::vector<float> ph(2 * kFbMPerBit);
+            nco_block_table((uint32_t)(25u * fcw), kFbMPerBit, ph.data());       // e^{j phi_c(25 u)}, u < 40
+            for (int u = 0; u < kFbMPerBit; ++u) h->bp.w40[c][u] = make_float2(ph[2 * (size_t)u], ph[2 * (size_t)u + 1]);
+            std::memcpy(h->bp.C1[c], h->fp.C1[c], sizeof h->bp.C1[c]);
+        }
+        std::memcpy(h->bp.G2, h->fp.G2, sizeof h->bp.G2);
+        CK(cudaMalloc(&h->d_resp, resp.size() * sizeof(float)));
+        CK(cudaMemcpy(h->d_resp, resp.data(), resp.size() * sizeof(float), cudaMemcpyHostToDevice));
+        h->bp.resp = h->d_resp;
+    }
     cudaError_t ce = fwd_configure_device();
     if (ce != cudaSuccess) { delete h; return set_cuda_error(ce, "fwd_configure_device"); }
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -93,6 +141,10 @@ extern "C" int amps_fwd_create(const amps_fwd_params *p, amps_fwd **out) {
             CK(cudaMalloc(&h->d_hsym[b][c], kFwdHistLen));
             CK(cudaMalloc(&h->d_hS[b][c], sizeof(int32_t) * kFwdHistLen));
         }
+    }
+    for (int c = 0; c < kFwdMaxCar; ++c) {
+        CK(cudaMalloc(&h->d_bits[c], h->max_sym / kFbSymPerBit + 16));
+        for (int b = 0; b < 2; ++b) CK(cudaMalloc(&h->d_hbits[b][c], 16));
     }
     CK(cudaMalloc(&h->d_carry, sizeof(int32_t) * kFwdMaxCar));
     CK(cudaMalloc(&h->d_out, sizeof(float2) * (size_t)h->max_sym * kFwdInterp));
@@ -111,7 +163,8 @@ extern "C" int amps_fwd_destroy(amps_fwd *h) {
         cudaFree(h->d_sym[c]); cudaFree(h->d_sloc[c]); cudaFree(h->d_btot[c]); cudaFree(h->d_boff[c]);
         for (int b = 0; b < 2; ++b) { cudaFree(h->d_hsym[b][c]); cudaFree(h->d_hS[b][c]); }
     }
-    cudaFree(h->d_carry); cudaFree(h->d_out);
+    for (int c = 0; c < kFwdMaxCar; ++c) { cudaFree(h->d_bits[c]); cudaFree(h->d_hbits[0][c]); cudaFree(h->d_hbits[1][c]); }
+    cudaFree(h->d_carry); cudaFree(h->d_out); cudaFree(h->d_resp);
     delete h;
     return AMPS_OK;
 }
@@ -138,6 +191,8 @@ extern "C" int amps_fwd_submit_dev(amps_fwd *h, const void *const *d_sym, size_t
     if (nsym > h->max_sym) return set_error(AMPS_E_OVERFLOW, "nsym exceeds max_samples / 100");
     if (reinterpret_cast<uintptr_t>(d_out_iq) & 15u) return set_error(AMPS_E_ALIGN, "d_out_iq must be 16-byte aligned");
     for (int c = 0; c < h->ncar; ++c) if (!d_sym[c]) return set_error(AMPS_E_INVAL, "null symbol stream");
+    if (h->mode == 2) return set_error(AMPS_E_STATE, "handle is streaming data bits; reset() before switching to half-symbol input");
+    h->mode = 1;
     CK(cudaSetDevice(h->device));
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     const int cur = h->hist_cur, nxt = cur ^ 1;
@@ -181,6 +236,65 @@ extern "C" int amps_fwd_work(amps_fwd *h, const uint8_t *const *sym, size_t nsym
     int rc = amps_fwd_submit_dev(h, dptr, nsym, h->d_out, h->stream);
     if (rc != AMPS_OK) return rc;
     CK(cudaMemcpyAsync(out_iq_host, h->d_out, sizeof(float2) * nsym * kFwdInterp, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return AMPS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Manchester-bit fast path: one byte per 10 kbit/s data bit (0, 1, 0xFF = muted), 1000 output samples per bit
+// ---------------------------------------------------------------------------------------------
+extern "C" int amps_fwd_submit_bits_dev(amps_fwd *h, const void *const *d_bits, size_t nbits, void *d_out_iq, void *cuda_stream) {
+    if (!h || !d_bits || (nbits && !d_out_iq)) return set_error(AMPS_E_INVAL, "null argument");
+    if (nbits == 0) return AMPS_OK;
+    if (nbits * kFbSymPerBit > h->max_sym) return set_error(AMPS_E_OVERFLOW, "nbits exceeds max_samples / 1000");
+    if (reinterpret_cast<uintptr_t>(d_out_iq) & 15u) return set_error(AMPS_E_ALIGN, "d_out_iq must be 16-byte aligned");
+    for (int c = 0; c < h->ncar; ++c) if (!d_bits[c]) return set_error(AMPS_E_INVAL, "null bit stream");
+    if (h->mode == 1) return set_error(AMPS_E_STATE, "handle is streaming half-symbols; reset() before switching to data-bit input");
+    h->mode = 2;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    const int cur = h->hbits_cur, nxt = cur ^ 1;
+    FwdBitsParams p = h->bp;
+    for (int c = 0; c < kFwdMaxCar; ++c) {
+        const int cc = c < h->ncar ? c : 0;
+        p.bits[c] = static_cast<const uint8_t *>(d_bits[cc]);
+        p.hbits[c] = h->d_hbits[cur][c];
+    }
+    p.out = static_cast<float2 *>(d_out_iq);
+    p.nbits = (uint32_t)nbits;
+    p.bit_base = h->bit_total;
+    const uint32_t ntiles = ((uint32_t)nbits + kFbTileBits - 1) / kFbTileBits;
+    uint32_t grid = 3u * (uint32_t)h->sm_count;
+    if (grid > ntiles) grid = ntiles;
+    CKL(launch_fwd_bits(p, (int)grid, st));
+    // history for the next call: the last kFbHistBits of (old history ++ these bits)
+    for (int c = 0; c < h->ncar; ++c) {
+        if (nbits >= (size_t)kFbHistBits) {
+            CK(cudaMemcpyAsync(h->d_hbits[nxt][c], p.bits[c] + (nbits - kFbHistBits), kFbHistBits, cudaMemcpyDeviceToDevice, st));
+        } else {
+            CK(cudaMemcpyAsync(h->d_hbits[nxt][c], h->d_hbits[cur][c] + nbits, kFbHistBits - nbits, cudaMemcpyDeviceToDevice, st));
+            CK(cudaMemcpyAsync(h->d_hbits[nxt][c] + (kFbHistBits - nbits), p.bits[c], nbits, cudaMemcpyDeviceToDevice, st));
+        }
+    }
+    h->hbits_cur = nxt;
+    h->bit_total += nbits;
+    return AMPS_OK;
+}
+
+extern "C" int amps_fwd_work_bits(amps_fwd *h, const uint8_t *const *bits, size_t nbits, float *out_iq_host) {
+    if (!h || !bits || (nbits && !out_iq_host)) return set_error(AMPS_E_INVAL, "null argument");
+    if (nbits == 0) return AMPS_OK;
+    if (nbits * kFbSymPerBit > h->max_sym) return set_error(AMPS_E_OVERFLOW, "nbits exceeds max_samples / 1000");
+    CK(cudaSetDevice(h->device));
+    const void *dptr[kFwdMaxCar] = {};
+    for (int c = 0; c < h->ncar; ++c) {
+        if (!bits[c]) return set_error(AMPS_E_INVAL, "null bit stream");
+        CK(cudaMemcpyAsync(h->d_bits[c], bits[c], nbits, cudaMemcpyHostToDevice, h->stream));
+        dptr[c] = h->d_bits[c];
+    }
+    int rc = amps_fwd_submit_bits_dev(h, dptr, nbits, h->d_out, h->stream);
+    if (rc != AMPS_OK) return rc;
+    CK(cudaMemcpyAsync(out_iq_host, h->d_out, sizeof(float2) * nbits * kFbOutPerBit, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return AMPS_OK;
 }

@@ -265,7 +265,136 @@ __global__ void __launch_bounds__(kFwdThreads, 3) fwd_fused_kernel(const __grid_
     if (t == 0) tma_store_wait_all();
 }
 
+// ---------------------------------------------------------------------------------------------
+// Manchester-bit fast path.  Every FOCC / FVC data bit is the half-symbol pair (-1 x5, +1 x5) or (+1 x5, -1 x5), so
+// the FM phase returns to zero at every bit boundary and the modulator output over one bit is one of two fixed
+// 10-sample waveforms.  The x4 polyphase interpolator is linear, hence its 400 kS/s output is a sum of per-bit
+// responses: a[m] = sum_{d<9} R[bit(q-d)][(m - 40 q) + 40 d], q = m div 40 -- nine table lookups instead of 49..81
+// taps, no prefix sum, no sincos per sample ("closed-form Manchester symbol lookup").
+// The rest (x5 CIC^3 with folded mixers, carriers summed at 2 MS/s, shared x5 CIC^3, TMA bulk store) is the same.
+// ---------------------------------------------------------------------------------------------
+struct FwdBitsSmem {
+    float2  out[kFbTileM * 25];                               // 5000 output samples (TMA store source)
+    float2  B[5 * (kFbTileM + 1) + 3];
+    float2  a[kFwdMaxCar][kFbTileM + 4];                      // rotated 400 kS/s samples m0-4 .. m0+199
+    float2  resp[kFwdMaxCar][2][kFbRespLen];
+    float2  Wq[kFwdMaxCar][kFbTileBits + 1];                  // mixer phasor at the start of bits q0-1 .. q0+4
+    uint8_t bits[kFwdMaxCar][kFbTileBits + kFbHistBits + 1 + 3];   // bits q0-10 .. q0+4
+};
+
+size_t fwd_bits_smem_bytes() { return sizeof(FwdBitsSmem); }
+
+__global__ void __launch_bounds__(kFwdThreads, 3) fwd_bits_kernel(const __grid_constant__ FwdBitsParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    FwdBitsSmem *sm = reinterpret_cast<FwdBitsSmem *>(smem_raw);
+    const int t = threadIdx.x;
+    const uint32_t ntiles = (p.nbits + kFbTileBits - 1) / kFbTileBits;
+    for (int i = t; i < p.ncar * 2 * kFbRespLen; i += kFwdThreads) (&sm->resp[0][0][0])[i] = p.resp[i];
+
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long q0 = (long)tile * kFbTileBits;                  // first bit of the tile (call-local)
+        const int nvalid = (int)((long)p.nbits - q0 < kFbTileBits ? (long)p.nbits - q0 : kFbTileBits);
+        // ---- bits q0-10 .. q0+4 and the per-bit mixer phasors
+        constexpr int kNB = kFbTileBits + kFbHistBits + 1;         // 15
+        if (t < p.ncar * kNB) {
+            const int c = t / kNB, k = t - c * kNB;
+            const long q = q0 - (kFbHistBits + 1) + k;
+            uint8_t b = 0xFF;
+            if (q >= (long)p.nbits) b = 0xFF;
+            else if (q >= 0) b = p.bits[c][q];
+            else if (q >= -(long)kFbHistBits) b = p.hbits[c][kFbHistBits + q];
+            sm->bits[c][k] = b;
+        } else if (t >= 64 && t < 64 + p.ncar * (kFbTileBits + 1)) {
+            const int idx = t - 64, c = idx / (kFbTileBits + 1), k = idx - c * (kFbTileBits + 1);
+            const uint32_t qabs = (uint32_t)(p.bit_base + (unsigned long long)(q0 - 1 + k));
+            sm->Wq[c][k] = sincos_phase(qabs * p.fcw_mix1000[c]);
+        }
+        __syncthreads();
+
+        // ---- phase A: 400 kS/s samples by table lookup, rotated by the carrier NCO.  thread = one sample m0-4+t
+        if (t < kFbTileM + 4) {
+            const int mrel = t - 4;                                 // relative to the tile's first sample
+            const int qrel = mrel >= 0 ? mrel / kFbMPerBit : -1;     // bit containing it, relative to q0
+            const int u0 = mrel - qrel * kFbMPerBit;                // 0..39
+#pragma unroll
+            for (int c = 0; c < kFwdMaxCar; ++c) {
+                if (c < p.ncar) {
+                    float2 acc = make_float2(0.f, 0.f);
+                    const uint8_t *bq = &sm->bits[c][qrel + kFbHistBits + 1];      // bit q0 + qrel
+#pragma unroll
+                    for (int d = 0; d < kFbRespBits; ++d) {
+                        const uint8_t b = bq[-d];
+                        if (b <= 1) acc = add2(acc, sm->resp[c][b][u0 + kFbMPerBit * d]);
+                    }
+                    const float2 W = cmul(sm->Wq[c][qrel + 1], p.w40[c][u0]);
+                    sm->a[c][t] = cmul(acc, W);
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- phase 3a: x5 CIC^3 to 2 MS/s with folded mixers, carriers summed (as in fwd_fused_kernel)
+        if (t < kFbTileM + 1) {
+            float2 acc[5];
+#pragma unroll
+            for (int r = 0; r < 5; ++r) acc[r] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int c = 0; c < kFwdMaxCar; ++c) {
+                if (c < p.ncar) {
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        const float2 x = sm->a[c][t + 3 - j];
+                        const float2 xr = splat(x.x), xi = splat(x.y);
+#pragma unroll
+                        for (int r = 0; r < 5; ++r) {
+                            if (r + 5 * j < 13) {
+                                const float2 C = p.C1[c][r + 5 * j];
+                                acc[r] = fma2(xi, make_float2(-C.y, C.x), fma2(xr, C, acc[r]));
+                            }
+                        }
+                    }
+                }
+            }
+            float2 *Bo = &sm->B[5 * t];
+#pragma unroll
+            for (int r = 0; r < 5; ++r) Bo[r] = acc[r];
+        }
+        if (t == 0) tma_store_wait_read0();
+        __syncthreads();
+
+        // ---- phase 3b: shared x5 CIC^3 to 10 MS/s
+        if (t < kFbMPerBit * nvalid) {
+            const float2 *Bi = &sm->B[5 * (t + 1)];
+            float2 b[7];
+#pragma unroll
+            for (int k = 0; k < 7; ++k) b[k] = Bi[k - 2];
+            float2 *o = &sm->out[25 * t];
+#pragma unroll
+            for (int qq = 0; qq < 5; ++qq)
+#pragma unroll
+                for (int r = 0; r < 5; ++r) {
+                    float2 v = mul2(splat(p.G2[r]), b[qq + 2]);
+                    v = fma2(splat(p.G2[r + 5]), b[qq + 1], v);
+                    if (r + 10 < 13) v = fma2(splat(p.G2[r + 10]), b[qq], v);
+                    o[5 * qq + r] = v;
+                }
+        }
+        fence_async_smem();
+        __syncthreads();
+        if (t == 0) tma_store_1d(p.out + (size_t)q0 * kFbOutPerBit, sm->out, (uint32_t)nvalid * kFbOutPerBit * (uint32_t)sizeof(float2));
+    }
+    if (t == 0) tma_store_wait_all();
+}
+
+cudaError_t launch_fwd_bits(const FwdBitsParams &p, int grid, cudaStream_t st) {
+    if (p.nbits == 0) return cudaSuccess;
+    fwd_bits_kernel<<<grid, kFwdThreads, sizeof(FwdBitsSmem), st>>>(p);
+    return cudaGetLastError();
+}
+
 cudaError_t fwd_configure_device() {
+    cudaError_t e = cudaFuncSetAttribute(fwd_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FwdBitsSmem));
+    if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(fwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FwdSmem));
 }
 

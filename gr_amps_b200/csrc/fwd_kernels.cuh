@@ -45,6 +45,32 @@ struct FwdParams {
     float          taps[kFwdMaxCar][4 * kFwdMaxTap4];
 };
 
+// ---- Manchester-bit fast path: input is one byte per 10 kbit/s data bit (0, 1, 0xFF = muted) instead of half-symbol samples
+constexpr int kFbTileBits  = 5;                  // bits per tile -> 200 samples @400 kS/s -> 5000 output samples
+constexpr int kFbSymPerBit = 10;                 // 100 kS/s FM samples per bit (2 half-symbols x 5)
+constexpr int kFbMPerBit   = 40;                 // 400 kS/s samples per bit
+constexpr int kFbOutPerBit = 1000;               // 10 MS/s samples per bit
+constexpr int kFbRespBits  = 9;                  // bits whose response overlaps one 400 kS/s sample: ceil((40 + 320) / 40)
+constexpr int kFbRespLen   = kFbRespBits * kFbMPerBit;   // 360
+constexpr int kFbHistBits  = 9;                  // bits of history a call needs from the previous one
+constexpr int kFbTileM     = kFbTileBits * kFbMPerBit;   // 200
+
+struct FwdBitsParams {
+    const uint8_t *bits[kFwdMaxCar];             // this call's bits
+    const uint8_t *hbits[kFwdMaxCar];            // previous call's last kFbHistBits bits (0xFF at stream start)
+    const float2  *resp;                         // [ncar][2][kFbRespLen] response of the x4 interpolator to one Manchester bit
+    float2        *out;
+    uint32_t       nbits;
+    int            ncar;
+    unsigned long long bit_base;                 // absolute index of this call's first bit
+    uint32_t       fcw_mix1000[kFwdMaxCar];      // mixer phase step per bit (1000 output samples)
+    float2         w40[kFwdMaxCar][kFbMPerBit];  // mixer phasors of the 40 400-kS/s steps inside a bit
+    float2         C1[kFwdMaxCar][15];
+    float          G2[15];
+};
+
+size_t fwd_bits_smem_bytes();
+cudaError_t launch_fwd_bits(const FwdBitsParams &p, int grid, cudaStream_t st);
 size_t fwd_smem_bytes();
 cudaError_t fwd_configure_device();
 cudaError_t launch_fwd_scan(const FwdScanParams &p, int ncar, cudaStream_t st);

@@ -239,6 +239,13 @@ AMPS_B200_API int amps_fwd_reset(amps_fwd *h);
  * nsym * (samp_rate/symrate) complex samples. */
 AMPS_B200_API int amps_fwd_work(amps_fwd *h, const uint8_t *const *sym, size_t nsym, float *out_iq_host);
 AMPS_B200_API int amps_fwd_submit_dev(amps_fwd *h, const void *const *d_sym, size_t nsym, void *d_out_iq, void *cuda_stream);
+/* Manchester-bit fast path: the same chain driven by DATA BITS, one byte per 10 kbit/s bit (0, 1, 0xFF = muted;
+ * bit 0 -> half-symbols (+1,-1), bit 1 -> (-1,+1) as lib/amps_packet.h:52-70), 1000 output samples per bit.  Because the
+ * FM phase returns to zero at every Manchester bit boundary the interpolator output is a sum of per-bit table
+ * entries: same result as feeding the expanded half-symbols to amps_fwd_work (within fp32 rounding), several times
+ * faster.  A handle streams either half-symbols or bits; reset() to switch. */
+AMPS_B200_API int amps_fwd_work_bits(amps_fwd *h, const uint8_t *const *bits, size_t nbits, float *out_iq_host);
+AMPS_B200_API int amps_fwd_submit_bits_dev(amps_fwd *h, const void *const *d_bits, size_t nbits, void *d_out_iq, void *cuda_stream);
 AMPS_B200_API int amps_fwd_interp(const amps_fwd *h);
 AMPS_B200_API int amps_fwd_get_taps(const amps_fwd *h, int carrier, float *out, int cap);
 

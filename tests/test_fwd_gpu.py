@@ -97,3 +97,47 @@ def test_device_resident_submit(capi, oracle):
     torch.cuda.synchronize()
     ref = oracle.fwd_chain_f64(syms)
     assert rms(out.cpu().numpy().view(np.complex64).astype(np.complex128) - ref) <= 1e-6
+
+
+# ------------------------------------------------------------------ Manchester-bit fast path
+def bits_of(sym_bytes, sps=5):
+    """Half-symbol bytes (+1 = 0x01, -1 = 0xFF), 2*sps per bit -> data bits (bit 1 = (low, high))."""
+    hs = np.asarray(sym_bytes).reshape(-1, 2 * sps)
+    return (hs[:, sps] == 1).astype(np.uint8)
+
+
+def test_bit_fast_path_matches_float64_chain(capi, oracle):
+    nbits = 4200
+    syms = config3_symbols(oracle, nbits * 10)
+    bits = [bits_of(s) for s in syms]
+    bits[2][1000:1400] = 0xFF                                    # a muted stretch on the third carrier
+    syms[2] = syms[2].copy()
+    syms[2][10000:14000] = 0
+    fw = capi.Fwd(max_samples=nbits * 1000)
+    y = fw.work_bits(bits)
+    ref = oracle.fwd_chain_f64(syms)
+    assert y.shape == ref.shape
+    assert rms(y.astype(np.complex128) - ref) <= 1e-6
+    # and it agrees with the general half-symbol path to fp32 rounding
+    g = capi.Fwd(max_samples=nbits * 1000).work(syms)
+    assert rms(y.astype(np.complex128) - g.astype(np.complex128)) <= 1e-6
+    with pytest.raises(capi.AmpsError):
+        fw.work(syms)                                            # no mixing of input kinds without reset()
+    fw.reset()
+    assert np.array_equal(fw.work(syms).view(np.float32), g.view(np.float32))
+
+
+def test_bit_fast_path_streaming(capi, oracle):
+    nbits = 3000
+    syms = config3_symbols(oracle, nbits * 10)
+    bits = [bits_of(s) for s in syms]
+    one = capi.Fwd(max_samples=nbits * 1000).work_bits(bits)
+    fw = capi.Fwd(max_samples=nbits * 1000)
+    rng = np.random.default_rng(9)
+    parts, pos = [], 0
+    while pos < nbits:
+        n = int(rng.integers(1, 400))
+        parts.append(fw.work_bits([b[pos:pos + n] for b in bits]))
+        pos += n
+    got = np.concatenate(parts)
+    assert np.array_equal(got.view(np.float32), one.view(np.float32))
