@@ -291,24 +291,32 @@ __global__ void __launch_bounds__(kFwdThreads, 3) fwd_bits_kernel(const __grid_c
     const uint32_t ntiles = (p.nbits + kFbTileBits - 1) / kFbTileBits;
     for (int i = t; i < p.ncar * 2 * kFbRespLen; i += kFwdThreads) (&sm->resp[0][0][0])[i] = p.resp[i];
 
+    // the bits a tile needs (15 per carrier) are fetched one tile ahead, so their global-load latency hides behind a tile of work
+    constexpr int kNB = kFbTileBits + kFbHistBits + 1;             // 15: bits q0-10 .. q0+4
+    auto fetch_bit = [&](uint32_t tile_) -> uint8_t {
+        if (t >= p.ncar * kNB || tile_ >= ntiles) return 0xFF;
+        const int c = t / kNB, k = t - c * kNB;
+        const long q = (long)tile_ * kFbTileBits - (kFbHistBits + 1) + k;
+        if (q >= (long)p.nbits) return 0xFF;
+        if (q >= 0) return p.bits[c][q];
+        if (q >= -(long)kFbHistBits) return p.hbits[c][kFbHistBits + q];
+        return 0xFF;
+    };
+    uint8_t bit_next = fetch_bit(blockIdx.x);
+
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long q0 = (long)tile * kFbTileBits;                  // first bit of the tile (call-local)
         const int nvalid = (int)((long)p.nbits - q0 < kFbTileBits ? (long)p.nbits - q0 : kFbTileBits);
         // ---- bits q0-10 .. q0+4 and the per-bit mixer phasors
-        constexpr int kNB = kFbTileBits + kFbHistBits + 1;         // 15
         if (t < p.ncar * kNB) {
             const int c = t / kNB, k = t - c * kNB;
-            const long q = q0 - (kFbHistBits + 1) + k;
-            uint8_t b = 0xFF;
-            if (q >= (long)p.nbits) b = 0xFF;
-            else if (q >= 0) b = p.bits[c][q];
-            else if (q >= -(long)kFbHistBits) b = p.hbits[c][kFbHistBits + q];
-            sm->bits[c][k] = b;
+            sm->bits[c][k] = bit_next;
         } else if (t >= 64 && t < 64 + p.ncar * (kFbTileBits + 1)) {
             const int idx = t - 64, c = idx / (kFbTileBits + 1), k = idx - c * (kFbTileBits + 1);
             const uint32_t qabs = (uint32_t)(p.bit_base + (unsigned long long)(q0 - 1 + k));
             sm->Wq[c][k] = sincos_phase(qabs * p.fcw_mix1000[c]);
         }
+        bit_next = fetch_bit(tile + gridDim.x);
         __syncthreads();
 
         // ---- phase A: 400 kS/s samples by table lookup, rotated by the carrier NCO.  thread = one sample m0-4+t
