@@ -180,6 +180,9 @@ def measure_fwd(local_rank, steps, warmup, bits=False):
         # one byte per data bit: the second half-symbol of a bit is high for a 1 (lib/amps_packet.h:52-70)
         syms = [(s.view(-1, 10)[:, 5] == 1).to(torch.uint8).contiguous() for s in syms]
         nunits = nsym // 10
+        fb = capi.Focc(100000, False, device=local_rank)            # the FOCC source can emit data bits directly
+        fb.generate_bits_dev(syms[0].data_ptr(), nunits, stream.cuda_stream)
+        torch.cuda.synchronize()
         submit = lambda: fw.submit_bits_dev([s.data_ptr() for s in syms], nunits, out.data_ptr(), stream.cuda_stream)
     else:
         ptrs = [s.data_ptr() for s in syms]

@@ -92,7 +92,7 @@ EXPORTS = [
     "amps_recc_decode_create", "amps_recc_decode_destroy", "amps_recc_decode_burst", "amps_recc_decode_bursts",
     "amps_recc_create", "amps_recc_destroy", "amps_recc_work", "amps_recc_work_chunks",
     "amps_focc_create", "amps_focc_destroy", "amps_focc_work", "amps_focc_generate", "amps_focc_generate_dev",
-    "amps_focc_push_words", "amps_focc_set_busy_idle",
+    "amps_focc_push_words", "amps_focc_set_busy_idle", "amps_focc_generate_bits", "amps_focc_generate_bits_dev",
     "amps_fvc_create", "amps_fvc_destroy", "amps_fvc_push_words", "amps_fvc_work",
     "amps_fwd_create", "amps_fwd_destroy", "amps_fwd_reset", "amps_fwd_work", "amps_fwd_submit_dev",
     "amps_fwd_interp", "amps_fwd_get_taps", "amps_fwd_work_bits", "amps_fwd_submit_bits_dev",
@@ -149,6 +149,8 @@ def lib() -> C.CDLL:
         L.amps_focc_generate.argtypes = [C.c_void_p, u8p, C.c_size_t]
         L.amps_focc_generate_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.amps_focc_push_words.argtypes = [C.c_void_p, C.c_long, u8p, C.c_long]
+        L.amps_focc_generate_bits.argtypes = [C.c_void_p, u8p, C.c_size_t]
+        L.amps_focc_generate_bits_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.amps_focc_set_busy_idle.argtypes = [C.c_void_p, C.c_int]
     if hasattr(L, "amps_fvc_create"):
         L.amps_fvc_create.argtypes = [C.c_ulong, C.c_int, C.POINTER(C.c_void_p)]
@@ -346,6 +348,14 @@ class Focc:
 
     def generate_dev(self, dev_ptr: int, n: int, stream: int = 0):
         check(lib().amps_focc_generate_dev(self.h, C.c_void_p(dev_ptr), n, C.c_void_p(stream)))
+
+    def generate_bits(self, nbits: int) -> np.ndarray:
+        buf = np.zeros(nbits, np.uint8)
+        check(lib().amps_focc_generate_bits(self.h, buf.ctypes.data_as(u8p), nbits))
+        return buf
+
+    def generate_bits_dev(self, dev_ptr: int, nbits: int, stream: int = 0):
+        check(lib().amps_focc_generate_bits_dev(self.h, C.c_void_p(dev_ptr), nbits, C.c_void_p(stream)))
 
     def push_words(self, stream: int, words):
         w = np.ascontiguousarray(words, dtype=np.uint8).reshape(-1)

@@ -131,6 +131,27 @@ cudaError_t launch_focc_bytes(const uint8_t *slots, const int *sched, unsigned l
     return cudaGetLastError();
 }
 
+// FOCC as data bits (one byte per 10 kbit/s bit, busy/idle resolved): the input of the forward path's bit entry point
+__global__ void __launch_bounds__(256) focc_bits_kernel(const uint8_t *__restrict__ slots, const int *__restrict__ sched,
+                                                       unsigned long long first_bit, unsigned long long n, int busy_idle,
+                                                       uint8_t *__restrict__ out) {
+    const unsigned long long x = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= n) return;
+    const unsigned long long a = first_bit + x;
+    const unsigned long long fk = a / kFoccFrameBits;
+    unsigned int bit = slots[(size_t)sched[fk] * kFoccFrameBits + (unsigned int)(a - fk * kFoccFrameBits)];
+    if (bit == 2u) bit = busy_idle ? 1u : 0u;
+    out[x] = (uint8_t)bit;
+}
+
+cudaError_t launch_focc_bits(const uint8_t *slots, const int *sched, unsigned long long first_bit, unsigned long long n,
+                             int busy_idle, uint8_t *out, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    const unsigned int grid = (unsigned int)((n + 255) / 256);
+    focc_bits_kernel<<<grid, 256, 0, stream>>>(slots, sched, first_bit, n, busy_idle, out);
+    return cudaGetLastError();
+}
+
 // FVC: byte x of the run is byte (first + x) of the replay of `bits`.
 __global__ void __launch_bounds__(256) fvc_bytes_kernel(const uint8_t *__restrict__ bits, unsigned long long first,
                                                        unsigned long long n, unsigned int sps, uint8_t *__restrict__ out) {

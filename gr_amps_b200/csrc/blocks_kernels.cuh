@@ -18,6 +18,8 @@ cudaError_t launch_recc_compat(ReccCompatState *st, const uint8_t *in, const int
                                uint8_t *blobs_out, int max_blobs, int *nblobs_out, cudaStream_t stream);
 cudaError_t launch_focc_bytes(const uint8_t *slots, const int *sched, unsigned long long first, unsigned long long n,
                               unsigned int sps, int busy_idle, uint8_t *out, cudaStream_t stream);
+cudaError_t launch_focc_bits(const uint8_t *slots, const int *sched, unsigned long long first_bit, unsigned long long n,
+                             int busy_idle, uint8_t *out, cudaStream_t stream);
 cudaError_t launch_fvc_bytes(const uint8_t *bits, unsigned long long first, unsigned long long n, unsigned int sps,
                              uint8_t *out, cudaStream_t stream);
 

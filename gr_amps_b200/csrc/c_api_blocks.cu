@@ -316,6 +316,39 @@ extern "C" int amps_focc_generate_dev(amps_focc *h, void *d_out, size_t n, void 
     return focc_emit(h, first, n, static_cast<uint8_t *>(d_out), st);
 }
 
+// The same stream as data bits (1 byte per bit): advances the state exactly as generating nbits * 2 * sps bytes would.
+extern "C" int amps_focc_generate_bits_dev(amps_focc *h, void *d_out, size_t nbits, void *cuda_stream) {
+    if (!h || (nbits && !d_out)) return set_error(AMPS_E_INVAL, "null argument");
+    if (nbits == 0) return AMPS_OK;
+    if (h->off != 0) return set_error(AMPS_E_STATE, "the stream is in the middle of a bit (a byte-level call stopped there)");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    CK(cudaStreamSynchronize(st));
+    const unsigned long long two = 2ull * h->sps;
+    const unsigned long long first = focc_plan(h, (unsigned long long)nbits * two);
+    if (h->h_sched.size() > h->sched_cap) {
+        cudaFree(h->d_sched); h->d_sched = nullptr;
+        h->sched_cap = h->h_sched.size() * 2 + 64;
+        CK(cudaMalloc(&h->d_sched, sizeof(int) * h->sched_cap));
+    }
+    CK(cudaMemcpyAsync(h->d_sched, h->h_sched.data(), sizeof(int) * h->h_sched.size(), cudaMemcpyHostToDevice, st));
+    CKL(launch_focc_bits(h->d_slots, h->d_sched, first / two, nbits, h->busy_idle, static_cast<uint8_t *>(d_out), st));
+    return AMPS_OK;
+}
+
+extern "C" int amps_focc_generate_bits(amps_focc *h, uint8_t *out, size_t nbits) {
+    if (!h || (nbits && !out)) return set_error(AMPS_E_INVAL, "null argument");
+    if (nbits == 0) return AMPS_OK;
+    CK(cudaSetDevice(h->device));
+    int rc = focc_host_out(h, nbits);
+    if (rc != AMPS_OK) return rc;
+    rc = amps_focc_generate_bits_dev(h, h->d_out, nbits, h->stream);
+    if (rc != AMPS_OK) return rc;
+    CK(cudaMemcpyAsync(out, h->d_out, nbits, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return AMPS_OK;
+}
+
 extern "C" int amps_focc_generate(amps_focc *h, uint8_t *out, size_t n) {
     if (!h || (n && !out)) return set_error(AMPS_E_INVAL, "null argument");
     if (n == 0) return AMPS_OK;

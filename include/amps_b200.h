@@ -197,6 +197,10 @@ AMPS_B200_API int amps_focc_work(amps_focc *h, uint8_t *out, int noutput_items, 
 /* bulk form: the concatenation of successive work() outputs until exactly n bytes were produced */
 AMPS_B200_API int amps_focc_generate(amps_focc *h, uint8_t *out, size_t n);
 AMPS_B200_API int amps_focc_generate_dev(amps_focc *h, void *d_out, size_t n, void *cuda_stream);
+/* the same stream as DATA BITS (one byte per bit, busy/idle resolved): the input of amps_fwd_*_bits; only valid on a
+ * bit boundary; advances the state exactly as generating nbits * 2 * (symrate / 20000) bytes would */
+AMPS_B200_API int amps_focc_generate_bits(amps_focc *h, uint8_t *out, size_t nbits);
+AMPS_B200_API int amps_focc_generate_bits_dev(amps_focc *h, void *d_out, size_t nbits, void *cuda_stream);
 /* focc_words message (lib/focc_impl.cc:521-563): stream 1=A 2=B 3=BOTH, words28 = nwords x 28 bytes */
 AMPS_B200_API int amps_focc_push_words(amps_focc *h, long stream, const uint8_t *words28, long nwords);
 AMPS_B200_API int amps_focc_set_busy_idle(amps_focc *h, int idle);      /* lib/amps_common.h:7 */

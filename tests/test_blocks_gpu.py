@@ -82,6 +82,23 @@ def test_focc_busy_idle_and_device_output(capi, oracle):
     assert np.array_equal(t.cpu().numpy(), oracle.Focc(10_000_000, False).generate(5_000_000, chunk=1 << 22))
 
 
+def test_focc_bits_match_bytes(capi, oracle):
+    """generate_bits is the byte stream seen as data bits, and leaves the state where the bytes would."""
+    g = capi.Focc(100000, False)
+    w = oracle.word("orc_focc_word1", 1, 0, 0x13579)
+    g.push_words(3, w)
+    o = oracle.Focc(100000, False)
+    o.push_words(3, w)
+    ref = o.generate(463 * 25 * 10, chunk=1 << 20)               # 25 frames
+    hs = ref.reshape(-1, 10)
+    assert np.array_equal(g.generate_bits(463 * 20), (hs[:463 * 20, 5] == 1).astype(np.uint8))
+    assert np.array_equal(g.generate(4630 * 5), ref[4630 * 20:])   # the byte stream continues where the bits stopped
+    assert g.work(3)[0] == 0                                     # the frame just ended: this call only steps over FOCC_END
+    assert g.work(3)[0] == 3
+    with pytest.raises(capi.AmpsError):
+        g.generate_bits(10)                                      # not on a bit boundary
+
+
 # ------------------------------------------------------------------ fvc
 def test_fvc_parity(capi, oracle):
     rng = np.random.default_rng(8)
