@@ -1,0 +1,58 @@
+"""CPU tests of the PRODUCT's host-side helpers (gr_amps_b200/csrc/proto.cc, design.cc) through host/qa_proto:
+word builders + BCH(40,28) against the golden KATs, frame/train layouts and filter designs against the oracle."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="module")
+def proto():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "gr_amps_b200"), "host/qa_proto"])
+    out = subprocess.check_output([os.path.join(ROOT, "gr_amps_b200", "host", "qa_proto")], text=True)
+    return json.loads(out)
+
+
+def test_words_and_bch_match_kats(proto, oracle):
+    kat = json.load(open(os.path.join(GOLD, "kat_bch.json")))
+    for name, (info, parity) in kat.items():
+        assert proto["words"][name] == [info, parity], name
+    # the message words recc_decode's responses are built from, against the oracle builders
+    bits = lambda w: "".join(map(str, w))
+    for name, w in [("focc_word1", oracle.word("orc_focc_word1", 1, 0, 0xABCDE)),
+                    ("focc_word2_general", oracle.word("orc_focc_word2_general", 0x155, 0, 0, 7)),
+                    ("focc_word2_voice_channel", oracle.word("orc_focc_word2_voice_channel", 1, 0x2AA, 0, 355))]:
+        assert proto["words"][name][0] == bits(w)
+        assert proto["words"][name][1] == bits(oracle.bch_encode_40_28(w)[28:])
+
+
+def test_frame_and_train_layouts(proto, oracle):
+    # frame 0 of the default superframe, B/I slots marked '2': compare with the oracle's byte stream at sps = 1
+    ref = oracle.Focc(20000, False).generate(926)
+    bits_ref = (ref.reshape(-1, 2)[:, 1] == 1).astype(int)
+    slots = proto["frame_slots"]
+    assert len(slots) == 463 and slots.count("2") == 42
+    assert all(s == "2" or int(s) == b for s, b in zip(slots, bits_ref))
+    assert all(bits_ref[i] == 1 for i, s in enumerate(slots) if s == "2")        # busy/idle = idle = 1
+    v = oracle.Fvc(20000)
+    v.push_words(oracle.word("orc_fvc_word1_general", 1, 0, 0, 1))
+    r, b, _ = v.work(4096)
+    assert r == 2064
+    assert proto["fvc_train"] == "".join(str(int(x)) for x in (b.reshape(-1, 2)[:, 1] == 1))
+
+
+def test_filter_designs_match_oracle(proto, oracle):
+    L = oracle.lib()
+    assert proto["fcw"] == [L.orc_nco_fcw(-160e3, 10e6), L.orc_nco_fcw(-160e3, 400e3)]
+    t = proto["taps"]
+    assert np.array_equal(np.float32(t["lpf"]), oracle.lpf_taps()) and len(t["lpf"]) == 299
+    assert np.array_equal(np.float32(t["focc_interp"]), oracle.firdes_low_pass(1.0, 400e3, 10e3, 5e3, 0)) and len(t["focc_interp"]) == 193
+    assert np.array_equal(np.float32(t["fvc_interp"]), oracle.firdes_low_pass(1.0, 400e3, 10e3, 3e3, 0)) and len(t["fvc_interp"]) == 321
+    c = np.float32(t["cic25"])
+    assert len(c) == 73 and abs(float(c.astype(np.float64).sum()) - 1.0) < 1e-6 and np.array_equal(c, c[::-1])
+    assert c[0] == np.float32(1 / 15625) and c[36] == np.float32(469 / 15625)
