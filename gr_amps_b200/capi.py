@@ -93,7 +93,7 @@ EXPORTS = [
     "amps_recc_create", "amps_recc_destroy", "amps_recc_work", "amps_recc_work_chunks",
     "amps_focc_create", "amps_focc_destroy", "amps_focc_work", "amps_focc_generate", "amps_focc_generate_dev",
     "amps_focc_push_words", "amps_focc_set_busy_idle", "amps_focc_generate_bits", "amps_focc_generate_bits_dev",
-    "amps_fvc_create", "amps_fvc_destroy", "amps_fvc_push_words", "amps_fvc_work",
+    "amps_fvc_create", "amps_fvc_destroy", "amps_fvc_push_words", "amps_fvc_work", "amps_fvc_work_bits",
     "amps_fwd_create", "amps_fwd_destroy", "amps_fwd_reset", "amps_fwd_work", "amps_fwd_submit_dev",
     "amps_fwd_interp", "amps_fwd_get_taps", "amps_fwd_work_bits", "amps_fwd_submit_bits_dev",
 ]
@@ -157,6 +157,7 @@ def lib() -> C.CDLL:
         L.amps_fvc_destroy.argtypes = [C.c_void_p]
         L.amps_fvc_push_words.argtypes = [C.c_void_p, u8p, C.c_long, C.c_int, C.c_uint64]
         L.amps_fvc_work.argtypes = [C.c_void_p, u8p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.amps_fvc_work_bits.argtypes = [C.c_void_p, u8p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     if hasattr(L, "amps_fwd_create"):
         L.amps_fwd_create.argtypes = [C.POINTER(FwdParams), C.POINTER(C.c_void_p)]
         L.amps_fwd_destroy.argtypes = [C.c_void_p]

@@ -454,3 +454,34 @@ extern "C" int amps_fvc_work(amps_fvc *h, uint8_t *out, int noutput_items, int *
     *produced = (int)take;
     return AMPS_OK;
 }
+
+// fvc as DATA BITS (one byte per bit, 0xFF = muted while no word was ever pushed): same replay / timerhack semantics as
+// amps_fvc_work, in units of bits; only valid on a bit boundary of the replay.  The bits are control data that already
+// live on the host (the word train), so this is a copy, not a kernel.
+extern "C" int amps_fvc_work_bits(amps_fvc *h, uint8_t *out_bits, int nbits, int *produced, int *fvc_off) {
+    if (!h || !produced || (nbits > 0 && !out_bits)) return set_error(AMPS_E_INVAL, "null argument");
+    if (fvc_off) *fvc_off = 0;
+    *produced = 0;
+    if (nbits < 1) return AMPS_OK;
+    const unsigned long long two = 2ull * h->sps;
+    if (h->bits.empty()) {
+        std::memset(out_bits, 0xFF, (size_t)nbits);
+        *produced = nbits;
+        return AMPS_OK;
+    }
+    if (h->replay_pos % two) return set_error(AMPS_E_STATE, "the replay is in the middle of a bit (a byte-level call stopped there)");
+    if (h->replay_pos == h->replay_len) {
+        if (h->timer >= 1) {
+            h->timer--;
+            if (h->timer == 0 && fvc_off) *fvc_off = 1;
+        }
+        h->replay_len = (unsigned long long)h->bits.size() * two;
+        h->replay_pos = 0;
+    }
+    const unsigned long long left = (h->replay_len - h->replay_pos) / two;
+    const unsigned long long take = (unsigned long long)nbits < left ? (unsigned long long)nbits : left;
+    std::memcpy(out_bits, h->bits.data() + h->replay_pos / two, (size_t)take);
+    h->replay_pos += take * two;
+    *produced = (int)take;
+    return AMPS_OK;
+}

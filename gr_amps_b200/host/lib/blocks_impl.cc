@@ -5,6 +5,7 @@
 #include "blocks_impl.h"
 #include "../../csrc/proto.h"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <stdexcept>
@@ -179,6 +180,78 @@ void recc_decode_impl::handle_origination(const amps_recc_words &w) {           
     message_port_pub(pmt::mp("audio_mute"), pmt::from_bool(false));
     const std::string m = std::string("page ") + w.dialed;
     message_port_pub(pmt::mp("command_out"), pmt::cons(pmt::make_dict(), pmt::init_u8vector(m.size(), (const uint8_t *)m.data())));
+}
+
+// ------------------------------------------------------------------ forward_iq (new composite source block)
+static const int kSamplesPerBit = 1000;            // 10 MS/s / 10 kbit/s
+static const size_t kMaxBitsPerWork = 4096;
+
+forward_iq::sptr forward_iq::make(bool aggressive_registration, int device) {
+    return gnuradio::get_initial_sptr(new forward_iq_impl(aggressive_registration, device));
+}
+forward_iq_impl::forward_iq_impl(bool aggressive_registration, int device)
+    : gr::sync_block("forward_iq", gr::io_signature::make(0, 0, 0), gr::io_signature::make(1, 1, sizeof(std::complex<float>))),
+      d_focc(NULL), d_fvc(NULL), d_fwd(NULL), d_fvc_mute(true) {
+    must(amps_focc_create(100000, aggressive_registration ? 1 : 0, device, &d_focc), "forward_iq/focc");
+    must(amps_fvc_create(100000, device, &d_fvc), "forward_iq/fvc");
+    amps_fwd_params p;
+    std::memset(&p, 0, sizeof p);
+    p.samp_rate = 10e6; p.symrate = 100e3; p.max_deviation = 8000; p.device = device; p.ncarriers = 3;
+    p.carrier_freq[0] = 0; p.carrier_freq[1] = 60e3; p.carrier_freq[2] = 90e3;          // grc/ampsbs.grc:841,904
+    p.lpf_transition[0] = 5e3; p.lpf_transition[1] = 3e3; p.lpf_transition[2] = 3e3;    // :2227, :2172
+    p.out_scale = 0.5f;                                                                  // :1367
+    p.max_samples = (uint32_t)(kMaxBitsPerWork * kSamplesPerBit);
+    must(amps_fwd_create(&p, &d_fwd), "forward_iq/fwd");
+    message_port_register_in(pmt::mp("focc_words"));
+    set_msg_handler(pmt::mp("focc_words"), [this](pmt::pmt_t m) { this->focc_words_message(m); });
+    message_port_register_in(pmt::mp("fvc_words"));
+    set_msg_handler(pmt::mp("fvc_words"), [this](pmt::pmt_t m) { this->fvc_words_message(m); });
+    message_port_register_in(pmt::mp("fvc_mute"));
+    set_msg_handler(pmt::mp("fvc_mute"), [this](pmt::pmt_t m) { this->d_fvc_mute = pmt::to_bool(m); });
+    message_port_register_out(pmt::mp("command_out"));
+}
+forward_iq_impl::~forward_iq_impl() { amps_fwd_destroy(d_fwd); amps_fvc_destroy(d_fvc); amps_focc_destroy(d_focc); }
+
+void forward_iq_impl::focc_words_message(pmt::pmt_t msg) {
+    if (!pmt::is_tuple(msg) || pmt::length(msg) < 3) return;
+    const long stream = pmt::to_long(pmt::tuple_ref(msg, 0)), nwords = pmt::to_long(pmt::tuple_ref(msg, 1));
+    std::vector<uint8_t> w((size_t)28 * (size_t)nwords);
+    for (long i = 0; i < nwords; i++) std::memcpy(&w[(size_t)28 * (size_t)i], pmt::blob_data(pmt::tuple_ref(msg, 2 + (size_t)i)), 28);
+    warn(amps_focc_push_words(d_focc, stream, w.data(), nwords), "forward_iq focc_words");
+}
+void forward_iq_impl::fvc_words_message(pmt::pmt_t msg) {
+    if (!pmt::is_tuple(msg) || pmt::length(msg) < 2) return;
+    const size_t len = pmt::length(msg);
+    const long nwords = pmt::to_long(pmt::tuple_ref(msg, 0));
+    std::vector<uint8_t> w((size_t)28 * (size_t)nwords);
+    for (long i = 0; i < nwords; i++) std::memcpy(&w[(size_t)28 * (size_t)i], pmt::blob_data(pmt::tuple_ref(msg, 1 + (size_t)i)), 28);
+    const bool has_timer = len > (size_t)(1 + nwords);
+    warn(amps_fvc_push_words(d_fvc, w.data(), nwords, has_timer ? 1 : 0, has_timer ? pmt::to_uint64(pmt::tuple_ref(msg, 1 + (size_t)nwords)) : 0),
+         "forward_iq fvc_words");
+}
+
+int forward_iq_impl::work(int noutput_items, gr_vector_const_void_star &, gr_vector_void_star &output_items) {
+    // whole bits only (a real GNU Radio build calls set_output_multiple(1000) in the constructor)
+    size_t nbits = (size_t)noutput_items / kSamplesPerBit;
+    if (nbits > kMaxBitsPerWork) nbits = kMaxBitsPerWork;
+    if (nbits == 0) return 0;
+    for (int c = 0; c < 3; c++) d_bits[c].assign(nbits, 0xFF);
+    warn(amps_focc_generate_bits(d_focc, d_bits[0].data(), nbits), "forward_iq focc bits");
+    // the FVC source runs whether or not its leg is muted (as the fvc block does behind mute_xx)
+    size_t got = 0;
+    while (got < nbits) {
+        int produced = 0, off = 0;
+        if (amps_fvc_work_bits(d_fvc, d_bits[1].data() + got, (int)(nbits - got), &produced, &off) != AMPS_OK || produced <= 0) break;
+        if (off) {
+            const char *m = "fvc off";
+            message_port_pub(pmt::mp("command_out"), pmt::cons(pmt::make_dict(), pmt::init_u8vector(std::strlen(m), (const uint8_t *)m)));
+        }
+        got += (size_t)produced;
+    }
+    if (d_fvc_mute) std::fill(d_bits[1].begin(), d_bits[1].end(), (uint8_t)0xFF);
+    const uint8_t *bits[3] = {d_bits[0].data(), d_bits[1].data(), d_bits[2].data()};
+    warn(amps_fwd_work_bits(d_fwd, bits, nbits, static_cast<float *>(output_items[0])), "forward_iq work");
+    return (int)(nbits * kSamplesPerBit);
 }
 
 }}  // namespace gr::amps

@@ -6,6 +6,8 @@
 #include <amps/recc.h>
 #include <amps/recc_decode.h>
 #include <amps/recc_iq.h>
+#include <amps/forward_iq.h>
+#include <vector>
 #include <amps_b200.h>
 
 #include <string>
@@ -62,6 +64,20 @@ public:
     void handle_origination(const amps_recc_words &w);
     void handle_response(const amps_recc_words &w);
     void handle_registration(const amps_recc_words &w);
+};
+
+class forward_iq_impl : public forward_iq {
+    amps_focc *d_focc;
+    amps_fvc *d_fvc;
+    amps_fwd *d_fwd;
+    bool d_fvc_mute;                       // the reference graph starts with the FVC leg muted (grc/ampsbs.grc:1601)
+    std::vector<uint8_t> d_bits[3];
+public:
+    forward_iq_impl(bool aggressive_registration, int device);
+    ~forward_iq_impl();
+    void focc_words_message(pmt::pmt_t msg);
+    void fvc_words_message(pmt::pmt_t msg);
+    int work(int noutput_items, gr_vector_const_void_star &input_items, gr_vector_void_star &output_items);
 };
 
 }}  // namespace gr::amps

@@ -11,6 +11,7 @@
 #include <amps/recc.h>
 #include <amps/recc_decode.h>
 #include <amps/recc_iq.h>
+#include <amps/forward_iq.h>
 #include <amps_b200.h>
 
 #include <complex>
@@ -189,12 +190,44 @@ static int run_fwd(int argc, char **argv) {
     return 0;
 }
 
+// forward_iq block: FOCC with an injected word pair, FVC alert train unmuted half-way, IQ to a file
+static int run_txblock(int argc, char **argv) {
+    if (argc < 4) return 2;
+    const size_t nbits = std::strtoull(argv[2], NULL, 10);
+    forward_iq::sptr tx = forward_iq::make(false, 0);
+    probe pr;
+    gr::msg_connect(*tx, "command_out", pr, "command_out");
+    // page a mobile: word 1 + word 2 on both streams (what command_processor / recc_decode would send)
+    unsigned char w1[28] = {0,1,0,0, 0,0,0,1,0,0,1,0,0,0,1,1,0,1,0,0,0,1,0,1,0,1,1,0}, w2[28] = {1,0,1,1, 0,1,0,1,0,1,0,1,0,1, 0, 0,0,0,0,0, 0,0,0, 0,0,0,0,0};
+    tx->dispatch_msg("focc_words", pmt::make_tuple(pmt::from_long(3), pmt::from_long(2), pmt::mp(w1, 28), pmt::mp(w2, 28)));
+    unsigned char alert[28] = {1,0,1,1,0,1,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,1};
+    tx->dispatch_msg("fvc_words", pmt::make_tuple(pmt::from_long(1), pmt::mp(alert, 28), pmt::from_uint64(2)));
+    std::vector<std::complex<float>> out(nbits * 1000), buf(700 * 1000);
+    gr_vector_const_void_star noin;
+    gr_vector_void_star outs(1);
+    size_t done = 0;
+    while (done < nbits) {
+        if (done >= nbits / 2) tx->dispatch_msg("fvc_mute", pmt::from_bool(false));
+        size_t want = nbits - done < 700 ? nbits - done : 700;
+        if (done < nbits / 2 && done + want > nbits / 2) want = nbits / 2 - done;
+        outs[0] = buf.data();
+        const int r = tx->work((int)(want * 1000), noin, outs);
+        if (r <= 0 || r % 1000) return 3;
+        std::memcpy(&out[done * 1000], buf.data(), (size_t)r * sizeof(std::complex<float>));
+        done += (size_t)r / 1000;
+    }
+    std::ofstream(argv[3], std::ios::binary).write(reinterpret_cast<const char *>(out.data()), (std::streamsize)(out.size() * sizeof(std::complex<float>)));
+    for (size_t i = 0; i < pr.lines.size(); i++) std::printf("%s\n", pr.lines[i].c_str());
+    return 0;
+}
+
 int main(int argc, char **argv) {
     if (argc < 2) { std::fprintf(stderr, "usage: qa_blocks focc|loop|fwd ...\n"); return 2; }
     try {
         if (!std::strcmp(argv[1], "focc")) return run_focc(argc, argv);
         if (!std::strcmp(argv[1], "loop")) return run_loop(argc, argv);
         if (!std::strcmp(argv[1], "fwd")) return run_fwd(argc, argv);
+        if (!std::strcmp(argv[1], "txblock")) return run_txblock(argc, argv);
     } catch (const std::exception &e) {
         std::fprintf(stderr, "qa_blocks: %s\n", e.what());
         return 10;

@@ -217,6 +217,8 @@ AMPS_B200_API int amps_fvc_push_words(amps_fvc *h, const uint8_t *words28, long 
  * noutput_items WITHOUT writing (lib/fvc_impl.cc:159-161); this library writes zeros there
  * (documented deviation).  *fvc_off is set when the "fvc off" PDU is due (:163-171). */
 AMPS_B200_API int amps_fvc_work(amps_fvc *h, uint8_t *out, int noutput_items, int *produced, int *fvc_off);
+/* the same replay as DATA BITS (one byte per bit; 0xFF = muted while no word was ever pushed), for amps_fwd_*_bits */
+AMPS_B200_API int amps_fvc_work_bits(amps_fvc *h, uint8_t *out_bits, int nbits, int *produced, int *fvc_off);
 
 /* ------------------------------------------------------------------------------------------
  * Fused forward path: symbols -> char_to_float -> frequency_modulator_fc -> pfb interpolator (x4, the

@@ -91,3 +91,33 @@ def test_closed_loop_flowgraph(oracle, tmp_path):
         r, b, _ = ofvc.work(4096)
         ref += b.tobytes()
     assert np.array_equal(gv, np.frombuffer(bytes(ref), np.uint8)[:len(gv)])
+
+
+def test_forward_iq_block(oracle, tmp_path):
+    """The composite forward_iq block (FOCC + FVC sources -> fused modulator, data-bit fast path) against the oracle:
+    oracle focc/fvc byte streams -> float64 forward chain."""
+    nbits = 4000
+    out = run(["txblock", nbits, tmp_path / "tx.bin"], tmp_path)
+    y = np.fromfile(str(tmp_path / "tx.bin"), np.complex64)
+    assert len(y) == nbits * 1000
+    w1 = [0,1,0,0, 0,0,0,1,0,0,1,0,0,0,1,1,0,1,0,0,0,1,0,1,0,1,1,0]
+    w2 = [1,0,1,1, 0,1,0,1,0,1,0,1,0,1, 0, 0,0,0,0,0, 0,0,0, 0,0,0,0,0]
+    alert = [1,0,1,1,0,1,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,1]
+    fo = oracle.Focc(100000, False)
+    fo.push_words(3, np.array([w1, w2], np.uint8))
+    s0 = fo.generate(nbits * 10, chunk=1 << 20)
+    fv = oracle.Fvc(100000)
+    fv.push_words(np.array(alert, np.uint8), timer=2)
+    s1, offs = bytearray(), 0
+    while len(s1) < nbits * 10:
+        r, b, off = fv.work(min(8192, nbits * 10 - len(s1)))
+        s1 += b.tobytes()
+        offs += off
+    s1 = np.frombuffer(bytes(s1), np.uint8).copy()
+    s1[:nbits // 2 * 10] = 0                                   # the FVC leg is muted for the first half
+    s2 = np.zeros(nbits * 10, np.uint8)
+    ref = oracle.fwd_chain_f64([s0, s1, s2])
+    err = float(np.sqrt(np.mean(np.abs(y.astype(np.complex128) - ref) ** 2)))
+    assert err <= 1e-6, err
+    lines = [json.loads(l) for l in out.splitlines() if l.startswith("{")]
+    assert lines == [{"port": "command_out", "text": "fvc off"}] * offs and offs == 1
