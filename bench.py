@@ -420,5 +420,22 @@ def main():
     return 0
 
 
+def _only_json_on_stdout():
+    """Libraries (NCCL's version banner, torchrun notices) write to fd 1; the contract is ONE JSON line on stdout.
+    Point fd 1 at stderr for the whole run and hand back a file object on the real stdout for the final line."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(real, "w")
+
+
 if __name__ == "__main__":
+    _real_stdout = _only_json_on_stdout()
+    _print = print
+
+    def print(*a, **k):            # noqa: A001 -- every print() in this module is the JSON line
+        k.pop("file", None)
+        _print(*a, file=_real_stdout, **k)
+        _real_stdout.flush()
+
     sys.exit(main())
