@@ -117,6 +117,25 @@ Word28 focc_word2_voice_channel(unsigned scc, uint64_t min2, unsigned vmac, unsi
     return w;
 }
 
+uint64_t compute_min_3(char d1c, char d2c, char d3c) {
+    uint64_t d[3] = {(uint64_t)(d1c - '0'), (uint64_t)(d2c - '0'), (uint64_t)(d3c - '0')};
+    for (auto &x : d)
+        if (x == 0) x = 10;                                   // digit 0 counts as ten (TIA-553 2.3.1)
+    return 100 * d[0] + 10 * d[1] + d[2] - 111;
+}
+
+bool parse_min(const std::string &min, uint64_t &min1, uint64_t &min2) {
+    if (min.size() != 10) return false;
+    for (char c : min)
+        if (c < '0' || c > '9') return false;
+    min2 = compute_min_3(min[0], min[1], min[2]);
+    uint64_t thousands = (uint64_t)(min[6] - '0');
+    if (thousands == 0) thousands = 10;
+    min1 = ((compute_min_3(min[3], min[4], min[5]) & 0x3ff) << 14) | ((thousands & 0xf) << 10) |
+           (compute_min_3(min[7], min[8], min[9]) & 0x3ff);
+    return true;
+}
+
 std::array<uint8_t, 463> focc_frame_slots(const uint8_t *wa, const uint8_t *wb) {
     static const uint8_t dot[10] = {1, 0, 1, 0, 1, 0, 1, 0, 1, 0};
     static const uint8_t sync[11] = {1, 1, 1, 0, 0, 0, 1, 0, 0, 1, 0};

@@ -4,6 +4,7 @@
 #pragma once
 #include <array>
 #include <cstdint>
+#include <string>
 #include <vector>
 
 namespace amps {
@@ -25,6 +26,11 @@ Word28 focc_word1(bool multiword, unsigned dcc, uint64_t min1);
 Word28 focc_word2_general(uint64_t min2, unsigned msg_type, unsigned ordq, unsigned order);
 Word28 fvc_word1_general(unsigned pscc, unsigned msg_type, unsigned ordq, unsigned order);
 Word28 focc_word2_voice_channel(unsigned scc, uint64_t min2, unsigned vmac, unsigned chan);
+
+// MIN digits <-> MIN1 (24 bit) / MIN2 (10 bit): lib/amps_packet.h:305-349.  parse_min needs exactly 10 digits
+// (the reference accepts 1..10 but reads min[0..9] regardless; the short cases are out-of-bounds reads there).
+uint64_t compute_min_3(char d1, char d2, char d3);
+bool parse_min(const std::string &min, uint64_t &min1, uint64_t &min2);
 
 // 463 slots: [BI] dotting(10) [BI] sync(11), then 5 x (A, B) words as 4 x ([BI] + 10 bits)
 std::array<uint8_t, 463> focc_frame_slots(const uint8_t *word_a28, const uint8_t *word_b28);

@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cctype>
 #include <cstring>
 #include <stdexcept>
 #include <vector>
@@ -180,6 +181,69 @@ void recc_decode_impl::handle_origination(const amps_recc_words &w) {           
     message_port_pub(pmt::mp("audio_mute"), pmt::from_bool(false));
     const std::string m = std::string("page ") + w.dialed;
     message_port_pub(pmt::mp("command_out"), pmt::cons(pmt::make_dict(), pmt::init_u8vector(m.size(), (const uint8_t *)m.data())));
+}
+
+// ------------------------------------------------------------------ command_processor (lib/command_processor_impl.cc)
+command_processor::sptr command_processor::make() { return gnuradio::get_initial_sptr(new command_processor_impl()); }
+command_processor_impl::command_processor_impl()
+    : gr::block("command_processor", gr::io_signature::make(0, 0, 0), gr::io_signature::make(0, 0, 0)) {
+    message_port_register_in(pmt::mp("commands"));                                     // :41-49
+    set_msg_handler(pmt::mp("commands"), [this](pmt::pmt_t m) { this->commands_message(m); });
+    message_port_register_out(pmt::mp("focc_words"));
+    message_port_register_out(pmt::mp("debug_output"));
+    message_port_register_out(pmt::mp("fvc_words"));
+    message_port_register_out(pmt::mp("audio_mute"));
+    message_port_register_out(pmt::mp("fvc_mute"));
+}
+
+void command_processor_impl::debug_msg(const char *msg) {                              // :52-56
+    message_port_pub(pmt::mp("debug_output"), pmt::cons(pmt::make_dict(), pmt::init_u8vector(std::strlen(msg), (const uint8_t *)msg)));
+}
+
+void command_processor_impl::handle_page(const std::string numstr) {                   // :58-82: page = Word 1 + Word 2, order 0
+    if (numstr.empty()) { debug_msg("missing MIN in page command\n"); return; }
+    debug_msg("paging!\n");
+    uint64_t min1, min2;
+    if (!::amps::parse_min(numstr, min1, min2)) { debug_msg("invalid MIN entered"); return; }
+    const ::amps::Word28 w1 = ::amps::focc_word1(true, GLOBAL_DCC_SHORT, min1);
+    const ::amps::Word28 w2 = ::amps::focc_word2_general(min2, 0, 0, 0);
+    message_port_pub(pmt::mp("focc_words"), pmt::make_tuple(pmt::from_long(STREAM_BOTH), pmt::from_long(2), word_blob(w1), word_blob(w2)));
+}
+
+static bool has_prefix(const std::string &s, const char *p, bool any_case) {
+    for (size_t i = 0; p[i]; i++) {
+        if (i >= s.size()) return false;
+        const unsigned char a = (unsigned char)s[i], b = (unsigned char)p[i];
+        if (any_case ? std::tolower(a) != std::tolower(b) : a != b) return false;
+    }
+    return true;
+}
+
+void command_processor_impl::commands_message(pmt::pmt_t msg) {                        // :84-113: PDU (dict . u8vector of text)
+    if (!pmt::is_pair(msg) || !pmt::is_u8vector(pmt::cdr(msg))) return;
+    size_t n = 0;
+    const uint8_t *chars = pmt::u8vector_elements(pmt::cdr(msg), n);
+    std::string cmd(reinterpret_cast<const char *>(chars), n);
+    cmd = cmd.substr(0, cmd.find('\0'));                                               // the reference goes through a C string
+    if (has_prefix(cmd, "fvc off", false)) {
+        message_port_pub(pmt::mp("fvc_mute"), pmt::from_bool(true));
+        message_port_pub(pmt::mp("audio_mute"), pmt::from_bool(false));
+        debug_msg("turning FVC data OFF; audio ON\n");
+    } else if (has_prefix(cmd, "fvc on", false)) {
+        message_port_pub(pmt::mp("fvc_mute"), pmt::from_bool(false));
+        message_port_pub(pmt::mp("audio_mute"), pmt::from_bool(true));
+        debug_msg("turning FVC data ON; audio OFF\n");
+    } else if (has_prefix(cmd, "fvc alert", false)) {
+        const ::amps::Word28 fv = ::amps::fvc_word1_general(GLOBAL_SCC, 0, 0, 1);
+        message_port_pub(pmt::mp("fvc_words"), pmt::make_tuple(pmt::from_long(1), word_blob(fv)));
+    } else if (has_prefix(cmd, "page ", true)) {
+        size_t b = 5, e = cmd.size();
+        while (b < e && std::isspace((unsigned char)cmd[b])) b++;
+        while (e > b && std::isspace((unsigned char)cmd[e - 1])) e--;
+        handle_page(cmd.substr(b, e - b));
+    } else {
+        debug_msg("invalid command\n");
+    }
 }
 
 // ------------------------------------------------------------------ forward_iq (new composite source block)

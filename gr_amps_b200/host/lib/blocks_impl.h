@@ -7,6 +7,7 @@
 #include <amps/recc_decode.h>
 #include <amps/recc_iq.h>
 #include <amps/forward_iq.h>
+#include <amps/command_processor.h>
 #include <vector>
 #include <amps_b200.h>
 
@@ -64,6 +65,14 @@ public:
     void handle_origination(const amps_recc_words &w);
     void handle_response(const amps_recc_words &w);
     void handle_registration(const amps_recc_words &w);
+};
+
+class command_processor_impl : public command_processor {            // host-only: text commands -> control words
+    void debug_msg(const char *msg);
+    void handle_page(const std::string numstr);
+public:
+    command_processor_impl();
+    void commands_message(pmt::pmt_t msg);
 };
 
 class forward_iq_impl : public forward_iq {

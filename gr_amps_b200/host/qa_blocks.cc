@@ -6,12 +6,14 @@
 //   qa_blocks focc <symrate> <aggr 0|1> <total_bytes> <seed> <out.bin>
 //   qa_blocks loop <iq.bin> <nsamples> <chunk> <focc_bytes> <out_prefix>
 //   qa_blocks fwd <nsym> <out.bin>
+//   qa_blocks cmd <text> [<text> ...]          (host only: command_processor, no GPU needed)
 #include <amps/focc.h>
 #include <amps/fvc.h>
 #include <amps/recc.h>
 #include <amps/recc_decode.h>
 #include <amps/recc_iq.h>
 #include <amps/forward_iq.h>
+#include <amps/command_processor.h>
 #include <amps_b200.h>
 
 #include <complex>
@@ -35,7 +37,7 @@ class probe : public gr::block {
 public:
     std::vector<std::string> lines;
     probe() : gr::block("probe", gr::io_signature::make(0, 0, 0), gr::io_signature::make(0, 0, 0)) {
-        const char *ports[] = {"focc_words", "fvc_words", "audio_mute", "fvc_mute", "command_out", "bursts"};
+        const char *ports[] = {"focc_words", "fvc_words", "audio_mute", "fvc_mute", "command_out", "bursts", "debug_output"};
         for (size_t i = 0; i < sizeof(ports) / sizeof(ports[0]); i++) {
             const std::string port = ports[i];
             message_port_register_in(pmt::mp(port));
@@ -62,10 +64,12 @@ public:
             }
         } else if (port == "audio_mute" || port == "fvc_mute") {
             js += std::string(", \"value\": ") + (pmt::to_bool(m) ? "true" : "false");
-        } else if (port == "command_out") {
+        } else if (port == "command_out" || port == "debug_output") {
             size_t n = 0;
             const uint8_t *d = pmt::u8vector_elements(pmt::cdr(m), n);
-            js += ", \"text\": \"" + std::string(reinterpret_cast<const char *>(d), n) + "\"";
+            std::string text;
+            for (size_t i = 0; i < n; i++) text += (d[i] == '\n') ? std::string("\\n") : std::string(1, (char)d[i]);
+            js += ", \"text\": \"" + text + "\"";
         } else if (port == "bursts") {
             std::snprintf(buf, sizeof buf, ", \"len\": %zu", pmt::blob_length(m));
             js += buf;
@@ -221,6 +225,22 @@ static int run_txblock(int argc, char **argv) {
     return 0;
 }
 
+// command_processor wired as grc/ampsbs.grc:4404-4412: every command is one PDU on "commands"
+static int run_cmd(int argc, char **argv) {
+    command_processor::sptr cp = command_processor::make();
+    probe pr;
+    const char *ports[] = {"focc_words", "fvc_words", "audio_mute", "fvc_mute", "debug_output"};
+    for (size_t i = 0; i < sizeof(ports) / sizeof(ports[0]); i++) gr::msg_connect(*cp, ports[i], pr, ports[i]);
+    for (int i = 2; i < argc; i++) {
+        pr.lines.clear();
+        cp->dispatch_msg("commands", pmt::cons(pmt::make_dict(), pmt::init_u8vector(std::strlen(argv[i]), (const uint8_t *)argv[i])));
+        std::printf("[");
+        for (size_t k = 0; k < pr.lines.size(); k++) std::printf("%s%s", k ? ", " : "", pr.lines[k].c_str());
+        std::printf("]\n");
+    }
+    return 0;
+}
+
 int main(int argc, char **argv) {
     if (argc < 2) { std::fprintf(stderr, "usage: qa_blocks focc|loop|fwd ...\n"); return 2; }
     try {
@@ -228,6 +248,7 @@ int main(int argc, char **argv) {
         if (!std::strcmp(argv[1], "loop")) return run_loop(argc, argv);
         if (!std::strcmp(argv[1], "fwd")) return run_fwd(argc, argv);
         if (!std::strcmp(argv[1], "txblock")) return run_txblock(argc, argv);
+        if (!std::strcmp(argv[1], "cmd")) return run_cmd(argc, argv);
     } catch (const std::exception &e) {
         std::fprintf(stderr, "qa_blocks: %s\n", e.what());
         return 10;

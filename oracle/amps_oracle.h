@@ -120,6 +120,17 @@ typedef struct {
     char     command[48];        /* command_out PDU text, "" = none */
 } orc_recc_actions;
 void   orc_recc_actions_for(const orc_recc_result *r, orc_recc_actions *a);     /* lib/recc_decode_impl.cc:181-272 */
+typedef struct {                 /* what amps.command_processor publishes for one command (command_proc.c) */
+    int32_t  n_focc;
+    int64_t  focc_stream;
+    uint8_t  focc_words[2][28];
+    int32_t  has_fvc;            /* fvc_words tuple (1, word), no timer */
+    uint8_t  fvc_word[28];
+    int32_t  fvc_mute, audio_mute;   /* -1 = not published */
+    int32_t  n_debug;
+    char     debug[2][48];       /* debug_output PDUs, in order */
+} orc_cmd_actions;
+void   orc_command_actions(const char *cmd, orc_cmd_actions *a);                /* lib/command_processor_impl.cc:52-117 */
 
 /* ---------------------------------------------------------------- DSP chain (dsp_chain.c) */
 /* gr::filter::firdes::low_pass (EXTERNAL). window: 0 hamming, 1 hann, 2 blackman.

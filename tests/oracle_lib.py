@@ -44,6 +44,12 @@ class ReccActions(C.Structure):
                 ("fvc_mute", C.c_int32), ("audio_mute", C.c_int32), ("command", C.c_char * 48)]
 
 
+class CmdActions(C.Structure):
+    _fields_ = [("n_focc", C.c_int32), ("focc_stream", C.c_int64), ("focc_words", (C.c_uint8 * 28) * 2),
+                ("has_fvc", C.c_int32), ("fvc_word", C.c_uint8 * 28), ("fvc_mute", C.c_int32), ("audio_mute", C.c_int32),
+                ("n_debug", C.c_int32), ("debug", (C.c_char * 48) * 2)]
+
+
 class Burst(C.Structure):
     _fields_ = [("d_index", C.c_uint64), ("corr", C.c_float), ("symbols", C.c_uint8 * 3374)]
 
@@ -240,6 +246,14 @@ def cpu_baseline_run(x: np.ndarray, threads: int, reps: int, center=-160e3, fs=1
     nb = C.c_int(0)
     sec = lib().orc_cpu_baseline_run(ptr(iq, f32p), n, fcw, ptr(taps, f32p), len(taps), threads, reps, C.byref(nb))
     return sec, nb.value
+
+
+def command_actions(cmd: str) -> CmdActions:
+    a = CmdActions()
+    lib().orc_command_actions.argtypes = [C.c_char_p, C.POINTER(CmdActions)]
+    lib().orc_command_actions.restype = None
+    lib().orc_command_actions(cmd.encode(), C.byref(a))
+    return a
 
 
 def recc_actions(result: ReccResult) -> ReccActions:

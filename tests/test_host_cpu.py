@@ -1,5 +1,6 @@
 """CPU tests of the PRODUCT's host-side helpers (gr_amps_b200/csrc/proto.cc, design.cc) through host/qa_proto:
 word builders + BCH(40,28) against the golden KATs, frame/train layouts and filter designs against the oracle."""
+import ctypes as C
 import json
 import os
 import subprocess
@@ -56,3 +57,39 @@ def test_filter_designs_match_oracle(proto, oracle):
     c = np.float32(t["cic25"])
     assert len(c) == 73 and abs(float(c.astype(np.float64).sum()) - 1.0) < 1e-6 and np.array_equal(c, c[::-1])
     assert c[0] == np.float32(1 / 15625) and c[36] == np.float32(469 / 15625)
+
+
+def test_command_processor_matches_oracle(oracle):
+    """gr::amps::command_processor (host only) against the oracle's restatement of lib/command_processor_impl.cc:52-117."""
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "gr_amps_b200"), "host"])
+    cmds = ["fvc off", "fvc on now", "fvc alert", "PAGE  2125551234 ", "page 0000000000", "page 9075550199\n", "page 12", "page ",
+            "page", "Fvc off", "page 212555123x", "page 21255512345", "", "fvc", "pAgE 3105550100"]
+    out = subprocess.check_output([os.path.join(ROOT, "gr_amps_b200", "host", "qa_blocks"), "cmd"] + cmds, text=True)
+    lines = out.strip().split("\n")
+    assert len(lines) == len(cmds)
+    bits = lambda w: "".join(str(int(b)) for b in w)
+    n_pages = 0
+    for cmd, line in zip(cmds, lines):
+        got = json.loads(line)
+        a = oracle.command_actions(cmd)
+        want = []                                            # publication order of the reference
+        if a.fvc_mute >= 0:
+            want += [{"port": "fvc_mute", "value": bool(a.fvc_mute)}, {"port": "audio_mute", "value": bool(a.audio_mute)}]
+        if a.has_fvc:
+            want.append({"port": "fvc_words", "words": [bits(a.fvc_word)]})
+        dbg = [{"port": "debug_output", "text": a.debug[i].value.decode()} for i in range(a.n_debug)]
+        if a.n_focc:
+            want += dbg + [{"port": "focc_words", "stream": a.focc_stream, "n": a.n_focc, "words": [bits(a.focc_words[i]) for i in range(a.n_focc)]}]
+            n_pages += 1
+        else:
+            want += dbg
+        assert got == want, cmd
+    assert n_pages == 4
+    # the page words carry the MIN: decode them back with the oracle's MIN arithmetic
+    a = oracle.command_actions("page 2125551234")
+    w1, w2 = np.array(a.focc_words[0]), np.array(a.focc_words[1])
+    min1 = int("".join(map(str, w1[4:28])), 2)
+    min2 = int("".join(map(str, w2[4:14])), 2)
+    buf = (C.c_char * 11)()
+    oracle.lib().orc_calc_min(min1, min2, buf)
+    assert buf.value == b"2125551234"
