@@ -82,6 +82,7 @@ BLOB_CB = C.CFUNCTYPE(None, u8p, C.c_void_p)
 
 RX_DUMP_BASEBAND = 1
 RX_TIME_KERNELS = 2
+RX_TIMING_MM = 4
 
 # every symbol include/amps_b200.h declares
 EXPORTS = [
@@ -181,10 +182,10 @@ class ReccIq:
     """Fused RECC receive path on IQ (amps_recc_iq_*)."""
 
     def __init__(self, max_samples: int, center_freq=-160e3, samp_rate=10e6, device=0, max_bursts=256,
-                 dump_baseband=False, lpf_taps: np.ndarray | None = None, time_kernels=False):
+                 dump_baseband=False, lpf_taps: np.ndarray | None = None, time_kernels=False, timing_mm=False):
         self._taps = None if lpf_taps is None else np.ascontiguousarray(lpf_taps, dtype=np.float32)
         p = ReccIqParams(samp_rate, center_freq, device, max_samples, max_bursts,
-                         (RX_DUMP_BASEBAND if dump_baseband else 0) | (RX_TIME_KERNELS if time_kernels else 0),
+                         (RX_DUMP_BASEBAND if dump_baseband else 0) | (RX_TIME_KERNELS if time_kernels else 0) | (RX_TIMING_MM if timing_mm else 0),
                          None if self._taps is None else self._taps.ctypes.data_as(f32p),
                          0 if self._taps is None else len(self._taps))
         self.h = C.c_void_p()

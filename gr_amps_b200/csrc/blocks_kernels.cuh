@@ -12,6 +12,7 @@ struct ReccCompatState {
     uint8_t  buf[kReccBuf];
     uint32_t len;
     int32_t  pending;                  // offset of a found trigger, -1 if none
+    unsigned long long appended;       // bytes appended since stream start (bookkeeping only, not in the reference)
 };
 
 cudaError_t launch_recc_compat(ReccCompatState *st, const uint8_t *in, const int *chunk_sizes, int nchunks,

@@ -49,6 +49,15 @@ struct amps_recc_iq {
     cudaEvent_t  ev_side[2] = {nullptr, nullptr};   // detection of call k finished (k & 1)
     uint64_t     call_no = 0;
     bool         serial = false;         // AMPS_RX_SERIAL=1: no overlap (profiling / A-B measurements)
+    // AMPS_RX_TIMING_MM: the reference graph's serial tail instead of the feed-forward detector
+    bool         mm_mode = false;
+    MmState     *d_mm = nullptr;
+    float       *d_mmtab = nullptr;
+    uint8_t     *d_sym = nullptr;
+    uint32_t     sym_cap = 0;
+    ReccCompatState *d_compat = nullptr;
+    uint8_t     *d_blobs = nullptr;
+    unsigned long long *d_blob_idx = nullptr;
 
     size_t       carry = 0;              // unprocessed samples sitting at the front of d_stage
     uint64_t     samples_in = 0;         // samples handed to the kernels
@@ -60,6 +69,17 @@ struct amps_recc_iq {
     cudaEvent_t  ev0[kEv] = {}, ev1[kEv] = {};
     uint64_t     ev_count = 0;
 };
+
+static int mm_reset(amps_recc_iq *h) {
+    MmState m;
+    std::memset(&m, 0, sizeof m);
+    m.omega = 10.0f;                                                   // grc/ampsbs.grc:1807 (omega = 10, mu = 0)
+    CK(cudaMemcpy(h->d_mm, &m, sizeof m, cudaMemcpyHostToDevice));
+    CK(cudaMemset(h->d_compat, 0, sizeof(ReccCompatState)));
+    const int32_t none = -1;
+    CK(cudaMemcpy(&h->d_compat->pending, &none, sizeof none, cudaMemcpyHostToDevice));
+    return AMPS_OK;
+}
 
 static int rx_alloc(amps_recc_iq *h) {
     const size_t max_d = (size_t)h->max_samples / h->decim + kPassOut;
@@ -84,6 +104,19 @@ static int rx_alloc(amps_recc_iq *h) {
     CK(cudaMemset(h->d_state, 0, sizeof(RxState)));
     CK(cudaMalloc(&h->d_cand, sizeof(Candidate) * kMaxCand));
     CK(cudaMalloc(&h->d_acc, sizeof(Accepted) * kMaxAccept));
+    if (h->mm_mode) {
+        h->sym_cap = (uint32_t)(max_d / 8 + 64);
+        const std::vector<float> tab = mmse_interp_table();
+        CK(cudaMalloc(&h->d_mm, sizeof(MmState)));
+        CK(cudaMalloc(&h->d_mmtab, tab.size() * sizeof(float)));
+        CK(cudaMemcpy(h->d_mmtab, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&h->d_sym, h->sym_cap));
+        CK(cudaMalloc(&h->d_compat, sizeof(ReccCompatState)));
+        CK(cudaMalloc(&h->d_blobs, (size_t)kMaxAccept * kCapture));
+        CK(cudaMalloc(&h->d_blob_idx, (size_t)kMaxAccept * sizeof(unsigned long long)));
+        int rc = mm_reset(h);
+        if (rc != AMPS_OK) return rc;
+    }
     CK(cudaHostAlloc(&h->h_ring, sizeof(amps_burst) * h->max_records, cudaHostAllocMapped));
     CK(cudaHostAlloc(&h->h_pub, sizeof(RxPublished), cudaHostAllocMapped));
     std::memset(h->h_pub, 0, sizeof(RxPublished));
@@ -118,6 +151,7 @@ extern "C" int amps_recc_iq_create(const amps_recc_iq_params *params, amps_recc_
     h->max_samples = (uint32_t)(((uint64_t)params->max_samples + h->pass_in - 1) / h->pass_in * h->pass_in);
     h->max_records = params->max_bursts ? params->max_bursts : 256;
     h->flags = params->flags;
+    h->mm_mode = (params->flags & AMPS_RX_TIMING_MM) != 0;
     { const char *e = std::getenv("AMPS_RX_SERIAL"); h->serial = e && e[0] == '1'; }
     if (params->lpf_taps) h->lpf.assign(params->lpf_taps, params->lpf_taps + params->n_lpf_taps);
     else h->lpf = firdes_low_pass(3.0, 400e3, 10e3, 4500.0, WIN_BLACKMAN);     // grc/ampsbs.grc:138-184
@@ -150,6 +184,7 @@ extern "C" int amps_recc_iq_destroy(amps_recc_iq *h) {
     for (int i = 0; i < amps_recc_iq::kEv; ++i) { if (h->ev0[i]) cudaEventDestroy(h->ev0[i]); if (h->ev1[i]) cudaEventDestroy(h->ev1[i]); }
     cudaFree(h->d_stage); cudaFree(h->d_tail[0]); cudaFree(h->d_tail[1]); cudaFree(h->d_dring); cudaFree(h->d_hring);
     cudaFree(h->d_ydump); cudaFree(h->d_state); cudaFree(h->d_cand); cudaFree(h->d_acc);
+    cudaFree(h->d_mm); cudaFree(h->d_mmtab); cudaFree(h->d_sym); cudaFree(h->d_compat); cudaFree(h->d_blobs); cudaFree(h->d_blob_idx);
     if (h->h_ring) cudaFreeHost(h->h_ring);
     if (h->h_pub) cudaFreeHost(h->h_pub);
     delete h;
@@ -163,6 +198,7 @@ extern "C" int amps_recc_iq_reset(amps_recc_iq *h) {
     for (int i = 0; i < 2; ++i) CK(cudaMemset(h->d_tail[i], 0, (size_t)h->hist * sizeof(float2)));
     CK(cudaMemset(h->d_state, 0, sizeof(RxState)));
     CK(cudaMemset(h->d_dring, 0, ((size_t)h->dmask + 1) * sizeof(float)));
+    if (h->mm_mode) { int rc = mm_reset(h); if (rc != AMPS_OK) return rc; }
     std::memset(h->h_pub, 0, sizeof(RxPublished));
     h->consumed = 0; h->call_no = 0;
     h->tail_cur = 0; h->carry = 0; h->samples_in = 0; h->total_d = 0; h->scan_hi = 0;
@@ -211,7 +247,17 @@ static int rx_enqueue(amps_recc_iq *h, const float2 *d_chunk, uint32_t npass, cu
     CK(cudaEventRecord(h->ev_front, st));
     cudaStream_t sd = h->serial ? st : h->side;
     if (!h->serial) CK(cudaStreamWaitEvent(sd, h->ev_front, 0));
-    if (h->total_d > (uint64_t)kSpan) {
+    if (h->mm_mode) {
+        // serial tail: M&M + slicer over everything demodulated so far, amps.recc on the new half-symbols, then
+        // one CTA per blob decodes and publishes it
+        CKL(launch_rx_mm(h->d_dring, h->dmask, h->total_d, h->d_mm, h->d_mmtab, h->d_sym, h->sym_cap, h->d_compat, h->d_blobs,
+                         h->d_blob_idx, kMaxAccept, h->d_state, h->h_pub, sd));
+        int max_new = (int)((uint64_t)npass * kPassOut / (8u * (unsigned)kMmQuantum)) + 2;   // <= one blob per work() quantum
+        if (max_new > kMaxAccept) max_new = kMaxAccept;
+        CKL(launch_rx_capture(h->d_dring, h->dmask, h->d_state, h->d_acc, max_new, h->h_ring, h->max_records, h->h_pub, h->decim, sd,
+                              h->d_blobs, h->d_blob_idx));
+        h->launches += 3;
+    } else if (h->total_d > (uint64_t)kSpan) {
         const uint64_t hi = h->total_d - (uint64_t)kSpan;
         const uint64_t lo = h->scan_hi > 64 ? h->scan_hi - 64 : 0;
         if (hi > h->scan_hi) {
@@ -247,7 +293,8 @@ static int rx_fetch(amps_recc_iq *h, uint64_t *n_out) {
     CK(cudaStreamSynchronize(h->side));
     CK(cudaStreamSynchronize(h->last_stream));
     if (h->h_pub->cand_overflow)
-        return set_error(AMPS_E_OVERFLOW, "trigger candidate list overflowed (more than 8192 matches in one call)");
+        return set_error(AMPS_E_OVERFLOW, h->mm_mode ? "more than 512 bursts captured in one call"
+                                                     : "trigger candidate list overflowed (more than 8192 matches in one call)");
     const uint64_t total = h->h_pub->nrec_total;
     if (total - h->consumed > h->max_records) {           // the ring wrapped over uncollected records
         h->lost += total - h->consumed - h->max_records;

@@ -1,5 +1,8 @@
 #include "design.h"
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <utility>
 
 namespace amps {
 
@@ -51,6 +54,43 @@ void cic3_taps(int decim, std::vector<float> &taps) {
     const double norm = (double)decim * decim * decim;
     taps.resize(c.size());
     for (size_t i = 0; i < c.size(); i++) taps[i] = (float)(c[i] / norm);
+}
+
+// Normal equations of the band-limited (|f| < 1/4) least-squares interpolator:
+//   sum_j r(i - j) h_j = r(i - 3 - mu),   r(t) = sin(pi t / 2) / (pi t),  r(0) = 1/2
+// Gauss-Jordan in double; the result is then cut to the 6 significant digits GNU Radio's table is printed with.
+static double band_autocorr(double t) { return std::fabs(t) < 1e-12 ? 0.5 : std::sin(0.5 * kPi * t) / (kPi * t); }
+
+std::vector<float> mmse_interp_table() {
+    const int N = 8, rows = 129;
+    std::vector<float> table((size_t)rows * N);
+    for (int m = 0; m < rows; m++) {
+        const double mu = m / 128.0;
+        double a[N][N + 1];
+        for (int i = 0; i < N; i++) {
+            for (int j = 0; j < N; j++) a[i][j] = band_autocorr(i - j);
+            a[i][N] = band_autocorr(i - 3.0 - mu);
+        }
+        for (int c = 0; c < N; c++) {
+            int best = c;
+            for (int r = c + 1; r < N; r++)
+                if (std::fabs(a[r][c]) > std::fabs(a[best][c])) best = r;
+            for (int k = 0; k <= N; k++) std::swap(a[c][k], a[best][k]);
+            const double inv = 1.0 / a[c][c];
+            for (int k = c; k <= N; k++) a[c][k] *= inv;
+            for (int r = 0; r < N; r++) {
+                if (r == c) continue;
+                const double f = a[r][c];
+                for (int k = c; k <= N; k++) a[r][k] -= f * a[c][k];
+            }
+        }
+        for (int k = 0; k < N; k++) {
+            char txt[32];
+            std::snprintf(txt, sizeof txt, "%.5e", std::fabs(a[k][N]) < 1e-9 ? 0.0 : a[k][N]);
+            table[(size_t)m * N + k] = (float)std::strtod(txt, nullptr);
+        }
+    }
+    return table;
 }
 
 }  // namespace amps

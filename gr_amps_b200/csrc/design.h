@@ -12,4 +12,7 @@ std::vector<float> firdes_low_pass(double gain, double fs, double fc, double tw,
 uint32_t nco_fcw(double center_freq, double samp_rate);          // phase step for a shift by -center_freq
 void nco_block_table(uint32_t fcw, int n, float *re_im_pairs);   // e^{j 2 pi (k*fcw mod 2^32) / 2^32}, k < n
 void cic3_taps(int decim, std::vector<float> &taps);              // boxcar^3 / decim^3
+// 129 x 8 MMSE interpolator of clock_recovery_mm_ff (bandwidth 1/4, 6 significant digits like GNU Radio's header);
+// row m, column k weights sample pos+k for mu = m/128
+std::vector<float> mmse_interp_table();
 }  // namespace amps

@@ -15,6 +15,7 @@
 // streaming kernel: each CTA owns a contiguous run of passes, keeps the filter history in shared
 // memory and re-reads only one warm-up pass at the start of its run.
 #include "rx_kernels.cuh"
+#include "recc_compat.cuh"
 
 namespace amps {
 
@@ -573,9 +574,13 @@ cudaError_t launch_rx_select(RxState *state, Candidate *cand, Accepted *acc, uns
     return cudaGetLastError();
 }
 
+// blobs == nullptr: feed-forward timing, the symbols are sliced out of the demod ring at the accepted phase.
+// blobs != nullptr: M&M timing mode, amps.recc already cut the 3374-byte blobs (rx_mm_recc_kernel).
 __global__ void __launch_bounds__(256) rx_capture_kernel(const float *__restrict__ dring, uint32_t dmask, RxState *state,
                                                         const Accepted *acc, amps_burst *host_ring, unsigned int ring_len,
-                                                        RxPublished *host_pub, unsigned int decim) {
+                                                        RxPublished *host_pub, unsigned int decim,
+                                                        const uint8_t *__restrict__ blobs,
+                                                        const unsigned long long *__restrict__ blob_sym_index) {
     __shared__ __align__(16) unsigned char rec_raw[sizeof(amps_burst)];
     __shared__ uint8_t s_valid[40];
     __shared__ unsigned int s_errs[8];
@@ -583,18 +588,32 @@ __global__ void __launch_bounds__(256) rx_capture_kernel(const float *__restrict
     if (blockIdx.x >= n_acc) return;
     const int t = threadIdx.x, nt = blockDim.x;
     amps_burst *rec = reinterpret_cast<amps_burst *>(rec_raw);
-    const Accepted a = acc[blockIdx.x];
-    // the 3374 half-symbols after the trigger, sliced at the chosen sampling phase (recc_impl.cc:124-126)
-    for (int s = t; s < kCapture; s += nt) {
-        const float v = dring[(a.pos + (unsigned long long)(kOS * (kTrig + s))) & dmask];
-        rec->symbols[s] = v >= 0.0f ? 1 : 0;
-    }
-    if (t == 0) {
-        rec->demod_index = a.pos;
-        rec->sample_index = a.pos * (unsigned long long)decim;
-        rec->corr = a.corr;
-        rec->run_length = a.run;
-        rec->pad[0] = 0; rec->pad[1] = 0;
+    if (blobs) {
+        for (int s = t; s < kCapture; s += nt) rec->symbols[s] = blobs[(size_t)blockIdx.x * kCapture + s];
+        if (t == 0) {
+            // position bookkeeping is nominal here: the recovered half-symbol index, 10 demod samples per half-symbol
+            const unsigned long long first_sym = blob_sym_index[blockIdx.x];
+            const unsigned long long trig_sym = first_sym >= (unsigned long long)kTrig ? first_sym - kTrig : 0ull;
+            rec->demod_index = trig_sym * (unsigned long long)kOS;
+            rec->sample_index = rec->demod_index * (unsigned long long)decim;
+            rec->corr = 0.0f;
+            rec->run_length = 0;
+            rec->pad[0] = 0; rec->pad[1] = 0;
+        }
+    } else {
+        const Accepted a = acc[blockIdx.x];
+        // the 3374 half-symbols after the trigger, sliced at the chosen sampling phase (recc_impl.cc:124-126)
+        for (int s = t; s < kCapture; s += nt) {
+            const float v = dring[(a.pos + (unsigned long long)(kOS * (kTrig + s))) & dmask];
+            rec->symbols[s] = v >= 0.0f ? 1 : 0;
+        }
+        if (t == 0) {
+            rec->demod_index = a.pos;
+            rec->sample_index = a.pos * (unsigned long long)decim;
+            rec->corr = a.corr;
+            rec->run_length = a.run;
+            rec->pad[0] = 0; rec->pad[1] = 0;
+        }
     }
     __syncthreads();
     decode_burst_block(rec->symbols, &rec->decoded, s_valid, s_errs);
@@ -621,10 +640,119 @@ __global__ void __launch_bounds__(256) rx_capture_kernel(const float *__restrict
 
 cudaError_t launch_rx_capture(const float *dring, uint32_t dmask, RxState *state, const Accepted *acc, int grid,
                               amps_burst *host_ring, unsigned int ring_len, RxPublished *host_pub, unsigned int decim,
-                              cudaStream_t st) {
+                              cudaStream_t st, const uint8_t *blobs, const unsigned long long *blob_sym_index) {
     if (grid <= 0) return cudaSuccess;
     if (grid > kMaxAccept) grid = kMaxAccept;
-    rx_capture_kernel<<<grid, 256, 0, st>>>(dring, dmask, state, acc, host_ring, ring_len, host_pub, decim);
+    rx_capture_kernel<<<grid, 256, 0, st>>>(dring, dmask, state, acc, host_ring, ring_len, host_pub, decim, blobs, blob_sym_index);
+    return cudaGetLastError();
+}
+
+// ============================================================================================
+// M&M timing mode (AMPS_RX_TIMING_MM): the reference graph's own serial tail
+//   clock_recovery_mm_ff(10, 0.02296875, 0, 0.05, 0.005) -> binary_slicer_fb -> amps.recc
+// (grc/ampsbs.grc:1751-1813, 1712-1750, 4602) on the demodulated stream.  The loop is a recurrence
+// over symbols (mu, omega and the sample position all feed the next step), so ONE thread walks it;
+// the other threads of the CTA only stage the demod ring into shared memory and write the symbols
+// out.  The exact fp32 operation order is the one oracle/mm_timing.c states.
+// ============================================================================================
+constexpr int kMmStage = 4096;     // demod samples staged per round
+constexpr int kMmSymStage = 512;   // symbols produced per round at most
+
+__global__ void __launch_bounds__(128) rx_mm_kernel(const float *__restrict__ dring, uint32_t dmask, unsigned long long total_d,
+                                                   MmState *st, const float *__restrict__ table, uint8_t *__restrict__ sym_out,
+                                                   unsigned int sym_cap) {
+    __shared__ float s_tab[kMmPhases * 8];
+    __shared__ float s_d[kMmStage + 8];
+    __shared__ uint8_t s_sym[kMmSymStage];
+    __shared__ unsigned long long s_pos;
+    __shared__ int s_n;
+    const int t = threadIdx.x, nt = blockDim.x;
+    for (int i = t; i < kMmPhases * 8; i += nt) s_tab[i] = table[i];
+    if (t == 0) s_pos = st->pos;
+    float mu = st->mu, omega = st->omega, last = st->last;          // only thread 0's copies matter
+    const float omega_mid = 10.0f, gain_omega = 0.02296875f, gain_mu = 0.05f;
+    const float omega_lim = __fmul_rn(omega_mid, 0.005f);
+    unsigned int out_n = 0;
+    __syncthreads();
+    for (;;) {
+        const unsigned long long base = s_pos;
+        if (base + 8ull > total_d || out_n >= sym_cap) break;
+        const unsigned long long avail = total_d - base;
+        const int n_ld = avail < (unsigned long long)(kMmStage + 8) ? (int)avail : kMmStage + 8;
+        for (int i = t; i < n_ld; i += nt) s_d[i] = dring[(base + (unsigned long long)i) & dmask];
+        __syncthreads();
+        if (t == 0) {
+            int p = 0, n = 0;
+            const unsigned int room = sym_cap - out_n;
+            const int n_max = room < (unsigned)kMmSymStage ? (int)room : kMmSymStage;
+            while (p + 8 <= n_ld && p < kMmStage && n < n_max) {
+                const int imu = __float2int_rn(__fmul_rn(mu, 128.0f));
+                const float *tp = s_tab + 8 * imu, *x = s_d + p;
+                float s = __fmul_rn(tp[0], x[0]);
+#pragma unroll
+                for (int k = 1; k < 8; ++k) s = __fmaf_rn(tp[k], x[k], s);
+                const float a = last < 0.0f ? -s : s;                 // sgn(last) * s
+                const float b = s < 0.0f ? -last : last;              // sgn(s) * last
+                const float mm = __fsub_rn(a, b);
+                last = s;
+                omega = __fadd_rn(omega, __fmul_rn(gain_omega, mm));
+                const float dev = __fsub_rn(omega, omega_mid);
+                omega = __fadd_rn(omega_mid, __fmul_rn(0.5f, __fsub_rn(fabsf(__fadd_rn(dev, omega_lim)), fabsf(__fsub_rn(dev, omega_lim)))));
+                mu = __fadd_rn(__fadd_rn(mu, omega), __fmul_rn(gain_mu, mm));
+                float f = floorf(mu);
+                if (f >= 1.0f && f <= 64.0f) mu = __fsub_rn(mu, f);
+                else { f = f > 64.0f ? 64.0f : 1.0f; mu = 0.0f; }
+                p += (int)f;
+                s_sym[n++] = s >= 0.0f ? 1 : 0;                       // binary_slicer_fb
+            }
+            s_pos = base + (unsigned long long)p;
+            s_n = n;
+        }
+        __syncthreads();
+        const int n = s_n;
+        for (int i = t; i < n; i += nt) sym_out[out_n + i] = s_sym[i];
+        out_n += (unsigned int)n;
+        __syncthreads();
+        if (n == 0) break;
+    }
+    if (t == 0) {
+        st->mu = mu; st->omega = omega; st->last = last;
+        st->pos = s_pos;
+        st->n_new = out_n;
+        st->nsym_total += out_n;
+    }
+}
+
+// amps.recc on the symbols the M&M kernel just produced, in work() calls of kMmQuantum bytes (the reference sees the
+// stream in scheduler-sized pieces and searches / publishes at most once per call, lib/recc_impl.cc:115-126), then the
+// bookkeeping rx_select_kernel does in the feed-forward mode.
+__global__ void __launch_bounds__(256) rx_mm_recc_kernel(ReccCompatState *cs, const MmState *mm, const uint8_t *__restrict__ sym,
+                                                        uint8_t *blobs, unsigned long long *blob_sym_index, int max_blobs,
+                                                        RxState *state, RxPublished *host_pub) {
+    const unsigned int n = mm->n_new;
+    const int nchunks = (int)((n + (unsigned)kMmQuantum - 1u) / (unsigned)kMmQuantum);
+    int nb = recc_compat_run(cs, sym, nchunks,
+                             [n](int c) { const unsigned int rem = n - (unsigned)c * (unsigned)kMmQuantum; return rem < (unsigned)kMmQuantum ? rem : (unsigned)kMmQuantum; },
+                             blobs, max_blobs, blob_sym_index);
+    if (threadIdx.x == 0) {
+        if (nb > max_blobs) { state->cand_overflow = 1; nb = max_blobs; }
+        state->n_acc = (unsigned int)nb;
+        state->done = 0;
+        state->rec_base = state->nrec_total;
+        state->nrec_total += (unsigned long long)nb;
+        if (nb == 0) {
+            __threadfence_system();
+            host_pub->cand_overflow = state->cand_overflow;
+        }
+    }
+}
+
+cudaError_t launch_rx_mm(const float *dring, uint32_t dmask, unsigned long long total_d, MmState *mm, const float *table,
+                         uint8_t *sym, unsigned int sym_cap, ReccCompatState *cs, uint8_t *blobs,
+                         unsigned long long *blob_sym_index, int max_blobs, RxState *state, RxPublished *host_pub,
+                         cudaStream_t st) {
+    rx_mm_kernel<<<1, 128, 0, st>>>(dring, dmask, total_d, mm, table, sym, sym_cap);
+    rx_mm_recc_kernel<<<1, 256, 0, st>>>(cs, mm, sym, blobs, blob_sym_index, max_blobs, state, host_pub);
     return cudaGetLastError();
 }
 

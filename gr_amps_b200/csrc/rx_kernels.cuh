@@ -1,6 +1,7 @@
 // rx_kernels.cuh -- launch interface of the fused RECC receive kernels (implementation: rx_kernels.cu)
 #pragma once
 #include "spec.cuh"
+#include "blocks_kernels.cuh"
 #include "../../include/amps_b200.h"
 
 namespace amps {
@@ -68,6 +69,16 @@ struct Candidate {
     unsigned int       run;     // run length; bit 31 set = the run reaches the end of the searched range
 };
 
+// M&M timing mode: state of the clock_recovery_mm_ff recurrence (device-resident, carried between calls)
+struct MmState {
+    float mu, omega, last;
+    unsigned int       n_new;       // half-symbols produced by the last rx_mm_kernel launch
+    unsigned long long pos;         // absolute demod index of the interpolator window's first sample
+    unsigned long long nsym_total;
+};
+constexpr int kMmPhases = 129;     // interpolator table rows (mu = 0, 1/128 .. 1)
+constexpr int kMmQuantum = 256;    // bytes per emulated amps.recc work() call
+
 constexpr int kMaxCand = 8192;
 constexpr int kMaxAccept = 512;    // bursts one call can publish
 
@@ -84,7 +95,13 @@ cudaError_t launch_rx_select(RxState *state, Candidate *cand, Accepted *acc, uns
 // decodes, and streams the record into host_ring[(rec_base + b) % ring_len] (mapped pinned host memory)
 cudaError_t launch_rx_capture(const float *dring, uint32_t dmask, RxState *state, const Accepted *acc, int grid,
                               amps_burst *host_ring, unsigned int ring_len, RxPublished *host_pub, unsigned int decim,
-                              cudaStream_t st);
+                              cudaStream_t st, const uint8_t *blobs = nullptr, const unsigned long long *blob_sym_index = nullptr);
+// M&M timing mode: serial clock recovery + slicer over the demod ring up to total_d, then amps.recc on the new
+// half-symbols; leaves state->n_acc blobs (<= max_blobs) for launch_rx_capture(..., blobs, blob_sym_index)
+cudaError_t launch_rx_mm(const float *dring, uint32_t dmask, unsigned long long total_d, MmState *mm, const float *table,
+                         uint8_t *sym, unsigned int sym_cap, ReccCompatState *cs, uint8_t *blobs,
+                         unsigned long long *blob_sym_index, int max_blobs, RxState *state, RxPublished *host_pub,
+                         cudaStream_t st);
 cudaError_t launch_decode_blobs(const uint8_t *blobs, int nbursts, amps_recc_words *out, cudaStream_t st);
 
 }  // namespace amps

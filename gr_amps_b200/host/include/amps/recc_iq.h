@@ -10,6 +10,8 @@ namespace gr { namespace amps {
 class AMPS_API recc_iq : virtual public gr::sync_block {
 public:
     typedef std::shared_ptr<recc_iq> sptr;
-    static sptr make(double samp_rate, double center_freq, int device = 0);
+    // mm_timing: symbol timing by the reference graph's clock_recovery_mm_ff -> binary_slicer_fb -> amps.recc tail
+    // (AMPS_RX_TIMING_MM) instead of the feed-forward trigger detector
+    static sptr make(double samp_rate, double center_freq, int device = 0, bool mm_timing = false);
 };
 }}

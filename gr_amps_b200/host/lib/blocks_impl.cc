@@ -99,15 +99,16 @@ int recc_impl::work(int noutput_items, gr_vector_const_void_star &input_items, g
 }
 
 // ------------------------------------------------------------------ recc_iq (new sibling block)
-recc_iq::sptr recc_iq::make(double samp_rate, double center_freq, int device) {
-    return gnuradio::get_initial_sptr(new recc_iq_impl(samp_rate, center_freq, device));
+recc_iq::sptr recc_iq::make(double samp_rate, double center_freq, int device, bool mm_timing) {
+    return gnuradio::get_initial_sptr(new recc_iq_impl(samp_rate, center_freq, device, mm_timing));
 }
-recc_iq_impl::recc_iq_impl(double samp_rate, double center_freq, int device)
+recc_iq_impl::recc_iq_impl(double samp_rate, double center_freq, int device, bool mm_timing)
     : gr::sync_block("recc_iq", gr::io_signature::make(1, 1, sizeof(std::complex<float>)), gr::io_signature::make(0, 0, 0)), d_h(NULL) {
     amps_recc_iq_params p;
     std::memset(&p, 0, sizeof p);
     p.samp_rate = samp_rate; p.center_freq = center_freq; p.device = device;
     p.max_samples = 1u << 22;                      // the scheduler never hands a block more than this at once
+    p.flags = mm_timing ? AMPS_RX_TIMING_MM : 0u;
     must(amps_recc_iq_create(&p, &d_h), "recc_iq");
     message_port_register_out(pmt::mp("bursts"));
 }

@@ -54,7 +54,8 @@ int main() {
     taps("lpf", firdes_low_pass(3.0, 400e3, 10e3, 4500.0, WIN_BLACKMAN));
     taps("focc_interp", firdes_low_pass(1.0, 400e3, 10e3, 5e3, WIN_HAMMING));
     taps("fvc_interp", firdes_low_pass(1.0, 400e3, 10e3, 3e3, WIN_HAMMING));
-    taps("cic25", cic, true);
+    taps("cic25", cic);
+    taps("mmse", mmse_interp_table(), true);
     std::printf(" }\n}\n");
     return 0;
 }

@@ -118,6 +118,12 @@ typedef struct amps_recc_iq_params {
 
 #define AMPS_RX_DUMP_BASEBAND 1u   /* keep the 200 kS/s complex baseband of the last call for inspection */
 #define AMPS_RX_TIME_KERNELS  2u   /* bracket every front-end kernel launch with CUDA events (roofline accounting) */
+#define AMPS_RX_TIMING_MM     4u   /* symbol timing by the reference graph's own serial tail -- clock_recovery_mm_ff(10,
+                                      0.02296875, 0, 0.05, 0.005) -> binary_slicer_fb -> amps.recc with its buffer quirks, fed in
+                                      256-byte work() calls (grc/ampsbs.grc:1751-1813, 1712-1750; lib/recc_impl.cc:93-145) --
+                                      instead of the feed-forward detector.  One GPU thread walks the recurrence, so this mode
+                                      runs at tens of Msymbols/s, not at the memory roofline.  In the burst record demod_index /
+                                      sample_index are then nominal (recovered half-symbol index x 10), corr and run_length 0. */
 
 typedef void (*amps_burst_cb)(const amps_burst *burst, void *user);
 

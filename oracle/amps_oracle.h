@@ -160,6 +160,12 @@ typedef struct {
 } orc_burst;
 int  orc_rx_detect(const float *d, size_t nd, orc_burst *out, int max);
 
+/* ---------------------------------------------------------------- serial M&M timing tail (mm_timing.c) */
+typedef struct { float mu, omega, last; uint32_t pad; uint64_t pos; } orc_mm_state;
+void   orc_mmse_table(float *T /* 129 x 8 */);
+void   orc_mm_init(orc_mm_state *st);
+size_t orc_mm_process(orc_mm_state *st, const float *d, uint64_t total, const float *T, uint8_t *sym, size_t cap);
+
 /* Forward (TX) chain, f64 "ideal" (config 3); see dsp_chain.c for the definition. */
 void orc_fwd_chain_f64(const int8_t *const *sym, int ncarriers, size_t nsym, uint32_t fcw_fm,
                        const float *const *taps, const int *ntaps, const uint32_t *fcw_mix, double scale,

@@ -237,6 +237,37 @@ def rx_detect(d: np.ndarray, max_bursts=64):
     return [(int(arr[i].d_index), float(arr[i].corr), np.frombuffer(bytes(arr[i].symbols), np.uint8).copy()) for i in range(n)]
 
 
+class MmState(C.Structure):
+    _fields_ = [("mu", C.c_float), ("omega", C.c_float), ("last", C.c_float), ("pad", C.c_uint32), ("pos", C.c_uint64)]
+
+
+def mmse_table() -> np.ndarray:
+    t = np.zeros(129 * 8, np.float32)
+    lib().orc_mmse_table.argtypes = [f32p]
+    lib().orc_mmse_table(ptr(t, f32p))
+    return t.reshape(129, 8)
+
+
+class MmTiming:
+    """Serial clock_recovery_mm_ff + binary_slicer_fb on a growing demod stream (oracle/mm_timing.c)."""
+
+    def __init__(self):
+        L = lib()
+        L.orc_mm_init.argtypes = [C.POINTER(MmState)]
+        L.orc_mm_process.argtypes = [C.POINTER(MmState), f32p, C.c_uint64, f32p, u8p, C.c_size_t]
+        L.orc_mm_process.restype = C.c_size_t
+        self.st = MmState()
+        L.orc_mm_init(C.byref(self.st))
+        self.table = np.ascontiguousarray(mmse_table().reshape(-1))
+
+    def process(self, d: np.ndarray, total: int) -> np.ndarray:
+        """d = the whole stream so far (float32, from its first sample); returns the new half-symbols."""
+        d = np.ascontiguousarray(d, dtype=np.float32)
+        out = np.zeros(total // 8 + 16, np.uint8)
+        n = lib().orc_mm_process(C.byref(self.st), ptr(d, f32p), total, ptr(self.table, f32p), ptr(out, u8p), len(out))
+        return out[:n]
+
+
 def cpu_baseline_run(x: np.ndarray, threads: int, reps: int, center=-160e3, fs=10e6):
     """Time the fp32 oracle chain (+detect+decode) on `threads` host threads; returns (seconds, bursts)."""
     iq = iq_f32(x)

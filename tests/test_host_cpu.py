@@ -54,6 +54,7 @@ def test_filter_designs_match_oracle(proto, oracle):
     assert np.array_equal(np.float32(t["lpf"]), oracle.lpf_taps()) and len(t["lpf"]) == 299
     assert np.array_equal(np.float32(t["focc_interp"]), oracle.firdes_low_pass(1.0, 400e3, 10e3, 5e3, 0)) and len(t["focc_interp"]) == 193
     assert np.array_equal(np.float32(t["fvc_interp"]), oracle.firdes_low_pass(1.0, 400e3, 10e3, 3e3, 0)) and len(t["fvc_interp"]) == 321
+    assert np.array_equal(np.float32(t["mmse"]).reshape(129, 8), oracle.mmse_table())
     c = np.float32(t["cic25"])
     assert len(c) == 73 and abs(float(c.astype(np.float64).sum()) - 1.0) < 1e-6 and np.array_equal(c, c[::-1])
     assert c[0] == np.float32(1 / 15625) and c[36] == np.float32(469 / 15625)

@@ -310,3 +310,34 @@ def test_rx_detect_resume_and_run_semantics(oracle):
     b = oracle.rx_detect(d)
     assert len(b) == 2 and b[1][0] - b[0][0] == 55 * 38400 // 50
     assert np.array_equal(b[0][2], b[1][2])
+
+
+def test_mmse_table_and_mm_loop_properties(oracle):
+    """oracle/mm_timing.c: the interpolator table against the two rows of GNU Radio's interpolator_taps.h that are
+    on record (recalled, 6 significant digits; GNU Radio stores them reversed for its FIR), its symmetries, and the
+    chunking invariance of the recurrence."""
+    T = oracle.mmse_table()
+    assert T.shape == (129, 8)
+    assert np.array_equal(T[0], np.float32([0, 0, 0, 1, 0, 0, 0, 0])) and np.array_equal(T[128], np.float32([0, 0, 0, 0, 1, 0, 0, 0]))
+    assert np.array_equal(T[64], np.float32([-6.77751e-03, 3.94578e-02, -1.42658e-01, 6.09836e-01, 6.09836e-01, -1.42658e-01, 3.94578e-02, -6.77751e-03]))
+    assert np.array_equal(T[1][::-1], np.float32([-1.54700e-04, 8.53777e-04, -2.76968e-03, 7.89295e-03, 9.98534e-01, -5.41054e-03, 1.24642e-03, -1.98993e-04]))
+    for m in range(129):
+        assert np.array_equal(T[m], T[128 - m][::-1])
+        assert abs(float(T[m].astype(np.float64).sum()) - 1.0) < 5e-4
+    # random NRZ data, 10 samples per symbol, smoothed edges: the loop locks and returns the data
+    n = 40000
+    data = np.random.default_rng(1).integers(0, 2, n // 10)
+    nrz = np.repeat(2.0 * data - 1.0, 10)
+    d = (0.25 * np.convolve(nrz, np.hanning(13) / np.hanning(13).sum(), mode="same")).astype(np.float32)
+    one = oracle.MmTiming()
+    s1 = one.process(d, n)
+    assert abs(len(s1) - n / 10) < 25
+    assert any(np.array_equal(s1[300:3900], data[300 + k:3900 + k]) for k in range(-2, 3))
+    rng = np.random.default_rng(2)
+    st, parts, total = oracle.MmTiming(), [], 0
+    while total < n:
+        total = min(n, total + int(rng.integers(1, 3000)))
+        parts.append(st.process(d, total))
+    assert np.array_equal(np.concatenate(parts), s1)
+    assert (st.st.mu, st.st.omega, st.st.pos) == (one.st.mu, one.st.omega, one.st.pos)
+    assert 9.95 <= one.st.omega <= 10.05
