@@ -77,6 +77,11 @@ class FwdParams(C.Structure):
     ]
 
 
+class FwdVoiceParams(C.Structure):
+    _fields_ = [("carrier_gated", C.c_int), ("carrier_open", C.c_int), ("audio_rate", C.c_double), ("max_dev", C.c_double),
+                ("tau", C.c_double), ("sat_freq", C.c_double), ("sat_amp", C.c_double)]
+
+
 BURST_CB = C.CFUNCTYPE(None, C.POINTER(Burst), C.c_void_p)
 BLOB_CB = C.CFUNCTYPE(None, u8p, C.c_void_p)
 
@@ -97,6 +102,7 @@ EXPORTS = [
     "amps_fvc_create", "amps_fvc_destroy", "amps_fvc_push_words", "amps_fvc_work", "amps_fvc_work_bits",
     "amps_fwd_create", "amps_fwd_destroy", "amps_fwd_reset", "amps_fwd_work", "amps_fwd_submit_dev",
     "amps_fwd_interp", "amps_fwd_get_taps", "amps_fwd_work_bits", "amps_fwd_submit_bits_dev",
+    "amps_fwd_enable_voice", "amps_fwd_work_voice", "amps_fwd_submit_voice_dev",
 ]
 
 _lib = None
@@ -432,6 +438,28 @@ class Fwd:
     def submit_dev(self, dev_ptrs, nsym: int, out_ptr: int, stream: int = 0):
         ptrs = (C.c_void_p * 3)(*list(dev_ptrs) + [None] * (3 - len(dev_ptrs)))
         check(lib().amps_fwd_submit_dev(self.h, ptrs, nsym, C.c_void_p(out_ptr), C.c_void_p(stream)))
+
+    def enable_voice(self, carrier_gated=1, carrier_open=2, sat_amp=0.05):
+        """Voice legs of the reference graph: nbfm_tx(16 kS/s) -> x25 arb resampler in front of the carriers' mixers."""
+        vp = FwdVoiceParams(carrier_gated, carrier_open, 16000.0, 8e3, 75e-6, 6000.0, sat_amp)
+        lib().amps_fwd_enable_voice.argtypes = [C.c_void_p, C.POINTER(FwdVoiceParams)]
+        check(lib().amps_fwd_enable_voice(self.h, C.byref(vp)))
+
+    def work_voice(self, syms, audio, audio_mute=False) -> np.ndarray:
+        arrs = [np.ascontiguousarray(s, dtype=np.uint8) for s in syms]
+        nsym = len(arrs[0])
+        a = np.ascontiguousarray(audio, dtype=np.float32)
+        assert len(a) == nsym * 4 // 25
+        ptrs = (C.c_void_p * 3)(*[x.ctypes.data for x in arrs] + [None] * (3 - len(arrs)))
+        out = np.zeros(2 * nsym * self.interp, np.float32)
+        lib().amps_fwd_work_voice.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), f32p, C.c_size_t, C.c_int, f32p]
+        check(lib().amps_fwd_work_voice(self.h, ptrs, a.ctypes.data_as(f32p), nsym, int(bool(audio_mute)), out.ctypes.data_as(f32p)))
+        return out.view(np.complex64)
+
+    def submit_voice_dev(self, dev_ptrs, audio_ptr: int, nsym: int, out_ptr: int, audio_mute=False, stream: int = 0):
+        ptrs = (C.c_void_p * 3)(*list(dev_ptrs) + [None] * (3 - len(dev_ptrs)))
+        lib().amps_fwd_submit_voice_dev.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]
+        check(lib().amps_fwd_submit_voice_dev(self.h, ptrs, C.c_void_p(audio_ptr), nsym, int(bool(audio_mute)), C.c_void_p(out_ptr), C.c_void_p(stream)))
 
     def work_bits(self, bits) -> np.ndarray:
         """Manchester-bit fast path: bits = list of uint8 arrays (0, 1, 0xFF = muted); 1000 output samples per bit."""

@@ -32,7 +32,30 @@ struct amps_fwd {
     int hbits_cur = 0;
     uint64_t bit_total = 0;
     int mode = 0;                             // 0 unset, 1 symbol stream, 2 bit stream (no mixing without reset)
+    // voice legs
+    bool voice = false;
+    VoicePrepParams vp{};
+    float *d_audio = nullptr;                 // host-path staging
+    double *d_hx[2] = {};
+    unsigned long long *d_delta = nullptr, *d_phase = nullptr;
+    float2 *d_vph[kFwdVoiceLegs] = {};
+    float2 *d_vhist[2][kFwdVoiceLegs] = {};
+    int vhist_cur = 0;
+    uint64_t audio_total = 0;
+    uint32_t max_audio = 0;
 };
+
+static int voice_reset_state(amps_fwd *h) {
+    if (!h->voice) return AMPS_OK;
+    for (int b = 0; b < 2; ++b) {
+        CK(cudaMemset(h->d_hx[b], 0, sizeof(double) * kVoiceImp));
+        for (int l = 0; l < kFwdVoiceLegs; ++l) CK(cudaMemset(h->d_vhist[b][l], 0, sizeof(float2) * kFwdVoiceHist));
+    }
+    CK(cudaMemset(h->d_phase, 0, sizeof(unsigned long long)));
+    h->vhist_cur = 0;
+    h->audio_total = 0;
+    return AMPS_OK;
+}
 
 static int fwd_reset_state(amps_fwd *h) {
     for (int b = 0; b < 2; ++b)
@@ -45,7 +68,7 @@ static int fwd_reset_state(amps_fwd *h) {
         for (int c = 0; c < kFwdMaxCar; ++c) CK(cudaMemset(h->d_hbits[b][c], 0xFF, 16));    // "muted" before the stream starts
     h->hist_cur = 0; h->hbits_cur = 0;
     h->sym_total = 0; h->bit_total = 0; h->mode = 0;
-    return AMPS_OK;
+    return voice_reset_state(h);
 }
 
 extern "C" int amps_fwd_create(const amps_fwd_params *p, amps_fwd **out) {
@@ -165,6 +188,9 @@ extern "C" int amps_fwd_destroy(amps_fwd *h) {
     }
     for (int c = 0; c < kFwdMaxCar; ++c) { cudaFree(h->d_bits[c]); cudaFree(h->d_hbits[0][c]); cudaFree(h->d_hbits[1][c]); }
     cudaFree(h->d_carry); cudaFree(h->d_out); cudaFree(h->d_resp);
+    cudaFree(h->d_audio); cudaFree(h->d_delta); cudaFree(h->d_phase);
+    for (int b = 0; b < 2; ++b) { cudaFree(h->d_hx[b]); for (int l = 0; l < kFwdVoiceLegs; ++l) cudaFree(h->d_vhist[b][l]); }
+    for (int l = 0; l < kFwdVoiceLegs; ++l) cudaFree(h->d_vph[l]);
     delete h;
     return AMPS_OK;
 }
@@ -185,8 +211,15 @@ extern "C" int amps_fwd_get_taps(const amps_fwd *h, int carrier, float *out, int
     return n;
 }
 
+static int fwd_submit_symbols(amps_fwd *h, const void *const *d_sym, size_t nsym, void *d_out_iq, cudaStream_t st, bool with_voice);
+
 extern "C" int amps_fwd_submit_dev(amps_fwd *h, const void *const *d_sym, size_t nsym, void *d_out_iq, void *cuda_stream) {
     if (!h || !d_sym || (nsym && !d_out_iq)) return set_error(AMPS_E_INVAL, "null argument");
+    if (h->voice) return set_error(AMPS_E_STATE, "voice legs are enabled: use amps_fwd_submit_voice_dev / amps_fwd_work_voice");
+    return fwd_submit_symbols(h, d_sym, nsym, d_out_iq, static_cast<cudaStream_t>(cuda_stream), false);
+}
+
+static int fwd_submit_symbols(amps_fwd *h, const void *const *d_sym, size_t nsym, void *d_out_iq, cudaStream_t st, bool with_voice) {
     if (nsym == 0) return AMPS_OK;
     if (nsym > h->max_sym) return set_error(AMPS_E_OVERFLOW, "nsym exceeds max_samples / 100");
     if (reinterpret_cast<uintptr_t>(d_out_iq) & 15u) return set_error(AMPS_E_ALIGN, "d_out_iq must be 16-byte aligned");
@@ -194,7 +227,6 @@ extern "C" int amps_fwd_submit_dev(amps_fwd *h, const void *const *d_sym, size_t
     if (h->mode == 2) return set_error(AMPS_E_STATE, "handle is streaming data bits; reset() before switching to half-symbol input");
     h->mode = 1;
     CK(cudaSetDevice(h->device));
-    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     const int cur = h->hist_cur, nxt = cur ^ 1;
     FwdScanParams sp{};
     FwdParams p = h->fp;
@@ -214,9 +246,10 @@ extern "C" int amps_fwd_submit_dev(amps_fwd *h, const void *const *d_sym, size_t
     p.nsym = (uint32_t)nsym;
     p.m_base = (uint32_t)(h->sym_total * 4u);
     const uint32_t ntiles = ((uint32_t)nsym + kFwdTileSym - 1) / kFwdTileSym;
-    uint32_t grid = 3u * (uint32_t)h->sm_count;                  // 70 KB smem, 60 registers: 3 CTAs per SM
+    uint32_t grid = (with_voice ? 2u : 3u) * (uint32_t)h->sm_count;   // 74 KB smem (83 KB with the voice legs), 60 registers
     if (grid > ntiles) grid = ntiles;
-    CKL(launch_fwd_fused(p, (int)grid, st));
+    if (with_voice) CKL(launch_fwd_fused_voice(p, (int)grid, st));
+    else CKL(launch_fwd_fused(p, (int)grid, st));
     h->hist_cur = nxt;
     h->sym_total += nsym;
     return AMPS_OK;
@@ -241,6 +274,103 @@ extern "C" int amps_fwd_work(amps_fwd *h, const uint8_t *const *sym, size_t nsym
 }
 
 // ---------------------------------------------------------------------------------------------
+// voice legs: audio @16 kS/s -> nbfm_tx -> x25 arb resampler, added in front of a carrier's mixer
+// ---------------------------------------------------------------------------------------------
+extern "C" int amps_fwd_enable_voice(amps_fwd *h, const amps_fwd_voice_params *vp) {
+    if (!h || !vp) return set_error(AMPS_E_INVAL, "null argument");
+    if (h->voice) return set_error(AMPS_E_STATE, "voice legs are already enabled");
+    if (h->mode != 0) return set_error(AMPS_E_STATE, "enable voice before streaming (or after reset())");
+    if (vp->audio_rate != 16000.0) return set_error(AMPS_E_INVAL, "audio_rate must be 16000 (x25 to 400 kS/s)");
+    if (vp->carrier_gated >= h->ncar || vp->carrier_open >= h->ncar || (vp->carrier_gated < 0 && vp->carrier_open < 0))
+        return set_error(AMPS_E_INVAL, "voice legs need a carrier index below ncarriers");
+    if (!(vp->max_dev > 0) || !(vp->tau > 0)) return set_error(AMPS_E_INVAL, "max_dev and tau must be positive");
+    // the SAT is generated from an 8-entry table: 6000 / 16000 = 3 / 8 turn per audio sample
+    if (vp->sat_amp != 0.0 && vp->sat_freq != 6000.0) return set_error(AMPS_E_INVAL, "sat_freq must be 6000");
+    CK(cudaSetDevice(h->device));
+    const double kTwoPi = 6.283185307179586476925286766559;
+    std::memset(&h->vp, 0, sizeof h->vp);
+    const std::vector<double> g = fm_preemph_impulse(vp->audio_rate, vp->tau, -1.0, kVoiceImp);    // nbfm_tx fh = -1 (grc :742)
+    for (int k = 0; k < kVoiceImp; ++k) h->vp.g[k] = g[(size_t)k];
+    for (int k = 0; k < 8; ++k) h->vp.sat[k] = vp->sat_amp * std::cos(kTwoPi * (double)((3 * k) % 8) / 8.0);
+    h->vp.cycles_per_unit = vp->max_dev / vp->audio_rate;
+    // voice_lpf_taps (grc :138-184 sibling block): firdes.low_pass(3, 400e3, 15e3, 6e3, BLACKMAN), 225 taps
+    int per = 0;
+    const std::vector<float> E = arb25_taps(firdes_low_pass(3.0, 400e3, 15e3, 6e3, WIN_BLACKMAN), per);
+    if (per > kFwdVoicePer) return set_error(AMPS_E_INVAL, "voice resampler has too many taps per arm");
+    h->fp.vper = per;
+    for (int r = 0; r < 25; ++r)
+        for (int k = 0; k < per; ++k) h->fp.E[r * kFwdVoicePer + k] = E[(size_t)r * per + k];
+    h->fp.vcar[0] = vp->carrier_gated;
+    h->fp.vcar[1] = vp->carrier_open;
+    h->max_audio = (uint32_t)(((uint64_t)h->max_sym * 4u + 24u) / 25u);
+    CK(cudaMalloc(&h->d_audio, sizeof(float) * h->max_audio));
+    CK(cudaMalloc(&h->d_delta, sizeof(unsigned long long) * h->max_audio));
+    CK(cudaMalloc(&h->d_phase, sizeof(unsigned long long)));
+    for (int b = 0; b < 2; ++b) {
+        CK(cudaMalloc(&h->d_hx[b], sizeof(double) * kVoiceImp));
+        for (int l = 0; l < kFwdVoiceLegs; ++l) CK(cudaMalloc(&h->d_vhist[b][l], sizeof(float2) * kFwdVoiceHist));
+    }
+    for (int l = 0; l < kFwdVoiceLegs; ++l) CK(cudaMalloc(&h->d_vph[l], sizeof(float2) * h->max_audio));
+    h->voice = true;
+    return voice_reset_state(h);
+}
+
+extern "C" int amps_fwd_submit_voice_dev(amps_fwd *h, const void *const *d_sym, const void *d_audio, size_t nsym, int audio_mute,
+                                         void *d_out_iq, void *cuda_stream) {
+    if (!h || !d_sym || (nsym && (!d_out_iq || !d_audio))) return set_error(AMPS_E_INVAL, "null argument");
+    if (!h->voice) return set_error(AMPS_E_STATE, "amps_fwd_enable_voice() was not called");
+    if (nsym == 0) return AMPS_OK;
+    if (nsym % 25) return set_error(AMPS_E_ALIGN, "nsym must be a multiple of 25 (whole 16 kS/s audio samples)");
+    if (nsym > h->max_sym) return set_error(AMPS_E_OVERFLOW, "nsym exceeds max_samples / 100");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    const uint32_t n_audio = (uint32_t)(nsym * 4 / 25);
+    const int cur = h->vhist_cur, nxt = cur ^ 1;
+    VoicePrepParams vp = h->vp;
+    vp.audio = static_cast<const float *>(d_audio);
+    vp.hx_old = h->d_hx[cur]; vp.hx_new = h->d_hx[nxt];
+    vp.delta = h->d_delta; vp.phase = h->d_phase;
+    for (int l = 0; l < kFwdVoiceLegs; ++l) {
+        vp.vph[l] = h->fp.vcar[l] >= 0 ? h->d_vph[l] : nullptr;
+        vp.vhist_old[l] = h->d_vhist[cur][l]; vp.vhist_new[l] = h->d_vhist[nxt][l];
+    }
+    vp.leg_muted[0] = audio_mute ? 1 : 0;                       // mute_xx(audio_mute) sits in front of the gated leg only
+    vp.leg_muted[1] = 0;
+    vp.a_base = h->audio_total;
+    vp.n_audio = n_audio;
+    CKL(launch_voice_prep(vp, st));
+    for (int l = 0; l < kFwdVoiceLegs; ++l) { h->fp.vph[l] = h->d_vph[l]; h->fp.vhist[l] = h->d_vhist[cur][l]; }
+    h->fp.n_audio = n_audio;
+    int rc = fwd_submit_symbols(h, d_sym, nsym, d_out_iq, st, true);
+    if (rc != AMPS_OK) return rc;
+    h->vhist_cur = nxt;
+    h->audio_total += n_audio;
+    return AMPS_OK;
+}
+
+extern "C" int amps_fwd_work_voice(amps_fwd *h, const uint8_t *const *sym, const float *audio, size_t nsym, int audio_mute,
+                                   float *out_iq_host) {
+    if (!h || !sym || (nsym && (!out_iq_host || !audio))) return set_error(AMPS_E_INVAL, "null argument");
+    if (!h->voice) return set_error(AMPS_E_STATE, "amps_fwd_enable_voice() was not called");
+    if (nsym == 0) return AMPS_OK;
+    if (nsym % 25) return set_error(AMPS_E_ALIGN, "nsym must be a multiple of 25 (whole 16 kS/s audio samples)");
+    if (nsym > h->max_sym) return set_error(AMPS_E_OVERFLOW, "nsym exceeds max_samples / 100");
+    CK(cudaSetDevice(h->device));
+    const void *dptr[kFwdMaxCar] = {};
+    for (int c = 0; c < h->ncar; ++c) {
+        if (!sym[c]) return set_error(AMPS_E_INVAL, "null symbol stream");
+        CK(cudaMemcpyAsync(h->d_sym[c], sym[c], nsym, cudaMemcpyHostToDevice, h->stream));
+        dptr[c] = h->d_sym[c];
+    }
+    CK(cudaMemcpyAsync(h->d_audio, audio, sizeof(float) * (nsym * 4 / 25), cudaMemcpyHostToDevice, h->stream));
+    int rc = amps_fwd_submit_voice_dev(h, dptr, h->d_audio, nsym, audio_mute, h->d_out, h->stream);
+    if (rc != AMPS_OK) return rc;
+    CK(cudaMemcpyAsync(out_iq_host, h->d_out, sizeof(float2) * nsym * kFwdInterp, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return AMPS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Manchester-bit fast path: one byte per 10 kbit/s data bit (0, 1, 0xFF = muted), 1000 output samples per bit
 // ---------------------------------------------------------------------------------------------
 extern "C" int amps_fwd_submit_bits_dev(amps_fwd *h, const void *const *d_bits, size_t nbits, void *d_out_iq, void *cuda_stream) {
@@ -250,6 +380,7 @@ extern "C" int amps_fwd_submit_bits_dev(amps_fwd *h, const void *const *d_bits, 
     if (reinterpret_cast<uintptr_t>(d_out_iq) & 15u) return set_error(AMPS_E_ALIGN, "d_out_iq must be 16-byte aligned");
     for (int c = 0; c < h->ncar; ++c) if (!d_bits[c]) return set_error(AMPS_E_INVAL, "null bit stream");
     if (h->mode == 1) return set_error(AMPS_E_STATE, "handle is streaming half-symbols; reset() before switching to data-bit input");
+    if (h->voice) return set_error(AMPS_E_STATE, "voice legs need the half-symbol input (amps_fwd_work_voice)");
     h->mode = 2;
     CK(cudaSetDevice(h->device));
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);

@@ -93,4 +93,39 @@ std::vector<float> mmse_interp_table() {
     return table;
 }
 
+void fm_preemph_taps(double fs, double tau, double fh, double b[2], double a[2]) {
+    if (fh <= 0.0 || fh >= 0.5 * fs) fh = 0.925 * 0.5 * fs;
+    // corner frequencies 1/tau and 2 pi fh, pre-warped, through the bilinear transform
+    const double kl = -std::tan(1.0 / (2.0 * tau * fs)), kh = -std::tan(kPi * fh / fs);
+    const double zero = (1.0 + kl) / (1.0 - kl), pole = (1.0 + kh) / (1.0 - kh), b0 = (1.0 - kl) / (1.0 - kh);
+    const double gain = std::fabs(1.0 - pole) / (b0 * std::fabs(1.0 - zero));       // 0 dB at DC
+    b[0] = gain * b0; b[1] = -gain * b0 * zero;
+    a[0] = 1.0; a[1] = -pole;
+}
+
+std::vector<double> fm_preemph_impulse(double fs, double tau, double fh, int n) {
+    double b[2], a[2];
+    fm_preemph_taps(fs, tau, fh, b, a);
+    std::vector<double> g((size_t)n, 0.0);
+    double y = 0.0;
+    for (int k = 0; k < n; k++) {
+        y = (k == 0 ? b[0] : (k == 1 ? b[1] : 0.0)) - a[1] * y;
+        g[(size_t)k] = y;
+    }
+    return g;
+}
+
+std::vector<float> arb25_taps(const std::vector<float> &taps, int &per) {
+    const int n = (int)taps.size();
+    per = (n + 7) / 8;
+    std::vector<float> E((size_t)25 * per);
+    auto h = [&](int i) { return i < n ? (double)taps[(size_t)i] : 0.0; };
+    for (int r = 0; r < 25; r++) {
+        const int arm = 8 * r / 25;
+        const double frac = (8 * r % 25) / 25.0;                  // position between arm and arm + 1
+        for (int k = 0; k < per; k++) E[(size_t)r * per + k] = (float)(h(arm + 8 * k) + frac * (h(arm + 8 * k + 1) - h(arm + 8 * k)));
+    }
+    return E;
+}
+
 }  // namespace amps

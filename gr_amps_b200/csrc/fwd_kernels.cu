@@ -135,6 +135,7 @@ struct FwdSmem {
 };
 
 size_t fwd_smem_bytes() { return sizeof(FwdSmem); }
+static size_t fwd_voice_smem_bytes();
 
 __device__ __forceinline__ void tma_store_1d(void *gdst, const void *smem_src, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
@@ -144,10 +145,26 @@ __device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+__device__ __forceinline__ long floor_div(long a, long b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
+
+// voice legs (kVoice): the phasors a tile needs, the x25 resampler taps and the legs' rotated 400 kS/s samples
+constexpr int kVoiceStage = 48;                // audio samples staged per tile: 11 new + kFwdVoicePer - 1 of history, rounded up
+struct FwdVoiceSmem {
+    float  E[25 * kFwdVoicePer];
+    float2 vph[kFwdVoiceLegs][kVoiceStage];
+    float2 va[kFwdVoiceLegs][4 * (kFwdTileSym + 1) + 16];     // same indexing as FwdSmem::a
+};
+
+static size_t fwd_voice_smem_bytes() { return ((sizeof(FwdSmem) + 15) & ~(size_t)15) + sizeof(FwdVoiceSmem); }
+
+template <bool kVoice>
 __global__ void __launch_bounds__(kFwdThreads, 3) fwd_fused_kernel(const __grid_constant__ FwdParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     FwdSmem *sm = reinterpret_cast<FwdSmem *>(smem_raw);
+    FwdVoiceSmem *sv = reinterpret_cast<FwdVoiceSmem *>(smem_raw + ((sizeof(FwdSmem) + 15) & ~(size_t)15));
     const int t = threadIdx.x;
+    if (kVoice)
+        for (int i = t; i < 25 * kFwdVoicePer; i += kFwdThreads) sv->E[i] = p.E[i];
     const uint32_t ntiles = (p.nsym + kFwdTileSym - 1) / kFwdTileSym;
     constexpr int kFmLen = kFwdTileSym + 1 + kFwdMaxTap4;          // 145
     for (int i = t; i < kFwdMaxCar * 4 * kFwdMaxTap4; i += kFwdThreads) (&sm->taps[0][0])[i] = (&p.taps[0][0])[i];
@@ -168,6 +185,20 @@ __global__ void __launch_bounds__(kFwdThreads, 3) fwd_fused_kernel(const __grid_
             float2 v = make_float2(0.f, 0.f);
             if (s != 0) v = sincos_phase((uint32_t)S * p.fcw_fm);
             sm->fm[c][k] = v;
+        }
+        // voice: phasors for audio samples ia0 .. ia0 + 47, ia0 = floor(4 (i0 - 1) / 25) - (kFwdVoicePer - 1)
+        const long ia0 = floor_div(4 * (i0 - 1), 25) - (kFwdVoicePer - 1);
+        if (kVoice) {
+            for (int idx = t; idx < kFwdVoiceLegs * kVoiceStage; idx += kFwdThreads) {
+                const int l = idx / kVoiceStage, k = idx - l * kVoiceStage;
+                const long ia = ia0 + k;
+                float2 v = make_float2(0.f, 0.f);
+                if (p.vcar[l] >= 0) {
+                    if (ia >= 0) { if (ia < (long)p.n_audio) v = p.vph[l][ia]; }
+                    else if (ia >= -(long)kFwdVoiceHist) v = p.vhist[l][kFwdVoiceHist + ia];
+                }
+                sv->vph[l][k] = v;
+            }
         }
         __syncthreads();
 
@@ -207,6 +238,23 @@ __global__ void __launch_bounds__(kFwdThreads, 3) fwd_fused_kernel(const __grid_
             a[5] = cmul(hi1, W); W = cmul(W, w25);
             a[6] = cmul(hi2, W); W = cmul(W, w25);
             a[7] = cmul(hi3, W);
+        } else if (kVoice && t >= 96) {
+            // the warps the symbol carriers leave idle: x25 polyphase resampling of the voice phasors, rotated by the
+            // carrier NCO like the symbol legs.  One output = 400 kS/s sample m = 4 (i0 - 1) + idx of one leg.
+            for (int o = t - 96; o < kFwdVoiceLegs * 4 * (kFwdTileSym + 1); o += kFwdThreads - 96) {
+                const int l = o / (4 * (kFwdTileSym + 1)), idx = o - l * 4 * (kFwdTileSym + 1);
+                const int c = p.vcar[l];
+                if (c < 0) continue;
+                const long m = 4 * (i0 - 1) + idx;
+                const long ia = floor_div(m, 25);
+                const int r = (int)(m - 25 * ia);
+                const float *Er = &sv->E[r * kFwdVoicePer];
+                const float2 *x = &sv->vph[l][ia - ia0];              // x[-k] = phasor of audio sample ia - k
+                float2 acc = make_float2(0.f, 0.f);
+                for (int k = 0; k < p.vper; ++k) acc = fma2(splat(Er[k]), x[-k], acc);
+                const float2 W = sincos_phase((p.m_base + (uint32_t)m) * p.fcw_mix25[c]);
+                sv->va[l][idx] = cmul(acc, W);
+            }
         }
         __syncthreads();
 
@@ -221,7 +269,11 @@ __global__ void __launch_bounds__(kFwdThreads, 3) fwd_fused_kernel(const __grid_
                 if (c < p.ncar) {
 #pragma unroll
                     for (int j = 0; j < 3; ++j) {
-                        const float2 x = sm->a[c][t + 3 - j];
+                        float2 x = sm->a[c][t + 3 - j];
+                        if (kVoice) {                              // add_xx before the mixer: the legs share this carrier's NCO
+                            if (p.vcar[0] == c) x = add2(x, sv->va[0][t + 3 - j]);
+                            if (p.vcar[1] == c) x = add2(x, sv->va[1][t + 3 - j]);
+                        }
                         const float2 xr = splat(x.x), xi = splat(x.y);
 #pragma unroll
                         for (int r = 0; r < 5; ++r) {
@@ -403,12 +455,106 @@ cudaError_t launch_fwd_bits(const FwdBitsParams &p, int grid, cudaStream_t st) {
 cudaError_t fwd_configure_device() {
     cudaError_t e = cudaFuncSetAttribute(fwd_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FwdBitsSmem));
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(fwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FwdSmem));
+    e = cudaFuncSetAttribute(fwd_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FwdSmem));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(fwd_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_voice_smem_bytes());
 }
 
 cudaError_t launch_fwd_fused(const FwdParams &p, int grid, cudaStream_t st) {
     if (p.nsym == 0) return cudaSuccess;
-    fwd_fused_kernel<<<grid, kFwdThreads, sizeof(FwdSmem), st>>>(p);
+    fwd_fused_kernel<false><<<grid, kFwdThreads, sizeof(FwdSmem), st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fwd_fused_voice(const FwdParams &p, int grid, cudaStream_t st) {
+    if (p.nsym == 0) return cudaSuccess;
+    fwd_fused_kernel<true><<<grid, kFwdThreads, fwd_voice_smem_bytes(), st>>>(p);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// voice pre-pass (16 kS/s: 1/625 of the output rate, so these kernels are off the roofline).
+//   x[n] = audio[n] + SAT;  y[n] = sum_k g[k] x[n - k]   (fm_preemph's IIR as its truncated impulse response: no
+//   recurrence, any sample computable on its own, float64);  delta[n] = frac(y[n] max_dev / fs) * 2^64
+//   Phi[n] = Phi[n-1] + delta[n] (mod 2^64, an exact integer scan);  phasor[n] = e^{j 2 pi Phi[n] / 2^64}
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) voice_delta_kernel(const __grid_constant__ VoicePrepParams p) {
+    __shared__ double s_x[256 + kVoiceImp];
+    __shared__ double s_g[kVoiceImp];
+    const int t = threadIdx.x;
+    const long n0 = (long)blockIdx.x * 256;
+    for (int i = t; i < kVoiceImp; i += 256) s_g[i] = p.g[i];
+    for (int i = t; i < 256 + kVoiceImp; i += 256) {
+        const long n = n0 - kVoiceImp + i;
+        double x = 0.0;
+        if (n >= (long)p.n_audio) x = 0.0;
+        else if (n >= 0) x = (double)p.audio[n] + p.sat[(p.a_base + (unsigned long long)n) & 7ull];
+        else x = p.hx_old[kVoiceImp + n];
+        s_x[i] = x;
+    }
+    __syncthreads();
+    const long n = n0 + t;
+    if (n < (long)p.n_audio) {
+        double y = 0.0;
+        for (int k = 0; k < kVoiceImp; ++k) y = fma(s_g[k], s_x[kVoiceImp + t - k], y);
+        double cyc = y * p.cycles_per_unit;
+        cyc -= floor(cyc);
+        p.delta[n] = __double2ull_rn(cyc * 18446744073709551616.0);
+    }
+    // history of inputs for the next call: the last kVoiceImp of (old history ++ this call's inputs)
+    if (blockIdx.x == 0 && t < kVoiceImp) {
+        const long src = (long)p.n_audio - kVoiceImp + t;
+        double x;
+        if (src >= 0) x = (double)p.audio[src] + p.sat[(p.a_base + (unsigned long long)src) & 7ull];
+        else x = p.hx_old[kVoiceImp + src];
+        p.hx_new[t] = x;
+    }
+}
+
+__global__ void __launch_bounds__(1024) voice_scan_kernel(const __grid_constant__ VoicePrepParams p) {
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_carry;
+    const int t = threadIdx.x;
+    if (t == 0) s_carry = *p.phase;
+    __syncthreads();
+    const uint32_t per = (p.n_audio + 1023u) / 1024u;                // contiguous run per thread
+    const uint32_t lo = (uint32_t)t * per, hi = lo + per < p.n_audio ? lo + per : p.n_audio;
+    unsigned long long run = 0;
+    for (uint32_t n = lo; n < hi; ++n) run += p.delta[n];
+    unsigned long long incl = run;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long o = __shfl_up_sync(0xffffffffu, incl, d);
+        if ((t & 31) >= d) incl += o;
+    }
+    if ((t & 31) == 31) s_warp[t >> 5] = incl;
+    __syncthreads();
+    unsigned long long woff = 0;
+    for (int w = 0; w < (t >> 5); ++w) woff += s_warp[w];
+    unsigned long long phi = s_carry + woff + incl - run;           // phase before this thread's first sample
+    for (uint32_t n = lo; n < hi; ++n) {
+        phi += p.delta[n];
+        const float2 v = sincos_phase((uint32_t)(phi >> 32));
+#pragma unroll
+        for (int l = 0; l < kFwdVoiceLegs; ++l)
+            if (p.vph[l]) p.vph[l][n] = p.leg_muted[l] ? make_float2(0.f, 0.f) : v;
+    }
+    __syncthreads();
+    if (t == 1023) *p.phase = s_carry + woff + incl;
+    __syncthreads();
+    // phasor history for the next call
+    if (t < kFwdVoiceHist) {
+        const long src = (long)p.n_audio - kFwdVoiceHist + t;
+#pragma unroll
+        for (int l = 0; l < kFwdVoiceLegs; ++l)
+            if (p.vph[l]) p.vhist_new[l][t] = src >= 0 ? p.vph[l][src] : p.vhist_old[l][kFwdVoiceHist + src];
+    }
+}
+
+cudaError_t launch_voice_prep(const VoicePrepParams &p, cudaStream_t st) {
+    if (p.n_audio == 0) return cudaSuccess;
+    voice_delta_kernel<<<(p.n_audio + 255u) / 256u, 256, 0, st>>>(p);
+    voice_scan_kernel<<<1, 1024, 0, st>>>(p);
     return cudaGetLastError();
 }
 

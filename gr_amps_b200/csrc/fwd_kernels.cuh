@@ -11,6 +11,9 @@ constexpr int kFwdHistLen  = kFwdMaxTap4 + 1;    // symbols of history a call ne
 constexpr int kFwdThreads  = 256;
 constexpr int kFwdScanBlock = 4096;              // symbols per block of the prefix-sum kernels
 constexpr int kFwdInterp   = 100;                // 10 MS/s / 100 kS/s = 4 (reference) x 25 (CIC)
+constexpr int kFwdVoiceLegs = 2;                 // voice legs: one gated by audio_mute (+60 kHz), one always on (+90 kHz)
+constexpr int kFwdVoicePer  = 32;                // max taps per arm of the x25 voice resampler (225 taps / 8 arms -> 29)
+constexpr int kFwdVoiceHist = 32;                // phasors of history a call needs from the previous one
 
 struct FwdScanParams {
     const uint8_t *sym[kFwdMaxCar];
@@ -43,7 +46,36 @@ struct FwdParams {
     float2         C1[kFwdMaxCar][15];           // 5 cic5[u] e^{j phi_c(5 u)}: first x5 CIC^3 stage carrying the mixer
     float          G2[15];                       // out_scale * 5 cic5[u]: second (shared) x5 CIC^3 stage
     float          taps[kFwdMaxCar][4 * kFwdMaxTap4];
+    // ---- voice legs (fwd_fused_kernel<true> only): nbfm_tx phasors @16 kS/s, x25 arb resampler, added to a carrier's
+    //      400 kS/s samples before its mixer (grc/ampsbs.grc:4494-4500, 4632-4638)
+    const float2  *vph[kFwdVoiceLegs];           // this call's phasors (4 nsym / 25 of them), already muted where gated
+    const float2  *vhist[kFwdVoiceLegs];         // previous call's last kFwdVoiceHist phasors
+    int            vcar[kFwdVoiceLegs];          // carrier whose mixer the leg shares, -1 = leg unused
+    int            vper;                         // taps per arm of the x25 resampler (<= kFwdVoicePer)
+    uint32_t       n_audio;                      // audio samples of this call
+    float          E[25 * kFwdVoicePer];         // E[r * kFwdVoicePer + k]
 };
+
+// ---- voice pre-pass: audio (+SAT) -> pre-emphasis -> FM phase -> phasors @16 kS/s
+constexpr int kVoiceImp = 192;                   // terms of the pre-emphasis impulse response kept (|pole|^192 ~ 1e-20)
+struct VoicePrepParams {
+    const float *audio;                          // this call's samples
+    const double *hx_old;                        // previous call's last kVoiceImp inputs (audio + SAT), zeros at stream start
+    double      *hx_new;
+    unsigned long long *delta;                   // per-sample FM phase step, 2^64 = one turn
+    unsigned long long *phase;                   // running FM phase (device scalar, carried between calls)
+    float2      *vph[kFwdVoiceLegs];
+    const float2 *vhist_old[kFwdVoiceLegs];
+    float2      *vhist_new[kFwdVoiceLegs];
+    int          leg_muted[kFwdVoiceLegs];       // 1 = this call's phasors of the leg are zeros (mute_xx before the resampler)
+    unsigned long long a_base;                   // absolute index of audio[0] (selects the SAT phase)
+    uint32_t     n_audio;
+    double       cycles_per_unit;                // max_dev / audio_rate
+    double       g[kVoiceImp];
+    double       sat[8];                         // sat_amp * cos(2 pi 3 k / 8): 6 kHz at 16 kS/s
+};
+cudaError_t launch_voice_prep(const VoicePrepParams &p, cudaStream_t st);
+cudaError_t launch_fwd_fused_voice(const FwdParams &p, int grid, cudaStream_t st);
 
 // ---- Manchester-bit fast path: input is one byte per 10 kbit/s data bit (0, 1, 0xFF = muted) instead of half-symbol samples
 constexpr int kFbTileBits  = 5;                  // bits per tile -> 200 samples @400 kS/s -> 5000 output samples

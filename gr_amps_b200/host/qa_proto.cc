@@ -55,7 +55,19 @@ int main() {
     taps("focc_interp", firdes_low_pass(1.0, 400e3, 10e3, 5e3, WIN_HAMMING));
     taps("fvc_interp", firdes_low_pass(1.0, 400e3, 10e3, 3e3, WIN_HAMMING));
     taps("cic25", cic);
-    taps("mmse", mmse_interp_table(), true);
+    taps("mmse", mmse_interp_table());
+    {
+        int per = 0;
+        taps("voice_arb25", arb25_taps(firdes_low_pass(3.0, 400e3, 15e3, 6e3, WIN_BLACKMAN), per));
+        double b[2], a[2];
+        fm_preemph_taps(16000.0, 75e-6, -1.0, b, a);
+        std::printf("  \"preemph\": [%.17g, %.17g, %.17g, %.17g],\n", b[0], b[1], a[0], a[1]);
+        const std::vector<double> g = fm_preemph_impulse(16000.0, 75e-6, -1.0, 192);
+        std::printf("  \"preemph_impulse\": [");
+        for (size_t i = 0; i < g.size(); i++) std::printf("%s%.17g", i ? ", " : "", g[i]);
+        std::printf("],\n");
+    }
+    taps("voice_lpf", firdes_low_pass(3.0, 400e3, 15e3, 6e3, WIN_BLACKMAN), true);
     std::printf(" }\n}\n");
     return 0;
 }

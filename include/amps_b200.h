@@ -258,6 +258,27 @@ AMPS_B200_API int amps_fwd_submit_dev(amps_fwd *h, const void *const *d_sym, siz
  * faster.  A handle streams either half-symbols or bits; reset() to switch. */
 AMPS_B200_API int amps_fwd_work_bits(amps_fwd *h, const uint8_t *const *bits, size_t nbits, float *out_iq_host);
 AMPS_B200_API int amps_fwd_submit_bits_dev(amps_fwd *h, const void *const *d_bits, size_t nbits, void *d_out_iq, void *cuda_stream);
+/* Voice legs: wavfile/audio @16 kS/s + 6 kHz SAT -> analog.nbfm_tx(16000, 16000, tau 75 us, max_dev 8 kHz)
+ * -> [mute_xx audio_mute] -> pfb.arb_resampler_ccf(25, voice_lpf_taps = firdes.low_pass(3, 400e3, 15e3, 6e3, BLACKMAN), 8 arms)
+ * added to a carrier's 400 kS/s samples in front of its mixer (grc/ampsbs.grc:715-773, 943-1005, 1994-2119, 4494-4500,
+ * 4632-4638).  In the reference graph the gated leg shares the +60 kHz mixer with the FVC data and the open leg feeds the
+ * +90 kHz mixer alone (give that carrier an all-zero symbol stream). */
+typedef struct amps_fwd_voice_params {
+    int    carrier_gated;        /* carrier index of the leg behind mute_xx(audio_mute) (1 in the reference graph), -1 = none */
+    int    carrier_open;         /* carrier index of the leg that is always on (2 in the reference graph), -1 = none */
+    double audio_rate;           /* 16000 (x25 to the reference's 400 kS/s) */
+    double max_dev;              /* 8e3 */
+    double tau;                  /* 75e-6 */
+    double sat_freq;             /* 6000 */
+    double sat_amp;              /* 0.05; 0 = no supervisory tone */
+} amps_fwd_voice_params;
+AMPS_B200_API int amps_fwd_enable_voice(amps_fwd *h, const amps_fwd_voice_params *vp);
+/* half-symbol streams as amps_fwd_work plus 4 nsym / 25 audio samples (float, 16 kS/s); nsym must be a multiple of 25.
+ * audio_mute != 0 mutes the gated leg for this call's audio samples. */
+AMPS_B200_API int amps_fwd_work_voice(amps_fwd *h, const uint8_t *const *sym, const float *audio, size_t nsym, int audio_mute,
+                                      float *out_iq_host);
+AMPS_B200_API int amps_fwd_submit_voice_dev(amps_fwd *h, const void *const *d_sym, const void *d_audio, size_t nsym,
+                                            int audio_mute, void *d_out_iq, void *cuda_stream);
 AMPS_B200_API int amps_fwd_interp(const amps_fwd *h);
 AMPS_B200_API int amps_fwd_get_taps(const amps_fwd *h, int carrier, float *out, int cap);
 

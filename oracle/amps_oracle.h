@@ -170,6 +170,14 @@ size_t orc_mm_process(orc_mm_state *st, const float *d, uint64_t total, const fl
 void orc_fwd_chain_f64(const int8_t *const *sym, int ncarriers, size_t nsym, uint32_t fcw_fm,
                        const float *const *taps, const int *ntaps, const uint32_t *fcw_mix, double scale,
                        double *out /* nsym*100 complex */);
+void orc_fwd_chain_voice_f64(const int8_t *const *sym, int ncarriers, size_t nsym, uint32_t fcw_fm,
+                             const float *const *taps, const int *ntaps, const uint32_t *fcw_mix, double scale,
+                             const double *const *extra400, double *out);
+/* ---------------------------------------------------------------- voice leg of the forward graph (voice_tx.c) */
+void orc_fm_preemph_taps(double fs, double tau, double fh, double b[2], double a[2]);
+int  orc_arb25_taps(const float *taps, int ntaps, double *E);
+void orc_voice_tx_f64(const float *audio, size_t n_a, double sat_amp, const uint8_t *mute, const float *taps, int ntaps,
+                      double *out /* 25 * n_a complex */);
 
 #ifdef __cplusplus
 }

@@ -353,9 +353,9 @@ int orc_rx_detect(const float *d, size_t nd, orc_burst *out, int max) {
  * A symbol byte of 0 mutes that symbol (the reference's mute_xx, :1508-1601, gates the interpolator output;
  * gating its input differs only in the 0.8 ms filter transient).
  */
-void orc_fwd_chain_f64(const int8_t *const *sym, int ncarriers, size_t nsym, uint32_t fcw_fm,
-                       const float *const *taps, const int *ntaps, const uint32_t *fcw_mix, double scale,
-                       double *out /* nsym*100 complex */) {
+static void fwd_chain_core(const int8_t *const *sym, int ncarriers, size_t nsym, uint32_t fcw_fm,
+                           const float *const *taps, const int *ntaps, const uint32_t *fcw_mix, double scale,
+                           const double *const *extra400, double *out /* nsym*100 complex */) {
     const size_t nm = nsym * 4, nq = nsym * 20, nout = nsym * 100;
     double g5[15];
     {   /* 5 * (boxcar5 * boxcar5 * boxcar5) / 125, 13 taps */
@@ -386,6 +386,8 @@ void orc_fwd_chain_f64(const int8_t *const *sym, int ncarriers, size_t nsym, uin
                 }
                 ar[4 * i + j] = sr; ai[4 * i + j] = si;
             }
+        if (extra400 && extra400[c])                       /* voice leg sharing this carrier's mixer (add_xx before multiply_xx) */
+            for (size_t m = 0; m < nm; m++) { ar[m] += extra400[c][2 * m]; ai[m] += extra400[c][2 * m + 1]; }
         for (size_t m = 0; m < nm; m++)
             for (int r = 0; r < 5; r++) {
                 double br = 0, bi = 0;
@@ -413,4 +415,18 @@ void orc_fwd_chain_f64(const int8_t *const *sym, int ncarriers, size_t nsym, uin
         }
     (void)nout;
     free(fr); free(fi); free(ar); free(ai); free(Br); free(Bi);
+}
+
+void orc_fwd_chain_f64(const int8_t *const *sym, int ncarriers, size_t nsym, uint32_t fcw_fm,
+                       const float *const *taps, const int *ntaps, const uint32_t *fcw_mix, double scale,
+                       double *out /* nsym*100 complex */) {
+    fwd_chain_core(sym, ncarriers, nsym, fcw_fm, taps, ntaps, fcw_mix, scale, NULL, out);
+}
+
+/* the same with a complex 400 kS/s baseband (4 nsym samples, e.g. orc_voice_tx_f64's output) added to carrier c's
+ * interpolator output before its mixer; extra400[c] may be NULL */
+void orc_fwd_chain_voice_f64(const int8_t *const *sym, int ncarriers, size_t nsym, uint32_t fcw_fm,
+                             const float *const *taps, const int *ntaps, const uint32_t *fcw_mix, double scale,
+                             const double *const *extra400, double *out) {
+    fwd_chain_core(sym, ncarriers, nsym, fcw_fm, taps, ntaps, fcw_mix, scale, extra400, out);
 }

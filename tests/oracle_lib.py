@@ -310,6 +310,46 @@ def fwd_chain_f64(syms, carrier_freq=(0.0, 60e3, 90e3), lpf_transition=(5e3, 3e3
     return out.view(np.complex128)
 
 
+def voice_lpf_taps() -> np.ndarray:
+    """variable_low_pass_filter_taps voice_lpf_taps: firdes.low_pass(3, 400e3, 15e3, 6e3, BLACKMAN)."""
+    return firdes_low_pass(3.0, 400e3, 15e3, 6e3, 2)
+
+
+def voice_tx_f64(audio, mute=None, sat_amp=0.05) -> np.ndarray:
+    """float64 voice leg (oracle/voice_tx.c): audio @16 kS/s -> complex baseband @400 kS/s (25 per audio sample)."""
+    a = np.ascontiguousarray(audio, dtype=np.float32)
+    taps = voice_lpf_taps()
+    out = np.zeros(2 * 25 * len(a), np.float64)
+    m = None if mute is None else np.ascontiguousarray(mute, dtype=np.uint8)
+    L = lib()
+    L.orc_voice_tx_f64.argtypes = [f32p, C.c_size_t, C.c_double, C.c_void_p, f32p, C.c_int, f64p]
+    L.orc_voice_tx_f64.restype = None
+    L.orc_voice_tx_f64(ptr(a, f32p), len(a), sat_amp, None if m is None else m.ctypes.data, ptr(taps, f32p), len(taps), ptr(out, f64p))
+    return out.view(np.complex128)
+
+
+def fwd_chain_voice_f64(syms, extra400, carrier_freq=(0.0, 60e3, 90e3), lpf_transition=(5e3, 3e3, 3e3), scale=0.5,
+                        max_deviation=8000.0, symrate=100e3, fs=10e6) -> np.ndarray:
+    """fwd_chain_f64 with extra400[c] (complex128 @400 kS/s or None) added to carrier c in front of its mixer."""
+    n = len(syms)
+    arrs = [np.ascontiguousarray(s, dtype=np.uint8) for s in syms]
+    nsym = len(arrs[0])
+    taps = [firdes_low_pass(1.0, 400e3, 10e3, lpf_transition[c], 0) for c in range(n)]
+    symp = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+    tapp = (C.c_void_p * n)(*[t.ctypes.data for t in taps])
+    nt = (C.c_int * n)(*[len(t) for t in taps])
+    fcw = (C.c_uint32 * n)(*[lib().orc_nco_fcw(-carrier_freq[c], fs) for c in range(n)])
+    fcw_fm = int(round(max_deviation / symrate * 4294967296.0)) & 0xffffffff
+    ex = [None if e is None else np.ascontiguousarray(e, dtype=np.complex128) for e in extra400]
+    exp = (C.c_void_p * n)(*[None if e is None else e.ctypes.data for e in ex])
+    out = np.zeros(2 * nsym * 100, np.float64)
+    L = lib()
+    L.orc_fwd_chain_voice_f64.argtypes = L.orc_fwd_chain_f64.argtypes[:8] + [C.POINTER(C.c_void_p), f64p]
+    L.orc_fwd_chain_voice_f64.restype = None
+    L.orc_fwd_chain_voice_f64(symp, n, nsym, fcw_fm, tapp, nt, fcw, scale, exp, ptr(out, f64p))
+    return out.view(np.complex128)
+
+
 def recc_decode(blob) -> ReccResult:
     b = as_u8(blob)
     assert len(b) == 3374

@@ -55,6 +55,22 @@ def test_filter_designs_match_oracle(proto, oracle):
     assert np.array_equal(np.float32(t["focc_interp"]), oracle.firdes_low_pass(1.0, 400e3, 10e3, 5e3, 0)) and len(t["focc_interp"]) == 193
     assert np.array_equal(np.float32(t["fvc_interp"]), oracle.firdes_low_pass(1.0, 400e3, 10e3, 3e3, 0)) and len(t["fvc_interp"]) == 321
     assert np.array_equal(np.float32(t["mmse"]).reshape(129, 8), oracle.mmse_table())
+    # voice leg designs: pre-emphasis IIR, its impulse response, and the x25 form of the arb resampler
+    L.orc_fm_preemph_taps.argtypes = [C.c_double] * 3 + [C.POINTER(C.c_double)] * 2
+    b, a = (C.c_double * 2)(), (C.c_double * 2)()
+    L.orc_fm_preemph_taps(16000.0, 75e-6, -1.0, b, a)
+    assert np.allclose(t["preemph"], [b[0], b[1], a[0], a[1]], rtol=1e-14, atol=0)
+    imp = np.zeros(192); y = 0.0
+    for k in range(192):
+        y = (b[0] if k == 0 else b[1] if k == 1 else 0.0) - a[1] * y
+        imp[k] = y
+    assert np.allclose(t["preemph_impulse"], imp, rtol=1e-13, atol=1e-30) and abs(imp[-1]) < 1e-18
+    vt = oracle.voice_lpf_taps()
+    assert len(vt) == 225 and np.array_equal(np.float32(t["voice_lpf"]), vt)
+    E = np.zeros(25 * 29)
+    L.orc_arb25_taps.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    assert L.orc_arb25_taps(vt.ctypes.data, 225, E.ctypes.data) == 29
+    assert np.array_equal(np.float32(t["voice_arb25"]), E.astype(np.float32))
     c = np.float32(t["cic25"])
     assert len(c) == 73 and abs(float(c.astype(np.float64).sum()) - 1.0) < 1e-6 and np.array_equal(c, c[::-1])
     assert c[0] == np.float32(1 / 15625) and c[36] == np.float32(469 / 15625)

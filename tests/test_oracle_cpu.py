@@ -341,3 +341,45 @@ def test_mmse_table_and_mm_loop_properties(oracle):
     assert np.array_equal(np.concatenate(parts), s1)
     assert (st.st.mu, st.st.omega, st.st.pos) == (one.st.mu, one.st.omega, one.st.pos)
     assert 9.95 <= one.st.omega <= 10.05
+
+
+def test_voice_leg_oracle_properties(oracle):
+    """oracle/voice_tx.c: pre-emphasis normalisation, the closed-form x25 resampler against a literal walk of the
+    arb-resampler loop (filter index / fractional accumulator, exact rationals), FM constant envelope before the filter."""
+    import ctypes as C
+    from fractions import Fraction
+    L = oracle.lib()
+    L.orc_fm_preemph_taps.argtypes = [C.c_double] * 3 + [C.POINTER(C.c_double)] * 2
+    b, a = (C.c_double * 2)(), (C.c_double * 2)()
+    L.orc_fm_preemph_taps(16000.0, 75e-6, -1.0, b, a)
+    assert abs((b[0] + b[1]) / (1 + a[1]) - 1.0) < 1e-12                 # 0 dB at DC
+    assert (b[0] - b[1]) / (1 - a[1]) > 10                                # +20 dB-class boost at fs/2
+    w = 2 * np.pi * 75e-6 * 2122.0                                       # the analog corner 1/(2 pi tau) = 2122 Hz: +3 dB
+    z = np.exp(-1j * 2 * np.pi * 2122.0 / 16000.0)
+    assert abs(abs((b[0] + b[1] * z) / (1 + a[1] * z)) - np.sqrt(2)) < 0.05 and w > 0.99
+    taps = oracle.voice_lpf_taps()
+    E = np.zeros(25 * 29)
+    L.orc_arb25_taps.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.orc_arb25_taps(taps.ctypes.data, 225, E.ctypes.data)
+    E = E.reshape(25, 29)
+    # literal loop of pfb_arb_resampler: int_rate 8, dec_rate 0, flt_rate 8/25; j, acc advance per output
+    h = np.concatenate([taps.astype(np.float64), np.zeros(8)])
+    j, acc, i_in, rows = 0, Fraction(0), 0, []
+    for n in range(50):
+        rows.append((i_in, j, acc))
+        acc += Fraction(8, 25)
+        j += int(acc)                                                     # floor
+        acc -= int(acc)
+        i_in += j // 8
+        j %= 8
+    for n, (i_in, j, acc) in enumerate(rows):
+        assert i_in == n // 25
+        want = np.array([h[j + 8 * k] + float(acc) * (h[j + 1 + 8 * k] - h[j + 8 * k]) for k in range(29)])
+        assert np.allclose(E[n % 25], want, rtol=0, atol=1e-15)
+    # DC: a constant phasor comes out at gain sum(taps)/8 = 3/8 on every phase
+    v = oracle.voice_tx_f64(np.zeros(200, np.float32), sat_amp=0.0)
+    assert np.allclose(v[25 * 40:], 0.375, atol=2e-6)
+    # muting zeroes the resampler input; the output decays within the 29-sample filter
+    m = np.zeros(200, np.uint8); m[100:] = 1
+    vm = oracle.voice_tx_f64(np.zeros(200, np.float32), mute=m, sat_amp=0.0)
+    assert np.allclose(vm[25 * 40:25 * 100], 0.375, atol=2e-6) and np.all(vm[25 * 130:] == 0)
