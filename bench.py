@@ -149,11 +149,13 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def measure_fwd(local_rank, steps, warmup, bits=False):
+def measure_fwd(local_rank, steps, warmup, bits=False, voice=False):
     """BASELINE config 3 on this rank's GPU: FOCC @0 Hz + FVC @+60 kHz + FVC @+90 kHz, x0.5 -> 10 MS/s complex,
     device resident.  Algorithmic bytes: 8 B written per output sample (+ 3 symbol bytes per 100 samples read).
     bits=False: half-symbol input (amps_fwd_submit_dev); bits=True: data-bit input, the Manchester fast path
-    (amps_fwd_submit_bits_dev).  Returns (samples per step, ms per step)."""
+    (amps_fwd_submit_bits_dev); voice=True: half-symbol input plus the two voice legs of the reference graph (audio @16 kS/s
+    -> nbfm_tx -> x25 resampler on the +60 / +90 kHz carriers, the +90 kHz symbol stream all zero).
+    Returns (samples per step, ms per step)."""
     import torch
     from gr_amps_b200 import capi
     dev = torch.device("cuda", local_rank)
@@ -176,7 +178,15 @@ def measure_fwd(local_rank, steps, warmup, bits=False):
     out = torch.empty(2 * nsym * 100, dtype=torch.float32, device=dev)
     fw = capi.Fwd(max_samples=nsym * 100, device=local_rank)
     stream = torch.cuda.current_stream()
-    if bits:
+    if voice:
+        nsym -= nsym % 25
+        fw.enable_voice()
+        syms[2].zero_()
+        tt = torch.arange(nsym * 4 // 25, device=dev, dtype=torch.float32) / 16000.0
+        audio = (0.2 * torch.sin(6.2831853 * 440.0 * tt) + 0.1 * torch.sin(6.2831853 * 1330.0 * tt)).contiguous()
+        ptrs = [s.data_ptr() for s in syms]
+        submit = lambda: fw.submit_voice_dev(ptrs, audio.data_ptr(), nsym, out.data_ptr(), False, stream.cuda_stream)
+    elif bits:
         # one byte per data bit: the second half-symbol of a bit is high for a 1 (lib/amps_packet.h:52-70)
         syms = [(s.view(-1, 10)[:, 5] == 1).to(torch.uint8).contiguous() for s in syms]
         nunits = nsym // 10
@@ -211,6 +221,7 @@ def run_fwd(args, rank, local_rank, world):
     sampler.start()
     n, ms = measure_fwd(local_rank, args.steps, args.warmup, bits=True)
     _, ms_general = measure_fwd(local_rank, args.steps, args.warmup, bits=False)
+    nv, ms_voice = measure_fwd(local_rank, args.steps, args.warmup, voice=True)
     clocks = sampler.stop()
     peak, peak_src = load_peaks()
     achieved = (8.0 * n + 0.03 * n) / (ms * 1e-3) / 1e9
@@ -223,6 +234,8 @@ def run_fwd(args, rank, local_rank, world):
                      "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": None},
         "general_path": {"kernel": "fwd_fused_kernel (+2 scan kernels), half-symbol input", "ms_per_step": ms_general,
                          "value": n / (ms_general * 1e-3) / 1e6, "frac": 8.03 * n / (ms_general * 1e-3) / 1e9 / peak},
+        "voice_path": {"kernel": "fwd_fused_kernel<voice> (+2 scan, +2 voice pre-pass kernels), half-symbols + 16 kS/s audio",
+                       "ms_per_step": ms_voice, "value": nv / (ms_voice * 1e-3) / 1e6, "frac": 8.03 * nv / (ms_voice * 1e-3) / 1e9 / peak},
         "clocks": clocks}), flush=True)
     return 0
 

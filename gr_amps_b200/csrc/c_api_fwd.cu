@@ -36,8 +36,9 @@ struct amps_fwd {
     bool voice = false;
     VoicePrepParams vp{};
     float *d_audio = nullptr;                 // host-path staging
+    float *d_E = nullptr;                     // x25 resampler taps
     double *d_hx[2] = {};
-    unsigned long long *d_delta = nullptr, *d_phase = nullptr;
+    unsigned long long *d_delta = nullptr, *d_phase = nullptr, *d_vbtot = nullptr, *d_vboff = nullptr;
     float2 *d_vph[kFwdVoiceLegs] = {};
     float2 *d_vhist[2][kFwdVoiceLegs] = {};
     int vhist_cur = 0;
@@ -188,7 +189,7 @@ extern "C" int amps_fwd_destroy(amps_fwd *h) {
     }
     for (int c = 0; c < kFwdMaxCar; ++c) { cudaFree(h->d_bits[c]); cudaFree(h->d_hbits[0][c]); cudaFree(h->d_hbits[1][c]); }
     cudaFree(h->d_carry); cudaFree(h->d_out); cudaFree(h->d_resp);
-    cudaFree(h->d_audio); cudaFree(h->d_delta); cudaFree(h->d_phase);
+    cudaFree(h->d_audio); cudaFree(h->d_E); cudaFree(h->d_delta); cudaFree(h->d_phase); cudaFree(h->d_vbtot); cudaFree(h->d_vboff);
     for (int b = 0; b < 2; ++b) { cudaFree(h->d_hx[b]); for (int l = 0; l < kFwdVoiceLegs; ++l) cudaFree(h->d_vhist[b][l]); }
     for (int l = 0; l < kFwdVoiceLegs; ++l) cudaFree(h->d_vph[l]);
     delete h;
@@ -246,7 +247,7 @@ static int fwd_submit_symbols(amps_fwd *h, const void *const *d_sym, size_t nsym
     p.nsym = (uint32_t)nsym;
     p.m_base = (uint32_t)(h->sym_total * 4u);
     const uint32_t ntiles = ((uint32_t)nsym + kFwdTileSym - 1) / kFwdTileSym;
-    uint32_t grid = (with_voice ? 2u : 3u) * (uint32_t)h->sm_count;   // 74 KB smem (83 KB with the voice legs), 60 registers
+    uint32_t grid = 3u * (uint32_t)h->sm_count;                  // 74 KB smem, 72 registers: 3 CTAs per SM
     if (grid > ntiles) grid = ntiles;
     if (with_voice) CKL(launch_fwd_fused_voice(p, (int)grid, st));
     else CKL(launch_fwd_fused(p, (int)grid, st));
@@ -298,14 +299,21 @@ extern "C" int amps_fwd_enable_voice(amps_fwd *h, const amps_fwd_voice_params *v
     const std::vector<float> E = arb25_taps(firdes_low_pass(3.0, 400e3, 15e3, 6e3, WIN_BLACKMAN), per);
     if (per > kFwdVoicePer) return set_error(AMPS_E_INVAL, "voice resampler has too many taps per arm");
     h->fp.vper = per;
+    std::vector<float> Epad((size_t)25 * kFwdVoicePer, 0.0f);
     for (int r = 0; r < 25; ++r)
-        for (int k = 0; k < per; ++k) h->fp.E[r * kFwdVoicePer + k] = E[(size_t)r * per + k];
+        for (int k = 0; k < per; ++k) Epad[(size_t)r * kFwdVoicePer + k] = E[(size_t)r * per + k];
+    CK(cudaMalloc(&h->d_E, Epad.size() * sizeof(float)));
+    CK(cudaMemcpy(h->d_E, Epad.data(), Epad.size() * sizeof(float), cudaMemcpyHostToDevice));
+    h->fp.Eg = h->d_E;
+    if (vp->carrier_gated == vp->carrier_open) return set_error(AMPS_E_INVAL, "the two voice legs must feed different carriers");
     h->fp.vcar[0] = vp->carrier_gated;
     h->fp.vcar[1] = vp->carrier_open;
     h->max_audio = (uint32_t)(((uint64_t)h->max_sym * 4u + 24u) / 25u);
     CK(cudaMalloc(&h->d_audio, sizeof(float) * h->max_audio));
     CK(cudaMalloc(&h->d_delta, sizeof(unsigned long long) * h->max_audio));
     CK(cudaMalloc(&h->d_phase, sizeof(unsigned long long)));
+    CK(cudaMalloc(&h->d_vbtot, sizeof(unsigned long long) * (h->max_audio / 256 + 1)));
+    CK(cudaMalloc(&h->d_vboff, sizeof(unsigned long long) * (h->max_audio / 256 + 1)));
     for (int b = 0; b < 2; ++b) {
         CK(cudaMalloc(&h->d_hx[b], sizeof(double) * kVoiceImp));
         for (int l = 0; l < kFwdVoiceLegs; ++l) CK(cudaMalloc(&h->d_vhist[b][l], sizeof(float2) * kFwdVoiceHist));
@@ -329,7 +337,7 @@ extern "C" int amps_fwd_submit_voice_dev(amps_fwd *h, const void *const *d_sym, 
     VoicePrepParams vp = h->vp;
     vp.audio = static_cast<const float *>(d_audio);
     vp.hx_old = h->d_hx[cur]; vp.hx_new = h->d_hx[nxt];
-    vp.delta = h->d_delta; vp.phase = h->d_phase;
+    vp.delta = h->d_delta; vp.phase = h->d_phase; vp.btot = h->d_vbtot; vp.boff = h->d_vboff;
     for (int l = 0; l < kFwdVoiceLegs; ++l) {
         vp.vph[l] = h->fp.vcar[l] >= 0 ? h->d_vph[l] : nullptr;
         vp.vhist_old[l] = h->d_vhist[cur][l]; vp.vhist_new[l] = h->d_vhist[nxt][l];

@@ -145,26 +145,27 @@ __device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__device__ __forceinline__ long floor_div(long a, long b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
+__device__ __forceinline__ int floor_div(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
 
 // voice legs (kVoice): the phasors a tile needs, the x25 resampler taps and the legs' rotated 400 kS/s samples
 constexpr int kVoiceStage = 48;                // audio samples staged per tile: 11 new + kFwdVoicePer - 1 of history, rounded up
-struct FwdVoiceSmem {
-    float  E[25 * kFwdVoicePer];
+constexpr int kVoiceERow = kFwdVoicePer + 1;   // odd row stride: the 25 rows start in different banks
+struct FwdVoiceSmem {                           // overlays FwdSmem::B, which is dead during phases 1-2 (refilled every tile)
+    float  E[25 * kVoiceERow];
     float2 vph[kFwdVoiceLegs][kVoiceStage];
-    float2 va[kFwdVoiceLegs][4 * (kFwdTileSym + 1) + 16];     // same indexing as FwdSmem::a
 };
+static_assert(sizeof(FwdVoiceSmem) <= sizeof(FwdSmem::B), "voice staging must fit into the 2 MS/s buffer it overlays");
+constexpr int kVoiceThreads = kFwdThreads - 96;                                   // warps 3..7
+constexpr int kVoiceOutPerThread = (kFwdVoiceLegs * 4 * (kFwdTileSym + 1) + kVoiceThreads - 1) / kVoiceThreads;   // 4
 
-static size_t fwd_voice_smem_bytes() { return ((sizeof(FwdSmem) + 15) & ~(size_t)15) + sizeof(FwdVoiceSmem); }
+static size_t fwd_voice_smem_bytes() { return sizeof(FwdSmem); }
 
 template <bool kVoice>
 __global__ void __launch_bounds__(kFwdThreads, 3) fwd_fused_kernel(const __grid_constant__ FwdParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     FwdSmem *sm = reinterpret_cast<FwdSmem *>(smem_raw);
-    FwdVoiceSmem *sv = reinterpret_cast<FwdVoiceSmem *>(smem_raw + ((sizeof(FwdSmem) + 15) & ~(size_t)15));
+    FwdVoiceSmem *sv = reinterpret_cast<FwdVoiceSmem *>(&sm->B[0]);
     const int t = threadIdx.x;
-    if (kVoice)
-        for (int i = t; i < 25 * kFwdVoicePer; i += kFwdThreads) sv->E[i] = p.E[i];
     const uint32_t ntiles = (p.nsym + kFwdTileSym - 1) / kFwdTileSym;
     constexpr int kFmLen = kFwdTileSym + 1 + kFwdMaxTap4;          // 145
     for (int i = t; i < kFwdMaxCar * 4 * kFwdMaxTap4; i += kFwdThreads) (&sm->taps[0][0])[i] = (&p.taps[0][0])[i];
@@ -187,15 +188,16 @@ __global__ void __launch_bounds__(kFwdThreads, 3) fwd_fused_kernel(const __grid_
             sm->fm[c][k] = v;
         }
         // voice: phasors for audio samples ia0 .. ia0 + 47, ia0 = floor(4 (i0 - 1) / 25) - (kFwdVoicePer - 1)
-        const long ia0 = floor_div(4 * (i0 - 1), 25) - (kFwdVoicePer - 1);
+        const int ia0 = floor_div(4 * ((int)i0 - 1), 25) - (kFwdVoicePer - 1);
         if (kVoice) {
+            for (int i = t; i < 25 * kFwdVoicePer; i += kFwdThreads) sv->E[(i / kFwdVoicePer) * kVoiceERow + (i % kFwdVoicePer)] = p.Eg[i];
             for (int idx = t; idx < kFwdVoiceLegs * kVoiceStage; idx += kFwdThreads) {
                 const int l = idx / kVoiceStage, k = idx - l * kVoiceStage;
-                const long ia = ia0 + k;
+                const int ia = ia0 + k;
                 float2 v = make_float2(0.f, 0.f);
                 if (p.vcar[l] >= 0) {
-                    if (ia >= 0) { if (ia < (long)p.n_audio) v = p.vph[l][ia]; }
-                    else if (ia >= -(long)kFwdVoiceHist) v = p.vhist[l][kFwdVoiceHist + ia];
+                    if (ia >= 0) { if (ia < (int)p.n_audio) v = p.vph[l][ia]; }
+                    else if (ia >= -kFwdVoiceHist) v = p.vhist[l][kFwdVoiceHist + ia];
                 }
                 sv->vph[l][k] = v;
             }
@@ -238,25 +240,45 @@ __global__ void __launch_bounds__(kFwdThreads, 3) fwd_fused_kernel(const __grid_
             a[5] = cmul(hi1, W); W = cmul(W, w25);
             a[6] = cmul(hi2, W); W = cmul(W, w25);
             a[7] = cmul(hi3, W);
-        } else if (kVoice && t >= 96) {
-            // the warps the symbol carriers leave idle: x25 polyphase resampling of the voice phasors, rotated by the
-            // carrier NCO like the symbol legs.  One output = 400 kS/s sample m = 4 (i0 - 1) + idx of one leg.
-            for (int o = t - 96; o < kFwdVoiceLegs * 4 * (kFwdTileSym + 1); o += kFwdThreads - 96) {
+        }
+        // the warps the symbol carriers leave idle: x25 polyphase resampling of the voice phasors, rotated by the carrier
+        // NCO like the symbol legs.  One output = 400 kS/s sample m = 4 (i0 - 1) + idx of one leg; kept in registers
+        // until the symbol warps have stored theirs, then added in place (add_xx in front of the mixer).
+        float2 vout[kVoiceOutPerThread];
+        if (kVoice && t >= 96) {
+#pragma unroll
+            for (int j = 0; j < kVoiceOutPerThread; ++j) {
+                const int o = t - 96 + j * kVoiceThreads;
+                vout[j] = make_float2(0.f, 0.f);
+                if (o >= kFwdVoiceLegs * 4 * (kFwdTileSym + 1)) continue;
                 const int l = o / (4 * (kFwdTileSym + 1)), idx = o - l * 4 * (kFwdTileSym + 1);
                 const int c = p.vcar[l];
                 if (c < 0) continue;
-                const long m = 4 * (i0 - 1) + idx;
-                const long ia = floor_div(m, 25);
-                const int r = (int)(m - 25 * ia);
-                const float *Er = &sv->E[r * kFwdVoicePer];
+                const int m = 4 * ((int)i0 - 1) + idx;
+                const int ia = floor_div(m, 25);
+                const int r = m - 25 * ia;
+                const float *Er = &sv->E[r * kVoiceERow];
                 const float2 *x = &sv->vph[l][ia - ia0];              // x[-k] = phasor of audio sample ia - k
                 float2 acc = make_float2(0.f, 0.f);
                 for (int k = 0; k < p.vper; ++k) acc = fma2(splat(Er[k]), x[-k], acc);
                 const float2 W = sincos_phase((p.m_base + (uint32_t)m) * p.fcw_mix25[c]);
-                sv->va[l][idx] = cmul(acc, W);
+                vout[j] = cmul(acc, W);
             }
         }
         __syncthreads();
+        if (kVoice) {
+            if (t >= 96) {
+#pragma unroll
+                for (int j = 0; j < kVoiceOutPerThread; ++j) {
+                    const int o = t - 96 + j * kVoiceThreads;
+                    if (o >= kFwdVoiceLegs * 4 * (kFwdTileSym + 1)) continue;
+                    const int l = o / (4 * (kFwdTileSym + 1)), idx = o - l * 4 * (kFwdTileSym + 1);
+                    const int c = p.vcar[l];
+                    if (c >= 0) sm->a[c][idx] = add2(sm->a[c][idx], vout[j]);
+                }
+            }
+            __syncthreads();
+        }
 
         // ---- phase 3a: x5 CIC^3 interpolation to 2 MS/s with the mixer folded into complex taps, carriers summed.
         //      B[5 m + r] = sum_c sum_j C1_c[r + 5 j] at_c[m - j];  thread = one 400 kS/s sample -> 5 outputs
@@ -269,11 +291,7 @@ __global__ void __launch_bounds__(kFwdThreads, 3) fwd_fused_kernel(const __grid_
                 if (c < p.ncar) {
 #pragma unroll
                     for (int j = 0; j < 3; ++j) {
-                        float2 x = sm->a[c][t + 3 - j];
-                        if (kVoice) {                              // add_xx before the mixer: the legs share this carrier's NCO
-                            if (p.vcar[0] == c) x = add2(x, sv->va[0][t + 3 - j]);
-                            if (p.vcar[1] == c) x = add2(x, sv->va[1][t + 3 - j]);
-                        }
+                        const float2 x = sm->a[c][t + 3 - j];
                         const float2 xr = splat(x.x), xi = splat(x.y);
 #pragma unroll
                         for (int r = 0; r < 5; ++r) {
@@ -476,11 +494,12 @@ cudaError_t launch_fwd_fused_voice(const FwdParams &p, int grid, cudaStream_t st
 // voice pre-pass (16 kS/s: 1/625 of the output rate, so these kernels are off the roofline).
 //   x[n] = audio[n] + SAT;  y[n] = sum_k g[k] x[n - k]   (fm_preemph's IIR as its truncated impulse response: no
 //   recurrence, any sample computable on its own, float64);  delta[n] = frac(y[n] max_dev / fs) * 2^64
-//   Phi[n] = Phi[n-1] + delta[n] (mod 2^64, an exact integer scan);  phasor[n] = e^{j 2 pi Phi[n] / 2^64}
+//   Phi[n] = Phi[n-1] + delta[n] (mod 2^64, an exact integer scan in two levels);  phasor[n] = e^{j 2 pi Phi[n] / 2^64}
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) voice_delta_kernel(const __grid_constant__ VoicePrepParams p) {
     __shared__ double s_x[256 + kVoiceImp];
     __shared__ double s_g[kVoiceImp];
+    __shared__ unsigned long long s_warp[8];
     const int t = threadIdx.x;
     const long n0 = (long)blockIdx.x * 256;
     for (int i = t; i < kVoiceImp; i += 256) s_g[i] = p.g[i];
@@ -494,13 +513,27 @@ __global__ void __launch_bounds__(256) voice_delta_kernel(const __grid_constant_
     }
     __syncthreads();
     const long n = n0 + t;
+    unsigned long long d = 0;
     if (n < (long)p.n_audio) {
         double y = 0.0;
         for (int k = 0; k < kVoiceImp; ++k) y = fma(s_g[k], s_x[kVoiceImp + t - k], y);
         double cyc = y * p.cycles_per_unit;
         cyc -= floor(cyc);
-        p.delta[n] = __double2ull_rn(cyc * 18446744073709551616.0);
+        d = __double2ull_rn(cyc * 18446744073709551616.0);
     }
+    // inclusive scan of the phase steps inside the block (mod 2^64: exact), block total for the second level
+    unsigned long long incl = d;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+        const unsigned long long o = __shfl_up_sync(0xffffffffu, incl, s);
+        if ((t & 31) >= s) incl += o;
+    }
+    if ((t & 31) == 31) s_warp[t >> 5] = incl;
+    __syncthreads();
+    unsigned long long woff = 0;
+    for (int w = 0; w < (t >> 5); ++w) woff += s_warp[w];
+    if (n < (long)p.n_audio) p.delta[n] = woff + incl;
+    if (t == 255) p.btot[blockIdx.x] = woff + incl;
     // history of inputs for the next call: the last kVoiceImp of (old history ++ this call's inputs)
     if (blockIdx.x == 0 && t < kVoiceImp) {
         const long src = (long)p.n_audio - kVoiceImp + t;
@@ -511,50 +544,64 @@ __global__ void __launch_bounds__(256) voice_delta_kernel(const __grid_constant_
     }
 }
 
-__global__ void __launch_bounds__(1024) voice_scan_kernel(const __grid_constant__ VoicePrepParams p) {
+// one CTA: exclusive scan of the block totals on top of the running phase; the running phase for the next call
+__global__ void __launch_bounds__(1024) voice_totals_kernel(const __grid_constant__ VoicePrepParams p) {
     __shared__ unsigned long long s_warp[32];
     __shared__ unsigned long long s_carry;
     const int t = threadIdx.x;
+    const uint32_t nblk = (p.n_audio + 255u) / 256u;
     if (t == 0) s_carry = *p.phase;
     __syncthreads();
-    const uint32_t per = (p.n_audio + 1023u) / 1024u;                // contiguous run per thread
-    const uint32_t lo = (uint32_t)t * per, hi = lo + per < p.n_audio ? lo + per : p.n_audio;
-    unsigned long long run = 0;
-    for (uint32_t n = lo; n < hi; ++n) run += p.delta[n];
-    unsigned long long incl = run;
+    for (uint32_t base = 0; base < nblk; base += 1024) {
+        const uint32_t b = base + t;
+        const unsigned long long v = b < nblk ? p.btot[b] : 0ull;
+        unsigned long long incl = v;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const unsigned long long o = __shfl_up_sync(0xffffffffu, incl, d);
-        if ((t & 31) >= d) incl += o;
+        for (int s = 1; s < 32; s <<= 1) {
+            const unsigned long long o = __shfl_up_sync(0xffffffffu, incl, s);
+            if ((t & 31) >= s) incl += o;
+        }
+        if ((t & 31) == 31) s_warp[t >> 5] = incl;
+        __syncthreads();
+        unsigned long long woff = 0;
+        for (int w = 0; w < (t >> 5); ++w) woff += s_warp[w];
+        const unsigned long long carry = s_carry;
+        if (b < nblk) p.boff[b] = carry + woff + incl - v;
+        __syncthreads();
+        if (t == 1023) s_carry = carry + woff + incl;
+        __syncthreads();
     }
-    if ((t & 31) == 31) s_warp[t >> 5] = incl;
-    __syncthreads();
-    unsigned long long woff = 0;
-    for (int w = 0; w < (t >> 5); ++w) woff += s_warp[w];
-    unsigned long long phi = s_carry + woff + incl - run;           // phase before this thread's first sample
-    for (uint32_t n = lo; n < hi; ++n) {
-        phi += p.delta[n];
+    if (t == 0) *p.phase = s_carry;
+}
+
+__global__ void __launch_bounds__(256) voice_phasor_kernel(const __grid_constant__ VoicePrepParams p) {
+    const int t = threadIdx.x;
+    const long n = (long)blockIdx.x * 256 + t;
+    const long h0 = (long)p.n_audio - kFwdVoiceHist;               // samples >= h0 are the next call's history
+    if (n < (long)p.n_audio) {
+        const unsigned long long phi = p.boff[blockIdx.x] + p.delta[n];
         const float2 v = sincos_phase((uint32_t)(phi >> 32));
 #pragma unroll
-        for (int l = 0; l < kFwdVoiceLegs; ++l)
-            if (p.vph[l]) p.vph[l][n] = p.leg_muted[l] ? make_float2(0.f, 0.f) : v;
+        for (int l = 0; l < kFwdVoiceLegs; ++l) {
+            if (!p.vph[l]) continue;
+            const float2 w = p.leg_muted[l] ? make_float2(0.f, 0.f) : v;
+            p.vph[l][n] = w;
+            if (n >= h0) p.vhist_new[l][n - h0] = w;
+        }
     }
-    __syncthreads();
-    if (t == 1023) *p.phase = s_carry + woff + incl;
-    __syncthreads();
-    // phasor history for the next call
-    if (t < kFwdVoiceHist) {
-        const long src = (long)p.n_audio - kFwdVoiceHist + t;
+    if (blockIdx.x == 0 && t < kFwdVoiceHist && h0 + t < 0) {      // fewer than 32 new samples: the rest comes from the old history
 #pragma unroll
         for (int l = 0; l < kFwdVoiceLegs; ++l)
-            if (p.vph[l]) p.vhist_new[l][t] = src >= 0 ? p.vph[l][src] : p.vhist_old[l][kFwdVoiceHist + src];
+            if (p.vph[l]) p.vhist_new[l][t] = p.vhist_old[l][kFwdVoiceHist + h0 + t];
     }
 }
 
 cudaError_t launch_voice_prep(const VoicePrepParams &p, cudaStream_t st) {
     if (p.n_audio == 0) return cudaSuccess;
-    voice_delta_kernel<<<(p.n_audio + 255u) / 256u, 256, 0, st>>>(p);
-    voice_scan_kernel<<<1, 1024, 0, st>>>(p);
+    const unsigned int nblk = (p.n_audio + 255u) / 256u;
+    voice_delta_kernel<<<nblk, 256, 0, st>>>(p);
+    voice_totals_kernel<<<1, 1024, 0, st>>>(p);
+    voice_phasor_kernel<<<nblk, 256, 0, st>>>(p);
     return cudaGetLastError();
 }
 

@@ -53,7 +53,7 @@ struct FwdParams {
     int            vcar[kFwdVoiceLegs];          // carrier whose mixer the leg shares, -1 = leg unused
     int            vper;                         // taps per arm of the x25 resampler (<= kFwdVoicePer)
     uint32_t       n_audio;                      // audio samples of this call
-    float          E[25 * kFwdVoicePer];         // E[r * kFwdVoicePer + k]
+    const float   *Eg;                           // device copy of the resampler taps, E[r * kFwdVoicePer + k]
 };
 
 // ---- voice pre-pass: audio (+SAT) -> pre-emphasis -> FM phase -> phasors @16 kS/s
@@ -62,7 +62,8 @@ struct VoicePrepParams {
     const float *audio;                          // this call's samples
     const double *hx_old;                        // previous call's last kVoiceImp inputs (audio + SAT), zeros at stream start
     double      *hx_new;
-    unsigned long long *delta;                   // per-sample FM phase step, 2^64 = one turn
+    unsigned long long *delta;                   // FM phase steps (2^64 = one turn), inclusive-scanned inside each 256-sample block
+    unsigned long long *btot, *boff;             // block totals / absolute phase in front of each block
     unsigned long long *phase;                   // running FM phase (device scalar, carried between calls)
     float2      *vph[kFwdVoiceLegs];
     const float2 *vhist_old[kFwdVoiceLegs];

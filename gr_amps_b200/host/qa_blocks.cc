@@ -4,8 +4,8 @@
 // GNU Radio scheduler would.  Results go to files / JSON lines that tests/test_host_gpu.py compares with the oracle.
 //
 //   qa_blocks focc <symrate> <aggr 0|1> <total_bytes> <seed> <out.bin>
-//   qa_blocks loop <iq.bin> <nsamples> <chunk> <focc_bytes> <out_prefix>
-//   qa_blocks fwd <nsym> <out.bin>
+//   qa_blocks loop <iq.bin> <nsamples> <chunk> <focc_bytes> <out_prefix> [mm]
+//   qa_blocks fwd <nsym> <out.bin> [voice]
 //   qa_blocks cmd <text> [<text> ...]          (host only: command_processor, no GPU needed)
 #include <amps/focc.h>
 #include <amps/fvc.h>
@@ -16,6 +16,7 @@
 #include <amps/command_processor.h>
 #include <amps_b200.h>
 
+#include <cmath>
 #include <complex>
 #include <cstdio>
 #include <cstdlib>
@@ -114,7 +115,8 @@ static int run_loop(int argc, char **argv) {
     if (!f) { std::fprintf(stderr, "short read of %s\n", argv[2]); return 4; }
 
     // the message wiring of grc/ampsbs.grc:4404-4470 around the RECC/FOCC/FVC blocks
-    recc_iq::sptr rx = recc_iq::make(10e6, -160e3, 0);
+    const bool mm_timing = argc > 7 && !std::strcmp(argv[7], "mm");                   // M&M timing tail instead of the detector
+    recc_iq::sptr rx = recc_iq::make(10e6, -160e3, 0, mm_timing);
     recc_decode::sptr dec = recc_decode::make();
     focc::sptr fo = focc::make(100000, false);
     fvc::sptr fv = fvc::make(100000);
@@ -185,9 +187,24 @@ static int run_fwd(int argc, char **argv) {
     std::vector<float> out(2 * nsym * 100);
     const uint8_t *syms[3] = {s0.data(), s1.data(), s2.data()};
     size_t half = nsym / 2;                                                         // two calls: exercises the carried history
+    const bool voice = argc > 4 && !std::strcmp(argv[4], "voice");
+    if (voice) {                                                                    // nsym must be a multiple of 50 here
+        amps_fwd_voice_params vp = {1, 2, 16000.0, 8e3, 75e-6, 6000.0, 0.05};
+        if (amps_fwd_enable_voice(h, &vp) != AMPS_OK) { std::fprintf(stderr, "%s\n", amps_b200_last_error()); return 7; }
+        std::vector<float> audio(nsym * 4 / 25);
+        for (size_t i = 0; i < audio.size(); i++) audio[i] = 0.3f * std::sin(0.17f * (float)i);
+        half -= half % 25;
+        if (amps_fwd_work_voice(h, syms, audio.data(), half, 0, out.data()) != AMPS_OK) return 5;
+        const uint8_t *syms2[3] = {s0.data() + half, s1.data() + half, s2.data() + half};
+        if (amps_fwd_work_voice(h, syms2, audio.data() + half * 4 / 25, nsym - half, 1, out.data() + 2 * half * 100) != AMPS_OK) {
+            std::fprintf(stderr, "%s\n", amps_b200_last_error());
+            return 6;
+        }
+    } else {
     if (amps_fwd_work(h, syms, half, out.data()) != AMPS_OK) return 5;
     const uint8_t *syms2[3] = {s0.data() + half, s1.data() + half, s2.data() + half};
     if (amps_fwd_work(h, syms2, nsym - half, out.data() + 2 * half * 100) != AMPS_OK) return 6;
+    }
     amps_fwd_destroy(h);
     std::ofstream(argv[3], std::ios::binary).write(reinterpret_cast<const char *>(out.data()), (std::streamsize)(out.size() * sizeof(float)));
     std::printf("{\"samples\": %zu}\n", nsym * 100);

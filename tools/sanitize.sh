@@ -19,8 +19,15 @@ PY
 N=$(cat /tmp/san/n.txt)
 QA=gr_amps_b200/host/qa_blocks
 for tool in memcheck racecheck synccheck; do
+  if [ "${ONLY_NEW:-0}" != "1" ]; then
   timeout 1200 compute-sanitizer --tool $tool --error-exitcode 9 $QA loop /tmp/san/iq.bin $N 262144 87970 /tmp/san/out > gpurun_out/sanitize_$tool.log 2>&1
   echo "loop $tool rc=$? $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' gpurun_out/sanitize_$tool.log | tail -1)"
   timeout 1200 compute-sanitizer --tool $tool --error-exitcode 9 $QA fwd 20000 /tmp/san/fwd.bin > gpurun_out/sanitize_fwd_$tool.log 2>&1
   echo "fwd  $tool rc=$? $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' gpurun_out/sanitize_fwd_$tool.log | tail -1)"
+  fi
+  # round-1 additions: the M&M timing tail of recc_iq and the voice legs of the forward path
+  timeout 1200 compute-sanitizer --tool $tool --error-exitcode 9 $QA loop /tmp/san/iq.bin $N 262144 87970 /tmp/san/outmm mm > gpurun_out/sanitize_mm_$tool.log 2>&1
+  echo "mm   $tool rc=$? $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' gpurun_out/sanitize_mm_$tool.log | tail -1)"
+  timeout 1200 compute-sanitizer --tool $tool --error-exitcode 9 $QA fwd 20000 /tmp/san/fwdv.bin voice > gpurun_out/sanitize_voice_$tool.log 2>&1
+  echo "voice $tool rc=$? $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' gpurun_out/sanitize_voice_$tool.log | tail -1)"
 done
