@@ -49,6 +49,8 @@ struct amps_recc_iq {
     cudaEvent_t  ev_side[2] = {nullptr, nullptr};   // detection of call k finished (k & 1)
     uint64_t     call_no = 0;
     bool         serial = false;         // AMPS_RX_SERIAL=1: no overlap (profiling / A-B measurements)
+    int          diag = 0;               // AMPS_RX_DIAG (measurement aid): 1 = no capture launch, 2 = no detect/select launch
+    bool         front_only = false;     // AMPS_RX_FRONT_ONLY=1: no detection at all (pipeline measurements only: no bursts come out)
     // AMPS_RX_TIMING_MM: the reference graph's serial tail instead of the feed-forward detector
     bool         mm_mode = false;
     MmState     *d_mm = nullptr;
@@ -102,7 +104,7 @@ static int rx_alloc(amps_recc_iq *h) {
     }
     CK(cudaMalloc(&h->d_state, sizeof(RxState)));
     CK(cudaMemset(h->d_state, 0, sizeof(RxState)));
-    CK(cudaMalloc(&h->d_cand, sizeof(Candidate) * kMaxCand));
+    CK(cudaMalloc(&h->d_cand, sizeof(Candidate) * kMaxCand * 2));      // candidates + the select kernel's sorted copy
     CK(cudaMalloc(&h->d_acc, sizeof(Accepted) * kMaxAccept));
     if (h->mm_mode) {
         h->sym_cap = (uint32_t)(max_d / 8 + 64);
@@ -153,6 +155,8 @@ extern "C" int amps_recc_iq_create(const amps_recc_iq_params *params, amps_recc_
     h->flags = params->flags;
     h->mm_mode = (params->flags & AMPS_RX_TIMING_MM) != 0;
     { const char *e = std::getenv("AMPS_RX_SERIAL"); h->serial = e && e[0] == '1'; }
+    { const char *e = std::getenv("AMPS_RX_FRONT_ONLY"); h->front_only = e && e[0] == '1'; }
+    { const char *e = std::getenv("AMPS_RX_DIAG"); h->diag = e ? std::atoi(e) : 0; }
     if (params->lpf_taps) h->lpf.assign(params->lpf_taps, params->lpf_taps + params->n_lpf_taps);
     else h->lpf = firdes_low_pass(3.0, 400e3, 10e3, 4500.0, WIN_BLACKMAN);     // grc/ampsbs.grc:138-184
     h->fcw = nco_fcw(params->center_freq, params->samp_rate);
@@ -247,7 +251,9 @@ static int rx_enqueue(amps_recc_iq *h, const float2 *d_chunk, uint32_t npass, cu
     CK(cudaEventRecord(h->ev_front, st));
     cudaStream_t sd = h->serial ? st : h->side;
     if (!h->serial) CK(cudaStreamWaitEvent(sd, h->ev_front, 0));
-    if (h->mm_mode) {
+    if (h->front_only) {
+        // measurement aid: nothing after the front kernel
+    } else if (h->mm_mode) {
         // serial tail: M&M + slicer over everything demodulated so far, amps.recc on the new half-symbols, then
         // one CTA per blob decodes and publishes it
         CKL(launch_rx_mm(h->d_dring, h->dmask, h->total_d, h->d_mm, h->d_mmtab, h->d_sym, h->sym_cap, h->d_compat, h->d_blobs,
@@ -261,10 +267,13 @@ static int rx_enqueue(amps_recc_iq *h, const float2 *d_chunk, uint32_t npass, cu
         const uint64_t hi = h->total_d - (uint64_t)kSpan;
         const uint64_t lo = h->scan_hi > 64 ? h->scan_hi - 64 : 0;
         if (hi > h->scan_hi) {
-            CKL(launch_rx_detect(h->d_dring, h->d_hring, h->dmask, h->d_state, h->d_cand, lo, hi, sd));
+            if (!(h->diag & 2)) {
+            CKL(launch_rx_detect(h->d_dring, h->d_hring, h->dmask, h->d_state, h->d_cand, lo, hi, 0, sd));
             CKL(launch_rx_select(h->d_state, h->d_cand, h->d_acc, hi, h->h_pub, sd));
+            }
             // at most one burst per kBurstLen searched positions (+1 for a run deferred from the last call)
             const int max_new = (int)((hi - lo) / (uint64_t)kBurstLen) + 2;
+            if (!(h->diag & 1))
             CKL(launch_rx_capture(h->d_dring, h->dmask, h->d_state, h->d_acc, max_new, h->h_ring, h->max_records, h->h_pub, h->decim, sd));
             h->launches += 3;
             h->scan_hi = hi;

@@ -284,11 +284,10 @@ __device__ __forceinline__ float trig_corr(const float *__restrict__ dring, uint
 // One thread per group of 32 sampling positions.  The thread owning the FIRST position of a run of
 // matches (at most 10 long: the pattern cannot match one half-symbol later) emits one candidate for
 // the whole run: its soft-correlation peak (first maximum) is the sampling phase.
-__global__ void __launch_bounds__(256) rx_detect_kernel(const float *__restrict__ dring, const uint32_t *__restrict__ hring,
-                                                       uint32_t dmask, RxState *state, Candidate *cand,
-                                                       unsigned long long scan_lo, unsigned long long scan_hi) {
-    const unsigned long long i0 = (scan_lo & ~31ull) + 32ull * ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x);
-    if (i0 >= scan_hi) return;
+// (Grid-stride loop; the launcher may cap the grid.  Measured on B200: the grid size does not matter for the pipeline, the
+// shared-memory carve-out preference set in rx_configure_device() does.)
+__device__ void detect_group(const float *__restrict__ dring, const uint32_t *__restrict__ hring, uint32_t dmask, RxState *state,
+                             Candidate *cand, unsigned long long scan_lo, unsigned long long scan_hi, unsigned long long i0) {
     const uint32_t wmask = dmask >> 5;
     const uint32_t m0 = group_match(hring, wmask, i0);
     if (!m0) return;
@@ -327,11 +326,21 @@ __global__ void __launch_bounds__(256) rx_detect_kernel(const float *__restrict_
     }
 }
 
+__global__ void __launch_bounds__(256) rx_detect_kernel(const float *__restrict__ dring, const uint32_t *__restrict__ hring,
+                                                       uint32_t dmask, RxState *state, Candidate *cand,
+                                                       unsigned long long scan_lo, unsigned long long scan_hi) {
+    const unsigned long long base = scan_lo & ~31ull;
+    const unsigned long long stride = 32ull * (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i0 = base + 32ull * ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x); i0 < scan_hi; i0 += stride)
+        detect_group(dring, hring, dmask, state, cand, scan_lo, scan_hi, i0);
+}
+
 cudaError_t launch_rx_detect(const float *dring, const uint32_t *hring, uint32_t dmask, RxState *state, Candidate *cand,
-                             unsigned long long scan_lo, unsigned long long scan_hi, cudaStream_t st) {
+                             unsigned long long scan_lo, unsigned long long scan_hi, int max_ctas, cudaStream_t st) {
     if (scan_hi <= scan_lo) return cudaSuccess;
     const unsigned long long groups = (scan_hi - (scan_lo & ~31ull) + 31ull) / 32ull;
-    const unsigned int grid = (unsigned int)((groups + 255) / 256);
+    unsigned int grid = (unsigned int)((groups + 255) / 256);
+    if (max_ctas > 0 && grid > (unsigned int)max_ctas) grid = (unsigned int)max_ctas;
     rx_detect_kernel<<<grid, 256, 0, st>>>(dring, hring, dmask, state, cand, scan_lo, scan_hi);
     return cudaGetLastError();
 }
@@ -517,10 +526,10 @@ cudaError_t launch_decode_blobs(const uint8_t *blobs, int nbursts, amps_recc_wor
 // ============================================================================================
 // candidate selection (single CTA; candidates are rare) and burst capture (one CTA per burst)
 // ============================================================================================
-__global__ void __launch_bounds__(256) rx_select_kernel(RxState *state, Candidate *cand, Accepted *acc,
+// `sorted` is global scratch (kMaxCand entries) rather than 196 KB of shared memory, so that this CTA can become resident
+// next to the front-kernel CTAs of the following call.
+__global__ void __launch_bounds__(256) rx_select_kernel(RxState *state, Candidate *cand, Candidate *sorted, Accepted *acc,
                                                        unsigned long long scan_hi, RxPublished *host_pub) {
-    extern __shared__ unsigned char sel_raw[];
-    Candidate *sorted = reinterpret_cast<Candidate *>(sel_raw);                          // kMaxCand
     const int t = threadIdx.x, nt = blockDim.x;
     unsigned int n = state->ncand;
     if (n > (unsigned)kMaxCand) n = kMaxCand;
@@ -569,8 +578,7 @@ __global__ void __launch_bounds__(256) rx_select_kernel(RxState *state, Candidat
 
 cudaError_t launch_rx_select(RxState *state, Candidate *cand, Accepted *acc, unsigned long long scan_hi,
                              RxPublished *host_pub, cudaStream_t st) {
-    const size_t smem = (size_t)kMaxCand * sizeof(Candidate);
-    rx_select_kernel<<<1, 256, smem, st>>>(state, cand, acc, scan_hi, host_pub);
+    rx_select_kernel<<<1, 256, 0, st>>>(state, cand, cand + kMaxCand, acc, scan_hi, host_pub);   // cand holds 2 x kMaxCand entries
     return cudaGetLastError();
 }
 
@@ -760,8 +768,16 @@ cudaError_t launch_rx_mm(const float *dring, uint32_t dmask, unsigned long long 
 cudaError_t rx_configure_device() {
     cudaError_t e = cudaFuncSetAttribute(rx_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rx_front_smem_bytes());
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(rx_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)((size_t)kMaxCand * sizeof(Candidate)));
+    // The side-stream kernels share SMs with the NEXT call's front kernel, whose two CTAs need 199 KB of shared memory per
+    // SM.  An SM's L1/shared split is fixed while CTAs are resident: if a kernel that wants a big L1 gets there first, the
+    // front CTAs wait until it has left.  Ask for the front kernel's split everywhere.
+    const void *side[] = {(const void *)rx_detect_kernel, (const void *)rx_select_kernel, (const void *)rx_capture_kernel,
+                          (const void *)rx_mm_kernel, (const void *)rx_mm_recc_kernel, (const void *)rx_front_kernel};
+    for (const void *f : side) {
+        e = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 }  // namespace amps

@@ -87,8 +87,9 @@ cudaError_t rx_configure_device();
 cudaError_t launch_rx_front(const RxFrontParams &p, int grid, cudaStream_t st);
 cudaError_t launch_rx_front400(const RxFrontParams &p, int grid, cudaStream_t st);
 cudaError_t launch_rx_detect(const float *dring, const uint32_t *hring, uint32_t dmask, RxState *state, Candidate *cand,
-                             unsigned long long scan_lo, unsigned long long scan_hi, cudaStream_t st);
-// select: sorts the candidates, groups runs, picks sampling phases -> acc[0 .. state->n_acc)
+                             unsigned long long scan_lo, unsigned long long scan_hi, int max_ctas, cudaStream_t st);
+// select: sorts the candidates (cand must hold 2 x kMaxCand entries: list + sorted scratch), groups runs, picks sampling
+// phases -> acc[0 .. state->n_acc)
 cudaError_t launch_rx_select(RxState *state, Candidate *cand, Accepted *acc, unsigned long long scan_hi,
                              RxPublished *host_pub, cudaStream_t st);
 // capture: one CTA per accepted burst (grid = upper bound, surplus CTAs exit): gathers the 3374 half-symbols,
