@@ -234,13 +234,15 @@ static int rx_enqueue(amps_recc_iq *h, const float2 *d_chunk, uint32_t npass, cu
     const bool timed = (h->flags & AMPS_RX_TIME_KERNELS) != 0;
     const int  evi = (int)(h->ev_count % amps_recc_iq::kEv);
     if (timed) CK(cudaEventRecord(h->ev0[evi], st));
+    p.tail_out = h->native400 ? nullptr : h->d_tail[h->tail_cur ^ 1];
     if (h->native400) CKL(launch_rx_front400(p, grid, st));
     else CKL(launch_rx_front(p, grid, st));
     if (timed) { CK(cudaEventRecord(h->ev1[evi], st)); h->ev_count++; }
     h->launches++;
-    // history for the next call = the last pass of this one
-    CK(cudaMemcpyAsync(h->d_tail[h->tail_cur ^ 1], d_chunk + ((size_t)npass * h->pass_in - h->hist), (size_t)h->hist * sizeof(float2),
-                       cudaMemcpyDeviceToDevice, st));
+    // history for the next call = the tail of this one (the 10 MS/s front kernel copies it itself)
+    if (h->native400)
+        CK(cudaMemcpyAsync(h->d_tail[h->tail_cur ^ 1], d_chunk + ((size_t)npass * h->pass_in - h->hist), (size_t)h->hist * sizeof(float2),
+                           cudaMemcpyDeviceToDevice, st));
     h->tail_cur ^= 1;
     h->ydump_first = h->total_d;
     h->ydump_count = (uint64_t)npass * kPassOut;

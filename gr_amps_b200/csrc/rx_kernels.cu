@@ -138,6 +138,15 @@ __global__ void __launch_bounds__(kTB, 2) rx_front_kernel(const __grid_constant_
     FrontSmem *sm = reinterpret_cast<FrontSmem *>(smem_raw);
     const int t = threadIdx.x;
 
+    // history for the next call = the last kHist samples of this chunk; every CTA copies a slice (saves a memcpy node
+    // between consecutive front kernels)
+    if (p.tail_out) {
+        const uint32_t per = ((uint32_t)kHist + gridDim.x - 1u) / gridDim.x;
+        const uint32_t lo = blockIdx.x * per, hi = lo + per < (uint32_t)kHist ? lo + per : (uint32_t)kHist;
+        const float2 *src = p.chunk + ((size_t)p.npass * kPass - kHist);
+        for (uint32_t i = lo + (uint32_t)t; i < hi; i += kTB) p.tail_out[i] = src[i];
+    }
+
     uint32_t pa = blockIdx.x * p.pass_per_cta;
     if (pa >= p.npass) return;
     uint32_t pb = pa + p.pass_per_cta;

@@ -28,6 +28,7 @@ struct RxFrontParams {
     const float2 *chunk;     // logical samples [0, npass*kPass)
     const float2 *tail;      // logical samples [-kHist, 0)
     float        *dring;     // demod ring, indexed by (absolute demod index & dmask)
+    float2       *tail_out;  // 10 MS/s kernel: where to leave the next call's history (kHist samples), or nullptr
     uint32_t     *hring;     // hard decisions d >= 0, bit (i & 31) of word ((i & dmask) >> 5)
     float2       *ydump;     // optional: complex baseband of this call (npass*kPassOut entries) or nullptr
     uint64_t      q_base;    // absolute demod index of this call's first output
