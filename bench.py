@@ -149,6 +149,29 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def _bind_near_gpu(local_rank):
+    """Pin this process to the CPUs local to the GPU (sysfs local_cpulist of its PCI device); returns the old mask or None."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/local_cpulist" % bdf) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        old = os.sched_getaffinity(0)
+        cpus &= old
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        print("bench.py: e2e staging bound to %d CPUs local to GPU %s" % (len(cpus), bdf), file=sys.stderr)
+        return old
+    except Exception as e:                                  # measurement nicety only
+        print("bench.py: no NUMA binding (%s)" % e, file=sys.stderr)
+        return None
+
+
 def measure_fwd(local_rank, steps, warmup, bits=False, voice=False):
     """BASELINE config 3 on this rank's GPU: FOCC @0 Hz + FVC @+60 kHz + FVC @+90 kHz, x0.5 -> 10 MS/s complex,
     device resident.  Algorithmic bytes: 8 B written per output sample (+ 3 symbol bytes per 100 samples read).
@@ -343,6 +366,8 @@ def main():
     rx.consume(count)
 
     # ---- end-to-end arm: pinned host buffer through amps_recc_iq_work ----------------------------
+    # the staging buffer is allocated (first-touched) from a core of the GPU's own NUMA node, as a deployment would do
+    old_affinity = _bind_near_gpu(local_rank)
     host = torch.empty(batch.shape, dtype=torch.float32, pin_memory=True)
     host.copy_(batch)
     torch.cuda.synchronize()
@@ -363,6 +388,8 @@ def main():
     if len(got) < e2e_steps * nper - 2 or any(m != expect_min for m in got):
         raise SystemExit("bench.py: e2e parity gate failed (%d bursts)" % len(got))
     rec_bytes = 24 + (len(got) / e2e_steps) * float(capi.C.sizeof(capi.Burst))
+    if old_affinity is not None:
+        os.sched_setaffinity(0, old_affinity)              # the CPU baseline below uses every core again
 
     # ---- secondary: the forward path (config 3 / the FOCC half of config 4) on every rank's GPU
     del host, batch
