@@ -319,9 +319,10 @@ class Recc:
 
     __del__ = close
 
-    def work(self, syms) -> None:
+    def work(self, syms) -> int:
         s = np.ascontiguousarray(syms, dtype=np.uint8)
         check(lib().amps_recc_work(self.h, s.ctypes.data_as(u8p), len(s), self._cb, None))
+        return 0    # recc_impl::work always returns 0 (lib/recc_impl.cc:144)
 
     def work_chunks(self, syms, sizes) -> None:
         s = np.ascontiguousarray(syms, dtype=np.uint8)

@@ -418,8 +418,8 @@ extern "C" int amps_fvc_work(amps_fvc *h, uint8_t *out, int noutput_items, int *
     if (noutput_items < 1) return AMPS_OK;
     CK(cudaSetDevice(h->device));
     if (h->bits.empty()) {
-        // the reference claims noutput_items and leaves the buffer untouched (:159-161); we hand back silence
-        std::memset(out, 0, (size_t)noutput_items);
+        // no word was ever queued: claim noutput_items and leave the buffer untouched, exactly as the reference does
+        // (:159-161; the stream is muted downstream, grc/ampsbs.grc:1555-1601)
         *produced = noutput_items;
         return AMPS_OK;
     }

@@ -56,6 +56,7 @@ inline pmt_t cdr(const pmt_t &p) { return p->items.at(1); }
 inline bool is_pair(const pmt_t &p) { return p->kind == pmt_base::PAIR; }
 inline pmt_t init_u8vector(size_t n, const uint8_t *d) { pmt_t p = make(pmt_base::U8VECTOR); p->bytes.assign(d, d + n); return p; }
 inline const uint8_t *u8vector_elements(const pmt_t &p, size_t &n) { n = p->bytes.size(); return p->bytes.data(); }
+inline std::vector<uint8_t> u8vector_elements(const pmt_t &p) { return p->bytes; }
 inline bool is_u8vector(const pmt_t &p) { return p->kind == pmt_base::U8VECTOR; }
 
 }  // namespace pmt

@@ -219,9 +219,9 @@ AMPS_B200_API int amps_fvc_create(unsigned long symrate, int device, amps_fvc **
 AMPS_B200_API int amps_fvc_destroy(amps_fvc *h);
 /* fvc_words message (lib/fvc_impl.cc:109-143); has_timer/timer = the optional trailing uint64 */
 AMPS_B200_API int amps_fvc_push_words(amps_fvc *h, const uint8_t *words28, long nwords, int has_timer, uint64_t timer);
-/* work(): *produced = items produced; while no word was ever pushed the reference returns
- * noutput_items WITHOUT writing (lib/fvc_impl.cc:159-161); this library writes zeros there
- * (documented deviation).  *fvc_off is set when the "fvc off" PDU is due (:163-171). */
+/* work(): *produced = items produced; while no word was ever pushed it is noutput_items and `out` is
+ * NOT written, as in the reference (lib/fvc_impl.cc:159-161).  *fvc_off is set when the "fvc off" PDU is
+ * due (:163-171). */
 AMPS_B200_API int amps_fvc_work(amps_fvc *h, uint8_t *out, int noutput_items, int *produced, int *fvc_off);
 /* the same replay as DATA BITS (one byte per bit; 0xFF = muted while no word was ever pushed), for amps_fwd_*_bits */
 AMPS_B200_API int amps_fvc_work_bits(amps_fvc *h, uint8_t *out_bits, int nbits, int *produced, int *fvc_off);

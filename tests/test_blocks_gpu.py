@@ -104,7 +104,7 @@ def test_fvc_parity(capi, oracle):
     rng = np.random.default_rng(8)
     o, g = oracle.Fvc(100000), capi.Fvc(100000)
     r, b, off = g.work(512)
-    assert r == 512 and not off and np.all(b == 0)               # idle: silence (reference leaves the buffer untouched)
+    assert r == 512 and not off and np.all(b == 0x55)            # idle: claims n, buffer untouched (lib/fvc_impl.cc:159-161)
     alert = oracle.word("orc_fvc_word1_general", 1, 0, 0, 1)
     for step in range(300):
         if step == 0:
