@@ -6,13 +6,13 @@
  * and bench.py's cpu_baseline / --impl reference legs may load it.  The product
  * (gr_amps_b200/) never links, imports or calls anything in here.
  *
- * PARITY STATUS: "parity unpinned".  The reference ships no golden vectors and an
- * empty test-suite (reference lib/qa_amps.cc:9-15), and none of it can be built in
- * this image (GNU Radio 3.7, IT++, Boost absent).  Integer paths are
- * restated line-for-meaning from the cited reference sources and cross-checked with
- * an independent numpy GF(2) implementation + the KATs derived in SURVEY.md App. A.
- * Floating paths follow the documented equations of the stock GNU Radio blocks
- * wired up in grc/ampsbs.grc (source not in the reference tree).
+ * PARITY STATUS.  Integer paths (BCH, words, FOCC/FVC sources, RECC capture, RECC decode + responses, command
+ * processor): PINNED to the reference's own code -- oracle/_ref/libamps_ref.so is gr-amps's unmodified lib/*.cc compiled
+ * from /root/reference against stand-in GNU Radio / Boost / IT++ headers (oracle/Makefile, oracle/ref_harness.cc), and
+ * tests/test_ref_pin_cpu.py requires byte-identical transcripts, live and through tests/golden/ref_vectors.json.
+ * Floating paths (dsp_chain.c, mm_timing.c, voice_tx.c): "parity unpinned" -- they restate stock GNU Radio 3.7 blocks
+ * whose source is not in the reference tree, from their documented equations (grc/ampsbs.grc gives the parameters); the
+ * reference ships no golden vectors and an empty test-suite (reference lib/qa_amps.cc:9-15).
  *
  * All citations are relative to /root/reference/.
  */
