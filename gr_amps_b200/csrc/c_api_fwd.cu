@@ -27,6 +27,7 @@ struct amps_fwd {
     // Manchester-bit fast path
     FwdBitsParams bp{};
     float2 *d_resp = nullptr;                 // [ncar][2][360] per-bit responses of the x4 interpolator
+    float *d_fast = nullptr;                  // [ncar][kFbFastLen] the same, grouped three bits per lookup
     uint8_t *d_bits[kFwdMaxCar] = {};         // host-path staging
     uint8_t *d_hbits[2][kFwdMaxCar] = {};
     int hbits_cur = 0;
@@ -119,6 +120,8 @@ extern "C" int amps_fwd_create(const amps_fwd_params *p, amps_fwd **out) {
         std::memset(&h->bp, 0, sizeof h->bp);
         h->bp.ncar = h->ncar;
         std::vector<float> resp((size_t)h->ncar * 2 * kFbRespLen * 2, 0.0f);
+        std::vector<float> fast((size_t)h->ncar * kFbFastLen, 0.0f);
+        std::vector<double> r0((size_t)2 * kFbRespLen);             // R0' = (R0 + conj R1) / 2 of the current carrier, in double
         const double kTwoPi = 6.283185307179586476925286766559;
         for (int c = 0; c < h->ncar; ++c) {
             const int nt = (int)h->taps[c].size();
@@ -138,6 +141,9 @@ extern "C" int amps_fwd_create(const amps_fwd_params *p, amps_fwd **out) {
                     }
                     const size_t o = (((size_t)c * 2 + (size_t)b) * kFbRespLen + (size_t)u) * 2;
                     resp[o] = (float)re; resp[o + 1] = (float)im;
+                    // a Manchester 1 mirrors a 0, so R1 = conj(R0) up to the rounding of the two cos/sin evaluations
+                    if (b == 0) { r0[2 * (size_t)u] = 0.5 * re; r0[2 * (size_t)u + 1] = 0.5 * im; }
+                    else { r0[2 * (size_t)u] += 0.5 * re; r0[2 * (size_t)u + 1] -= 0.5 * im; }
                 }
             }
             const uint32_t fcw = nco_fcw(-p->carrier_freq[c], p->samp_rate);
@@ -146,8 +152,29 @@ extern "C" int amps_fwd_create(const amps_fwd_params *p, amps_fwd **out) {
             nco_block_table((uint32_t)(25u * fcw), kFbMPerBit, ph.data());       // e^{j phi_c(25 u)}, u < 40
             for (int u = 0; u < kFbMPerBit; ++u) h->bp.w40[c][u] = make_float2(ph[2 * (size_t)u], ph[2 * (size_t)u + 1]);
             std::memcpy(h->bp.C1[c], h->fp.C1[c], sizeof h->bp.C1[c]);
+            // grouped tables (fwd_kernels.cuh: kFbFastLen)
+            float *F = fast.data() + (size_t)c * kFbFastLen;
+            for (int u = 0; u < kFbMPerBit; ++u) {
+                double resum = 0;
+                for (int d = 0; d < kFbRespBits; ++d) resum += r0[2 * (size_t)(u + kFbMPerBit * d)];
+                const double wr = (double)h->bp.w40[c][u].x, wi = (double)h->bp.w40[c][u].y;
+                F[2 * u] = (float)(resum * wr); F[2 * u + 1] = (float)(resum * wi);                       // RW
+                F[2 * kFbMPerBit + 2 * u] = (float)-wi; F[2 * kFbMPerBit + 2 * u + 1] = (float)wr;        // JW = j w40
+                for (int G = 0; G < 3; ++G)
+                    for (int pat = 0; pat < 8; ++pat) {
+                        double acc = 0;
+                        for (int k = 0; k < 3; ++k) {
+                            const double im = r0[2 * (size_t)(u + kFbMPerBit * (8 - 3 * G - k)) + 1];
+                            acc += ((pat >> k) & 1) ? -im : im;
+                        }
+                        F[4 * kFbMPerBit + (G * 8 + pat) * kFbMPerBit + u] = (float)acc;
+                    }
+            }
         }
         std::memcpy(h->bp.G2, h->fp.G2, sizeof h->bp.G2);
+        CK(cudaMalloc(&h->d_fast, fast.size() * sizeof(float)));
+        CK(cudaMemcpy(h->d_fast, fast.data(), fast.size() * sizeof(float), cudaMemcpyHostToDevice));
+        h->bp.fast = h->d_fast;
         CK(cudaMalloc(&h->d_resp, resp.size() * sizeof(float)));
         CK(cudaMemcpy(h->d_resp, resp.data(), resp.size() * sizeof(float), cudaMemcpyHostToDevice));
         h->bp.resp = h->d_resp;
@@ -188,7 +215,7 @@ extern "C" int amps_fwd_destroy(amps_fwd *h) {
         for (int b = 0; b < 2; ++b) { cudaFree(h->d_hsym[b][c]); cudaFree(h->d_hS[b][c]); }
     }
     for (int c = 0; c < kFwdMaxCar; ++c) { cudaFree(h->d_bits[c]); cudaFree(h->d_hbits[0][c]); cudaFree(h->d_hbits[1][c]); }
-    cudaFree(h->d_carry); cudaFree(h->d_out); cudaFree(h->d_resp);
+    cudaFree(h->d_carry); cudaFree(h->d_out); cudaFree(h->d_resp); cudaFree(h->d_fast);
     cudaFree(h->d_audio); cudaFree(h->d_E); cudaFree(h->d_delta); cudaFree(h->d_phase); cudaFree(h->d_vbtot); cudaFree(h->d_vboff);
     for (int b = 0; b < 2; ++b) { cudaFree(h->d_hx[b]); for (int l = 0; l < kFwdVoiceLegs; ++l) cudaFree(h->d_vhist[b][l]); }
     for (int l = 0; l < kFwdVoiceLegs; ++l) cudaFree(h->d_vph[l]);

@@ -347,9 +347,12 @@ struct FwdBitsSmem {
     float2  out[kFbTileM * 25];                               // 5000 output samples (TMA store source)
     float2  B[5 * (kFbTileM + 1) + 3];
     float2  a[kFwdMaxCar][kFbTileM + 4];                      // rotated 400 kS/s samples m0-4 .. m0+199
-    float2  resp[kFwdMaxCar][2][kFbRespLen];
+    float2  RW[kFwdMaxCar][kFbMPerBit];                       // grouped response tables (kFbFastLen)
+    float2  JW[kFwdMaxCar][kFbMPerBit];
+    float   I3[kFwdMaxCar][3][8][kFbMPerBit];
     float2  Wq[kFwdMaxCar][kFbTileBits + 1];                  // mixer phasor at the start of bits q0-1 .. q0+4
-    uint8_t bits[kFwdMaxCar][kFbTileBits + kFbHistBits + 1 + 3];   // bits q0-10 .. q0+4
+    uint32_t bval[kFwdMaxCar];                                // bit k = value of bit q0-10+k (0 where muted)
+    uint32_t bmute[kFwdMaxCar];                               // bit k = bit q0-10+k is muted (0xFF)
 };
 
 size_t fwd_bits_smem_bytes() { return sizeof(FwdBitsSmem); }
@@ -359,17 +362,24 @@ __global__ void __launch_bounds__(kFwdThreads, 3) fwd_bits_kernel(const __grid_c
     FwdBitsSmem *sm = reinterpret_cast<FwdBitsSmem *>(smem_raw);
     const int t = threadIdx.x;
     const uint32_t ntiles = (p.nbits + kFbTileBits - 1) / kFbTileBits;
-    for (int i = t; i < p.ncar * 2 * kFbRespLen; i += kFwdThreads) (&sm->resp[0][0][0])[i] = p.resp[i];
+    for (int i = t; i < p.ncar * kFbFastLen; i += kFwdThreads) {
+        const int c = i / kFbFastLen, k = i - c * kFbFastLen;
+        const float v = p.fast[i];
+        if (k < 2 * kFbMPerBit) (&sm->RW[c][0].x)[k] = v;
+        else if (k < 4 * kFbMPerBit) (&sm->JW[c][0].x)[k - 2 * kFbMPerBit] = v;
+        else (&sm->I3[c][0][0][0])[k - 4 * kFbMPerBit] = v;
+    }
 
-    // the bits a tile needs (15 per carrier) are fetched one tile ahead, so their global-load latency hides behind a tile of work
-    constexpr int kNB = kFbTileBits + kFbHistBits + 1;             // 15: bits q0-10 .. q0+4
+    // the bits a tile needs (15 per carrier: q0-10 .. q0+4) are fetched one tile ahead by lanes 0..14 of warp c, so their
+    // global-load latency hides behind a tile of work; a ballot turns them into a value mask and a mute mask per carrier
+    constexpr int kNB = kFbTileBits + kFbHistBits + 1;             // 15
+    const int fc = t >> 5, fk = t & 31;
     auto fetch_bit = [&](uint32_t tile_) -> uint8_t {
-        if (t >= p.ncar * kNB || tile_ >= ntiles) return 0xFF;
-        const int c = t / kNB, k = t - c * kNB;
-        const long q = (long)tile_ * kFbTileBits - (kFbHistBits + 1) + k;
+        if (fc >= p.ncar || fk >= kNB || tile_ >= ntiles) return 0xFF;
+        const long q = (long)tile_ * kFbTileBits - (kFbHistBits + 1) + fk;
         if (q >= (long)p.nbits) return 0xFF;
-        if (q >= 0) return p.bits[c][q];
-        if (q >= -(long)kFbHistBits) return p.hbits[c][kFbHistBits + q];
+        if (q >= 0) return p.bits[fc][q];
+        if (q >= -(long)kFbHistBits) return p.hbits[fc][kFbHistBits + q];
         return 0xFF;
     };
     uint8_t bit_next = fetch_bit(blockIdx.x);
@@ -377,12 +387,13 @@ __global__ void __launch_bounds__(kFwdThreads, 3) fwd_bits_kernel(const __grid_c
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long q0 = (long)tile * kFbTileBits;                  // first bit of the tile (call-local)
         const int nvalid = (int)((long)p.nbits - q0 < kFbTileBits ? (long)p.nbits - q0 : kFbTileBits);
-        // ---- bits q0-10 .. q0+4 and the per-bit mixer phasors
-        if (t < p.ncar * kNB) {
-            const int c = t / kNB, k = t - c * kNB;
-            sm->bits[c][k] = bit_next;
-        } else if (t >= 64 && t < 64 + p.ncar * (kFbTileBits + 1)) {
-            const int idx = t - 64, c = idx / (kFbTileBits + 1), k = idx - c * (kFbTileBits + 1);
+        // ---- bit masks and the per-bit mixer phasors
+        if (fc < kFwdMaxCar) {                                      // warps 0..2, whole warps: ballots are convergent
+            const uint32_t val = __ballot_sync(0xffffffffu, bit_next == 1);
+            const uint32_t mut = __ballot_sync(0xffffffffu, bit_next > 1);
+            if (fk == 0 && fc < p.ncar) { sm->bval[fc] = val & 0x7FFFu; sm->bmute[fc] = mut & 0x7FFFu; }
+        } else if (t >= 96 && t < 96 + p.ncar * (kFbTileBits + 1)) {
+            const int idx = t - 96, c = idx / (kFbTileBits + 1), k = idx - c * (kFbTileBits + 1);
             const uint32_t qabs = (uint32_t)(p.bit_base + (unsigned long long)(q0 - 1 + k));
             sm->Wq[c][k] = sincos_phase(qabs * p.fcw_mix1000[c]);
         }
@@ -394,18 +405,35 @@ __global__ void __launch_bounds__(kFwdThreads, 3) fwd_bits_kernel(const __grid_c
             const int mrel = t - 4;                                 // relative to the tile's first sample
             const int qrel = mrel >= 0 ? mrel / kFbMPerBit : -1;     // bit containing it, relative to q0
             const int u0 = mrel - qrel * kFbMPerBit;                // 0..39
+            const int k0 = qrel + kFbHistBits + 1;                  // its index in the tile's bit window (9..14)
 #pragma unroll
             for (int c = 0; c < kFwdMaxCar; ++c) {
                 if (c < p.ncar) {
-                    float2 acc = make_float2(0.f, 0.f);
-                    const uint8_t *bq = &sm->bits[c][qrel + kFbHistBits + 1];      // bit q0 + qrel
-#pragma unroll
-                    for (int d = 0; d < kFbRespBits; ++d) {
-                        const uint8_t b = bq[-d];
-                        if (b <= 1) acc = add2(acc, sm->resp[c][b][u0 + kFbMPerBit * d]);
+                    // the path is chosen from the sample's OWN nine bits, so a sample's value does not depend on where the
+                    // tile (i.e. the call) boundaries fall: bit-identical under any chunking
+                    const uint32_t mute = (sm->bmute[c] >> (k0 - 8)) & 0x1FFu;
+                    float2 v = make_float2(0.f, 0.f);
+                    if (mute == 0u) {
+                        // nothing muted: real part is data-independent, imaginary part three bits per lookup.
+                        // window bit i <-> response slot d = 8 - i
+                        const uint32_t w = (sm->bval[c] >> (k0 - 8)) & 0x1FFu;
+                        float im = sm->I3[c][0][w & 7u][u0];
+                        im = __fadd_rn(im, sm->I3[c][1][(w >> 3) & 7u][u0]);
+                        im = __fadd_rn(im, sm->I3[c][2][(w >> 6) & 7u][u0]);
+                        v = cmul(fma2(splat(im), sm->JW[c][u0], sm->RW[c][u0]), sm->Wq[c][qrel + 1]);
+                    } else if (mute != 0x1FFu) {
+                        // a mute transition inside the window (stream start, fvc/audio switch-over): per-bit walk
+                        const uint32_t val = sm->bval[c], mu = sm->bmute[c];
+                        float2 acc = make_float2(0.f, 0.f);
+                        const float2 *R = p.resp + (size_t)c * 2 * kFbRespLen;
+#pragma unroll 1
+                        for (int d = 0; d < kFbRespBits; ++d) {
+                            const int k = k0 - d;
+                            if (!((mu >> k) & 1u)) acc = add2(acc, __ldg(&R[((val >> k) & 1u) * kFbRespLen + u0 + kFbMPerBit * d]));
+                        }
+                        v = cmul(acc, cmul(sm->Wq[c][qrel + 1], p.w40[c][u0]));
                     }
-                    const float2 W = cmul(sm->Wq[c][qrel + 1], p.w40[c][u0]);
-                    sm->a[c][t] = cmul(acc, W);
+                    sm->a[c][t] = v;
                 }
             }
         }

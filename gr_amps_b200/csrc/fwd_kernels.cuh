@@ -87,11 +87,19 @@ constexpr int kFbRespBits  = 9;                  // bits whose response overlaps
 constexpr int kFbRespLen   = kFbRespBits * kFbMPerBit;   // 360
 constexpr int kFbHistBits  = 9;                  // bits of history a call needs from the previous one
 constexpr int kFbTileM     = kFbTileBits * kFbMPerBit;   // 200
+// Grouped form of the per-bit response, used while none of a tile's bits is muted.  A Manchester 1 is the mirror image of
+// a 0, so its FM waveform -- and, the interpolator taps being real, its response -- is the complex conjugate: R1 = conj(R0).
+// The real part of a 400 kS/s sample therefore does not depend on the data at all, and the imaginary part is a signed sum
+// that is looked up three bits at a time.  Per carrier: RW[40] = (sum_d Re R0[u+40d]) * w40[u] (float2), JW[40] = j w40[u]
+// (float2), I3[3][8][40] = sum_{k<3} (+-) Im R0[u + 40 (8 - 3G - k)] (float), sign - where bit k of the pattern is 1.
+constexpr int kFbFastLen   = 2 * 2 * kFbMPerBit + 3 * 8 * kFbMPerBit;   // 1120 floats
 
 struct FwdBitsParams {
     const uint8_t *bits[kFwdMaxCar];             // this call's bits
     const uint8_t *hbits[kFwdMaxCar];            // previous call's last kFbHistBits bits (0xFF at stream start)
     const float2  *resp;                         // [ncar][2][kFbRespLen] response of the x4 interpolator to one Manchester bit
+                                                 // (global memory; only tiles that straddle a mute transition walk it)
+    const float   *fast;                         // [ncar][kFbFastLen] grouped tables of the same response (see kFbFastLen)
     float2        *out;
     uint32_t       nbits;
     int            ncar;
