@@ -391,9 +391,60 @@ def main():
     if old_affinity is not None:
         os.sched_setaffinity(0, old_affinity)              # the CPU baseline below uses every core again
 
-    # ---- secondary: the forward path (config 3 / the FOCC half of config 4) on every rank's GPU
-    del host, batch
+    # ---- secondary: the same workload with sc16 input (AMPS_RX_INPUT_SC16: the USRP's wire format, 4 B per sample over
+    #      PCIe and out of HBM, converted in the front kernel).  Reported beside the fc32 numbers, never instead of them.
+    del host
     rx.close(); rx2.close()
+    SC16_SCALE = 1.0 / 8192.0                               # +-4.0 full scale: signal 0.5 + wideband noise sigma 0.65
+    b16 = torch.clamp(torch.round(batch * (1.0 / SC16_SCALE)), -32768, 32767).to(torch.int16)
+    del batch
+    torch.cuda.empty_cache()
+    rx3 = capi.ReccIq(max_samples=n, center_freq=center, device=local_rank, max_bursts=min(nper * 26, 65536), time_kernels=True,
+                      sc16=True, sc16_scale=SC16_SCALE)
+    for _ in range(3):
+        rx3.submit_dev(b16.data_ptr(), n, stream.cuda_stream)
+    _, _, _, c3 = rx3.peek()
+    rx3.consume(c3)
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sc_steps = 20
+    s0.record(stream)
+    for _ in range(sc_steps):
+        rx3.submit_dev(b16.data_ptr(), n, stream.cuda_stream)
+    ring3, ring3_len, first3, count3 = rx3.peek()
+    s1.record(stream)
+    barrier()
+    sc_ms = s0.elapsed_time(s1)
+    good3 = sum(1 for i in range(count3) if ring3[(first3 + i) % ring3_len].decoded.min == expect_min
+                and list(ring3[(first3 + i) % ring3_len].decoded.valid) == [1] * 7)
+    if good3 != count3 or count3 < sc_steps * nper - 2:
+        raise SystemExit("bench.py: sc16 parity gate failed: %d bursts, %d good" % (count3, good3))
+    rx3.consume(count3)
+    sc_front_ms = float(np.mean(rx3.front_times_ms(256)[-sc_steps:]))
+    sc_total, sc_ms_max = multi.whole_job_throughput(float(sc_steps) * n, sc_ms, dev)
+    old_affinity = _bind_near_gpu(local_rank)
+    host16 = torch.empty(b16.shape, dtype=torch.int16, pin_memory=True)
+    host16.copy_(b16)
+    torch.cuda.synchronize()
+    got.clear()
+    for _ in range(2):
+        rx3.work_ptr(host16.data_ptr(), n, cb)
+    got.clear()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        rx3.work_ptr(host16.data_ptr(), n, cb)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    sc_e2e_samples, sc_e2e_sec = multi.whole_job_throughput(float(e2e_steps) * n, t1 - t0, dev)
+    if len(got) < e2e_steps * nper - 2 or any(m != expect_min for m in got):
+        raise SystemExit("bench.py: sc16 e2e parity gate failed (%d bursts)" % len(got))
+    if old_affinity is not None:
+        os.sched_setaffinity(0, old_affinity)
+    del host16, b16
+    rx3.close()
+
+    # ---- secondary: the forward path (config 3 / the FOCC half of config 4) on every rank's GPU
     torch.cuda.empty_cache()
     barrier()
     fwd_n, fwd_ms = measure_fwd(local_rank, 20, 3, bits=True)
@@ -448,6 +499,12 @@ def main():
         "e2e": {"value": e2e_samples / e2e_sec / 1e6, "unit": "Msamples/s",
                 "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": int(rec_bytes), "steps": e2e_steps,
                 "api": "amps_recc_iq_work (pinned host buffer, burst callbacks)"},
+        "sc16_input": {"note": "same workload, samples as interleaved int16 I,Q (AMPS_RX_INPUT_SC16, the USRP wire format): 4 B/sample over PCIe and from HBM, "
+                               "converted in the front kernel; bit-identical to the fc32 path on the converted floats (tests/test_rx_sc16_gpu.py)",
+                       "value": sc_total / (sc_ms_max * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": sc_ms_max / sc_steps,
+                       "front_launch_ms": sc_front_ms, "front_hbm_frac": (n * 4.0036) / (sc_front_ms * 1e-3) / 1e9 / peak,
+                       "e2e": {"value": sc_e2e_samples / sc_e2e_sec / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": n * 4,
+                               "d2h_bytes_per_step": int(rec_bytes), "steps": e2e_steps, "api": "amps_recc_iq_work_sc16"}},
         "forward": {"metric": "Msamples/s out of the fused forward path (config 3: FOCC + 2 FVC carriers per GPU, data-bit input)",
                     "value": fwd_total / (fwd_ms_max * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": fwd_ms_max,
                     "hbm_frac": 8.03 * fwd_n / (fwd_ms * 1e-3) / 1e9 / peak},
@@ -473,7 +530,10 @@ if __name__ == "__main__":
     _real_stdout = _only_json_on_stdout()
     _print = print
 
-    def print(*a, **k):            # noqa: A001 -- every print() in this module is the JSON line
+    def print(*a, **k):            # noqa: A001 -- a bare print() in this module is the JSON line; diagnostics name sys.stderr
+        if k.get("file") not in (None, sys.stdout):
+            _print(*a, **k)
+            return
         k.pop("file", None)
         _print(*a, file=_real_stdout, **k)
         _real_stdout.flush()

@@ -64,7 +64,7 @@ class ReccIqParams(C.Structure):
     _fields_ = [
         ("samp_rate", C.c_double), ("center_freq", C.c_double), ("device", C.c_int),
         ("max_samples", C.c_uint32), ("max_bursts", C.c_uint32), ("flags", C.c_uint32),
-        ("lpf_taps", f32p), ("n_lpf_taps", C.c_uint32),
+        ("lpf_taps", f32p), ("n_lpf_taps", C.c_uint32), ("sc16_scale", C.c_float),
     ]
 
 
@@ -88,12 +88,13 @@ BLOB_CB = C.CFUNCTYPE(None, u8p, C.c_void_p)
 RX_DUMP_BASEBAND = 1
 RX_TIME_KERNELS = 2
 RX_TIMING_MM = 4
+RX_INPUT_SC16 = 8
 
 # every symbol include/amps_b200.h declares
 EXPORTS = [
     "amps_b200_version", "amps_b200_strerror", "amps_b200_last_error", "amps_b200_device_count", "amps_b200_abi_sizes",
     "amps_recc_iq_create", "amps_recc_iq_destroy", "amps_recc_iq_reset", "amps_recc_iq_work",
-    "amps_recc_iq_submit_dev", "amps_recc_iq_collect", "amps_recc_iq_peek", "amps_recc_iq_consume", "amps_recc_iq_poll", "amps_recc_iq_granularity", "amps_recc_iq_read_demod",
+    "amps_recc_iq_submit_dev", "amps_recc_iq_work_sc16", "amps_recc_iq_submit_sc16_dev", "amps_recc_iq_collect", "amps_recc_iq_peek", "amps_recc_iq_consume", "amps_recc_iq_poll", "amps_recc_iq_granularity", "amps_recc_iq_read_demod",
     "amps_recc_iq_read_baseband", "amps_recc_iq_stats", "amps_recc_iq_front_times", "amps_recc_iq_get_taps",
     "amps_recc_decode_create", "amps_recc_decode_destroy", "amps_recc_decode_burst", "amps_recc_decode_bursts",
     "amps_recc_create", "amps_recc_destroy", "amps_recc_work", "amps_recc_work_chunks",
@@ -124,6 +125,8 @@ def lib() -> C.CDLL:
     L.amps_recc_iq_reset.argtypes = [C.c_void_p]
     L.amps_recc_iq_work.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, BURST_CB, C.c_void_p]
     L.amps_recc_iq_submit_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.amps_recc_iq_work_sc16.argtypes = L.amps_recc_iq_work.argtypes
+    L.amps_recc_iq_submit_sc16_dev.argtypes = L.amps_recc_iq_submit_dev.argtypes
     L.amps_recc_iq_collect.argtypes = [C.c_void_p, C.POINTER(Burst), C.c_int, C.POINTER(C.c_int)]
     L.amps_recc_iq_granularity.argtypes = [C.c_void_p]
     L.amps_recc_iq_peek.argtypes = [C.c_void_p, C.POINTER(C.POINTER(Burst)), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
@@ -188,12 +191,15 @@ class ReccIq:
     """Fused RECC receive path on IQ (amps_recc_iq_*)."""
 
     def __init__(self, max_samples: int, center_freq=-160e3, samp_rate=10e6, device=0, max_bursts=256,
-                 dump_baseband=False, lpf_taps: np.ndarray | None = None, time_kernels=False, timing_mm=False):
+                 dump_baseband=False, lpf_taps: np.ndarray | None = None, time_kernels=False, timing_mm=False,
+                 sc16=False, sc16_scale=0.0):
         self._taps = None if lpf_taps is None else np.ascontiguousarray(lpf_taps, dtype=np.float32)
         p = ReccIqParams(samp_rate, center_freq, device, max_samples, max_bursts,
-                         (RX_DUMP_BASEBAND if dump_baseband else 0) | (RX_TIME_KERNELS if time_kernels else 0) | (RX_TIMING_MM if timing_mm else 0),
+                         (RX_DUMP_BASEBAND if dump_baseband else 0) | (RX_TIME_KERNELS if time_kernels else 0) | (RX_TIMING_MM if timing_mm else 0)
+                         | (RX_INPUT_SC16 if sc16 else 0),
                          None if self._taps is None else self._taps.ctypes.data_as(f32p),
-                         0 if self._taps is None else len(self._taps))
+                         0 if self._taps is None else len(self._taps), sc16_scale)
+        self.sc16 = sc16
         self.h = C.c_void_p()
         check(lib().amps_recc_iq_create(C.byref(p), C.byref(self.h)))
         self.granularity = lib().amps_recc_iq_granularity(self.h)
@@ -210,8 +216,11 @@ class ReccIq:
         check(lib().amps_recc_iq_reset(self.h))
 
     def work(self, iq: np.ndarray) -> list[Burst]:
-        """Host-buffer call; iq complex64 (or its float32 view).  Returns the bursts published."""
+        """Host-buffer call; iq complex64 (or its float32 view), or interleaved int16 I,Q for an sc16 handle.
+        Returns the bursts published."""
         iq = np.ascontiguousarray(iq)
+        if self.sc16 != (iq.dtype == np.int16):
+            raise TypeError("sc16 handles take int16 I,Q; fc32 handles take complex64 / float32")
         n = iq.size if iq.dtype == np.complex64 else iq.size // 2
         got: list[Burst] = []
 
@@ -221,14 +230,17 @@ class ReccIq:
             got.append(b)
 
         cb = BURST_CB(on)
-        check(lib().amps_recc_iq_work(self.h, iq.ctypes.data_as(C.c_void_p), n, cb, None))
+        fn = lib().amps_recc_iq_work_sc16 if self.sc16 else lib().amps_recc_iq_work
+        check(fn(self.h, iq.ctypes.data_as(C.c_void_p), n, cb, None))
         return got
 
     def work_ptr(self, host_ptr: int, nsamples: int, cb=None):
-        check(lib().amps_recc_iq_work(self.h, C.c_void_p(host_ptr), nsamples, cb or C.cast(None, BURST_CB), None))
+        fn = lib().amps_recc_iq_work_sc16 if self.sc16 else lib().amps_recc_iq_work
+        check(fn(self.h, C.c_void_p(host_ptr), nsamples, cb or C.cast(None, BURST_CB), None))
 
     def submit_dev(self, dev_ptr: int, nsamples: int, stream: int = 0):
-        check(lib().amps_recc_iq_submit_dev(self.h, C.c_void_p(dev_ptr), nsamples, C.c_void_p(stream)))
+        fn = lib().amps_recc_iq_submit_sc16_dev if self.sc16 else lib().amps_recc_iq_submit_dev
+        check(fn(self.h, C.c_void_p(dev_ptr), nsamples, C.c_void_p(stream)))
 
     def collect(self, max_bursts: int | None = None) -> list[Burst]:
         m = max_bursts or self.max_bursts

@@ -27,8 +27,10 @@ struct amps_recc_iq {
     uint32_t     decim = kD1 * kD2;      // input samples per demodulated sample
 
     RxFrontParams fp{};                  // constant part filled at create
-    float2      *d_stage = nullptr;      // host path: [carry | new chunk]
-    float2      *d_tail[2] = {nullptr, nullptr};
+    bool         sc16 = false;           // AMPS_RX_INPUT_SC16: interleaved int16 I/Q instead of float
+    size_t       isz = sizeof(float2);   // bytes per complex input sample (8 or 4)
+    uint8_t     *d_stage = nullptr;      // host path: [carry | new chunk]
+    uint8_t     *d_tail[2] = {nullptr, nullptr};
     int          tail_cur = 0;
     float       *d_dring = nullptr;
     uint32_t    *d_hring = nullptr;      // hard decisions (d >= 0), 1 bit per demod sample, same ring indexing
@@ -89,10 +91,10 @@ static int rx_alloc(amps_recc_iq *h) {
     // two calls' worth: the detection of call k overlaps the front kernel of call k+1
     while (cap < 2 * max_d + (size_t)kSpan + 4096) cap <<= 1;
     h->dmask = (uint32_t)(cap - 1);
-    CK(cudaMalloc(&h->d_stage, ((size_t)h->max_samples + h->pass_in) * sizeof(float2)));
+    CK(cudaMalloc(&h->d_stage, ((size_t)h->max_samples + h->pass_in) * h->isz));
     for (int i = 0; i < 2; ++i) {
-        CK(cudaMalloc(&h->d_tail[i], (size_t)h->hist * sizeof(float2)));
-        CK(cudaMemset(h->d_tail[i], 0, (size_t)h->hist * sizeof(float2)));
+        CK(cudaMalloc(&h->d_tail[i], (size_t)h->hist * h->isz));
+        CK(cudaMemset(h->d_tail[i], 0, (size_t)h->hist * h->isz));
     }
     CK(cudaMalloc(&h->d_dring, cap * sizeof(float)));
     CK(cudaMemset(h->d_dring, 0, cap * sizeof(float)));
@@ -154,6 +156,8 @@ extern "C" int amps_recc_iq_create(const amps_recc_iq_params *params, amps_recc_
     h->max_records = params->max_bursts ? params->max_bursts : 256;
     h->flags = params->flags;
     h->mm_mode = (params->flags & AMPS_RX_TIMING_MM) != 0;
+    h->sc16 = (params->flags & AMPS_RX_INPUT_SC16) != 0;
+    h->isz = h->sc16 ? sizeof(short2) : sizeof(float2);
     { const char *e = std::getenv("AMPS_RX_SERIAL"); h->serial = e && e[0] == '1'; }
     { const char *e = std::getenv("AMPS_RX_FRONT_ONLY"); h->front_only = e && e[0] == '1'; }
     { const char *e = std::getenv("AMPS_RX_DIAG"); h->diag = e ? std::atoi(e) : 0; }
@@ -163,6 +167,7 @@ extern "C" int amps_recc_iq_create(const amps_recc_iq_params *params, amps_recc_
 
     std::memset(&h->fp, 0, sizeof h->fp);
     h->fp.fcw25 = (uint32_t)(25u * h->fcw);
+    h->fp.in_scale = params->sc16_scale != 0.0f ? params->sc16_scale : 1.0f / 32768.0f;
     nco_block_table(h->fcw, kD1, reinterpret_cast<float *>(h->fp.w));
     std::vector<float> cic;
     cic3_taps(kD1, cic);
@@ -199,7 +204,7 @@ extern "C" int amps_recc_iq_reset(amps_recc_iq *h) {
     if (!h) return set_error(AMPS_E_INVAL, "null handle");
     CK(cudaSetDevice(h->device));
     CK(cudaDeviceSynchronize());
-    for (int i = 0; i < 2; ++i) CK(cudaMemset(h->d_tail[i], 0, (size_t)h->hist * sizeof(float2)));
+    for (int i = 0; i < 2; ++i) CK(cudaMemset(h->d_tail[i], 0, (size_t)h->hist * h->isz));
     CK(cudaMemset(h->d_state, 0, sizeof(RxState)));
     CK(cudaMemset(h->d_dring, 0, ((size_t)h->dmask + 1) * sizeof(float)));
     if (h->mm_mode) { int rc = mm_reset(h); if (rc != AMPS_OK) return rc; }
@@ -213,7 +218,7 @@ extern "C" int amps_recc_iq_reset(amps_recc_iq *h) {
 extern "C" int amps_recc_iq_granularity(const amps_recc_iq *h) { return h ? (int)h->pass_in : kPass; }
 
 // Enqueue everything for `npass` passes whose samples start at d_chunk.
-static int rx_enqueue(amps_recc_iq *h, const float2 *d_chunk, uint32_t npass, cudaStream_t st) {
+static int rx_enqueue(amps_recc_iq *h, const uint8_t *d_chunk, uint32_t npass, cudaStream_t st) {
     RxFrontParams p = h->fp;
     p.chunk = d_chunk;
     p.tail = h->d_tail[h->tail_cur];
@@ -226,7 +231,8 @@ static int rx_enqueue(amps_recc_iq *h, const float2 *d_chunk, uint32_t npass, cu
     p.n_base = h->samples_in;
     p.ydump = h->d_ydump;
     // whole passes per CTA, grid sized so that (nearly) every CTA gets the same count within one wave
-    p.pass_per_cta = (npass + 2u * (uint32_t)h->sm_count - 1u) / (2u * (uint32_t)h->sm_count);
+    const uint32_t resident = (uint32_t)rx_front_ctas_per_sm(h->sc16) * (uint32_t)h->sm_count;
+    p.pass_per_cta = (npass + resident - 1u) / resident;
     const int grid = (int)((npass + p.pass_per_cta - 1u) / p.pass_per_cta);
     // the demod ring holds two calls: do not overwrite what the detection of call k-2 may still read
     const int par = (int)(h->call_no & 1u);
@@ -235,13 +241,13 @@ static int rx_enqueue(amps_recc_iq *h, const float2 *d_chunk, uint32_t npass, cu
     const int  evi = (int)(h->ev_count % amps_recc_iq::kEv);
     if (timed) CK(cudaEventRecord(h->ev0[evi], st));
     p.tail_out = h->native400 ? nullptr : h->d_tail[h->tail_cur ^ 1];
-    if (h->native400) CKL(launch_rx_front400(p, grid, st));
-    else CKL(launch_rx_front(p, grid, st));
+    if (h->native400) CKL(launch_rx_front400(p, grid, st, h->sc16));
+    else CKL(launch_rx_front(p, grid, st, h->sc16));
     if (timed) { CK(cudaEventRecord(h->ev1[evi], st)); h->ev_count++; }
     h->launches++;
     // history for the next call = the tail of this one (the 10 MS/s front kernel copies it itself)
     if (h->native400)
-        CK(cudaMemcpyAsync(h->d_tail[h->tail_cur ^ 1], d_chunk + ((size_t)npass * h->pass_in - h->hist), (size_t)h->hist * sizeof(float2),
+        CK(cudaMemcpyAsync(h->d_tail[h->tail_cur ^ 1], d_chunk + ((size_t)npass * h->pass_in - h->hist) * h->isz, (size_t)h->hist * h->isz,
                            cudaMemcpyDeviceToDevice, st));
     h->tail_cur ^= 1;
     h->ydump_first = h->total_d;
@@ -287,15 +293,22 @@ static int rx_enqueue(amps_recc_iq *h, const float2 *d_chunk, uint32_t npass, cu
     return AMPS_OK;
 }
 
-extern "C" int amps_recc_iq_submit_dev(amps_recc_iq *h, const void *d_iq, size_t nsamples, void *cuda_stream) {
+static int rx_submit_dev(amps_recc_iq *h, const void *d_iq, size_t nsamples, void *cuda_stream, bool sc16) {
     if (!h || (!d_iq && nsamples)) return set_error(AMPS_E_INVAL, "null argument");
+    if (h->sc16 != sc16) return set_error(AMPS_E_STATE, sc16 ? "handle was not created with AMPS_RX_INPUT_SC16" : "handle was created with AMPS_RX_INPUT_SC16: use the _sc16 entry points");
     if (nsamples == 0) return AMPS_OK;
     if (nsamples % h->pass_in) return set_error(AMPS_E_ALIGN, "nsamples must be a multiple of amps_recc_iq_granularity()");
     if (reinterpret_cast<uintptr_t>(d_iq) & 15u) return set_error(AMPS_E_ALIGN, "d_iq must be 16-byte aligned");
     if (nsamples > h->max_samples) return set_error(AMPS_E_OVERFLOW, "nsamples exceeds max_samples");
     if (h->carry) return set_error(AMPS_E_STATE, "host-path samples are pending; reset() or keep using work()");
     CK(cudaSetDevice(h->device));
-    return rx_enqueue(h, static_cast<const float2 *>(d_iq), (uint32_t)(nsamples / h->pass_in), static_cast<cudaStream_t>(cuda_stream));
+    return rx_enqueue(h, static_cast<const uint8_t *>(d_iq), (uint32_t)(nsamples / h->pass_in), static_cast<cudaStream_t>(cuda_stream));
+}
+extern "C" int amps_recc_iq_submit_dev(amps_recc_iq *h, const void *d_iq, size_t nsamples, void *cuda_stream) {
+    return rx_submit_dev(h, d_iq, nsamples, cuda_stream, false);
+}
+extern "C" int amps_recc_iq_submit_sc16_dev(amps_recc_iq *h, const void *d_iq, size_t nsamples, void *cuda_stream) {
+    return rx_submit_dev(h, d_iq, nsamples, cuda_stream, true);
 }
 
 // Wait for the stream; afterwards records [h->consumed, h->consumed + *n_out) sit in the host ring.
@@ -359,13 +372,14 @@ extern "C" int amps_recc_iq_consume(amps_recc_iq *h, uint64_t count) {
     return AMPS_OK;
 }
 
-extern "C" int amps_recc_iq_work(amps_recc_iq *h, const float *iq_host, size_t nsamples, amps_burst_cb cb, void *user) {
+static int rx_work(amps_recc_iq *h, const void *iq_host, size_t nsamples, amps_burst_cb cb, void *user, bool sc16) {
     if (!h || (!iq_host && nsamples)) return set_error(AMPS_E_INVAL, "null argument");
+    if (h->sc16 != sc16) return set_error(AMPS_E_STATE, sc16 ? "handle was not created with AMPS_RX_INPUT_SC16" : "handle was created with AMPS_RX_INPUT_SC16: use the _sc16 entry points");
     if (nsamples > h->max_samples) return set_error(AMPS_E_OVERFLOW, "nsamples exceeds max_samples");
     CK(cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
     if (nsamples)
-        CK(cudaMemcpyAsync(h->d_stage + h->carry, iq_host, nsamples * sizeof(float2), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(h->d_stage + h->carry * h->isz, iq_host, nsamples * h->isz, cudaMemcpyHostToDevice, st));
     const size_t avail = h->carry + nsamples;
     const uint32_t npass = (uint32_t)(avail / h->pass_in);
     h->last_stream = st;
@@ -374,7 +388,7 @@ extern "C" int amps_recc_iq_work(amps_recc_iq *h, const float *iq_host, size_t n
         if (rc != AMPS_OK) return rc;
         const size_t left = avail - (size_t)npass * h->pass_in;
         if (left)
-            CK(cudaMemcpyAsync(h->d_stage, h->d_stage + (size_t)npass * h->pass_in, left * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+            CK(cudaMemcpyAsync(h->d_stage, h->d_stage + (size_t)npass * h->pass_in * h->isz, left * h->isz, cudaMemcpyDeviceToDevice, st));
         h->carry = left;
     } else {
         h->carry = avail;
@@ -388,6 +402,12 @@ extern "C" int amps_recc_iq_work(amps_recc_iq *h, const float *iq_host, size_t n
     h->consumed += n;
     h->bursts += n;
     return AMPS_OK;
+}
+extern "C" int amps_recc_iq_work(amps_recc_iq *h, const float *iq_host, size_t nsamples, amps_burst_cb cb, void *user) {
+    return rx_work(h, iq_host, nsamples, cb, user, false);
+}
+extern "C" int amps_recc_iq_work_sc16(amps_recc_iq *h, const int16_t *iq_host, size_t nsamples, amps_burst_cb cb, void *user) {
+    return rx_work(h, iq_host, nsamples, cb, user, true);
 }
 
 extern "C" int amps_recc_iq_read_demod(amps_recc_iq *h, uint64_t first, float *out, size_t n) {

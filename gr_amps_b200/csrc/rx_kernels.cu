@@ -33,21 +33,29 @@ struct PassSmem {                         // what stage 2 + demod work on (share
     float2   ylast[kTB];                  // each thread's last output of the current pass
     float2   ycarry[2];                   // last output of a pass, by pass parity
 };
+// input sample formats: fc32 (gr_complex, what the reference's flowgraph carries) and sc16 (interleaved int16 I/Q, what
+// the USRP puts on the wire before UHD's host-side conversion, grc/ampsbs.grc:3750): x = (float)int16 * in_scale
+__device__ __forceinline__ float2 to_c32(float2 v, float) { return v; }
+__device__ __forceinline__ float2 to_c32(short2 v, float s) { return make_float2(__fmul_rn((float)v.x, s), __fmul_rn((float)v.y, s)); }
+
+template <typename In>
 struct FrontSmem {
-    float2   in[kStages][kTile];          // TMA landing ring
+    In       in[kStages][kTile];          // TMA landing ring
     PassSmem ps;
     float2   pb[3][2][kTB];               // [tile % 3][P1|P2][block] rotated CIC partial sums (3 buffers: a tile reads its
                                           // own and the previous tile's, the next tile may already be writing)
     uint64_t full[kStages];
 };
 
-size_t rx_front_smem_bytes() { return sizeof(FrontSmem); }
+size_t rx_front_smem_bytes() { return sizeof(FrontSmem<float2>); }
 
-__device__ __forceinline__ void issue_tile(const RxFrontParams &p, FrontSmem *sm, long tile, int stage) {
+template <typename In>
+__device__ __forceinline__ void issue_tile(const RxFrontParams &p, FrontSmem<In> *sm, long tile, int stage) {
     // tiles with a negative index come from the history buffer (kWarmTiles tiles long)
-    const float2 *src = tile < 0 ? p.tail + (long)kHist + tile * (long)kTile : p.chunk + tile * (long)kTile;
-    mbar_expect_tx(&sm->full[stage], kTile * (uint32_t)sizeof(float2));
-    tma_load_1d(sm->in[stage], src, kTile * (uint32_t)sizeof(float2), &sm->full[stage]);
+    const In *src = tile < 0 ? static_cast<const In *>(p.tail) + (long)kHist + tile * (long)kTile
+                             : static_cast<const In *>(p.chunk) + tile * (long)kTile;
+    mbar_expect_tx(&sm->full[stage], kTile * (uint32_t)sizeof(In));
+    tma_load_1d(sm->in[stage], src, kTile * (uint32_t)sizeof(In), &sm->full[stage]);
 }
 
 __host__ __device__ constexpr int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
@@ -133,9 +141,10 @@ __device__ __forceinline__ void finish_pass(const RxFrontParams &p, PassSmem *ps
     }
 }
 
-__global__ void __launch_bounds__(kTB, 2) rx_front_kernel(const __grid_constant__ RxFrontParams p) {
+template <typename In, int kMinCtas>
+__global__ void __launch_bounds__(kTB, kMinCtas) rx_front_kernel(const __grid_constant__ RxFrontParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    FrontSmem *sm = reinterpret_cast<FrontSmem *>(smem_raw);
+    FrontSmem<In> *sm = reinterpret_cast<FrontSmem<In> *>(smem_raw);
     const int t = threadIdx.x;
 
     // history for the next call = the last kHist samples of this chunk; every CTA copies a slice (saves a memcpy node
@@ -143,8 +152,8 @@ __global__ void __launch_bounds__(kTB, 2) rx_front_kernel(const __grid_constant_
     if (p.tail_out) {
         const uint32_t per = ((uint32_t)kHist + gridDim.x - 1u) / gridDim.x;
         const uint32_t lo = blockIdx.x * per, hi = lo + per < (uint32_t)kHist ? lo + per : (uint32_t)kHist;
-        const float2 *src = p.chunk + ((size_t)p.npass * kPass - kHist);
-        for (uint32_t i = lo + (uint32_t)t; i < hi; i += kTB) p.tail_out[i] = src[i];
+        const In *src = static_cast<const In *>(p.chunk) + ((size_t)p.npass * kPass - kHist);
+        for (uint32_t i = lo + (uint32_t)t; i < hi; i += kTB) static_cast<In *>(p.tail_out)[i] = src[i];
     }
 
     uint32_t pa = blockIdx.x * p.pass_per_cta;
@@ -171,11 +180,11 @@ __global__ void __launch_bounds__(kTB, 2) rx_front_kernel(const __grid_constant_
         mbar_wait(&sm->full[s], (uint32_t)(i / kStages) & 1u);
 
         // ---- stage 1: NCO rotate + CIC^3 polyphase partial sums over this thread's 25 samples
-        const float2 *xin = sm->in[s] + kD1 * t;
+        const In *xin = sm->in[s] + kD1 * t;
         float2 P0 = make_float2(0.f, 0.f), P1 = P0, P2 = P0;
 #pragma unroll
         for (int k = 0; k < kD1; ++k) {
-            float2 u = cmul(xin[k], p.w[k]);
+            float2 u = cmul(to_c32(xin[k], p.in_scale), p.w[k]);
             P0 = fma2(splat(p.g[24 - k]), u, P0);
             P1 = fma2(splat(p.g[49 - k]), u, P1);
             if (74 - k < kNCic) P2 = fma2(splat(p.g[74 - k]), u, P2);
@@ -212,6 +221,7 @@ __global__ void __launch_bounds__(kTB, 2) rx_front_kernel(const __grid_constant_
 // quadrature_demod_cf.  At 0.4 MS/s real time this kernel is never a bottleneck (it is FFMA-bound: 150 FFMA2 per
 // 8-byte sample); it exists so that recc_iq drops into the reference flowgraph at its native rate.
 // ---------------------------------------------------------------------------------------------
+template <typename In>
 __global__ void __launch_bounds__(kTB, 4) rx_front400_kernel(const __grid_constant__ RxFrontParams p) {
     __shared__ PassSmem ps;
     const int t = threadIdx.x;
@@ -220,7 +230,7 @@ __global__ void __launch_bounds__(kTB, 4) rx_front400_kernel(const __grid_consta
     uint32_t pb = pa + p.pass_per_cta;
     if (pb > p.npass) pb = p.npass;
     auto load = [&](long L) -> float2 {                   // logical sample L of this call; L < 0 = history
-        const float2 x = L < 0 ? p.tail[(long)kPass400 + L] : p.chunk[L];
+        const float2 x = to_c32(L < 0 ? static_cast<const In *>(p.tail)[(long)kPass400 + L] : static_cast<const In *>(p.chunk)[L], p.in_scale);
         const unsigned long long nabs = p.n_base + (unsigned long long)(long long)L;    // (x is 0 where this wraps: stream start)
         const uint32_t b = (uint32_t)(nabs / kD1), k = (uint32_t)(nabs % kD1);
         return cmul(cmul(x, p.w[k]), sincos_phase(b * p.fcw25));
@@ -241,15 +251,20 @@ __global__ void __launch_bounds__(kTB, 4) rx_front400_kernel(const __grid_consta
     }
 }
 
-cudaError_t launch_rx_front400(const RxFrontParams &p, int grid, cudaStream_t st) {
-    rx_front400_kernel<<<grid, kTB, 0, st>>>(p);
+cudaError_t launch_rx_front400(const RxFrontParams &p, int grid, cudaStream_t st, bool sc16) {
+    if (sc16) rx_front400_kernel<short2><<<grid, kTB, 0, st>>>(p);
+    else rx_front400_kernel<float2><<<grid, kTB, 0, st>>>(p);
     return cudaGetLastError();
 }
 
-cudaError_t launch_rx_front(const RxFrontParams &p, int grid, cudaStream_t st) {
-    rx_front_kernel<<<grid, kTB, rx_front_smem_bytes(), st>>>(p);
+// sc16 tiles are half the size, so three CTAs fit an SM (the kernel is no longer HBM-bound at 4 B/sample)
+constexpr int kSc16Ctas = 3;
+cudaError_t launch_rx_front(const RxFrontParams &p, int grid, cudaStream_t st, bool sc16) {
+    if (sc16) rx_front_kernel<short2, kSc16Ctas><<<grid, kTB, sizeof(FrontSmem<short2>), st>>>(p);
+    else rx_front_kernel<float2, 2><<<grid, kTB, sizeof(FrontSmem<float2>), st>>>(p);
     return cudaGetLastError();
 }
+int rx_front_ctas_per_sm(bool sc16) { return sc16 ? kSc16Ctas : 2; }
 
 // ============================================================================================
 // trigger detection
@@ -775,13 +790,16 @@ cudaError_t launch_rx_mm(const float *dring, uint32_t dmask, unsigned long long 
 
 // per-device opt-in to large dynamic shared memory (call once per device after cudaSetDevice)
 cudaError_t rx_configure_device() {
-    cudaError_t e = cudaFuncSetAttribute(rx_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rx_front_smem_bytes());
+    cudaError_t e = cudaFuncSetAttribute(rx_front_kernel<float2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrontSmem<float2>));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(rx_front_kernel<short2, kSc16Ctas>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrontSmem<short2>));
     if (e != cudaSuccess) return e;
     // The side-stream kernels share SMs with the NEXT call's front kernel, whose two CTAs need 199 KB of shared memory per
     // SM.  An SM's L1/shared split is fixed while CTAs are resident: if a kernel that wants a big L1 gets there first, the
     // front CTAs wait until it has left.  Ask for the front kernel's split everywhere.
     const void *side[] = {(const void *)rx_detect_kernel, (const void *)rx_select_kernel, (const void *)rx_capture_kernel,
-                          (const void *)rx_mm_kernel, (const void *)rx_mm_recc_kernel, (const void *)rx_front_kernel};
+                          (const void *)rx_mm_kernel, (const void *)rx_mm_recc_kernel, (const void *)rx_front_kernel<float2, 2>,
+                          (const void *)rx_front_kernel<short2, kSc16Ctas>};
     for (const void *f : side) {
         e = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;

@@ -25,10 +25,10 @@ constexpr int kRowLen    = kPorchCols + kTB + 2; // pairs per row (+2: rows land
 constexpr int kPass400   = kPassTiles * kTB;     // native 400 kS/s front end: 1536 input samples per pass (no CIC stage)
 
 struct RxFrontParams {
-    const float2 *chunk;     // logical samples [0, npass*kPass)
-    const float2 *tail;      // logical samples [-kHist, 0)
+    const void   *chunk;     // logical samples [0, npass*kPass): float2 (fc32) or short2 (sc16, the USRP's wire format)
+    const void   *tail;      // logical samples [-kHist, 0), same format
     float        *dring;     // demod ring, indexed by (absolute demod index & dmask)
-    float2       *tail_out;  // 10 MS/s kernel: where to leave the next call's history (kHist samples), or nullptr
+    void         *tail_out;  // 10 MS/s kernel: where to leave the next call's history (kHist samples), or nullptr
     uint32_t     *hring;     // hard decisions d >= 0, bit (i & 31) of word ((i & dmask) >> 5)
     float2       *ydump;     // optional: complex baseband of this call (npass*kPassOut entries) or nullptr
     uint64_t      q_base;    // absolute demod index of this call's first output
@@ -38,6 +38,7 @@ struct RxFrontParams {
     unsigned long long n_base;  // 400 kS/s front end: absolute index of logical sample 0
     uint32_t      blk_base;  // absolute 25-sample block index (mod 2^32) of logical sample 0
     uint32_t      fcw25;     // NCO phase step per block (25 * fcw mod 2^32)
+    float         in_scale;  // sc16 input: x = (float)int16 * in_scale (one fp32 multiply per component)
     float2        w[kD1];    // NCO phasors inside a block
     float         g[75];     // CIC^3 taps (73 + 2 zeros)
     float         h2[300];   // channel filter (299 + pad)
@@ -85,8 +86,9 @@ constexpr int kMaxAccept = 512;    // bursts one call can publish
 
 size_t rx_front_smem_bytes();
 cudaError_t rx_configure_device();
-cudaError_t launch_rx_front(const RxFrontParams &p, int grid, cudaStream_t st);
-cudaError_t launch_rx_front400(const RxFrontParams &p, int grid, cudaStream_t st);
+cudaError_t launch_rx_front(const RxFrontParams &p, int grid, cudaStream_t st, bool sc16 = false);
+int rx_front_ctas_per_sm(bool sc16);
+cudaError_t launch_rx_front400(const RxFrontParams &p, int grid, cudaStream_t st, bool sc16 = false);
 cudaError_t launch_rx_detect(const float *dring, const uint32_t *hring, uint32_t dmask, RxState *state, Candidate *cand,
                              unsigned long long scan_lo, unsigned long long scan_hi, int max_ctas, cudaStream_t st);
 // select: sorts the candidates (cand must hold 2 x kMaxCand entries: list + sorted scratch), groups runs, picks sampling

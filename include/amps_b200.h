@@ -114,6 +114,7 @@ typedef struct amps_recc_iq_params {
     uint32_t flags;              /* AMPS_RX_* */
     const float *lpf_taps;       /* channel filter taps @400 kS/s, NULL -> firdes.low_pass(3,400e3,10e3,4.5e3,BLACKMAN) */
     uint32_t n_lpf_taps;         /* <= 299 */
+    float    sc16_scale;         /* AMPS_RX_INPUT_SC16: x = (float)int16 * sc16_scale per component; 0 -> 1/32768 */
 } amps_recc_iq_params;
 
 #define AMPS_RX_DUMP_BASEBAND 1u   /* keep the 200 kS/s complex baseband of the last call for inspection */
@@ -124,6 +125,12 @@ typedef struct amps_recc_iq_params {
                                       instead of the feed-forward detector.  One GPU thread walks the recurrence, so this mode
                                       runs at tens of Msymbols/s, not at the memory roofline.  In the burst record demod_index /
                                       sample_index are then nominal (recovered half-symbol index x 10), corr and run_length 0. */
+
+#define AMPS_RX_INPUT_SC16    8u   /* samples arrive as interleaved int16 I,Q ("sc16": what the USRP puts on the wire before UHD
+                                      converts to the fc32 stream of uhd.usrp_source, grc/ampsbs.grc:3750) through the *_sc16
+                                      entry points: 4 bytes per sample over PCIe and out of HBM instead of 8; the conversion
+                                      (float)int16 * sc16_scale happens in the front kernel.  Everything downstream is
+                                      bit-identical to feeding amps_recc_iq_work() the converted floats. */
 
 typedef void (*amps_burst_cb)(const amps_burst *burst, void *user);
 
@@ -139,10 +146,15 @@ AMPS_B200_API int amps_recc_iq_reset(amps_recc_iq *h);          /* back to strea
 AMPS_B200_API int amps_recc_iq_work(amps_recc_iq *h, const float *iq_host, size_t nsamples,
                                     amps_burst_cb cb, void *user);
 
+/* The same call for a handle created with AMPS_RX_INPUT_SC16: nsamples complex samples = 2*nsamples int16. */
+AMPS_B200_API int amps_recc_iq_work_sc16(amps_recc_iq *h, const int16_t *iq_host, size_t nsamples,
+                                         amps_burst_cb cb, void *user);
+
 /* Device-resident variant: d_iq is a device pointer (16-byte aligned) on the handle's device,
  * nsamples a multiple of amps_recc_iq_granularity(); kernels are enqueued on cuda_stream
  * (a cudaStream_t, NULL = default stream) and the call returns without synchronising. */
 AMPS_B200_API int amps_recc_iq_submit_dev(amps_recc_iq *h, const void *d_iq, size_t nsamples, void *cuda_stream);
+AMPS_B200_API int amps_recc_iq_submit_sc16_dev(amps_recc_iq *h, const void *d_iq, size_t nsamples, void *cuda_stream);
 /* Waits for the stream, copies out the bursts published since the last collect (at most max; the
  * rest stays queued). */
 AMPS_B200_API int amps_recc_iq_collect(amps_recc_iq *h, amps_burst *out, int max, int *n_out);
