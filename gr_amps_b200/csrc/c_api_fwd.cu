@@ -115,6 +115,31 @@ extern "C" int amps_fwd_create(const amps_fwd_params *p, amps_fwd **out) {
         }
         h->fp.w25[c] = make_float2(ph[50], ph[51]);
     }
+    // ---- polyphase work split over the eight warps of fwd_fused_kernel<false> (FwdParams::seg): at most three warps per
+    //      carrier (one owner + two helpers), the next warp always going to the carrier with the most tap groups per warp
+    {
+        int nslot[kFwdMaxCar] = {0, 0, 0};
+        for (int c = 0; c < h->ncar; ++c) nslot[c] = 1;
+        for (int used = h->ncar; used < kFwdThreads / 32; ++used) {
+            int best = -1;
+            for (int c = 0; c < h->ncar; ++c)
+                if (nslot[c] < 3 && (best < 0 || h->fp.ntap4[c] * nslot[best] > h->fp.ntap4[best] * nslot[c])) best = c;
+            if (best < 0) break;
+            nslot[best]++;
+        }
+        int w = 0, helper = 0;
+        for (int c = 0; c < h->ncar; ++c) {
+            const int first_helper = helper;
+            for (int sl = 0; sl < nslot[c]; ++sl, ++w) {
+                FwdParams::Seg &sg = h->fp.seg[w];
+                sg.c = (int8_t)c; sg.slot = (int8_t)sl; sg.nslot = (int8_t)nslot[c];
+                sg.hidx = (int8_t)(sl == 0 ? first_helper : helper++);
+                sg.k0 = (int16_t)((long)h->fp.ntap4[c] * sl / nslot[c]);
+                sg.k1 = (int16_t)((long)h->fp.ntap4[c] * (sl + 1) / nslot[c]);
+            }
+        }
+        for (; w < kFwdThreads / 32; ++w) { h->fp.seg[w].c = -1; h->fp.seg[w].slot = 0; h->fp.seg[w].nslot = 0; h->fp.seg[w].hidx = 0; h->fp.seg[w].k0 = h->fp.seg[w].k1 = 0; }
+    }
     // ---- Manchester-bit fast path tables: response of the x4 interpolator to one bit's 10 FM samples
     {
         std::memset(&h->bp, 0, sizeof h->bp);

@@ -128,10 +128,13 @@ cudaError_t launch_fwd_scan(const FwdScanParams &p, int ncar, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------
 struct FwdSmem {
     float2 out[kFwdTileSym * 100];             // output tile (TMA store source); its store overlaps phases 1-3a of the next tile
-    float2 B[5 * (4 * kFwdTileSym + 1) + 3];   // 2 MS/s samples (carriers mixed and summed) for m = m0-1 .. m0+251
+    float2 B[5 * (4 * kFwdTileSym + 1) + 3 + 12];   // 2 MS/s samples (carriers mixed and summed) for m = m0-1 .. m0+251;
+                                               // before that, the polyphase partial sums of the helper warps (5 x 8 x 32)
     float2 fm[kFwdMaxCar][kFwdTileSym + 1 + kFwdMaxTap4];     // FM samples for symbols i0-1-81 .. i0+62
     alignas(16) float taps[kFwdMaxCar][4 * kFwdMaxTap4];       // polyphase taps (broadcast LDS.128 instead of constant loads)
-    float2 a[kFwdMaxCar][4 * (kFwdTileSym + 1) + 16];         // 400 kS/s samples for symbols i0-1 .. i0+62 (+ slack for unrolled reads)
+    float2 a[kFwdMaxCar][4 * (kFwdTileSym + 1) + 16 + (4 * (kFwdTileSym + 1) + 16) / 8 + 1];   // 400 kS/s samples for symbols i0-1 .. i0+62
+                                               // (+ slack for unrolled reads), sample m at a_idx(m): one slot skipped every 8, so the
+                                               // polyphase warps' stride-8 stores spread over all banks
 };
 
 size_t fwd_smem_bytes() { return sizeof(FwdSmem); }
@@ -145,6 +148,7 @@ __device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+__device__ __forceinline__ int a_idx(int m) { return m + (m >> 3); }
 __device__ __forceinline__ int floor_div(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
 
 // voice legs (kVoice): the phasors a tile needs, the x25 resampler taps and the legs' rotated 400 kS/s samples
@@ -154,6 +158,7 @@ struct FwdVoiceSmem {                           // overlays FwdSmem::B, which is
     float  E[25 * kVoiceERow];
     float2 vph[kFwdVoiceLegs][kVoiceStage];
 };
+static_assert(sizeof(FwdSmem::B) >= 5 * 8 * 32 * sizeof(float2), "room for the partial sums of five helper warps");
 static_assert(sizeof(FwdVoiceSmem) <= sizeof(FwdSmem::B), "voice staging must fit into the 2 MS/s buffer it overlays");
 constexpr int kVoiceThreads = kFwdThreads - 96;                                   // warps 3..7
 constexpr int kVoiceOutPerThread = (kFwdVoiceLegs * 4 * (kFwdTileSym + 1) + kVoiceThreads - 1) / kVoiceThreads;   // 4
@@ -170,23 +175,46 @@ __global__ void __launch_bounds__(kFwdThreads, 3) fwd_fused_kernel(const __grid_
     constexpr int kFmLen = kFwdTileSym + 1 + kFwdMaxTap4;          // 145
     for (int i = t; i < kFwdMaxCar * 4 * kFwdMaxTap4; i += kFwdThreads) (&sm->taps[0][0])[i] = (&p.taps[0][0])[i];
 
+    // The symbols and phase sums a tile needs (145 per carrier: i0-82 .. i0+62) are fetched ONE TILE AHEAD into registers,
+    // two items per thread, so their global-load latency hides behind a tile of work instead of opening every tile.
+    static_assert(kFwdMaxCar * kFmLen <= 2 * kFwdThreads, "two FM items per thread");
+    int fc_[2], fk_[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int idx = t + r * kFwdThreads;
+        fc_[r] = idx < p.ncar * kFmLen ? idx / kFmLen : -1;
+        fk_[r] = idx - (fc_[r] < 0 ? 0 : fc_[r]) * kFmLen;
+    }
+    // (the two addends of a phase sum stay in separate registers until they are used: adding them here would wait for the loads)
+    auto fetch = [&](uint32_t tile_, int r, uint8_t &s_, int &Sa_, int &Sb_) {
+        s_ = 0; Sa_ = 0; Sb_ = 0;
+        const int c = fc_[r];
+        if (c < 0 || tile_ >= ntiles) return;
+        const long i = (long)tile_ * kFwdTileSym - (kFwdMaxTap4 + 1) + fk_[r];
+        if (i >= (long)p.nsym) return;
+        if (i >= 0) { s_ = p.sym[c][i]; Sa_ = p.boff[c][i / kFwdScanBlock]; Sb_ = p.sloc[c][i]; }
+        else if (i >= -(long)kFwdHistLen) { s_ = p.hsym[c][kFwdHistLen + i]; Sa_ = p.hS[c][kFwdHistLen + i]; }
+    };
+    uint8_t ns[2];
+    int nSa[2], nSb[2];
+    fetch(blockIdx.x, 0, ns[0], nSa[0], nSb[0]);
+    fetch(blockIdx.x, 1, ns[1], nSa[1], nSb[1]);
+
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long i0 = (long)tile * kFwdTileSym;                  // first new symbol of the tile
         const int nvalid = (int)((long)p.nsym - i0 < kFwdTileSym ? (long)p.nsym - i0 : kFwdTileSym);
 
         // ---- phase 1: FM samples fm[c][k] for symbol i0 - 82 + k, k < 145
-        for (int idx = t; idx < p.ncar * kFmLen; idx += kFwdThreads) {
-            const int c = idx / kFmLen, k = idx - c * kFmLen;
-            const long i = i0 - (kFwdMaxTap4 + 1) + k;
-            uint8_t s = 0;
-            int S = 0;
-            if (i >= (long)p.nsym) { s = 0; }
-            else if (i >= 0) { s = p.sym[c][i]; S = p.boff[c][i / kFwdScanBlock] + p.sloc[c][i]; }
-            else if (i >= -(long)kFwdHistLen) { s = p.hsym[c][kFwdHistLen + i]; S = p.hS[c][kFwdHistLen + i]; }
-            float2 v = make_float2(0.f, 0.f);
-            if (s != 0) v = sincos_phase((uint32_t)S * p.fcw_fm);
-            sm->fm[c][k] = v;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            if (fc_[r] >= 0) {
+                float2 v = make_float2(0.f, 0.f);
+                if (ns[r] != 0) v = sincos_phase((uint32_t)(nSa[r] + nSb[r]) * p.fcw_fm);
+                sm->fm[fc_[r]][fk_[r]] = v;
+            }
         }
+        fetch(tile + gridDim.x, 0, ns[0], nSa[0], nSb[0]);
+        fetch(tile + gridDim.x, 1, ns[1], nSa[1], nSb[1]);
         // voice: phasors for audio samples ia0 .. ia0 + 47, ia0 = floor(4 (i0 - 1) / 25) - (kFwdVoicePer - 1)
         const int ia0 = floor_div(4 * ((int)i0 - 1), 25) - (kFwdVoicePer - 1);
         if (kVoice) {
@@ -208,29 +236,48 @@ __global__ void __launch_bounds__(kFwdThreads, 3) fwd_fused_kernel(const __grid_
         //      FM sample loaded for symbol i at tap k is symbol i+1's sample at tap k+1, so each shared-memory load and
         //      each uniform 4-tap load feeds 8 FFMA2.  One warp per carrier.  The 400 kS/s samples are stored already
         //      rotated by the carrier's NCO: at[m] = a[m] e^{j phi_c(25 m)}.
-        if (t < 32 * p.ncar) {
-            const int c = t >> 5, ip = t & 31;                      // symbols i0 - 1 + 2 ip, i0 + 2 ip   (c is warp-uniform)
+        // Without voice legs all eight warps share the taps (p.seg: e.g. 49 + 81 + 81 tap groups -> 2 + 3 + 3 warps of
+        // 25..27 groups each); with voice legs the five spare warps resample the audio and each carrier keeps one warp.
+        const FwdParams::Seg sg = kVoice ? FwdParams::Seg{(int8_t)((t >> 5) < p.ncar ? (t >> 5) : -1), 0, 1, 0, 0, (int16_t)((t >> 5) < p.ncar ? p.ntap4[(t >> 5) < p.ncar ? (t >> 5) : 0] : 0)}
+                                         : p.seg[t >> 5];
+        float2 lo0 = make_float2(0.f, 0.f), lo1 = lo0, lo2 = lo0, lo3 = lo0, hi0 = lo0, hi1 = lo0, hi2 = lo0, hi3 = lo0;
+        const int ip = t & 31;                                      // symbols i0 - 1 + 2 ip, i0 + 2 ip
+        if (sg.c >= 0) {
+            const int c = sg.c;                                     // warp-uniform
             const float2 *f = &sm->fm[c][2 * ip + kFwdMaxTap4];     // fm of the first symbol of the pair
-            float2 lo0 = make_float2(0.f, 0.f), lo1 = lo0, lo2 = lo0, lo3 = lo0, hi0 = lo0, hi1 = lo0, hi2 = lo0, hi3 = lo0;
-            auto arm = [&](const float *T, int n4) {
-                float2 xh = f[1];                                   // fm[i+1 - 0]
+            const float *T = sm->taps[c];
+            float2 xh = f[1 - sg.k0];                               // fm[i+1 - k0]
 #pragma unroll 3
-                for (int k = 0; k < n4; ++k) {
-                    const float2 xl = f[-k];                        // fm[i - k] == fm[(i+1) - (k+1)]
-                    const float4 tk = *reinterpret_cast<const float4 *>(T + 4 * k);     // same address in every lane: broadcast LDS.128
-                    lo0 = fma2(splat(tk.x), xl, lo0); hi0 = fma2(splat(tk.x), xh, hi0);
-                    lo1 = fma2(splat(tk.y), xl, lo1); hi1 = fma2(splat(tk.y), xh, hi1);
-                    lo2 = fma2(splat(tk.z), xl, lo2); hi2 = fma2(splat(tk.z), xh, hi2);
-                    lo3 = fma2(splat(tk.w), xl, lo3); hi3 = fma2(splat(tk.w), xh, hi3);
-                    xh = xl;
+            for (int k = sg.k0; k < sg.k1; ++k) {
+                const float2 xl = f[-k];                            // fm[i - k] == fm[(i+1) - (k+1)]
+                const float4 tk = *reinterpret_cast<const float4 *>(T + 4 * k);     // same address in every lane: broadcast LDS.128
+                lo0 = fma2(splat(tk.x), xl, lo0); hi0 = fma2(splat(tk.x), xh, hi0);
+                lo1 = fma2(splat(tk.y), xl, lo1); hi1 = fma2(splat(tk.y), xh, hi1);
+                lo2 = fma2(splat(tk.z), xl, lo2); hi2 = fma2(splat(tk.z), xh, hi2);
+                lo3 = fma2(splat(tk.w), xl, lo3); hi3 = fma2(splat(tk.w), xh, hi3);
+                xh = xl;
+            }
+            if (!kVoice && sg.slot > 0) {                           // helper warp: hand the partial sums over
+                float2 *ps = &sm->B[(sg.hidx * 8) * 32 + ip];
+                ps[0 * 32] = lo0; ps[1 * 32] = lo1; ps[2 * 32] = lo2; ps[3 * 32] = lo3;
+                ps[4 * 32] = hi0; ps[5 * 32] = hi1; ps[6 * 32] = hi2; ps[7 * 32] = hi3;
+            }
+        }
+        if (!kVoice) __syncthreads();
+        if (sg.c >= 0 && sg.slot == 0) {
+            const int c = sg.c;
+            if (!kVoice) {
+                for (int s2 = 1; s2 < sg.nslot; ++s2) {
+                    const float2 *ps = &sm->B[((sg.hidx + s2 - 1) * 8) * 32 + ip];
+                    lo0 = add2(lo0, ps[0 * 32]); lo1 = add2(lo1, ps[1 * 32]); lo2 = add2(lo2, ps[2 * 32]); lo3 = add2(lo3, ps[3 * 32]);
+                    hi0 = add2(hi0, ps[4 * 32]); hi1 = add2(hi1, ps[5 * 32]); hi2 = add2(hi2, ps[6 * 32]); hi3 = add2(hi3, ps[7 * 32]);
                 }
-            };
-            arm(sm->taps[c], p.ntap4[c]);
+            }
             const uint32_t m8 = p.m_base + (uint32_t)(4 * (i0 - 1 + 2 * ip));
             const float2 w25 = p.w25[c];
             // each symbol starts its own phasor recurrence, so a sample's value does not depend on how symbols pair up
             float2 W = sincos_phase(m8 * p.fcw_mix25[c]);
-            float2 *a = &sm->a[c][8 * ip];
+            float2 *a = &sm->a[c][9 * ip];                          // a_idx(8 ip + j) = 9 ip + j, j < 8
             a[0] = cmul(lo0, W); W = cmul(W, w25);
             a[1] = cmul(lo1, W); W = cmul(W, w25);
             a[2] = cmul(lo2, W); W = cmul(W, w25);
@@ -274,7 +321,7 @@ __global__ void __launch_bounds__(kFwdThreads, 3) fwd_fused_kernel(const __grid_
                     if (o >= kFwdVoiceLegs * 4 * (kFwdTileSym + 1)) continue;
                     const int l = o / (4 * (kFwdTileSym + 1)), idx = o - l * 4 * (kFwdTileSym + 1);
                     const int c = p.vcar[l];
-                    if (c >= 0) sm->a[c][idx] = add2(sm->a[c][idx], vout[j]);
+                    if (c >= 0) sm->a[c][a_idx(idx)] = add2(sm->a[c][a_idx(idx)], vout[j]);
                 }
             }
             __syncthreads();
@@ -291,7 +338,7 @@ __global__ void __launch_bounds__(kFwdThreads, 3) fwd_fused_kernel(const __grid_
                 if (c < p.ncar) {
 #pragma unroll
                     for (int j = 0; j < 3; ++j) {
-                        const float2 x = sm->a[c][t + 3 - j];
+                        const float2 x = sm->a[c][a_idx(t + 3 - j)];
                         const float2 xr = splat(x.x), xi = splat(x.y);
 #pragma unroll
                         for (int r = 0; r < 5; ++r) {

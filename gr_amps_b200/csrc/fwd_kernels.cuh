@@ -46,6 +46,10 @@ struct FwdParams {
     float2         C1[kFwdMaxCar][15];           // 5 cic5[u] e^{j phi_c(5 u)}: first x5 CIC^3 stage carrying the mixer
     float          G2[15];                       // out_scale * 5 cic5[u]: second (shared) x5 CIC^3 stage
     float          taps[kFwdMaxCar][4 * kFwdMaxTap4];
+    // polyphase work split of fwd_fused_kernel<false>: warp w runs taps [k0, k1) of carrier c for all 64 symbols of the
+    // tile; slot 0 of a carrier owns the result, slots 1.. hand their partial sums over through shared memory and are
+    // added in slot order (a fixed order: a sample's value does not depend on tiling or chunking)
+    struct Seg { int8_t c, slot, nslot, hidx; int16_t k0, k1; } seg[kFwdThreads / 32];   // hidx: helper slot in smem (owner: its first helper's)
     // ---- voice legs (fwd_fused_kernel<true> only): nbfm_tx phasors @16 kS/s, x25 arb resampler, added to a carrier's
     //      400 kS/s samples before its mixer (grc/ampsbs.grc:4494-4500, 4632-4638)
     const float2  *vph[kFwdVoiceLegs];           // this call's phasors (4 nsym / 25 of them), already muted where gated
