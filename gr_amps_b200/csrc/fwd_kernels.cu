@@ -126,11 +126,15 @@ cudaError_t launch_fwd_scan(const FwdScanParams &p, int ncar, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------
 // fused modulator
 // ---------------------------------------------------------------------------------------------
+constexpr int kFmHalf = (kFwdTileSym + 1 + kFwdMaxTap4 + 1) / 2 + 1;   // 74 (odd/even halves land in different banks)
+__device__ __forceinline__ int fm_idx(int k) { return (k & 1) * kFmHalf + (k >> 1); }
 struct FwdSmem {
     float2 out[kFwdTileSym * 100];             // output tile (TMA store source); its store overlaps phases 1-3a of the next tile
     float2 B[5 * (4 * kFwdTileSym + 1) + 3 + 12];   // 2 MS/s samples (carriers mixed and summed) for m = m0-1 .. m0+251;
                                                // before that, the polyphase partial sums of the helper warps (5 x 8 x 32)
-    float2 fm[kFwdMaxCar][kFwdTileSym + 1 + kFwdMaxTap4];     // FM samples for symbols i0-1-81 .. i0+62
+    float2 fm[kFwdMaxCar][2 * kFmHalf];        // FM samples for symbols i0-1-81 .. i0+62 (145), de-interleaved: sample k sits at
+                                               // fm_idx(k) = (k & 1) * kFmHalf + (k >> 1), so the polyphase warps, whose lanes are two
+                                               // symbols apart, read consecutive slots (no bank conflicts)
     alignas(16) float taps[kFwdMaxCar][4 * kFwdMaxTap4];       // polyphase taps (broadcast LDS.128 instead of constant loads)
     float2 a[kFwdMaxCar][4 * (kFwdTileSym + 1) + 16 + (4 * (kFwdTileSym + 1) + 16) / 8 + 1];   // 400 kS/s samples for symbols i0-1 .. i0+62
                                                // (+ slack for unrolled reads), sample m at a_idx(m): one slot skipped every 8, so the
@@ -210,7 +214,7 @@ __global__ void __launch_bounds__(kFwdThreads, 3) fwd_fused_kernel(const __grid_
             if (fc_[r] >= 0) {
                 float2 v = make_float2(0.f, 0.f);
                 if (ns[r] != 0) v = sincos_phase((uint32_t)(nSa[r] + nSb[r]) * p.fcw_fm);
-                sm->fm[fc_[r]][fk_[r]] = v;
+                sm->fm[fc_[r]][fm_idx(fk_[r])] = v;
             }
         }
         fetch(tile + gridDim.x, 0, ns[0], nSa[0], nSb[0]);
@@ -244,19 +248,30 @@ __global__ void __launch_bounds__(kFwdThreads, 3) fwd_fused_kernel(const __grid_
         const int ip = t & 31;                                      // symbols i0 - 1 + 2 ip, i0 + 2 ip
         if (sg.c >= 0) {
             const int c = sg.c;                                     // warp-uniform
-            const float2 *f = &sm->fm[c][2 * ip + kFwdMaxTap4];     // fm of the first symbol of the pair
+            // fm of the pair's first symbol at tap k is sample 2 ip + 81 - k: odd samples for even k, even samples for odd k
+            const float2 *F = sm->fm[c];
             const float *T = sm->taps[c];
-            float2 xh = f[1 - sg.k0];                               // fm[i+1 - k0]
-#pragma unroll 3
-            for (int k = sg.k0; k < sg.k1; ++k) {
-                const float2 xl = f[-k];                            // fm[i - k] == fm[(i+1) - (k+1)]
+            const int base = 2 * ip + kFwdMaxTap4;
+            float2 xh = F[fm_idx(base + 1 - sg.k0)];                // fm[i+1 - k0]
+            auto tap = [&](int k, float2 xl) {                      // xl = fm[i - k] == fm[(i+1) - (k+1)]
                 const float4 tk = *reinterpret_cast<const float4 *>(T + 4 * k);     // same address in every lane: broadcast LDS.128
                 lo0 = fma2(splat(tk.x), xl, lo0); hi0 = fma2(splat(tk.x), xh, hi0);
                 lo1 = fma2(splat(tk.y), xl, lo1); hi1 = fma2(splat(tk.y), xh, hi1);
                 lo2 = fma2(splat(tk.z), xl, lo2); hi2 = fma2(splat(tk.z), xh, hi2);
                 lo3 = fma2(splat(tk.w), xl, lo3); hi3 = fma2(splat(tk.w), xh, hi3);
                 xh = xl;
+            };
+            int k = sg.k0;
+            if ((k & 1) && k < sg.k1) { tap(k, F[fm_idx(base - k)]); ++k; }
+            const float2 *pO = F + kFmHalf + ((base - k) >> 1);      // k even: odd sample (base - k), then even sample (base - k - 1)
+            const float2 *pE = F + ((base - k - 1) >> 1);
+#pragma unroll 2
+            for (; k + 1 < sg.k1; k += 2) {
+                tap(k, *pO);
+                tap(k + 1, *pE);
+                --pO; --pE;
             }
+            if (k < sg.k1) tap(k, *pO);
             if (!kVoice && sg.slot > 0) {                           // helper warp: hand the partial sums over
                 float2 *ps = &sm->B[(sg.hidx * 8) * 32 + ip];
                 ps[0 * 32] = lo0; ps[1 * 32] = lo1; ps[2 * 32] = lo2; ps[3 * 32] = lo3;
