@@ -19,6 +19,16 @@ PY
 N=$(cat /tmp/san/n.txt)
 QA=gr_amps_b200/host/qa_blocks
 for tool in memcheck racecheck synccheck; do
+  # the Manchester-bit fast path (fwd_bits_kernel) through the forward_iq composite block
+  timeout 1200 compute-sanitizer --tool $tool --error-exitcode 9 $QA txblock 6000 /tmp/san/tx.bin > gpurun_out/sanitize_txblock_$tool.log 2>&1
+  echo "txblock $tool rc=$? $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' gpurun_out/sanitize_txblock_$tool.log | tail -1)"
+  if [ "${FWD_ONLY:-0}" = "1" ]; then
+    timeout 1200 compute-sanitizer --tool $tool --error-exitcode 9 $QA fwd 20000 /tmp/san/fwd.bin > gpurun_out/sanitize_fwd_$tool.log 2>&1
+    echo "fwd  $tool rc=$? $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' gpurun_out/sanitize_fwd_$tool.log | tail -1)"
+    timeout 1200 compute-sanitizer --tool $tool --error-exitcode 9 $QA fwd 20000 /tmp/san/fwdv.bin voice > gpurun_out/sanitize_voice_$tool.log 2>&1
+    echo "voice $tool rc=$? $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' gpurun_out/sanitize_voice_$tool.log | tail -1)"
+    continue
+  fi
   if [ "${ONLY_NEW:-0}" != "1" ]; then
   timeout 1200 compute-sanitizer --tool $tool --error-exitcode 9 $QA loop /tmp/san/iq.bin $N 262144 87970 /tmp/san/out > gpurun_out/sanitize_$tool.log 2>&1
   echo "loop $tool rc=$? $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' gpurun_out/sanitize_$tool.log | tail -1)"
