@@ -20,7 +20,7 @@ static void word(const char *name, const Word28 &w, bool last = false) {
 }
 static void taps(const char *name, const std::vector<float> &t, bool last = false) {
     std::printf("  \"%s\": [", name);
-    for (size_t i = 0; i < t.size(); i++) std::printf("%s%.9g", i ? ", " : "", (double)t[i]);
+    for (size_t i = 0; i < t.size(); i++) std::printf("%s%.17g", i ? ", " : "", (double)t[i]);
     std::printf("]%s\n", last ? "" : ",");
 }
 
@@ -51,6 +51,7 @@ int main() {
     std::vector<float> cic;
     cic3_taps(25, cic);
     std::printf(" \"taps\": {\n");
+    taps("gr_qa_firdes_low_pass", firdes_low_pass(1.0, 1.0, 0.4, 0.2, WIN_HAMMING));     // GNU Radio qa_firdes.py test_low_pass
     taps("lpf", firdes_low_pass(3.0, 400e3, 10e3, 4500.0, WIN_BLACKMAN));
     taps("focc_interp", firdes_low_pass(1.0, 400e3, 10e3, 5e3, WIN_HAMMING));
     taps("fvc_interp", firdes_low_pass(1.0, 400e3, 10e3, 3e3, WIN_HAMMING));

@@ -47,6 +47,17 @@ def test_frame_and_train_layouts(proto, oracle):
     assert proto["fvc_train"] == "".join(str(int(x)) for x in (b.reshape(-1, 2)[:, 1] == 1))
 
 
+def test_firdes_reproduces_gnuradios_own_qa_vector(proto, oracle):
+    """firdes.low_pass is GNU Radio code that is not in the reference tree; GNU Radio's QA suite publishes the taps of
+    low_pass(1, 1, 0.4, 0.2) (qa_firdes.py, test_low_pass).  Both the product's design code and the oracle's restatement
+    reproduce them bit for bit (float32)."""
+    kat = json.load(open(os.path.join(ROOT, "tests", "golden", "kat_gnuradio_firdes.json")))
+    want = np.asarray(kat["taps"], np.float64).astype(np.float32)
+    assert np.array_equal(want.astype(np.float64), np.asarray(kat["taps"]))       # the published values ARE float32 numbers
+    assert np.array_equal(np.float32(proto["taps"]["gr_qa_firdes_low_pass"]), want)
+    assert np.array_equal(oracle.firdes_low_pass(1.0, 1.0, 0.4, 0.2, 0), want)
+
+
 def test_filter_designs_match_oracle(proto, oracle):
     L = oracle.lib()
     assert proto["fcw"] == [L.orc_nco_fcw(-160e3, 10e6), L.orc_nco_fcw(-160e3, 400e3)]
