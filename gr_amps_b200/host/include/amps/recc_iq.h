@@ -12,6 +12,8 @@ public:
     typedef std::shared_ptr<recc_iq> sptr;
     // mm_timing: symbol timing by the reference graph's clock_recovery_mm_ff -> binary_slicer_fb -> amps.recc tail
     // (AMPS_RX_TIMING_MM) instead of the feed-forward trigger detector
-    static sptr make(double samp_rate, double center_freq, int device = 0, bool mm_timing = false);
+    // sc16: the input stream is interleaved int16 I,Q (item size 4: the USRP's wire format, uhd stream_args cpu_format
+    // "sc16") instead of gr_complex; converted on the GPU as (float)int16 / 32768 (AMPS_RX_INPUT_SC16)
+    static sptr make(double samp_rate, double center_freq, int device = 0, bool mm_timing = false, bool sc16 = false);
 };
 }}

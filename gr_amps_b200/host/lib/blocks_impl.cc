@@ -99,16 +99,17 @@ int recc_impl::work(int noutput_items, gr_vector_const_void_star &input_items, g
 }
 
 // ------------------------------------------------------------------ recc_iq (new sibling block)
-recc_iq::sptr recc_iq::make(double samp_rate, double center_freq, int device, bool mm_timing) {
-    return gnuradio::get_initial_sptr(new recc_iq_impl(samp_rate, center_freq, device, mm_timing));
+recc_iq::sptr recc_iq::make(double samp_rate, double center_freq, int device, bool mm_timing, bool sc16) {
+    return gnuradio::get_initial_sptr(new recc_iq_impl(samp_rate, center_freq, device, mm_timing, sc16));
 }
-recc_iq_impl::recc_iq_impl(double samp_rate, double center_freq, int device, bool mm_timing)
-    : gr::sync_block("recc_iq", gr::io_signature::make(1, 1, sizeof(std::complex<float>)), gr::io_signature::make(0, 0, 0)), d_h(NULL) {
+recc_iq_impl::recc_iq_impl(double samp_rate, double center_freq, int device, bool mm_timing, bool sc16)
+    : gr::sync_block("recc_iq", gr::io_signature::make(1, 1, sc16 ? 2 * sizeof(short) : sizeof(std::complex<float>)), gr::io_signature::make(0, 0, 0)),
+      d_h(NULL), d_sc16(sc16) {
     amps_recc_iq_params p;
     std::memset(&p, 0, sizeof p);
     p.samp_rate = samp_rate; p.center_freq = center_freq; p.device = device;
     p.max_samples = 1u << 22;                      // the scheduler never hands a block more than this at once
-    p.flags = mm_timing ? AMPS_RX_TIMING_MM : 0u;
+    p.flags = (mm_timing ? AMPS_RX_TIMING_MM : 0u) | (sc16 ? AMPS_RX_INPUT_SC16 : 0u);
     must(amps_recc_iq_create(&p, &d_h), "recc_iq");
     message_port_register_out(pmt::mp("bursts"));
 }
@@ -119,7 +120,10 @@ void recc_iq_impl::on_burst(const amps_burst *b, void *self) {
 int recc_iq_impl::work(int noutput_items, gr_vector_const_void_star &input_items, gr_vector_void_star &) {
     if (noutput_items < 1) return 0;
     // gr_complex is std::complex<float>: interleaved re, im -- exactly what the ABI takes
-    warn(amps_recc_iq_work(d_h, static_cast<const float *>(input_items[0]), (size_t)noutput_items, &recc_iq_impl::on_burst, this), "recc_iq work");
+    if (d_sc16)
+        warn(amps_recc_iq_work_sc16(d_h, static_cast<const int16_t *>(input_items[0]), (size_t)noutput_items, &recc_iq_impl::on_burst, this), "recc_iq work");
+    else
+        warn(amps_recc_iq_work(d_h, static_cast<const float *>(input_items[0]), (size_t)noutput_items, &recc_iq_impl::on_burst, this), "recc_iq work");
     return noutput_items;
 }
 

@@ -51,7 +51,8 @@ class recc_iq_impl : public recc_iq {
     amps_recc_iq *d_h;
     static void on_burst(const amps_burst *b, void *self);
 public:
-    recc_iq_impl(double samp_rate, double center_freq, int device, bool mm_timing);
+    bool d_sc16;
+    recc_iq_impl(double samp_rate, double center_freq, int device, bool mm_timing, bool sc16);
     ~recc_iq_impl();
     int work(int noutput_items, gr_vector_const_void_star &input_items, gr_vector_void_star &output_items);
 };

@@ -116,7 +116,17 @@ static int run_loop(int argc, char **argv) {
 
     // the message wiring of grc/ampsbs.grc:4404-4470 around the RECC/FOCC/FVC blocks
     const bool mm_timing = argc > 7 && !std::strcmp(argv[7], "mm");                   // M&M timing tail instead of the detector
-    recc_iq::sptr rx = recc_iq::make(10e6, -160e3, 0, mm_timing);
+    const bool sc16 = argc > 7 && !std::strcmp(argv[7], "sc16");                     // int16 I,Q input (x 1/32768 on the GPU)
+    std::vector<int16_t> iq16;
+    if (sc16) {
+        iq16.resize(2 * nsamples);
+        const float *f32 = reinterpret_cast<const float *>(iq.data());
+        for (size_t i = 0; i < 2 * nsamples; i++) {
+            float v = std::nearbyint(f32[i] * 32768.0f);
+            iq16[i] = (int16_t)(v > 32767.f ? 32767.f : (v < -32768.f ? -32768.f : v));
+        }
+    }
+    recc_iq::sptr rx = recc_iq::make(10e6, -160e3, 0, mm_timing, sc16);
     recc_decode::sptr dec = recc_decode::make();
     focc::sptr fo = focc::make(100000, false);
     fvc::sptr fv = fvc::make(100000);
@@ -133,7 +143,7 @@ static int run_loop(int argc, char **argv) {
     gr_vector_void_star none;
     for (size_t pos = 0; pos < nsamples; pos += chunk) {
         const size_t n = nsamples - pos < chunk ? nsamples - pos : chunk;
-        in[0] = &iq[pos];
+        in[0] = sc16 ? static_cast<const void *>(&iq16[2 * pos]) : static_cast<const void *>(&iq[pos]);
         if (rx->work((int)n, in, none) != (int)n) return 5;
     }
     // then let the sources run, as the scheduler would

@@ -36,7 +36,10 @@ def test_focc_block_work_schedule(oracle, tmp_path, symrate, aggr, seed):
     assert np.array_equal(got, np.frombuffer(bytes(ref), np.uint8))
 
 
-def test_closed_loop_flowgraph(oracle, tmp_path):
+@pytest.mark.parametrize("sc16", [False, True], ids=["fc32", "sc16"])
+def test_closed_loop_flowgraph(oracle, tmp_path, sc16):
+    """sc16: the recc_iq block takes interleaved int16 I,Q (item size 4) and converts on the GPU; the oracle is fed the
+    floats those integers stand for."""
     period = 55 * 38400
     msgs = [synth.origination_words(min10="2125550101", dialed="4155551212"),
             synth.page_response_words(min10="2125550102"),
@@ -47,8 +50,11 @@ def test_closed_loop_flowgraph(oracle, tmp_path):
     iq = tmp_path / "iq.bin"
     x.tofile(iq)
     focc_bytes = 3 * 19 * 4630
-    out = run(["loop", iq, len(x), 262144, focc_bytes, tmp_path / "loop"], tmp_path)
+    out = run(["loop", iq, len(x), 262144, focc_bytes, tmp_path / "loop"] + (["sc16"] if sc16 else []), tmp_path)
     lines = [json.loads(l) for l in out.splitlines() if l.startswith("{")]
+    if sc16:
+        q = np.clip(np.rint(x.view(np.float32) * np.float32(32768.0)), -32768, 32767).astype(np.int16)
+        x = (q.astype(np.float32) * np.float32(1.0 / 32768.0)).view(np.complex64)
 
     # oracle side of the same loop
     _, d = oracle.rx_chain_f32(x)
