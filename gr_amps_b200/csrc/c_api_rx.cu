@@ -169,6 +169,7 @@ extern "C" int amps_recc_iq_create(const amps_recc_iq_params *params, amps_recc_
     h->fp.fcw25 = (uint32_t)(25u * h->fcw);
     h->fp.in_scale = params->sc16_scale != 0.0f ? params->sc16_scale : 1.0f / 32768.0f;
     nco_block_table(h->fcw, kD1, reinterpret_cast<float *>(h->fp.w));
+    for (int k = 0; k < kD1; ++k) h->fp.wj[k] = make_float2(-h->fp.w[k].y, h->fp.w[k].x);
     std::vector<float> cic;
     cic3_taps(kD1, cic);
     for (size_t i = 0; i < cic.size(); ++i) h->fp.g[i] = cic[i];

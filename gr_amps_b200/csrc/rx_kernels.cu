@@ -184,7 +184,8 @@ __global__ void __launch_bounds__(kTB, kMinCtas) rx_front_kernel(const __grid_co
         float2 P0 = make_float2(0.f, 0.f), P1 = P0, P2 = P0;
 #pragma unroll
         for (int k = 0; k < kD1; ++k) {
-            float2 u = cmul(to_c32(xin[k], p.in_scale), p.w[k]);
+            const float2 x = to_c32(xin[k], p.in_scale);
+            const float2 u = fma2(splat(x.y), p.wj[k], mul2(splat(x.x), p.w[k]));      // = cmul(x, w[k]), same operations
             P0 = fma2(splat(p.g[24 - k]), u, P0);
             P1 = fma2(splat(p.g[49 - k]), u, P1);
             if (74 - k < kNCic) P2 = fma2(splat(p.g[74 - k]), u, P2);
@@ -233,7 +234,7 @@ __global__ void __launch_bounds__(kTB, 4) rx_front400_kernel(const __grid_consta
         const float2 x = to_c32(L < 0 ? static_cast<const In *>(p.tail)[(long)kPass400 + L] : static_cast<const In *>(p.chunk)[L], p.in_scale);
         const unsigned long long nabs = p.n_base + (unsigned long long)(long long)L;    // (x is 0 where this wraps: stream start)
         const uint32_t b = (uint32_t)(nabs / kD1), k = (uint32_t)(nabs % kD1);
-        return cmul(cmul(x, p.w[k]), sincos_phase(b * p.fcw25));
+        return cmul(fma2(splat(x.y), p.wj[k], mul2(splat(x.x), p.w[k])), sincos_phase(b * p.fcw25));
     };
     const long first = (long)pa * kPass400;
     // warm-up: the kPorchCols columns of history in front of the first pass

@@ -40,6 +40,8 @@ struct RxFrontParams {
     uint32_t      fcw25;     // NCO phase step per block (25 * fcw mod 2^32)
     float         in_scale;  // sc16 input: x = (float)int16 * in_scale (one fp32 multiply per component)
     float2        w[kD1];    // NCO phasors inside a block
+    float2        wj[kD1];   // j * w = (-w.im, w.re): the second operand of the complex product, ready-made so that it is a
+                             // uniform-register operand of FFMA2 instead of a negate + move per sample
     float         g[75];     // CIC^3 taps (73 + 2 zeros)
     float         h2[300];   // channel filter (299 + pad)
 };
