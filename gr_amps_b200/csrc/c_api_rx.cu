@@ -5,6 +5,7 @@
 #include "design.h"
 #include "rx_kernels.cuh"
 
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -28,6 +29,7 @@ struct amps_recc_iq {
 
     RxFrontParams fp{};                  // constant part filled at create
     bool         sc16 = false;           // AMPS_RX_INPUT_SC16: interleaved int16 I/Q instead of float
+    bool         sc16_unit = false;      // sc16 scale is a power of two: folded into the NCO tables, no multiply in the kernel
     size_t       isz = sizeof(float2);   // bytes per complex input sample (8 or 4)
     uint8_t     *d_stage = nullptr;      // host path: [carry | new chunk]
     uint8_t     *d_tail[2] = {nullptr, nullptr};
@@ -169,6 +171,14 @@ extern "C" int amps_recc_iq_create(const amps_recc_iq_params *params, amps_recc_
     h->fp.fcw25 = (uint32_t)(25u * h->fcw);
     h->fp.in_scale = params->sc16_scale != 0.0f ? params->sc16_scale : 1.0f / 32768.0f;
     nco_block_table(h->fcw, kD1, reinterpret_cast<float *>(h->fp.w));
+    if (h->sc16) {
+        int e = 0;
+        const float m = std::frexp(h->fp.in_scale, &e);
+        if (m == 0.5f && e > -40 && e < 40) {                       // power of two: (I s) w == I (s w) exactly
+            h->sc16_unit = true;
+            for (int k = 0; k < kD1; ++k) { h->fp.w[k].x *= h->fp.in_scale; h->fp.w[k].y *= h->fp.in_scale; }
+        }
+    }
     for (int k = 0; k < kD1; ++k) h->fp.wj[k] = make_float2(-h->fp.w[k].y, h->fp.w[k].x);
     std::vector<float> cic;
     cic3_taps(kD1, cic);
@@ -242,8 +252,8 @@ static int rx_enqueue(amps_recc_iq *h, const uint8_t *d_chunk, uint32_t npass, c
     const int  evi = (int)(h->ev_count % amps_recc_iq::kEv);
     if (timed) CK(cudaEventRecord(h->ev0[evi], st));
     p.tail_out = h->native400 ? nullptr : h->d_tail[h->tail_cur ^ 1];
-    if (h->native400) CKL(launch_rx_front400(p, grid, st, h->sc16));
-    else CKL(launch_rx_front(p, grid, st, h->sc16));
+    if (h->native400) CKL(launch_rx_front400(p, grid, st, h->sc16, h->sc16_unit));
+    else CKL(launch_rx_front(p, grid, st, h->sc16, h->sc16_unit));
     if (timed) { CK(cudaEventRecord(h->ev1[evi], st)); h->ev_count++; }
     h->launches++;
     // history for the next call = the tail of this one (the 10 MS/s front kernel copies it itself)

@@ -35,8 +35,13 @@ struct PassSmem {                         // what stage 2 + demod work on (share
 };
 // input sample formats: fc32 (gr_complex, what the reference's flowgraph carries) and sc16 (interleaved int16 I/Q, what
 // the USRP puts on the wire before UHD's host-side conversion, grc/ampsbs.grc:3750): x = (float)int16 * in_scale
-__device__ __forceinline__ float2 to_c32(float2 v, float) { return v; }
-__device__ __forceinline__ float2 to_c32(short2 v, float s) { return make_float2(__fmul_rn((float)v.x, s), __fmul_rn((float)v.y, s)); }
+// kUnit: the scale is a power of two and has been folded into the NCO tables on the host -- (I s) w and I (s w) are the
+// same real number when s is a power of two, so the result is bit-identical and the two multiplies per sample go away.
+template <bool kUnit> __device__ __forceinline__ float2 to_c32(float2 v, float) { return v; }
+template <bool kUnit> __device__ __forceinline__ float2 to_c32(short2 v, float s) {
+    if (kUnit) return make_float2((float)v.x, (float)v.y);
+    return make_float2(__fmul_rn((float)v.x, s), __fmul_rn((float)v.y, s));
+}
 
 template <typename In>
 struct FrontSmem {
@@ -141,7 +146,7 @@ __device__ __forceinline__ void finish_pass(const RxFrontParams &p, PassSmem *ps
     }
 }
 
-template <typename In, int kMinCtas>
+template <typename In, int kMinCtas, bool kUnit>
 __global__ void __launch_bounds__(kTB, kMinCtas) rx_front_kernel(const __grid_constant__ RxFrontParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     FrontSmem<In> *sm = reinterpret_cast<FrontSmem<In> *>(smem_raw);
@@ -184,7 +189,7 @@ __global__ void __launch_bounds__(kTB, kMinCtas) rx_front_kernel(const __grid_co
         float2 P0 = make_float2(0.f, 0.f), P1 = P0, P2 = P0;
 #pragma unroll
         for (int k = 0; k < kD1; ++k) {
-            const float2 x = to_c32(xin[k], p.in_scale);
+            const float2 x = to_c32<kUnit>(xin[k], p.in_scale);
             const float2 u = fma2(splat(x.y), p.wj[k], mul2(splat(x.x), p.w[k]));      // = cmul(x, w[k]), same operations
             P0 = fma2(splat(p.g[24 - k]), u, P0);
             P1 = fma2(splat(p.g[49 - k]), u, P1);
@@ -222,7 +227,7 @@ __global__ void __launch_bounds__(kTB, kMinCtas) rx_front_kernel(const __grid_co
 // quadrature_demod_cf.  At 0.4 MS/s real time this kernel is never a bottleneck (it is FFMA-bound: 150 FFMA2 per
 // 8-byte sample); it exists so that recc_iq drops into the reference flowgraph at its native rate.
 // ---------------------------------------------------------------------------------------------
-template <typename In>
+template <typename In, bool kUnit>
 __global__ void __launch_bounds__(kTB, 4) rx_front400_kernel(const __grid_constant__ RxFrontParams p) {
     __shared__ PassSmem ps;
     const int t = threadIdx.x;
@@ -231,7 +236,7 @@ __global__ void __launch_bounds__(kTB, 4) rx_front400_kernel(const __grid_consta
     uint32_t pb = pa + p.pass_per_cta;
     if (pb > p.npass) pb = p.npass;
     auto load = [&](long L) -> float2 {                   // logical sample L of this call; L < 0 = history
-        const float2 x = to_c32(L < 0 ? static_cast<const In *>(p.tail)[(long)kPass400 + L] : static_cast<const In *>(p.chunk)[L], p.in_scale);
+        const float2 x = to_c32<kUnit>(L < 0 ? static_cast<const In *>(p.tail)[(long)kPass400 + L] : static_cast<const In *>(p.chunk)[L], p.in_scale);
         const unsigned long long nabs = p.n_base + (unsigned long long)(long long)L;    // (x is 0 where this wraps: stream start)
         const uint32_t b = (uint32_t)(nabs / kD1), k = (uint32_t)(nabs % kD1);
         return cmul(fma2(splat(x.y), p.wj[k], mul2(splat(x.x), p.w[k])), sincos_phase(b * p.fcw25));
@@ -252,17 +257,19 @@ __global__ void __launch_bounds__(kTB, 4) rx_front400_kernel(const __grid_consta
     }
 }
 
-cudaError_t launch_rx_front400(const RxFrontParams &p, int grid, cudaStream_t st, bool sc16) {
-    if (sc16) rx_front400_kernel<short2><<<grid, kTB, 0, st>>>(p);
-    else rx_front400_kernel<float2><<<grid, kTB, 0, st>>>(p);
+cudaError_t launch_rx_front400(const RxFrontParams &p, int grid, cudaStream_t st, bool sc16, bool unit) {
+    if (sc16 && unit) rx_front400_kernel<short2, true><<<grid, kTB, 0, st>>>(p);
+    else if (sc16) rx_front400_kernel<short2, false><<<grid, kTB, 0, st>>>(p);
+    else rx_front400_kernel<float2, false><<<grid, kTB, 0, st>>>(p);
     return cudaGetLastError();
 }
 
 // sc16 tiles are half the size, so three CTAs fit an SM (the kernel is no longer HBM-bound at 4 B/sample)
 constexpr int kSc16Ctas = 3;
-cudaError_t launch_rx_front(const RxFrontParams &p, int grid, cudaStream_t st, bool sc16) {
-    if (sc16) rx_front_kernel<short2, kSc16Ctas><<<grid, kTB, sizeof(FrontSmem<short2>), st>>>(p);
-    else rx_front_kernel<float2, 2><<<grid, kTB, sizeof(FrontSmem<float2>), st>>>(p);
+cudaError_t launch_rx_front(const RxFrontParams &p, int grid, cudaStream_t st, bool sc16, bool unit) {
+    if (sc16 && unit) rx_front_kernel<short2, kSc16Ctas, true><<<grid, kTB, sizeof(FrontSmem<short2>), st>>>(p);
+    else if (sc16) rx_front_kernel<short2, kSc16Ctas, false><<<grid, kTB, sizeof(FrontSmem<short2>), st>>>(p);
+    else rx_front_kernel<float2, 2, false><<<grid, kTB, sizeof(FrontSmem<float2>), st>>>(p);
     return cudaGetLastError();
 }
 int rx_front_ctas_per_sm(bool sc16) { return sc16 ? kSc16Ctas : 2; }
@@ -791,16 +798,18 @@ cudaError_t launch_rx_mm(const float *dring, uint32_t dmask, unsigned long long 
 
 // per-device opt-in to large dynamic shared memory (call once per device after cudaSetDevice)
 cudaError_t rx_configure_device() {
-    cudaError_t e = cudaFuncSetAttribute(rx_front_kernel<float2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrontSmem<float2>));
+    cudaError_t e = cudaFuncSetAttribute(rx_front_kernel<float2, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrontSmem<float2>));
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(rx_front_kernel<short2, kSc16Ctas>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrontSmem<short2>));
+    e = cudaFuncSetAttribute(rx_front_kernel<short2, kSc16Ctas, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrontSmem<short2>));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(rx_front_kernel<short2, kSc16Ctas, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrontSmem<short2>));
     if (e != cudaSuccess) return e;
     // The side-stream kernels share SMs with the NEXT call's front kernel, whose two CTAs need 199 KB of shared memory per
     // SM.  An SM's L1/shared split is fixed while CTAs are resident: if a kernel that wants a big L1 gets there first, the
     // front CTAs wait until it has left.  Ask for the front kernel's split everywhere.
     const void *side[] = {(const void *)rx_detect_kernel, (const void *)rx_select_kernel, (const void *)rx_capture_kernel,
-                          (const void *)rx_mm_kernel, (const void *)rx_mm_recc_kernel, (const void *)rx_front_kernel<float2, 2>,
-                          (const void *)rx_front_kernel<short2, kSc16Ctas>};
+                          (const void *)rx_mm_kernel, (const void *)rx_mm_recc_kernel, (const void *)rx_front_kernel<float2, 2, false>,
+                          (const void *)rx_front_kernel<short2, kSc16Ctas, false>, (const void *)rx_front_kernel<short2, kSc16Ctas, true>};
     for (const void *f : side) {
         e = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;

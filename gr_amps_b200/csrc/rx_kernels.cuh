@@ -88,9 +88,9 @@ constexpr int kMaxAccept = 512;    // bursts one call can publish
 
 size_t rx_front_smem_bytes();
 cudaError_t rx_configure_device();
-cudaError_t launch_rx_front(const RxFrontParams &p, int grid, cudaStream_t st, bool sc16 = false);
+cudaError_t launch_rx_front(const RxFrontParams &p, int grid, cudaStream_t st, bool sc16 = false, bool unit = false);
 int rx_front_ctas_per_sm(bool sc16);
-cudaError_t launch_rx_front400(const RxFrontParams &p, int grid, cudaStream_t st, bool sc16 = false);
+cudaError_t launch_rx_front400(const RxFrontParams &p, int grid, cudaStream_t st, bool sc16 = false, bool unit = false);
 cudaError_t launch_rx_detect(const float *dring, const uint32_t *hring, uint32_t dmask, RxState *state, Candidate *cand,
                              unsigned long long scan_lo, unsigned long long scan_hi, int max_ctas, cudaStream_t st);
 // select: sorts the candidates (cand must hold 2 x kMaxCand entries: list + sorted scratch), groups runs, picks sampling
