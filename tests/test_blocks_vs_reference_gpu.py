@@ -92,3 +92,19 @@ def test_live_decode_vs_compiled_reference(G):
         assert K.result_bytes(g, False) == K.result_bytes(R.recc_fields(blob), False)
         _, info = R.recc_bursts_message(blob)
         assert K.dispatch_tuple_oracle(g) == K.dispatch_tuple_ref(info)
+
+
+def test_testalloc_properties_hold_for_the_cuda_focc(G):
+    """The reference's only executable checks (apps/testalloc.cc:64-92: focc at symrate 200000, 10240-byte requests,
+    every sample of a half-symbol equal and non-zero, every pair (+1,-1) or (-1,+1)), on the CUDA source."""
+    sps = 10
+    f = G.Focc(200000, False)
+    bits = 0
+    while bits < 20000:
+        r, b = f.work(10240)
+        assert r % sps == 0 and r % 2 == 0
+        s = b.view(np.int8).reshape(-1, sps)
+        assert np.all(s == s[:, :1]) and np.all(s[:, 0] != 0)
+        sym = s[:, 0]
+        assert np.all(sym[0::2] == -sym[1::2])
+        bits += r // sps // 2
