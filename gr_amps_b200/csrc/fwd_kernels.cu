@@ -238,8 +238,8 @@ __global__ void __launch_bounds__(kFwdThreads, 3) fwd_fused_kernel(const __grid_
 
         // ---- phase 2: x4 polyphase interpolation.  One thread = two adjacent symbols (8 outputs) of one carrier: the
         //      FM sample loaded for symbol i at tap k is symbol i+1's sample at tap k+1, so each shared-memory load and
-        //      each uniform 4-tap load feeds 8 FFMA2.  One warp per carrier.  The 400 kS/s samples are stored already
-        //      rotated by the carrier's NCO: at[m] = a[m] e^{j phi_c(25 m)}.
+        //      each uniform 4-tap load feeds 8 FFMA2.  The 400 kS/s samples are stored already rotated by the carrier's
+        //      NCO: at[m] = a[m] e^{j phi_c(25 m)}.
         // Without voice legs all eight warps share the taps (p.seg: e.g. 49 + 81 + 81 tap groups -> 2 + 3 + 3 warps of
         // 25..27 groups each); with voice legs the five spare warps resample the audio and each carrier keeps one warp.
         const FwdParams::Seg sg = kVoice ? FwdParams::Seg{(int8_t)((t >> 5) < p.ncar ? (t >> 5) : -1), 0, 1, 0, 0, (int16_t)((t >> 5) < p.ncar ? p.ntap4[(t >> 5) < p.ncar ? (t >> 5) : 0] : 0)}
@@ -401,8 +401,10 @@ __global__ void __launch_bounds__(kFwdThreads, 3) fwd_fused_kernel(const __grid_
 // Manchester-bit fast path.  Every FOCC / FVC data bit is the half-symbol pair (-1 x5, +1 x5) or (+1 x5, -1 x5), so
 // the FM phase returns to zero at every bit boundary and the modulator output over one bit is one of two fixed
 // 10-sample waveforms.  The x4 polyphase interpolator is linear, hence its 400 kS/s output is a sum of per-bit
-// responses: a[m] = sum_{d<9} R[bit(q-d)][(m - 40 q) + 40 d], q = m div 40 -- nine table lookups instead of 49..81
-// taps, no prefix sum, no sincos per sample ("closed-form Manchester symbol lookup").
+// responses: a[m] = sum_{d<9} R[bit(q-d)][(m - 40 q) + 40 d], q = m div 40 -- table lookups instead of 49..81
+// taps, no prefix sum, no sincos per sample ("closed-form Manchester symbol lookup").  And since a 1 is
+// the mirror image of a 0, R1 = conj(R0): the real part of a[m] does not depend on the data and the imaginary part is a
+// signed sum, looked up three bits at a time (RW / JW / I3 tables, fwd_kernels.cuh: kFbFastLen).
 // The rest (x5 CIC^3 with folded mixers, carriers summed at 2 MS/s, shared x5 CIC^3, TMA bulk store) is the same.
 // ---------------------------------------------------------------------------------------------
 struct FwdBitsSmem {
