@@ -112,6 +112,7 @@ extern "C" int amps_fwd_create(const amps_fwd_params *p, amps_fwd **out) {
         for (int u = 0; u < 15; ++u) {                              // tap u of the 2 MS/s stage sits 5 u output samples later
             const float g = u < (int)cic5.size() ? 5.0f * cic5[(size_t)u] : 0.0f;
             h->fp.C1[c][u] = make_float2(g * ph[2 * (size_t)(5 * u)], g * ph[2 * (size_t)(5 * u) + 1]);
+            h->fp.C1j[c][u] = make_float2(-h->fp.C1[c][u].y, h->fp.C1[c][u].x);
         }
         h->fp.w25[c] = make_float2(ph[50], ph[51]);
     }

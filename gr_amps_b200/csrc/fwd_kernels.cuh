@@ -44,6 +44,8 @@ struct FwdParams {
     int            ntap4[kFwdMaxCar];
     float2         w25[kFwdMaxCar];              // mixer phasor of one 400 kS/s step
     float2         C1[kFwdMaxCar][15];           // 5 cic5[u] e^{j phi_c(5 u)}: first x5 CIC^3 stage carrying the mixer
+    float2         C1j[kFwdMaxCar][15];          // j C1 = (-C1.im, C1.re), ready-made: a uniform-register FFMA2 operand instead of a
+                                                 // negate + move per tap
     float          G2[15];                       // out_scale * 5 cic5[u]: second (shared) x5 CIC^3 stage
     float          taps[kFwdMaxCar][4 * kFwdMaxTap4];
     // polyphase work split of fwd_fused_kernel<false>: warp w runs taps [k0, k1) of carrier c for all 64 symbols of the
