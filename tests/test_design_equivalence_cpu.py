@@ -1,0 +1,100 @@
+"""The 10 MS/s extrapolation against a LITERAL scaling of the reference's receive design.
+
+The reference's graph filters at 400 kS/s with firdes.low_pass(3, 400e3, 10e3, 4.5e3, BLACKMAN) inside a decimating
+freq_xlating_fir_filter (grc/ampsbs.grc:138-184, 1814-1872).  Scaled literally to BASELINE's 10 MS/s that is ONE 7475-tap
+filter decimating by 50 -- 150 complex MACs per input sample, which is why the product runs
+NCO -> CIC^3 /25 -> the reference's own 299 taps /2 instead.  This test shows the two designs are interchangeable where it
+matters: same channel response, and the same half-symbols and words out of the same noisy bursts."""
+import numpy as np
+import pytest
+from scipy import signal
+
+from gr_amps_b200 import synth
+
+FS = 10e6
+PASS = 38400
+
+
+def literal_chain(x, oracle, center=-160e3):
+    """numpy float64: rotate to baseband, one firdes.low_pass(3, 10e6, 10e3, 4.5e3, BLACKMAN) decimating by 50, then
+    quadrature_demod_cf (gain 1)."""
+    h = oracle.firdes_low_pass(3.0, FS, 10e3, 4.5e3, 2).astype(np.float64)
+    n = np.arange(len(x), dtype=np.float64)
+    xr = x.astype(np.complex128) * np.exp(-2j * np.pi * ((center / FS * n) % 1.0))
+    y = signal.upfirdn(h, xr, up=1, down=50)[:len(x) // 50]
+    d = np.angle(y[1:] * np.conj(y[:-1]))
+    return h, y, np.concatenate([[0.0], d]).astype(np.float32)
+
+
+def test_literal_filter_has_the_survey_length(oracle):
+    h = oracle.firdes_low_pass(3.0, FS, 10e3, 4.5e3, 2)
+    assert len(h) == 7475                                    # "R10M literal scaling => 7475 taps"
+
+
+def test_cascade_response_matches_the_literal_filter(oracle):
+    """|H| of (CIC^3 /25 at 10 MS/s) x (299 taps at 400 kS/s) vs the literal 7475-tap filter: equal within 0.1 dB over the
+    +-10 kHz passband the FSK occupies, both more than 70 dB down from 20 kHz outwards (the adjacent 30 kHz channel)."""
+    h_lit = oracle.firdes_low_pass(3.0, FS, 10e3, 4.5e3, 2).astype(np.float64)
+    h2 = oracle.lpf_taps().astype(np.float64)
+    box = np.ones(25) / 25.0
+    cic = np.convolve(np.convolve(box, box), box)            # 73 taps, unit DC gain
+    up2 = np.zeros(25 * (len(h2) - 1) + 1)
+    up2[::25] = h2                                           # the 400 kS/s filter seen at 10 MS/s
+    h_cas = np.convolve(cic, up2)
+    f = np.concatenate([np.linspace(0, 10e3, 81), np.linspace(20e3, 195e3, 701)])
+    w = 2 * np.pi * f / FS
+    H_lit = np.abs(signal.freqz(h_lit, worN=w)[1])
+    H_cas = np.abs(signal.freqz(h_cas, worN=w)[1])
+    pb = f <= 10e3
+    assert np.max(np.abs(20 * np.log10(H_cas[pb] / H_lit[pb]))) < 0.1
+    dc = H_lit[0]
+    assert abs(dc - 3.0) < 1e-3 and abs(H_cas[0] - 3.0) < 1e-3         # gain 3 as in the reference (grc/ampsbs.grc:138-184)
+    sb = f >= 20e3
+    assert 20 * np.log10(np.max(H_lit[sb]) / dc) < -70 and 20 * np.log10(np.max(H_cas[sb]) / dc) < -70
+    # the images of the 400 kS/s filter at multiples of 400 kHz sit in the CIC^3 nulls
+    fi = np.concatenate([k * 400e3 + np.linspace(-15e3, 15e3, 61) for k in range(1, 13)])
+    Hi = np.abs(signal.freqz(h_cas, worN=2 * np.pi * fi / FS)[1])
+    assert 20 * np.log10(np.max(Hi) / dc) < -80
+
+
+@pytest.mark.parametrize("snr,seed", [(None, 1), (30.0, 2), (20.0, 3), (15.0, 4)])
+def test_same_symbols_and_words_as_the_literal_chain(oracle, snr, seed):
+    """One config-2 burst through both designs (float64), then the same detector / slicer / decoder: identical half-symbols
+    (= the transmitted ones) and identical decoded words."""
+    x, hs, _ = synth.config2_period(n_total=55 * PASS, snr_db=snr, seed=seed)
+    _, _, d_lit = literal_chain(x, oracle)
+    _, d_cas = oracle.rx_chain_f64(x)
+    b_lit = oracle.rx_detect(d_lit)
+    b_cas = oracle.rx_detect(d_cas.astype(np.float32))
+    assert len(b_lit) == len(b_cas) == 1
+    assert np.array_equal(b_lit[0][2], b_cas[0][2])
+    assert np.array_equal(b_cas[0][2], hs[82:82 + 3374])
+    # the two group delays differ by (7475 - 1)/2 - (36 + 25 * 149) = -24 input samples = half a demodulated sample
+    assert abs(b_lit[0][0] - b_cas[0][0]) <= 1
+    r1, r2 = oracle.recc_decode(b_lit[0][2]), oracle.recc_decode(b_cas[0][2])
+    assert bytes(r1.min) == bytes(r2.min) and list(r1.valid) == list(r2.valid) == [1] * 7 and r1.kind == r2.kind == 4
+
+
+def test_forward_chain_matches_the_literal_x100_interpolator(oracle):
+    """Transmit side: the reference interpolates x4 to 400 kS/s with firdes.low_pass(1, 400e3, 10e3, 5e3) (grc/ampsbs.grc:2227);
+    scaled literally to 10 MS/s that is pfb.interpolator_ccf(100, firdes.low_pass(1, 10e6, 10e3, 5e3)) = 4819 taps (SURVEY 8d
+    config 3).  The product keeps the reference's own x4 stage and adds two x5 CIC^3 stages.  Same FOCC symbols through both
+    (float64): after aligning delay and gain the waveforms agree to better than -50 dB.  The gain ratio is 25: pfb.interpolator
+    does not compensate its 1/R amplitude, and the cascade keeps the reference's 400 kS/s level."""
+    nsym = 6000
+    s = oracle.Focc(100000, False).generate(nsym)
+    y = oracle.fwd_chain_f64([s], carrier_freq=(0.0,), lpf_transition=(5e3,), scale=1.0)
+    x = s.view(np.int8).astype(np.float64)                                        # char_to_float
+    fm = np.exp(1j * np.cumsum(x) * (2 * np.pi * 8000.0 / 100e3))                 # frequency_modulator_fc
+    h = oracle.firdes_low_pass(1.0, FS, 10e3, 5e3, 0).astype(np.float64)
+    assert len(h) == 4819
+    lit = signal.upfirdn(h, fm, up=100)
+    a = y[100000:400000]
+    c = signal.correlate(lit[90000:410000], a, mode="valid", method="fft")
+    lag = int(np.argmax(np.abs(c))) - 10000
+    assert abs(lag) < 100                                                         # group delays: 2409 vs 2436 samples
+    seg = lit[100000 + lag:400000 + lag]
+    g = np.vdot(seg, a) / np.vdot(seg, seg)
+    resid = np.mean(np.abs(a - g * seg) ** 2) / np.mean(np.abs(a) ** 2)
+    assert 10 * np.log10(resid) < -50.0
+    assert abs(abs(g) - 25.0) < 0.125 and abs(np.angle(g)) < 1e-3
