@@ -7,7 +7,7 @@
  * (gr_amps_b200/) never links, imports or calls anything in here.
  *
  * PARITY STATUS.  Integer paths (BCH, words, FOCC/FVC sources, RECC capture, RECC decode + responses, command
- * processor): PINNED to the reference's own code -- oracle/_ref/libamps_ref.so is gr-amps's unmodified lib/*.cc compiled
+ * processor): PINNED to the reference's own code -- oracle/_ref/libamps_ref.so is gr-amps's unmodified lib/ sources compiled
  * from /root/reference against stand-in GNU Radio / Boost / IT++ headers (oracle/Makefile, oracle/ref_harness.cc), and
  * tests/test_ref_pin_cpu.py requires byte-identical transcripts, live and through tests/golden/ref_vectors.json.
  * Floating paths (dsp_chain.c, mm_timing.c, voice_tx.c): "parity unpinned" -- they restate stock GNU Radio 3.7 blocks
