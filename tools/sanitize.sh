@@ -40,4 +40,7 @@ for tool in memcheck racecheck synccheck; do
   echo "mm   $tool rc=$? $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' gpurun_out/sanitize_mm_$tool.log | tail -1)"
   timeout 1200 compute-sanitizer --tool $tool --error-exitcode 9 $QA fwd 20000 /tmp/san/fwdv.bin voice > gpurun_out/sanitize_voice_$tool.log 2>&1
   echo "voice $tool rc=$? $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' gpurun_out/sanitize_voice_$tool.log | tail -1)"
+  # the sc16 instance of the front kernel (int16 I,Q input, 3 CTAs/SM)
+  timeout 1200 compute-sanitizer --tool $tool --error-exitcode 9 $QA loop /tmp/san/iq.bin $N 262144 87970 /tmp/san/out16 sc16 > gpurun_out/sanitize_sc16_$tool.log 2>&1
+  echo "sc16 $tool rc=$? $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' gpurun_out/sanitize_sc16_$tool.log | tail -1)"
 done
