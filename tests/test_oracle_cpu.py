@@ -383,3 +383,53 @@ def test_voice_leg_oracle_properties(oracle):
     m = np.zeros(200, np.uint8); m[100:] = 1
     vm = oracle.voice_tx_f64(np.zeros(200, np.float32), mute=m, sat_amp=0.0)
     assert np.allclose(vm[25 * 40:25 * 100], 0.375, atol=2e-6) and np.all(vm[25 * 130:] == 0)
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/audio/boot16k.wav"), reason="needs the reference tree (its audio asset is not copied into this repo)")
+def test_voice_leg_on_the_references_own_audio(oracle):
+    """The reference graph plays audio/boot16k.wav (16 kS/s mono, grc/ampsbs.grc:1681) + a 6 kHz SAT at 0.05 into nbfm_tx.
+    Run the first second of that file through the float64 voice leg and demodulate it again: the SAT line comes back at
+    max_dev * sat_amp * |H_preemph(6 kHz)| of deviation, the envelope sits around the x25 resampler's DC gain 3/8, and the
+    instantaneous frequency never leaves what the pre-emphasised audio peak allows."""
+    import ctypes as C
+    import wave
+    w = wave.open("/root/reference/audio/boot16k.wav")
+    assert (w.getnchannels(), w.getsampwidth(), w.getframerate()) == (1, 2, 16000)
+    audio = (np.frombuffer(w.readframes(16000), np.int16).astype(np.float32) / np.float32(32768.0))
+    y = oracle.voice_tx_f64(audio, sat_amp=0.05)
+    assert len(y) == 25 * len(audio)
+    body = y[25 * 64:]
+    # nbfm_tx runs the modulator AT 16 kS/s (quad_rate 16000, grc/ampsbs.grc:943-1005): with kHz of deviation the FM
+    # spectrum fills that band, and the x25 resampler's 15 kHz low-pass lets part of the first image through -- the
+    # envelope ripples around the resampler's DC gain 3/8 instead of being constant (a property of the reference's graph)
+    env = np.abs(body)
+    assert abs(np.mean(env) - 0.375) < 0.03 and 0.15 < np.min(env) and np.max(env) < 0.45
+    f_inst = np.angle(body[1:] * np.conj(body[:-1])) * 400e3 / (2 * np.pi)
+    L = oracle.lib()
+    L.orc_fm_preemph_taps.argtypes = [C.c_double] * 3 + [C.POINTER(C.c_double)] * 2
+    b, a = (C.c_double * 2)(), (C.c_double * 2)()
+    L.orc_fm_preemph_taps(16000.0, 75e-6, -1.0, b, a)
+    x = audio.astype(np.float64) + 0.05 * np.cos(2 * np.pi * 6000.0 / 16000.0 * np.arange(len(audio)))
+    from scipy import signal
+    pre = signal.lfilter([b[0], b[1]], [1.0, a[1]], x)
+    assert np.max(np.abs(f_inst)) <= 8000.0 * np.max(np.abs(pre)) * 1.05 + 50.0
+    # SAT: the modulator swings +-8000 * 0.05 * |H_preemph(6 kHz)| = 2.1 kHz at 6 kHz, but almost none of it survives the
+    # resampler: voice_lpf_taps is designed for 400 kS/s (15 kHz cut-off, grc/ampsbs.grc voice_lpf_taps) while
+    # pfb.arb_resampler_ccf runs its prototype at nfilts x 16 kS/s = 128 kS/s, where that cut-off lands at 4.8 kHz --
+    # the 6 kHz sidebands sit in its stop band.  (A property of the reference's graph, reproduced, not corrected.)
+    n = len(f_inst) - len(f_inst) % 400                            # whole periods of 6 kHz at 400 kS/s
+    t = np.arange(n) / 400e3
+    sat = 2.0 * np.abs(np.mean(f_inst[:n] * np.exp(-2j * np.pi * 6000.0 * t)))
+    z = np.exp(-1j * 2 * np.pi * 6000.0 / 16000.0)
+    h6 = abs((b[0] + b[1] * z) / (1 + a[1] * z))
+    assert 8000.0 * 0.05 * h6 > 2000.0 and sat < 0.05 * 8000.0 * 0.05 * h6
+    # whereas a 1 kHz test tone (inside the 4.8 kHz) comes through with the deviation the modulator gave it
+    tone = (0.1 * np.cos(2 * np.pi * 1000.0 / 16000.0 * np.arange(8000))).astype(np.float32)
+    yt = oracle.voice_tx_f64(tone, sat_amp=0.0)[25 * 64:]
+    ft = np.angle(yt[1:] * np.conj(yt[:-1])) * 400e3 / (2 * np.pi)
+    m = len(ft) - len(ft) % 400
+    dev = 2.0 * np.abs(np.mean(ft[:m] * np.exp(-2j * np.pi * 1000.0 * np.arange(m) / 400e3)))
+    z1 = np.exp(-1j * 2 * np.pi * 1000.0 / 16000.0)
+    h1 = abs((b[0] + b[1] * z1) / (1 + a[1] * z1))
+    # (a phase step of k*y per 16 kS/s sample is a deviation of k*y*fs/2pi scaled by sinc-like pi f/fs / sin(pi f/fs) ~ 1.006 at 1 kHz)
+    assert abs(dev / (8000.0 * 0.1 * h1) - 1.0) < 0.03
