@@ -141,3 +141,18 @@ def test_bit_fast_path_streaming(capi, oracle):
         pos += n
     got = np.concatenate(parts)
     assert np.array_equal(got.view(np.float32), one.view(np.float32))
+
+
+@pytest.mark.parametrize("ncar", [1, 2])
+def test_fewer_carriers_both_input_kinds(capi, oracle, ncar):
+    """One and two carriers (the polyphase taps are then shared by three / six warps, the bit path's ballots run on idle
+    warps too): half-symbol input and data-bit input against the float64 chain, and against each other."""
+    nbits = 2100
+    syms = config3_symbols(oracle, nbits * 10)[:ncar]
+    cf, tw = (0.0, 60e3)[:ncar], (5e3, 3e3)[:ncar]
+    ref = oracle.fwd_chain_f64(syms, carrier_freq=cf, lpf_transition=tw, scale=0.5)
+    g = capi.Fwd(max_samples=nbits * 1000, carrier_freq=cf, lpf_transition=tw).work(syms)
+    assert rms(g.astype(np.complex128) - ref) <= 1e-6
+    b = capi.Fwd(max_samples=nbits * 1000, carrier_freq=cf, lpf_transition=tw).work_bits([bits_of(s) for s in syms])
+    assert rms(b.astype(np.complex128) - ref) <= 1e-6
+    assert rms(b.astype(np.complex128) - g.astype(np.complex128)) <= 1e-6
