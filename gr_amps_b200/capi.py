@@ -84,6 +84,7 @@ class FwdVoiceParams(C.Structure):
 
 BURST_CB = C.CFUNCTYPE(None, C.POINTER(Burst), C.c_void_p)
 BLOB_CB = C.CFUNCTYPE(None, u8p, C.c_void_p)
+BATCH_BURST_CB = C.CFUNCTYPE(None, C.c_int, C.POINTER(Burst), C.c_void_p)
 
 RX_DUMP_BASEBAND = 1
 RX_TIME_KERNELS = 2
@@ -96,6 +97,8 @@ EXPORTS = [
     "amps_recc_iq_create", "amps_recc_iq_destroy", "amps_recc_iq_reset", "amps_recc_iq_work",
     "amps_recc_iq_submit_dev", "amps_recc_iq_work_sc16", "amps_recc_iq_submit_sc16_dev", "amps_recc_iq_collect", "amps_recc_iq_peek", "amps_recc_iq_consume", "amps_recc_iq_poll", "amps_recc_iq_granularity", "amps_recc_iq_read_demod",
     "amps_recc_iq_read_baseband", "amps_recc_iq_stats", "amps_recc_iq_front_times", "amps_recc_iq_get_taps",
+    "amps_recc_iq_batch_create", "amps_recc_iq_batch_destroy", "amps_recc_iq_batch_size", "amps_recc_iq_batch_submit_dev",
+    "amps_recc_iq_batch_work_shared", "amps_recc_iq_batch_front_times", "amps_recc_iq_batch_stats",
     "amps_recc_decode_create", "amps_recc_decode_destroy", "amps_recc_decode_burst", "amps_recc_decode_bursts",
     "amps_recc_create", "amps_recc_destroy", "amps_recc_work", "amps_recc_work_chunks",
     "amps_focc_create", "amps_focc_destroy", "amps_focc_work", "amps_focc_generate", "amps_focc_generate_dev",
@@ -143,6 +146,13 @@ def lib() -> C.CDLL:
     L.amps_recc_iq_stats.argtypes = [C.c_void_p] + [C.POINTER(C.c_uint64)] * 4
     L.amps_recc_iq_get_taps.argtypes = [C.c_void_p, f32p, C.c_int]
     L.amps_recc_iq_front_times.argtypes = [C.c_void_p, f32p, C.c_int, C.POINTER(C.c_int)]
+    L.amps_recc_iq_batch_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_uint32, C.POINTER(C.c_void_p)]
+    L.amps_recc_iq_batch_destroy.argtypes = [C.c_void_p]
+    L.amps_recc_iq_batch_size.argtypes = [C.c_void_p]
+    L.amps_recc_iq_batch_submit_dev.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_void_p]
+    L.amps_recc_iq_batch_work_shared.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, BATCH_BURST_CB, C.c_void_p]
+    L.amps_recc_iq_batch_front_times.argtypes = [C.c_void_p, f32p, C.c_int, C.POINTER(C.c_int)]
+    L.amps_recc_iq_batch_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.amps_recc_decode_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
     L.amps_recc_decode_destroy.argtypes = [C.c_void_p]
     L.amps_recc_decode_burst.argtypes = [C.c_void_p, u8p, C.POINTER(ReccWords)]
@@ -281,6 +291,7 @@ class ReccIq:
         check(lib().amps_recc_iq_stats(self.h, *[C.byref(x) for x in v]))
         return dict(samples_in=v[0].value, demod_out=v[1].value, bursts=v[2].value, kernel_launches=v[3].value)
 
+
     def front_times_ms(self, cap: int = 256) -> np.ndarray:
         out = np.zeros(cap, np.float32)
         n = C.c_int(0)
@@ -293,6 +304,58 @@ class ReccIq:
         lib().amps_recc_iq_get_taps(self.h, t.ctypes.data_as(f32p), n)
         return t
 
+
+class ReccIqBatch:
+    """K ReccIq handles of one GPU served by one front launch + one capture launch per call (amps_recc_iq_batch_*)."""
+
+    def __init__(self, handles: list, time_kernels=False):
+        self.handles = list(handles)
+        arr = (C.c_void_p * len(handles))(*[h.h for h in handles])
+        self.b = C.c_void_p()
+        check(lib().amps_recc_iq_batch_create(arr, len(handles), RX_TIME_KERNELS if time_kernels else 0, C.byref(self.b)))
+
+    def close(self):
+        if getattr(self, "b", None):
+            lib().amps_recc_iq_batch_destroy(self.b)
+            self.b = None
+
+    __del__ = close
+
+    def submit_dev(self, dev_ptrs, nsamples, stream: int = 0):
+        k = len(self.handles)
+        ns = [nsamples] * k if isinstance(nsamples, int) else list(nsamples)
+        ptrs = (C.c_void_p * k)(*dev_ptrs)
+        cnt = (C.c_size_t * k)(*ns)
+        check(lib().amps_recc_iq_batch_submit_dev(self.b, ptrs, cnt, C.c_void_p(stream)))
+
+    def work_shared(self, iq: np.ndarray) -> list:
+        """One host buffer for every channel; returns [(channel, Burst), ...]."""
+        iq = np.ascontiguousarray(iq)
+        n = iq.size if iq.dtype == np.complex64 else iq.size // 2
+        got = []
+
+        def on(ch, bp, _user):
+            b = Burst()
+            C.memmove(C.byref(b), bp, C.sizeof(Burst))
+            got.append((ch, b))
+
+        cb = BATCH_BURST_CB(on)
+        check(lib().amps_recc_iq_batch_work_shared(self.b, iq.ctypes.data_as(C.c_void_p), n, cb, None))
+        return got
+
+    def work_shared_ptr(self, host_ptr: int, nsamples: int, cb=None):
+        check(lib().amps_recc_iq_batch_work_shared(self.b, C.c_void_p(host_ptr), nsamples, cb or C.cast(None, BATCH_BURST_CB), None))
+
+    def front_times_ms(self, cap=256) -> np.ndarray:
+        out = np.zeros(cap, np.float32)
+        n = C.c_int(0)
+        check(lib().amps_recc_iq_batch_front_times(self.b, out.ctypes.data_as(f32p), cap, C.byref(n)))
+        return out[:n.value]
+
+    def stats(self) -> dict:
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        check(lib().amps_recc_iq_batch_stats(self.b, C.byref(a), C.byref(b)))
+        return dict(calls=a.value, kernel_launches=b.value)
 
 class ReccDecode:
     """Message-only burst decoder (amps_recc_decode_*)."""

@@ -1,5 +1,5 @@
-// c_api_rx.cu -- extern "C" entry points of the receive side: amps_recc_iq_* (fused IQ path) and
-// amps_recc_decode_* (message-only burst decoder).  See include/amps_b200.h for the contract and
+// c_api_rx.cu -- extern "C" entry points of the receive side: amps_recc_iq_* (fused IQ path, single channel and batched)
+// and amps_recc_decode_* (message-only burst decoder).  See include/amps_b200.h for the contract and
 // the reference interfaces each entry point replaces.
 #include "common.h"
 #include "design.h"
@@ -13,6 +13,8 @@
 
 using namespace amps;
 
+struct amps_recc_iq_batch;
+
 struct amps_recc_iq {
     int          device = 0;
     int          sm_count = 0;
@@ -23,16 +25,18 @@ struct amps_recc_iq {
     std::vector<float> lpf;
     uint32_t     fcw = 0;
     bool         native400 = false;      // samp_rate == 400e3: the reference's own rate, no CIC stage
-    uint32_t     pass_in = kPass;        // input samples per pass (API granularity)
+    uint32_t     gran = kUnit;           // input samples per processing quantum (API granularity)
     uint32_t     hist = kHist;           // input samples of history carried between calls
     uint32_t     decim = kD1 * kD2;      // input samples per demodulated sample
+    uint32_t     gran_out = kUnitOut;    // demodulated samples per quantum
 
-    RxFrontParams fp{};                  // constant part filled at create
+    RxFrontParams1   fp{};               // 10 MS/s: constant part filled at create
+    RxFront400Params fp400{};            // 400 kS/s: constant part filled at create
     bool         sc16 = false;           // AMPS_RX_INPUT_SC16: interleaved int16 I/Q instead of float
     bool         sc16_unit = false;      // sc16 scale is a power of two: folded into the NCO tables, no multiply in the kernel
     size_t       isz = sizeof(float2);   // bytes per complex input sample (8 or 4)
     uint8_t     *d_stage = nullptr;      // host path: [carry | new chunk]
-    uint8_t     *d_tail[2] = {nullptr, nullptr};
+    uint8_t     *d_tail[2] = {nullptr, nullptr};   // history (+ device-path carry) of the next call, double-buffered
     int          tail_cur = 0;
     float       *d_dring = nullptr;
     uint32_t    *d_hring = nullptr;      // hard decisions (d >= 0), 1 bit per demod sample, same ring indexing
@@ -42,19 +46,23 @@ struct amps_recc_iq {
     uint64_t     ydump_first = 0, ydump_count = 0;
     RxState     *d_state = nullptr;
     Candidate   *d_cand = nullptr;
-    Accepted    *d_acc = nullptr;        // bursts accepted by the last select (kMaxAccept entries)
-    amps_burst  *h_ring = nullptr;       // mapped pinned host ring the select kernel publishes into
+    Accepted    *d_acc = nullptr;        // bursts accepted by the select of call parity 0 / 1 (2 x kMaxAccept entries)
+    uint32_t    *d_flags = nullptr;      // per-CTA completion flags of the front kernel (kMaxGrid words)
+    amps_burst  *h_ring = nullptr;       // mapped pinned host ring the capture kernel publishes into
     RxPublished *h_pub = nullptr;        // mapped pinned counters
     uint64_t     consumed = 0;           // bursts already handed to the caller
     uint64_t     lost = 0;               // bursts overwritten in the ring before they were collected
+    uint32_t     overflow_seen = 0;      // candidate-list overflows already reported to the caller
     cudaStream_t last_stream = nullptr;
-    cudaStream_t side = nullptr;         // detect / select / capture run here, overlapped with the next front kernel
+    cudaStream_t side = nullptr;         // capture (and the M&M / 400 kS/s tails) run here, overlapped with the next front kernel
     cudaEvent_t  ev_front = nullptr;     // front kernel of the current call finished
-    cudaEvent_t  ev_side[2] = {nullptr, nullptr};   // detection of call k finished (k & 1)
+    cudaEvent_t  ev_side[2] = {nullptr, nullptr};   // tail of call k finished (k & 1)
     uint64_t     call_no = 0;
     bool         serial = false;         // AMPS_RX_SERIAL=1: no overlap (profiling / A-B measurements)
-    int          diag = 0;               // AMPS_RX_DIAG (measurement aid): 1 = no capture launch, 2 = no detect/select launch
-    bool         front_only = false;     // AMPS_RX_FRONT_ONLY=1: no detection at all (pipeline measurements only: no bursts come out)
+    bool         front_only = false;     // AMPS_RX_FRONT_ONLY=1: no capture (pipeline measurements only: no bursts come out)
+    bool         defer_all = false;      // AMPS_RX_DEFER=1 (test hook): every boundary search is left to the channel's last CTA
+    int          grid_cap = 0;           // AMPS_RX_GRID (test hook): cap on the front kernel's grid
+    amps_recc_iq_batch *batch = nullptr; // the handle is driven through a batch
     // AMPS_RX_TIMING_MM: the reference graph's serial tail instead of the feed-forward detector
     bool         mm_mode = false;
     MmState     *d_mm = nullptr;
@@ -65,12 +73,34 @@ struct amps_recc_iq {
     uint8_t     *d_blobs = nullptr;
     unsigned long long *d_blob_idx = nullptr;
 
-    size_t       carry = 0;              // unprocessed samples sitting at the front of d_stage
+    size_t       carry = 0;              // host path: unprocessed samples sitting at the front of d_stage
+    uint32_t     dev_carry = 0;          // device path: unprocessed samples sitting behind the history in d_tail[tail_cur]
     uint64_t     samples_in = 0;         // samples handed to the kernels
     uint64_t     total_d = 0;            // demod samples produced
-    uint64_t     scan_hi = 0;            // positions below this have been searched
+    uint64_t     groups_done = 0;        // 400 kS/s: trigger-search groups already searched
     uint64_t     bursts = 0, launches = 0;
     // AMPS_RX_TIME_KERNELS: ring of event pairs around the front-end kernel
+    static constexpr int kEv = 256;
+    cudaEvent_t  ev0[kEv] = {}, ev1[kEv] = {};
+    uint64_t     ev_count = 0;
+};
+
+// A set of channels (handles) served by ONE front launch + ONE capture launch per call: K carriers of one GPU, or K
+// independent buffers.  The handles keep their own rings and records; the batch owns the streams and the call counter.
+struct amps_recc_iq_batch {
+    int          device = 0;
+    int          sm_count = 0;
+    std::vector<amps_recc_iq *> ch;
+    bool         sc16 = false, sc16_unit = false;
+    size_t       isz = sizeof(float2);
+    cudaStream_t stream = nullptr, side = nullptr, last_stream = nullptr;
+    cudaEvent_t  ev_front = nullptr, ev_side[2] = {nullptr, nullptr};
+    uint64_t     call_no = 0;
+    uint64_t     launches = 0;
+    uint8_t     *d_stage = nullptr;      // shared-buffer host path: [carry | new chunk], every channel reads it
+    uint32_t     stage_cap = 0;          // samples
+    size_t       carry = 0;
+    bool         timed = false;
     static constexpr int kEv = 256;
     cudaEvent_t  ev0[kEv] = {}, ev1[kEv] = {};
     uint64_t     ev_count = 0;
@@ -87,16 +117,18 @@ static int mm_reset(amps_recc_iq *h) {
     return AMPS_OK;
 }
 
+static size_t tail_samples(const amps_recc_iq *h) { return (size_t)h->hist + h->gran; }
+
 static int rx_alloc(amps_recc_iq *h) {
-    const size_t max_d = (size_t)h->max_samples / h->decim + kPassOut;
+    const size_t max_d = ((size_t)h->max_samples + h->gran) / h->decim + kPassOut;
     size_t cap = 1;
-    // two calls' worth: the detection of call k overlaps the front kernel of call k+1
+    // two calls' worth: the capture of call k overlaps the front kernel of call k+1
     while (cap < 2 * max_d + (size_t)kSpan + 4096) cap <<= 1;
     h->dmask = (uint32_t)(cap - 1);
-    CK(cudaMalloc(&h->d_stage, ((size_t)h->max_samples + h->pass_in) * h->isz));
+    CK(cudaMalloc(&h->d_stage, ((size_t)h->max_samples + h->gran) * h->isz));
     for (int i = 0; i < 2; ++i) {
-        CK(cudaMalloc(&h->d_tail[i], (size_t)h->hist * h->isz));
-        CK(cudaMemset(h->d_tail[i], 0, (size_t)h->hist * h->isz));
+        CK(cudaMalloc(&h->d_tail[i], tail_samples(h) * h->isz));
+        CK(cudaMemset(h->d_tail[i], 0, tail_samples(h) * h->isz));
     }
     CK(cudaMalloc(&h->d_dring, cap * sizeof(float)));
     CK(cudaMemset(h->d_dring, 0, cap * sizeof(float)));
@@ -108,8 +140,10 @@ static int rx_alloc(amps_recc_iq *h) {
     }
     CK(cudaMalloc(&h->d_state, sizeof(RxState)));
     CK(cudaMemset(h->d_state, 0, sizeof(RxState)));
-    CK(cudaMalloc(&h->d_cand, sizeof(Candidate) * kMaxCand * 2));      // candidates + the select kernel's sorted copy
-    CK(cudaMalloc(&h->d_acc, sizeof(Accepted) * kMaxAccept));
+    CK(cudaMalloc(&h->d_cand, sizeof(Candidate) * kMaxCand * 2));      // candidates + the select's sorted copy
+    CK(cudaMalloc(&h->d_acc, sizeof(Accepted) * kMaxAccept * 2));
+    CK(cudaMalloc(&h->d_flags, sizeof(uint32_t) * kMaxGrid));
+    CK(cudaMemset(h->d_flags, 0, sizeof(uint32_t) * kMaxGrid));
     if (h->mm_mode) {
         h->sym_cap = (uint32_t)(max_d / 8 + 64);
         const std::vector<float> tab = mmse_interp_table();
@@ -151,10 +185,10 @@ extern "C" int amps_recc_iq_create(const amps_recc_iq_params *params, amps_recc_
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, params->device);
     h->sm_count = prop.multiProcessorCount;
-    // round the per-call capacity up to whole passes
     h->native400 = params->samp_rate == 400e3;
-    if (h->native400) { h->pass_in = kPass400; h->hist = kPass400; h->decim = kD2; }
-    h->max_samples = (uint32_t)(((uint64_t)params->max_samples + h->pass_in - 1) / h->pass_in * h->pass_in);
+    if (h->native400) { h->gran = kPass400; h->hist = kPass400; h->decim = kD2; h->gran_out = kPassOut; }
+    // round the per-call capacity up to whole processing quanta
+    h->max_samples = (uint32_t)(((uint64_t)params->max_samples + h->gran - 1) / h->gran * h->gran);
     h->max_records = params->max_bursts ? params->max_bursts : 256;
     h->flags = params->flags;
     h->mm_mode = (params->flags & AMPS_RX_TIMING_MM) != 0;
@@ -162,28 +196,37 @@ extern "C" int amps_recc_iq_create(const amps_recc_iq_params *params, amps_recc_
     h->isz = h->sc16 ? sizeof(short2) : sizeof(float2);
     { const char *e = std::getenv("AMPS_RX_SERIAL"); h->serial = e && e[0] == '1'; }
     { const char *e = std::getenv("AMPS_RX_FRONT_ONLY"); h->front_only = e && e[0] == '1'; }
-    { const char *e = std::getenv("AMPS_RX_DIAG"); h->diag = e ? std::atoi(e) : 0; }
+    { const char *e = std::getenv("AMPS_RX_DEFER"); h->defer_all = e && e[0] == '1'; }
+    { const char *e = std::getenv("AMPS_RX_GRID"); h->grid_cap = e ? std::atoi(e) : 0; }
     if (params->lpf_taps) h->lpf.assign(params->lpf_taps, params->lpf_taps + params->n_lpf_taps);
     else h->lpf = firdes_low_pass(3.0, 400e3, 10e3, 4500.0, WIN_BLACKMAN);     // grc/ampsbs.grc:138-184
     h->fcw = nco_fcw(params->center_freq, params->samp_rate);
 
     std::memset(&h->fp, 0, sizeof h->fp);
-    h->fp.fcw25 = (uint32_t)(25u * h->fcw);
-    h->fp.in_scale = params->sc16_scale != 0.0f ? params->sc16_scale : 1.0f / 32768.0f;
-    nco_block_table(h->fcw, kD1, reinterpret_cast<float *>(h->fp.w));
+    std::memset(&h->fp400, 0, sizeof h->fp400);
+    RxChan &c = h->fp.ch[0];
+    c.fcw25 = (uint32_t)(25u * h->fcw);
+    c.in_scale = params->sc16_scale != 0.0f ? params->sc16_scale : 1.0f / 32768.0f;
+    nco_block_table(h->fcw, kD1, reinterpret_cast<float *>(c.w));
     if (h->sc16) {
         int e = 0;
-        const float m = std::frexp(h->fp.in_scale, &e);
+        const float m = std::frexp(c.in_scale, &e);
         if (m == 0.5f && e > -40 && e < 40) {                       // power of two: (I s) w == I (s w) exactly
             h->sc16_unit = true;
-            for (int k = 0; k < kD1; ++k) { h->fp.w[k].x *= h->fp.in_scale; h->fp.w[k].y *= h->fp.in_scale; }
+            for (int k = 0; k < kD1; ++k) { c.w[k].x *= c.in_scale; c.w[k].y *= c.in_scale; }
         }
     }
-    for (int k = 0; k < kD1; ++k) h->fp.wj[k] = make_float2(-h->fp.w[k].y, h->fp.w[k].x);
+    for (int k = 0; k < kD1; ++k) h->fp.wj0[k] = make_float2(-c.w[k].y, c.w[k].x);
     std::vector<float> cic;
     cic3_taps(kD1, cic);
     for (size_t i = 0; i < cic.size(); ++i) h->fp.g[i] = cic[i];
     for (size_t i = 0; i < h->lpf.size(); ++i) h->fp.h2[i] = h->lpf[i];
+    h->fp.nchan = 1;
+    h->fp.defer_all = h->defer_all ? 1u : 0u;
+    h->fp400.fcw25 = c.fcw25;
+    h->fp400.in_scale = c.in_scale;
+    for (int k = 0; k < kD1; ++k) { h->fp400.w[k] = c.w[k]; h->fp400.wj[k] = h->fp.wj0[k]; }
+    for (size_t i = 0; i < h->lpf.size(); ++i) h->fp400.h2[i] = h->lpf[i];
 
     cudaError_t ce = rx_configure_device();
     if (ce != cudaSuccess) { delete h; return set_cuda_error(ce, "rx_configure_device"); }
@@ -203,7 +246,7 @@ extern "C" int amps_recc_iq_destroy(amps_recc_iq *h) {
     for (int i = 0; i < 2; ++i) if (h->ev_side[i]) cudaEventDestroy(h->ev_side[i]);
     for (int i = 0; i < amps_recc_iq::kEv; ++i) { if (h->ev0[i]) cudaEventDestroy(h->ev0[i]); if (h->ev1[i]) cudaEventDestroy(h->ev1[i]); }
     cudaFree(h->d_stage); cudaFree(h->d_tail[0]); cudaFree(h->d_tail[1]); cudaFree(h->d_dring); cudaFree(h->d_hring);
-    cudaFree(h->d_ydump); cudaFree(h->d_state); cudaFree(h->d_cand); cudaFree(h->d_acc);
+    cudaFree(h->d_ydump); cudaFree(h->d_state); cudaFree(h->d_cand); cudaFree(h->d_acc); cudaFree(h->d_flags);
     cudaFree(h->d_mm); cudaFree(h->d_mmtab); cudaFree(h->d_sym); cudaFree(h->d_compat); cudaFree(h->d_blobs); cudaFree(h->d_blob_idx);
     if (h->h_ring) cudaFreeHost(h->h_ring);
     if (h->h_pub) cudaFreeHost(h->h_pub);
@@ -215,22 +258,137 @@ extern "C" int amps_recc_iq_reset(amps_recc_iq *h) {
     if (!h) return set_error(AMPS_E_INVAL, "null handle");
     CK(cudaSetDevice(h->device));
     CK(cudaDeviceSynchronize());
-    for (int i = 0; i < 2; ++i) CK(cudaMemset(h->d_tail[i], 0, (size_t)h->hist * h->isz));
+    for (int i = 0; i < 2; ++i) CK(cudaMemset(h->d_tail[i], 0, tail_samples(h) * h->isz));
     CK(cudaMemset(h->d_state, 0, sizeof(RxState)));
+    CK(cudaMemset(h->d_flags, 0, sizeof(uint32_t) * kMaxGrid));
     CK(cudaMemset(h->d_dring, 0, ((size_t)h->dmask + 1) * sizeof(float)));
     if (h->mm_mode) { int rc = mm_reset(h); if (rc != AMPS_OK) return rc; }
     std::memset(h->h_pub, 0, sizeof(RxPublished));
-    h->consumed = 0; h->call_no = 0;
-    h->tail_cur = 0; h->carry = 0; h->samples_in = 0; h->total_d = 0; h->scan_hi = 0;
+    h->consumed = 0; h->call_no = 0; h->overflow_seen = 0;
+    h->tail_cur = 0; h->carry = 0; h->dev_carry = 0; h->samples_in = 0; h->total_d = 0; h->groups_done = 0;
     h->ydump_first = 0; h->ydump_count = 0;
     return AMPS_OK;
 }
 
-extern "C" int amps_recc_iq_granularity(const amps_recc_iq *h) { return h ? (int)h->pass_in : kPass; }
+extern "C" int amps_recc_iq_granularity(const amps_recc_iq *h) { return h ? (int)h->gran : kUnit; }
 
-// Enqueue everything for `npass` passes whose samples start at d_chunk.
-static int rx_enqueue(amps_recc_iq *h, const uint8_t *d_chunk, uint32_t npass, cudaStream_t st) {
-    RxFrontParams p = h->fp;
+// ---- per-channel pieces of a 10 MS/s call -----------------------------------------------------
+// Fills the launch arguments of one channel for `units` whole units out of [tail carry | chunk] and advances the handle's
+// host-side stream position.  par = call parity of whoever owns the call counter (the handle or its batch).
+static void chan_begin(amps_recc_iq *h, RxChan &c, const uint8_t *d_chunk, uint32_t nchunk, uint32_t units, uint32_t par, uint32_t epoch) {
+    c = h->fp.ch[0];                                   // constant part (NCO tables, scale)
+    c.chunk = d_chunk;
+    c.tail = h->d_tail[h->tail_cur];
+    c.tail_out = h->d_tail[h->tail_cur ^ 1];
+    c.dring = h->d_dring;
+    c.hring = h->d_hring;
+    c.ydump = h->d_ydump;
+    c.state = h->d_state;
+    c.cand = h->d_cand;
+    c.acc = h->d_acc;
+    c.host_pub = h->h_pub;
+    c.flags = h->d_flags;
+    c.q_base = h->total_d;
+    c.dmask = h->dmask;
+    c.units = units;
+    c.carry = h->dev_carry;
+    c.nchunk = nchunk;
+    c.blk_base = (uint32_t)(h->samples_in / kD1);
+    c.epoch = epoch;
+    c.par = par;
+    c.search = h->mm_mode ? 0u : 1u;
+    h->tail_cur ^= 1;
+    h->dev_carry = h->dev_carry + nchunk - units * (uint32_t)kUnit;
+    h->ydump_first = h->total_d;
+    h->ydump_count = (uint64_t)units * kUnitOut;
+    h->samples_in += (uint64_t)units * kUnit;
+    h->total_d += (uint64_t)units * kUnitOut;
+}
+
+static void chan_capture(const amps_recc_iq *h, RxCaptureChan &cc, uint32_t par, uint32_t cta_first, uint32_t cta_count) {
+    cc.dring = h->d_dring;
+    cc.state = h->d_state;
+    cc.acc = h->d_acc + (size_t)par * kMaxAccept;
+    cc.host_ring = h->h_ring;
+    cc.host_pub = h->h_pub;
+    cc.blobs = h->mm_mode ? h->d_blobs : nullptr;
+    cc.blob_sym_index = h->mm_mode ? h->d_blob_idx : nullptr;
+    cc.dmask = h->dmask;
+    cc.ring_len = h->max_records;
+    cc.decim = h->decim;
+    cc.par = par;
+    cc.cta_first = cta_first;
+    cc.cta_count = cta_count;
+}
+
+// bursts one call of `outputs` demodulated samples can make capturable: they are at least kBurstLen apart, +1 for a run
+// that became decidable at the edge, +1 for leftovers of a call that had more than the list holds
+static uint32_t capture_ctas(uint64_t outputs) {
+    uint64_t n = outputs / (uint64_t)kBurstLen + 2;
+    return (uint32_t)(n > (uint64_t)kMaxAccept ? (uint64_t)kMaxAccept : n);
+}
+
+// fewer than one unit in [carry | chunk]: nothing to launch, the samples join the carry behind the history
+static int chan_append_carry(amps_recc_iq *h, const uint8_t *d_chunk, uint32_t nchunk, cudaStream_t st) {
+    if (nchunk)
+        CK(cudaMemcpyAsync(h->d_tail[h->tail_cur] + ((size_t)h->hist + h->dev_carry) * h->isz, d_chunk, (size_t)nchunk * h->isz,
+                           cudaMemcpyDeviceToDevice, st));
+    h->dev_carry += nchunk;
+    return AMPS_OK;
+}
+
+// Enqueue everything for one call of a single 10 MS/s channel: [tail carry | nchunk samples at d_chunk].
+static int rx_enqueue10(amps_recc_iq *h, const uint8_t *d_chunk, uint32_t nchunk, cudaStream_t st) {
+    const uint32_t units = (h->dev_carry + nchunk) / (uint32_t)kUnit;
+    h->last_stream = st;
+    if (units == 0) return chan_append_carry(h, d_chunk, nchunk, st);
+    const uint32_t par = (uint32_t)(h->call_no & 1u);
+    // the demod ring and the accepted-burst lists hold two calls: do not overwrite what the capture of call k-2 may still read
+    if (h->call_no >= 2) CK(cudaStreamWaitEvent(st, h->ev_side[par], 0));
+    RxFrontParams1 p = h->fp;
+    chan_begin(h, p.ch[0], d_chunk, nchunk, units, par, (uint32_t)(h->call_no + 1));
+    const uint32_t tiles = rx_tiles_of(units);
+    p.tile_cum[0] = 0; p.tile_cum[1] = tiles;
+    uint32_t grid = (uint32_t)rx_front_ctas_per_sm(h->sc16) * (uint32_t)h->sm_count;
+    if (h->grid_cap > 0 && grid > (uint32_t)h->grid_cap) grid = (uint32_t)h->grid_cap;
+    if (grid > (uint32_t)kMaxGrid) grid = kMaxGrid;
+    if (grid > tiles) grid = tiles;
+    const bool timed = (h->flags & AMPS_RX_TIME_KERNELS) != 0;
+    const int  evi = (int)(h->ev_count % amps_recc_iq::kEv);
+    if (timed) CK(cudaEventRecord(h->ev0[evi], st));
+    CKL(launch_rx_front(p, (int)grid, st, h->sc16, h->sc16_unit));
+    if (timed) { CK(cudaEventRecord(h->ev1[evi], st)); h->ev_count++; }
+    h->launches++;
+    // capture (and the M&M tail) on the side stream, so that the next call's front kernel (HBM-bound, 2 CTAs/SM) overlaps
+    // these small latency-bound kernels
+    CK(cudaEventRecord(h->ev_front, st));
+    cudaStream_t sd = h->serial ? st : h->side;
+    if (!h->serial) CK(cudaStreamWaitEvent(sd, h->ev_front, 0));
+    if (!h->front_only) {
+        RxCaptureParams cp;
+        cp.nchan = 1;
+        uint32_t nc = capture_ctas((uint64_t)units * kUnitOut);
+        if (h->mm_mode) {
+            // serial tail: M&M + slicer over everything demodulated so far, amps.recc on the new half-symbols, then
+            // one CTA per blob decodes and publishes it
+            CKL(launch_rx_mm(h->d_dring, h->dmask, h->total_d, h->d_mm, h->d_mmtab, h->d_sym, h->sym_cap, h->d_compat, h->d_blobs,
+                             h->d_blob_idx, kMaxAccept, h->d_state, h->h_pub, par, sd));
+            uint64_t mx = (uint64_t)units * kUnitOut / (8u * (unsigned)kMmQuantum) + 2;      // <= one blob per work() quantum
+            nc = (uint32_t)(mx > (uint64_t)kMaxAccept ? (uint64_t)kMaxAccept : mx);
+            h->launches += 2;
+        }
+        chan_capture(h, cp.ch[0], par, 0, nc);
+        CKL(launch_rx_capture(cp, (int)nc, sd));
+        h->launches++;
+    }
+    CK(cudaEventRecord(h->ev_side[par], sd));
+    h->call_no++;
+    return AMPS_OK;
+}
+
+// Enqueue everything for `npass` whole passes of the 400 kS/s front end whose samples start at d_chunk.
+static int rx_enqueue400(amps_recc_iq *h, const uint8_t *d_chunk, uint32_t npass, cudaStream_t st) {
+    RxFront400Params p = h->fp400;
     p.chunk = d_chunk;
     p.tail = h->d_tail[h->tail_cur];
     p.dring = h->d_dring;
@@ -238,65 +396,51 @@ static int rx_enqueue(amps_recc_iq *h, const uint8_t *d_chunk, uint32_t npass, c
     p.dmask = h->dmask;
     p.q_base = h->total_d;
     p.npass = npass;
-    p.blk_base = (uint32_t)(h->samples_in / kD1);
     p.n_base = h->samples_in;
     p.ydump = h->d_ydump;
-    // whole passes per CTA, grid sized so that (nearly) every CTA gets the same count within one wave
-    const uint32_t resident = (uint32_t)rx_front_ctas_per_sm(h->sc16) * (uint32_t)h->sm_count;
+    const uint32_t resident = 4u * (uint32_t)h->sm_count;
     p.pass_per_cta = (npass + resident - 1u) / resident;
     const int grid = (int)((npass + p.pass_per_cta - 1u) / p.pass_per_cta);
-    // the demod ring holds two calls: do not overwrite what the detection of call k-2 may still read
-    const int par = (int)(h->call_no & 1u);
+    const uint32_t par = (uint32_t)(h->call_no & 1u);
     if (h->call_no >= 2) CK(cudaStreamWaitEvent(st, h->ev_side[par], 0));
     const bool timed = (h->flags & AMPS_RX_TIME_KERNELS) != 0;
     const int  evi = (int)(h->ev_count % amps_recc_iq::kEv);
     if (timed) CK(cudaEventRecord(h->ev0[evi], st));
-    p.tail_out = h->native400 ? nullptr : h->d_tail[h->tail_cur ^ 1];
-    if (h->native400) CKL(launch_rx_front400(p, grid, st, h->sc16, h->sc16_unit));
-    else CKL(launch_rx_front(p, grid, st, h->sc16, h->sc16_unit));
+    CKL(launch_rx_front400(p, grid, st, h->sc16, h->sc16_unit));
     if (timed) { CK(cudaEventRecord(h->ev1[evi], st)); h->ev_count++; }
     h->launches++;
-    // history for the next call = the tail of this one (the 10 MS/s front kernel copies it itself)
-    if (h->native400)
-        CK(cudaMemcpyAsync(h->d_tail[h->tail_cur ^ 1], d_chunk + ((size_t)npass * h->pass_in - h->hist) * h->isz, (size_t)h->hist * h->isz,
-                           cudaMemcpyDeviceToDevice, st));
+    // history for the next call = the tail of this one
+    CK(cudaMemcpyAsync(h->d_tail[h->tail_cur ^ 1], d_chunk + ((size_t)npass * h->gran - h->hist) * h->isz, (size_t)h->hist * h->isz,
+                       cudaMemcpyDeviceToDevice, st));
     h->tail_cur ^= 1;
     h->ydump_first = h->total_d;
     h->ydump_count = (uint64_t)npass * kPassOut;
-    h->samples_in += (uint64_t)npass * h->pass_in;
+    h->samples_in += (uint64_t)npass * h->gran;
     h->total_d += (uint64_t)npass * kPassOut;
-    // search every position whose capture is complete -- on the side stream, so that the next call's
-    // front kernel (HBM-bound, 2 CTAs/SM) overlaps these small latency-bound kernels
     CK(cudaEventRecord(h->ev_front, st));
     cudaStream_t sd = h->serial ? st : h->side;
     if (!h->serial) CK(cudaStreamWaitEvent(sd, h->ev_front, 0));
-    if (h->front_only) {
-        // measurement aid: nothing after the front kernel
-    } else if (h->mm_mode) {
-        // serial tail: M&M + slicer over everything demodulated so far, amps.recc on the new half-symbols, then
-        // one CTA per blob decodes and publishes it
-        CKL(launch_rx_mm(h->d_dring, h->dmask, h->total_d, h->d_mm, h->d_mmtab, h->d_sym, h->sym_cap, h->d_compat, h->d_blobs,
-                         h->d_blob_idx, kMaxAccept, h->d_state, h->h_pub, sd));
-        int max_new = (int)((uint64_t)npass * kPassOut / (8u * (unsigned)kMmQuantum)) + 2;   // <= one blob per work() quantum
-        if (max_new > kMaxAccept) max_new = kMaxAccept;
-        CKL(launch_rx_capture(h->d_dring, h->dmask, h->d_state, h->d_acc, max_new, h->h_ring, h->max_records, h->h_pub, h->decim, sd,
-                              h->d_blobs, h->d_blob_idx));
-        h->launches += 3;
-    } else if (h->total_d > (uint64_t)kSpan) {
-        const uint64_t hi = h->total_d - (uint64_t)kSpan;
-        const uint64_t lo = h->scan_hi > 64 ? h->scan_hi - 64 : 0;
-        if (hi > h->scan_hi) {
-            if (!(h->diag & 2)) {
-            CKL(launch_rx_detect(h->d_dring, h->d_hring, h->dmask, h->d_state, h->d_cand, lo, hi, 0, sd));
-            CKL(launch_rx_select(h->d_state, h->d_cand, h->d_acc, hi, h->h_pub, sd));
-            }
-            // at most one burst per kBurstLen searched positions (+1 for a run deferred from the last call)
-            const int max_new = (int)((hi - lo) / (uint64_t)kBurstLen) + 2;
-            if (!(h->diag & 1))
-            CKL(launch_rx_capture(h->d_dring, h->dmask, h->d_state, h->d_acc, max_new, h->h_ring, h->max_records, h->h_pub, h->decim, sd));
-            h->launches += 3;
-            h->scan_hi = hi;
+    if (!h->front_only) {
+        RxCaptureParams cp;
+        cp.nchan = 1;
+        uint32_t nc = capture_ctas((uint64_t)npass * kPassOut);
+        if (h->mm_mode) {
+            CKL(launch_rx_mm(h->d_dring, h->dmask, h->total_d, h->d_mm, h->d_mmtab, h->d_sym, h->sym_cap, h->d_compat, h->d_blobs,
+                             h->d_blob_idx, kMaxAccept, h->d_state, h->h_pub, par, sd));
+            uint64_t mx = (uint64_t)npass * kPassOut / (8u * (unsigned)kMmQuantum) + 2;
+            nc = (uint32_t)(mx > (uint64_t)kMaxAccept ? (uint64_t)kMaxAccept : mx);
+            h->launches += 2;
+        } else {
+            // search every group whose lookahead is complete, then select (one launch)
+            const uint64_t g_hi = h->total_d / kUnitOut >= (uint64_t)kGroupLag ? h->total_d / kUnitOut - kGroupLag : 0;
+            CKL(launch_rx_search(h->d_dring, h->d_hring, h->dmask, h->d_state, h->d_cand, h->d_acc, h->h_pub, h->groups_done,
+                                 g_hi > h->groups_done ? g_hi : h->groups_done, h->total_d, par, sd));
+            if (g_hi > h->groups_done) h->groups_done = g_hi;
+            h->launches++;
         }
+        chan_capture(h, cp.ch[0], par, 0, nc);
+        CKL(launch_rx_capture(cp, (int)nc, sd));
+        h->launches++;
     }
     CK(cudaEventRecord(h->ev_side[par], sd));
     h->call_no++;
@@ -306,14 +450,21 @@ static int rx_enqueue(amps_recc_iq *h, const uint8_t *d_chunk, uint32_t npass, c
 
 static int rx_submit_dev(amps_recc_iq *h, const void *d_iq, size_t nsamples, void *cuda_stream, bool sc16) {
     if (!h || (!d_iq && nsamples)) return set_error(AMPS_E_INVAL, "null argument");
+    if (h->batch) return set_error(AMPS_E_STATE, "the handle belongs to a batch: use amps_recc_iq_batch_*");
     if (h->sc16 != sc16) return set_error(AMPS_E_STATE, sc16 ? "handle was not created with AMPS_RX_INPUT_SC16" : "handle was created with AMPS_RX_INPUT_SC16: use the _sc16 entry points");
     if (nsamples == 0) return AMPS_OK;
-    if (nsamples % h->pass_in) return set_error(AMPS_E_ALIGN, "nsamples must be a multiple of amps_recc_iq_granularity()");
     if (reinterpret_cast<uintptr_t>(d_iq) & 15u) return set_error(AMPS_E_ALIGN, "d_iq must be 16-byte aligned");
     if (nsamples > h->max_samples) return set_error(AMPS_E_OVERFLOW, "nsamples exceeds max_samples");
     if (h->carry) return set_error(AMPS_E_STATE, "host-path samples are pending; reset() or keep using work()");
     CK(cudaSetDevice(h->device));
-    return rx_enqueue(h, static_cast<const uint8_t *>(d_iq), (uint32_t)(nsamples / h->pass_in), static_cast<cudaStream_t>(cuda_stream));
+    if (h->native400) {
+        if (nsamples % h->gran) return set_error(AMPS_E_ALIGN, "nsamples must be a multiple of amps_recc_iq_granularity() at 400 kS/s");
+        return rx_enqueue400(h, static_cast<const uint8_t *>(d_iq), (uint32_t)(nsamples / h->gran), static_cast<cudaStream_t>(cuda_stream));
+    }
+    // any length whose byte count is a multiple of 16 (the bulk-copy engine's granule): what does not fill a 1600-sample unit
+    // is carried on the device to the next call
+    if ((nsamples * h->isz) & 15u) return set_error(AMPS_E_ALIGN, sc16 ? "nsamples must be a multiple of 4" : "nsamples must be a multiple of 2");
+    return rx_enqueue10(h, static_cast<const uint8_t *>(d_iq), (uint32_t)nsamples, static_cast<cudaStream_t>(cuda_stream));
 }
 extern "C" int amps_recc_iq_submit_dev(amps_recc_iq *h, const void *d_iq, size_t nsamples, void *cuda_stream) {
     return rx_submit_dev(h, d_iq, nsamples, cuda_stream, false);
@@ -323,13 +474,19 @@ extern "C" int amps_recc_iq_submit_sc16_dev(amps_recc_iq *h, const void *d_iq, s
 }
 
 // Wait for the stream; afterwards records [h->consumed, h->consumed + *n_out) sit in the host ring.
-static int rx_fetch(amps_recc_iq *h, uint64_t *n_out) {
+// *overflowed is set ONCE per overflow of the candidate list (the bursts that were captured are still delivered).
+static int rx_fetch(amps_recc_iq *h, uint64_t *n_out, bool *overflowed) {
     *n_out = 0;
-    CK(cudaStreamSynchronize(h->side));
-    CK(cudaStreamSynchronize(h->last_stream));
-    if (h->h_pub->cand_overflow)
-        return set_error(AMPS_E_OVERFLOW, h->mm_mode ? "more than 512 bursts captured in one call"
-                                                     : "trigger candidate list overflowed (more than 8192 matches in one call)");
+    *overflowed = false;
+    if (h->batch) {
+        CK(cudaStreamSynchronize(h->batch->side));
+        CK(cudaStreamSynchronize(h->batch->last_stream));       // (a null handle is the default stream)
+    } else {
+        CK(cudaStreamSynchronize(h->side));
+        CK(cudaStreamSynchronize(h->last_stream));
+    }
+    const uint32_t ov = h->h_pub->cand_overflow;
+    if (ov != h->overflow_seen) { h->overflow_seen = ov; *overflowed = true; }
     const uint64_t total = h->h_pub->nrec_total;
     if (total - h->consumed > h->max_records) {           // the ring wrapped over uncollected records
         h->lost += total - h->consumed - h->max_records;
@@ -338,30 +495,36 @@ static int rx_fetch(amps_recc_iq *h, uint64_t *n_out) {
     *n_out = total - h->consumed;
     return AMPS_OK;
 }
+static int overflow_status(const amps_recc_iq *h) {
+    return set_error(AMPS_E_OVERFLOW, h->mm_mode ? "more than 512 bursts captured in one call: the surplus was dropped (reported once; the stream goes on)"
+                                                 : "trigger candidate list overflowed (more than 8192 undecided matches): candidates were dropped (reported once; the stream goes on)");
+}
 
 extern "C" int amps_recc_iq_collect(amps_recc_iq *h, amps_burst *out, int max, int *n_out) {
     if (!h || !n_out || (max > 0 && !out)) return set_error(AMPS_E_INVAL, "null argument");
     *n_out = 0;
     CK(cudaSetDevice(h->device));
     uint64_t n = 0;
-    int rc = rx_fetch(h, &n);
+    bool ov = false;
+    int rc = rx_fetch(h, &n, &ov);
     if (rc != AMPS_OK) return rc;
     const uint64_t give = n < (uint64_t)max ? n : (uint64_t)max;     // the rest stays for the next collect
     for (uint64_t i = 0; i < give; ++i) out[i] = h->h_ring[(h->consumed + i) % h->max_records];
     h->consumed += give;
     h->bursts += give;
     *n_out = (int)give;
-    return AMPS_OK;
+    return ov ? overflow_status(h) : AMPS_OK;
 }
 
 extern "C" int amps_recc_iq_peek(amps_recc_iq *h, const amps_burst **ring, uint32_t *ring_len, uint64_t *first, uint64_t *count) {
     if (!h || !ring || !ring_len || !first || !count) return set_error(AMPS_E_INVAL, "null argument");
     CK(cudaSetDevice(h->device));
     uint64_t n = 0;
-    int rc = rx_fetch(h, &n);
+    bool ov = false;
+    int rc = rx_fetch(h, &n, &ov);
     if (rc != AMPS_OK) return rc;
     *ring = h->h_ring; *ring_len = h->max_records; *first = h->consumed; *count = n;
-    return AMPS_OK;
+    return ov ? overflow_status(h) : AMPS_OK;
 }
 
 extern "C" int amps_recc_iq_poll(amps_recc_iq *h, const amps_burst **ring, uint32_t *ring_len, uint64_t *first, uint64_t *count) {
@@ -385,21 +548,23 @@ extern "C" int amps_recc_iq_consume(amps_recc_iq *h, uint64_t count) {
 
 static int rx_work(amps_recc_iq *h, const void *iq_host, size_t nsamples, amps_burst_cb cb, void *user, bool sc16) {
     if (!h || (!iq_host && nsamples)) return set_error(AMPS_E_INVAL, "null argument");
+    if (h->batch) return set_error(AMPS_E_STATE, "the handle belongs to a batch: use amps_recc_iq_batch_*");
     if (h->sc16 != sc16) return set_error(AMPS_E_STATE, sc16 ? "handle was not created with AMPS_RX_INPUT_SC16" : "handle was created with AMPS_RX_INPUT_SC16: use the _sc16 entry points");
     if (nsamples > h->max_samples) return set_error(AMPS_E_OVERFLOW, "nsamples exceeds max_samples");
+    if (h->dev_carry) return set_error(AMPS_E_STATE, "device-path samples are pending; reset() or keep using submit_dev()");
     CK(cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
     if (nsamples)
         CK(cudaMemcpyAsync(h->d_stage + h->carry * h->isz, iq_host, nsamples * h->isz, cudaMemcpyHostToDevice, st));
     const size_t avail = h->carry + nsamples;
-    const uint32_t npass = (uint32_t)(avail / h->pass_in);
+    const uint32_t nq = (uint32_t)(avail / h->gran);       // whole processing quanta (units at 10 MS/s, passes at 400 kS/s)
     h->last_stream = st;
-    if (npass) {
-        int rc = rx_enqueue(h, h->d_stage, npass, st);
+    if (nq) {
+        int rc = h->native400 ? rx_enqueue400(h, h->d_stage, nq, st) : rx_enqueue10(h, h->d_stage, nq * h->gran, st);
         if (rc != AMPS_OK) return rc;
-        const size_t left = avail - (size_t)npass * h->pass_in;
+        const size_t left = avail - (size_t)nq * h->gran;
         if (left)
-            CK(cudaMemcpyAsync(h->d_stage, h->d_stage + (size_t)npass * h->pass_in * h->isz, left * h->isz, cudaMemcpyDeviceToDevice, st));
+            CK(cudaMemcpyAsync(h->d_stage, h->d_stage + (size_t)nq * h->gran * h->isz, left * h->isz, cudaMemcpyDeviceToDevice, st));
         h->carry = left;
     } else {
         h->carry = avail;
@@ -407,12 +572,13 @@ static int rx_work(amps_recc_iq *h, const void *iq_host, size_t nsamples, amps_b
     // deliver bursts in stream order, like message_port_pub("bursts", ...) from work() (lib/recc_impl.cc:126);
     // the callback sees the record in place in the pinned ring
     uint64_t n = 0;
-    int rc = rx_fetch(h, &n);
+    bool ov = false;
+    int rc = rx_fetch(h, &n, &ov);
     if (rc != AMPS_OK) return rc;
     if (cb) for (uint64_t i = 0; i < n; ++i) cb(&h->h_ring[(h->consumed + i) % h->max_records], user);
     h->consumed += n;
     h->bursts += n;
-    return AMPS_OK;
+    return ov ? overflow_status(h) : AMPS_OK;
 }
 extern "C" int amps_recc_iq_work(amps_recc_iq *h, const float *iq_host, size_t nsamples, amps_burst_cb cb, void *user) {
     return rx_work(h, iq_host, nsamples, cb, user, false);
@@ -459,20 +625,24 @@ extern "C" int amps_recc_iq_stats(const amps_recc_iq *h, uint64_t *samples_in, u
     return AMPS_OK;
 }
 
+static int event_times(cudaEvent_t *ev0, cudaEvent_t *ev1, uint64_t ev_count, int ring, float *ms_out, int cap, int *n_out) {
+    uint64_t have = ev_count < (uint64_t)ring ? ev_count : (uint64_t)ring;
+    if (have > (uint64_t)cap) have = (uint64_t)cap;
+    for (uint64_t k = 0; k < have; ++k) {
+        const int i = (int)((ev_count - have + k) % ring);
+        CK(cudaEventElapsedTime(&ms_out[k], ev0[i], ev1[i]));
+    }
+    *n_out = (int)have;
+    return AMPS_OK;
+}
+
 extern "C" int amps_recc_iq_front_times(amps_recc_iq *h, float *ms_out, int cap, int *n_out) {
     if (!h || !n_out || (cap > 0 && !ms_out)) return set_error(AMPS_E_INVAL, "null argument");
     *n_out = 0;
     if (!(h->flags & AMPS_RX_TIME_KERNELS)) return set_error(AMPS_E_STATE, "handle was not created with AMPS_RX_TIME_KERNELS");
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->last_stream));
-    uint64_t have = h->ev_count < (uint64_t)amps_recc_iq::kEv ? h->ev_count : (uint64_t)amps_recc_iq::kEv;
-    if (have > (uint64_t)cap) have = (uint64_t)cap;
-    for (uint64_t k = 0; k < have; ++k) {
-        const int i = (int)((h->ev_count - have + k) % amps_recc_iq::kEv);
-        CK(cudaEventElapsedTime(&ms_out[k], h->ev0[i], h->ev1[i]));
-    }
-    *n_out = (int)have;
-    return AMPS_OK;
+    return event_times(h->ev0, h->ev1, h->ev_count, amps_recc_iq::kEv, ms_out, cap, n_out);
 }
 
 extern "C" int amps_recc_iq_get_taps(const amps_recc_iq *h, float *lpf_out, int cap) {
@@ -480,6 +650,184 @@ extern "C" int amps_recc_iq_get_taps(const amps_recc_iq *h, float *lpf_out, int 
     const int n = (int)h->lpf.size();
     if (lpf_out) for (int i = 0; i < n && i < cap; ++i) lpf_out[i] = h->lpf[i];
     return n;
+}
+
+// --------------------------------------------------------------------------------------------
+// batched calls: K channels, one front launch + one capture launch (per kMaxBatch channels)
+// --------------------------------------------------------------------------------------------
+extern "C" int amps_recc_iq_batch_create(amps_recc_iq *const *handles, int count, uint32_t flags, amps_recc_iq_batch **out) {
+    if (!handles || !out || count < 1) return set_error(AMPS_E_INVAL, "bad argument");
+    *out = nullptr;
+    const amps_recc_iq *h0 = handles[0];
+    for (int i = 0; i < count; ++i) {
+        const amps_recc_iq *h = handles[i];
+        if (!h) return set_error(AMPS_E_INVAL, "null handle in the batch");
+        if (h->batch) return set_error(AMPS_E_STATE, "a handle already belongs to a batch");
+        if (h->native400 || h->mm_mode) return set_error(AMPS_E_INVAL, "batches take 10 MS/s feed-forward handles only");
+        if (h->device != h0->device || h->sc16 != h0->sc16 || h->sc16_unit != h0->sc16_unit)
+            return set_error(AMPS_E_INVAL, "all handles of a batch must share the device and the input format");
+        if (h->call_no || h->carry || h->dev_carry) return set_error(AMPS_E_STATE, "handles must be fresh (or reset) when they join a batch");
+        for (int j = 0; j < i; ++j) if (handles[j] == h) return set_error(AMPS_E_INVAL, "the same handle twice in a batch");
+    }
+    CK(cudaSetDevice(h0->device));
+    amps_recc_iq_batch *b = new (std::nothrow) amps_recc_iq_batch();
+    if (!b) return set_error(AMPS_E_NOMEM, "out of host memory");
+    b->device = h0->device; b->sm_count = h0->sm_count; b->sc16 = h0->sc16; b->sc16_unit = h0->sc16_unit; b->isz = h0->isz;
+    b->ch.assign(handles, handles + count);
+    b->timed = (flags & AMPS_RX_TIME_KERNELS) != 0;
+    cudaError_t e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->side, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_front, cudaEventDisableTiming);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&b->ev_side[i], cudaEventDisableTiming);
+    if (b->timed)
+        for (int i = 0; i < amps_recc_iq_batch::kEv && e == cudaSuccess; ++i) { e = cudaEventCreate(&b->ev0[i]); if (e == cudaSuccess) e = cudaEventCreate(&b->ev1[i]); }
+    if (e != cudaSuccess) { amps_recc_iq_batch_destroy(b); return set_cuda_error(e, "batch streams / events"); }
+    for (amps_recc_iq *h : b->ch) h->batch = b;
+    *out = b;
+    return AMPS_OK;
+}
+
+extern "C" int amps_recc_iq_batch_destroy(amps_recc_iq_batch *b) {
+    if (!b) return AMPS_OK;
+    cudaSetDevice(b->device);
+    cudaDeviceSynchronize();
+    for (amps_recc_iq *h : b->ch) if (h->batch == b) h->batch = nullptr;
+    if (b->stream) cudaStreamDestroy(b->stream);
+    if (b->side) cudaStreamDestroy(b->side);
+    if (b->ev_front) cudaEventDestroy(b->ev_front);
+    for (int i = 0; i < 2; ++i) if (b->ev_side[i]) cudaEventDestroy(b->ev_side[i]);
+    for (int i = 0; i < amps_recc_iq_batch::kEv; ++i) { if (b->ev0[i]) cudaEventDestroy(b->ev0[i]); if (b->ev1[i]) cudaEventDestroy(b->ev1[i]); }
+    cudaFree(b->d_stage);
+    delete b;
+    return AMPS_OK;
+}
+
+extern "C" int amps_recc_iq_batch_size(const amps_recc_iq_batch *b) { return b ? (int)b->ch.size() : 0; }
+
+// one call: channel i gets nsamples[i] new samples at d_iq[i] (device pointers; several channels may share one buffer)
+static int batch_enqueue(amps_recc_iq_batch *b, const void *const *d_iq, const size_t *nsamples, cudaStream_t st) {
+    const uint32_t par = (uint32_t)(b->call_no & 1u);
+    const uint32_t epoch = (uint32_t)(b->call_no + 1);
+    b->last_stream = st;
+    if (b->call_no >= 2) CK(cudaStreamWaitEvent(st, b->ev_side[par], 0));
+    const uint32_t resident = (uint32_t)rx_front_ctas_per_sm(b->sc16) * (uint32_t)b->sm_count;
+    const int evi = (int)(b->ev_count % amps_recc_iq_batch::kEv);
+    if (b->timed) CK(cudaEventRecord(b->ev0[evi], st));
+    cudaStream_t sd = b->side;
+    static thread_local RxFrontParamsB p;                  // 24 KB: not on the stack
+    size_t i = 0;
+    const size_t K = b->ch.size();
+    std::vector<RxCaptureParams> caps;
+    std::vector<uint32_t> cap_grid;
+    while (i < K) {
+        // next group of up to kMaxBatch channels that have at least one whole unit
+        const amps_recc_iq *h0 = b->ch[0];
+        std::memcpy(p.g, h0->fp.g, sizeof p.g);
+        std::memcpy(p.h2, h0->fp.h2, sizeof p.h2);
+        p.defer_all = h0->fp.defer_all;
+        uint32_t n = 0, tiles = 0, cap_ctas = 0;
+        RxCaptureParams cp;
+        p.tile_cum[0] = 0;
+        for (; i < K && n < (uint32_t)kMaxBatch; ++i) {
+            amps_recc_iq *h = b->ch[i];
+            const uint32_t nchunk = (uint32_t)nsamples[i];
+            const uint32_t units = (h->dev_carry + nchunk) / (uint32_t)kUnit;
+            if (units == 0) { int rc = chan_append_carry(h, static_cast<const uint8_t *>(d_iq[i]), nchunk, st); if (rc != AMPS_OK) return rc; continue; }
+            chan_begin(h, p.ch[n], static_cast<const uint8_t *>(d_iq[i]), nchunk, units, par, epoch);
+            tiles += rx_tiles_of(units);
+            p.tile_cum[n + 1] = tiles;
+            const uint32_t nc = capture_ctas((uint64_t)units * kUnitOut);
+            chan_capture(h, cp.ch[n], par, cap_ctas, nc);
+            cap_ctas += nc;
+            ++n;
+        }
+        if (n == 0) continue;
+        p.nchan = n;
+        cp.nchan = n;
+        uint32_t grid = resident > (uint32_t)kMaxGrid ? (uint32_t)kMaxGrid : resident;
+        if (grid > tiles) grid = tiles;
+        CKL(launch_rx_front_batch(p, (int)grid, st, b->sc16, b->sc16_unit));
+        b->launches++;
+        caps.push_back(cp);
+        cap_grid.push_back(cap_ctas);
+    }
+    if (b->timed) { CK(cudaEventRecord(b->ev1[evi], st)); b->ev_count++; }
+    CK(cudaEventRecord(b->ev_front, st));
+    CK(cudaStreamWaitEvent(sd, b->ev_front, 0));
+    for (size_t k = 0; k < caps.size(); ++k) { CKL(launch_rx_capture(caps[k], (int)cap_grid[k], sd)); b->launches++; }
+    CK(cudaEventRecord(b->ev_side[par], sd));
+    b->call_no++;
+    return AMPS_OK;
+}
+
+extern "C" int amps_recc_iq_batch_submit_dev(amps_recc_iq_batch *b, const void *const *d_iq, const size_t *nsamples, void *cuda_stream) {
+    if (!b || !d_iq || !nsamples) return set_error(AMPS_E_INVAL, "null argument");
+    if (b->carry) return set_error(AMPS_E_STATE, "host-path samples are pending; keep using amps_recc_iq_batch_work_shared()");
+    for (size_t i = 0; i < b->ch.size(); ++i) {
+        const amps_recc_iq *h = b->ch[i];
+        if (!d_iq[i] && nsamples[i]) return set_error(AMPS_E_INVAL, "null device pointer");
+        if (reinterpret_cast<uintptr_t>(d_iq[i]) & 15u) return set_error(AMPS_E_ALIGN, "d_iq[i] must be 16-byte aligned");
+        if ((nsamples[i] * h->isz) & 15u) return set_error(AMPS_E_ALIGN, b->sc16 ? "nsamples[i] must be a multiple of 4" : "nsamples[i] must be a multiple of 2");
+        if (nsamples[i] > h->max_samples) return set_error(AMPS_E_OVERFLOW, "nsamples[i] exceeds the channel's max_samples");
+    }
+    CK(cudaSetDevice(b->device));
+    return batch_enqueue(b, d_iq, nsamples, static_cast<cudaStream_t>(cuda_stream));
+}
+
+// ONE host buffer -> uploaded once -> every channel of the batch (its own center_freq) demodulates it: the carriers of one
+// wideband capture share the PCIe transfer.
+extern "C" int amps_recc_iq_batch_work_shared(amps_recc_iq_batch *b, const void *iq_host, size_t nsamples, amps_batch_burst_cb cb, void *user) {
+    if (!b || (!iq_host && nsamples)) return set_error(AMPS_E_INVAL, "null argument");
+    uint32_t cap = b->ch[0]->max_samples;
+    for (const amps_recc_iq *h : b->ch) { if (h->max_samples < cap) cap = h->max_samples; if (h->dev_carry) return set_error(AMPS_E_STATE, "device-path samples are pending"); }
+    if (nsamples > cap) return set_error(AMPS_E_OVERFLOW, "nsamples exceeds max_samples");
+    CK(cudaSetDevice(b->device));
+    if (!b->d_stage) { b->stage_cap = cap + (uint32_t)kUnit; CK(cudaMalloc(&b->d_stage, (size_t)b->stage_cap * b->isz)); }
+    cudaStream_t st = b->stream;
+    if (nsamples) CK(cudaMemcpyAsync(b->d_stage + b->carry * b->isz, iq_host, nsamples * b->isz, cudaMemcpyHostToDevice, st));
+    const size_t avail = b->carry + nsamples;
+    const size_t nq = avail / kUnit;
+    b->last_stream = st;
+    if (nq) {
+        std::vector<const void *> ptrs(b->ch.size(), b->d_stage);
+        std::vector<size_t> ns(b->ch.size(), nq * kUnit);
+        int rc = batch_enqueue(b, ptrs.data(), ns.data(), st);
+        if (rc != AMPS_OK) return rc;
+        const size_t left = avail - nq * kUnit;
+        if (left) CK(cudaMemcpyAsync(b->d_stage, b->d_stage + nq * kUnit * b->isz, left * b->isz, cudaMemcpyDeviceToDevice, st));
+        b->carry = left;
+    } else {
+        b->carry = avail;
+    }
+    bool any_ov = false;
+    for (size_t i = 0; i < b->ch.size(); ++i) {
+        amps_recc_iq *h = b->ch[i];
+        uint64_t n = 0;
+        bool ov = false;
+        int rc = rx_fetch(h, &n, &ov);
+        if (rc != AMPS_OK) return rc;
+        if (cb) for (uint64_t k = 0; k < n; ++k) cb((int)i, &h->h_ring[(h->consumed + k) % h->max_records], user);
+        h->consumed += n;
+        h->bursts += n;
+        any_ov |= ov;
+    }
+    return any_ov ? overflow_status(b->ch[0]) : AMPS_OK;
+}
+
+extern "C" int amps_recc_iq_batch_front_times(amps_recc_iq_batch *b, float *ms_out, int cap, int *n_out) {
+    if (!b || !n_out || (cap > 0 && !ms_out)) return set_error(AMPS_E_INVAL, "null argument");
+    *n_out = 0;
+    if (!b->timed) return set_error(AMPS_E_STATE, "batch was not created with AMPS_RX_TIME_KERNELS");
+    CK(cudaSetDevice(b->device));
+    CK(cudaStreamSynchronize(b->last_stream));
+    return event_times(b->ev0, b->ev1, b->ev_count, amps_recc_iq_batch::kEv, ms_out, cap, n_out);
+}
+
+extern "C" int amps_recc_iq_batch_stats(const amps_recc_iq_batch *b, uint64_t *calls, uint64_t *kernel_launches) {
+    if (!b) return set_error(AMPS_E_INVAL, "null handle");
+    if (calls) *calls = b->call_no;
+    if (kernel_launches) *kernel_launches = b->launches;
+    return AMPS_OK;
 }
 
 // --------------------------------------------------------------------------------------------

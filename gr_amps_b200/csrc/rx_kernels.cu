@@ -1,19 +1,20 @@
 // rx_kernels.cu -- fused RECC receive path for sm_100a.
 //
-//   rx_front_kernel  : IQ @10 MS/s --TMA--> smem -> NCO rotate -> CIC^3 /25 -> 299-tap channel
-//                      filter /2 (the reference's lpf_taps @400 kS/s) -> quadrature demod -> d[] @200 kS/s.
-//                      Replaces freq_xlating_fir_filter_ccc + quadrature_demod_cf
-//                      (grc/ampsbs.grc:1814-1872, 774-816) and the 25x front-end decimation the
-//                      10 MS/s configs need.
-//   rx_detect_kernel : exact 74/74 trigger match on sign(d) at every sampling phase + soft
-//                      correlation of the matches (the recc_impl.cc:118 memmem, at 10 phases).
-//   rx_select_kernel : run grouping, sampling-phase choice, 3374-symbol capture
-//                      (recc_impl.cc:124-126), Manchester decode + BCH validity + field parse
-//                      (recc_decode_impl.cc:81-169).
+//   rx_front_kernel   : IQ @10 MS/s --TMA--> smem -> NCO rotate -> CIC^3 /25 -> 299-tap channel filter /2 (the reference's
+//                       lpf_taps @400 kS/s) -> quadrature demod -> d[] @200 kS/s and its hard decisions, THEN, in the same
+//                       launch, the trigger search on what it just wrote (exact 74/74 match of sign(d) at every sampling
+//                       phase + soft correlation of the matches: the recc_impl.cc:118 memmem, at 10 phases) and, by the last
+//                       CTA of each channel, the choice of the bursts to capture.  Replaces freq_xlating_fir_filter_ccc +
+//                       quadrature_demod_cf (grc/ampsbs.grc:1814-1872, 774-816), the 25x front-end decimation the 10 MS/s
+//                       configs need and the trigger half of amps.recc (lib/recc_impl.cc:115-119).
+//                       One launch serves one channel or a batch of independent channels.
+//   rx_capture_kernel : 3374-symbol capture at the chosen phase (recc_impl.cc:124-126), Manchester decode + BCH validity +
+//                       field parse (recc_decode_impl.cc:81-169), record streamed into the pinned host ring.
+//   rx_front400_kernel / rx_search_kernel : the same chain at the reference's own 400 kS/s (no CIC stage).
 //
-// No tensor cores: there is no dense contraction on this path.  The front kernel is a persistent
-// streaming kernel: each CTA owns a contiguous run of passes, keeps the filter history in shared
-// memory and re-reads only one warm-up pass at the start of its run.
+// No tensor cores: there is no dense contraction on this path.  The front kernel is a persistent streaming kernel: the
+// launch's tiles (3 units of 1600 samples) are dealt evenly to the CTAs, each CTA keeps the filter history of its segment
+// in shared memory and re-reads only two warm-up tiles in front of it.
 #include "rx_kernels.cuh"
 #include "recc_compat.cuh"
 
@@ -21,261 +22,17 @@ namespace amps {
 
 static_assert(sizeof(amps_burst) % 8 == 0, "burst records are streamed to the host ring in 8-byte words");
 
-// ============================================================================================
-// front end
-// ============================================================================================
-// 400 kS/s samples are kept as PAIRS (v[2P], v[2P+1]) = one float4, de-interleaved over kR rows by
-// P mod kR: a thread that produces outputs R*c .. R*c+R-1 then walks pairs whose row is a
-// compile-time constant and whose column is c + const, so consecutive lanes read consecutive
-// 16-byte slots (conflict-free LDS.128) and every load feeds up to 2*kR FFMA2.
-struct PassSmem {                         // what stage 2 + demod work on (shared by the 10 MS/s and the 400 kS/s front ends)
-    float4   v[kR][kRowLen];              // row r, column c (c >= -kPorchCols) at v[r][c + kPorchCols]
-    float2   ylast[kTB];                  // each thread's last output of the current pass
-    float2   ycarry[2];                   // last output of a pass, by pass parity
-};
-// input sample formats: fc32 (gr_complex, what the reference's flowgraph carries) and sc16 (interleaved int16 I/Q, what
-// the USRP puts on the wire before UHD's host-side conversion, grc/ampsbs.grc:3750): x = (float)int16 * in_scale
-// kUnit: the scale is a power of two and has been folded into the NCO tables on the host -- (I s) w and I (s w) are the
-// same real number when s is a power of two, so the result is bit-identical and the two multiplies per sample go away.
-template <bool kUnit> __device__ __forceinline__ float2 to_c32(float2 v, float) { return v; }
-template <bool kUnit> __device__ __forceinline__ float2 to_c32(short2 v, float s) {
-    if (kUnit) return make_float2((float)v.x, (float)v.y);
-    return make_float2(__fmul_rn((float)v.x, s), __fmul_rn((float)v.y, s));
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
-
-template <typename In>
-struct FrontSmem {
-    In       in[kStages][kTile];          // TMA landing ring
-    PassSmem ps;
-    float2   pb[3][2][kTB];               // [tile % 3][P1|P2][block] rotated CIC partial sums (3 buffers: a tile reads its
-                                          // own and the previous tile's, the next tile may already be writing)
-    uint64_t full[kStages];
-};
-
-size_t rx_front_smem_bytes() { return sizeof(FrontSmem<float2>); }
-
-template <typename In>
-__device__ __forceinline__ void issue_tile(const RxFrontParams &p, FrontSmem<In> *sm, long tile, int stage) {
-    // tiles with a negative index come from the history buffer (kWarmTiles tiles long)
-    const In *src = tile < 0 ? static_cast<const In *>(p.tail) + (long)kHist + tile * (long)kTile
-                             : static_cast<const In *>(p.chunk) + tile * (long)kTile;
-    mbar_expect_tx(&sm->full[stage], kTile * (uint32_t)sizeof(In));
-    tma_load_1d(sm->in[stage], src, kTile * (uint32_t)sizeof(In), &sm->full[stage]);
+__device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-
-__host__ __device__ constexpr int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
-
-// y[q] = sum_k h2[k] v[2q-k] for the kR outputs q = kR*c0 + r, each as two FFMA2 chains (even taps,
-// odd taps), k ascending -- the order the oracle uses.  vcol points at column c0 of row 0.
-__device__ __forceinline__ void channel_filter(const RxFrontParams &p, const float4 *vcol, float2 (&y)[kR]) {
-    float2 E[kR], O[kR];
-#pragma unroll
-    for (int r = 0; r < kR; ++r) { E[r] = make_float2(0.f, 0.f); O[r] = make_float2(0.f, 0.f); }
-#pragma unroll
-    for (int s = 0; s < 150 + kR - 1; ++s) {
-        // pair P = kR*c0 + (kR-1) - s : row and column offset are compile-time
-        const int row = (kR - 1 - s) & (kR - 1);
-        const int cs  = floor_div(kR - 1 - s, kR);
-        const float4 pr = vcol[row * kRowLen + cs];
-#pragma unroll
-        for (int r = 0; r < kR; ++r) {
-            const int j = r - (kR - 1) + s;           // tap pair index for output r
-            if (j >= 0 && j <= 149) E[r] = fma2(splat(p.h2[2 * j]), make_float2(pr.x, pr.y), E[r]);
-            if (j >= 1 && j <= 149) O[r] = fma2(splat(p.h2[2 * j - 1]), make_float2(pr.z, pr.w), O[r]);
-        }
-    }
-#pragma unroll
-    for (int r = 0; r < kR; ++r) y[r] = add2(E[r], O[r]);
-}
-
-// store one 400 kS/s sample (index relative to the start of the current pass, negative = history) into the pair/row layout
-__device__ __forceinline__ void store_v(PassSmem *ps, int mrel, float2 v) {
-    const int P   = mrel >> 1;                                   // pair index (floor)
-    const int col = P >> kLogR;
-    if (col >= -kPorchCols) reinterpret_cast<float2 *>(&ps->v[P & (kR - 1)][col + kPorchCols])[mrel & 1] = v;
-}
-
-// End of a pass (all threads call it): stage 2 (299-tap channel filter /2, kR outputs per thread), quadrature demod,
-// hard decisions, and the history shuffle for the next pass.  With warm == true it only produces y[q0-1], the
-// predecessor the demod of the CTA's first real output needs; nothing is written for it.
-__device__ __forceinline__ void finish_pass(const RxFrontParams &p, PassSmem *ps, bool warm, int pc, uint32_t pa, int t) {
-    __syncthreads();                                   // the pass's new v samples are in place
-    float2 y[kR];
-#pragma unroll
-    for (int r = 0; r < kR; ++r) y[r] = make_float2(0.f, 0.f);
-    if (!warm || t == 0) {
-        const int c0 = warm ? -1 : t;
-        channel_filter(p, &ps->v[0][c0 + kPorchCols], y);
-        if (!warm) ps->ylast[t] = y[kR - 1];
-        if (warm || t == kTB - 1) ps->ycarry[pc & 1] = y[kR - 1];
-    }
-    __syncthreads();
-    if (!warm) {
-        // the last kPorchCols columns become the history of the next pass
-        if (t < kR * kPorchCols) {
-            const int r = t / kPorchCols, c = t % kPorchCols;
-            ps->v[r][c] = ps->v[r][kTB + c];
-        }
-        // ---- quadrature demod: arg(y[q] * conj(y[q-1]))
-        float2 yp = t == 0 ? ps->ycarry[(pc + 1) & 1] : ps->ylast[t - 1];
-        float d[kR];
-#pragma unroll
-        for (int r = 0; r < kR; ++r) {
-            const float zr = __fmaf_rn(y[r].y, yp.y, __fmul_rn(y[r].x, yp.x));
-            const float zi = __fmaf_rn(y[r].y, yp.x, -__fmul_rn(y[r].x, yp.y));
-            d[r] = atan2_spec(zi, zr);
-            yp = y[r];
-        }
-        const unsigned long long ql = (unsigned long long)(pa + (uint32_t)pc) * kPassOut + (unsigned long long)kR * t;
-        const unsigned long long qabs = p.q_base + ql;
-        float4 *dst = reinterpret_cast<float4 *>(&p.dring[qabs & p.dmask]);
-        *dst = make_float4(d[0], d[1], d[2], d[3]);
-        // hard decisions (binary_slicer_fb: x >= 0 -> 1), 32 per word: 8 lanes x 4 outputs
-        unsigned int hb = 0;
-#pragma unroll
-        for (int r = 0; r < kR; ++r) hb |= (d[r] >= 0.0f ? 1u : 0u) << r;
-        hb <<= 4 * (t & 7);
-        hb |= __shfl_xor_sync(0xffffffffu, hb, 1);
-        hb |= __shfl_xor_sync(0xffffffffu, hb, 2);
-        hb |= __shfl_xor_sync(0xffffffffu, hb, 4);
-        if ((t & 7) == 0) p.hring[(qabs & p.dmask) >> 5] = hb;
-        if (p.ydump) {
-#pragma unroll
-            for (int r = 0; r < kR; ++r) p.ydump[ql + r] = y[r];
-        }
-    }
-}
-
-template <typename In, int kMinCtas, bool kUnit>
-__global__ void __launch_bounds__(kTB, kMinCtas) rx_front_kernel(const __grid_constant__ RxFrontParams p) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    FrontSmem<In> *sm = reinterpret_cast<FrontSmem<In> *>(smem_raw);
-    const int t = threadIdx.x;
-
-    // history for the next call = the last kHist samples of this chunk; every CTA copies a slice (saves a memcpy node
-    // between consecutive front kernels)
-    if (p.tail_out) {
-        const uint32_t per = ((uint32_t)kHist + gridDim.x - 1u) / gridDim.x;
-        const uint32_t lo = blockIdx.x * per, hi = lo + per < (uint32_t)kHist ? lo + per : (uint32_t)kHist;
-        const In *src = static_cast<const In *>(p.chunk) + ((size_t)p.npass * kPass - kHist);
-        for (uint32_t i = lo + (uint32_t)t; i < hi; i += kTB) static_cast<In *>(p.tail_out)[i] = src[i];
-    }
-
-    uint32_t pa = blockIdx.x * p.pass_per_cta;
-    if (pa >= p.npass) return;
-    uint32_t pb = pa + p.pass_per_cta;
-    if (pb > p.npass) pb = p.npass;
-    const int  ntiles = kPassTiles * (int)(pb - pa) + kWarmTiles;     // warm-up tiles + the CTA's own passes
-    const long tile0  = (long)kPassTiles * pa - kWarmTiles;
-
-    if (t == 0) {
-        for (int s = 0; s < kStages; ++s) mbar_init(&sm->full[s], 1);
-        mbar_fence_init();
-    }
-    // partial sums "before the first tile": they only reach samples the warm-up never uses
-    sm->pb[2][0][t] = make_float2(0.f, 0.f);
-    sm->pb[2][1][t] = make_float2(0.f, 0.f);
-    __syncthreads();
-    if (t == 0) {
-        for (int s = 0; s < kStages && s < ntiles; ++s) issue_tile(p, sm, tile0 + s, s);
-    }
-
-    for (int i = 0; i < ntiles; ++i) {
-        const int s = i % kStages;
-        mbar_wait(&sm->full[s], (uint32_t)(i / kStages) & 1u);
-
-        // ---- stage 1: NCO rotate + CIC^3 polyphase partial sums over this thread's 25 samples
-        const In *xin = sm->in[s] + kD1 * t;
-        float2 P0 = make_float2(0.f, 0.f), P1 = P0, P2 = P0;
-#pragma unroll
-        for (int k = 0; k < kD1; ++k) {
-            const float2 x = to_c32<kUnit>(xin[k], p.in_scale);
-            const float2 u = fma2(splat(x.y), p.wj[k], mul2(splat(x.x), p.w[k]));      // = cmul(x, w[k]), same operations
-            P0 = fma2(splat(p.g[24 - k]), u, P0);
-            P1 = fma2(splat(p.g[49 - k]), u, P1);
-            if (74 - k < kNCic) P2 = fma2(splat(p.g[74 - k]), u, P2);
-        }
-        const long     blk  = (tile0 + i) * (long)kTB + t;
-        const uint32_t babs = p.blk_base + (uint32_t)blk;
-        const float2   W    = sincos_phase(babs * p.fcw25);
-        P0 = cmul(P0, W);
-        P1 = cmul(P1, W);
-        P2 = cmul(P2, W);
-        const int par = i % 3, prv = (i + 2) % 3;
-        sm->pb[par][0][t] = P1;
-        sm->pb[par][1][t] = P2;
-        __syncthreads();                                   // partials visible; in[s] fully consumed
-        if (t == 0 && i + kStages < ntiles) issue_tile(p, sm, tile0 + i + kStages, s);
-
-        // ---- v[m] = (P0[m] + P1[m-1]) + P2[m-2], stored into the pair/row layout
-        const float2 q1 = t >= 1 ? sm->pb[par][0][t - 1] : sm->pb[prv][0][kTB - 1];
-        const float2 q2 = t >= 2 ? sm->pb[par][1][t - 2] : sm->pb[prv][1][kTB - 2 + t];
-        const float2 v  = add2(add2(P0, q1), q2);
-        const bool warm = i < kWarmTiles;
-        const int  u    = warm ? 0 : (i - kWarmTiles) % kPassTiles;          // tile index inside the pass
-        store_v(&sm->ps, warm ? (i - kWarmTiles) * kTB + t : u * kTB + t, v);
-
-        const bool pass_end = !warm && u == kPassTiles - 1;
-        if (pass_end || i == kWarmTiles - 1)
-            finish_pass(p, &sm->ps, warm, warm ? -1 : (i - kWarmTiles) / kPassTiles, pa, t);
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// native-rate front end: complex IQ @400 kS/s (the reference's own operating point, grc/ampsbs.grc:263).
-// No decimating first stage: v[m] = x[m] e^{-j theta m}, then exactly freq_xlating_fir_filter_ccc's filter /2 and
-// quadrature_demod_cf.  At 0.4 MS/s real time this kernel is never a bottleneck (it is FFMA-bound: 150 FFMA2 per
-// 8-byte sample); it exists so that recc_iq drops into the reference flowgraph at its native rate.
-// ---------------------------------------------------------------------------------------------
-template <typename In, bool kUnit>
-__global__ void __launch_bounds__(kTB, 4) rx_front400_kernel(const __grid_constant__ RxFrontParams p) {
-    __shared__ PassSmem ps;
-    const int t = threadIdx.x;
-    uint32_t pa = blockIdx.x * p.pass_per_cta;
-    if (pa >= p.npass) return;
-    uint32_t pb = pa + p.pass_per_cta;
-    if (pb > p.npass) pb = p.npass;
-    auto load = [&](long L) -> float2 {                   // logical sample L of this call; L < 0 = history
-        const float2 x = to_c32<kUnit>(L < 0 ? static_cast<const In *>(p.tail)[(long)kPass400 + L] : static_cast<const In *>(p.chunk)[L], p.in_scale);
-        const unsigned long long nabs = p.n_base + (unsigned long long)(long long)L;    // (x is 0 where this wraps: stream start)
-        const uint32_t b = (uint32_t)(nabs / kD1), k = (uint32_t)(nabs % kD1);
-        return cmul(fma2(splat(x.y), p.wj[k], mul2(splat(x.x), p.w[k])), sincos_phase(b * p.fcw25));
-    };
-    const long first = (long)pa * kPass400;
-    // warm-up: the kPorchCols columns of history in front of the first pass
-    for (int idx = t; idx < 2 * kR * kPorchCols; idx += kTB) {
-        const int mrel = idx - 2 * kR * kPorchCols;
-        store_v(&ps, mrel, load(first + mrel));
-    }
-    finish_pass(p, &ps, true, -1, pa, t);
-    for (uint32_t pc = 0; pc < pb - pa; ++pc) {
-        const long base = first + (long)pc * kPass400;
-        __syncthreads();                                   // the history shuffle of the previous pass is done
-#pragma unroll
-        for (int u = 0; u < kPassTiles; ++u) store_v(&ps, u * kTB + t, load(base + u * kTB + t));
-        finish_pass(p, &ps, false, (int)pc, pa, t);
-    }
-}
-
-cudaError_t launch_rx_front400(const RxFrontParams &p, int grid, cudaStream_t st, bool sc16, bool unit) {
-    if (sc16 && unit) rx_front400_kernel<short2, true><<<grid, kTB, 0, st>>>(p);
-    else if (sc16) rx_front400_kernel<short2, false><<<grid, kTB, 0, st>>>(p);
-    else rx_front400_kernel<float2, false><<<grid, kTB, 0, st>>>(p);
-    return cudaGetLastError();
-}
-
-// sc16 tiles are half the size, so three CTAs fit an SM (the kernel is no longer HBM-bound at 4 B/sample)
-constexpr int kSc16Ctas = 3;
-cudaError_t launch_rx_front(const RxFrontParams &p, int grid, cudaStream_t st, bool sc16, bool unit) {
-    if (sc16 && unit) rx_front_kernel<short2, kSc16Ctas, true><<<grid, kTB, sizeof(FrontSmem<short2>), st>>>(p);
-    else if (sc16) rx_front_kernel<short2, kSc16Ctas, false><<<grid, kTB, sizeof(FrontSmem<short2>), st>>>(p);
-    else rx_front_kernel<float2, 2, false><<<grid, kTB, sizeof(FrontSmem<float2>), st>>>(p);
-    return cudaGetLastError();
-}
-int rx_front_ctas_per_sm(bool sc16) { return sc16 ? kSc16Ctas : 2; }
 
 // ============================================================================================
-// trigger detection
+// trigger search (device routines shared by rx_front_kernel and rx_search_kernel)
 // ============================================================================================
 // 74 half-symbols: Manchester("10" x 13 + "11100010010"), bit 0 -> (1,0), bit 1 -> (0,1)
 // (lib/recc_impl.cc:51-65,76).
@@ -286,18 +43,29 @@ __device__ __constant__ uint8_t c_trig[kTrig] = {
 // 74-symbol trigger packed LSB-first (symbol k = bit k)
 __device__ __constant__ uint32_t c_trig_bits[3] = {0x66666666u, 0x56A66666u, 0x00000196u};
 
+// The rings are read with ld.global.cg: inside rx_front_kernel the words were written during this very launch, some of them
+// by other SMs, and an L1 line fetched earlier by a co-resident CTA may predate them.
+__device__ __forceinline__ uint32_t hard_window(const uint32_t *__restrict__ hring, uint32_t wmask, unsigned long long b) {
+    const uint32_t wi = (uint32_t)(b >> 5);
+    const uint32_t w0 = __ldcg(&hring[wi & wmask]), w1 = __ldcg(&hring[(wi + 1) & wmask]);
+    return __funnelshift_r(w0, w1, (uint32_t)b & 31u);
+}
+
 // Exact 74/74 hard match for the 32 adjacent sampling positions i0 .. i0+31 (i0 a multiple of 32):
 // for half-symbol k the 32 hard decisions at positions i0+10k .. i0+10k+31 are one 32-bit window of
 // the bit ring, so one AND per symbol tests all 32 positions; a random group dies after ~6 symbols.
+// The first 8 windows are fetched together (one round trip to L2 decides 7 groups out of 8).
 __device__ __forceinline__ uint32_t group_match(const uint32_t *__restrict__ hring, uint32_t wmask, unsigned long long i0) {
+    uint32_t win[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) win[k] = hard_window(hring, wmask, i0 + (unsigned long long)(kOS * k));
     uint32_t m = 0xffffffffu;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) m &= ((0x66u >> k) & 1u) ? win[k] : ~win[k];      // c_trig_bits[0] & 0xff
 #pragma unroll 1
-    for (int k = 0; k < kTrig && m; ++k) {
-        const unsigned long long b = i0 + (unsigned long long)(kOS * k);
-        const uint32_t wi = (uint32_t)(b >> 5);
-        const uint32_t w0 = hring[wi & wmask], w1 = hring[(wi + 1) & wmask];
-        const uint32_t win = __funnelshift_r(w0, w1, (uint32_t)b & 31u);
-        m &= ((c_trig_bits[k >> 5] >> (k & 31)) & 1u) ? win : ~win;
+    for (int k = 8; k < kTrig && m; ++k) {
+        const uint32_t w = hard_window(hring, wmask, i0 + (unsigned long long)(kOS * k));
+        m &= ((c_trig_bits[k >> 5] >> (k & 31)) & 1u) ? w : ~w;
     }
     return m;
 }
@@ -306,20 +74,18 @@ __device__ __forceinline__ uint32_t group_match(const uint32_t *__restrict__ hri
 __device__ __forceinline__ float trig_corr(const float *__restrict__ dring, uint32_t dmask, unsigned long long i) {
     float v[kTrig];
 #pragma unroll
-    for (int k = 0; k < kTrig; ++k) v[k] = dring[(i + (unsigned long long)(kOS * k)) & dmask];
+    for (int k = 0; k < kTrig; ++k) v[k] = __ldcg(&dring[(i + (unsigned long long)(kOS * k)) & dmask]);
     float c = 0.0f;
 #pragma unroll
     for (int k = 0; k < kTrig; ++k) c = __fadd_rn(c, c_trig[k] ? v[k] : -v[k]);
     return c;
 }
 
-// One thread per group of 32 sampling positions.  The thread owning the FIRST position of a run of
-// matches (at most 10 long: the pattern cannot match one half-symbol later) emits one candidate for
-// the whole run: its soft-correlation peak (first maximum) is the sampling phase.
-// (Grid-stride loop; the launcher may cap the grid.  Measured on B200: the grid size does not matter for the pipeline, the
-// shared-memory carve-out preference set in rx_configure_device() does.)
+// One thread per group of 32 sampling positions.  The thread owning the FIRST position of a run of matches (at most 10
+// long: the pattern cannot match one half-symbol later) appends one candidate for the whole run: its soft-correlation
+// peak (first maximum) is the sampling phase.  Reads the stream up to i0 + 793; every group is searched exactly once.
 __device__ void detect_group(const float *__restrict__ dring, const uint32_t *__restrict__ hring, uint32_t dmask, RxState *state,
-                             Candidate *cand, unsigned long long scan_lo, unsigned long long scan_hi, unsigned long long i0) {
+                             Candidate *cand, unsigned long long i0) {
     const uint32_t wmask = dmask >> 5;
     const uint32_t m0 = group_match(hring, wmask, i0);
     if (!m0) return;
@@ -328,22 +94,16 @@ __device__ void detect_group(const float *__restrict__ dring, const uint32_t *__
     const uint32_t mnext = group_match(hring, wmask, i0 + 32);
     const unsigned long long M = (unsigned long long)m0 | ((unsigned long long)mnext << 32);
     uint32_t starts = m0 & ~((m0 << 1) | (mprev >> 31));
-    const unsigned long long lo = state->lo > scan_lo ? state->lo : scan_lo;
     while (starts) {
         const int bit = __ffs(starts) - 1;
         starts &= starts - 1;
         const unsigned long long i = i0 + (unsigned long long)bit;
-        if (i < lo || i >= scan_hi) continue;
         unsigned long long best = i;
         float bestc = trig_corr(dring, dmask, i);
         unsigned int run = 1;
-        bool open = false;
-        for (;;) {
-            const unsigned long long j = i + run;
-            if (j >= scan_hi) { open = true; break; }                 // the run may go on in data not searched yet
-            if (!((M >> (bit + run)) & 1ull)) break;
-            const float c = trig_corr(dring, dmask, j);
-            if (c > bestc) { bestc = c; best = j; }
+        while (run < 32u && ((M >> (bit + run)) & 1ull)) {
+            const float c = trig_corr(dring, dmask, i + run);
+            if (c > bestc) { bestc = c; best = i + run; }
             ++run;
         }
         const unsigned int slot = atomicAdd(&state->ncand, 1u);
@@ -351,30 +111,60 @@ __device__ void detect_group(const float *__restrict__ dring, const uint32_t *__
             cand[slot].start = i;
             cand[slot].best = best;
             cand[slot].corr = bestc;
-            cand[slot].run = run | (open ? 0x80000000u : 0u);
+            cand[slot].run = run;
         } else {
             atomicAdd(&state->cand_overflow, 1u);
         }
     }
 }
 
-__global__ void __launch_bounds__(256) rx_detect_kernel(const float *__restrict__ dring, const uint32_t *__restrict__ hring,
-                                                       uint32_t dmask, RxState *state, Candidate *cand,
-                                                       unsigned long long scan_lo, unsigned long long scan_hi) {
-    const unsigned long long base = scan_lo & ~31ull;
-    const unsigned long long stride = 32ull * (unsigned long long)gridDim.x * blockDim.x;
-    for (unsigned long long i0 = base + 32ull * ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x); i0 < scan_hi; i0 += stride)
-        detect_group(dring, hring, dmask, state, cand, scan_lo, scan_hi, i0);
-}
-
-cudaError_t launch_rx_detect(const float *dring, const uint32_t *hring, uint32_t dmask, RxState *state, Candidate *cand,
-                             unsigned long long scan_lo, unsigned long long scan_hi, int max_ctas, cudaStream_t st) {
-    if (scan_hi <= scan_lo) return cudaSuccess;
-    const unsigned long long groups = (scan_hi - (scan_lo & ~31ull) + 31ull) / 32ull;
-    unsigned int grid = (unsigned int)((groups + 255) / 256);
-    if (max_ctas > 0 && grid > (unsigned int)max_ctas) grid = (unsigned int)max_ctas;
-    rx_detect_kernel<<<grid, 256, 0, st>>>(dring, hring, dmask, state, cand, scan_lo, scan_hi);
-    return cudaGetLastError();
+// Candidate selection, all threads of the CTA (candidates are rare: about one per burst).  Sort the list by run start,
+// then walk it in stream order: a run is DECIDED once the stream reaches kSpan beyond its end (the whole capture is in the
+// ring) -- the first undecided run and everything after it stay on the list for a later call; a decided run that starts
+// inside an already captured burst is dropped; the others are accepted and the search resumes (74+3374)*10 positions after
+// the sampling position (oracle/dsp_chain.c orc_rx_detect).  The outcome does not depend on how the stream was cut into calls.
+__device__ void select_channel(RxState *state, Candidate *cand, Candidate *sorted, Accepted *acc, uint32_t par,
+                               unsigned long long total_d, RxPublished *host_pub) {
+    const int t = threadIdx.x, nt = blockDim.x;
+    unsigned int n = __ldcg(&state->ncand);
+    if (n > (unsigned)kMaxCand) n = kMaxCand;
+    for (unsigned int i = t; i < n; i += nt) {
+        Candidate c;
+        c.start = __ldcg(&cand[i].start); c.best = __ldcg(&cand[i].best); c.corr = __ldcg(&cand[i].corr); c.run = __ldcg(&cand[i].run);
+        unsigned int rank = 0;
+        for (unsigned int j = 0; j < n; ++j) rank += __ldcg(&cand[j].start) < c.start ? 1u : 0u;
+        sorted[rank] = c;
+    }
+    __syncthreads();
+    if (t == 0) {
+        unsigned long long resume = state->resume_at;
+        unsigned int na = 0, keep = 0;
+        for (unsigned int i = 0; i < n; ++i) {
+            const Candidate c = sorted[i];
+            const bool decided = c.start + c.run + (unsigned long long)kSpan < total_d;
+            if (!decided || na == (unsigned)kMaxAccept) {             // (or no room left in this call's list: next call)
+                for (unsigned int j = i; j < n; ++j) cand[keep++] = sorted[j];
+                break;
+            }
+            if (c.start < resume) continue;                // begins inside a burst that was already captured
+            acc[na].pos = c.best;
+            acc[na].corr = c.corr;
+            acc[na].run = c.run;
+            ++na;
+            resume = c.best + (unsigned long long)kBurstLen;
+        }
+        state->resume_at = resume;
+        state->ncand = keep;
+        state->n_acc[par] = na;
+        state->rec_base[par] = state->nrec_total;
+        state->nrec_total += na;
+        if (na == 0 && state->cand_overflow != state->pub_overflow) {     // nothing for the capture kernel to publish
+            state->pub_overflow = state->cand_overflow;
+            __threadfence_system();
+            host_pub->cand_overflow = state->cand_overflow;
+        }
+    }
+    __syncthreads();
 }
 
 // ============================================================================================
@@ -556,134 +346,547 @@ cudaError_t launch_decode_blobs(const uint8_t *blobs, int nbursts, amps_recc_wor
 }
 
 // ============================================================================================
-// candidate selection (single CTA; candidates are rare) and burst capture (one CTA per burst)
+// front end
 // ============================================================================================
-// `sorted` is global scratch (kMaxCand entries) rather than 196 KB of shared memory, so that this CTA can become resident
-// next to the front-kernel CTAs of the following call.
-__global__ void __launch_bounds__(256) rx_select_kernel(RxState *state, Candidate *cand, Candidate *sorted, Accepted *acc,
-                                                       unsigned long long scan_hi, RxPublished *host_pub) {
-    const int t = threadIdx.x, nt = blockDim.x;
-    unsigned int n = state->ncand;
-    if (n > (unsigned)kMaxCand) n = kMaxCand;
-    // rank sort by run start (the atomics made the order arbitrary; run starts are distinct)
-    for (unsigned int i = t; i < n; i += nt) {
-        const Candidate c = cand[i];
-        unsigned int rank = 0;
-        for (unsigned int j = 0; j < n; ++j) rank += cand[j].start < c.start ? 1u : 0u;
-        sorted[rank] = c;
+// 400 kS/s samples are kept as PAIRS (v[2P], v[2P+1]) = one float4, de-interleaved over kR rows by
+// P mod kR: a thread that produces outputs R*c .. R*c+R-1 then walks pairs whose row is a
+// compile-time constant and whose column is c + const, so consecutive lanes read consecutive
+// 16-byte slots (conflict-free LDS.128) and every load feeds up to 2*kR FFMA2.
+struct PassSmem {                         // what stage 2 + demod work on (shared by the 10 MS/s and the 400 kS/s front ends)
+    float4   v[kR][kRowLen];              // row r, column c (c >= -kPorchCols) at v[r][c + kPorchCols]
+    float2   ylast[kTB];                  // each thread's last output of the current pass
+    float2   ycarry[2];                   // last output of a pass, by pass parity
+};
+struct PassOut {                          // where a pass's outputs go
+    float    *dring;
+    uint32_t *hring;
+    float2   *ydump;
+    uint32_t  dmask;
+};
+// input sample formats: fc32 (gr_complex, what the reference's flowgraph carries) and sc16 (interleaved int16 I/Q, what
+// the USRP puts on the wire before UHD's host-side conversion, grc/ampsbs.grc:3750): x = (float)int16 * in_scale
+// kUnitScale: the scale is a power of two and has been folded into the NCO tables on the host -- (I s) w and I (s w) are the
+// same real number when s is a power of two, so the result is bit-identical and the two multiplies per sample go away.
+template <bool kUnitScale> __device__ __forceinline__ float2 to_c32(float2 v, float) { return v; }
+template <bool kUnitScale> __device__ __forceinline__ float2 to_c32(short2 v, float s) {
+    if (kUnitScale) return make_float2((float)v.x, (float)v.y);
+    return make_float2(__fmul_rn((float)v.x, s), __fmul_rn((float)v.y, s));
+}
+
+template <typename In>
+struct FrontSmem {
+    In       in[kStages][kTile];          // TMA landing ring
+    PassSmem ps;
+    float2   pb[3][2][kTB];               // [tile % 3][P1|P2][block] rotated CIC partial sums (3 buffers: a tile reads its
+                                          // own and the previous tile's, the next tile may already be writing)
+    uint64_t full[kStages];
+    uint32_t flag_ok;                     // search: the CTAs in front of this segment have published their outputs
+    uint32_t is_last;                     // this CTA is the last one of the channel to finish
+};
+
+size_t rx_front_smem_bytes() { return sizeof(FrontSmem<float2>); }
+
+__host__ __device__ constexpr int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+// y[q] = sum_k h2[k] v[2q-k] for the kR outputs q = kR*c0 + r, each as two FFMA2 chains (even taps,
+// odd taps), k ascending -- the order the oracle uses.  vcol points at column c0 of row 0.
+__device__ __forceinline__ void channel_filter(const float (&h2)[300], const float4 *vcol, float2 (&y)[kR]) {
+    float2 E[kR], O[kR];
+#pragma unroll
+    for (int r = 0; r < kR; ++r) { E[r] = make_float2(0.f, 0.f); O[r] = make_float2(0.f, 0.f); }
+#pragma unroll
+    for (int s = 0; s < 150 + kR - 1; ++s) {
+        // pair P = kR*c0 + (kR-1) - s : row and column offset are compile-time
+        const int row = (kR - 1 - s) & (kR - 1);
+        const int cs  = floor_div(kR - 1 - s, kR);
+        const float4 pr = vcol[row * kRowLen + cs];
+#pragma unroll
+        for (int r = 0; r < kR; ++r) {
+            const int j = r - (kR - 1) + s;           // tap pair index for output r
+            if (j >= 0 && j <= 149) E[r] = fma2(splat(h2[2 * j]), make_float2(pr.x, pr.y), E[r]);
+            if (j >= 1 && j <= 149) O[r] = fma2(splat(h2[2 * j - 1]), make_float2(pr.z, pr.w), O[r]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < kR; ++r) y[r] = add2(E[r], O[r]);
+}
+
+// store one 400 kS/s sample (index relative to the start of the current pass, negative = history) into the pair/row layout
+__device__ __forceinline__ void store_v(PassSmem *ps, int mrel, float2 v) {
+    const int P   = mrel >> 1;                                   // pair index (floor)
+    const int col = P >> kLogR;
+    if (col >= -kPorchCols) reinterpret_cast<float2 *>(&ps->v[P & (kR - 1)][col + kPorchCols])[mrel & 1] = v;
+}
+
+// End of a pass (all threads call it): stage 2 (299-tap channel filter /2, kR outputs per thread), quadrature demod,
+// hard decisions, and the history shuffle for the next pass.  Threads t < nact own valid outputs (nact = kTB for a full
+// pass, 8 per unit for the partial pass that ends a segment).  With warm == true it only produces y[q0-1], the predecessor
+// the demod of the segment's first real output needs; nothing is written for it.
+//   q_pass: absolute demod index of the pass's first output; ql_pass: the same relative to the call's first output.
+__device__ __forceinline__ void finish_pass(const float (&h2)[300], const PassOut &o, PassSmem *ps, bool warm, int pc,
+                                            unsigned long long q_pass, unsigned long long ql_pass, int nact, int t) {
+    __syncthreads();                                   // the pass's new v samples are in place
+    float2 y[kR];
+#pragma unroll
+    for (int r = 0; r < kR; ++r) y[r] = make_float2(0.f, 0.f);
+    if (warm ? t == 0 : t < nact) {
+        const int c0 = warm ? -1 : t;
+        channel_filter(h2, &ps->v[0][c0 + kPorchCols], y);
+        if (!warm) ps->ylast[t] = y[kR - 1];
+        if (warm || t == kTB - 1) ps->ycarry[pc & 1] = y[kR - 1];
     }
     __syncthreads();
-    if (t == 0) {
-        const unsigned long long lo = state->lo;
-        unsigned long long resume = state->resume_at;
-        unsigned long long new_lo = scan_hi > lo ? scan_hi : lo;
-        unsigned int na = 0;
-        for (unsigned int i = 0; i < n; ++i) {
-            const Candidate c = sorted[i];
-            if (c.start < lo) continue;                    // handled by an earlier call
-            if (c.run & 0x80000000u) {                     // run reaches the end of the searched range: decide next call
-                new_lo = c.start;
-                break;
-            }
-            if (c.start < resume) continue;                // begins inside a burst that was already captured
-            if (na < (unsigned)kMaxAccept) {
-                acc[na].pos = c.best;
-                acc[na].corr = c.corr;
-                acc[na].run = c.run;
-                ++na;
-            }
-            resume = c.best + (unsigned long long)kBurstLen;
+    if (!warm) {
+        // the last kPorchCols columns become the history of the next pass
+        if (t < kR * kPorchCols) {
+            const int r = t / kPorchCols, c = t % kPorchCols;
+            ps->v[r][c] = ps->v[r][kTB + c];
         }
-        state->lo = new_lo;
-        state->resume_at = resume;
-        state->ncand = 0;
-        state->n_acc = na;
-        state->done = 0;
-        state->rec_base = state->nrec_total;
-        state->nrec_total += na;
-        if (na == 0) {                                    // nothing for the capture kernel to publish
-            __threadfence_system();
-            host_pub->cand_overflow = state->cand_overflow;
+        // ---- quadrature demod: arg(y[q] * conj(y[q-1]))
+        float2 yp = t == 0 ? ps->ycarry[(pc + 1) & 1] : ps->ylast[t - 1];
+        float d[kR];
+#pragma unroll
+        for (int r = 0; r < kR; ++r) {
+            const float zr = __fmaf_rn(y[r].y, yp.y, __fmul_rn(y[r].x, yp.x));
+            const float zi = __fmaf_rn(y[r].y, yp.x, -__fmul_rn(y[r].x, yp.y));
+            d[r] = atan2_spec(zi, zr);
+            yp = y[r];
+        }
+        const unsigned long long qabs = q_pass + (unsigned long long)kR * t;
+        const bool act = t < nact;
+        if (act) *reinterpret_cast<float4 *>(&o.dring[qabs & o.dmask]) = make_float4(d[0], d[1], d[2], d[3]);
+        // hard decisions (binary_slicer_fb: x >= 0 -> 1), 32 per word: 8 lanes x 4 outputs
+        unsigned int hb = 0;
+#pragma unroll
+        for (int r = 0; r < kR; ++r) hb |= (d[r] >= 0.0f ? 1u : 0u) << r;
+        hb <<= 4 * (t & 7);
+        hb |= __shfl_xor_sync(0xffffffffu, hb, 1);
+        hb |= __shfl_xor_sync(0xffffffffu, hb, 2);
+        hb |= __shfl_xor_sync(0xffffffffu, hb, 4);
+        if (act && (t & 7) == 0) o.hring[(qabs & o.dmask) >> 5] = hb;
+        if (o.ydump && act) {
+            const unsigned long long ql = ql_pass + (unsigned long long)kR * t;
+#pragma unroll
+            for (int r = 0; r < kR; ++r) o.ydump[ql + r] = y[r];
         }
     }
 }
 
-cudaError_t launch_rx_select(RxState *state, Candidate *cand, Accepted *acc, unsigned long long scan_hi,
-                             RxPublished *host_pub, cudaStream_t st) {
-    rx_select_kernel<<<1, 256, 0, st>>>(state, cand, cand + kMaxCand, acc, scan_hi, host_pub);   // cand holds 2 x kMaxCand entries
+// ---- how a launch's tiles are dealt: CTA i of `grid` owns global tiles [Tt*i/grid, Tt*(i+1)/grid)
+__device__ __forceinline__ uint32_t cta_tile_lo(uint32_t Tt, uint32_t grid, uint32_t i) { return (uint32_t)((unsigned long long)Tt * i / grid); }
+__device__ __forceinline__ uint32_t tile_owner(uint32_t Tt, uint32_t grid, uint32_t tile) {
+    return (uint32_t)((((unsigned long long)tile + 1ull) * grid - 1ull) / Tt);
+}
+
+// samples [L0, L0 + n) of a channel's logical stream -> shared memory; logical samples below `carry` live in the tail
+// buffer (history + what the previous call could not use), the rest in this call's chunk; a tile may straddle the seam
+template <typename In>
+__device__ __forceinline__ void issue_tile(const RxChan &ch, In *dst, uint64_t *bar, long L0, uint32_t n) {
+    mbar_expect_tx(bar, n * (uint32_t)sizeof(In));
+    const long carry = (long)ch.carry;
+    const In *tail = static_cast<const In *>(ch.tail) + (long)kHist;      // logical sample 0 of the tail buffer
+    const In *chunk = static_cast<const In *>(ch.chunk) - carry;          // logical sample 0 of the chunk (virtual)
+    if (L0 + (long)n <= carry) tma_load_1d(dst, tail + L0, n * (uint32_t)sizeof(In), bar);
+    else if (L0 >= carry) tma_load_1d(dst, chunk + L0, n * (uint32_t)sizeof(In), bar);
+    else {
+        const uint32_t n1 = (uint32_t)(carry - L0);
+        tma_load_1d(dst, tail + L0, n1 * (uint32_t)sizeof(In), bar);
+        tma_load_1d(dst + n1, chunk + carry, (n - n1) * (uint32_t)sizeof(In), bar);
+    }
+}
+
+// groups [g_lo, g_hi) of one channel, one thread each
+__device__ __forceinline__ void search_groups(const RxChan &ch, unsigned long long g_lo, unsigned long long g_hi, int t) {
+    for (unsigned long long g = g_lo + (unsigned long long)t; g < g_hi; g += kTB)
+        detect_group(ch.dring, ch.hring, ch.dmask, ch.state, ch.cand, 32ull * g);
+}
+
+// the groups a segment [qs, qe) of demod samples has to search, and the first one that needs no other CTA's output
+struct SegGroups { unsigned long long lo, mid, hi; };
+__device__ __forceinline__ SegGroups seg_groups(unsigned long long qs, unsigned long long qe, bool first_of_call) {
+    SegGroups g;
+    g.lo = qs / kUnitOut >= (unsigned)kGroupLag ? qs / kUnitOut - kGroupLag : 0ull;
+    g.hi = qe / kUnitOut >= (unsigned)kGroupLag ? qe / kUnitOut - kGroupLag : 0ull;
+    g.mid = g.lo;
+    if (!first_of_call) {                       // groups below qs/32 + 1 look at samples in front of qs (written in this launch)
+        g.mid = qs / kUnitOut + 1;
+        if (g.mid > g.hi) g.mid = g.hi;
+        if (g.mid < g.lo) g.mid = g.lo;
+    }
+    return g;
+}
+
+// One segment = tiles [ta, tb) of channel c (tile j = units 3j .. 3j+2, the channel's last tile may be shorter), preceded by
+// kWarmTiles tiles of history.  `it` counts the tiles this CTA has consumed (TMA ring position / mbarrier phase).
+template <typename In, bool kUnitScale, int kMaxChan>
+__device__ __forceinline__ void run_segment(const RxFrontParamsT<kMaxChan> &p, const RxChan &ch, FrontSmem<In> *sm,
+                                            uint32_t ta, uint32_t tb, uint32_t &it, int t) {
+    const int  ntiles = (int)(tb - ta) + kWarmTiles;
+    const long tj0    = (long)ta - kWarmTiles;                          // channel tile index of tile i = 0
+    const uint32_t U  = ch.units;
+    auto tile_blocks = [&](int i) -> uint32_t {                         // valid 25-sample blocks of tile i
+        const long tj = tj0 + i;
+        if (tj < 0) return (uint32_t)kTB;
+        const uint32_t left = (U - (uint32_t)kTileUnits * (uint32_t)tj) * (uint32_t)kUnitBlk;
+        return left < (uint32_t)kTB ? left : (uint32_t)kTB;
+    };
+    PassOut o;
+    o.dring = ch.dring; o.hring = ch.hring; o.ydump = ch.ydump; o.dmask = ch.dmask;
+    const uint32_t useg = ((uint32_t)kTileUnits * tb < U ? (uint32_t)kTileUnits * tb : U) - (uint32_t)kTileUnits * ta;   // units of the segment
+    const unsigned long long ql0 = (unsigned long long)kUnitOut * kTileUnits * ta;     // first output, relative to the call
+
+    // partial sums "before the first tile": they only reach samples the warm-up never uses
+    sm->pb[2][0][t] = make_float2(0.f, 0.f);
+    sm->pb[2][1][t] = make_float2(0.f, 0.f);
+    __syncthreads();                                     // (also: the previous segment is done with ps / pb / in)
+    if (t == 0) {
+        for (int s = 0; s < kStages && s < ntiles; ++s)
+            issue_tile<In>(ch, sm->in[(it + s) % kStages], &sm->full[(it + s) % kStages], (tj0 + s) * (long)kTile, tile_blocks(s) * kD1);
+    }
+
+    for (int i = 0; i < ntiles; ++i, ++it) {
+        const int s = (int)(it % kStages);
+        mbar_wait(&sm->full[s], (it / kStages) & 1u);
+
+        // ---- stage 1: NCO rotate + CIC^3 polyphase partial sums over this thread's 25 samples
+        const In *xin = sm->in[s] + kD1 * t;
+        float2 P0 = make_float2(0.f, 0.f), P1 = P0, P2 = P0;
+#pragma unroll
+        for (int k = 0; k < kD1; ++k) {
+            const float2 x = to_c32<kUnitScale>(xin[k], ch.in_scale);
+            const float2 w = ch.w[k];
+            float2 wj;
+            if constexpr (kMaxChan == 1) wj = p.wj0[k]; else wj = make_float2(-w.y, w.x);
+            const float2 u = fma2(splat(x.y), wj, mul2(splat(x.x), w));      // = cmul(x, w[k]), same operations
+            P0 = fma2(splat(p.g[24 - k]), u, P0);
+            P1 = fma2(splat(p.g[49 - k]), u, P1);
+            if (74 - k < kNCic) P2 = fma2(splat(p.g[74 - k]), u, P2);
+        }
+        const long     blk  = (tj0 + i) * (long)kTB + t;                 // block index relative to logical sample 0
+        const uint32_t babs = ch.blk_base + (uint32_t)blk;
+        const float2   W    = sincos_phase(babs * ch.fcw25);
+        P0 = cmul(P0, W);
+        P1 = cmul(P1, W);
+        P2 = cmul(P2, W);
+        const int par = i % 3, prv = (i + 2) % 3;
+        sm->pb[par][0][t] = P1;
+        sm->pb[par][1][t] = P2;
+        __syncthreads();                                   // partials visible; in[s] fully consumed
+        if (t == 0 && i + kStages < ntiles)
+            issue_tile<In>(ch, sm->in[s], &sm->full[s], (tj0 + i + kStages) * (long)kTile, tile_blocks(i + kStages) * kD1);
+
+        // ---- v[m] = (P0[m] + P1[m-1]) + P2[m-2], stored into the pair/row layout
+        const float2 q1 = t >= 1 ? sm->pb[par][0][t - 1] : sm->pb[prv][0][kTB - 1];
+        const float2 q2 = t >= 2 ? sm->pb[par][1][t - 2] : sm->pb[prv][1][kTB - 2 + t];
+        const float2 v  = add2(add2(P0, q1), q2);
+        const bool warm = i < kWarmTiles;
+        const int  u    = warm ? 0 : (i - kWarmTiles) % kPassTiles;          // tile index inside the pass
+        store_v(&sm->ps, warm ? (i - kWarmTiles) * kTB + t : u * kTB + t, v);
+
+        const bool pass_end = !warm && (u == kPassTiles - 1 || i == ntiles - 1);
+        if (pass_end || i == kWarmTiles - 1) {
+            const int pc = warm ? -1 : (i - kWarmTiles) / kPassTiles;
+            int nact = kTB;
+            if (!warm) {
+                const uint32_t left = useg - (uint32_t)(kPassTiles * kTileUnits) * (uint32_t)pc;          // units from this pass on
+                if (left < (uint32_t)(kPassTiles * kTileUnits)) nact = (int)left * (kUnitOut / kR);
+            }
+            const unsigned long long ql = ql0 + (unsigned long long)(pc < 0 ? 0 : pc) * kPassOut;
+            finish_pass(p.h2, o, &sm->ps, warm, pc, ch.q_base + ql, ql, nact, t);
+        }
+    }
+}
+
+// After a segment: search the groups whose lookahead ends inside it, publish "my outputs are written", and if this CTA is
+// the last of the channel to get here, finish the channel (deferred groups, candidate selection).
+//   Groups near the front of the segment look at demod samples other CTAs of this launch produce.  Those CTAs have lower
+// indices, were dispatched earlier and do the same amount of work, so their flags are normally up already; the wait is
+// bounded all the same: when it runs out the boundary groups are left to the channel's last CTA, which by construction
+// runs after everybody's outputs are in place.  No CTA ever waits without bound on another.
+template <typename In, int kMaxChan>
+__device__ __forceinline__ void finish_segment(const RxFrontParamsT<kMaxChan> &p, const RxChan &ch, FrontSmem<In> *sm, uint32_t c,
+                                               uint32_t ta, uint32_t tb, uint32_t Tt, int t) {
+    const uint32_t grid = gridDim.x, cta = blockIdx.x;
+    const uint32_t cbase = p.tile_cum[c], cend = p.tile_cum[c + 1];
+    const uint32_t U = ch.units;
+    const unsigned long long qs = ch.q_base + (unsigned long long)kUnitOut * kTileUnits * ta;
+    const unsigned long long qe = ch.q_base + (unsigned long long)kUnitOut * ((uint32_t)kTileUnits * tb < U ? (uint32_t)kTileUnits * tb : U);
+    const unsigned long long total_d = ch.q_base + (unsigned long long)kUnitOut * U;
+    RxState *state = ch.state;
+    __syncthreads();                                      // this CTA's demod samples and decisions are visible to all its threads
+    if (ch.search) {
+        SegGroups g = seg_groups(qs, qe, ta == 0);
+        if (g.mid > g.lo) {
+            if (t == 0) {
+                const unsigned long long need = 32ull * g.lo >= 32ull ? 32ull * g.lo - 32ull : 0ull;   // first sample the boundary groups read
+                const uint32_t tile_lo = need > ch.q_base ? (uint32_t)((need - ch.q_base) / (unsigned)(kUnitOut * kTileUnits)) : 0u;
+                bool ok = p.defer_all == 0;
+                for (uint32_t k = tile_owner(Tt, grid, cbase + tile_lo); ok && k < cta; ++k) {
+                    int spins = 0;
+                    while (ld_acquire_u32(&ch.flags[k]) != ch.epoch) {
+                        if (++spins > 2000) { ok = false; break; }           // ~0.2 ms
+                        __nanosleep(100);
+                    }
+                }
+                if (!ok) atomicOr(&state->left_mask[cta >> 5], 1u << (cta & 31));
+                sm->flag_ok = ok ? 1u : 0u;
+            }
+            __syncthreads();
+            if (!sm->flag_ok) g.lo = g.mid;
+        }
+        search_groups(ch, g.lo, g.hi, t);
+    }
+    __syncthreads();
+    if (t == 0) {
+        __threadfence();
+        st_release_u32(&ch.flags[cta], ch.epoch);
+        const uint32_t n_touch = tile_owner(Tt, grid, cend - 1) - tile_owner(Tt, grid, cbase) + 1u;
+        const unsigned int prev = atomicAdd(&state->front_done, 1u);
+        sm->is_last = prev + 1u == n_touch ? 1u : 0u;
+    }
+    __syncthreads();
+    if (sm->is_last) {
+        __threadfence();
+        if (ch.search) {
+            // boundary groups other CTAs gave up waiting for
+            const uint32_t k0 = tile_owner(Tt, grid, cbase), k1 = tile_owner(Tt, grid, cend - 1);
+            for (uint32_t k = k0; k <= k1; ++k) {
+                if (!((__ldcg(&state->left_mask[k >> 5]) >> (k & 31)) & 1u)) continue;
+                uint32_t lo = cta_tile_lo(Tt, grid, k), hi = cta_tile_lo(Tt, grid, k + 1);
+                if (lo < cbase) lo = cbase;
+                if (hi > cend) hi = cend;
+                const unsigned long long ks = ch.q_base + (unsigned long long)kUnitOut * kTileUnits * (lo - cbase);
+                const uint32_t ku = (uint32_t)kTileUnits * (hi - cbase);
+                const unsigned long long ke = ch.q_base + (unsigned long long)kUnitOut * (ku < U ? ku : U);
+                const SegGroups g = seg_groups(ks, ke, lo == cbase);
+                search_groups(ch, g.lo, g.mid, t);
+            }
+            __syncthreads();
+            for (uint32_t w = t; w < (uint32_t)(kMaxGrid / 32); w += kTB) state->left_mask[w] = 0u;
+            __threadfence();
+            __syncthreads();
+            select_channel(state, ch.cand, ch.cand + kMaxCand, ch.acc + (size_t)ch.par * kMaxAccept, ch.par, total_d, ch.host_pub);
+        }
+        if (t == 0) state->front_done = 0u;
+    }
+}
+
+template <typename In, int kMinCtas, bool kUnitScale, int kMaxChan>
+__global__ void __launch_bounds__(kTB, kMinCtas) rx_front_kernel(const __grid_constant__ RxFrontParamsT<kMaxChan> p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    FrontSmem<In> *sm = reinterpret_cast<FrontSmem<In> *>(smem_raw);
+    const int t = threadIdx.x;
+    const uint32_t grid = gridDim.x, cta = blockIdx.x;
+    const uint32_t Tt = p.tile_cum[kMaxChan == 1 ? 1 : p.nchan];
+    const uint32_t gt_lo = cta_tile_lo(Tt, grid, cta), gt_hi = cta_tile_lo(Tt, grid, cta + 1);
+
+    if (t == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&sm->full[s], 1);
+        mbar_fence_init();
+    }
+    uint32_t it = 0, c = 0;
+    for (uint32_t g0 = gt_lo; g0 < gt_hi;) {
+        if constexpr (kMaxChan > 1) { while (p.tile_cum[c + 1] <= g0) ++c; }
+        const RxChan &ch = p.ch[kMaxChan == 1 ? 0 : c];
+        const uint32_t cbase = p.tile_cum[c], cend = p.tile_cum[c + 1];
+        const uint32_t g1 = gt_hi < cend ? gt_hi : cend;
+        const uint32_t ta = g0 - cbase, tb = g1 - cbase;
+
+        // next call's tail = logical samples [units*kUnit - kHist, carry + nchunk): the CTAs that touch the channel copy a slice
+        // each (saves a memcpy node between consecutive front kernels)
+        {
+            const uint32_t k0 = tile_owner(Tt, grid, cbase), nsl = tile_owner(Tt, grid, cend - 1) - k0 + 1u;
+            const long first = (long)ch.units * kUnit - kHist;
+            const uint32_t len = (uint32_t)((long)ch.carry + (long)ch.nchunk - first);
+            const uint32_t per = (len + nsl - 1u) / nsl;
+            const uint32_t lo = (cta - k0) * per, hi = lo + per < len ? lo + per : len;
+            const In *tl = static_cast<const In *>(ch.tail) + (long)kHist;
+            const In *ck = static_cast<const In *>(ch.chunk) - (long)ch.carry;
+            In *dst = static_cast<In *>(ch.tail_out);
+            for (uint32_t i = lo + (uint32_t)t; i < hi; i += kTB) {
+                const long L = first + (long)i;
+                dst[i] = L < (long)ch.carry ? tl[L] : ck[L];
+            }
+        }
+
+        run_segment<In, kUnitScale, kMaxChan>(p, ch, sm, ta, tb, it, t);
+        finish_segment<In, kMaxChan>(p, ch, sm, c, ta, tb, Tt, t);
+        g0 = g1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// native-rate front end: complex IQ @400 kS/s (the reference's own operating point, grc/ampsbs.grc:263).
+// No decimating first stage: v[m] = x[m] e^{-j theta m}, then exactly freq_xlating_fir_filter_ccc's filter /2 and
+// quadrature_demod_cf.  At 0.4 MS/s real time this kernel is never a bottleneck (it is FFMA-bound: 150 FFMA2 per
+// 8-byte sample); it exists so that recc_iq drops into the reference flowgraph at its native rate.
+// ---------------------------------------------------------------------------------------------
+template <typename In, bool kUnitScale>
+__global__ void __launch_bounds__(kTB, 4) rx_front400_kernel(const __grid_constant__ RxFront400Params p) {
+    __shared__ PassSmem ps;
+    const int t = threadIdx.x;
+    uint32_t pa = blockIdx.x * p.pass_per_cta;
+    if (pa >= p.npass) return;
+    uint32_t pb = pa + p.pass_per_cta;
+    if (pb > p.npass) pb = p.npass;
+    PassOut o;
+    o.dring = p.dring; o.hring = p.hring; o.ydump = p.ydump; o.dmask = p.dmask;
+    auto load = [&](long L) -> float2 {                   // logical sample L of this call; L < 0 = history
+        const float2 x = to_c32<kUnitScale>(L < 0 ? static_cast<const In *>(p.tail)[(long)kPass400 + L] : static_cast<const In *>(p.chunk)[L], p.in_scale);
+        const unsigned long long nabs = p.n_base + (unsigned long long)(long long)L;    // (x is 0 where this wraps: stream start)
+        const uint32_t b = (uint32_t)(nabs / kD1), k = (uint32_t)(nabs % kD1);
+        return cmul(fma2(splat(x.y), p.wj[k], mul2(splat(x.x), p.w[k])), sincos_phase(b * p.fcw25));
+    };
+    const long first = (long)pa * kPass400;
+    // warm-up: the kPorchCols columns of history in front of the first pass
+    for (int idx = t; idx < 2 * kR * kPorchCols; idx += kTB) {
+        const int mrel = idx - 2 * kR * kPorchCols;
+        store_v(&ps, mrel, load(first + mrel));
+    }
+    finish_pass(p.h2, o, &ps, true, -1, 0ull, 0ull, kTB, t);
+    for (uint32_t pc = 0; pc < pb - pa; ++pc) {
+        const long base = first + (long)pc * kPass400;
+        __syncthreads();                                   // the history shuffle of the previous pass is done
+#pragma unroll
+        for (int u = 0; u < kPassTiles; ++u) store_v(&ps, u * kTB + t, load(base + u * kTB + t));
+        const unsigned long long ql = (unsigned long long)(pa + pc) * kPassOut;
+        finish_pass(p.h2, o, &ps, false, (int)pc, p.q_base + ql, ql, kTB, t);
+    }
+}
+
+cudaError_t launch_rx_front400(const RxFront400Params &p, int grid, cudaStream_t st, bool sc16, bool unit) {
+    if (sc16 && unit) rx_front400_kernel<short2, true><<<grid, kTB, 0, st>>>(p);
+    else if (sc16) rx_front400_kernel<short2, false><<<grid, kTB, 0, st>>>(p);
+    else rx_front400_kernel<float2, false><<<grid, kTB, 0, st>>>(p);
     return cudaGetLastError();
 }
 
-// blobs == nullptr: feed-forward timing, the symbols are sliced out of the demod ring at the accepted phase.
-// blobs != nullptr: M&M timing mode, amps.recc already cut the 3374-byte blobs (rx_mm_recc_kernel).
-__global__ void __launch_bounds__(256) rx_capture_kernel(const float *__restrict__ dring, uint32_t dmask, RxState *state,
-                                                        const Accepted *acc, amps_burst *host_ring, unsigned int ring_len,
-                                                        RxPublished *host_pub, unsigned int decim,
-                                                        const uint8_t *__restrict__ blobs,
-                                                        const unsigned long long *__restrict__ blob_sym_index) {
-    __shared__ __align__(16) unsigned char rec_raw[sizeof(amps_burst)];
-    __shared__ uint8_t s_valid[40];
-    __shared__ unsigned int s_errs[8];
-    const unsigned int n_acc = state->n_acc;
-    if (blockIdx.x >= n_acc) return;
-    const int t = threadIdx.x, nt = blockDim.x;
-    amps_burst *rec = reinterpret_cast<amps_burst *>(rec_raw);
-    if (blobs) {
-        for (int s = t; s < kCapture; s += nt) rec->symbols[s] = blobs[(size_t)blockIdx.x * kCapture + s];
-        if (t == 0) {
-            // position bookkeeping is nominal here: the recovered half-symbol index, 10 demod samples per half-symbol
-            const unsigned long long first_sym = blob_sym_index[blockIdx.x];
-            const unsigned long long trig_sym = first_sym >= (unsigned long long)kTrig ? first_sym - kTrig : 0ull;
-            rec->demod_index = trig_sym * (unsigned long long)kOS;
-            rec->sample_index = rec->demod_index * (unsigned long long)decim;
-            rec->corr = 0.0f;
-            rec->run_length = 0;
-            rec->pad[0] = 0; rec->pad[1] = 0;
-        }
-    } else {
-        const Accepted a = acc[blockIdx.x];
-        // the 3374 half-symbols after the trigger, sliced at the chosen sampling phase (recc_impl.cc:124-126)
-        for (int s = t; s < kCapture; s += nt) {
-            const float v = dring[(a.pos + (unsigned long long)(kOS * (kTrig + s))) & dmask];
-            rec->symbols[s] = v >= 0.0f ? 1 : 0;
-        }
-        if (t == 0) {
-            rec->demod_index = a.pos;
-            rec->sample_index = a.pos * (unsigned long long)decim;
-            rec->corr = a.corr;
-            rec->run_length = a.run;
-            rec->pad[0] = 0; rec->pad[1] = 0;
-        }
+// sc16 tiles are half the size, so three CTAs fit an SM (the kernel is no longer HBM-bound at 4 B/sample)
+constexpr int kSc16Ctas = 3;
+cudaError_t launch_rx_front(const RxFrontParams1 &p, int grid, cudaStream_t st, bool sc16, bool unit) {
+    if (sc16 && unit) rx_front_kernel<short2, kSc16Ctas, true, 1><<<grid, kTB, sizeof(FrontSmem<short2>), st>>>(p);
+    else if (sc16) rx_front_kernel<short2, kSc16Ctas, false, 1><<<grid, kTB, sizeof(FrontSmem<short2>), st>>>(p);
+    else rx_front_kernel<float2, 2, false, 1><<<grid, kTB, sizeof(FrontSmem<float2>), st>>>(p);
+    return cudaGetLastError();
+}
+cudaError_t launch_rx_front_batch(const RxFrontParamsB &p, int grid, cudaStream_t st, bool sc16, bool unit) {
+    if (sc16 && unit) rx_front_kernel<short2, kSc16Ctas, true, kMaxBatch><<<grid, kTB, sizeof(FrontSmem<short2>), st>>>(p);
+    else if (sc16) rx_front_kernel<short2, kSc16Ctas, false, kMaxBatch><<<grid, kTB, sizeof(FrontSmem<short2>), st>>>(p);
+    else rx_front_kernel<float2, 2, false, kMaxBatch><<<grid, kTB, sizeof(FrontSmem<float2>), st>>>(p);
+    return cudaGetLastError();
+}
+int rx_front_ctas_per_sm(bool sc16) { return sc16 ? kSc16Ctas : 2; }
+
+// ---------------------------------------------------------------------------------------------
+// stand-alone trigger search + selection on a demod ring (the 400 kS/s front end's tail): groups [g_lo, g_hi), the same
+// rules as inside rx_front_kernel; the last CTA to finish selects.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rx_search_kernel(const float *__restrict__ dring, const uint32_t *__restrict__ hring, uint32_t dmask,
+                                                       RxState *state, Candidate *cand, Accepted *acc, RxPublished *host_pub,
+                                                       unsigned long long g_lo, unsigned long long g_hi, unsigned long long total_d,
+                                                       uint32_t par) {
+    __shared__ uint32_t s_last;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long g = g_lo + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; g < g_hi; g += stride)
+        detect_group(dring, hring, dmask, state, cand, 32ull * g);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(&state->front_done, 1u) + 1u == gridDim.x ? 1u : 0u;
     }
     __syncthreads();
-    decode_burst_block(rec->symbols, &rec->decoded, s_valid, s_errs);
-    // publish: stream the finished record into the host-visible ring (posted PCIe writes)
-    const unsigned long long rec_base = state->rec_base;
-    // (when one call accepts more bursts than the ring holds, only the newest ring_len are written: two CTAs must
-    // never race for the same slot)
-    if (n_acc - blockIdx.x <= ring_len) {
-        const unsigned long long *src = reinterpret_cast<const unsigned long long *>(rec);
-        unsigned long long *dst = reinterpret_cast<unsigned long long *>(&host_ring[(rec_base + blockIdx.x) % ring_len]);
-        for (int w = t; w < (int)(sizeof(amps_burst) / 8); w += nt) dst[w] = src[w];
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (t == 0) {
-        const unsigned int prev = atomicAdd(&state->done, 1u);
-        if (prev + 1 == n_acc) {                          // last CTA: every record is on its way, publish the count
-            __threadfence_system();
-            host_pub->cand_overflow = state->cand_overflow;
-            host_pub->nrec_total = rec_base + n_acc;
-        }
+    if (s_last) {
+        __threadfence();
+        select_channel(state, cand, cand + kMaxCand, acc + (size_t)par * kMaxAccept, par, total_d, host_pub);
+        if (threadIdx.x == 0) state->front_done = 0u;
     }
 }
 
-cudaError_t launch_rx_capture(const float *dring, uint32_t dmask, RxState *state, const Accepted *acc, int grid,
-                              amps_burst *host_ring, unsigned int ring_len, RxPublished *host_pub, unsigned int decim,
-                              cudaStream_t st, const uint8_t *blobs, const unsigned long long *blob_sym_index) {
+cudaError_t launch_rx_search(const float *dring, const uint32_t *hring, uint32_t dmask, RxState *state, Candidate *cand,
+                             Accepted *acc, RxPublished *host_pub, unsigned long long g_lo, unsigned long long g_hi,
+                             unsigned long long total_d, uint32_t par, cudaStream_t st) {
+    unsigned long long groups = g_hi > g_lo ? g_hi - g_lo : 0ull;
+    unsigned int grid = (unsigned int)((groups + 255ull) / 256ull);
+    if (grid < 1u) grid = 1u;
+    if (grid > 592u) grid = 592u;
+    rx_search_kernel<<<grid, 256, 0, st>>>(dring, hring, dmask, state, cand, acc, host_pub, g_lo, g_hi, total_d, par);
+    return cudaGetLastError();
+}
+
+// ============================================================================================
+// burst capture (CTAs [cta_first, cta_first + cta_count) of the launch serve channel c, one burst at a time)
+// ============================================================================================
+// blobs == nullptr: feed-forward timing, the symbols are sliced out of the demod ring at the accepted phase.
+// blobs != nullptr: M&M timing mode, amps.recc already cut the 3374-byte blobs (rx_mm_recc_kernel).
+__global__ void __launch_bounds__(256) rx_capture_kernel(const __grid_constant__ RxCaptureParams p) {
+    __shared__ __align__(16) unsigned char rec_raw[sizeof(amps_burst)];
+    __shared__ uint8_t s_valid[40];
+    __shared__ unsigned int s_errs[8];
+    uint32_t c = 0;
+    while (c + 1 < p.nchan && blockIdx.x >= p.ch[c + 1].cta_first) ++c;
+    const RxCaptureChan &ch = p.ch[c];
+    RxState *state = ch.state;
+    const unsigned int n_acc = state->n_acc[ch.par];
+    const unsigned long long rec_base = state->rec_base[ch.par];
+    const int t = threadIdx.x, nt = blockDim.x;
+    amps_burst *rec = reinterpret_cast<amps_burst *>(rec_raw);
+    for (unsigned int b = blockIdx.x - ch.cta_first; b < n_acc; b += ch.cta_count) {
+        if (ch.blobs) {
+            for (int s = t; s < kCapture; s += nt) rec->symbols[s] = ch.blobs[(size_t)b * kCapture + s];
+            if (t == 0) {
+                // position bookkeeping is nominal here: the recovered half-symbol index, 10 demod samples per half-symbol
+                const unsigned long long first_sym = ch.blob_sym_index[b];
+                const unsigned long long trig_sym = first_sym >= (unsigned long long)kTrig ? first_sym - kTrig : 0ull;
+                rec->demod_index = trig_sym * (unsigned long long)kOS;
+                rec->sample_index = rec->demod_index * (unsigned long long)ch.decim;
+                rec->corr = 0.0f;
+                rec->run_length = 0;
+                rec->pad[0] = 0; rec->pad[1] = 0;
+            }
+        } else {
+            const Accepted a = ch.acc[b];
+            // the 3374 half-symbols after the trigger, sliced at the chosen sampling phase (recc_impl.cc:124-126)
+            for (int s = t; s < kCapture; s += nt) {
+                const float v = ch.dring[(a.pos + (unsigned long long)(kOS * (kTrig + s))) & ch.dmask];
+                rec->symbols[s] = v >= 0.0f ? 1 : 0;
+            }
+            if (t == 0) {
+                rec->demod_index = a.pos;
+                rec->sample_index = a.pos * (unsigned long long)ch.decim;
+                rec->corr = a.corr;
+                rec->run_length = a.run;
+                rec->pad[0] = 0; rec->pad[1] = 0;
+            }
+        }
+        __syncthreads();
+        decode_burst_block(rec->symbols, &rec->decoded, s_valid, s_errs);
+        // publish: stream the finished record into the host-visible ring (posted PCIe writes)
+        // (when one call accepts more bursts than the ring holds, only the newest ring_len are written: two CTAs must
+        // never race for the same slot)
+        if (n_acc - b <= ch.ring_len) {
+            const unsigned long long *src = reinterpret_cast<const unsigned long long *>(rec);
+            unsigned long long *dst = reinterpret_cast<unsigned long long *>(&ch.host_ring[(rec_base + b) % ch.ring_len]);
+            for (int w = t; w < (int)(sizeof(amps_burst) / 8); w += nt) dst[w] = src[w];
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (t == 0) {
+            const unsigned int prev = atomicAdd(&state->done, 1u);
+            if (prev + 1 == n_acc) {                          // last burst of the call: every record is on its way, publish the count
+                state->done = 0;
+                state->pub_overflow = state->cand_overflow;
+                __threadfence_system();
+                ch.host_pub->cand_overflow = state->cand_overflow;
+                ch.host_pub->nrec_total = rec_base + n_acc;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+cudaError_t launch_rx_capture(const RxCaptureParams &p, int grid, cudaStream_t st) {
     if (grid <= 0) return cudaSuccess;
-    if (grid > kMaxAccept) grid = kMaxAccept;
-    rx_capture_kernel<<<grid, 256, 0, st>>>(dring, dmask, state, acc, host_ring, ring_len, host_pub, decim, blobs, blob_sym_index);
+    rx_capture_kernel<<<grid, 256, 0, st>>>(p);
     return cudaGetLastError();
 }
 
@@ -765,22 +968,22 @@ __global__ void __launch_bounds__(128) rx_mm_kernel(const float *__restrict__ dr
 
 // amps.recc on the symbols the M&M kernel just produced, in work() calls of kMmQuantum bytes (the reference sees the
 // stream in scheduler-sized pieces and searches / publishes at most once per call, lib/recc_impl.cc:115-126), then the
-// bookkeeping rx_select_kernel does in the feed-forward mode.
+// bookkeeping select_channel does in the feed-forward mode.
 __global__ void __launch_bounds__(256) rx_mm_recc_kernel(ReccCompatState *cs, const MmState *mm, const uint8_t *__restrict__ sym,
                                                         uint8_t *blobs, unsigned long long *blob_sym_index, int max_blobs,
-                                                        RxState *state, RxPublished *host_pub) {
+                                                        RxState *state, RxPublished *host_pub, uint32_t par) {
     const unsigned int n = mm->n_new;
     const int nchunks = (int)((n + (unsigned)kMmQuantum - 1u) / (unsigned)kMmQuantum);
     int nb = recc_compat_run(cs, sym, nchunks,
                              [n](int c) { const unsigned int rem = n - (unsigned)c * (unsigned)kMmQuantum; return rem < (unsigned)kMmQuantum ? rem : (unsigned)kMmQuantum; },
                              blobs, max_blobs, blob_sym_index);
     if (threadIdx.x == 0) {
-        if (nb > max_blobs) { state->cand_overflow = 1; nb = max_blobs; }
-        state->n_acc = (unsigned int)nb;
-        state->done = 0;
-        state->rec_base = state->nrec_total;
+        if (nb > max_blobs) { state->cand_overflow += (unsigned int)(nb - max_blobs); nb = max_blobs; }
+        state->n_acc[par] = (unsigned int)nb;
+        state->rec_base[par] = state->nrec_total;
         state->nrec_total += (unsigned long long)nb;
-        if (nb == 0) {
+        if (nb == 0 && state->cand_overflow != state->pub_overflow) {
+            state->pub_overflow = state->cand_overflow;
             __threadfence_system();
             host_pub->cand_overflow = state->cand_overflow;
         }
@@ -790,26 +993,32 @@ __global__ void __launch_bounds__(256) rx_mm_recc_kernel(ReccCompatState *cs, co
 cudaError_t launch_rx_mm(const float *dring, uint32_t dmask, unsigned long long total_d, MmState *mm, const float *table,
                          uint8_t *sym, unsigned int sym_cap, ReccCompatState *cs, uint8_t *blobs,
                          unsigned long long *blob_sym_index, int max_blobs, RxState *state, RxPublished *host_pub,
-                         cudaStream_t st) {
+                         uint32_t par, cudaStream_t st) {
     rx_mm_kernel<<<1, 128, 0, st>>>(dring, dmask, total_d, mm, table, sym, sym_cap);
-    rx_mm_recc_kernel<<<1, 256, 0, st>>>(cs, mm, sym, blobs, blob_sym_index, max_blobs, state, host_pub);
+    rx_mm_recc_kernel<<<1, 256, 0, st>>>(cs, mm, sym, blobs, blob_sym_index, max_blobs, state, host_pub, par);
     return cudaGetLastError();
 }
 
 // per-device opt-in to large dynamic shared memory (call once per device after cudaSetDevice)
+template <typename K>
+static cudaError_t front_attrs(K kernel, size_t smem) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
 cudaError_t rx_configure_device() {
-    cudaError_t e = cudaFuncSetAttribute(rx_front_kernel<float2, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrontSmem<float2>));
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(rx_front_kernel<short2, kSc16Ctas, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrontSmem<short2>));
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(rx_front_kernel<short2, kSc16Ctas, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrontSmem<short2>));
-    if (e != cudaSuccess) return e;
+    cudaError_t e;
+    if ((e = front_attrs(rx_front_kernel<float2, 2, false, 1>, sizeof(FrontSmem<float2>))) != cudaSuccess) return e;
+    if ((e = front_attrs(rx_front_kernel<short2, kSc16Ctas, false, 1>, sizeof(FrontSmem<short2>))) != cudaSuccess) return e;
+    if ((e = front_attrs(rx_front_kernel<short2, kSc16Ctas, true, 1>, sizeof(FrontSmem<short2>))) != cudaSuccess) return e;
+    if ((e = front_attrs(rx_front_kernel<float2, 2, false, kMaxBatch>, sizeof(FrontSmem<float2>))) != cudaSuccess) return e;
+    if ((e = front_attrs(rx_front_kernel<short2, kSc16Ctas, false, kMaxBatch>, sizeof(FrontSmem<short2>))) != cudaSuccess) return e;
+    if ((e = front_attrs(rx_front_kernel<short2, kSc16Ctas, true, kMaxBatch>, sizeof(FrontSmem<short2>))) != cudaSuccess) return e;
     // The side-stream kernels share SMs with the NEXT call's front kernel, whose two CTAs need 199 KB of shared memory per
     // SM.  An SM's L1/shared split is fixed while CTAs are resident: if a kernel that wants a big L1 gets there first, the
     // front CTAs wait until it has left.  Ask for the front kernel's split everywhere.
-    const void *side[] = {(const void *)rx_detect_kernel, (const void *)rx_select_kernel, (const void *)rx_capture_kernel,
-                          (const void *)rx_mm_kernel, (const void *)rx_mm_recc_kernel, (const void *)rx_front_kernel<float2, 2, false>,
-                          (const void *)rx_front_kernel<short2, kSc16Ctas, false>, (const void *)rx_front_kernel<short2, kSc16Ctas, true>};
+    const void *side[] = {(const void *)rx_search_kernel, (const void *)rx_capture_kernel, (const void *)rx_mm_kernel,
+                          (const void *)rx_mm_recc_kernel};
     for (const void *f : side) {
         e = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;

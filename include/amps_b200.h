@@ -140,9 +140,12 @@ AMPS_B200_API int amps_recc_iq_reset(amps_recc_iq *h);          /* back to strea
 
 /* Host-buffer streaming call -- what a gr::sync_block::work() does with the scheduler's input
  * buffer (interleaved float re,im; nsamples complex samples).  Copies H2D, runs the fused kernels,
- * copies burst records D2H and invokes cb once per burst, in stream order (the equivalent of
- * message_port_pub("bursts", ...), lib/recc_impl.cc:126).  Any nsamples >= 0 is accepted; samples
- * that do not fill a processing pass are carried to the next call. */
+ * and invokes cb once per burst, in stream order (the equivalent of message_port_pub("bursts", ...),
+ * lib/recc_impl.cc:126); the records arrive in a pinned host ring the capture kernel writes into.  Any
+ * nsamples >= 0 is accepted; samples that do not fill a processing quantum (amps_recc_iq_granularity():
+ * 1600 samples = 32 demodulated samples at 10 MS/s, 1536 at 400 kS/s) are carried to the next call.
+ * Returns AMPS_E_OVERFLOW ONCE (after delivering what was captured) when the device-side list of
+ * undecided trigger candidates overflowed (> 8192) and candidates had to be dropped; the stream goes on. */
 AMPS_B200_API int amps_recc_iq_work(amps_recc_iq *h, const float *iq_host, size_t nsamples,
                                     amps_burst_cb cb, void *user);
 
@@ -150,9 +153,12 @@ AMPS_B200_API int amps_recc_iq_work(amps_recc_iq *h, const float *iq_host, size_
 AMPS_B200_API int amps_recc_iq_work_sc16(amps_recc_iq *h, const int16_t *iq_host, size_t nsamples,
                                          amps_burst_cb cb, void *user);
 
-/* Device-resident variant: d_iq is a device pointer (16-byte aligned) on the handle's device,
- * nsamples a multiple of amps_recc_iq_granularity(); kernels are enqueued on cuda_stream
- * (a cudaStream_t, NULL = default stream) and the call returns without synchronising. */
+/* Device-resident variant: d_iq is a device pointer (16-byte aligned) on the handle's device; kernels are
+ * enqueued on cuda_stream (a cudaStream_t, NULL = default stream) and the call returns without synchronising:
+ * one front launch (filter + demod + trigger search + burst selection) and one capture launch per call.
+ * At 10 MS/s nsamples may be any count whose bytes are a multiple of 16 (fc32: even, sc16: multiple of 4):
+ * what does not fill a 1600-sample quantum is carried, on the device, into the next call.  At 400 kS/s
+ * nsamples must be a multiple of amps_recc_iq_granularity(). */
 AMPS_B200_API int amps_recc_iq_submit_dev(amps_recc_iq *h, const void *d_iq, size_t nsamples, void *cuda_stream);
 AMPS_B200_API int amps_recc_iq_submit_sc16_dev(amps_recc_iq *h, const void *d_iq, size_t nsamples, void *cuda_stream);
 /* Waits for the stream, copies out the bursts published since the last collect (at most max; the
@@ -177,6 +183,34 @@ AMPS_B200_API int amps_recc_iq_stats(const amps_recc_iq *h, uint64_t *samples_in
  * first, at most cap (the handle keeps the last 256).  Synchronises the stream. */
 AMPS_B200_API int amps_recc_iq_front_times(amps_recc_iq *h, float *ms_out, int cap, int *n_out);
 AMPS_B200_API int amps_recc_iq_get_taps(const amps_recc_iq *h, float *lpf_out, int cap);                   /* returns ntaps */
+
+/* ------------------------------------------------------------------------------------------
+ * Batched calls: K channels (handles) of ONE GPU served by one front launch + one capture launch per call
+ * (per 64 channels).  This is "one carrier per GPU, round-robin beyond 8"  when there are more
+ * carriers than GPUs, and the "one uploaded wideband buffer feeds several carriers" case: the reference
+ * would instantiate K freq_xlating_fir_filter -> ... -> amps.recc chains on one uhd.usrp_source
+ * (grc/ampsbs.grc:1814-1872 with K values of rx_offset, :212-238).
+ * Handles must be fresh (or reset), 10 MS/s, feed-forward timing, same device and input format; while they
+ * belong to a batch they are driven through it only.  Bursts are collected per handle with
+ * amps_recc_iq_collect / _peek / _poll / _consume as usual.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct amps_recc_iq_batch amps_recc_iq_batch;
+typedef void (*amps_batch_burst_cb)(int channel, const amps_burst *burst, void *user);
+AMPS_B200_API int amps_recc_iq_batch_create(amps_recc_iq *const *handles, int count, uint32_t flags /* AMPS_RX_TIME_KERNELS or 0 */,
+                                            amps_recc_iq_batch **out);
+AMPS_B200_API int amps_recc_iq_batch_destroy(amps_recc_iq_batch *b);     /* the handles stay valid and become individually usable again */
+AMPS_B200_API int amps_recc_iq_batch_size(const amps_recc_iq_batch *b);
+/* channel i gets nsamples[i] new samples at device pointer d_iq[i] (16-byte aligned, byte count a multiple of 16;
+ * several channels may name the same buffer).  Returns without synchronising. */
+AMPS_B200_API int amps_recc_iq_batch_submit_dev(amps_recc_iq_batch *b, const void *const *d_iq, const size_t *nsamples,
+                                                void *cuda_stream);
+/* ONE host buffer (fc32, or sc16 for sc16 handles), uploaded once; every channel demodulates it at its own
+ * center_freq.  cb is invoked per burst with the channel index, channel by channel, in stream order within a channel. */
+AMPS_B200_API int amps_recc_iq_batch_work_shared(amps_recc_iq_batch *b, const void *iq_host, size_t nsamples,
+                                                 amps_batch_burst_cb cb, void *user);
+/* needs AMPS_RX_TIME_KERNELS at batch_create: device time (ms) of the front launch(es) of the most recent calls */
+AMPS_B200_API int amps_recc_iq_batch_front_times(amps_recc_iq_batch *b, float *ms_out, int cap, int *n_out);
+AMPS_B200_API int amps_recc_iq_batch_stats(const amps_recc_iq_batch *b, uint64_t *calls, uint64_t *kernel_launches);
 
 /* ------------------------------------------------------------------------------------------
  * recc_decode: message-only block (lib/recc_decode_impl.cc:81-169).  blob = 3374 hard half-symbols.

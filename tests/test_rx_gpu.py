@@ -8,8 +8,9 @@ from tests.helpers import bits_equal_f32, words_equal
 
 pytestmark = pytest.mark.gpu
 
-PASS = 38400             # amps_recc_iq_granularity()
-N1 = 55 * PASS           # one config-2 period rounded to whole passes (2 112 000 samples)
+PASS = 38400             # one full pass of the front kernel (24 units)
+UNIT = 1600              # amps_recc_iq_granularity() at 10 MS/s: 32 demodulated samples, one word of hard decisions
+N1 = 55 * PASS           # one config-2 period (2 112 000 samples)
 
 
 @pytest.fixture(scope="module")
@@ -70,7 +71,7 @@ def test_chunked_stream_equals_one_shot(capi, oracle):
         n = int(rng.integers(1, 400000))
         got += st.work(x[pos:pos + n])
         pos += n
-    assert st.granularity == PASS and st.stats()["demod_out"] == len(x) // PASS * (PASS // 50)
+    assert st.granularity == UNIT and st.stats()["demod_out"] == len(x) // UNIT * (UNIT // 50)
     assert len(b1) == 2 and len(got) == 2
     for a, b in zip(b1, got):
         assert a.demod_index == b.demod_index and bytes(a.symbols) == bytes(b.symbols)
@@ -103,17 +104,20 @@ def test_device_resident_many_bursts(capi, oracle):
 def test_empty_and_tiny_calls(capi):
     rx = capi.ReccIq(max_samples=PASS * 4)
     assert rx.work(np.zeros(0, np.complex64)) == []
-    for n in (1, 7, 49, 50, 38399):                      # less than one pass: carried, nothing produced yet
+    for n in (1, 7, 49, 50, 1492):                       # less than one unit: carried, nothing produced yet
+        assert rx.work(np.zeros(n, np.complex64)) == []
+        assert rx.stats()["demod_out"] == 0
+    for n in (1, 38399):
         assert rx.work(np.zeros(n, np.complex64)) == []
     st = rx.stats()
-    assert st["demod_out"] == (1 + 7 + 49 + 50 + 38399) // PASS * (PASS // 50)
+    assert st["demod_out"] == (1 + 7 + 49 + 50 + 1492 + 1 + 38399) // UNIT * (UNIT // 50)
     with pytest.raises(capi.AmpsError):
         rx.work(np.zeros(PASS * 4 + PASS + 1, np.complex64))     # more than max_samples
     import torch
     t = torch.zeros(2 * PASS + 2, dtype=torch.float32, device="cuda")
     rx2 = capi.ReccIq(max_samples=PASS * 4)
     with pytest.raises(capi.AmpsError):
-        rx2.submit_dev(t.data_ptr(), PASS + 1, 0)        # not a multiple of the granularity
+        rx2.submit_dev(t.data_ptr(), PASS + 1, 0)        # an odd count: the byte length is not a multiple of 16
     with pytest.raises(capi.AmpsError):
         rx2.submit_dev(t.data_ptr() + 8, PASS, 0)        # not 16-byte aligned
     rx.close(); rx2.close()
