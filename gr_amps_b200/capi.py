@@ -90,13 +90,14 @@ RX_DUMP_BASEBAND = 1
 RX_TIME_KERNELS = 2
 RX_TIMING_MM = 4
 RX_INPUT_SC16 = 8
+RX_FUSED_SEARCH = 16
 
 # every symbol include/amps_b200.h declares
 EXPORTS = [
     "amps_b200_version", "amps_b200_strerror", "amps_b200_last_error", "amps_b200_device_count", "amps_b200_abi_sizes",
     "amps_recc_iq_create", "amps_recc_iq_destroy", "amps_recc_iq_reset", "amps_recc_iq_work",
     "amps_recc_iq_submit_dev", "amps_recc_iq_work_sc16", "amps_recc_iq_submit_sc16_dev", "amps_recc_iq_collect", "amps_recc_iq_peek", "amps_recc_iq_consume", "amps_recc_iq_poll", "amps_recc_iq_granularity", "amps_recc_iq_read_demod",
-    "amps_recc_iq_read_baseband", "amps_recc_iq_stats", "amps_recc_iq_front_times", "amps_recc_iq_get_taps",
+    "amps_recc_iq_read_baseband", "amps_recc_iq_stats", "amps_recc_iq_front_times", "amps_recc_iq_get_taps", "amps_recc_iq_debug_prof",
     "amps_recc_iq_batch_create", "amps_recc_iq_batch_destroy", "amps_recc_iq_batch_size", "amps_recc_iq_batch_submit_dev",
     "amps_recc_iq_batch_work_shared", "amps_recc_iq_batch_front_times", "amps_recc_iq_batch_stats",
     "amps_recc_decode_create", "amps_recc_decode_destroy", "amps_recc_decode_burst", "amps_recc_decode_bursts",
@@ -202,11 +203,11 @@ class ReccIq:
 
     def __init__(self, max_samples: int, center_freq=-160e3, samp_rate=10e6, device=0, max_bursts=256,
                  dump_baseband=False, lpf_taps: np.ndarray | None = None, time_kernels=False, timing_mm=False,
-                 sc16=False, sc16_scale=0.0):
+                 sc16=False, sc16_scale=0.0, fused_search=False):
         self._taps = None if lpf_taps is None else np.ascontiguousarray(lpf_taps, dtype=np.float32)
         p = ReccIqParams(samp_rate, center_freq, device, max_samples, max_bursts,
                          (RX_DUMP_BASEBAND if dump_baseband else 0) | (RX_TIME_KERNELS if time_kernels else 0) | (RX_TIMING_MM if timing_mm else 0)
-                         | (RX_INPUT_SC16 if sc16 else 0),
+                         | (RX_INPUT_SC16 if sc16 else 0) | (RX_FUSED_SEARCH if fused_search else 0),
                          None if self._taps is None else self._taps.ctypes.data_as(f32p),
                          0 if self._taps is None else len(self._taps), sc16_scale)
         self.sc16 = sc16
@@ -297,6 +298,12 @@ class ReccIq:
         n = C.c_int(0)
         check(lib().amps_recc_iq_front_times(self.h, out.ctypes.data_as(f32p), cap, C.byref(n)))
         return out[:n.value].copy()
+
+    def debug_prof(self, ctas: int) -> np.ndarray:
+        out = np.zeros((ctas, 16), np.uint64)
+        lib().amps_recc_iq_debug_prof.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        check(lib().amps_recc_iq_debug_prof(self.h, out.ctypes.data_as(C.c_void_p), ctas))
+        return out
 
     def taps(self) -> np.ndarray:
         n = lib().amps_recc_iq_get_taps(self.h, None, 0)

@@ -47,7 +47,7 @@ struct amps_recc_iq {
     RxState     *d_state = nullptr;
     Candidate   *d_cand = nullptr;
     Accepted    *d_acc = nullptr;        // bursts accepted by the select of call parity 0 / 1 (2 x kMaxAccept entries)
-    uint32_t    *d_flags = nullptr;      // per-CTA completion flags of the front kernel (kMaxGrid words)
+    uint32_t    *d_flags = nullptr;      // boundary counters of the front kernel (kMaxGrid words, zero between launches)
     amps_burst  *h_ring = nullptr;       // mapped pinned host ring the capture kernel publishes into
     RxPublished *h_pub = nullptr;        // mapped pinned counters
     uint64_t     consumed = 0;           // bursts already handed to the caller
@@ -60,11 +60,14 @@ struct amps_recc_iq {
     uint64_t     call_no = 0;
     bool         serial = false;         // AMPS_RX_SERIAL=1: no overlap (profiling / A-B measurements)
     bool         front_only = false;     // AMPS_RX_FRONT_ONLY=1: no capture (pipeline measurements only: no bursts come out)
-    bool         defer_all = false;      // AMPS_RX_DEFER=1 (test hook): every boundary search is left to the channel's last CTA
     int          grid_cap = 0;           // AMPS_RX_GRID (test hook): cap on the front kernel's grid
+    bool         want_prof = false;      // AMPS_RX_PROF=1 (measurement aid): per-CTA time stamps of the last front launch
+    unsigned long long *d_prof = nullptr;
+    bool         nosearch = false;       // AMPS_RX_NOSEARCH=1 (measurement aid): no trigger search / selection in the front kernel
     amps_recc_iq_batch *batch = nullptr; // the handle is driven through a batch
     // AMPS_RX_TIMING_MM: the reference graph's serial tail instead of the feed-forward detector
     bool         mm_mode = false;
+    bool         fused = false;          // AMPS_RX_FUSED_SEARCH: trigger search + selection inside the front kernel (2 launches per call)
     MmState     *d_mm = nullptr;
     float       *d_mmtab = nullptr;
     uint8_t     *d_sym = nullptr;
@@ -142,6 +145,7 @@ static int rx_alloc(amps_recc_iq *h) {
     CK(cudaMemset(h->d_state, 0, sizeof(RxState)));
     CK(cudaMalloc(&h->d_cand, sizeof(Candidate) * kMaxCand * 2));      // candidates + the select's sorted copy
     CK(cudaMalloc(&h->d_acc, sizeof(Accepted) * kMaxAccept * 2));
+    if (h->want_prof) { CK(cudaMalloc(&h->d_prof, sizeof(unsigned long long) * 16 * kMaxGrid)); CK(cudaMemset(h->d_prof, 0, sizeof(unsigned long long) * 16 * kMaxGrid)); }
     CK(cudaMalloc(&h->d_flags, sizeof(uint32_t) * kMaxGrid));
     CK(cudaMemset(h->d_flags, 0, sizeof(uint32_t) * kMaxGrid));
     if (h->mm_mode) {
@@ -192,12 +196,15 @@ extern "C" int amps_recc_iq_create(const amps_recc_iq_params *params, amps_recc_
     h->max_records = params->max_bursts ? params->max_bursts : 256;
     h->flags = params->flags;
     h->mm_mode = (params->flags & AMPS_RX_TIMING_MM) != 0;
+    h->fused = (params->flags & AMPS_RX_FUSED_SEARCH) != 0;
+    { const char *e = std::getenv("AMPS_RX_FUSED"); if (e && e[0] == '1') h->fused = true; }
     h->sc16 = (params->flags & AMPS_RX_INPUT_SC16) != 0;
     h->isz = h->sc16 ? sizeof(short2) : sizeof(float2);
     { const char *e = std::getenv("AMPS_RX_SERIAL"); h->serial = e && e[0] == '1'; }
     { const char *e = std::getenv("AMPS_RX_FRONT_ONLY"); h->front_only = e && e[0] == '1'; }
-    { const char *e = std::getenv("AMPS_RX_DEFER"); h->defer_all = e && e[0] == '1'; }
     { const char *e = std::getenv("AMPS_RX_GRID"); h->grid_cap = e ? std::atoi(e) : 0; }
+    { const char *e = std::getenv("AMPS_RX_NOSEARCH"); h->nosearch = e && e[0] == '1'; }
+    { const char *e = std::getenv("AMPS_RX_PROF"); h->want_prof = e && e[0] == '1'; }
     if (params->lpf_taps) h->lpf.assign(params->lpf_taps, params->lpf_taps + params->n_lpf_taps);
     else h->lpf = firdes_low_pass(3.0, 400e3, 10e3, 4500.0, WIN_BLACKMAN);     // grc/ampsbs.grc:138-184
     h->fcw = nco_fcw(params->center_freq, params->samp_rate);
@@ -222,7 +229,6 @@ extern "C" int amps_recc_iq_create(const amps_recc_iq_params *params, amps_recc_
     for (size_t i = 0; i < cic.size(); ++i) h->fp.g[i] = cic[i];
     for (size_t i = 0; i < h->lpf.size(); ++i) h->fp.h2[i] = h->lpf[i];
     h->fp.nchan = 1;
-    h->fp.defer_all = h->defer_all ? 1u : 0u;
     h->fp400.fcw25 = c.fcw25;
     h->fp400.in_scale = c.in_scale;
     for (int k = 0; k < kD1; ++k) { h->fp400.w[k] = c.w[k]; h->fp400.wj[k] = h->fp.wj0[k]; }
@@ -246,7 +252,7 @@ extern "C" int amps_recc_iq_destroy(amps_recc_iq *h) {
     for (int i = 0; i < 2; ++i) if (h->ev_side[i]) cudaEventDestroy(h->ev_side[i]);
     for (int i = 0; i < amps_recc_iq::kEv; ++i) { if (h->ev0[i]) cudaEventDestroy(h->ev0[i]); if (h->ev1[i]) cudaEventDestroy(h->ev1[i]); }
     cudaFree(h->d_stage); cudaFree(h->d_tail[0]); cudaFree(h->d_tail[1]); cudaFree(h->d_dring); cudaFree(h->d_hring);
-    cudaFree(h->d_ydump); cudaFree(h->d_state); cudaFree(h->d_cand); cudaFree(h->d_acc); cudaFree(h->d_flags);
+    cudaFree(h->d_ydump); cudaFree(h->d_state); cudaFree(h->d_cand); cudaFree(h->d_acc); cudaFree(h->d_flags); cudaFree(h->d_prof);
     cudaFree(h->d_mm); cudaFree(h->d_mmtab); cudaFree(h->d_sym); cudaFree(h->d_compat); cudaFree(h->d_blobs); cudaFree(h->d_blob_idx);
     if (h->h_ring) cudaFreeHost(h->h_ring);
     if (h->h_pub) cudaFreeHost(h->h_pub);
@@ -275,7 +281,7 @@ extern "C" int amps_recc_iq_granularity(const amps_recc_iq *h) { return h ? (int
 // ---- per-channel pieces of a 10 MS/s call -----------------------------------------------------
 // Fills the launch arguments of one channel for `units` whole units out of [tail carry | chunk] and advances the handle's
 // host-side stream position.  par = call parity of whoever owns the call counter (the handle or its batch).
-static void chan_begin(amps_recc_iq *h, RxChan &c, const uint8_t *d_chunk, uint32_t nchunk, uint32_t units, uint32_t par, uint32_t epoch) {
+static void chan_begin(amps_recc_iq *h, RxChan &c, const uint8_t *d_chunk, uint32_t nchunk, uint32_t units, uint32_t par) {
     c = h->fp.ch[0];                                   // constant part (NCO tables, scale)
     c.chunk = d_chunk;
     c.tail = h->d_tail[h->tail_cur];
@@ -294,9 +300,8 @@ static void chan_begin(amps_recc_iq *h, RxChan &c, const uint8_t *d_chunk, uint3
     c.carry = h->dev_carry;
     c.nchunk = nchunk;
     c.blk_base = (uint32_t)(h->samples_in / kD1);
-    c.epoch = epoch;
     c.par = par;
-    c.search = h->mm_mode ? 0u : 1u;
+    c.search = (h->fused && !h->mm_mode && !h->nosearch) ? 1u : 0u;
     h->tail_cur ^= 1;
     h->dev_carry = h->dev_carry + nchunk - units * (uint32_t)kUnit;
     h->ydump_first = h->total_d;
@@ -319,6 +324,19 @@ static void chan_capture(const amps_recc_iq *h, RxCaptureChan &cc, uint32_t par,
     cc.par = par;
     cc.cta_first = cta_first;
     cc.cta_count = cta_count;
+}
+
+// the stand-alone search of a channel: every group whose lookahead is complete and that was not searched yet
+static uint32_t chan_search(amps_recc_iq *h, RxSearchChan &sc, uint32_t par, uint32_t cta_first) {
+    const uint64_t g_hi = h->total_d / kUnitOut >= (uint64_t)kGroupLag ? h->total_d / kUnitOut - kGroupLag : 0;
+    sc.dring = h->d_dring; sc.hring = h->d_hring; sc.state = h->d_state; sc.cand = h->d_cand; sc.acc = h->d_acc; sc.host_pub = h->h_pub;
+    sc.g_lo = h->groups_done;
+    sc.g_hi = g_hi > h->groups_done ? g_hi : h->groups_done;
+    sc.total_d = h->total_d;
+    sc.dmask = h->dmask; sc.par = par; sc.cta_first = cta_first;
+    sc.cta_count = rx_search_ctas(sc.g_hi - sc.g_lo);
+    h->groups_done = sc.g_hi;
+    return sc.cta_count;
 }
 
 // bursts one call of `outputs` demodulated samples can make capturable: they are at least kBurstLen apart, +1 for a run
@@ -346,17 +364,17 @@ static int rx_enqueue10(amps_recc_iq *h, const uint8_t *d_chunk, uint32_t nchunk
     // the demod ring and the accepted-burst lists hold two calls: do not overwrite what the capture of call k-2 may still read
     if (h->call_no >= 2) CK(cudaStreamWaitEvent(st, h->ev_side[par], 0));
     RxFrontParams1 p = h->fp;
-    chan_begin(h, p.ch[0], d_chunk, nchunk, units, par, (uint32_t)(h->call_no + 1));
+    p.prof = h->d_prof;
+    chan_begin(h, p.ch[0], d_chunk, nchunk, units, par);
     const uint32_t tiles = rx_tiles_of(units);
     p.tile_cum[0] = 0; p.tile_cum[1] = tiles;
-    uint32_t grid = (uint32_t)rx_front_ctas_per_sm(h->sc16) * (uint32_t)h->sm_count;
-    if (h->grid_cap > 0 && grid > (uint32_t)h->grid_cap) grid = (uint32_t)h->grid_cap;
-    if (grid > (uint32_t)kMaxGrid) grid = kMaxGrid;
-    if (grid > tiles) grid = tiles;
+    uint32_t resident = (uint32_t)rx_front_ctas_per_sm(h->sc16) * (uint32_t)h->sm_count;
+    if (h->grid_cap > 0 && resident > (uint32_t)h->grid_cap) resident = (uint32_t)h->grid_cap;
+    const uint32_t grid = rx_make_deal(p.deal, tiles, resident);
     const bool timed = (h->flags & AMPS_RX_TIME_KERNELS) != 0;
     const int  evi = (int)(h->ev_count % amps_recc_iq::kEv);
     if (timed) CK(cudaEventRecord(h->ev0[evi], st));
-    CKL(launch_rx_front(p, (int)grid, st, h->sc16, h->sc16_unit));
+    CKL(launch_rx_front(p, (int)grid, st, h->sc16, h->sc16_unit, h->fused && !h->mm_mode && !h->nosearch));
     if (timed) { CK(cudaEventRecord(h->ev1[evi], st)); h->ev_count++; }
     h->launches++;
     // capture (and the M&M tail) on the side stream, so that the next call's front kernel (HBM-bound, 2 CTAs/SM) overlaps
@@ -376,6 +394,14 @@ static int rx_enqueue10(amps_recc_iq *h, const uint8_t *d_chunk, uint32_t nchunk
             uint64_t mx = (uint64_t)units * kUnitOut / (8u * (unsigned)kMmQuantum) + 2;      // <= one blob per work() quantum
             nc = (uint32_t)(mx > (uint64_t)kMaxAccept ? (uint64_t)kMaxAccept : mx);
             h->launches += 2;
+        }
+        if (!h->mm_mode && !h->fused && !h->nosearch) {
+            // trigger search + selection as their own launch, overlapped (like the capture) with the next call's front kernel
+            RxSearchParams sp;
+            sp.nchan = 1;
+            const uint32_t ns = chan_search(h, sp.ch[0], par, 0);
+            CKL(launch_rx_search(sp, (int)ns, sd));
+            h->launches++;
         }
         chan_capture(h, cp.ch[0], par, 0, nc);
         CKL(launch_rx_capture(cp, (int)nc, sd));
@@ -432,10 +458,10 @@ static int rx_enqueue400(amps_recc_iq *h, const uint8_t *d_chunk, uint32_t npass
             h->launches += 2;
         } else {
             // search every group whose lookahead is complete, then select (one launch)
-            const uint64_t g_hi = h->total_d / kUnitOut >= (uint64_t)kGroupLag ? h->total_d / kUnitOut - kGroupLag : 0;
-            CKL(launch_rx_search(h->d_dring, h->d_hring, h->dmask, h->d_state, h->d_cand, h->d_acc, h->h_pub, h->groups_done,
-                                 g_hi > h->groups_done ? g_hi : h->groups_done, h->total_d, par, sd));
-            if (g_hi > h->groups_done) h->groups_done = g_hi;
+            RxSearchParams sp;
+            sp.nchan = 1;
+            const uint32_t ns = chan_search(h, sp.ch[0], par, 0);
+            CKL(launch_rx_search(sp, (int)ns, sd));
             h->launches++;
         }
         chan_capture(h, cp.ch[0], par, 0, nc);
@@ -645,6 +671,15 @@ extern "C" int amps_recc_iq_front_times(amps_recc_iq *h, float *ms_out, int cap,
     return event_times(h->ev0, h->ev1, h->ev_count, amps_recc_iq::kEv, ms_out, cap, n_out);
 }
 
+extern "C" int amps_recc_iq_debug_prof(amps_recc_iq *h, unsigned long long *out, int ctas) {
+    if (!h || !out || ctas < 0 || ctas > kMaxGrid) return set_error(AMPS_E_INVAL, "bad argument");
+    if (!h->d_prof) return set_error(AMPS_E_STATE, "create the handle with AMPS_RX_PROF=1 in the environment");
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out, h->d_prof, sizeof(unsigned long long) * 16 * (size_t)ctas, cudaMemcpyDeviceToHost));
+    return AMPS_OK;
+}
+
 extern "C" int amps_recc_iq_get_taps(const amps_recc_iq *h, float *lpf_out, int cap) {
     if (!h) return set_error(AMPS_E_INVAL, "null handle");
     const int n = (int)h->lpf.size();
@@ -664,8 +699,8 @@ extern "C" int amps_recc_iq_batch_create(amps_recc_iq *const *handles, int count
         if (!h) return set_error(AMPS_E_INVAL, "null handle in the batch");
         if (h->batch) return set_error(AMPS_E_STATE, "a handle already belongs to a batch");
         if (h->native400 || h->mm_mode) return set_error(AMPS_E_INVAL, "batches take 10 MS/s feed-forward handles only");
-        if (h->device != h0->device || h->sc16 != h0->sc16 || h->sc16_unit != h0->sc16_unit)
-            return set_error(AMPS_E_INVAL, "all handles of a batch must share the device and the input format");
+        if (h->device != h0->device || h->sc16 != h0->sc16 || h->sc16_unit != h0->sc16_unit || h->fused != h0->fused)
+            return set_error(AMPS_E_INVAL, "all handles of a batch must share the device, the input format and AMPS_RX_FUSED_SEARCH");
         if (h->call_no || h->carry || h->dev_carry) return set_error(AMPS_E_STATE, "handles must be fresh (or reset) when they join a batch");
         for (int j = 0; j < i; ++j) if (handles[j] == h) return set_error(AMPS_E_INVAL, "the same handle twice in a batch");
     }
@@ -707,7 +742,6 @@ extern "C" int amps_recc_iq_batch_size(const amps_recc_iq_batch *b) { return b ?
 // one call: channel i gets nsamples[i] new samples at d_iq[i] (device pointers; several channels may share one buffer)
 static int batch_enqueue(amps_recc_iq_batch *b, const void *const *d_iq, const size_t *nsamples, cudaStream_t st) {
     const uint32_t par = (uint32_t)(b->call_no & 1u);
-    const uint32_t epoch = (uint32_t)(b->call_no + 1);
     b->last_stream = st;
     if (b->call_no >= 2) CK(cudaStreamWaitEvent(st, b->ev_side[par], 0));
     const uint32_t resident = (uint32_t)rx_front_ctas_per_sm(b->sc16) * (uint32_t)b->sm_count;
@@ -719,42 +753,51 @@ static int batch_enqueue(amps_recc_iq_batch *b, const void *const *d_iq, const s
     const size_t K = b->ch.size();
     std::vector<RxCaptureParams> caps;
     std::vector<uint32_t> cap_grid;
+    std::vector<RxSearchParams> srch;
+    std::vector<uint32_t> srch_grid;
+    const bool split = !b->ch[0]->fused && !b->ch[0]->nosearch;
     while (i < K) {
         // next group of up to kMaxBatch channels that have at least one whole unit
         const amps_recc_iq *h0 = b->ch[0];
         std::memcpy(p.g, h0->fp.g, sizeof p.g);
         std::memcpy(p.h2, h0->fp.h2, sizeof p.h2);
-        p.defer_all = h0->fp.defer_all;
-        uint32_t n = 0, tiles = 0, cap_ctas = 0;
+        p.prof = nullptr;
+        uint32_t n = 0, tiles = 0, cap_ctas = 0, srch_ctas = 0;
         RxCaptureParams cp;
+        RxSearchParams sp;
         p.tile_cum[0] = 0;
         for (; i < K && n < (uint32_t)kMaxBatch; ++i) {
             amps_recc_iq *h = b->ch[i];
             const uint32_t nchunk = (uint32_t)nsamples[i];
             const uint32_t units = (h->dev_carry + nchunk) / (uint32_t)kUnit;
             if (units == 0) { int rc = chan_append_carry(h, static_cast<const uint8_t *>(d_iq[i]), nchunk, st); if (rc != AMPS_OK) return rc; continue; }
-            chan_begin(h, p.ch[n], static_cast<const uint8_t *>(d_iq[i]), nchunk, units, par, epoch);
+            chan_begin(h, p.ch[n], static_cast<const uint8_t *>(d_iq[i]), nchunk, units, par);
             tiles += rx_tiles_of(units);
             p.tile_cum[n + 1] = tiles;
             const uint32_t nc = capture_ctas((uint64_t)units * kUnitOut);
             chan_capture(h, cp.ch[n], par, cap_ctas, nc);
             cap_ctas += nc;
+            if (split) srch_ctas += chan_search(h, sp.ch[n], par, srch_ctas);
             ++n;
         }
         if (n == 0) continue;
         p.nchan = n;
         cp.nchan = n;
-        uint32_t grid = resident > (uint32_t)kMaxGrid ? (uint32_t)kMaxGrid : resident;
-        if (grid > tiles) grid = tiles;
-        CKL(launch_rx_front_batch(p, (int)grid, st, b->sc16, b->sc16_unit));
+        const uint32_t grid = rx_make_deal(p.deal, tiles, resident);
+        CKL(launch_rx_front_batch(p, (int)grid, st, b->sc16, b->sc16_unit, !split));
         b->launches++;
         caps.push_back(cp);
         cap_grid.push_back(cap_ctas);
+        if (split) { sp.nchan = n; srch.push_back(sp); srch_grid.push_back(srch_ctas); }
     }
     if (b->timed) { CK(cudaEventRecord(b->ev1[evi], st)); b->ev_count++; }
     CK(cudaEventRecord(b->ev_front, st));
     CK(cudaStreamWaitEvent(sd, b->ev_front, 0));
-    for (size_t k = 0; k < caps.size(); ++k) { CKL(launch_rx_capture(caps[k], (int)cap_grid[k], sd)); b->launches++; }
+    for (size_t k = 0; k < caps.size(); ++k) {
+        if (split) { CKL(launch_rx_search(srch[k], (int)srch_grid[k], sd)); b->launches++; }
+        CKL(launch_rx_capture(caps[k], (int)cap_grid[k], sd));
+        b->launches++;
+    }
     CK(cudaEventRecord(b->ev_side[par], sd));
     b->call_no++;
     return AMPS_OK;

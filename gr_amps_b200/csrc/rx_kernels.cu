@@ -22,14 +22,13 @@ namespace amps {
 
 static_assert(sizeof(amps_burst) % 8 == 0, "burst records are streamed to the host ring in 8-byte words");
 
-__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
-    uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long v;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(v));
     return v;
 }
-__device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v) {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
+// measurement aid: time stamp `idx` of this CTA (thread 0 only)
+#define RX_PROF(p, idx) do { if ((p).prof && threadIdx.x == 0) (p).prof[blockIdx.x * 16 + (idx)] = global_ns(); } while (0)
 
 // ============================================================================================
 // trigger search (device routines shared by rx_front_kernel and rx_search_kernel)
@@ -54,7 +53,10 @@ __device__ __forceinline__ uint32_t hard_window(const uint32_t *__restrict__ hri
 // Exact 74/74 hard match for the 32 adjacent sampling positions i0 .. i0+31 (i0 a multiple of 32):
 // for half-symbol k the 32 hard decisions at positions i0+10k .. i0+10k+31 are one 32-bit window of
 // the bit ring, so one AND per symbol tests all 32 positions; a random group dies after ~6 symbols.
-// The first 8 windows are fetched together (one round trip to L2 decides 7 groups out of 8).
+// The first 8 windows are fetched together (one round trip to L2 decides 7 groups out of 8), the others 22 at a time.
+__device__ __forceinline__ uint32_t trig_and(uint32_t m, int k, uint32_t win) {
+    return m & (((c_trig_bits[k >> 5] >> (k & 31)) & 1u) ? win : ~win);
+}
 __device__ __forceinline__ uint32_t group_match(const uint32_t *__restrict__ hring, uint32_t wmask, unsigned long long i0) {
     uint32_t win[8];
 #pragma unroll
@@ -63,58 +65,131 @@ __device__ __forceinline__ uint32_t group_match(const uint32_t *__restrict__ hri
 #pragma unroll
     for (int k = 0; k < 8; ++k) m &= ((0x66u >> k) & 1u) ? win[k] : ~win[k];      // c_trig_bits[0] & 0xff
 #pragma unroll 1
-    for (int k = 8; k < kTrig && m; ++k) {
-        const uint32_t w = hard_window(hring, wmask, i0 + (unsigned long long)(kOS * k));
-        m &= ((c_trig_bits[k >> 5] >> (k & 31)) & 1u) ? w : ~w;
+    for (int k0 = 8; k0 < kTrig && m; k0 += 22) {         // 8 + 3 x 22 = 74
+        uint32_t w[22];
+#pragma unroll
+        for (int j = 0; j < 22; ++j) w[j] = hard_window(hring, wmask, i0 + (unsigned long long)(kOS * (k0 + j)));
+#pragma unroll
+        for (int j = 0; j < 22; ++j) m = trig_and(m, k0 + j, w[j]);
     }
     return m;
 }
 
-// soft correlation of the trigger at sampling position i: sum_k (+/-) d[i + 10k], k ascending
-__device__ __forceinline__ float trig_corr(const float *__restrict__ dring, uint32_t dmask, unsigned long long i) {
-    float v[kTrig];
-#pragma unroll
-    for (int k = 0; k < kTrig; ++k) v[k] = __ldcg(&dring[(i + (unsigned long long)(kOS * k)) & dmask]);
-    float c = 0.0f;
-#pragma unroll
-    for (int k = 0; k < kTrig; ++k) c = __fadd_rn(c, c_trig[k] ? v[k] : -v[k]);
-    return c;
+// The same test on the CTA's own recent decisions, kept in a shared-memory ring of kHwRing words (word index = absolute
+// demod index / 32): what rx_front_kernel runs after every pass, so that in a long segment the search costs nothing.
+constexpr int kHwRing = 128;
+__device__ __forceinline__ uint32_t group_match_smem(const uint32_t *hw, unsigned long long i0) {
+    uint32_t m = 0xffffffffu;
+#pragma unroll 1
+    for (int k = 0; k < kTrig && m; ++k) {
+        const unsigned long long b = i0 + (unsigned long long)(kOS * k);
+        const uint32_t wi = (uint32_t)(b >> 5);
+        m = trig_and(m, k, __funnelshift_r(hw[wi & (kHwRing - 1)], hw[(wi + 1) & (kHwRing - 1)], (uint32_t)b & 31u));
+    }
+    return m;
 }
 
-// One thread per group of 32 sampling positions.  The thread owning the FIRST position of a run of matches (at most 10
-// long: the pattern cannot match one half-symbol later) appends one candidate for the whole run: its soft-correlation
-// peak (first maximum) is the sampling phase.  Reads the stream up to i0 + 793; every group is searched exactly once.
-__device__ void detect_group(const float *__restrict__ dring, const uint32_t *__restrict__ hring, uint32_t dmask, RxState *state,
-                             Candidate *cand, unsigned long long i0) {
+// Shared-memory scratch of the search (one per CTA).
+constexpr int kSearchSpan = 32 + 10 + kOS * (kTrig - 1);      // demod samples a group's correlations can touch: 772
+constexpr int kLocalCand = 16;
+struct SearchScratch {
+    float     d[kSearchSpan + 4];
+    float     corr[48];
+    uint32_t  m0s[256];
+    uint32_t  wb[8];
+    uint32_t  mprev, mnext;
+    uint32_t  nlc;                        // candidates found by this CTA and not yet appended to the channel's list
+    uint32_t  pad;
+    Candidate lc[kLocalCand];
+};
+
+// append the CTA's local candidates to the channel's list (thread 0; one atomic for all of them)
+__device__ __forceinline__ void flush_candidates(RxState *state, Candidate *cand, SearchScratch *sc) {
+    const uint32_t n = sc->nlc;
+    if (n == 0u) return;
+    const unsigned int slot = atomicAdd(&state->ncand, n);
+    for (uint32_t i = 0; i < n; ++i) {
+        if (slot + i < (unsigned)kMaxCand) cand[slot + i] = sc->lc[i];
+        else atomicAdd(&state->cand_overflow, 1u);
+    }
+    sc->nlc = 0u;
+}
+
+// One group with at least one match (rare: about one per burst), all threads of the CTA: the neighbours' masks delimit
+// the runs, the demod samples under the group are staged once, one thread per sampling position sums its soft correlation
+// (sum_k +/- d[i + 10k], k ascending), and the first position of every run yields one candidate for the whole run: its
+// soft-correlation peak (first maximum) is the sampling phase (a run is at most 10 long: the pattern cannot match one
+// half-symbol later).  Reads the stream up to i0 + 793.  hw != nullptr: the neighbours are in the CTA's own decision ring.
+__device__ __noinline__ void resolve_group(const float *__restrict__ dring, const uint32_t *__restrict__ hring, uint32_t dmask, RxState *state,
+                                           Candidate *cand, unsigned long long i0, uint32_t m0, SearchScratch *sc, const uint32_t *hw) {
+    const int t = threadIdx.x, nt = blockDim.x;
     const uint32_t wmask = dmask >> 5;
-    const uint32_t m0 = group_match(hring, wmask, i0);
-    if (!m0) return;
-    // rare path: neighbours' match bits decide where runs start and end
-    const uint32_t mprev = i0 >= 32 ? group_match(hring, wmask, i0 - 32) : 0u;
-    const uint32_t mnext = group_match(hring, wmask, i0 + 32);
-    const unsigned long long M = (unsigned long long)m0 | ((unsigned long long)mnext << 32);
-    uint32_t starts = m0 & ~((m0 << 1) | (mprev >> 31));
-    while (starts) {
-        const int bit = __ffs(starts) - 1;
-        starts &= starts - 1;
-        const unsigned long long i = i0 + (unsigned long long)bit;
-        unsigned long long best = i;
-        float bestc = trig_corr(dring, dmask, i);
-        unsigned int run = 1;
-        while (run < 32u && ((M >> (bit + run)) & 1ull)) {
-            const float c = trig_corr(dring, dmask, i + run);
-            if (c > bestc) { bestc = c; best = i + run; }
-            ++run;
+    if (t == 0) sc->mprev = i0 >= 32 ? (hw ? group_match_smem(hw, i0 - 32) : group_match(hring, wmask, i0 - 32)) : 0u;
+    if (t == 32) sc->mnext = hw ? group_match_smem(hw, i0 + 32) : group_match(hring, wmask, i0 + 32);
+    for (int j = t; j < kSearchSpan; j += nt) sc->d[j] = __ldcg(&dring[(i0 + (unsigned long long)j) & dmask]);
+    __syncthreads();
+    const unsigned long long M = (unsigned long long)m0 | ((unsigned long long)sc->mnext << 32);
+    if (t < 42 && ((M >> t) & 1ull)) {
+        float c = 0.0f;
+#pragma unroll
+        for (int k = 0; k < kTrig; ++k) { const float v = sc->d[t + kOS * k]; c = __fadd_rn(c, c_trig[k] ? v : -v); }
+        sc->corr[t] = c;
+    }
+    __syncthreads();
+    if (t == 0) {
+        uint32_t starts = m0 & ~((m0 << 1) | (sc->mprev >> 31));
+        while (starts) {
+            const int bit = __ffs(starts) - 1;
+            starts &= starts - 1;
+            int best = bit;
+            float bestc = sc->corr[bit];
+            unsigned int run = 1;
+            while (run < 11u && ((M >> (bit + run)) & 1ull)) {
+                const float c = sc->corr[bit + run];
+                if (c > bestc) { bestc = c; best = bit + (int)run; }
+                ++run;
+            }
+            if (sc->nlc == (uint32_t)kLocalCand) flush_candidates(state, cand, sc);
+            Candidate &o = sc->lc[sc->nlc++];
+            o.start = i0 + (unsigned long long)bit;
+            o.best = i0 + (unsigned long long)best;
+            o.corr = bestc;
+            o.run = run;
         }
-        const unsigned int slot = atomicAdd(&state->ncand, 1u);
-        if (slot < (unsigned)kMaxCand) {
-            cand[slot].start = i;
-            cand[slot].best = best;
-            cand[slot].corr = bestc;
-            cand[slot].run = run;
-        } else {
-            atomicAdd(&state->cand_overflow, 1u);
+    }
+    __syncthreads();
+}
+
+// Second half of a search round, all threads of the CTA: thread t found the match mask m0 (mostly 0) for group base + t;
+// the CTA resolves the groups that matched.
+__device__ __noinline__ void resolve_round(const float *__restrict__ dring, const uint32_t *__restrict__ hring, uint32_t dmask, RxState *state,
+                                           Candidate *cand, unsigned long long base, uint32_t m0, SearchScratch *sc, const uint32_t *hw) {
+    const int t = threadIdx.x, nt = blockDim.x;
+    sc->m0s[t] = m0;
+    const uint32_t bal = __ballot_sync(0xffffffffu, m0 != 0u);
+    if ((t & 31) == 0) sc->wb[t >> 5] = bal;
+    __syncthreads();
+    for (int w = 0; w < nt / 32; ++w) {
+        uint32_t bits = sc->wb[w];
+        while (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            resolve_group(dring, hring, dmask, state, cand, 32ull * (base + (unsigned long long)(32 * w + b)), sc->m0s[32 * w + b], sc, hw);
         }
+    }
+    __syncthreads();
+}
+
+// Groups [g_lo, g_hi) from the rings in global memory, all threads of the CTA (uniform arguments): one group per thread and
+// round for the hard match, then the CTA resolves the groups that matched (candidates go to the CTA's local list: the caller
+// flushes it).  Every group is searched exactly once over the life of a stream.
+__device__ __noinline__ void search_groups(const float *__restrict__ dring, const uint32_t *__restrict__ hring, uint32_t dmask, RxState *state,
+                              Candidate *cand, unsigned long long g_lo, unsigned long long g_hi, SearchScratch *sc) {
+    const int t = threadIdx.x, nt = blockDim.x;
+    for (unsigned long long base = g_lo; base < g_hi; base += (unsigned long long)nt) {
+        const unsigned long long g = base + (unsigned long long)t;
+        const uint32_t m0 = g < g_hi ? group_match(hring, dmask >> 5, 32ull * g) : 0u;
+        if (__syncthreads_or(m0 != 0u)) resolve_round(dring, hring, dmask, state, cand, base, m0, sc, nullptr);
     }
 }
 
@@ -123,17 +198,34 @@ __device__ void detect_group(const float *__restrict__ dring, const uint32_t *__
 // ring) -- the first undecided run and everything after it stay on the list for a later call; a decided run that starts
 // inside an already captured burst is dropped; the others are accepted and the search resumes (74+3374)*10 positions after
 // the sampling position (oracle/dsp_chain.c orc_rx_detect).  The outcome does not depend on how the stream was cut into calls.
-__device__ void select_channel(RxState *state, Candidate *cand, Candidate *sorted, Accepted *acc, uint32_t par,
-                               unsigned long long total_d, RxPublished *host_pub) {
+__device__ __noinline__ void select_channel(RxState *state, Candidate *cand, Candidate *sorted, Accepted *acc, uint32_t par,
+                                            unsigned long long total_d, RxPublished *host_pub, Candidate *scratch, unsigned int scratch_cap) {
     const int t = threadIdx.x, nt = blockDim.x;
     unsigned int n = __ldcg(&state->ncand);
     if (n > (unsigned)kMaxCand) n = kMaxCand;
-    for (unsigned int i = t; i < n; i += nt) {
-        Candidate c;
-        c.start = __ldcg(&cand[i].start); c.best = __ldcg(&cand[i].best); c.corr = __ldcg(&cand[i].corr); c.run = __ldcg(&cand[i].run);
-        unsigned int rank = 0;
-        for (unsigned int j = 0; j < n; ++j) rank += __ldcg(&cand[j].start) < c.start ? 1u : 0u;
-        sorted[rank] = c;
+    if (2u * n <= scratch_cap) {
+        // the usual case: the whole list fits in shared memory (unsorted copy | sorted copy)
+        for (unsigned int i = t; i < n; i += nt) {
+            Candidate c;
+            c.start = __ldcg(&cand[i].start); c.best = __ldcg(&cand[i].best); c.corr = __ldcg(&cand[i].corr); c.run = __ldcg(&cand[i].run);
+            scratch[i] = c;
+        }
+        __syncthreads();
+        for (unsigned int i = t; i < n; i += nt) {
+            const Candidate c = scratch[i];
+            unsigned int rank = 0;
+            for (unsigned int j = 0; j < n; ++j) rank += scratch[j].start < c.start ? 1u : 0u;
+            scratch[n + rank] = c;
+        }
+        sorted = scratch + n;
+    } else {
+        for (unsigned int i = t; i < n; i += nt) {
+            Candidate c;
+            c.start = __ldcg(&cand[i].start); c.best = __ldcg(&cand[i].best); c.corr = __ldcg(&cand[i].corr); c.run = __ldcg(&cand[i].run);
+            unsigned int rank = 0;
+            for (unsigned int j = 0; j < n; ++j) rank += __ldcg(&cand[j].start) < c.start ? 1u : 0u;
+            sorted[rank] = c;
+        }
     }
     __syncthreads();
     if (t == 0) {
@@ -361,6 +453,7 @@ struct PassOut {                          // where a pass's outputs go
     float    *dring;
     uint32_t *hring;
     float2   *ydump;
+    uint32_t *hw;                         // shared-memory ring of the newest decisions (kHwRing words) or nullptr
     uint32_t  dmask;
 };
 // input sample formats: fc32 (gr_complex, what the reference's flowgraph carries) and sc16 (interleaved int16 I/Q, what
@@ -373,6 +466,7 @@ template <bool kUnitScale> __device__ __forceinline__ float2 to_c32(short2 v, fl
     return make_float2(__fmul_rn((float)v.x, s), __fmul_rn((float)v.y, s));
 }
 
+constexpr int kMaxBound = 16;           // a CTA's output is read by at most ceil(26 / 3) + 1 = 10 boundaries
 template <typename In>
 struct FrontSmem {
     In       in[kStages][kTile];          // TMA landing ring
@@ -380,8 +474,13 @@ struct FrontSmem {
     float2   pb[3][2][kTB];               // [tile % 3][P1|P2][block] rotated CIC partial sums (3 buffers: a tile reads its
                                           // own and the previous tile's, the next tile may already be writing)
     uint64_t full[kStages];
-    uint32_t flag_ok;                     // search: the CTAs in front of this segment have published their outputs
+    uint32_t hw[kHwRing];                 // the segment's newest hard decisions (trigger search without a trip to L2)
     uint32_t is_last;                     // this CTA is the last one of the channel to finish
+    uint32_t nb;                          // boundaries this CTA contributes to: whose (CTA index), the counter value that
+    uint32_t bj[kMaxBound];               // means "everybody else has been here", and whether this CTA was the last to arrive
+    uint32_t bneed[kMaxBound];
+    uint32_t bmine[kMaxBound];
+    SearchScratch sc;
 };
 
 size_t rx_front_smem_bytes() { return sizeof(FrontSmem<float2>); }
@@ -409,6 +508,21 @@ __device__ __forceinline__ void channel_filter(const float (&h2)[300], const flo
     }
 #pragma unroll
     for (int r = 0; r < kR; ++r) y[r] = add2(E[r], O[r]);
+}
+
+// the last of those kR outputs alone (q = kR*c0 + kR-1), same two chains in the same order: what a segment's warm-up needs
+__device__ __forceinline__ float2 channel_filter_last(const float (&h2)[300], const float4 *vcol) {
+    float2 E = make_float2(0.f, 0.f), O = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j <= 149; ++j) {
+        const int s = j;                               // r = kR-1: j = r - (kR-1) + s
+        const int row = (kR - 1 - s) & (kR - 1);
+        const int cs  = floor_div(kR - 1 - s, kR);
+        const float4 pr = vcol[row * kRowLen + cs];
+        E = fma2(splat(h2[2 * j]), make_float2(pr.x, pr.y), E);
+        if (j >= 1) O = fma2(splat(h2[2 * j - 1]), make_float2(pr.z, pr.w), O);
+    }
+    return add2(E, O);
 }
 
 // store one 400 kS/s sample (index relative to the start of the current pass, negative = history) into the pair/row layout
@@ -463,7 +577,10 @@ __device__ __forceinline__ void finish_pass(const float (&h2)[300], const PassOu
         hb |= __shfl_xor_sync(0xffffffffu, hb, 1);
         hb |= __shfl_xor_sync(0xffffffffu, hb, 2);
         hb |= __shfl_xor_sync(0xffffffffu, hb, 4);
-        if (act && (t & 7) == 0) o.hring[(qabs & o.dmask) >> 5] = hb;
+        if (act && (t & 7) == 0) {
+            o.hring[(qabs & o.dmask) >> 5] = hb;
+            if (o.hw) o.hw[(uint32_t)(qabs >> 5) & (kHwRing - 1)] = hb;
+        }
         if (o.ydump && act) {
             const unsigned long long ql = ql_pass + (unsigned long long)kR * t;
 #pragma unroll
@@ -472,10 +589,12 @@ __device__ __forceinline__ void finish_pass(const float (&h2)[300], const PassOu
     }
 }
 
-// ---- how a launch's tiles are dealt: CTA i of `grid` owns global tiles [Tt*i/grid, Tt*(i+1)/grid)
-__device__ __forceinline__ uint32_t cta_tile_lo(uint32_t Tt, uint32_t grid, uint32_t i) { return (uint32_t)((unsigned long long)Tt * i / grid); }
-__device__ __forceinline__ uint32_t tile_owner(uint32_t Tt, uint32_t grid, uint32_t tile) {
-    return (uint32_t)((((unsigned long long)tile + 1ull) * grid - 1ull) / Tt);
+// ---- how a launch's tiles are dealt: the Tt tiles are split evenly, CTA s owns tiles [Tt*s/grid, Tt*(s+1)/grid) -- its
+// SEGMENTS (one per channel the range touches).  (A pool of late segments for CTAs that finish early was tried on the
+// 2^28-sample batch: the spread between CTAs is not removed by it and the extra warm-up tiles cost 2 %.)
+__device__ __forceinline__ uint32_t deal_lo(const RxDeal &d, uint32_t s) { return (uint32_t)((unsigned long long)d.Tt * s / d.nstat); }
+__device__ __forceinline__ uint32_t deal_owner(const RxDeal &d, uint32_t tile) {
+    return (uint32_t)((((unsigned long long)tile + 1ull) * d.nstat - 1ull) / d.Tt);
 }
 
 // samples [L0, L0 + n) of a channel's logical stream -> shared memory; logical samples below `carry` live in the tail
@@ -495,12 +614,6 @@ __device__ __forceinline__ void issue_tile(const RxChan &ch, In *dst, uint64_t *
     }
 }
 
-// groups [g_lo, g_hi) of one channel, one thread each
-__device__ __forceinline__ void search_groups(const RxChan &ch, unsigned long long g_lo, unsigned long long g_hi, int t) {
-    for (unsigned long long g = g_lo + (unsigned long long)t; g < g_hi; g += kTB)
-        detect_group(ch.dring, ch.hring, ch.dmask, ch.state, ch.cand, 32ull * g);
-}
-
 // the groups a segment [qs, qe) of demod samples has to search, and the first one that needs no other CTA's output
 struct SegGroups { unsigned long long lo, mid, hi; };
 __device__ __forceinline__ SegGroups seg_groups(unsigned long long qs, unsigned long long qe, bool first_of_call) {
@@ -518,7 +631,7 @@ __device__ __forceinline__ SegGroups seg_groups(unsigned long long qs, unsigned 
 
 // One segment = tiles [ta, tb) of channel c (tile j = units 3j .. 3j+2, the channel's last tile may be shorter), preceded by
 // kWarmTiles tiles of history.  `it` counts the tiles this CTA has consumed (TMA ring position / mbarrier phase).
-template <typename In, bool kUnitScale, int kMaxChan>
+template <typename In, bool kUnitScale, int kMaxChan, bool kFused>
 __device__ __forceinline__ void run_segment(const RxFrontParamsT<kMaxChan> &p, const RxChan &ch, FrontSmem<In> *sm,
                                             uint32_t ta, uint32_t tb, uint32_t &it, int t) {
     const int  ntiles = (int)(tb - ta) + kWarmTiles;
@@ -531,9 +644,11 @@ __device__ __forceinline__ void run_segment(const RxFrontParamsT<kMaxChan> &p, c
         return left < (uint32_t)kTB ? left : (uint32_t)kTB;
     };
     PassOut o;
-    o.dring = ch.dring; o.hring = ch.hring; o.ydump = ch.ydump; o.dmask = ch.dmask;
+    o.dring = ch.dring; o.hring = ch.hring; o.ydump = ch.ydump; o.dmask = ch.dmask; o.hw = (kFused && ch.search) ? sm->hw : nullptr;
     const uint32_t useg = ((uint32_t)kTileUnits * tb < U ? (uint32_t)kTileUnits * tb : U) - (uint32_t)kTileUnits * ta;   // units of the segment
     const unsigned long long ql0 = (unsigned long long)kUnitOut * kTileUnits * ta;     // first output, relative to the call
+    // first group that reads nothing in front of the segment (the groups below it are searched in finish_segment)
+    unsigned long long g_next = (ch.q_base + ql0) / kUnitOut + 1ull;
 
     // partial sums "before the first tile": they only reach samples the warm-up never uses
     sm->pb[2][0][t] = make_float2(0.f, 0.f);
@@ -547,6 +662,8 @@ __device__ __forceinline__ void run_segment(const RxFrontParamsT<kMaxChan> &p, c
     for (int i = 0; i < ntiles; ++i, ++it) {
         const int s = (int)(it % kStages);
         mbar_wait(&sm->full[s], (it / kStages) & 1u);
+        if (i == 0) RX_PROF(p, 1);
+        if (i == kWarmTiles) RX_PROF(p, 2);
 
         // ---- stage 1: NCO rotate + CIC^3 polyphase partial sums over this thread's 25 samples
         const In *xin = sm->in[s] + kD1 * t;
@@ -593,125 +710,181 @@ __device__ __forceinline__ void run_segment(const RxFrontParamsT<kMaxChan> &p, c
             }
             const unsigned long long ql = ql0 + (unsigned long long)(pc < 0 ? 0 : pc) * kPassOut;
             finish_pass(p.h2, o, &sm->ps, warm, pc, ch.q_base + ql, ql, nact, t);
+            if (kFused && !warm && ch.search) {
+                // ---- trigger search on the segment's own output: the groups whose lookahead this pass completed
+                const unsigned long long q_done = ch.q_base + ql + (unsigned long long)(kR * nact);
+                const unsigned long long g_end = q_done / kUnitOut >= (unsigned)kGroupLag ? q_done / kUnitOut - kGroupLag : 0ull;
+                if (g_end > g_next) {                      // (at most 24 groups: one pass)
+                    __syncthreads();                       // the pass's decisions are in the ring (and its demod samples in L2)
+                    const unsigned long long g = g_next + (unsigned long long)t;
+                    const uint32_t m0 = g < g_end ? group_match_smem(sm->hw, 32ull * g) : 0u;
+                    if (__syncthreads_or(m0 != 0u)) resolve_round(ch.dring, ch.hring, ch.dmask, ch.state, ch.cand, g_next, m0, &sm->sc, sm->hw);
+                    g_next = g_end;
+                }
+            }
         }
     }
 }
 
-// After a segment: search the groups whose lookahead ends inside it, publish "my outputs are written", and if this CTA is
-// the last of the channel to get here, finish the channel (deferred groups, candidate selection).
-//   Groups near the front of the segment look at demod samples other CTAs of this launch produce.  Those CTAs have lower
-// indices, were dispatched earlier and do the same amount of work, so their flags are normally up already; the wait is
-// bounded all the same: when it runs out the boundary groups are left to the channel's last CTA, which by construction
-// runs after everybody's outputs are in place.  No CTA ever waits without bound on another.
-template <typename In, int kMaxChan>
+// Segment k's part of a channel that owns global tiles [cbase, cend): tiles [lo, hi) relative to the channel
+struct SegTiles { uint32_t lo, hi; };
+__device__ __forceinline__ SegTiles seg_tiles(const RxDeal &d, uint32_t k, uint32_t cbase, uint32_t cend) {
+    uint32_t lo = deal_lo(d, k), hi = deal_lo(d, k + 1);
+    if (lo < cbase) lo = cbase;
+    if (hi > cend) hi = cend;
+    SegTiles s;
+    s.lo = lo - cbase;
+    s.hi = hi > lo ? hi - cbase : s.lo;
+    return s;
+}
+// first segment whose output the boundary groups of a segment starting at channel tile ta (> 0) read: they look back
+// kGroupLag + 1 units from the segment's first output
+__device__ __forceinline__ uint32_t boundary_first(const RxDeal &d, uint32_t cbase, uint32_t ta) {
+    const uint32_t u0 = (uint32_t)kTileUnits * ta;
+    const uint32_t ulo = u0 > (uint32_t)(kGroupLag + 1) ? u0 - (uint32_t)(kGroupLag + 1) : 0u;
+    return deal_owner(d, cbase + ulo / (uint32_t)kTileUnits);
+}
+
+// After a segment: search the groups whose lookahead ends inside it, and if this CTA is the last of the channel to get
+// here, select the bursts.
+//   Groups near the front of a segment (its BOUNDARY groups) look at demod samples that other CTAs of this launch produce:
+// the segments from boundary_first() up to the segment itself.  Nobody waits for anybody: whoever finishes one of those
+// segments bumps the boundary's counter once its outputs are globally visible, and whoever arrives last searches the boundary
+// -- by then everything it reads is in place.  The counters reset themselves; the order in which segments run is irrelevant.
+template <typename In, int kMaxChan, bool kFused>
 __device__ __forceinline__ void finish_segment(const RxFrontParamsT<kMaxChan> &p, const RxChan &ch, FrontSmem<In> *sm, uint32_t c,
-                                               uint32_t ta, uint32_t tb, uint32_t Tt, int t) {
-    const uint32_t grid = gridDim.x, cta = blockIdx.x;
+                                               uint32_t seg, uint32_t ta, uint32_t tb, int t) {
+    const RxDeal &dl = p.deal;
     const uint32_t cbase = p.tile_cum[c], cend = p.tile_cum[c + 1];
     const uint32_t U = ch.units;
     const unsigned long long qs = ch.q_base + (unsigned long long)kUnitOut * kTileUnits * ta;
     const unsigned long long qe = ch.q_base + (unsigned long long)kUnitOut * ((uint32_t)kTileUnits * tb < U ? (uint32_t)kTileUnits * tb : U);
     const unsigned long long total_d = ch.q_base + (unsigned long long)kUnitOut * U;
+    if constexpr (!kFused) { RX_PROF(p, 3); RX_PROF(p, 7); return; }      // search and selection are a launch of their own
     RxState *state = ch.state;
+    const uint32_t k1 = deal_owner(dl, cend - 1);             // last segment of the channel
     __syncthreads();                                      // this CTA's demod samples and decisions are visible to all its threads
+    RX_PROF(p, 3);
     if (ch.search) {
-        SegGroups g = seg_groups(qs, qe, ta == 0);
-        if (g.mid > g.lo) {
-            if (t == 0) {
-                const unsigned long long need = 32ull * g.lo >= 32ull ? 32ull * g.lo - 32ull : 0ull;   // first sample the boundary groups read
-                const uint32_t tile_lo = need > ch.q_base ? (uint32_t)((need - ch.q_base) / (unsigned)(kUnitOut * kTileUnits)) : 0u;
-                bool ok = p.defer_all == 0;
-                for (uint32_t k = tile_owner(Tt, grid, cbase + tile_lo); ok && k < cta; ++k) {
-                    int spins = 0;
-                    while (ld_acquire_u32(&ch.flags[k]) != ch.epoch) {
-                        if (++spins > 2000) { ok = false; break; }           // ~0.2 ms
-                        __nanosleep(100);
-                    }
-                }
-                if (!ok) atomicOr(&state->left_mask[cta >> 5], 1u << (cta & 31));
-                sm->flag_ok = ok ? 1u : 0u;
+        // ---- which boundaries does this CTA contribute to?  Its own (if it has one) and those of the CTAs right behind it.
+        if (t == 0) {
+            __threadfence();                              // my outputs before my counter bumps
+            uint32_t n = 0;
+            for (uint32_t j = seg; j <= k1 && n < (uint32_t)kMaxBound; ++j) {
+                const SegTiles sj = seg_tiles(dl, j, cbase, cend);
+                if (sj.lo == 0u) continue;                // the channel's first segment of the call: nothing in front of it in this launch
+                const uint32_t first = boundary_first(dl, cbase, sj.lo);
+                if (first > seg) break;                   // segment j (and everything behind it) does not read my output
+                sm->bj[n] = j;
+                sm->bneed[n] = j - first;                 // counter value the last arrival sees
+                ++n;
             }
-            __syncthreads();
-            if (!sm->flag_ok) g.lo = g.mid;
+            sm->nb = n;
         }
-        search_groups(ch, g.lo, g.hi, t);
+        __syncthreads();
+        const uint32_t nb = sm->nb;
+        if ((uint32_t)t < nb) {
+            const uint32_t j = sm->bj[t];
+            const uint32_t prev = atomicAdd(&ch.flags[j], 1u);
+            const bool mine = prev == sm->bneed[t];
+            if (mine) ch.flags[j] = 0u;                   // everybody has been here: ready for the next launch
+            sm->bmine[t] = mine ? 1u : 0u;
+        }
+        // (the groups that read only this segment's own output were searched pass by pass in run_segment)
+        RX_PROF(p, 4);
+        if (ta == 0) {
+            // ---- the channel's first segment of the call: its front groups read the previous calls' output, which is in place
+            const SegGroups g = seg_groups(qs, qe, false);
+            search_groups(ch.dring, ch.hring, ch.dmask, state, ch.cand, g.lo, g.mid, &sm->sc);
+        }
+        // ---- the boundaries this CTA was the last to reach
+        __syncthreads();
+        for (uint32_t i = 0; i < nb; ++i) {
+            if (!sm->bmine[i]) continue;
+            __threadfence();
+            const SegTiles sj = seg_tiles(dl, sm->bj[i], cbase, cend);
+            const unsigned long long js = ch.q_base + (unsigned long long)kUnitOut * kTileUnits * sj.lo;
+            const uint32_t ju = (uint32_t)kTileUnits * sj.hi;
+            const unsigned long long je = ch.q_base + (unsigned long long)kUnitOut * (ju < U ? ju : U);
+            const SegGroups gj = seg_groups(js, je, false);
+            search_groups(ch.dring, ch.hring, ch.dmask, state, ch.cand, gj.lo, gj.mid, &sm->sc);
+        }
     }
     __syncthreads();
+    RX_PROF(p, 5);
     if (t == 0) {
+        if (ch.search) flush_candidates(state, ch.cand, &sm->sc);
         __threadfence();
-        st_release_u32(&ch.flags[cta], ch.epoch);
-        const uint32_t n_touch = tile_owner(Tt, grid, cend - 1) - tile_owner(Tt, grid, cbase) + 1u;
+        const uint32_t n_touch = k1 - deal_owner(dl, cbase) + 1u;
         const unsigned int prev = atomicAdd(&state->front_done, 1u);
         sm->is_last = prev + 1u == n_touch ? 1u : 0u;
     }
     __syncthreads();
+    RX_PROF(p, 6);
     if (sm->is_last) {
         __threadfence();
-        if (ch.search) {
-            // boundary groups other CTAs gave up waiting for
-            const uint32_t k0 = tile_owner(Tt, grid, cbase), k1 = tile_owner(Tt, grid, cend - 1);
-            for (uint32_t k = k0; k <= k1; ++k) {
-                if (!((__ldcg(&state->left_mask[k >> 5]) >> (k & 31)) & 1u)) continue;
-                uint32_t lo = cta_tile_lo(Tt, grid, k), hi = cta_tile_lo(Tt, grid, k + 1);
-                if (lo < cbase) lo = cbase;
-                if (hi > cend) hi = cend;
-                const unsigned long long ks = ch.q_base + (unsigned long long)kUnitOut * kTileUnits * (lo - cbase);
-                const uint32_t ku = (uint32_t)kTileUnits * (hi - cbase);
-                const unsigned long long ke = ch.q_base + (unsigned long long)kUnitOut * (ku < U ? ku : U);
-                const SegGroups g = seg_groups(ks, ke, lo == cbase);
-                search_groups(ch, g.lo, g.mid, t);
-            }
-            __syncthreads();
-            for (uint32_t w = t; w < (uint32_t)(kMaxGrid / 32); w += kTB) state->left_mask[w] = 0u;
-            __threadfence();
-            __syncthreads();
-            select_channel(state, ch.cand, ch.cand + kMaxCand, ch.acc + (size_t)ch.par * kMaxAccept, ch.par, total_d, ch.host_pub);
-        }
+        if (ch.search)
+            select_channel(state, ch.cand, ch.cand + kMaxCand, ch.acc + (size_t)ch.par * kMaxAccept, ch.par, total_d, ch.host_pub,
+                           reinterpret_cast<Candidate *>(sm->in), (unsigned int)(sizeof(sm->in) / sizeof(Candidate)));
         if (t == 0) state->front_done = 0u;
+        RX_PROF(p, 8);
+    }
+    RX_PROF(p, 7);
+}
+
+// next call's tail = logical samples [units*kUnit - kHist, carry + nchunk): the CTAs that touch the channel copy a slice each
+// (saves a memcpy node between consecutive front kernels)
+template <typename In>
+__device__ __forceinline__ void copy_tail(const RxChan &ch, const RxDeal &d, uint32_t cta, uint32_t cbase, uint32_t cend, int t) {
+    const uint32_t k0 = deal_owner(d, cbase), nsl = deal_owner(d, cend - 1) - k0 + 1u;
+    const long first = (long)ch.units * kUnit - kHist;
+    const uint32_t len = (uint32_t)((long)ch.carry + (long)ch.nchunk - first);
+    const uint32_t per = (len + nsl - 1u) / nsl;
+    const uint32_t lo = (cta - k0) * per, hi = lo + per < len ? lo + per : len;
+    const In *tl = static_cast<const In *>(ch.tail) + (long)kHist;
+    const In *ck = static_cast<const In *>(ch.chunk) - (long)ch.carry;
+    In *dst = static_cast<In *>(ch.tail_out);
+    for (uint32_t i = lo + (uint32_t)t; i < hi; i += kTB) {
+        const long L = first + (long)i;
+        dst[i] = L < (long)ch.carry ? tl[L] : ck[L];
     }
 }
 
-template <typename In, int kMinCtas, bool kUnitScale, int kMaxChan>
+template <typename In, int kMinCtas, bool kUnitScale, int kMaxChan, bool kFused>
 __global__ void __launch_bounds__(kTB, kMinCtas) rx_front_kernel(const __grid_constant__ RxFrontParamsT<kMaxChan> p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     FrontSmem<In> *sm = reinterpret_cast<FrontSmem<In> *>(smem_raw);
     const int t = threadIdx.x;
-    const uint32_t grid = gridDim.x, cta = blockIdx.x;
-    const uint32_t Tt = p.tile_cum[kMaxChan == 1 ? 1 : p.nchan];
-    const uint32_t gt_lo = cta_tile_lo(Tt, grid, cta), gt_hi = cta_tile_lo(Tt, grid, cta + 1);
+    const uint32_t cta = blockIdx.x;                     // == its first (static) segment; gridDim.x == p.deal.nstat
+    const RxDeal &dl = p.deal;
 
+    RX_PROF(p, 0);
     if (t == 0) {
         for (int s = 0; s < kStages; ++s) mbar_init(&sm->full[s], 1);
         mbar_fence_init();
+        sm->sc.nlc = 0u;
     }
-    uint32_t it = 0, c = 0;
-    for (uint32_t g0 = gt_lo; g0 < gt_hi;) {
-        if constexpr (kMaxChan > 1) { while (p.tile_cum[c + 1] <= g0) ++c; }
-        const RxChan &ch = p.ch[kMaxChan == 1 ? 0 : c];
-        const uint32_t cbase = p.tile_cum[c], cend = p.tile_cum[c + 1];
-        const uint32_t g1 = gt_hi < cend ? gt_hi : cend;
-        const uint32_t ta = g0 - cbase, tb = g1 - cbase;
-
-        // next call's tail = logical samples [units*kUnit - kHist, carry + nchunk): the CTAs that touch the channel copy a slice
-        // each (saves a memcpy node between consecutive front kernels)
-        {
-            const uint32_t k0 = tile_owner(Tt, grid, cbase), nsl = tile_owner(Tt, grid, cend - 1) - k0 + 1u;
-            const long first = (long)ch.units * kUnit - kHist;
-            const uint32_t len = (uint32_t)((long)ch.carry + (long)ch.nchunk - first);
-            const uint32_t per = (len + nsl - 1u) / nsl;
-            const uint32_t lo = (cta - k0) * per, hi = lo + per < len ? lo + per : len;
-            const In *tl = static_cast<const In *>(ch.tail) + (long)kHist;
-            const In *ck = static_cast<const In *>(ch.chunk) - (long)ch.carry;
-            In *dst = static_cast<In *>(ch.tail_out);
-            for (uint32_t i = lo + (uint32_t)t; i < hi; i += kTB) {
-                const long L = first + (long)i;
-                dst[i] = L < (long)ch.carry ? tl[L] : ck[L];
-            }
+    uint32_t it = 0;
+    if constexpr (kMaxChan == 1) {
+        // one channel: everything about the channel is a compile-time offset into the parameters
+        const RxChan &ch = p.ch[0];
+        const uint32_t lo = deal_lo(dl, cta), hi = deal_lo(dl, cta + 1);
+        copy_tail<In>(ch, dl, cta, 0u, dl.Tt, t);
+        run_segment<In, kUnitScale, kMaxChan, kFused>(p, ch, sm, lo, hi, it, t);
+        finish_segment<In, kMaxChan, kFused>(p, ch, sm, 0u, cta, lo, hi, t);
+    } else {
+        const uint32_t gt_lo = deal_lo(dl, cta), gt_hi = deal_lo(dl, cta + 1);
+        uint32_t c = 0;
+        for (uint32_t g0 = gt_lo; g0 < gt_hi;) {
+            while (p.tile_cum[c + 1] <= g0) ++c;
+            const RxChan &ch = p.ch[c];
+            const uint32_t cbase = p.tile_cum[c], cend = p.tile_cum[c + 1];
+            const uint32_t g1 = gt_hi < cend ? gt_hi : cend;
+            copy_tail<In>(ch, dl, cta, cbase, cend, t);
+            run_segment<In, kUnitScale, kMaxChan, kFused>(p, ch, sm, g0 - cbase, g1 - cbase, it, t);
+            finish_segment<In, kMaxChan, kFused>(p, ch, sm, c, cta, g0 - cbase, g1 - cbase, t);
+            g0 = g1;
         }
-
-        run_segment<In, kUnitScale, kMaxChan>(p, ch, sm, ta, tb, it, t);
-        finish_segment<In, kMaxChan>(p, ch, sm, c, ta, tb, Tt, t);
-        g0 = g1;
     }
 }
 
@@ -730,7 +903,7 @@ __global__ void __launch_bounds__(kTB, 4) rx_front400_kernel(const __grid_consta
     uint32_t pb = pa + p.pass_per_cta;
     if (pb > p.npass) pb = p.npass;
     PassOut o;
-    o.dring = p.dring; o.hring = p.hring; o.ydump = p.ydump; o.dmask = p.dmask;
+    o.dring = p.dring; o.hring = p.hring; o.ydump = p.ydump; o.dmask = p.dmask; o.hw = nullptr;
     auto load = [&](long L) -> float2 {                   // logical sample L of this call; L < 0 = history
         const float2 x = to_c32<kUnitScale>(L < 0 ? static_cast<const In *>(p.tail)[(long)kPass400 + L] : static_cast<const In *>(p.chunk)[L], p.in_scale);
         const unsigned long long nabs = p.n_base + (unsigned long long)(long long)L;    // (x is 0 where this wraps: stream start)
@@ -763,53 +936,69 @@ cudaError_t launch_rx_front400(const RxFront400Params &p, int grid, cudaStream_t
 
 // sc16 tiles are half the size, so three CTAs fit an SM (the kernel is no longer HBM-bound at 4 B/sample)
 constexpr int kSc16Ctas = 3;
-cudaError_t launch_rx_front(const RxFrontParams1 &p, int grid, cudaStream_t st, bool sc16, bool unit) {
-    if (sc16 && unit) rx_front_kernel<short2, kSc16Ctas, true, 1><<<grid, kTB, sizeof(FrontSmem<short2>), st>>>(p);
-    else if (sc16) rx_front_kernel<short2, kSc16Ctas, false, 1><<<grid, kTB, sizeof(FrontSmem<short2>), st>>>(p);
-    else rx_front_kernel<float2, 2, false, 1><<<grid, kTB, sizeof(FrontSmem<float2>), st>>>(p);
+// fc32: two CTAs fit an SM (shared memory); the bound is 3 to hold the kernel to 112 registers, so that a CTA of the search /
+// capture kernels of the previous call finds room (registers as well as shared memory) next to them
+constexpr int kFc32Regs = 2;
+template <int kMaxChan, bool kFused, typename P>
+static cudaError_t launch_front_t(const P &p, int grid, cudaStream_t st, bool sc16, bool unit) {
+    if (sc16 && unit) rx_front_kernel<short2, kSc16Ctas, true, kMaxChan, kFused><<<grid, kTB, sizeof(FrontSmem<short2>), st>>>(p);
+    else if (sc16) rx_front_kernel<short2, kSc16Ctas, false, kMaxChan, kFused><<<grid, kTB, sizeof(FrontSmem<short2>), st>>>(p);
+    else rx_front_kernel<float2, kFc32Regs, false, kMaxChan, kFused><<<grid, kTB, sizeof(FrontSmem<float2>), st>>>(p);
     return cudaGetLastError();
 }
-cudaError_t launch_rx_front_batch(const RxFrontParamsB &p, int grid, cudaStream_t st, bool sc16, bool unit) {
-    if (sc16 && unit) rx_front_kernel<short2, kSc16Ctas, true, kMaxBatch><<<grid, kTB, sizeof(FrontSmem<short2>), st>>>(p);
-    else if (sc16) rx_front_kernel<short2, kSc16Ctas, false, kMaxBatch><<<grid, kTB, sizeof(FrontSmem<short2>), st>>>(p);
-    else rx_front_kernel<float2, 2, false, kMaxBatch><<<grid, kTB, sizeof(FrontSmem<float2>), st>>>(p);
-    return cudaGetLastError();
+cudaError_t launch_rx_front(const RxFrontParams1 &p, int grid, cudaStream_t st, bool sc16, bool unit, bool fused) {
+    return fused ? launch_front_t<1, true>(p, grid, st, sc16, unit) : launch_front_t<1, false>(p, grid, st, sc16, unit);
+}
+cudaError_t launch_rx_front_batch(const RxFrontParamsB &p, int grid, cudaStream_t st, bool sc16, bool unit, bool fused) {
+    return fused ? launch_front_t<kMaxBatch, true>(p, grid, st, sc16, unit) : launch_front_t<kMaxBatch, false>(p, grid, st, sc16, unit);
 }
 int rx_front_ctas_per_sm(bool sc16) { return sc16 ? kSc16Ctas : 2; }
 
+uint32_t rx_make_deal(RxDeal &d, uint32_t tiles, uint32_t resident) {
+    uint32_t grid = resident < (uint32_t)kMaxGrid ? resident : (uint32_t)kMaxGrid;
+    if (grid > tiles) grid = tiles;
+    if (grid < 1u) grid = 1u;
+    d.Tt = tiles; d.nstat = grid;
+    return grid;
+}
+
 // ---------------------------------------------------------------------------------------------
-// stand-alone trigger search + selection on a demod ring (the 400 kS/s front end's tail): groups [g_lo, g_hi), the same
-// rules as inside rx_front_kernel; the last CTA to finish selects.
+// stand-alone trigger search + selection on the demod rings, one or many channels per launch: CTAs [cta_first, cta_first +
+// cta_count) of the launch search a contiguous slice each of channel c's groups [g_lo, g_hi); the last of them to finish
+// selects.  Same rules (and the same device routines) as inside rx_front_kernel.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) rx_search_kernel(const float *__restrict__ dring, const uint32_t *__restrict__ hring, uint32_t dmask,
-                                                       RxState *state, Candidate *cand, Accepted *acc, RxPublished *host_pub,
-                                                       unsigned long long g_lo, unsigned long long g_hi, unsigned long long total_d,
-                                                       uint32_t par) {
+__global__ void __launch_bounds__(256) rx_search_kernel(const __grid_constant__ RxSearchParams p) {
     __shared__ uint32_t s_last;
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    for (unsigned long long g = g_lo + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; g < g_hi; g += stride)
-        detect_group(dring, hring, dmask, state, cand, 32ull * g);
+    __shared__ SearchScratch sc;
+    __shared__ Candidate s_cand[64];                   // (small: this CTA must fit on an SM next to two front-kernel CTAs)
+    uint32_t c = 0;
+    while (c + 1 < p.nchan && blockIdx.x >= p.ch[c + 1].cta_first) ++c;
+    const RxSearchChan &ch = p.ch[c];
+    if (threadIdx.x == 0) sc.nlc = 0u;
+    __syncthreads();
+    const unsigned long long n = ch.g_hi > ch.g_lo ? ch.g_hi - ch.g_lo : 0ull;
+    const unsigned long long per = (n + ch.cta_count - 1) / ch.cta_count;
+    unsigned long long lo = ch.g_lo + per * (blockIdx.x - ch.cta_first), hi = lo + per;
+    if (lo > ch.g_hi) lo = ch.g_hi;
+    if (hi > ch.g_hi) hi = ch.g_hi;
+    search_groups(ch.dring, ch.hring, ch.dmask, ch.state, ch.cand, lo, hi, &sc);
     __syncthreads();
     if (threadIdx.x == 0) {
+        flush_candidates(ch.state, ch.cand, &sc);
         __threadfence();
-        s_last = atomicAdd(&state->front_done, 1u) + 1u == gridDim.x ? 1u : 0u;
+        s_last = atomicAdd(&ch.state->search_done, 1u) + 1u == ch.cta_count ? 1u : 0u;
     }
     __syncthreads();
     if (s_last) {
         __threadfence();
-        select_channel(state, cand, cand + kMaxCand, acc + (size_t)par * kMaxAccept, par, total_d, host_pub);
-        if (threadIdx.x == 0) state->front_done = 0u;
+        select_channel(ch.state, ch.cand, ch.cand + kMaxCand, ch.acc + (size_t)ch.par * kMaxAccept, ch.par, ch.total_d, ch.host_pub, s_cand, 64u);
+        if (threadIdx.x == 0) ch.state->search_done = 0u;
     }
 }
 
-cudaError_t launch_rx_search(const float *dring, const uint32_t *hring, uint32_t dmask, RxState *state, Candidate *cand,
-                             Accepted *acc, RxPublished *host_pub, unsigned long long g_lo, unsigned long long g_hi,
-                             unsigned long long total_d, uint32_t par, cudaStream_t st) {
-    unsigned long long groups = g_hi > g_lo ? g_hi - g_lo : 0ull;
-    unsigned int grid = (unsigned int)((groups + 255ull) / 256ull);
-    if (grid < 1u) grid = 1u;
-    if (grid > 592u) grid = 592u;
-    rx_search_kernel<<<grid, 256, 0, st>>>(dring, hring, dmask, state, cand, acc, host_pub, g_lo, g_hi, total_d, par);
+cudaError_t launch_rx_search(const RxSearchParams &p, int grid, cudaStream_t st) {
+    if (grid <= 0) return cudaSuccess;
+    rx_search_kernel<<<grid, 256, 0, st>>>(p);
     return cudaGetLastError();
 }
 
@@ -1006,14 +1195,19 @@ static cudaError_t front_attrs(K kernel, size_t smem) {
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
+template <int kMaxChan, bool kFused>
+static cudaError_t front_attrs_all() {
+    cudaError_t e;
+    if ((e = front_attrs(rx_front_kernel<float2, kFc32Regs, false, kMaxChan, kFused>, sizeof(FrontSmem<float2>))) != cudaSuccess) return e;
+    if ((e = front_attrs(rx_front_kernel<short2, kSc16Ctas, false, kMaxChan, kFused>, sizeof(FrontSmem<short2>))) != cudaSuccess) return e;
+    return front_attrs(rx_front_kernel<short2, kSc16Ctas, true, kMaxChan, kFused>, sizeof(FrontSmem<short2>));
+}
 cudaError_t rx_configure_device() {
     cudaError_t e;
-    if ((e = front_attrs(rx_front_kernel<float2, 2, false, 1>, sizeof(FrontSmem<float2>))) != cudaSuccess) return e;
-    if ((e = front_attrs(rx_front_kernel<short2, kSc16Ctas, false, 1>, sizeof(FrontSmem<short2>))) != cudaSuccess) return e;
-    if ((e = front_attrs(rx_front_kernel<short2, kSc16Ctas, true, 1>, sizeof(FrontSmem<short2>))) != cudaSuccess) return e;
-    if ((e = front_attrs(rx_front_kernel<float2, 2, false, kMaxBatch>, sizeof(FrontSmem<float2>))) != cudaSuccess) return e;
-    if ((e = front_attrs(rx_front_kernel<short2, kSc16Ctas, false, kMaxBatch>, sizeof(FrontSmem<short2>))) != cudaSuccess) return e;
-    if ((e = front_attrs(rx_front_kernel<short2, kSc16Ctas, true, kMaxBatch>, sizeof(FrontSmem<short2>))) != cudaSuccess) return e;
+    if ((e = front_attrs_all<1, false>()) != cudaSuccess) return e;
+    if ((e = front_attrs_all<1, true>()) != cudaSuccess) return e;
+    if ((e = front_attrs_all<kMaxBatch, false>()) != cudaSuccess) return e;
+    if ((e = front_attrs_all<kMaxBatch, true>()) != cudaSuccess) return e;
     // The side-stream kernels share SMs with the NEXT call's front kernel, whose two CTAs need 199 KB of shared memory per
     // SM.  An SM's L1/shared split is fixed while CTAs are resident: if a kernel that wants a big L1 gets there first, the
     // front CTAs wait until it has left.  Ask for the front kernel's split everywhere.

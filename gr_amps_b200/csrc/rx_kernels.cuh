@@ -51,9 +51,8 @@ struct RxState {             // device-resident stream state of one channel
     unsigned int       cand_overflow;   // candidates dropped because the list was full (monotonic)
     unsigned int       pub_overflow;    // value of cand_overflow last mirrored to the host
     unsigned int       done;        // capture: bursts of the current call finished (reset by the last one)
-    unsigned int       front_done;  // front kernel: CTAs that finished their segment of this channel (reset by the last one)
-    unsigned int       pad;
-    unsigned int       left_mask[kMaxGrid / 32];   // CTAs whose boundary groups were left to the channel's last CTA
+    unsigned int       front_done;  // front kernel: segments of this channel finished in the current launch (reset by the last one)
+    unsigned int       search_done; // stand-alone search kernel: CTAs of this channel finished (it may overlap the next front kernel)
 };
 
 struct Accepted { unsigned long long pos; float corr; unsigned int run; };
@@ -88,7 +87,8 @@ struct RxChan {
     Candidate    *cand;      // 2 x kMaxCand: list + the select's sorted scratch
     Accepted     *acc;       // 2 x kMaxAccept, by call parity
     RxPublished  *host_pub;
-    uint32_t     *flags;     // kMaxGrid words: flags[cta] == epoch  <=>  that CTA's segment of this call is written
+    uint32_t     *flags;     // kMaxGrid words, all zero between launches: flags[j] counts the CTAs whose output the boundary
+                             // groups of CTA j's segment read and that have published it (the last one searches them)
     uint64_t      q_base;    // absolute demod index of this call's first output
     uint32_t      dmask;
     uint32_t      units;     // whole units this call processes (> 0)
@@ -96,12 +96,19 @@ struct RxChan {
     uint32_t      nchunk;    // samples in `chunk`
     uint32_t      blk_base;  // absolute 25-sample block index (mod 2^32) of logical sample 0
     uint32_t      fcw25;     // NCO phase step per block (25 * fcw mod 2^32)
-    uint32_t      epoch;     // call number + 1 of this channel
     uint32_t      par;       // call parity: which acc / n_acc / rec_base slot this call's select fills
     uint32_t      search;    // 0: no trigger search in this launch (M&M timing mode runs its own tail)
     float         in_scale;  // sc16 input: x = (float)int16 * in_scale (one fp32 multiply per component)
     float2        w[kD1];    // NCO phasors inside a block
 };
+
+// how a launch's tiles are dealt to CTAs (see deal_lo() in rx_kernels.cu)
+struct RxDeal {
+    uint32_t Tt;             // tiles of the launch
+    uint32_t nstat;          // CTAs of the launch; CTA s owns tiles [Tt*s/nstat, Tt*(s+1)/nstat)
+};
+// fills a deal for `tiles` tiles on at most `resident` CTAs; returns the grid size
+uint32_t rx_make_deal(RxDeal &d, uint32_t tiles, uint32_t resident);
 
 template <int kMaxChan>
 struct RxFrontParamsT {
@@ -111,7 +118,8 @@ struct RxFrontParamsT {
                              // product ready-made, so that it is a uniform-register operand of FFMA2 instead of a negate +
                              // move per sample (a batched launch indexes ch[] at run time and negates in the kernel)
     uint32_t  nchan;
-    uint32_t  defer_all;     // test hook: leave every boundary search to the channel's last CTA (the slow path)
+    RxDeal    deal;
+    unsigned long long *prof; // measurement aid (AMPS_RX_PROF=1): 16 time stamps per CTA, else nullptr
     uint32_t  tile_cum[kMaxChan + 1];   // tiles of channels 0..c-1
     RxChan    ch[kMaxChan];
 };
@@ -159,6 +167,30 @@ struct RxCaptureParams {
     RxCaptureChan ch[kMaxBatch];
 };
 
+// stand-alone search + select launch: one entry per channel
+struct RxSearchChan {
+    const float    *dring;
+    const uint32_t *hring;
+    RxState        *state;
+    Candidate      *cand;
+    Accepted       *acc;        // 2 x kMaxAccept
+    RxPublished    *host_pub;
+    unsigned long long g_lo, g_hi;   // groups to search
+    unsigned long long total_d;      // demod samples produced so far (what select decides against)
+    uint32_t        dmask;
+    uint32_t        par;
+    uint32_t        cta_first, cta_count;
+};
+struct RxSearchParams {
+    uint32_t     nchan;
+    RxSearchChan ch[kMaxBatch];
+};
+// CTAs a channel with `groups` groups to search gets
+inline uint32_t rx_search_ctas(unsigned long long groups) {
+    unsigned long long n = (groups + 255ull) / 256ull;
+    return (uint32_t)(n < 1ull ? 1ull : (n > 592ull ? 592ull : n));
+}
+
 // M&M timing mode: state of the clock_recovery_mm_ff recurrence (device-resident, carried between calls)
 struct MmState {
     float mu, omega, last;
@@ -175,13 +207,12 @@ int rx_front_ctas_per_sm(bool sc16);
 // tiles a channel with `units` whole units contributes to a launch
 inline uint32_t rx_tiles_of(uint32_t units) { return (units + kTileUnits - 1) / kTileUnits; }
 // front end + trigger search + (by the last CTA of each channel) candidate selection, all channels of the launch
-cudaError_t launch_rx_front(const RxFrontParams1 &p, int grid, cudaStream_t st, bool sc16, bool unit);
-cudaError_t launch_rx_front_batch(const RxFrontParamsB &p, int grid, cudaStream_t st, bool sc16, bool unit);
+cudaError_t launch_rx_front(const RxFrontParams1 &p, int grid, cudaStream_t st, bool sc16, bool unit, bool fused);
+cudaError_t launch_rx_front_batch(const RxFrontParamsB &p, int grid, cudaStream_t st, bool sc16, bool unit, bool fused);
 cudaError_t launch_rx_front400(const RxFront400Params &p, int grid, cudaStream_t st, bool sc16 = false, bool unit = false);
-// stand-alone search + select for the 400 kS/s front end (same rules as inside rx_front_kernel): groups [g_lo, g_hi)
-cudaError_t launch_rx_search(const float *dring, const uint32_t *hring, uint32_t dmask, RxState *state, Candidate *cand,
-                             Accepted *acc, RxPublished *host_pub, unsigned long long g_lo, unsigned long long g_hi,
-                             unsigned long long total_d, uint32_t par, cudaStream_t st);
+// stand-alone trigger search + selection on the demod rings (same rules as inside rx_front_kernel): the tail of the 400 kS/s
+// front end, and of the 10 MS/s one unless AMPS_RX_FUSED_SEARCH asks for the search inside the front kernel
+cudaError_t launch_rx_search(const RxSearchParams &p, int grid, cudaStream_t st);
 // capture: CTAs [cta_first, cta_first + cta_count) of channel c walk its accepted bursts (stride cta_count): gather the
 // 3374 half-symbols, decode, and stream the record into host_ring[(rec_base + b) % ring_len] (mapped pinned host memory)
 cudaError_t launch_rx_capture(const RxCaptureParams &p, int grid, cudaStream_t st);

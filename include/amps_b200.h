@@ -132,6 +132,12 @@ typedef struct amps_recc_iq_params {
                                       (float)int16 * sc16_scale happens in the front kernel.  Everything downstream is
                                       bit-identical to feeding amps_recc_iq_work() the converted floats. */
 
+#define AMPS_RX_FUSED_SEARCH  16u  /* 10 MS/s: run the trigger search and the burst selection INSIDE the front kernel (two launches per
+                                      call: front, capture) instead of as a launch of their own on the side stream (three).  Same
+                                      results bit for bit.  Saves a launch; costs the front kernel its tail (the search of the last
+                                      CTAs to finish cannot overlap anything), so the default keeps it outside -- DESIGN.md 4.2 has
+                                      the measurements. */
+
 typedef void (*amps_burst_cb)(const amps_burst *burst, void *user);
 
 AMPS_B200_API int amps_recc_iq_create(const amps_recc_iq_params *params, amps_recc_iq **out);
@@ -183,6 +189,9 @@ AMPS_B200_API int amps_recc_iq_stats(const amps_recc_iq *h, uint64_t *samples_in
  * first, at most cap (the handle keeps the last 256).  Synchronises the stream. */
 AMPS_B200_API int amps_recc_iq_front_times(amps_recc_iq *h, float *ms_out, int cap, int *n_out);
 AMPS_B200_API int amps_recc_iq_get_taps(const amps_recc_iq *h, float *lpf_out, int cap);                   /* returns ntaps */
+/* Measurement aid (handles created while AMPS_RX_PROF=1 is in the environment): 16 %globaltimer stamps (ns) per CTA of the
+ * most recent 10 MS/s front launch -- tools/front_phases.py turns them into a phase breakdown. */
+AMPS_B200_API int amps_recc_iq_debug_prof(amps_recc_iq *h, unsigned long long *out, int ctas);
 
 /* ------------------------------------------------------------------------------------------
  * Batched calls: K channels (handles) of ONE GPU served by one front launch + one capture launch per call

@@ -1,6 +1,6 @@
 """GPU parity of the pieces BASELINE configs 4 and 5 lean on: the device-resident path at ANY buffer length (2^14 ... samples,
 the remainder of a 1600-sample unit carried on the device), the front kernel's work split and in-kernel trigger search under
-every grid size (including the deferred-boundary slow path), and the batched entry points (K channels per launch, one
+every grid size, and the batched entry points (K channels per launch, one
 uploaded buffer feeding several carriers).  Everything is compared with the oracle bit for bit through the C ABI."""
 import os
 
@@ -45,14 +45,15 @@ def same_bursts(got, ob, oracle):
         assert words_equal(g.decoded, oracle.recc_decode(o[2])) == []
 
 
+@pytest.mark.parametrize("fused", [True, False])
 @pytest.mark.parametrize("logn", [14, 15, 17, 20])
-def test_power_of_two_buffers_device_path(capi, torch, oracle, two_bursts, logn):
+def test_power_of_two_buffers_device_path(capi, torch, oracle, two_bursts, logn, fused):
     """BASELINE config 5's buffer sizes through amps_recc_iq_submit_dev: 2^k is not a multiple of the 1600-sample unit, the
     remainder is carried on the device; the demodulated stream and the bursts are those of the one-shot oracle."""
     x, d_orc, ob = two_bursts
     n = 1 << logn
     t = torch.from_numpy(x.view(np.float32).copy()).cuda()
-    rx = capi.ReccIq(max_samples=n)
+    rx = capi.ReccIq(max_samples=n, fused_search=fused)
     got, pos = [], 0
     while pos + n <= len(x):
         rx.submit_dev(t.data_ptr() + 8 * pos, n, torch.cuda.current_stream().cuda_stream)
@@ -90,14 +91,16 @@ def test_ragged_device_calls_and_mixed_sizes(capi, torch, oracle, two_bursts):
     rx.close()
 
 
-@pytest.mark.parametrize("grid,defer", [(1, "0"), (2, "0"), (7, "0"), (37, "1"), (296, "1"), (0, "1")])
-def test_result_does_not_depend_on_the_work_split(capi, oracle, two_bursts, grid, defer, monkeypatch):
-    """AMPS_RX_GRID caps the front kernel's grid (segments of every length, boundaries in different places);
-    AMPS_RX_DEFER=1 forces the slow path in which every boundary group is searched by the channel's last CTA."""
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("grid", [1, 2, 7, 37, 148, 296, 0])
+def test_result_does_not_depend_on_the_work_split(capi, oracle, two_bursts, grid, fused, monkeypatch):
+    """AMPS_RX_GRID caps the front kernel's grid: segments of every length and, with AMPS_RX_FUSED_SEARCH, the trigger-search
+    boundaries between CTAs in different places (a burst's trigger straddling two, or -- with short segments -- up to ten
+    CTAs).  Without the flag the search is a launch of its own: same bursts."""
     x, d_orc, ob = two_bursts
     if grid:
         monkeypatch.setenv("AMPS_RX_GRID", str(grid))
-    monkeypatch.setenv("AMPS_RX_DEFER", defer)
+    monkeypatch.setenv("AMPS_RX_FUSED", "1" if fused else "0")
     rx = capi.ReccIq(max_samples=len(x))
     got = rx.work(x[:3 * N1 // 2 + 1234]) + rx.work(x[3 * N1 // 2 + 1234:])
     assert bits_equal_f32(rx.read_demod(0, len(x) // 50), d_orc)
@@ -105,12 +108,13 @@ def test_result_does_not_depend_on_the_work_split(capi, oracle, two_bursts, grid
     rx.close()
 
 
-def test_small_calls_with_tiny_segments(capi, oracle, two_bursts):
-    """Calls of a few units on the full grid: every CTA owns one short tile and the trigger search of each segment leans on
-    up to nine CTAs in front of it."""
+@pytest.mark.parametrize("fused", [True, False])
+def test_small_calls_with_tiny_segments(capi, oracle, two_bursts, fused):
+    """Calls of a few units on the full grid: every CTA owns one short tile and (fused search) the trigger search of each
+    segment leans on up to nine CTAs in front of it."""
     x, d_orc, ob = two_bursts
     x = x[:N1 + 30 * PASS]
-    rx = capi.ReccIq(max_samples=1 << 20)
+    rx = capi.ReccIq(max_samples=1 << 20, fused_search=fused)
     got, pos = [], 0
     sizes = [UNIT, 3 * UNIT, 5 * UNIT + 7, 50 * UNIT, 301 * UNIT + 333, 1 << 20]
     k = 0
@@ -137,17 +141,19 @@ def carriers_period(ks, snr=20.0, n_total=N1):
     return out
 
 
-def test_batch_of_independent_channels(capi, torch, oracle):
-    """Eight carriers, eight different device buffers, ONE front launch + ONE capture launch per call; ragged lengths."""
+@pytest.mark.parametrize("fused", [True, False])
+def test_batch_of_independent_channels(capi, torch, oracle, fused):
+    """Eight carriers, eight different device buffers, ONE front launch (+ one search launch unless it is fused into the
+    front kernel) + ONE capture launch per call; ragged lengths."""
     cs = carriers_period(range(8))
-    hs = [capi.ReccIq(max_samples=N1, center_freq=c.center_freq) for c, _ in cs]
+    hs = [capi.ReccIq(max_samples=N1, center_freq=c.center_freq, fused_search=fused) for c, _ in cs]
     b = capi.ReccIqBatch(hs)
     ts = [torch.from_numpy(x.view(np.float32).copy()).cuda() for _, x in cs]
     cuts = [0, 700000, 700000 + 2 * 9999, N1]
     stream = torch.cuda.current_stream().cuda_stream
     for a, e in zip(cuts[:-1], cuts[1:]):
         b.submit_dev([t.data_ptr() + 8 * a for t in ts], e - a, stream)
-    assert b.stats() == dict(calls=3, kernel_launches=6)
+    assert b.stats() == dict(calls=3, kernel_launches=6 if fused else 9)
     for h, (c, x) in zip(hs, cs):
         got = h.collect()
         _, d = oracle.rx_chain_f32(x, center=c.center_freq)
@@ -165,7 +171,7 @@ def test_batch_larger_than_one_launch_and_uneven_lengths(capi, torch, oracle):
     """70 channels (more than one launch's 64) on 3 distinct buffers, channel i fed in calls of its own length."""
     cs = carriers_period([0, 3, 6], n_total=N1)
     K = 70
-    hs = [capi.ReccIq(max_samples=N1, center_freq=cs[i % 3][0].center_freq) for i in range(K)]
+    hs = [capi.ReccIq(max_samples=N1, center_freq=cs[i % 3][0].center_freq, fused_search=(K % 2 == 1)) for i in range(K)]
     b = capi.ReccIqBatch(hs, time_kernels=True)
     ts = [torch.from_numpy(x.view(np.float32).copy()).cuda() for _, x in cs]
     stream = torch.cuda.current_stream().cuda_stream
@@ -232,7 +238,8 @@ def test_batch_argument_checks(capi, torch):
     m = capi.ReccIq(max_samples=PASS, timing_mm=True)
     n4 = capi.ReccIq(max_samples=1536, samp_rate=400e3)
     s = capi.ReccIq(max_samples=PASS, sc16=True)
-    for bad in ([a, m], [a, n4], [a, s], [a, a], []):
+    f = capi.ReccIq(max_samples=PASS, fused_search=True)
+    for bad in ([a, m], [a, n4], [a, s], [a, a], [a, f], []):
         with pytest.raises((capi.AmpsError, ValueError)):
             capi.ReccIqBatch(bad)
     b = capi.ReccIqBatch([a])
@@ -246,5 +253,24 @@ def test_batch_argument_checks(capi, torch):
     b.submit_dev([t.data_ptr()], 0, 0)
     b.close()
     assert a.work(np.zeros(UNIT, np.complex64)) == []  # usable on its own again
-    for h in (a, m, n4, s):
+    for h in (a, m, n4, s, f):
         h.close()
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_large_call_many_bursts(capi, torch, oracle, fused):
+    """22 periods = 46.5 M samples in one submit (about 33 tiles per CTA on the full grid), against the one-shot oracle."""
+    periods = [synth.config2_period(n_total=N1, snr_db=20.0, seed=500 + i, min10="212555%04d" % (5000 + i))[0] for i in range(3)]
+    x = np.concatenate([periods[i % 3] for i in range(22)])
+    t = torch.from_numpy(x.view(np.float32).copy()).cuda()
+    rx = capi.ReccIq(max_samples=len(x), fused_search=fused)
+    rx.submit_dev(t.data_ptr(), len(x), torch.cuda.current_stream().cuda_stream)
+    got = rx.collect()
+    _, d = oracle.rx_chain_f32(x)
+    ob = oracle.rx_detect(d, max_bursts=64)
+    assert bits_equal_f32(rx.read_demod(0, len(x) // 50), d)
+    assert len(ob) == 22
+    same_bursts(got, ob, oracle)
+    rx.submit_dev(t.data_ptr(), len(x), torch.cuda.current_stream().cuda_stream)
+    assert len(rx.collect()) == 22
+    rx.close()
