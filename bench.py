@@ -8,7 +8,8 @@ N > 1 is launched by torchrun (one rank per GPU, NCCL only for the barrier / max
 no collective on the sample path: every rank demodulates its own independent carrier -- weak scaling).
 
 One step = one batch of synthetic 10 MS/s baseband (128 config-2 periods = 270 336 000 complex
-samples = 2.16 GB, larger than L2, so every step streams from HBM) through
+samples = 2.16 GB, larger than L2, so every step streams from HBM; SNR cycles inf / 30 / 15 dB over the periods; the
+bursts of the first six periods of every step are compared with the oracle inside the run) through
 amps_recc_iq_submit_dev (device-resident input; `value`) or amps_recc_iq_work (pinned HOST buffer,
 H2D + kernels + D2H of the burst records inside the timed region; `e2e`).
 
@@ -108,42 +109,68 @@ class ClockSampler(threading.Thread):
                 "power_w_max": max(self.power) if self.power else None}
 
 
-def make_clean_period(rank):
+WORKLOAD = ("config2: single RECC chain per GPU, 10 MS/s synthetic FM RECC bursts (7-word origination, one per 2 112 000-sample period; "
+            "periods cycle through SNR inf / 30 / 15 dB in the 30 kHz channel), demod + correlate + decode, bit-exact word recovery gated; "
+            "carrier g at -160 kHz + 30 kHz*g, one per GPU")
+SNRS = [None, 30.0, 15.0]            # BASELINE config 2
+HOST_PERIODS = 3                     # periods per batch (one per SNR) whose noise is made on the host from the seeded generator: the oracle sees them
+FLOP_PER_SAMPLE = 44.4               # fp32: NCO 6 + CIC^3 11.7 + block phasors 2 + 299 taps/50 samples 23.9 + demod 0.8
+
+
+def base_config(nper):
+    return {"workload": WORKLOAD, "period_samples": PERIOD, "periods_per_step_per_gpu": nper, "samples_per_step_per_gpu": nper * PERIOD,
+            "bursts_per_step_per_gpu": nper, "snr_db": ["inf", 30, 15],
+            "l2": "inputs larger than L2 (2.16 GB per step at the default 128 periods)",
+            "timing": "CUDA events on the launching stream, max over ranks"}
+
+
+def host_periods(rank):
+    """The first HOST_PERIODS periods of this rank's batch (signal + seeded host noise) and the clean period the rest is tiled from."""
     from gr_amps_b200 import multi, synth
-    # config 4: carrier g sits at -160 kHz + 30 kHz * g, its own MIN
-    c = multi.carrier(rank)
-    x, hs, _ = synth.config2_period(n_total=PERIOD, snr_db=None, center=c.center_freq, min10=c.min10)
-    return x, hs, c
+    c = multi.carrier(rank)                         # config 4: carrier g sits at -160 kHz + 30 kHz * g, its own MIN
+    clean, hs, _ = synth.config2_period(n_total=PERIOD, snr_db=None, center=c.center_freq, min10=c.min10)
+    per = [clean if SNRS[i % 3] is None else
+           synth.config2_period(n_total=PERIOD, snr_db=SNRS[i % 3], seed=c.seed + 1000 * i, center=c.center_freq, min10=c.min10)[0]
+           for i in range(HOST_PERIODS)]
+    return c, clean, per
+
+
+def cpu_baseline_measure(steps, warmup):
+    """The CPU arm, used by --impl reference AND by the cpu_baseline leg of the GPU line (same code, same averaging): the oracle
+    port of the chain (fp32 kernel-spec flavour + detect + decode), rebuilt -O3 -march=native on this box, one channel per host
+    thread, each thread one config-2 period per step (SNR cycling inf / 30 / 15 dB over the threads)."""
+    from tests import oracle_lib as O
+    cores = os.cpu_count() or 1
+    _, _, per = host_periods(0)
+    x = per[1]                                       # 30 dB period (the noise level does not change the CPU work)
+    _, flags = O.native_lib()
+    for _ in range(max(warmup, 1)):
+        O.cpu_baseline_run(x, cores, 1, native=True)
+    t_total, nb = 0.0, 0
+    for _ in range(steps):
+        sec, b = O.cpu_baseline_run(x, cores, 1, native=True)
+        t_total += sec
+        nb += b
+    sec1, _ = O.cpu_baseline_run(x, 1, 2, native=True)
+    v = float(steps) * cores * len(x) / t_total / 1e6
+    return {"value": v, "unit": "Msamples/s", "cores": cores, "kind": "port", "value_1_thread": 2 * len(x) / sec1 / 1e6,
+            "build": flags, "steps": steps, "ms_per_step": 1e3 * t_total / steps, "bursts_decoded": nb,
+            "sample": "%d host threads x one config-2 period (%d samples) per step, %d steps averaged; fp32 oracle chain + detect + decode; %.1f s CPU work"
+                      % (cores, len(x), steps, t_total * cores)}
 
 
 def run_reference(args, rank, world):
     """CPU arm: the oracle port of the chain on all host cores (rank 0 only)."""
     if rank != 0:
         return
-    from tests import oracle_lib as O
-    from gr_amps_b200 import synth
-    cores = os.cpu_count() or 1
-    x, _, _ = synth.config2_period(n_total=PERIOD, snr_db=20.0, seed=0xA3B5)
-    reps = 1                                   # per thread per step: one period (2.1 M samples)
-    for _ in range(max(args.warmup, 1)):
-        O.cpu_baseline_run(x, cores, 1)
-    t_total, nb = 0.0, 0
-    for _ in range(args.steps):
-        sec, b = O.cpu_baseline_run(x, cores, reps)
-        t_total += sec
-        nb += b
-    samples = float(args.steps) * cores * reps * len(x)
-    v = samples / t_total / 1e6
-    sample = "%d threads x %d x one config-2 period (%d samples) per step, same chain as the GPU arm (fp32 oracle port + detect + decode)" % (cores, reps, len(x))
+    cpu = cpu_baseline_measure(args.steps, args.warmup)
     line = {
-        "impl": "reference", "metric": "Msamples/s complex IQ through RECC demod+correlate", "value": v, "unit": "Msamples/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
+        "impl": "reference", "metric": "Msamples/s complex IQ through RECC demod+correlate", "value": cpu["value"], "unit": "Msamples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cpu["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "config2: 10 MS/s synthetic FM RECC bursts, 7-word origination, SNR 20 dB, one channel per host thread",
-                   "period_samples": PERIOD, "samples_per_step": cores * reps * len(x)},
-        "cpu_baseline": {"value": v, "unit": "Msamples/s", "cores": cores, "kind": "port", "sample": sample,
-                         "bursts_decoded": nb},
-        "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": base_config(args.periods),
+        "cpu_baseline": cpu,
+        "e2e": {"value": cpu["value"], "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
@@ -271,6 +298,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--periods", type=int, default=PERIODS_PER_BATCH)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--sustain", type=float, default=2.0, help="seconds of back-to-back steps for roofline.sustained (0 = skip)")
+    ap.add_argument("--shared-carriers", type=int, default=8, help="K of the one-upload-K-carriers end-to-end leg (0/1 = skip)")
     ap.add_argument("--workload", default="recc", choices=["recc", "fwd"],
                     help="recc = headline metric (config 2); fwd = forward path of config 3 (secondary line)")
     args = ap.parse_args()
@@ -299,19 +328,71 @@ def main():
     if args.warmup < 3:
         args.warmup = 3
 
-    # ---- synthetic batch: tile one clean period, add fresh AWGN (SNR 20 dB in 30 kHz) on the device
-    clean, hs, car = make_clean_period(rank)
+    from gr_amps_b200 import multi
+    from tests import oracle_lib as O
+
+    # ---- synthetic batch: one clean period tiled; AWGN per period at SNR inf / 30 / 15 dB (BASELINE config 2).  The first
+    #      HOST_PERIODS periods get their noise on the HOST from the seeded generator, so that the oracle sees exactly what
+    #      the GPU sees; the others get fresh device noise of the same level.
+    car, clean, hper = host_periods(rank)
     center = car.center_freq
     nper = args.periods
     n = nper * PERIOD
     g = torch.Generator(device=dev)
     g.manual_seed(car.seed)
     base = torch.from_numpy(clean.view(np.float32).copy()).to(dev)
-    sigma = float(np.sqrt(0.25 / 100.0 * (10e6 / 30e3) / 2.0))
     batch = base.repeat(nper)
-    batch.add_(torch.randn(batch.shape, generator=g, device=dev, dtype=torch.float32), alpha=sigma)
+    sig = [0.0 if v is None else float(np.sqrt(0.25 / (10.0 ** (v / 10.0)) * (10e6 / 30e3) / 2.0)) for v in SNRS]
+    per_view = batch.view(nper, 2 * PERIOD)
+    for i in range(nper):
+        if i < HOST_PERIODS:
+            per_view[i].copy_(torch.from_numpy(hper[i].view(np.float32)))
+        elif sig[i % 3] > 0.0:
+            per_view[i].add_(torch.randn(2 * PERIOD, generator=g, device=dev, dtype=torch.float32), alpha=sig[i % 3])
     del base
     torch.cuda.synchronize()
+    # What the oracle makes of a host period.  The NCO phase follows the ABSOLUTE sample index, so the fp32 results (the soft
+    # correlation to the last bit, and in principle a hard decision that sits within an ulp of zero) depend on where in the
+    # stream a period lies: the oracle demodulates host period p of step s at its own absolute position, from zero history
+    # (the burst starts 2 ms into the period, the filters remember 0.8 ms).  One oracle run per (step, host period), on a
+    # thread pool -- after the timed region.
+    nh = min(HOST_PERIODS, nper)
+    expect_min = car.min10.encode()
+    PD = PERIOD // 50
+    cache = {}
+
+    def oracle_period(pabs):
+        _, d = O.rx_chain_f32(hper[pabs % nper], center=center, blk0=pabs * (PERIOD // 25))
+        ob = O.rx_detect(d, max_bursts=4)
+        if len(ob) != 1:
+            raise SystemExit("bench.py: the oracle found %d bursts in a host period" % len(ob))
+        pos, corr, syms = ob[0]
+        return pabs, (int(pos), np.float32(corr), syms.tobytes(), O.recc_decode(syms))
+
+    def check_bursts(ring, ring_len, first, count, oracle_stride=1):
+        """parity gate: bursts that fall into a host period must equal the oracle's (position, correlation, 3374-byte blob,
+        decoded words) -- every oracle_stride-th step; returns (bursts, oracle-checked, decoded to this rank's MIN)."""
+        from concurrent.futures import ThreadPoolExecutor
+        from tests.helpers import words_equal
+        good = 0
+        todo = []
+        for i in range(count):
+            b = ring[(first + i) % ring_len]
+            pabs, off = divmod(b.demod_index, PD)
+            if pabs % nper < nh and (pabs // nper) % oracle_stride == 0:
+                todo.append((pabs, off, b))
+            if b.decoded.min == expect_min and list(b.decoded.valid) == [1] * 7 and b.decoded.kind == 4:
+                good += 1
+        need = sorted({t[0] for t in todo} - set(cache))
+        if need:
+            with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 1)) as ex:
+                cache.update(dict(ex.map(oracle_period, need)))
+        for pabs, off, b in todo:
+            e = cache[pabs]
+            if off != e[0] or np.float32(b.corr) != e[1] or bytes(b.symbols) != e[2] or words_equal(b.decoded, e[3]) != []:
+                raise SystemExit("bench.py: parity gate failed: burst at demod index %d differs from the oracle" % b.demod_index)
+        cache.clear()
+        return count, len(todo), good
 
     steps_total = args.warmup + args.steps
     # burst ring: holds every record of the run when that is reasonable, else it is drained on the fly (poll, no sync)
@@ -327,7 +408,8 @@ def main():
     # ---- device-resident arm ------------------------------------------------------------------
     for _ in range(args.warmup):
         rx.submit_dev(batch.data_ptr(), n, stream.cuda_stream)
-    _, _, _, warm_count = rx.peek()
+    ring, ring_len, first, warm_count = rx.peek()
+    check_bursts(ring, ring_len, first, warm_count)
     rx.consume(warm_count)
     launches0 = rx.stats()["kernel_launches"]
     sampler = ClockSampler(local_rank)
@@ -336,14 +418,14 @@ def main():
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    drained = 0
+    tot = [0, 0, 0]
     for k in range(args.steps):
         rx.submit_dev(batch.data_ptr(), n, stream.cuda_stream)
         if ring_cap < nper * (steps_total + 2) and (k & 63) == 63:
-            _, _, _, c = rx.poll()            # non-blocking: keep the ring from wrapping on very long runs
+            ring, ring_len, first, c = rx.poll()      # non-blocking: keep the ring from wrapping on very long runs
             if c > ring_cap // 2:
+                tot = [a + v for a, v in zip(tot, check_bursts(ring, ring_len, first, c))]
                 rx.consume(c)
-                drained += c
     ring, ring_len, first, count = rx.peek()   # stream sync; the kernels already published every record to the pinned host ring
     e1.record(stream)
     barrier()
@@ -351,19 +433,41 @@ def main():
     ms = e0.elapsed_time(e1)
     launches = rx.stats()["kernel_launches"] - launches0
     front_ms = rx.front_times_ms(256)[-args.steps:]
-    from gr_amps_b200 import multi
     total_samples, ms_max = multi.whole_job_throughput(float(args.steps) * n, ms, dev)
-
-    # correctness gate: the stream is continuous over the steps, so all but the burst straddling the
-    # last batch's end are captured; every one must decode to this rank's MIN with all words valid
-    expect_min = car.min10.encode()
-    bursts = [ring[(first + i) % ring_len] for i in range(count)]
-    ok = [b for b in bursts if b.decoded.min == expect_min and list(b.decoded.valid) == [1] * 7 and b.decoded.kind == 4]
-    if len(ok) + drained < args.steps * nper - 2 or len(ok) != len(bursts):
-        raise SystemExit("bench.py: parity gate failed: %d bursts, %d good, expected >= %d" % (len(bursts) + drained, len(ok), args.steps * nper - 2))
-    n_bursts = len(bursts) + drained
-    del bursts
+    tot = [a + v for a, v in zip(tot, check_bursts(ring, ring_len, first, count))]
     rx.consume(count)
+    n_bursts, n_checked, n_good = tot
+    # the stream is continuous over the steps, so all but the burst straddling the last batch's end are captured
+    if n_bursts < args.steps * nper - 2 or n_checked < nh * args.steps - 2 or n_good < 0.97 * n_bursts:
+        raise SystemExit("bench.py: parity gate failed: %d bursts (expected >= %d), %d equal to the oracle's (expected >= %d), %d good"
+                         % (n_bursts, args.steps * nper - 2, n_checked, nh * args.steps - 2, n_good))
+
+    # ---- the same, sustained: at least 2 s of back-to-back steps (the timed region above is a few ms at maximum clocks)
+    sustained = None
+    if args.sustain > 0 and ms < 1e3 * args.sustain:
+        k_sus = int(np.ceil(args.sustain * 1e3 / (ms / args.steps))) + 8
+        sus_sampler = ClockSampler(local_rank)
+        barrier()
+        sus_sampler.start()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        for k in range(k_sus):                      # nothing but launches: the ring wraps, the newest records survive
+            rx.submit_dev(batch.data_ptr(), n, stream.cuda_stream)
+        s1.record(stream)
+        ring, ring_len, first, c = rx.peek()
+        barrier()
+        sus_clk = sus_sampler.stop()
+        stride = max(1, (min(k_sus, ring_len // nper)) // 24)
+        sus_b = check_bursts(ring, ring_len, first, c, oracle_stride=stride)       # the last ring-full of records; every stride-th step against the oracle
+        rx.consume(c)
+        sus_ms = s0.elapsed_time(s1)
+        sus_front = float(np.mean(rx.front_times_ms(256)))
+        want = min(k_sus * nper - 2, ring_len)
+        if sus_b[0] < want or sus_b[1] < nh or sus_b[2] < 0.97 * sus_b[0]:
+            raise SystemExit("bench.py: parity gate failed in the sustained run: %s (wanted %d bursts)" % (list(sus_b), want))
+        sustained = {"seconds": sus_ms * 1e-3, "steps": k_sus, "ms_per_step": sus_ms / k_sus, "front_launch_ms": sus_front,
+                     "sm_mhz_median": sus_clk.get("sm_mhz"), "power_w_max": sus_clk.get("power_w_max"), "reasons": sus_clk.get("reasons"),
+                     "bursts_checked": sus_b[0], "bursts_equal_to_oracle": sus_b[1]}
 
     # ---- end-to-end arm: pinned host buffer through amps_recc_iq_work ----------------------------
     # the staging buffer is allocated (first-touched) from a core of the GPU's own NUMA node, as a deployment would do
@@ -373,11 +477,23 @@ def main():
     torch.cuda.synchronize()
     rx2 = capi.ReccIq(max_samples=n, center_freq=center, device=local_rank, max_bursts=2 * nper + 8)
     got = []
-    cb = capi.BURST_CB(lambda bp, user: got.append(bp.contents.decoded.min))
+
+    e2e_recs = []
+
+    def on_burst(bp, user):
+        b = bp.contents
+        got.append(b.decoded.min)
+        if (b.demod_index // PD) % nper < nh:
+            c = capi.Burst()
+            capi.C.memmove(capi.C.byref(c), bp, capi.C.sizeof(capi.Burst))
+            e2e_recs.append(c)
+
+    cb = capi.BURST_CB(on_burst)
     e2e_steps = max(3, min(args.steps, 10))
     for _ in range(2):
         rx2.work_ptr(host.data_ptr(), n, cb)
     got.clear()
+    e2e_recs.clear()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
@@ -385,9 +501,23 @@ def main():
     torch.cuda.synchronize()
     t1 = time.perf_counter()
     e2e_samples, e2e_sec = multi.whole_job_throughput(float(e2e_steps) * n, t1 - t0, dev)
-    if len(got) < e2e_steps * nper - 2 or any(m != expect_min for m in got):
-        raise SystemExit("bench.py: e2e parity gate failed (%d bursts)" % len(got))
+    arr = (capi.Burst * max(len(e2e_recs), 1))(*e2e_recs)
+    e2e_checked = check_bursts(arr, max(len(e2e_recs), 1), 0, len(e2e_recs))[1]
+    if len(got) < e2e_steps * nper - 2 or e2e_checked < nh * e2e_steps - 2 or sum(1 for m in got if m == expect_min) < 0.97 * len(got):
+        raise SystemExit("bench.py: e2e parity gate failed (%d bursts, %d equal to the oracle's)" % (len(got), e2e_checked))
     rec_bytes = 24 + (len(got) / e2e_steps) * float(capi.C.sizeof(capi.Burst))
+    # the ceiling of that arm: the same bytes from the same pinned buffer, a bare cudaMemcpyAsync per step and nothing else
+    dst = torch.empty_like(batch)
+    for _ in range(2):
+        dst.copy_(host, non_blocking=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        dst.copy_(host, non_blocking=True)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    h2d_samples, h2d_sec = multi.whole_job_throughput(float(e2e_steps) * n, t1 - t0, dev)
+    del dst
     if old_affinity is not None:
         os.sched_setaffinity(0, old_affinity)              # the CPU baseline below uses every core again
 
@@ -395,7 +525,7 @@ def main():
     #      PCIe and out of HBM, converted in the front kernel).  Reported beside the fc32 numbers, never instead of them.
     del host
     rx.close(); rx2.close()
-    SC16_SCALE = 1.0 / 8192.0                               # +-4.0 full scale: signal 0.5 + wideband noise sigma 0.65
+    SC16_SCALE = 1.0 / 8192.0                               # +-4.0 full scale: signal 0.5 + wideband noise sigma up to 1.2
     b16 = torch.clamp(torch.round(batch * (1.0 / SC16_SCALE)), -32768, 32767).to(torch.int16)
     del batch
     torch.cuda.empty_cache()
@@ -417,7 +547,7 @@ def main():
     sc_ms = s0.elapsed_time(s1)
     good3 = sum(1 for i in range(count3) if ring3[(first3 + i) % ring3_len].decoded.min == expect_min
                 and list(ring3[(first3 + i) % ring3_len].decoded.valid) == [1] * 7)
-    if good3 != count3 or count3 < sc_steps * nper - 2:
+    if good3 < 0.97 * count3 or count3 < sc_steps * nper - 2:
         raise SystemExit("bench.py: sc16 parity gate failed: %d bursts, %d good" % (count3, good3))
     rx3.consume(count3)
     sc_front_ms = float(np.mean(rx3.front_times_ms(256)[-sc_steps:]))
@@ -427,22 +557,57 @@ def main():
     host16.copy_(b16)
     torch.cuda.synchronize()
     got.clear()
+    cb_min = capi.BURST_CB(lambda bp, user: got.append(bp.contents.decoded.min))
     for _ in range(2):
-        rx3.work_ptr(host16.data_ptr(), n, cb)
+        rx3.work_ptr(host16.data_ptr(), n, cb_min)
     got.clear()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        rx3.work_ptr(host16.data_ptr(), n, cb)
+        rx3.work_ptr(host16.data_ptr(), n, cb_min)
     torch.cuda.synchronize()
     t1 = time.perf_counter()
     sc_e2e_samples, sc_e2e_sec = multi.whole_job_throughput(float(e2e_steps) * n, t1 - t0, dev)
-    if len(got) < e2e_steps * nper - 2 or any(m != expect_min for m in got):
+    if len(got) < e2e_steps * nper - 2 or sum(1 for m in got if m == expect_min) < 0.97 * len(got):
         raise SystemExit("bench.py: sc16 e2e parity gate failed (%d bursts)" % len(got))
+    rx3.close()
+
+    # ---- secondary: ONE uploaded wideband buffer feeding K carriers of this GPU (amps_recc_iq_batch_work_shared, sc16 wire
+    #      format): the PCIe transfer is shared, so the end-to-end rate in carrier-samples is K times the link's sample rate
+    #      until the device side (K front-kernel passes over the buffer) becomes the limit
+    shared = None
+    if args.shared_carriers > 1:
+        K = args.shared_carriers
+        hs = [capi.ReccIq(max_samples=n, center_freq=multi.carrier(k).center_freq, device=local_rank, max_bursts=2 * nper + 8,
+                          sc16=True, sc16_scale=SC16_SCALE) for k in range(K)]
+        bt = capi.ReccIqBatch(hs)
+        counts = [0] * K
+        rank_ch = rank % K                                   # the carrier whose signal is in this rank's buffer
+        def on_shared(ch, bp, user):
+            counts[ch] += 1
+        cbs = capi.BATCH_BURST_CB(on_shared)
+        for _ in range(2):
+            bt.work_shared_ptr(host16.data_ptr(), n, cbs)
+        counts = [0] * K
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            bt.work_shared_ptr(host16.data_ptr(), n, cbs)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        sh_samples, sh_sec = multi.whole_job_throughput(float(e2e_steps) * n * K, t1 - t0, dev)
+        if counts[rank_ch] < e2e_steps * nper - 2 or sum(counts) != counts[rank_ch]:
+            raise SystemExit("bench.py: shared-upload gate failed: bursts per carrier %s" % counts)
+        shared = {"carriers_per_gpu": K, "api": "amps_recc_iq_batch_work_shared (sc16)", "value": sh_samples / sh_sec / 1e6,
+                  "unit": "carrier-Msamples/s", "uploaded_Msamples_s": sh_samples / sh_sec / 1e6 / K, "h2d_bytes_per_step": n * 4,
+                  "steps": e2e_steps, "bursts": counts[rank_ch],
+                  "note": "the buffer carries this rank's carrier only: the other K-1 channels demodulate it and (correctly) find nothing"}
+        bt.close()
+        for h in hs:
+            h.close()
     if old_affinity is not None:
         os.sched_setaffinity(0, old_affinity)
     del host16, b16
-    rx3.close()
 
     # ---- secondary: the forward path (config 3 / the FOCC half of config 4) on every rank's GPU
     torch.cuda.empty_cache()
@@ -467,49 +632,47 @@ def main():
         "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": fm,
         "traffic": (traffic["dram_bytes_per_sample"] * n if traffic else None),
         "front_share_of_step": fm / (ms_max / args.steps),
+        "fp32_flop_per_sample": FLOP_PER_SAMPLE, "fp32_tflops": FLOP_PER_SAMPLE * n / (fm * 1e-3) / 1e12,
     }
+    if sustained:
+        sa = alg_bytes / (sustained["front_launch_ms"] * 1e-3) / 1e9
+        sustained["achieved"] = sa
+        sustained["frac"] = sa / peak
+        sustained["value"] = world * n / (sustained["ms_per_step"] * 1e-3) / 1e6
+        roofline["sustained"] = sustained
 
     cpu = None
     if world == 1 and not args.no_cpu:
-        from tests import oracle_lib as O
-        from gr_amps_b200 import synth
-        cores = os.cpu_count() or 1
-        xs, _, _ = synth.config2_period(n_total=PERIOD, snr_db=20.0, seed=0xA3B5)
-        O.cpu_baseline_run(xs, min(cores, 8), 1)      # warm the code and the page cache
-        reps = 1
-        sec, nb = O.cpu_baseline_run(xs, cores, reps)
-        sec1, _ = O.cpu_baseline_run(xs, 1, 2)
-        cpu = {"value": cores * reps * len(xs) / sec / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "port",
-               "value_1_thread": 2 * len(xs) / sec1 / 1e6,
-               "sample": "%d threads x %d x one config-2 period (%d samples); fp32 oracle chain + detect + decode; %.1f s CPU work"
-                         % (cores, reps, len(xs), sec * cores), "bursts_decoded": nb}
+        cpu = cpu_baseline_measure(8, 2)
 
     line = {
         "metric": "Msamples/s complex IQ through RECC demod+correlate",
         "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "config2: single RECC chain per GPU, 10 MS/s synthetic FM RECC bursts (7-word origination, SNR 20 dB), demod+correlate+decode, bit-exact word recovery gated",
-                   "samples_per_step_per_gpu": n, "bursts_per_step_per_gpu": nper, "period_samples": PERIOD,
-                   "carriers": "one per GPU at -160 kHz + 30 kHz*rank", "l2": "inputs larger than L2 (2.16 GB per step at the default 128 periods)",
-                   "timing": "CUDA events on the launching stream, max over ranks"},
+        "config": base_config(nper),
         "roofline": roofline,
         "cpu_baseline": cpu,
         "clocks": clocks,
         "e2e": {"value": e2e_samples / e2e_sec / 1e6, "unit": "Msamples/s",
                 "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": int(rec_bytes), "steps": e2e_steps,
-                "api": "amps_recc_iq_work (pinned host buffer, burst callbacks)"},
+                "api": "amps_recc_iq_work (pinned host buffer, burst callbacks)",
+                "h2d_ceiling": {"value": h2d_samples / h2d_sec / 1e6, "unit": "Msamples/s", "GBps_per_gpu": h2d_samples * 8 / h2d_sec / 1e9 / world,
+                                "what": "bare cudaMemcpyAsync of the same pinned buffer, same steps, all ranks at once: the host link's share of the e2e time"}},
         "sc16_input": {"note": "same workload, samples as interleaved int16 I,Q (AMPS_RX_INPUT_SC16, the USRP wire format): 4 B/sample over PCIe and from HBM, "
                                "converted in the front kernel; bit-identical to the fc32 path on the converted floats (tests/test_rx_sc16_gpu.py)",
                        "value": sc_total / (sc_ms_max * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": sc_ms_max / sc_steps,
                        "front_launch_ms": sc_front_ms, "front_hbm_frac": (n * 4.0036) / (sc_front_ms * 1e-3) / 1e9 / peak,
                        "e2e": {"value": sc_e2e_samples / sc_e2e_sec / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": n * 4,
                                "d2h_bytes_per_step": int(rec_bytes), "steps": e2e_steps, "api": "amps_recc_iq_work_sc16"}},
+        "shared_upload": shared,
         "forward": {"metric": "Msamples/s out of the fused forward path (config 3: FOCC + 2 FVC carriers per GPU, data-bit input)",
                     "value": fwd_total / (fwd_ms_max * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": fwd_ms_max,
                     "hbm_frac": 8.03 * fwd_n / (fwd_ms * 1e-3) / 1e9 / peak},
         "gpu_launches": int(launches) * world,
         "bursts_decoded": n_bursts,
+        "parity_checked_bursts": n_checked,
+        "bursts_all_words_valid": n_good,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

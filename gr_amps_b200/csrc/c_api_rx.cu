@@ -128,7 +128,6 @@ static int rx_alloc(amps_recc_iq *h) {
     // two calls' worth: the capture of call k overlaps the front kernel of call k+1
     while (cap < 2 * max_d + (size_t)kSpan + 4096) cap <<= 1;
     h->dmask = (uint32_t)(cap - 1);
-    CK(cudaMalloc(&h->d_stage, ((size_t)h->max_samples + h->gran) * h->isz));
     for (int i = 0; i < 2; ++i) {
         CK(cudaMalloc(&h->d_tail[i], tail_samples(h) * h->isz));
         CK(cudaMemset(h->d_tail[i], 0, tail_samples(h) * h->isz));
@@ -580,6 +579,8 @@ static int rx_work(amps_recc_iq *h, const void *iq_host, size_t nsamples, amps_b
     if (h->dev_carry) return set_error(AMPS_E_STATE, "device-path samples are pending; reset() or keep using submit_dev()");
     CK(cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
+    // the staging buffer of the host path exists from the first host call on (device-resident and batched use never needs it)
+    if (!h->d_stage) CK(cudaMalloc(&h->d_stage, ((size_t)h->max_samples + h->gran) * h->isz));
     if (nsamples)
         CK(cudaMemcpyAsync(h->d_stage + h->carry * h->isz, iq_host, nsamples * h->isz, cudaMemcpyHostToDevice, st));
     const size_t avail = h->carry + nsamples;

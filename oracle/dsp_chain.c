@@ -179,8 +179,16 @@ static void spec_stage2_demod(const float *vr, const float *vi, size_t nq, const
     }
 }
 
+/* blk0: absolute index (mod 2^32) of the stream's 25-sample block that iq[0] starts -- the NCO phase is a function of the
+ * absolute sample index, so a buffer cut out of a longer stream is demodulated exactly as it was inside the stream */
+void orc_rx_chain_f32_at(const float *iq, size_t n, uint32_t fcw, const float *h2, int nh2, uint32_t blk0,
+                         float *y_out, float *d_out);
 void orc_rx_chain_f32(const float *iq, size_t n, uint32_t fcw, const float *h2, int nh2,
                       float *y_out, float *d_out) {
+    orc_rx_chain_f32_at(iq, n, fcw, h2, nh2, 0u, y_out, d_out);
+}
+void orc_rx_chain_f32_at(const float *iq, size_t n, uint32_t fcw, const float *h2, int nh2, uint32_t blk0,
+                         float *y_out, float *d_out) {
     size_t nv = n / D1, nq = nv / 2;
     double cd[NCIC];
     float g[75];
@@ -210,7 +218,7 @@ void orc_rx_chain_f32(const float *iq, size_t n, uint32_t fcw, const float *h2, 
             }
         }
         float Wc, Ws;
-        spec_sincos((uint32_t)((uint32_t)b * fcw25), &Wc, &Ws);
+        spec_sincos((uint32_t)(((uint32_t)b + blk0) * fcw25), &Wc, &Ws);
         for (int j = 0; j < 3; j++) {
             float a1 = pr[j] * Wc, a2 = pr[j] * Ws;
             P[6 * b + 2 * j] = fmaf(-pi_[j], Ws, a1);

@@ -103,6 +103,7 @@ def lib() -> C.CDLL:
     L.orc_nco_fcw.restype = C.c_uint32
     L.orc_rx_chain_f64.argtypes = [f32p, C.c_size_t, C.c_uint32, f32p, C.c_int, f64p, f64p]
     L.orc_rx_chain_f32.argtypes = [f32p, C.c_size_t, C.c_uint32, f32p, C.c_int, f32p, f32p]
+    L.orc_rx_chain_f32_at.argtypes = [f32p, C.c_size_t, C.c_uint32, f32p, C.c_int, C.c_uint32, f32p, f32p]
     L.orc_rx_chain400_f64.argtypes = [f32p, C.c_size_t, C.c_uint32, f32p, C.c_int, f64p, f64p]
     L.orc_rx_chain400_f32.argtypes = [f32p, C.c_size_t, C.c_uint32, f32p, C.c_int, f32p, f32p]
     L.orc_rx_detect.argtypes = [f32p, C.c_size_t, C.POINTER(Burst), C.c_int]
@@ -186,14 +187,15 @@ def iq_f32(x: np.ndarray) -> np.ndarray:
     return x.view(np.float32)
 
 
-def rx_chain_f32(x: np.ndarray, center=-160e3, fs=10e6, taps=None):
+def rx_chain_f32(x: np.ndarray, center=-160e3, fs=10e6, taps=None, blk0=0):
+    """blk0: absolute index of the stream's 25-sample block x[0] starts (the NCO phase follows the absolute sample index)."""
     iq = iq_f32(x)
     n = len(x) - len(x) % 50
     taps = lpf_taps() if taps is None else taps
     fcw = lib().orc_nco_fcw(center, fs)
     y = np.zeros(2 * (n // 50), np.float32)
     d = np.zeros(n // 50, np.float32)
-    lib().orc_rx_chain_f32(ptr(iq, f32p), n, fcw, ptr(taps, f32p), len(taps), ptr(y, f32p), ptr(d, f32p))
+    lib().orc_rx_chain_f32_at(ptr(iq, f32p), n, fcw, ptr(taps, f32p), len(taps), blk0 & 0xFFFFFFFF, ptr(y, f32p), ptr(d, f32p))
     return y.view(np.complex64), d
 
 
@@ -268,14 +270,38 @@ class MmTiming:
         return out[:n]
 
 
-def cpu_baseline_run(x: np.ndarray, threads: int, reps: int, center=-160e3, fs=10e6):
+_native = None
+
+
+def native_lib():
+    """The oracle sources rebuilt -O3 -march=native ON THIS MACHINE, for the CPU-baseline legs of
+    bench.py only; falls back to the portable parity build if the compiler is not there.  Returns (CDLL, flags string)."""
+    global _native
+    if _native is not None:
+        return _native
+    path = os.path.join(ORACLE_DIR, "liboracle_native.so")
+    try:
+        subprocess.check_call(["make", "-s", "-B", "-C", ORACLE_DIR, "liboracle_native.so"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        L = C.CDLL(path)
+        flags = "-O3 -march=native -ffp-contract=off"
+    except Exception:
+        L = lib()
+        flags = "-O2 -march=x86-64-v3 -ffp-contract=off (portable parity build: native rebuild failed)"
+    L.orc_cpu_baseline_run.argtypes = [f32p, C.c_size_t, C.c_uint32, f32p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    L.orc_cpu_baseline_run.restype = C.c_double
+    _native = (L, flags)
+    return _native
+
+
+def cpu_baseline_run(x: np.ndarray, threads: int, reps: int, center=-160e3, fs=10e6, native=False):
     """Time the fp32 oracle chain (+detect+decode) on `threads` host threads; returns (seconds, bursts)."""
     iq = iq_f32(x)
     n = len(x) - len(x) % 50
     taps = lpf_taps()
     fcw = lib().orc_nco_fcw(center, fs)
     nb = C.c_int(0)
-    sec = lib().orc_cpu_baseline_run(ptr(iq, f32p), n, fcw, ptr(taps, f32p), len(taps), threads, reps, C.byref(nb))
+    L = native_lib()[0] if native else lib()
+    sec = L.orc_cpu_baseline_run(ptr(iq, f32p), n, fcw, ptr(taps, f32p), len(taps), threads, reps, C.byref(nb))
     return sec, nb.value
 
 

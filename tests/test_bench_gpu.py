@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_bench_prints_one_json_line_with_the_contract_keys():
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "3", "--warmup", "3", "--periods", "8", "--no-cpu"],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "3", "--warmup", "3", "--periods", "8", "--no-cpu", "--sustain", "0.3", "--shared-carriers", "4"],
                        capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-3000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
@@ -27,3 +27,10 @@ def test_bench_prints_one_json_line_with_the_contract_keys():
     assert e["value"] < d["value"]                           # host link in the timed region
     assert d["sc16_input"]["e2e"]["h2d_bytes_per_step"] == 4 * d["config"]["samples_per_step_per_gpu"]
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    # the parity gate inside the run: the bursts of the host-noise periods were compared with the oracle's, blob for blob
+    assert d["parity_checked_bursts"] >= 3 * 3 - 2 and d["bursts_decoded"] >= 3 * 8 - 2
+    assert d["config"]["snr_db"] == ["inf", 30, 15]
+    assert rf["fp32_tflops"] > 0 and rf["sustained"]["seconds"] >= 0.1 and rf["sustained"]["bursts_equal_to_oracle"] > 0
+    assert e["h2d_ceiling"]["value"] >= 0.8 * e["value"]
+    sh = d["shared_upload"]
+    assert sh["carriers_per_gpu"] == 4 and sh["value"] > 2.0 * d["sc16_input"]["e2e"]["value"]
