@@ -148,6 +148,7 @@ void orc_rx_chain_f64(const float *iq, size_t n, uint32_t fcw, const float *h2, 
                       double *y_out, double *d_out);
 void orc_rx_chain_f32(const float *iq, size_t n, uint32_t fcw, const float *h2, int nh2,
                       float *y_out, float *d_out);
+void orc_quad_demod(const float *iq, size_t n, float *d32, double *d64);   /* quadrature_demod_cf alone: kernel-spec f32 and libm f64 */
 void orc_rx_chain_f32_at(const float *iq, size_t n, uint32_t fcw, const float *h2, int nh2, uint32_t blk0,
                          float *y_out, float *d_out);   /* the same for a buffer that starts at absolute block blk0 of its stream */
 /* native 400 kS/s front end (the reference's own rate): NCO -> lpf_taps /2 -> quadrature demod */

@@ -154,6 +154,13 @@ static float spec_atan2(float y, float x) {
     return a;
 }
 
+/* arg(y conj(p)) in the kernel's operation order */
+static float spec_qdemod(float yr, float yi, float pr, float pi_) {
+    float zr = fmaf(yi, pi_, yr * pr);
+    float zi = fmaf(yi, pr, -(yr * pi_));
+    return spec_atan2(zi, zr);
+}
+
 /* stage 2 + demod of the fp32 kernel-spec chain: y[q] = E + O (FMA chains over even / odd taps, k ascending),
  * d[q] = atan2_spec(Im, Re) of y[q] conj(y[q-1]); shared by the 10 MS/s and the native 400 kS/s front ends */
 static void spec_stage2_demod(const float *vr, const float *vi, size_t nq, const float *h2, int nh2, float *y_out, float *d_out) {
@@ -172,10 +179,22 @@ static void spec_stage2_demod(const float *vr, const float *vi, size_t nq, const
         }
         float yr = er + orr, yi = ei + oi;
         if (y_out) { y_out[2 * q] = yr; y_out[2 * q + 1] = yi; }
-        float zr = fmaf(yi, pi_, yr * pr);
-        float zi = fmaf(yi, pr, -(yr * pi_));
-        if (d_out) d_out[q] = spec_atan2(zi, zr);
+        if (d_out) d_out[q] = spec_qdemod(yr, yi, pr, pi_);
         pr = yr; pi_ = yi;
+    }
+}
+
+/* quadrature_demod_cf on its own (gain applied in the caller's precision), zero history: the f32 flavour is the kernel's
+ * operation order (spec_qdemod), the f64 one is atan2 -- what GNU Radio's qa_quadrature_demod.py vector is held against */
+void orc_quad_demod(const float *iq, size_t n, float *d32, double *d64) {
+    float pr = 0, pi_ = 0;
+    double qr = 0, qi = 0;
+    for (size_t i = 0; i < n; i++) {
+        float yr = iq[2 * i], yi = iq[2 * i + 1];
+        if (d32) d32[i] = spec_qdemod(yr, yi, pr, pi_);
+        double zr = (double)yr * qr + (double)yi * qi, zi = (double)yi * qr - (double)yr * qi;
+        if (d64) d64[i] = (zr == 0.0 && zi == 0.0) ? 0.0 : atan2(zi, zr);
+        pr = yr; pi_ = yi; qr = yr; qi = yi;
     }
 }
 
