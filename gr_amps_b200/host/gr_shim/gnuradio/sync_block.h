@@ -3,6 +3,8 @@
 // message_port_pub of the sender; GNU Radio queues it to the receiver's thread -- same order per
 // port, which is all gr-amps relies on).  Used only where the real <gnuradio/sync_block.h> is absent.
 #pragma once
+#include "../boost_standin.h"
+#include <gnuradio/attributes.h>
 #include <pmt/pmt.h>
 
 #include <complex>
@@ -22,7 +24,7 @@ namespace gr {
 
 class io_signature {
 public:
-    typedef std::shared_ptr<io_signature> sptr;
+    typedef boost::shared_ptr<io_signature> sptr;
     static sptr make(int min_streams, int max_streams, int sizeof_item) {
         sptr s(new io_signature());
         s->d_min = min_streams; s->d_max = max_streams; s->d_size = sizeof_item;
@@ -74,10 +76,16 @@ public:
     block(const std::string &name, io_signature::sptr in, io_signature::sptr out) : basic_block(name, in, out) {}
     void consume_each(int n) { d_consumed += n; }
     long nitems_consumed() const { return d_consumed; }
+    // scheduler hints (recorded; the QA driver honours them the way the GNU Radio scheduler would)
+    void set_max_noutput_items(int m) { d_max_noutput = m; }
+    int max_noutput_items() const { return d_max_noutput; }
+    void set_output_multiple(int m) { d_output_multiple = m; }
+    int output_multiple() const { return d_output_multiple; }
     virtual void forecast(int, gr_vector_int &) {}
     virtual int general_work(int noutput_items, gr_vector_int &, gr_vector_const_void_star &, gr_vector_void_star &) { return noutput_items; }
 private:
     long d_consumed = 0;
+    int d_max_noutput = 0, d_output_multiple = 1;
 };
 
 class sync_block : public block {
@@ -94,5 +102,5 @@ inline void msg_connect(basic_block &src, const std::string &out_port, basic_blo
 }  // namespace gr
 
 namespace gnuradio {
-template <class T> std::shared_ptr<T> get_initial_sptr(T *p) { return std::shared_ptr<T>(p); }
+template <class T> boost::shared_ptr<T> get_initial_sptr(T *p) { return boost::shared_ptr<T>(p); }     // GNU Radio 3.7: boost::shared_ptr
 }

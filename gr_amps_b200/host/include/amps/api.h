@@ -1,7 +1,8 @@
-// api.h -- export macro, as include/amps/api.h:6-10 of the reference
+// api.h -- export macro, as include/amps/api.h:4-10 of the reference
 #pragma once
-#if defined(__GNUC__)
-#define AMPS_API __attribute__((visibility("default")))
+#include <gnuradio/attributes.h>
+#ifdef gnuradio_amps_EXPORTS
+#  define AMPS_API __GR_ATTR_EXPORT
 #else
-#define AMPS_API
+#  define AMPS_API __GR_ATTR_IMPORT
 #endif

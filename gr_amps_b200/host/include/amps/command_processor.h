@@ -16,13 +16,12 @@
 #include <amps/api.h>
 #include <gnuradio/block.h>
 
-#include <memory>
 
 namespace gr { namespace amps {
 
 class AMPS_API command_processor : virtual public gr::block {
 public:
-    typedef std::shared_ptr<command_processor> sptr;      // boost::shared_ptr under a GNU Radio 3.7 build (gr_shim maps it)
+    typedef boost::shared_ptr<command_processor> sptr;     // GNU Radio 3.7's block pointer type (include/amps/focc.h:24 of the reference)
     static sptr make();
 };
 

@@ -12,7 +12,7 @@
 namespace gr { namespace amps {
 class AMPS_API forward_iq : virtual public gr::sync_block {
 public:
-    typedef std::shared_ptr<forward_iq> sptr;
+    typedef boost::shared_ptr<forward_iq> sptr;     // GNU Radio 3.7's block pointer type (include/amps/focc.h:24 of the reference)
     static sptr make(bool aggressive_registration, int device = 0);
 };
 }}

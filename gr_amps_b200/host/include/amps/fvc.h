@@ -5,7 +5,7 @@
 namespace gr { namespace amps {
 class AMPS_API fvc : virtual public gr::sync_block {
 public:
-    typedef std::shared_ptr<fvc> sptr;
+    typedef boost::shared_ptr<fvc> sptr;     // GNU Radio 3.7's block pointer type (include/amps/focc.h:24 of the reference)
     static sptr make(unsigned long symrate);
 };
 }}

@@ -5,7 +5,7 @@
 namespace gr { namespace amps {
 class AMPS_API recc : virtual public gr::sync_block {
 public:
-    typedef std::shared_ptr<recc> sptr;
+    typedef boost::shared_ptr<recc> sptr;     // GNU Radio 3.7's block pointer type (include/amps/focc.h:24 of the reference)
     static sptr make();
 };
 }}

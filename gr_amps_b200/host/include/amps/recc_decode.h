@@ -5,7 +5,7 @@
 namespace gr { namespace amps {
 class AMPS_API recc_decode : virtual public gr::block {
 public:
-    typedef std::shared_ptr<recc_decode> sptr;
+    typedef boost::shared_ptr<recc_decode> sptr;     // GNU Radio 3.7's block pointer type (include/amps/focc.h:24 of the reference)
     static sptr make();
 };
 }}

@@ -9,7 +9,7 @@
 namespace gr { namespace amps {
 class AMPS_API recc_iq : virtual public gr::sync_block {
 public:
-    typedef std::shared_ptr<recc_iq> sptr;
+    typedef boost::shared_ptr<recc_iq> sptr;     // GNU Radio 3.7's block pointer type (include/amps/focc.h:24 of the reference)
     // mm_timing: symbol timing by the reference graph's clock_recovery_mm_ff -> binary_slicer_fb -> amps.recc tail
     // (AMPS_RX_TIMING_MM) instead of the feed-forward trigger detector
     // sc16: the input stream is interleaved int16 I,Q (item size 4: the USRP's wire format, uhd stream_args cpu_format

@@ -21,6 +21,26 @@ static void warn(int status, const char *what) {
     if (status != AMPS_OK) std::fprintf(stderr, "gr-amps(b200) %s: %s\n", what, amps_b200_last_error());
 }
 
+// (first, first + 1, ...) = nwords blobs of 28 bytes each, copied into one buffer.  The reference asserts nwords == len - 2
+// (lib/focc_impl.cc:527, compiled out in its Release build); a malformed tuple is dropped with a warning here.
+static bool words_from_tuple(pmt::pmt_t msg, size_t first, long nwords, size_t max_extra, std::vector<uint8_t> &w, const char *what) {
+    const size_t len = pmt::length(msg);
+    if (nwords < 0 || nwords > 4096 || first + (size_t)nwords > len || len > first + (size_t)nwords + max_extra) {
+        std::fprintf(stderr, "gr-amps(b200) %s: malformed message (%ld words announced, %zu elements): dropped\n", what, nwords, len);
+        return false;
+    }
+    w.resize((size_t)28 * (size_t)nwords);
+    for (long i = 0; i < nwords; i++) {
+        pmt::pmt_t blob = pmt::tuple_ref(msg, first + (size_t)i);
+        if (!pmt::is_blob(blob) || pmt::blob_length(blob) != 28) {
+            std::fprintf(stderr, "gr-amps(b200) %s: word %ld is not a 28-byte blob: message dropped\n", what, i);
+            return false;
+        }
+        std::memcpy(&w[(size_t)28 * (size_t)i], pmt::blob_data(blob), 28);
+    }
+    return true;
+}
+
 // ------------------------------------------------------------------ focc (lib/focc_impl.cc)
 focc::sptr focc::make(unsigned long symrate, bool aggressive_registration) {
     return gnuradio::get_initial_sptr(new focc_impl(symrate, aggressive_registration));
@@ -29,24 +49,25 @@ focc_impl::focc_impl(unsigned long symrate, bool aggressive_registration)
     : gr::sync_block("focc", gr::io_signature::make(0, 0, 0), gr::io_signature::make(1, 1, sizeof(unsigned char))), d_h(NULL) {
     must(amps_focc_create(symrate, aggressive_registration ? 1 : 0, 0, &d_h), "focc");
     message_port_register_in(pmt::mp("focc_words"));                                   // lib/focc_impl.cc:127-130
-    set_msg_handler(pmt::mp("focc_words"), [this](pmt::pmt_t m) { this->focc_words_message(m); });
+    set_msg_handler(pmt::mp("focc_words"), boost::bind(&focc_impl::focc_words_message, this, _1));
 }
 focc_impl::~focc_impl() { amps_focc_destroy(d_h); }
 void focc_impl::focc_words_message(pmt::pmt_t msg) {                                   // lib/focc_impl.cc:521-563
     if (!pmt::is_tuple(msg) || pmt::length(msg) < 3) return;
     const long stream = pmt::to_long(pmt::tuple_ref(msg, 0));
     const long nwords = pmt::to_long(pmt::tuple_ref(msg, 1));
-    std::vector<uint8_t> w((size_t)28 * (size_t)nwords);
-    for (long i = 0; i < nwords; i++) {
-        pmt::pmt_t blob = pmt::tuple_ref(msg, 2 + (size_t)i);
-        if (pmt::blob_length(blob) != 28) return;
-        std::memcpy(&w[(size_t)28 * (size_t)i], pmt::blob_data(blob), 28);
-    }
+    std::vector<uint8_t> w;
+    if (!words_from_tuple(msg, 2, nwords, 0, w, "focc_words")) return;
+    boost::mutex::scoped_lock lock(d_mutex);                                            // lib/focc_impl.cc:567
     warn(amps_focc_push_words(d_h, stream, w.data(), nwords), "focc_words");
 }
 int focc_impl::work(int noutput_items, gr_vector_const_void_star &, gr_vector_void_star &output_items) {
     int produced = 0;
-    warn(amps_focc_work(d_h, static_cast<uint8_t *>(output_items[0]), noutput_items, &produced), "focc work");
+    boost::mutex::scoped_lock lock(d_mutex);                                            // lib/focc_impl.cc:573
+    if (amps_focc_work(d_h, static_cast<uint8_t *>(output_items[0]), noutput_items, &produced) != AMPS_OK) {
+        warn(AMPS_E_CUDA, "focc work");
+        return WORK_DONE;                                                               // a dead device ends the flowgraph; it does not emit garbage
+    }
     return produced;      // <= one burst, possibly 0, -1 (WORK_DONE) when noutput_items < 1 (lib/focc_impl.cc:590-593,630-632)
 }
 
@@ -56,7 +77,7 @@ fvc_impl::fvc_impl(unsigned long symrate)
     : gr::sync_block("fvc", gr::io_signature::make(0, 0, 0), gr::io_signature::make(1, 1, sizeof(unsigned char))), d_h(NULL) {
     must(amps_fvc_create(symrate, 0, &d_h), "fvc");
     message_port_register_in(pmt::mp("fvc_words"));                                    // lib/fvc_impl.cc:62-66
-    set_msg_handler(pmt::mp("fvc_words"), [this](pmt::pmt_t m) { this->fvc_words_message(m); });
+    set_msg_handler(pmt::mp("fvc_words"), boost::bind(&fvc_impl::fvc_words_message, this, _1));
     message_port_register_out(pmt::mp("command_out"));
 }
 fvc_impl::~fvc_impl() { amps_fvc_destroy(d_h); }
@@ -64,15 +85,22 @@ void fvc_impl::fvc_words_message(pmt::pmt_t msg) {                              
     if (!pmt::is_tuple(msg) || pmt::length(msg) < 2) return;
     const size_t len = pmt::length(msg);
     const long nwords = pmt::to_long(pmt::tuple_ref(msg, 0));
-    std::vector<uint8_t> w((size_t)28 * (size_t)nwords);
-    for (long i = 0; i < nwords; i++) std::memcpy(&w[(size_t)28 * (size_t)i], pmt::blob_data(pmt::tuple_ref(msg, 1 + (size_t)i)), 28);
+    std::vector<uint8_t> w;
+    if (!words_from_tuple(msg, 1, nwords, 1, w, "fvc_words")) return;                   // (+ the optional trailing uint64 timer)
     const bool has_timer = len > (size_t)(1 + nwords);
     const uint64_t timer = has_timer ? pmt::to_uint64(pmt::tuple_ref(msg, 1 + (size_t)nwords)) : 0;
+    boost::mutex::scoped_lock lock(d_mutex);
     warn(amps_fvc_push_words(d_h, w.data(), nwords, has_timer ? 1 : 0, timer), "fvc_words");
 }
 int fvc_impl::work(int noutput_items, gr_vector_const_void_star &, gr_vector_void_star &output_items) {
     int produced = 0, off = 0;
-    warn(amps_fvc_work(d_h, static_cast<uint8_t *>(output_items[0]), noutput_items, &produced, &off), "fvc work");
+    {
+        boost::mutex::scoped_lock lock(d_mutex);
+        if (amps_fvc_work(d_h, static_cast<uint8_t *>(output_items[0]), noutput_items, &produced, &off) != AMPS_OK) {
+            warn(AMPS_E_CUDA, "fvc work");
+            return WORK_DONE;
+        }
+    }
     if (off) {                                                                          // lib/fvc_impl.cc:163-171
         const char *m = "fvc off";
         message_port_pub(pmt::mp("command_out"), pmt::cons(pmt::make_dict(), pmt::init_u8vector(std::strlen(m), (const uint8_t *)m)));
@@ -93,12 +121,16 @@ void recc_impl::on_blob(const uint8_t *blob, void *self) {
 }
 int recc_impl::work(int noutput_items, gr_vector_const_void_star &input_items, gr_vector_void_star &) {
     if (noutput_items < 1) return 0;                                                   // :98-101
-    warn(amps_recc_work(d_h, static_cast<const uint8_t *>(input_items[0]), noutput_items, &recc_impl::on_blob, this), "recc work");
+    if (amps_recc_work(d_h, static_cast<const uint8_t *>(input_items[0]), noutput_items, &recc_impl::on_blob, this) != AMPS_OK) {
+        warn(AMPS_E_CUDA, "recc work");
+        return WORK_DONE;                                                               // not consumed: nothing is silently dropped
+    }
     consume_each(noutput_items);                                                       // :113
     return 0;                                                                          // :144
 }
 
 // ------------------------------------------------------------------ recc_iq (new sibling block)
+static const uint32_t kMaxItemsPerWork = 1u << 22;
 recc_iq::sptr recc_iq::make(double samp_rate, double center_freq, int device, bool mm_timing, bool sc16) {
     return gnuradio::get_initial_sptr(new recc_iq_impl(samp_rate, center_freq, device, mm_timing, sc16));
 }
@@ -108,9 +140,10 @@ recc_iq_impl::recc_iq_impl(double samp_rate, double center_freq, int device, boo
     amps_recc_iq_params p;
     std::memset(&p, 0, sizeof p);
     p.samp_rate = samp_rate; p.center_freq = center_freq; p.device = device;
-    p.max_samples = 1u << 22;                      // the scheduler never hands a block more than this at once
+    p.max_samples = kMaxItemsPerWork;
     p.flags = (mm_timing ? AMPS_RX_TIMING_MM : 0u) | (sc16 ? AMPS_RX_INPUT_SC16 : 0u);
     must(amps_recc_iq_create(&p, &d_h), "recc_iq");
+    set_max_noutput_items((int)kMaxItemsPerWork);  // the handle's buffers are sized for it: the scheduler never hands the block more at once
     message_port_register_out(pmt::mp("bursts"));
 }
 recc_iq_impl::~recc_iq_impl() { amps_recc_iq_destroy(d_h); }
@@ -119,11 +152,23 @@ void recc_iq_impl::on_burst(const amps_burst *b, void *self) {
 }
 int recc_iq_impl::work(int noutput_items, gr_vector_const_void_star &input_items, gr_vector_void_star &) {
     if (noutput_items < 1) return 0;
-    // gr_complex is std::complex<float>: interleaved re, im -- exactly what the ABI takes
-    if (d_sc16)
-        warn(amps_recc_iq_work_sc16(d_h, static_cast<const int16_t *>(input_items[0]), (size_t)noutput_items, &recc_iq_impl::on_burst, this), "recc_iq work");
-    else
-        warn(amps_recc_iq_work(d_h, static_cast<const float *>(input_items[0]), (size_t)noutput_items, &recc_iq_impl::on_burst, this), "recc_iq work");
+    // gr_complex is std::complex<float>: interleaved re, im -- exactly what the ABI takes.  A scheduler that ignores
+    // set_max_noutput_items is served in slices.
+    size_t done = 0;
+    while (done < (size_t)noutput_items) {
+        const size_t n = std::min((size_t)noutput_items - done, (size_t)kMaxItemsPerWork);
+        const int st = d_sc16
+            ? amps_recc_iq_work_sc16(d_h, static_cast<const int16_t *>(input_items[0]) + 2 * done, n, &recc_iq_impl::on_burst, this)
+            : amps_recc_iq_work(d_h, static_cast<const float *>(input_items[0]) + 2 * done, n, &recc_iq_impl::on_burst, this);
+        if (st == AMPS_E_OVERFLOW) {
+            warn(st, "recc_iq work (candidate list overflow: bursts may have been missed; the stream goes on)");
+        } else if (st != AMPS_OK) {
+            warn(st, "recc_iq work");
+            // samples must not disappear silently: report what was taken so far and end the flowgraph
+            return done ? (int)done : WORK_DONE;
+        }
+        done += n;
+    }
     return noutput_items;
 }
 
@@ -133,7 +178,7 @@ recc_decode_impl::recc_decode_impl()
     : gr::block("recc_decode", gr::io_signature::make(0, 0, 0), gr::io_signature::make(0, 0, 0)), d_h(NULL) {
     must(amps_recc_decode_create(0, &d_h), "recc_decode");
     message_port_register_in(pmt::mp("bursts"));                                       // lib/recc_decode_impl.cc:38-46
-    set_msg_handler(pmt::mp("bursts"), [this](pmt::pmt_t m) { this->bursts_message(m); });
+    set_msg_handler(pmt::mp("bursts"), boost::bind(&recc_decode_impl::bursts_message, this, _1));
     message_port_register_out(pmt::mp("focc_words"));
     message_port_register_out(pmt::mp("fvc_words"));
     message_port_register_out(pmt::mp("audio_mute"));
@@ -193,7 +238,7 @@ command_processor::sptr command_processor::make() { return gnuradio::get_initial
 command_processor_impl::command_processor_impl()
     : gr::block("command_processor", gr::io_signature::make(0, 0, 0), gr::io_signature::make(0, 0, 0)) {
     message_port_register_in(pmt::mp("commands"));                                     // :41-49
-    set_msg_handler(pmt::mp("commands"), [this](pmt::pmt_t m) { this->commands_message(m); });
+    set_msg_handler(pmt::mp("commands"), boost::bind(&command_processor_impl::commands_message, this, _1));
     message_port_register_out(pmt::mp("focc_words"));
     message_port_register_out(pmt::mp("debug_output"));
     message_port_register_out(pmt::mp("fvc_words"));
@@ -271,12 +316,13 @@ forward_iq_impl::forward_iq_impl(bool aggressive_registration, int device)
     p.out_scale = 0.5f;                                                                  // :1367
     p.max_samples = (uint32_t)(kMaxBitsPerWork * kSamplesPerBit);
     must(amps_fwd_create(&p, &d_fwd), "forward_iq/fwd");
+    set_output_multiple(kSamplesPerBit);            // whole data bits per call
     message_port_register_in(pmt::mp("focc_words"));
-    set_msg_handler(pmt::mp("focc_words"), [this](pmt::pmt_t m) { this->focc_words_message(m); });
+    set_msg_handler(pmt::mp("focc_words"), boost::bind(&forward_iq_impl::focc_words_message, this, _1));
     message_port_register_in(pmt::mp("fvc_words"));
-    set_msg_handler(pmt::mp("fvc_words"), [this](pmt::pmt_t m) { this->fvc_words_message(m); });
+    set_msg_handler(pmt::mp("fvc_words"), boost::bind(&forward_iq_impl::fvc_words_message, this, _1));
     message_port_register_in(pmt::mp("fvc_mute"));
-    set_msg_handler(pmt::mp("fvc_mute"), [this](pmt::pmt_t m) { this->d_fvc_mute = pmt::to_bool(m); });
+    set_msg_handler(pmt::mp("fvc_mute"), boost::bind(&forward_iq_impl::fvc_mute_message, this, _1));
     message_port_register_out(pmt::mp("command_out"));
 }
 forward_iq_impl::~forward_iq_impl() { amps_fwd_destroy(d_fwd); amps_fvc_destroy(d_fvc); amps_focc_destroy(d_focc); }
@@ -284,26 +330,32 @@ forward_iq_impl::~forward_iq_impl() { amps_fwd_destroy(d_fwd); amps_fvc_destroy(
 void forward_iq_impl::focc_words_message(pmt::pmt_t msg) {
     if (!pmt::is_tuple(msg) || pmt::length(msg) < 3) return;
     const long stream = pmt::to_long(pmt::tuple_ref(msg, 0)), nwords = pmt::to_long(pmt::tuple_ref(msg, 1));
-    std::vector<uint8_t> w((size_t)28 * (size_t)nwords);
-    for (long i = 0; i < nwords; i++) std::memcpy(&w[(size_t)28 * (size_t)i], pmt::blob_data(pmt::tuple_ref(msg, 2 + (size_t)i)), 28);
+    std::vector<uint8_t> w;
+    if (!words_from_tuple(msg, 2, nwords, 0, w, "forward_iq focc_words")) return;
+    boost::mutex::scoped_lock lock(d_mutex);
     warn(amps_focc_push_words(d_focc, stream, w.data(), nwords), "forward_iq focc_words");
 }
 void forward_iq_impl::fvc_words_message(pmt::pmt_t msg) {
     if (!pmt::is_tuple(msg) || pmt::length(msg) < 2) return;
     const size_t len = pmt::length(msg);
     const long nwords = pmt::to_long(pmt::tuple_ref(msg, 0));
-    std::vector<uint8_t> w((size_t)28 * (size_t)nwords);
-    for (long i = 0; i < nwords; i++) std::memcpy(&w[(size_t)28 * (size_t)i], pmt::blob_data(pmt::tuple_ref(msg, 1 + (size_t)i)), 28);
+    std::vector<uint8_t> w;
+    if (!words_from_tuple(msg, 1, nwords, 1, w, "forward_iq fvc_words")) return;
     const bool has_timer = len > (size_t)(1 + nwords);
+    boost::mutex::scoped_lock lock(d_mutex);
     warn(amps_fvc_push_words(d_fvc, w.data(), nwords, has_timer ? 1 : 0, has_timer ? pmt::to_uint64(pmt::tuple_ref(msg, 1 + (size_t)nwords)) : 0),
          "forward_iq fvc_words");
 }
+void forward_iq_impl::fvc_mute_message(pmt::pmt_t msg) {
+    boost::mutex::scoped_lock lock(d_mutex);
+    d_fvc_mute = pmt::to_bool(msg);
+}
 
 int forward_iq_impl::work(int noutput_items, gr_vector_const_void_star &, gr_vector_void_star &output_items) {
-    // whole bits only (a real GNU Radio build calls set_output_multiple(1000) in the constructor)
     size_t nbits = (size_t)noutput_items / kSamplesPerBit;
     if (nbits > kMaxBitsPerWork) nbits = kMaxBitsPerWork;
     if (nbits == 0) return 0;
+    boost::mutex::scoped_lock lock(d_mutex);
     for (int c = 0; c < 3; c++) d_bits[c].assign(nbits, 0xFF);
     warn(amps_focc_generate_bits(d_focc, d_bits[0].data(), nbits), "forward_iq focc bits");
     // the FVC source runs whether or not its leg is muted (as the fvc block does behind mute_xx)
@@ -319,7 +371,10 @@ int forward_iq_impl::work(int noutput_items, gr_vector_const_void_star &, gr_vec
     }
     if (d_fvc_mute) std::fill(d_bits[1].begin(), d_bits[1].end(), (uint8_t)0xFF);
     const uint8_t *bits[3] = {d_bits[0].data(), d_bits[1].data(), d_bits[2].data()};
-    warn(amps_fwd_work_bits(d_fwd, bits, nbits, static_cast<float *>(output_items[0])), "forward_iq work");
+    if (amps_fwd_work_bits(d_fwd, bits, nbits, static_cast<float *>(output_items[0])) != AMPS_OK) {
+        warn(AMPS_E_CUDA, "forward_iq work");
+        return WORK_DONE;
+    }
     return (int)(nbits * kSamplesPerBit);
 }
 

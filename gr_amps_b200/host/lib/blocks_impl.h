@@ -20,8 +20,12 @@ enum focc_streams { STREAM_A = 1, STREAM_B = 2, STREAM_BOTH = 3 };     // lib/am
 #define GLOBAL_DCC_SHORT 0
 #define GLOBAL_SCC 1
 
+// One C-ABI handle = one thread at a time.  GNU Radio runs a block's handlers and its work() on the block's own thread; the
+// mutexes make the blocks safe under the stronger condition the reference also guards against (lib/focc_impl.cc:567,573):
+// a handler entered from another thread while work() runs.
 class focc_impl : public focc {
     amps_focc *d_h;
+    boost::mutex d_mutex;
 public:
     focc_impl(unsigned long symrate, bool aggressive_registration);
     ~focc_impl();
@@ -31,6 +35,7 @@ public:
 
 class fvc_impl : public fvc {
     amps_fvc *d_h;
+    boost::mutex d_mutex;
 public:
     explicit fvc_impl(unsigned long symrate);
     ~fvc_impl();
@@ -81,12 +86,14 @@ class forward_iq_impl : public forward_iq {
     amps_fvc *d_fvc;
     amps_fwd *d_fwd;
     bool d_fvc_mute;                       // the reference graph starts with the FVC leg muted (grc/ampsbs.grc:1601)
+    boost::mutex d_mutex;
     std::vector<uint8_t> d_bits[3];
 public:
     forward_iq_impl(bool aggressive_registration, int device);
     ~forward_iq_impl();
     void focc_words_message(pmt::pmt_t msg);
     void fvc_words_message(pmt::pmt_t msg);
+    void fvc_mute_message(pmt::pmt_t msg);
     int work(int noutput_items, gr_vector_const_void_star &input_items, gr_vector_void_star &output_items);
 };
 

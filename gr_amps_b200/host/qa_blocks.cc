@@ -7,6 +7,8 @@
 //   qa_blocks loop <iq.bin> <nsamples> <chunk> <focc_bytes> <out_prefix> [mm]
 //   qa_blocks fwd <nsym> <out.bin> [voice]
 //   qa_blocks cmd <text> [<text> ...]          (host only: command_processor, no GPU needed)
+//   qa_blocks threads <total_bytes> <nmsgs> <out.bin>   (focc_words posted from a second thread while work() runs)
+//   qa_blocks badmsg                           (malformed focc_words / fvc_words tuples are dropped, not crashed on)
 #include <amps/focc.h>
 #include <amps/fvc.h>
 #include <amps/recc.h>
@@ -22,7 +24,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <atomic>
+#include <chrono>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace gr::amps;
@@ -253,6 +258,77 @@ static int run_txblock(int argc, char **argv) {
 }
 
 // command_processor wired as grc/ampsbs.grc:4404-4412: every command is one PDU on "commands"
+// The one real concurrency hazard of the block surface: another block's thread delivering focc_words while the scheduler
+// thread is inside work() (lib/focc_impl.cc:567-580 guards its queue for that).  Thread B posts nmsgs two-word messages
+// (stream BOTH; word i carries its own number), thread A keeps calling work(); the stream must stay a valid sequence of
+// frames with every injected word in it exactly once, in order (checked by tests/test_host_gpu.py).
+static int run_threads(int argc, char **argv) {
+    if (argc < 5) return 2;
+    const size_t total = std::strtoull(argv[2], NULL, 10);
+    const int nmsgs = std::atoi(argv[3]);
+    focc::sptr blk = focc::make(100000, false);
+    std::atomic<bool> failed(false);
+    std::atomic<size_t> produced(0);
+    std::thread poster([&]() {
+        for (int i = 0; i < nmsgs && !failed; i++) {
+            unsigned char w[2][28];
+            for (int k = 0; k < 2; k++) {
+                const unsigned v = 0x5A00000u | (unsigned)(2 * i + k);               // 28 bits, MSB first
+                for (int b = 0; b < 28; b++) w[k][b] = (unsigned char)((v >> (27 - b)) & 1u);
+            }
+            blk->dispatch_msg("focc_words", pmt::make_tuple(pmt::from_long(3), pmt::from_long(2), pmt::mp(w[0], 28), pmt::mp(w[1], 28)));
+            // pace the posts over the first half of the run (a frame is 4630 bytes, a message two frames, and only the 15 filler
+            // slots of a 19-frame superframe carry queued frames): the queue has drained when the run ends
+            while (!failed && produced.load() < (size_t)(i + 1) * (total / (size_t)(2 * nmsgs + 4))) std::this_thread::sleep_for(std::chrono::microseconds(50));
+        }
+    });
+    std::vector<unsigned char> out, buf(1 << 16);
+    gr_vector_const_void_star in;
+    gr_vector_void_star outs(1);
+    unsigned long long lcg = 99;
+    while (out.size() < total) {
+        lcg = lcg * 6364136223846793005ull + 1442695040888963407ull;
+        int n = 1 + (int)((lcg >> 33) % 3000);
+        if ((size_t)n > total - out.size()) n = (int)(total - out.size());
+        outs[0] = buf.data();
+        const int r = blk->work(n, in, outs);
+        if (r < 0) { failed = true; break; }
+        out.insert(out.end(), buf.begin(), buf.begin() + r);
+        produced = out.size();
+    }
+    produced = total * 2;
+    poster.join();
+    if (failed) return 3;
+    std::ofstream(argv[4], std::ios::binary).write(reinterpret_cast<const char *>(out.data()), (std::streamsize)out.size());
+    std::printf("{\"bytes\": %zu, \"messages\": %d}\n", out.size(), nmsgs);
+    return 0;
+}
+
+// malformed word messages: dropped with a warning (the reference asserts, lib/focc_impl.cc:523-532), never read past the tuple
+static int run_badmsg() {
+    focc::sptr f = focc::make(100000, false);
+    fvc::sptr v = fvc::make(100000);
+    unsigned char w[28] = {0};
+    pmt::pmt_t good = pmt::mp(w, 28), shortb = pmt::mp(w, 5);
+    f->dispatch_msg("focc_words", pmt::make_tuple(pmt::from_long(3), pmt::from_long(7), good));            // announces 7, carries 1
+    f->dispatch_msg("focc_words", pmt::make_tuple(pmt::from_long(3), pmt::from_long(-2), good));           // negative count
+    f->dispatch_msg("focc_words", pmt::make_tuple(pmt::from_long(3), pmt::from_long(1), shortb));          // short blob
+    f->dispatch_msg("focc_words", pmt::make_tuple(pmt::from_long(3), pmt::from_long(1), good, good));      // more elements than words
+    v->dispatch_msg("fvc_words", pmt::make_tuple(pmt::from_long(3), good));
+    v->dispatch_msg("fvc_words", pmt::make_tuple(pmt::from_long(-1), good));
+    v->dispatch_msg("fvc_words", pmt::make_tuple(pmt::from_long(1), shortb));
+    // nothing was queued: the FOCC stream is the plain superframe, the FVC is still idle (buffer untouched)
+    std::vector<unsigned char> a(4630), b(64, 0x77);
+    gr_vector_const_void_star in;
+    gr_vector_void_star outs(1);
+    outs[0] = b.data();
+    const int r = v->work(64, in, outs);
+    bool untouched = true;
+    for (size_t i = 0; i < b.size(); i++) untouched = untouched && b[i] == 0x77;
+    std::printf("{\"fvc_work\": %d, \"fvc_buffer_untouched\": %s}\n", r, untouched ? "true" : "false");
+    return 0;
+}
+
 static int run_cmd(int argc, char **argv) {
     command_processor::sptr cp = command_processor::make();
     probe pr;
@@ -276,6 +352,8 @@ int main(int argc, char **argv) {
         if (!std::strcmp(argv[1], "fwd")) return run_fwd(argc, argv);
         if (!std::strcmp(argv[1], "txblock")) return run_txblock(argc, argv);
         if (!std::strcmp(argv[1], "cmd")) return run_cmd(argc, argv);
+        if (!std::strcmp(argv[1], "threads")) return run_threads(argc, argv);
+        if (!std::strcmp(argv[1], "badmsg")) return run_badmsg();
     } catch (const std::exception &e) {
         std::fprintf(stderr, "qa_blocks: %s\n", e.what());
         return 10;

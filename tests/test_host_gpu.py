@@ -127,3 +127,50 @@ def test_forward_iq_block(oracle, tmp_path):
     assert err <= 1e-6, err
     lines = [json.loads(l) for l in out.splitlines() if l.startswith("{")]
     assert lines == [{"port": "command_out", "text": "fvc off"}] * offs and offs == 1
+
+
+# ------------------------------------------------------------------ concurrency and malformed messages
+def focc_frames(stream_bytes, sps=5):
+    """FOCC byte stream (+1 = 0x01, -1 = 0xFF, sps bytes per half-symbol) -> list of (word A info bits, word B info bits, ok):
+    frame = [BI][dotting 1010101010][BI][sync 11100010010] + 5 x (A, B) words, each 4 x ([BI] + 10 bits) (lib/focc_impl.cc:178-218);
+    Manchester: bit 0 -> (+1, -1), bit 1 -> (-1, +1) (lib/amps_packet.h:52-70)."""
+    hs = np.asarray(stream_bytes)[::sps]
+    bits = (hs.reshape(-1, 2)[:, 0] == 0xFF).astype(np.uint8)
+    frames = []
+    for f in range(len(bits) // 463):
+        b = bits[463 * f:463 * (f + 1)]
+        ok = list(b[1:11]) == [1, 0] * 5 and list(b[12:23]) == [1, 1, 1, 0, 0, 0, 1, 0, 0, 1, 0]
+        words = []
+        for w in range(10):
+            seg = b[23 + 44 * w:23 + 44 * (w + 1)].reshape(4, 11)[:, 1:].reshape(-1)       # drop the busy/idle bit in front of each 10
+            words.append(seg)
+        a, bb = words[0::2], words[1::2]
+        ok = ok and all(np.array_equal(a[0], x) for x in a) and all(np.array_equal(bb[0], x) for x in bb)
+        frames.append((a[0], bb[0], ok))
+    return frames
+
+
+def test_focc_words_from_another_thread_while_work_runs(oracle, tmp_path):
+    """Messages posted from a second thread while the scheduler thread is inside focc::work(): the stream stays a valid
+    sequence of frames, every word is BCH-consistent, and the 2 x nmsgs injected words appear exactly once, in order."""
+    nmsgs, total = 40, 130 * 4630
+    out = tmp_path / "thr.bin"
+    run(["threads", total, nmsgs, out], tmp_path)
+    frames = focc_frames(np.fromfile(out, np.uint8))
+    assert len(frames) == 130 and all(ok for _, _, ok in frames)
+    injected = []
+    for a, b, _ in frames:
+        for w in (a, b):
+            assert np.array_equal(oracle.bch_encode_40_28(w[:28]), w)               # parity of every transmitted word
+        v = int("".join(map(str, a[:28])), 2)
+        if (v >> 20) == 0x5A:
+            assert np.array_equal(a, b)                                              # stream BOTH: the word on A and on B
+            injected.append(v & 0xFFFFF)
+    assert injected == list(range(2 * nmsgs))
+
+
+def test_malformed_word_messages_are_dropped(tmp_path):
+    out = subprocess.run([QA, "badmsg"], cwd=tmp_path, capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert json.loads(out.stdout.strip().splitlines()[-1]) == {"fvc_work": 64, "fvc_buffer_untouched": True}
+    assert out.stderr.count("dropped") == 7
