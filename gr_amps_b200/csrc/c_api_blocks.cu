@@ -47,6 +47,16 @@ static int recc_reserve(amps_recc *h, size_t total, int nchunks) {
     return AMPS_OK;
 }
 
+static int recc_init(amps_recc *h) {
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CK(cudaMalloc(&h->d_state, sizeof(ReccCompatState)));
+    CK(cudaMemset(h->d_state, 0, sizeof(ReccCompatState)));            // zero-initialised buffer (:75)
+    const int32_t none = -1;
+    CK(cudaMemcpy(&h->d_state->pending, &none, sizeof none, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&h->d_nblobs, sizeof(int)));
+    return AMPS_OK;
+}
+
 extern "C" int amps_recc_create(int device, amps_recc **out) {
     if (!out) return set_error(AMPS_E_INVAL, "null argument");
     *out = nullptr;
@@ -55,12 +65,8 @@ extern "C" int amps_recc_create(int device, amps_recc **out) {
     amps_recc *h = new (std::nothrow) amps_recc();
     if (!h) return set_error(AMPS_E_NOMEM, "out of host memory");
     h->device = device;
-    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    CK(cudaMalloc(&h->d_state, sizeof(ReccCompatState)));
-    CK(cudaMemset(h->d_state, 0, sizeof(ReccCompatState)));            // zero-initialised buffer (:75)
-    const int32_t none = -1;
-    CK(cudaMemcpy(&h->d_state->pending, &none, sizeof none, cudaMemcpyHostToDevice));
-    CK(cudaMalloc(&h->d_nblobs, sizeof(int)));
+    st = recc_init(h);
+    if (st != AMPS_OK) { amps_recc_destroy(h); return st; }           // (the error text set by the failing call survives the clean-up)
     *out = h;
     return AMPS_OK;
 }
@@ -123,6 +129,8 @@ static const int kEphemeralPool = 4096;
 struct amps_focc {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaEvent_t ev_gen = nullptr;          // recorded behind the last generate on whatever stream it ran
+    bool gen_pending = false;
     unsigned sps = 1;
     int nsuper = 0;
     std::vector<bool> filler;              // per superframe slot
@@ -167,17 +175,9 @@ static int focc_upload_frame(amps_focc *h, int id, const uint8_t *wa, const uint
     return AMPS_OK;
 }
 
-extern "C" int amps_focc_create(unsigned long symrate, int aggressive_registration, int device, amps_focc **out) {
-    if (!out) return set_error(AMPS_E_INVAL, "null argument");
-    *out = nullptr;
-    if (symrate < 20000) return set_error(AMPS_E_INVAL, "symrate must be >= 20000 (samples_per_sym = symrate / 20000)");
-    int st = select_device(device);
-    if (st != AMPS_OK) return st;
-    amps_focc *h = new (std::nothrow) amps_focc();
-    if (!h) return set_error(AMPS_E_NOMEM, "out of host memory");
-    h->device = device;
-    h->sps = (unsigned)(symrate / 20000);
+static int focc_init(amps_focc *h, int aggressive_registration) {
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_gen, cudaEventDisableTiming));
     // superframe (lib/focc_impl.cc:383-406 / :420-466)
     std::vector<Word28> words;
     const int halves = aggressive_registration ? 2 : 1;
@@ -194,9 +194,24 @@ extern "C" int amps_focc_create(unsigned long symrate, int aggressive_registrati
     CK(cudaMalloc(&h->d_slots, (size_t)(h->nsuper + kEphemeralPool) * kFoccFrameBits));
     for (int i = 0; i < h->nsuper; ++i) {
         int rc = focc_upload_frame(h, i, words[(size_t)i].data(), words[(size_t)i].data());
-        if (rc != AMPS_OK) { amps_focc_destroy(h); return rc; }
+        if (rc != AMPS_OK) return rc;
     }
     h->frame_idx = 0; h->cur_id = 0; h->bit = 0; h->off = 0; h->at_end = false;
+    return AMPS_OK;
+}
+
+extern "C" int amps_focc_create(unsigned long symrate, int aggressive_registration, int device, amps_focc **out) {
+    if (!out) return set_error(AMPS_E_INVAL, "null argument");
+    *out = nullptr;
+    if (symrate < 20000) return set_error(AMPS_E_INVAL, "symrate must be >= 20000 (samples_per_sym = symrate / 20000)");
+    int st = select_device(device);
+    if (st != AMPS_OK) return st;
+    amps_focc *h = new (std::nothrow) amps_focc();
+    if (!h) return set_error(AMPS_E_NOMEM, "out of host memory");
+    h->device = device;
+    h->sps = (unsigned)(symrate / 20000);
+    st = focc_init(h, aggressive_registration);
+    if (st != AMPS_OK) { amps_focc_destroy(h); return st; }
     *out = h;
     return AMPS_OK;
 }
@@ -206,6 +221,7 @@ extern "C" int amps_focc_destroy(amps_focc *h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->ev_gen) cudaEventDestroy(h->ev_gen);
     cudaFree(h->d_slots); cudaFree(h->d_sched); cudaFree(h->d_out);
     delete h;
     return AMPS_OK;
@@ -221,13 +237,16 @@ extern "C" int amps_focc_push_words(amps_focc *h, long stream, const uint8_t *wo
     if (!h || nwords < 0 || (nwords && !words28)) return set_error(AMPS_E_INVAL, "bad argument");
     if (stream < 1 || stream > 3) return set_error(AMPS_E_INVAL, "stream must be 1 (A), 2 (B) or 3 (BOTH)");
     CK(cudaSetDevice(h->device));
-    if ((long)h->queue.size() + nwords > kEphemeralPool) return set_error(AMPS_E_OVERFLOW, "too many queued FOCC frames");
+    // one slot stays reserved: the frame that was popped and is being transmitted (cur_id) is not in the queue any more
+    if ((long)h->queue.size() + nwords >= kEphemeralPool) return set_error(AMPS_E_OVERFLOW, "too many queued FOCC frames");
+    // a slot about to be rewritten may still be read by the last generate, which ran on the CALLER's stream
+    if (h->gen_pending) { CK(cudaEventSynchronize(h->ev_gen)); h->gen_pending = false; }
+    CK(cudaStreamSynchronize(h->stream));
     const Word28 fill = control_filler_word();
     for (long i = 0; i < nwords; ++i) {                                 // one ephemeral frame per word (:529-562)
         const uint8_t *w = words28 + 28 * i;
         const int id = h->nsuper + h->pool_next;
         h->pool_next = (h->pool_next + 1) % kEphemeralPool;
-        CK(cudaStreamSynchronize(h->stream));                           // the slot may still be read by an async generate
         int rc = focc_upload_frame(h, id, stream == 2 ? fill.data() : w, stream == 1 ? fill.data() : w);
         if (rc != AMPS_OK) return rc;
         h->queue.push_back(id);
@@ -271,6 +290,8 @@ static int focc_emit(amps_focc *h, unsigned long long first, unsigned long long 
     }
     CK(cudaMemcpyAsync(h->d_sched, h->h_sched.data(), sizeof(int) * h->h_sched.size(), cudaMemcpyHostToDevice, st));
     CKL(launch_focc_bytes(h->d_slots, h->d_sched, first, n, h->sps, h->busy_idle, d_out, st));
+    CK(cudaEventRecord(h->ev_gen, st));
+    h->gen_pending = true;
     return AMPS_OK;
 }
 
@@ -333,6 +354,8 @@ extern "C" int amps_focc_generate_bits_dev(amps_focc *h, void *d_out, size_t nbi
     }
     CK(cudaMemcpyAsync(h->d_sched, h->h_sched.data(), sizeof(int) * h->h_sched.size(), cudaMemcpyHostToDevice, st));
     CKL(launch_focc_bits(h->d_slots, h->d_sched, first / two, nbits, h->busy_idle, static_cast<uint8_t *>(d_out), st));
+    CK(cudaEventRecord(h->ev_gen, st));
+    h->gen_pending = true;
     return AMPS_OK;
 }
 
@@ -386,7 +409,8 @@ extern "C" int amps_fvc_create(unsigned long symrate, int device, amps_fvc **out
     if (!h) return set_error(AMPS_E_NOMEM, "out of host memory");
     h->device = device;
     h->sps = (unsigned)(symrate / 20000);
-    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    const cudaError_t ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (ce != cudaSuccess) { delete h; return set_cuda_error(ce, "cudaStreamCreateWithFlags"); }
     *out = h;
     return AMPS_OK;
 }

@@ -510,21 +510,6 @@ __device__ __forceinline__ void channel_filter(const float (&h2)[300], const flo
     for (int r = 0; r < kR; ++r) y[r] = add2(E[r], O[r]);
 }
 
-// the last of those kR outputs alone (q = kR*c0 + kR-1), same two chains in the same order: what a segment's warm-up needs
-__device__ __forceinline__ float2 channel_filter_last(const float (&h2)[300], const float4 *vcol) {
-    float2 E = make_float2(0.f, 0.f), O = make_float2(0.f, 0.f);
-#pragma unroll
-    for (int j = 0; j <= 149; ++j) {
-        const int s = j;                               // r = kR-1: j = r - (kR-1) + s
-        const int row = (kR - 1 - s) & (kR - 1);
-        const int cs  = floor_div(kR - 1 - s, kR);
-        const float4 pr = vcol[row * kRowLen + cs];
-        E = fma2(splat(h2[2 * j]), make_float2(pr.x, pr.y), E);
-        if (j >= 1) O = fma2(splat(h2[2 * j - 1]), make_float2(pr.z, pr.w), O);
-    }
-    return add2(E, O);
-}
-
 // store one 400 kS/s sample (index relative to the start of the current pass, negative = history) into the pair/row layout
 __device__ __forceinline__ void store_v(PassSmem *ps, int mrel, float2 v) {
     const int P   = mrel >> 1;                                   // pair index (floor)
@@ -543,6 +528,10 @@ __device__ __forceinline__ void finish_pass(const float (&h2)[300], const PassOu
     float2 y[kR];
 #pragma unroll
     for (int r = 0; r < kR; ++r) y[r] = make_float2(0.f, 0.f);
+    // (warm-up: one thread computes the kR outputs in front of the segment and keeps the last.  A one-output variant of the
+    // filter would be 4x shorter, but as a second unrolled block it more than doubles the kernel's registers -- a CTA of the
+    // search / capture kernels then no longer fits next to two of these -- and as a real call it reads the taps through
+    // generic loads: measured 4 us slower per segment.)
     if (warm ? t == 0 : t < nact) {
         const int c0 = warm ? -1 : t;
         channel_filter(h2, &ps->v[0][c0 + kPorchCols], y);
@@ -629,11 +618,30 @@ __device__ __forceinline__ SegGroups seg_groups(unsigned long long qs, unsigned 
     return g;
 }
 
+// next call's tail = logical samples [units*kUnit - kHist, carry + nchunk): the CTAs that touch the channel copy a slice each
+// (saves a memcpy node between consecutive front kernels)
+template <typename In>
+__device__ __forceinline__ void copy_tail(const RxChan &ch, const RxDeal &d, uint32_t cta, uint32_t cbase, uint32_t cend, int t) {
+    const uint32_t k0 = deal_owner(d, cbase), nsl = deal_owner(d, cend - 1) - k0 + 1u;
+    const long first = (long)ch.units * kUnit - kHist;
+    const uint32_t len = (uint32_t)((long)ch.carry + (long)ch.nchunk - first);
+    const uint32_t per = (len + nsl - 1u) / nsl;
+    const uint32_t lo = (cta - k0) * per, hi = lo + per < len ? lo + per : len;
+    const In *tl = static_cast<const In *>(ch.tail) + (long)kHist;
+    const In *ck = static_cast<const In *>(ch.chunk) - (long)ch.carry;
+    In *dst = static_cast<In *>(ch.tail_out);
+    for (uint32_t i = lo + (uint32_t)t; i < hi; i += kTB) {
+        const long L = first + (long)i;
+        dst[i] = L < (long)ch.carry ? tl[L] : ck[L];
+    }
+}
+
 // One segment = tiles [ta, tb) of channel c (tile j = units 3j .. 3j+2, the channel's last tile may be shorter), preceded by
 // kWarmTiles tiles of history.  `it` counts the tiles this CTA has consumed (TMA ring position / mbarrier phase).
 template <typename In, bool kUnitScale, int kMaxChan, bool kFused>
 __device__ __forceinline__ void run_segment(const RxFrontParamsT<kMaxChan> &p, const RxChan &ch, FrontSmem<In> *sm,
-                                            uint32_t ta, uint32_t tb, uint32_t &it, int t) {
+                                            uint32_t ta, uint32_t tb, uint32_t &it, int t, const RxDeal &dl, uint32_t cta,
+                                            uint32_t cbase, uint32_t cend) {
     const int  ntiles = (int)(tb - ta) + kWarmTiles;
     const long tj0    = (long)ta - kWarmTiles;                          // channel tile index of tile i = 0
     const uint32_t U  = ch.units;
@@ -643,6 +651,7 @@ __device__ __forceinline__ void run_segment(const RxFrontParamsT<kMaxChan> &p, c
         const uint32_t left = (U - (uint32_t)kTileUnits * (uint32_t)tj) * (uint32_t)kUnitBlk;
         return left < (uint32_t)kTB ? left : (uint32_t)kTB;
     };
+    const In *chunk0 = static_cast<const In *>(ch.chunk) - (long)ch.carry;      // logical sample 0 of the chunk (virtual)
     PassOut o;
     o.dring = ch.dring; o.hring = ch.hring; o.ydump = ch.ydump; o.dmask = ch.dmask; o.hw = (kFused && ch.search) ? sm->hw : nullptr;
     const uint32_t useg = ((uint32_t)kTileUnits * tb < U ? (uint32_t)kTileUnits * tb : U) - (uint32_t)kTileUnits * ta;   // units of the segment
@@ -658,6 +667,8 @@ __device__ __forceinline__ void run_segment(const RxFrontParamsT<kMaxChan> &p, c
         for (int s = 0; s < kStages && s < ntiles; ++s)
             issue_tile<In>(ch, sm->in[(it + s) % kStages], &sm->full[(it + s) % kStages], (tj0 + s) * (long)kTile, tile_blocks(s) * kD1);
     }
+    // (with the first tiles on their way) this CTA's slice of the next call's history
+    copy_tail<In>(ch, dl, cta, cbase, cend, t);
 
     for (int i = 0; i < ntiles; ++i, ++it) {
         const int s = (int)(it % kStages);
@@ -689,8 +700,18 @@ __device__ __forceinline__ void run_segment(const RxFrontParamsT<kMaxChan> &p, c
         sm->pb[par][0][t] = P1;
         sm->pb[par][1][t] = P2;
         __syncthreads();                                   // partials visible; in[s] fully consumed
-        if (t == 0 && i + kStages < ntiles)
-            issue_tile<In>(ch, sm->in[s], &sm->full[s], (tj0 + i + kStages) * (long)kTile, tile_blocks(i + kStages) * kD1);
+        if (t == 0 && i + kStages < ntiles) {
+            // the common case by the shortest route (this thread's warp is the one every tile waits for): a whole tile that lies
+            // in the chunk; the seam with the tail buffer and the segment's last (possibly short) tile take the general one
+            const int j = i + kStages;
+            const long L0 = (tj0 + j) * (long)kTile;
+            if (L0 >= (long)ch.carry && j != ntiles - 1) {
+                mbar_expect_tx(&sm->full[s], kTile * (uint32_t)sizeof(In));
+                tma_load_1d(sm->in[s], chunk0 + L0, kTile * (uint32_t)sizeof(In), &sm->full[s]);
+            } else {
+                issue_tile<In>(ch, sm->in[s], &sm->full[s], L0, tile_blocks(j) * kD1);
+            }
+        }
 
         // ---- v[m] = (P0[m] + P1[m-1]) + P2[m-2], stored into the pair/row layout
         const float2 q1 = t >= 1 ? sm->pb[par][0][t - 1] : sm->pb[prv][0][kTB - 1];
@@ -832,24 +853,6 @@ __device__ __forceinline__ void finish_segment(const RxFrontParamsT<kMaxChan> &p
     RX_PROF(p, 7);
 }
 
-// next call's tail = logical samples [units*kUnit - kHist, carry + nchunk): the CTAs that touch the channel copy a slice each
-// (saves a memcpy node between consecutive front kernels)
-template <typename In>
-__device__ __forceinline__ void copy_tail(const RxChan &ch, const RxDeal &d, uint32_t cta, uint32_t cbase, uint32_t cend, int t) {
-    const uint32_t k0 = deal_owner(d, cbase), nsl = deal_owner(d, cend - 1) - k0 + 1u;
-    const long first = (long)ch.units * kUnit - kHist;
-    const uint32_t len = (uint32_t)((long)ch.carry + (long)ch.nchunk - first);
-    const uint32_t per = (len + nsl - 1u) / nsl;
-    const uint32_t lo = (cta - k0) * per, hi = lo + per < len ? lo + per : len;
-    const In *tl = static_cast<const In *>(ch.tail) + (long)kHist;
-    const In *ck = static_cast<const In *>(ch.chunk) - (long)ch.carry;
-    In *dst = static_cast<In *>(ch.tail_out);
-    for (uint32_t i = lo + (uint32_t)t; i < hi; i += kTB) {
-        const long L = first + (long)i;
-        dst[i] = L < (long)ch.carry ? tl[L] : ck[L];
-    }
-}
-
 template <typename In, int kMinCtas, bool kUnitScale, int kMaxChan, bool kFused>
 __global__ void __launch_bounds__(kTB, kMinCtas) rx_front_kernel(const __grid_constant__ RxFrontParamsT<kMaxChan> p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -869,8 +872,7 @@ __global__ void __launch_bounds__(kTB, kMinCtas) rx_front_kernel(const __grid_co
         // one channel: everything about the channel is a compile-time offset into the parameters
         const RxChan &ch = p.ch[0];
         const uint32_t lo = deal_lo(dl, cta), hi = deal_lo(dl, cta + 1);
-        copy_tail<In>(ch, dl, cta, 0u, dl.Tt, t);
-        run_segment<In, kUnitScale, kMaxChan, kFused>(p, ch, sm, lo, hi, it, t);
+        run_segment<In, kUnitScale, kMaxChan, kFused>(p, ch, sm, lo, hi, it, t, dl, cta, 0u, dl.Tt);
         finish_segment<In, kMaxChan, kFused>(p, ch, sm, 0u, cta, lo, hi, t);
     } else {
         const uint32_t gt_lo = deal_lo(dl, cta), gt_hi = deal_lo(dl, cta + 1);
@@ -880,8 +882,7 @@ __global__ void __launch_bounds__(kTB, kMinCtas) rx_front_kernel(const __grid_co
             const RxChan &ch = p.ch[c];
             const uint32_t cbase = p.tile_cum[c], cend = p.tile_cum[c + 1];
             const uint32_t g1 = gt_hi < cend ? gt_hi : cend;
-            copy_tail<In>(ch, dl, cta, cbase, cend, t);
-            run_segment<In, kUnitScale, kMaxChan, kFused>(p, ch, sm, g0 - cbase, g1 - cbase, it, t);
+            run_segment<In, kUnitScale, kMaxChan, kFused>(p, ch, sm, g0 - cbase, g1 - cbase, it, t, dl, cta, cbase, cend);
             finish_segment<In, kMaxChan, kFused>(p, ch, sm, c, cta, g0 - cbase, g1 - cbase, t);
             g0 = g1;
         }

@@ -227,3 +227,29 @@ def test_bch_validity_matches_oracle_on_random_error_patterns(capi, oracle):
     for bi in range(40):
         r = oracle.recc_decode(blobs[bi])
         assert list(out[bi].valid) == list(r.valid) and list(out[bi].valid_repeat) == list(r.valid_repeat)
+
+
+def test_focc_queue_capacity_keeps_the_frame_in_flight(capi, oracle):
+    """The pool of ephemeral frames holds 4096; one slot stays reserved for the frame that has been popped and is being
+    transmitted, so 4095 words can be queued, the 4096th is refused (AMPS_E_OVERFLOW) -- and a device-side generate that is
+    still reading a slot is waited for before the slot is rewritten (the stream stays the oracle's)."""
+    torch = pytest.importorskip("torch")
+    f, o = capi.Focc(20000, False), oracle.Focc(20000, False)
+    w = lambda i: np.array([int(c) for c in format(0x5A00000 | i, "028b")], np.uint8)
+    many = np.concatenate([w(i) for i in range(4095)])
+    f.push_words(3, many)
+    o.push_words(3, many.reshape(-1, 28))
+    with pytest.raises(capi.AmpsError) as e:
+        f.push_words(3, w(4095))
+    assert e.value.status == -6
+    # drain part of the queue through the device-resident entry point, push again right behind it, keep generating
+    n1 = 300 * 926
+    t = torch.empty(n1, dtype=torch.uint8, device="cuda")
+    f.generate_dev(t.data_ptr(), n1, torch.cuda.current_stream().cuda_stream)
+    more = np.concatenate([w(5000 + i) for i in range(200)])
+    f.push_words(3, more)                                  # rewrites pool slots the generate above may still be reading
+    o_first = o.generate(n1, chunk=4096)
+    o.push_words(3, more.reshape(-1, 28))
+    assert np.array_equal(t.cpu().numpy(), o_first)
+    n2 = 6000 * 926
+    assert np.array_equal(f.generate(n2), o.generate(n2, chunk=1 << 16))
