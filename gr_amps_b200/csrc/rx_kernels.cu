@@ -673,8 +673,10 @@ __device__ __forceinline__ void run_segment(const RxFrontParamsT<kMaxChan> &p, c
     for (int i = 0; i < ntiles; ++i, ++it) {
         const int s = (int)(it % kStages);
         mbar_wait(&sm->full[s], (it / kStages) & 1u);
+#ifdef AMPS_RX_PROF_TILES                                  // (two compares per tile: only in a build made for tools/front_phases.py)
         if (i == 0) RX_PROF(p, 1);
         if (i == kWarmTiles) RX_PROF(p, 2);
+#endif
 
         // ---- stage 1: NCO rotate + CIC^3 polyphase partial sums over this thread's 25 samples
         const In *xin = sm->in[s] + kD1 * t;
@@ -690,8 +692,8 @@ __device__ __forceinline__ void run_segment(const RxFrontParamsT<kMaxChan> &p, c
             P1 = fma2(splat(p.g[49 - k]), u, P1);
             if (74 - k < kNCic) P2 = fma2(splat(p.g[74 - k]), u, P2);
         }
-        const long     blk  = (tj0 + i) * (long)kTB + t;                 // block index relative to logical sample 0
-        const uint32_t babs = ch.blk_base + (uint32_t)blk;
+        // absolute block index (mod 2^32): blocks of logical sample 0 + (tile index relative to it) * kTB + t
+        const uint32_t babs = ch.blk_base + (uint32_t)((int)tj0 + i) * (uint32_t)kTB + (uint32_t)t;
         const float2   W    = sincos_phase(babs * ch.fcw25);
         P0 = cmul(P0, W);
         P1 = cmul(P1, W);

@@ -9,6 +9,7 @@
 //   qa_blocks cmd <text> [<text> ...]          (host only: command_processor, no GPU needed)
 //   qa_blocks threads <total_bytes> <nmsgs> <out.bin>   (focc_words posted from a second thread while work() runs)
 //   qa_blocks badmsg                           (malformed focc_words / fvc_words tuples are dropped, not crashed on)
+//   qa_blocks batch <iq.bin> <nsamples> <K> <chunk>   (C ABI: K carriers on one uploaded buffer, amps_recc_iq_batch_work_shared)
 #include <amps/focc.h>
 #include <amps/fvc.h>
 #include <amps/recc.h>
@@ -24,6 +25,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <string>
@@ -329,6 +331,46 @@ static int run_badmsg() {
     return 0;
 }
 
+// K carriers (-160 kHz + 30 kHz * k) demodulating ONE uploaded buffer through the batched C-ABI entry points; prints the bursts
+// per channel as JSON lines (channel, demod_index, MIN) -- compared with stand-alone handles / the oracle by the tests, and a
+// compact all-kernels scenario for compute-sanitizer.
+struct batch_probe { std::vector<std::string> lines; };
+static void on_batch_burst(int channel, const amps_burst *b, void *user) {
+    char buf[160];
+    std::snprintf(buf, sizeof buf, "{\"channel\": %d, \"demod_index\": %llu, \"min\": \"%.10s\", \"valid\": %d}", channel,
+                  (unsigned long long)b->demod_index, b->decoded.min, (int)(b->decoded.valid[0] + b->decoded.valid[1] + b->decoded.valid[2] +
+                  b->decoded.valid[3] + b->decoded.valid[4] + b->decoded.valid[5] + b->decoded.valid[6]));
+    static_cast<batch_probe *>(user)->lines.push_back(buf);
+}
+static int run_batch(int argc, char **argv) {
+    if (argc < 6) return 2;
+    const size_t nsamples = std::strtoull(argv[3], NULL, 10);
+    const int K = std::atoi(argv[4]);
+    const size_t chunk = std::strtoull(argv[5], NULL, 10);
+    std::vector<float> iq(2 * nsamples);
+    std::ifstream f(argv[2], std::ios::binary);
+    f.read(reinterpret_cast<char *>(iq.data()), (std::streamsize)(iq.size() * sizeof(float)));
+    if (!f) { std::fprintf(stderr, "short read of %s\n", argv[2]); return 4; }
+    std::vector<amps_recc_iq *> hs((size_t)K, NULL);
+    for (int k = 0; k < K; k++) {
+        amps_recc_iq_params p;
+        std::memset(&p, 0, sizeof p);
+        p.samp_rate = 10e6; p.center_freq = -160e3 + 30e3 * k; p.device = 0; p.max_samples = (uint32_t)chunk;
+        if (amps_recc_iq_create(&p, &hs[(size_t)k]) != AMPS_OK) { std::fprintf(stderr, "%s\n", amps_b200_last_error()); return 5; }
+    }
+    amps_recc_iq_batch *b = NULL;
+    if (amps_recc_iq_batch_create(hs.data(), K, 0, &b) != AMPS_OK) { std::fprintf(stderr, "%s\n", amps_b200_last_error()); return 6; }
+    batch_probe pr;
+    for (size_t pos = 0; pos < nsamples; pos += chunk) {
+        const size_t n = std::min(chunk, nsamples - pos);
+        if (amps_recc_iq_batch_work_shared(b, iq.data() + 2 * pos, n, &on_batch_burst, &pr) != AMPS_OK) { std::fprintf(stderr, "%s\n", amps_b200_last_error()); return 7; }
+    }
+    for (size_t i = 0; i < pr.lines.size(); i++) std::printf("%s\n", pr.lines[i].c_str());
+    amps_recc_iq_batch_destroy(b);
+    for (int k = 0; k < K; k++) amps_recc_iq_destroy(hs[(size_t)k]);
+    return 0;
+}
+
 static int run_cmd(int argc, char **argv) {
     command_processor::sptr cp = command_processor::make();
     probe pr;
@@ -354,6 +396,7 @@ int main(int argc, char **argv) {
         if (!std::strcmp(argv[1], "cmd")) return run_cmd(argc, argv);
         if (!std::strcmp(argv[1], "threads")) return run_threads(argc, argv);
         if (!std::strcmp(argv[1], "badmsg")) return run_badmsg();
+        if (!std::strcmp(argv[1], "batch")) return run_batch(argc, argv);
     } catch (const std::exception &e) {
         std::fprintf(stderr, "qa_blocks: %s\n", e.what());
         return 10;

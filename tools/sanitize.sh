@@ -18,6 +18,23 @@ open('/tmp/san/n.txt', 'w').write(str(len(x)))
 PY
 N=$(cat /tmp/san/n.txt)
 QA=gr_amps_b200/host/qa_blocks
+if [ "${R2_ONLY:-0}" = "1" ]; then
+  # round 2: the re-dealt front kernel + stand-alone search kernel (default), the fused search (per-pass shared-memory search,
+  # boundary counters between CTAs, in-kernel selection), its sc16 instance, and the batched kernels (4 carriers, one upload)
+  for tool in memcheck racecheck synccheck; do
+    timeout 1500 compute-sanitizer --tool $tool --error-exitcode 9 $QA loop /tmp/san/iq.bin $N 262144 87970 /tmp/san/out > gpurun_out/sanitize_r2_split_$tool.log 2>&1
+    echo "r2 split $tool rc=$? $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' gpurun_out/sanitize_r2_split_$tool.log | tail -1)"
+    AMPS_RX_FUSED=1 timeout 1500 compute-sanitizer --tool $tool --error-exitcode 9 $QA loop /tmp/san/iq.bin $N 262144 87970 /tmp/san/outf > gpurun_out/sanitize_r2_fused_$tool.log 2>&1
+    echo "r2 fused $tool rc=$? $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' gpurun_out/sanitize_r2_fused_$tool.log | tail -1)"
+    AMPS_RX_FUSED=1 timeout 1500 compute-sanitizer --tool $tool --error-exitcode 9 $QA loop /tmp/san/iq.bin $N 99999 87970 /tmp/san/outf16 sc16 > gpurun_out/sanitize_r2_fused_sc16_$tool.log 2>&1
+    echo "r2 fused sc16 $tool rc=$? $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' gpurun_out/sanitize_r2_fused_sc16_$tool.log | tail -1)"
+    timeout 1500 compute-sanitizer --tool $tool --error-exitcode 9 $QA batch /tmp/san/iq.bin $N 4 1000001 > gpurun_out/sanitize_r2_batch_$tool.log 2>&1
+    echo "r2 batch $tool rc=$? $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' gpurun_out/sanitize_r2_batch_$tool.log | tail -1)"
+    AMPS_RX_FUSED=1 timeout 1500 compute-sanitizer --tool $tool --error-exitcode 9 $QA batch /tmp/san/iq.bin $N 4 1000001 > gpurun_out/sanitize_r2_batch_fused_$tool.log 2>&1
+    echo "r2 batch fused $tool rc=$? $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' gpurun_out/sanitize_r2_batch_fused_$tool.log | tail -1)"
+  done
+  exit 0
+fi
 for tool in memcheck racecheck synccheck; do
   # the Manchester-bit fast path (fwd_bits_kernel) through the forward_iq composite block
   timeout 1200 compute-sanitizer --tool $tool --error-exitcode 9 $QA txblock 6000 /tmp/san/tx.bin > gpurun_out/sanitize_txblock_$tool.log 2>&1
