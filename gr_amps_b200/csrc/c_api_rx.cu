@@ -338,6 +338,16 @@ static uint32_t chan_search(amps_recc_iq *h, RxSearchChan &sc, uint32_t par, uin
     return sc.cta_count;
 }
 
+// the M&M tail of a channel
+static void chan_mm(const amps_recc_iq *h, RxMmChan &m, uint32_t par) {
+    m.dring = h->d_dring; m.mm = h->d_mm; m.sym = h->d_sym; m.cs = h->d_compat; m.blobs = h->d_blobs; m.blob_sym_index = h->d_blob_idx;
+    m.state = h->d_state; m.host_pub = h->h_pub; m.total_d = h->total_d; m.dmask = h->dmask; m.sym_cap = h->sym_cap; m.par = par; m.pad = 0;
+}
+static uint32_t mm_capture_ctas(uint64_t outputs) {                      // <= one blob per emulated work() quantum
+    const uint64_t mx = outputs / (8u * (unsigned)kMmQuantum) + 2;
+    return (uint32_t)(mx > (uint64_t)kMaxAccept ? (uint64_t)kMaxAccept : mx);
+}
+
 // bursts one call of `outputs` demodulated samples can make capturable: they are at least kBurstLen apart, +1 for a run
 // that became decidable at the edge, +1 for leftovers of a call that had more than the list holds
 static uint32_t capture_ctas(uint64_t outputs) {
@@ -388,10 +398,11 @@ static int rx_enqueue10(amps_recc_iq *h, const uint8_t *d_chunk, uint32_t nchunk
         if (h->mm_mode) {
             // serial tail: M&M + slicer over everything demodulated so far, amps.recc on the new half-symbols, then
             // one CTA per blob decodes and publishes it
-            CKL(launch_rx_mm(h->d_dring, h->dmask, h->total_d, h->d_mm, h->d_mmtab, h->d_sym, h->sym_cap, h->d_compat, h->d_blobs,
-                             h->d_blob_idx, kMaxAccept, h->d_state, h->h_pub, par, sd));
-            uint64_t mx = (uint64_t)units * kUnitOut / (8u * (unsigned)kMmQuantum) + 2;      // <= one blob per work() quantum
-            nc = (uint32_t)(mx > (uint64_t)kMaxAccept ? (uint64_t)kMaxAccept : mx);
+            static thread_local RxMmParams mp;
+            mp.nchan = 1; mp.max_blobs = kMaxAccept; mp.table = h->d_mmtab;
+            chan_mm(h, mp.ch[0], par);
+            CKL(launch_rx_mm(mp, sd));
+            nc = mm_capture_ctas((uint64_t)units * kUnitOut);
             h->launches += 2;
         }
         if (!h->mm_mode && !h->fused && !h->nosearch) {
@@ -450,10 +461,11 @@ static int rx_enqueue400(amps_recc_iq *h, const uint8_t *d_chunk, uint32_t npass
         cp.nchan = 1;
         uint32_t nc = capture_ctas((uint64_t)npass * kPassOut);
         if (h->mm_mode) {
-            CKL(launch_rx_mm(h->d_dring, h->dmask, h->total_d, h->d_mm, h->d_mmtab, h->d_sym, h->sym_cap, h->d_compat, h->d_blobs,
-                             h->d_blob_idx, kMaxAccept, h->d_state, h->h_pub, par, sd));
-            uint64_t mx = (uint64_t)npass * kPassOut / (8u * (unsigned)kMmQuantum) + 2;
-            nc = (uint32_t)(mx > (uint64_t)kMaxAccept ? (uint64_t)kMaxAccept : mx);
+            static thread_local RxMmParams mp;
+            mp.nchan = 1; mp.max_blobs = kMaxAccept; mp.table = h->d_mmtab;
+            chan_mm(h, mp.ch[0], par);
+            CKL(launch_rx_mm(mp, sd));
+            nc = mm_capture_ctas((uint64_t)npass * kPassOut);
             h->launches += 2;
         } else {
             // search every group whose lookahead is complete, then select (one launch)
@@ -699,9 +711,9 @@ extern "C" int amps_recc_iq_batch_create(amps_recc_iq *const *handles, int count
         const amps_recc_iq *h = handles[i];
         if (!h) return set_error(AMPS_E_INVAL, "null handle in the batch");
         if (h->batch) return set_error(AMPS_E_STATE, "a handle already belongs to a batch");
-        if (h->native400 || h->mm_mode) return set_error(AMPS_E_INVAL, "batches take 10 MS/s feed-forward handles only");
-        if (h->device != h0->device || h->sc16 != h0->sc16 || h->sc16_unit != h0->sc16_unit || h->fused != h0->fused)
-            return set_error(AMPS_E_INVAL, "all handles of a batch must share the device, the input format and AMPS_RX_FUSED_SEARCH");
+        if (h->native400) return set_error(AMPS_E_INVAL, "batches take 10 MS/s handles only");
+        if (h->device != h0->device || h->sc16 != h0->sc16 || h->sc16_unit != h0->sc16_unit || h->fused != h0->fused || h->mm_mode != h0->mm_mode)
+            return set_error(AMPS_E_INVAL, "all handles of a batch must share the device, the input format, the timing mode and AMPS_RX_FUSED_SEARCH");
         if (h->call_no || h->carry || h->dev_carry) return set_error(AMPS_E_STATE, "handles must be fresh (or reset) when they join a batch");
         for (int j = 0; j < i; ++j) if (handles[j] == h) return set_error(AMPS_E_INVAL, "the same handle twice in a batch");
     }
@@ -756,7 +768,9 @@ static int batch_enqueue(amps_recc_iq_batch *b, const void *const *d_iq, const s
     std::vector<uint32_t> cap_grid;
     std::vector<RxSearchParams> srch;
     std::vector<uint32_t> srch_grid;
-    const bool split = !b->ch[0]->fused && !b->ch[0]->nosearch;
+    const bool mm = b->ch[0]->mm_mode;
+    const bool split = !mm && !b->ch[0]->fused && !b->ch[0]->nosearch;
+    std::vector<RxMmParams> mms;
     while (i < K) {
         // next group of up to kMaxBatch channels that have at least one whole unit
         const amps_recc_iq *h0 = b->ch[0];
@@ -766,6 +780,8 @@ static int batch_enqueue(amps_recc_iq_batch *b, const void *const *d_iq, const s
         uint32_t n = 0, tiles = 0, cap_ctas = 0, srch_ctas = 0;
         RxCaptureParams cp;
         RxSearchParams sp;
+        RxMmParams mp;
+        mp.max_blobs = kMaxAccept; mp.table = b->ch[0]->d_mmtab;
         p.tile_cum[0] = 0;
         for (; i < K && n < (uint32_t)kMaxBatch; ++i) {
             amps_recc_iq *h = b->ch[i];
@@ -775,7 +791,8 @@ static int batch_enqueue(amps_recc_iq_batch *b, const void *const *d_iq, const s
             chan_begin(h, p.ch[n], static_cast<const uint8_t *>(d_iq[i]), nchunk, units, par);
             tiles += rx_tiles_of(units);
             p.tile_cum[n + 1] = tiles;
-            const uint32_t nc = capture_ctas((uint64_t)units * kUnitOut);
+            const uint32_t nc = mm ? mm_capture_ctas((uint64_t)units * kUnitOut) : capture_ctas((uint64_t)units * kUnitOut);
+            if (mm) chan_mm(h, mp.ch[n], par);
             chan_capture(h, cp.ch[n], par, cap_ctas, nc);
             cap_ctas += nc;
             if (split) srch_ctas += chan_search(h, sp.ch[n], par, srch_ctas);
@@ -785,17 +802,19 @@ static int batch_enqueue(amps_recc_iq_batch *b, const void *const *d_iq, const s
         p.nchan = n;
         cp.nchan = n;
         const uint32_t grid = rx_make_deal(p.deal, tiles, resident);
-        CKL(launch_rx_front_batch(p, (int)grid, st, b->sc16, b->sc16_unit, !split));
+        CKL(launch_rx_front_batch(p, (int)grid, st, b->sc16, b->sc16_unit, !split && !mm));
         b->launches++;
         caps.push_back(cp);
         cap_grid.push_back(cap_ctas);
         if (split) { sp.nchan = n; srch.push_back(sp); srch_grid.push_back(srch_ctas); }
+        if (mm) { mp.nchan = n; mms.push_back(mp); }
     }
     if (b->timed) { CK(cudaEventRecord(b->ev1[evi], st)); b->ev_count++; }
     CK(cudaEventRecord(b->ev_front, st));
     CK(cudaStreamWaitEvent(sd, b->ev_front, 0));
     for (size_t k = 0; k < caps.size(); ++k) {
         if (split) { CKL(launch_rx_search(srch[k], (int)srch_grid[k], sd)); b->launches++; }
+        if (mm) { CKL(launch_rx_mm(mms[k], sd)); b->launches += 2; }
         CKL(launch_rx_capture(caps[k], (int)cap_grid[k], sd));
         b->launches++;
     }

@@ -1093,9 +1093,15 @@ cudaError_t launch_rx_capture(const RxCaptureParams &p, int grid, cudaStream_t s
 constexpr int kMmStage = 4096;     // demod samples staged per round
 constexpr int kMmSymStage = 512;   // symbols produced per round at most
 
-__global__ void __launch_bounds__(128) rx_mm_kernel(const float *__restrict__ dring, uint32_t dmask, unsigned long long total_d,
-                                                   MmState *st, const float *__restrict__ table, uint8_t *__restrict__ sym_out,
-                                                   unsigned int sym_cap) {
+__global__ void __launch_bounds__(128) rx_mm_kernel(const __grid_constant__ RxMmParams p) {
+    const RxMmChan &c = p.ch[blockIdx.x];                                 // one CTA per channel
+    const float *__restrict__ dring = c.dring;
+    const uint32_t dmask = c.dmask;
+    const unsigned long long total_d = c.total_d;
+    MmState *st = c.mm;
+    const float *__restrict__ table = p.table;
+    uint8_t *__restrict__ sym_out = c.sym;
+    const unsigned int sym_cap = c.sym_cap;
     __shared__ float s_tab[kMmPhases * 8];
     __shared__ float s_d[kMmStage + 8];
     __shared__ uint8_t s_sym[kMmSymStage];
@@ -1161,9 +1167,17 @@ __global__ void __launch_bounds__(128) rx_mm_kernel(const float *__restrict__ dr
 // amps.recc on the symbols the M&M kernel just produced, in work() calls of kMmQuantum bytes (the reference sees the
 // stream in scheduler-sized pieces and searches / publishes at most once per call, lib/recc_impl.cc:115-126), then the
 // bookkeeping select_channel does in the feed-forward mode.
-__global__ void __launch_bounds__(256) rx_mm_recc_kernel(ReccCompatState *cs, const MmState *mm, const uint8_t *__restrict__ sym,
-                                                        uint8_t *blobs, unsigned long long *blob_sym_index, int max_blobs,
-                                                        RxState *state, RxPublished *host_pub, uint32_t par) {
+__global__ void __launch_bounds__(256) rx_mm_recc_kernel(const __grid_constant__ RxMmParams p) {
+    const RxMmChan &c = p.ch[blockIdx.x];
+    ReccCompatState *cs = c.cs;
+    const MmState *mm = c.mm;
+    const uint8_t *__restrict__ sym = c.sym;
+    uint8_t *blobs = c.blobs;
+    unsigned long long *blob_sym_index = c.blob_sym_index;
+    const int max_blobs = p.max_blobs;
+    RxState *state = c.state;
+    RxPublished *host_pub = c.host_pub;
+    const uint32_t par = c.par;
     const unsigned int n = mm->n_new;
     const int nchunks = (int)((n + (unsigned)kMmQuantum - 1u) / (unsigned)kMmQuantum);
     int nb = recc_compat_run(cs, sym, nchunks,
@@ -1182,12 +1196,10 @@ __global__ void __launch_bounds__(256) rx_mm_recc_kernel(ReccCompatState *cs, co
     }
 }
 
-cudaError_t launch_rx_mm(const float *dring, uint32_t dmask, unsigned long long total_d, MmState *mm, const float *table,
-                         uint8_t *sym, unsigned int sym_cap, ReccCompatState *cs, uint8_t *blobs,
-                         unsigned long long *blob_sym_index, int max_blobs, RxState *state, RxPublished *host_pub,
-                         uint32_t par, cudaStream_t st) {
-    rx_mm_kernel<<<1, 128, 0, st>>>(dring, dmask, total_d, mm, table, sym, sym_cap);
-    rx_mm_recc_kernel<<<1, 256, 0, st>>>(cs, mm, sym, blobs, blob_sym_index, max_blobs, state, host_pub, par);
+cudaError_t launch_rx_mm(const RxMmParams &p, cudaStream_t st) {
+    if (p.nchan == 0) return cudaSuccess;
+    rx_mm_kernel<<<p.nchan, 128, 0, st>>>(p);
+    rx_mm_recc_kernel<<<p.nchan, 256, 0, st>>>(p);
     return cudaGetLastError();
 }
 

@@ -216,12 +216,28 @@ cudaError_t launch_rx_search(const RxSearchParams &p, int grid, cudaStream_t st)
 // capture: CTAs [cta_first, cta_first + cta_count) of channel c walk its accepted bursts (stride cta_count): gather the
 // 3374 half-symbols, decode, and stream the record into host_ring[(rec_base + b) % ring_len] (mapped pinned host memory)
 cudaError_t launch_rx_capture(const RxCaptureParams &p, int grid, cudaStream_t st);
-// M&M timing mode: serial clock recovery + slicer over the demod ring up to total_d, then amps.recc on the new
-// half-symbols; leaves state->n_acc[par] blobs (<= max_blobs) for the capture launch
-cudaError_t launch_rx_mm(const float *dring, uint32_t dmask, unsigned long long total_d, MmState *mm, const float *table,
-                         uint8_t *sym, unsigned int sym_cap, ReccCompatState *cs, uint8_t *blobs,
-                         unsigned long long *blob_sym_index, int max_blobs, RxState *state, RxPublished *host_pub,
-                         uint32_t par, cudaStream_t st);
+// M&M timing mode, one CTA per channel and kernel (the recurrences of different channels run side by side): serial clock
+// recovery + slicer over the demod ring up to total_d, then amps.recc on the new half-symbols; leaves state->n_acc[par] blobs
+// (<= max_blobs) for the capture launch
+struct RxMmChan {
+    const float *dring;
+    MmState     *mm;
+    uint8_t     *sym;
+    ReccCompatState *cs;
+    uint8_t     *blobs;
+    unsigned long long *blob_sym_index;
+    RxState     *state;
+    RxPublished *host_pub;
+    unsigned long long total_d;
+    uint32_t     dmask, sym_cap, par, pad;
+};
+struct RxMmParams {
+    uint32_t     nchan;
+    int          max_blobs;
+    const float *table;      // 129 x 8 MMSE interpolator (one per device)
+    RxMmChan     ch[kMaxBatch];
+};
+cudaError_t launch_rx_mm(const RxMmParams &p, cudaStream_t st);
 cudaError_t launch_decode_blobs(const uint8_t *blobs, int nbursts, amps_recc_words *out, cudaStream_t st);
 
 }  // namespace amps

@@ -130,3 +130,42 @@ def test_mm_and_feed_forward_agree_on_clean_bursts(capi, oracle):
     for p, q, hs in zip(ga, gb, hss):
         assert np.array_equal(p.symbols_np(), hs[82:82 + 3374]) and np.array_equal(q.symbols_np(), hs[82:82 + 3374])
     a.close(); b.close()
+
+
+def test_mm_tail_batched_channels(capi, oracle):
+    """The M&M tails of several channels in ONE pair of launches (one CTA per channel walks its recurrence, side by side): three
+    carriers in one wideband buffer, uploaded once; every channel delivers, call by call, what the oracle's tail delivers."""
+    from gr_amps_b200 import multi
+    ks = [0, 3, 6]
+    parts = []
+    for k in ks:
+        c = multi.carrier(k)
+        x, _ = synth.burst_period(synth.origination_words(min10=c.min10), lead=20000 + 5000 * k, snr_db=None, center=c.center_freq)
+        parts.append(x)
+    rng = np.random.default_rng(5)
+    x = (sum(parts) + 0.03 * (rng.standard_normal(N1) + 1j * rng.standard_normal(N1))).astype(np.complex64)
+    hs = [capi.ReccIq(max_samples=N1, center_freq=multi.carrier(k).center_freq, timing_mm=True) for k in ks]
+    b = capi.ReccIqBatch(hs)
+    tails = []
+    for k in ks:
+        _, d = oracle.rx_chain_f32(x, center=multi.carrier(k).center_freq)
+        tails.append(OracleTail(oracle, d))
+    pos, total = 0, [0, 0, 0]
+    for n in (300001, 700000, 555555, N1):
+        n = min(n, N1 - pos)
+        got = b.work_shared(x[pos:pos + n])
+        pos += n
+        for i, h in enumerate(hs):
+            want = tails[i].advance(h.stats()["demod_out"])
+            mine = [g for ch, g in got if ch == i]
+            assert len(mine) == len(want)
+            for g, w in zip(mine, want):
+                assert np.array_equal(g.symbols_np(), w) and words_equal(g.decoded, oracle.recc_decode(w)) == []
+            total[i] += len(mine)
+        if pos >= N1:
+            break
+    assert total == [1, 1, 1]
+    assert b.stats()["kernel_launches"] == 4 * b.stats()["calls"]          # front, M&M, amps.recc, capture -- whatever K is
+    b.close()
+    for h in hs:
+        h.close()
