@@ -614,6 +614,7 @@ def main():
     barrier()
     fwd_n, fwd_ms = measure_fwd(local_rank, 20, 3, bits=True)
     fwd_total, fwd_ms_max = multi.whole_job_throughput(float(fwd_n), fwd_ms, dev)
+    fwd_g_n, fwd_g_ms = measure_fwd(local_rank, 10, 3, bits=False)      # the same carriers from half-symbol bytes (general modulator)
 
     if rank != 0:
         if world > 1:
@@ -668,7 +669,9 @@ def main():
         "shared_upload": shared,
         "forward": {"metric": "Msamples/s out of the fused forward path (config 3: FOCC + 2 FVC carriers per GPU, data-bit input)",
                     "value": fwd_total / (fwd_ms_max * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": fwd_ms_max,
-                    "hbm_frac": 8.03 * fwd_n / (fwd_ms * 1e-3) / 1e9 / peak},
+                    "hbm_frac": 8.03 * fwd_n / (fwd_ms * 1e-3) / 1e9 / peak,
+                    "half_symbol_input": {"kernel": "fwd_fused_kernel (+2 scan kernels): what the unchanged focc / fvc byte blocks feed", "ms_per_step": fwd_g_ms,
+                                          "value_per_gpu": fwd_g_n / (fwd_g_ms * 1e-3) / 1e6, "hbm_frac": 8.03 * fwd_g_n / (fwd_g_ms * 1e-3) / 1e9 / peak}},
         "gpu_launches": int(launches) * world,
         "bursts_decoded": n_bursts,
         "parity_checked_bursts": n_checked,

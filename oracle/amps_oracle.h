@@ -10,9 +10,14 @@
  * processor): PINNED to the reference's own code -- oracle/_ref/libamps_ref.so is gr-amps's unmodified lib/ sources compiled
  * from /root/reference against stand-in GNU Radio / Boost / IT++ headers (oracle/Makefile, oracle/ref_harness.cc), and
  * tests/test_ref_pin_cpu.py requires byte-identical transcripts, live and through tests/golden/ref_vectors.json.
- * Floating paths (dsp_chain.c, mm_timing.c, voice_tx.c): "parity unpinned" -- they restate stock GNU Radio 3.7 blocks
- * whose source is not in the reference tree, from their documented equations (grc/ampsbs.grc gives the parameters); the
- * reference ships no golden vectors and an empty test-suite (reference lib/qa_amps.cc:9-15).
+ * Floating paths (dsp_chain.c, mm_timing.c, voice_tx.c) restate stock GNU Radio 3.7 blocks whose source is not in the
+ * reference tree, from their documented equations (grc/ampsbs.grc gives the parameters); the reference ships no golden
+ * vectors and an empty test-suite (reference lib/qa_amps.cc:9-15).  They are held against (a) an independent numpy/scipy
+ * implementation of the same blocks in GNU Radio's own structure (tests/scipy_chain.py, tests/test_independent_chain_*.py)
+ * and (b) GNU Radio's own QA known answers for firdes.low_pass, quadrature_demod_cf and the M&M interpolator's DC gain
+ * (tests/golden/kat_gnuradio_*.json).  Still "parity unpinned": GNU Radio's fast_atan2f table, the rest of its MMSE table,
+ * VOLK's summation order, fm_preemph / pfb.arb_resampler of the voice leg, and IT++'s BCH decoder (restated, not linked).
+ * The checker itself runs clean under -fsanitize=address,undefined (selftest.c, `make selftest_asan`).
  *
  * All citations are relative to /root/reference/.
  */

@@ -433,3 +433,20 @@ def test_voice_leg_on_the_references_own_audio(oracle):
     h1 = abs((b[0] + b[1] * z1) / (1 + a[1] * z1))
     # (a phase step of k*y per 16 kS/s sample is a deviation of k*y*fs/2pi scaled by sinc-like pi f/fs / sin(pi f/fs) ~ 1.006 at 1 kHz)
     assert abs(dev / (8000.0 * 0.1 * h1) - 1.0) < 0.03
+
+
+def test_oracle_is_clean_under_asan_and_ubsan():
+    """The checker itself under -fsanitize=address,undefined: every oracle routine through a seeded scenario (oracle/selftest.c:
+    word builders, BCH, FOCC/FVC sources with injections, amps.recc under random chunkings, decode + responses on real and
+    garbage blobs, the float chains at both rates, detection, M&M tail, forward chain, voice leg)."""
+    import os
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle")
+    subprocess.check_call(["make", "-s", "-C", d, "selftest_asan"])
+    r = subprocess.run([os.path.join(d, "selftest_asan")], capture_output=True, text=True, timeout=300,
+                       env=dict(os.environ, ASAN_OPTIONS="detect_leaks=1:abort_on_error=0", UBSAN_OPTIONS="print_stacktrace=1"))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "0 failed checks" in r.stdout and "runtime error" not in r.stderr
