@@ -274,6 +274,7 @@ extern "C" int amps_fwd_submit_dev(amps_fwd *h, const void *const *d_sym, size_t
 }
 
 static int fwd_submit_symbols(amps_fwd *h, const void *const *d_sym, size_t nsym, void *d_out_iq, cudaStream_t st, bool with_voice) {
+    AMPS_NVTX("amps_fwd: submit half-symbols");
     if (nsym == 0) return AMPS_OK;
     if (nsym > h->max_sym) return set_error(AMPS_E_OVERFLOW, "nsym exceeds max_samples / 100");
     if (reinterpret_cast<uintptr_t>(d_out_iq) & 15u) return set_error(AMPS_E_ALIGN, "d_out_iq must be 16-byte aligned");
@@ -310,6 +311,7 @@ static int fwd_submit_symbols(amps_fwd *h, const void *const *d_sym, size_t nsym
 }
 
 extern "C" int amps_fwd_work(amps_fwd *h, const uint8_t *const *sym, size_t nsym, float *out_iq_host) {
+    AMPS_NVTX("amps_fwd_work");
     if (!h || !sym || (nsym && !out_iq_host)) return set_error(AMPS_E_INVAL, "null argument");
     if (nsym == 0) return AMPS_OK;
     if (nsym > h->max_sym) return set_error(AMPS_E_OVERFLOW, "nsym exceeds max_samples / 100");
@@ -435,6 +437,7 @@ extern "C" int amps_fwd_work_voice(amps_fwd *h, const uint8_t *const *sym, const
 // Manchester-bit fast path: one byte per 10 kbit/s data bit (0, 1, 0xFF = muted), 1000 output samples per bit
 // ---------------------------------------------------------------------------------------------
 extern "C" int amps_fwd_submit_bits_dev(amps_fwd *h, const void *const *d_bits, size_t nbits, void *d_out_iq, void *cuda_stream) {
+    AMPS_NVTX("amps_fwd_submit_bits_dev");
     if (!h || !d_bits || (nbits && !d_out_iq)) return set_error(AMPS_E_INVAL, "null argument");
     if (nbits == 0) return AMPS_OK;
     if (nbits * kFbSymPerBit > h->max_sym) return set_error(AMPS_E_OVERFLOW, "nbits exceeds max_samples / 1000");
@@ -474,6 +477,7 @@ extern "C" int amps_fwd_submit_bits_dev(amps_fwd *h, const void *const *d_bits, 
 }
 
 extern "C" int amps_fwd_work_bits(amps_fwd *h, const uint8_t *const *bits, size_t nbits, float *out_iq_host) {
+    AMPS_NVTX("amps_fwd_work_bits");
     if (!h || !bits || (nbits && !out_iq_host)) return set_error(AMPS_E_INVAL, "null argument");
     if (nbits == 0) return AMPS_OK;
     if (nbits * kFbSymPerBit > h->max_sym) return set_error(AMPS_E_OVERFLOW, "nbits exceeds max_samples / 1000");

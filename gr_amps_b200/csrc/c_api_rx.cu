@@ -366,6 +366,7 @@ static int chan_append_carry(amps_recc_iq *h, const uint8_t *d_chunk, uint32_t n
 
 // Enqueue everything for one call of a single 10 MS/s channel: [tail carry | nchunk samples at d_chunk].
 static int rx_enqueue10(amps_recc_iq *h, const uint8_t *d_chunk, uint32_t nchunk, cudaStream_t st) {
+    AMPS_NVTX("amps_recc_iq: enqueue (front + search + capture)");
     const uint32_t units = (h->dev_carry + nchunk) / (uint32_t)kUnit;
     h->last_stream = st;
     if (units == 0) return chan_append_carry(h, d_chunk, nchunk, st);
@@ -424,6 +425,7 @@ static int rx_enqueue10(amps_recc_iq *h, const uint8_t *d_chunk, uint32_t nchunk
 
 // Enqueue everything for `npass` whole passes of the 400 kS/s front end whose samples start at d_chunk.
 static int rx_enqueue400(amps_recc_iq *h, const uint8_t *d_chunk, uint32_t npass, cudaStream_t st) {
+    AMPS_NVTX("amps_recc_iq: enqueue 400 kS/s");
     RxFront400Params p = h->fp400;
     p.chunk = d_chunk;
     p.tail = h->d_tail[h->tail_cur];
@@ -513,6 +515,7 @@ extern "C" int amps_recc_iq_submit_sc16_dev(amps_recc_iq *h, const void *d_iq, s
 // Wait for the stream; afterwards records [h->consumed, h->consumed + *n_out) sit in the host ring.
 // *overflowed is set ONCE per overflow of the candidate list (the bursts that were captured are still delivered).
 static int rx_fetch(amps_recc_iq *h, uint64_t *n_out, bool *overflowed) {
+    AMPS_NVTX("amps_recc_iq: fetch bursts");
     *n_out = 0;
     *overflowed = false;
     if (h->batch) {
@@ -584,6 +587,7 @@ extern "C" int amps_recc_iq_consume(amps_recc_iq *h, uint64_t count) {
 }
 
 static int rx_work(amps_recc_iq *h, const void *iq_host, size_t nsamples, amps_burst_cb cb, void *user, bool sc16) {
+    AMPS_NVTX("amps_recc_iq_work");
     if (!h || (!iq_host && nsamples)) return set_error(AMPS_E_INVAL, "null argument");
     if (h->batch) return set_error(AMPS_E_STATE, "the handle belongs to a batch: use amps_recc_iq_batch_*");
     if (h->sc16 != sc16) return set_error(AMPS_E_STATE, sc16 ? "handle was not created with AMPS_RX_INPUT_SC16" : "handle was created with AMPS_RX_INPUT_SC16: use the _sc16 entry points");
@@ -754,6 +758,7 @@ extern "C" int amps_recc_iq_batch_size(const amps_recc_iq_batch *b) { return b ?
 
 // one call: channel i gets nsamples[i] new samples at d_iq[i] (device pointers; several channels may share one buffer)
 static int batch_enqueue(amps_recc_iq_batch *b, const void *const *d_iq, const size_t *nsamples, cudaStream_t st) {
+    AMPS_NVTX("amps_recc_iq_batch: enqueue");
     const uint32_t par = (uint32_t)(b->call_no & 1u);
     b->last_stream = st;
     if (b->call_no >= 2) CK(cudaStreamWaitEvent(st, b->ev_side[par], 0));
@@ -840,6 +845,7 @@ extern "C" int amps_recc_iq_batch_submit_dev(amps_recc_iq_batch *b, const void *
 // ONE host buffer -> uploaded once -> every channel of the batch (its own center_freq) demodulates it: the carriers of one
 // wideband capture share the PCIe transfer.
 extern "C" int amps_recc_iq_batch_work_shared(amps_recc_iq_batch *b, const void *iq_host, size_t nsamples, amps_batch_burst_cb cb, void *user) {
+    AMPS_NVTX("amps_recc_iq_batch_work_shared");
     if (!b || (!iq_host && nsamples)) return set_error(AMPS_E_INVAL, "null argument");
     uint32_t cap = b->ch[0]->max_samples;
     for (const amps_recc_iq *h : b->ch) { if (h->max_samples < cap) cap = h->max_samples; if (h->dev_carry) return set_error(AMPS_E_STATE, "device-path samples are pending"); }
