@@ -46,7 +46,7 @@ struct amps_recc_iq {
     uint64_t     ydump_first = 0, ydump_count = 0;
     RxState     *d_state = nullptr;
     Candidate   *d_cand = nullptr;
-    Accepted    *d_acc = nullptr;        // bursts accepted by the select of call parity 0 / 1 (2 x kMaxAccept entries)
+    Accepted    *d_acc = nullptr;        // bursts accepted by the select of call slot 0 .. kRxDepth-1 (kRxDepth x kMaxAccept entries)
     uint32_t    *d_flags = nullptr;      // boundary counters of the front kernel (kMaxGrid words, zero between launches)
     amps_burst  *h_ring = nullptr;       // mapped pinned host ring the capture kernel publishes into
     RxPublished *h_pub = nullptr;        // mapped pinned counters
@@ -56,7 +56,8 @@ struct amps_recc_iq {
     cudaStream_t last_stream = nullptr;
     cudaStream_t side = nullptr;         // capture (and the M&M / 400 kS/s tails) run here, overlapped with the next front kernel
     cudaEvent_t  ev_front = nullptr;     // front kernel of the current call finished
-    cudaEvent_t  ev_side[2] = {nullptr, nullptr};   // tail of call k finished (k & 1)
+    cudaEvent_t  ev_side[kRxDepth] = {};            // side-stream work of call k finished (k mod kRxDepth)
+    bool         ev_side_valid[kRxDepth] = {};      // ... and whether call k used the side stream at all
     uint64_t     call_no = 0;
     bool         serial = false;         // AMPS_RX_SERIAL=1: no overlap (profiling / A-B measurements)
     bool         front_only = false;     // AMPS_RX_FRONT_ONLY=1: no capture (pipeline measurements only: no bursts come out)
@@ -97,7 +98,7 @@ struct amps_recc_iq_batch {
     bool         sc16 = false, sc16_unit = false;
     size_t       isz = sizeof(float2);
     cudaStream_t stream = nullptr, side = nullptr, last_stream = nullptr;
-    cudaEvent_t  ev_front = nullptr, ev_side[2] = {nullptr, nullptr};
+    cudaEvent_t  ev_front = nullptr, ev_side[kRxDepth] = {};
     uint64_t     call_no = 0;
     uint64_t     launches = 0;
     uint8_t     *d_stage = nullptr;      // shared-buffer host path: [carry | new chunk], every channel reads it
@@ -125,8 +126,9 @@ static size_t tail_samples(const amps_recc_iq *h) { return (size_t)h->hist + h->
 static int rx_alloc(amps_recc_iq *h) {
     const size_t max_d = ((size_t)h->max_samples + h->gran) / h->decim + kPassOut;
     size_t cap = 1;
-    // two calls' worth: the capture of call k overlaps the front kernel of call k+1
-    while (cap < 2 * max_d + (size_t)kSpan + 4096) cap <<= 1;
+    // kRxDepth + 1 calls' worth: the search / capture of call k may still read its part while the front kernels of calls
+    // k+1 .. k+kRxDepth-1 write theirs (small pipelined calls are then bound by the front kernel, not by the side stream)
+    while (cap < (size_t)(kRxDepth + 1) * max_d + (size_t)kSpan + 4096) cap <<= 1;
     h->dmask = (uint32_t)(cap - 1);
     for (int i = 0; i < 2; ++i) {
         CK(cudaMalloc(&h->d_tail[i], tail_samples(h) * h->isz));
@@ -143,7 +145,7 @@ static int rx_alloc(amps_recc_iq *h) {
     CK(cudaMalloc(&h->d_state, sizeof(RxState)));
     CK(cudaMemset(h->d_state, 0, sizeof(RxState)));
     CK(cudaMalloc(&h->d_cand, sizeof(Candidate) * kMaxCand * 2));      // candidates + the select's sorted copy
-    CK(cudaMalloc(&h->d_acc, sizeof(Accepted) * kMaxAccept * 2));
+    CK(cudaMalloc(&h->d_acc, sizeof(Accepted) * kMaxAccept * kRxDepth));
     if (h->want_prof) { CK(cudaMalloc(&h->d_prof, sizeof(unsigned long long) * 16 * kMaxGrid)); CK(cudaMemset(h->d_prof, 0, sizeof(unsigned long long) * 16 * kMaxGrid)); }
     CK(cudaMalloc(&h->d_flags, sizeof(uint32_t) * kMaxGrid));
     CK(cudaMemset(h->d_flags, 0, sizeof(uint32_t) * kMaxGrid));
@@ -166,7 +168,7 @@ static int rx_alloc(amps_recc_iq *h) {
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&h->ev_front, cudaEventDisableTiming));
-    for (int i = 0; i < 2; ++i) CK(cudaEventCreateWithFlags(&h->ev_side[i], cudaEventDisableTiming));
+    for (int i = 0; i < kRxDepth; ++i) CK(cudaEventCreateWithFlags(&h->ev_side[i], cudaEventDisableTiming));
     if (h->flags & AMPS_RX_TIME_KERNELS)
         for (int i = 0; i < amps_recc_iq::kEv; ++i) { CK(cudaEventCreate(&h->ev0[i])); CK(cudaEventCreate(&h->ev1[i])); }
     return AMPS_OK;
@@ -248,7 +250,7 @@ extern "C" int amps_recc_iq_destroy(amps_recc_iq *h) {
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->side) cudaStreamDestroy(h->side);
     if (h->ev_front) cudaEventDestroy(h->ev_front);
-    for (int i = 0; i < 2; ++i) if (h->ev_side[i]) cudaEventDestroy(h->ev_side[i]);
+    for (int i = 0; i < kRxDepth; ++i) if (h->ev_side[i]) cudaEventDestroy(h->ev_side[i]);
     for (int i = 0; i < amps_recc_iq::kEv; ++i) { if (h->ev0[i]) cudaEventDestroy(h->ev0[i]); if (h->ev1[i]) cudaEventDestroy(h->ev1[i]); }
     cudaFree(h->d_stage); cudaFree(h->d_tail[0]); cudaFree(h->d_tail[1]); cudaFree(h->d_dring); cudaFree(h->d_hring);
     cudaFree(h->d_ydump); cudaFree(h->d_state); cudaFree(h->d_cand); cudaFree(h->d_acc); cudaFree(h->d_flags); cudaFree(h->d_prof);
@@ -270,6 +272,7 @@ extern "C" int amps_recc_iq_reset(amps_recc_iq *h) {
     if (h->mm_mode) { int rc = mm_reset(h); if (rc != AMPS_OK) return rc; }
     std::memset(h->h_pub, 0, sizeof(RxPublished));
     h->consumed = 0; h->call_no = 0; h->overflow_seen = 0;
+    for (int i = 0; i < kRxDepth; ++i) h->ev_side_valid[i] = false;
     h->tail_cur = 0; h->carry = 0; h->dev_carry = 0; h->samples_in = 0; h->total_d = 0; h->groups_done = 0;
     h->ydump_first = 0; h->ydump_count = 0;
     return AMPS_OK;
@@ -334,6 +337,7 @@ static uint32_t chan_search(amps_recc_iq *h, RxSearchChan &sc, uint32_t par, uin
     sc.total_d = h->total_d;
     sc.dmask = h->dmask; sc.par = par; sc.cta_first = cta_first;
     sc.cta_count = rx_search_ctas(sc.g_hi - sc.g_lo);
+    sc.host_ring = h->h_ring; sc.ring_len = h->max_records; sc.decim = h->decim;
     h->groups_done = sc.g_hi;
     return sc.cta_count;
 }
@@ -365,14 +369,17 @@ static int chan_append_carry(amps_recc_iq *h, const uint8_t *d_chunk, uint32_t n
 }
 
 // Enqueue everything for one call of a single 10 MS/s channel: [tail carry | nchunk samples at d_chunk].
-static int rx_enqueue10(amps_recc_iq *h, const uint8_t *d_chunk, uint32_t nchunk, cudaStream_t st) {
+// in_order: the caller synchronises right after this call (the host-buffer path), so nothing is gained by moving the search /
+// capture to the side stream -- they follow the front kernel on `st` and four driver calls (two event records, two waits) go.
+static int rx_enqueue10(amps_recc_iq *h, const uint8_t *d_chunk, uint32_t nchunk, cudaStream_t st, bool in_order = false) {
     AMPS_NVTX("amps_recc_iq: enqueue (front + search + capture)");
     const uint32_t units = (h->dev_carry + nchunk) / (uint32_t)kUnit;
     h->last_stream = st;
     if (units == 0) return chan_append_carry(h, d_chunk, nchunk, st);
-    const uint32_t par = (uint32_t)(h->call_no & 1u);
-    // the demod ring and the accepted-burst lists hold two calls: do not overwrite what the capture of call k-2 may still read
-    if (h->call_no >= 2) CK(cudaStreamWaitEvent(st, h->ev_side[par], 0));
+    const uint32_t par = (uint32_t)(h->call_no % kRxDepth);
+    // the demod ring holds kRxDepth + 1 calls, the accepted-burst lists kRxDepth: do not overwrite what the side-stream work of
+    // call k - kRxDepth may still read
+    if (h->ev_side_valid[par]) CK(cudaStreamWaitEvent(st, h->ev_side[par], 0));
     RxFrontParams1 p = h->fp;
     p.prof = h->d_prof;
     chan_begin(h, p.ch[0], d_chunk, nchunk, units, par);
@@ -389,9 +396,12 @@ static int rx_enqueue10(amps_recc_iq *h, const uint8_t *d_chunk, uint32_t nchunk
     h->launches++;
     // capture (and the M&M tail) on the side stream, so that the next call's front kernel (HBM-bound, 2 CTAs/SM) overlaps
     // these small latency-bound kernels
-    CK(cudaEventRecord(h->ev_front, st));
-    cudaStream_t sd = h->serial ? st : h->side;
-    if (!h->serial) CK(cudaStreamWaitEvent(sd, h->ev_front, 0));
+    const bool serial = h->serial || in_order;
+    cudaStream_t sd = serial ? st : h->side;
+    if (!serial) {
+        CK(cudaEventRecord(h->ev_front, st));
+        CK(cudaStreamWaitEvent(sd, h->ev_front, 0));
+    }
     if (!h->front_only) {
         RxCaptureParams cp;
         cp.nchan = 1;
@@ -406,19 +416,24 @@ static int rx_enqueue10(amps_recc_iq *h, const uint8_t *d_chunk, uint32_t nchunk
             nc = mm_capture_ctas((uint64_t)units * kUnitOut);
             h->launches += 2;
         }
+        // a call that can make at most two bursts capturable: the search kernel's last CTA captures them itself (2 launches)
+        const bool small = !h->mm_mode && !h->fused && !h->nosearch && nc <= 2u;
         if (!h->mm_mode && !h->fused && !h->nosearch) {
             // trigger search + selection as their own launch, overlapped (like the capture) with the next call's front kernel
             RxSearchParams sp;
             sp.nchan = 1;
             const uint32_t ns = chan_search(h, sp.ch[0], par, 0);
-            CKL(launch_rx_search(sp, (int)ns, sd));
+            CKL(launch_rx_search(sp, (int)ns, small, sd));
             h->launches++;
         }
-        chan_capture(h, cp.ch[0], par, 0, nc);
-        CKL(launch_rx_capture(cp, (int)nc, sd));
-        h->launches++;
+        if (!small) {
+            chan_capture(h, cp.ch[0], par, 0, nc);
+            CKL(launch_rx_capture(cp, (int)nc, sd));
+            h->launches++;
+        }
     }
-    CK(cudaEventRecord(h->ev_side[par], sd));
+    h->ev_side_valid[par] = !serial;
+    if (!serial) CK(cudaEventRecord(h->ev_side[par], sd));
     h->call_no++;
     return AMPS_OK;
 }
@@ -439,8 +454,8 @@ static int rx_enqueue400(amps_recc_iq *h, const uint8_t *d_chunk, uint32_t npass
     const uint32_t resident = 4u * (uint32_t)h->sm_count;
     p.pass_per_cta = (npass + resident - 1u) / resident;
     const int grid = (int)((npass + p.pass_per_cta - 1u) / p.pass_per_cta);
-    const uint32_t par = (uint32_t)(h->call_no & 1u);
-    if (h->call_no >= 2) CK(cudaStreamWaitEvent(st, h->ev_side[par], 0));
+    const uint32_t par = (uint32_t)(h->call_no % kRxDepth);
+    if (h->ev_side_valid[par]) CK(cudaStreamWaitEvent(st, h->ev_side[par], 0));
     const bool timed = (h->flags & AMPS_RX_TIME_KERNELS) != 0;
     const int  evi = (int)(h->ev_count % amps_recc_iq::kEv);
     if (timed) CK(cudaEventRecord(h->ev0[evi], st));
@@ -474,7 +489,7 @@ static int rx_enqueue400(amps_recc_iq *h, const uint8_t *d_chunk, uint32_t npass
             RxSearchParams sp;
             sp.nchan = 1;
             const uint32_t ns = chan_search(h, sp.ch[0], par, 0);
-            CKL(launch_rx_search(sp, (int)ns, sd));
+            CKL(launch_rx_search(sp, (int)ns, false, sd));
             h->launches++;
         }
         chan_capture(h, cp.ch[0], par, 0, nc);
@@ -482,6 +497,7 @@ static int rx_enqueue400(amps_recc_iq *h, const uint8_t *d_chunk, uint32_t npass
         h->launches++;
     }
     CK(cudaEventRecord(h->ev_side[par], sd));
+    h->ev_side_valid[par] = true;
     h->call_no++;
     h->last_stream = st;
     return AMPS_OK;
@@ -603,7 +619,7 @@ static int rx_work(amps_recc_iq *h, const void *iq_host, size_t nsamples, amps_b
     const uint32_t nq = (uint32_t)(avail / h->gran);       // whole processing quanta (units at 10 MS/s, passes at 400 kS/s)
     h->last_stream = st;
     if (nq) {
-        int rc = h->native400 ? rx_enqueue400(h, h->d_stage, nq, st) : rx_enqueue10(h, h->d_stage, nq * h->gran, st);
+        int rc = h->native400 ? rx_enqueue400(h, h->d_stage, nq, st) : rx_enqueue10(h, h->d_stage, nq * h->gran, st, /*in_order=*/true);
         if (rc != AMPS_OK) return rc;
         const size_t left = avail - (size_t)nq * h->gran;
         if (left)
@@ -730,7 +746,7 @@ extern "C" int amps_recc_iq_batch_create(amps_recc_iq *const *handles, int count
     cudaError_t e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->side, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_front, cudaEventDisableTiming);
-    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&b->ev_side[i], cudaEventDisableTiming);
+    for (int i = 0; i < kRxDepth && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&b->ev_side[i], cudaEventDisableTiming);
     if (b->timed)
         for (int i = 0; i < amps_recc_iq_batch::kEv && e == cudaSuccess; ++i) { e = cudaEventCreate(&b->ev0[i]); if (e == cudaSuccess) e = cudaEventCreate(&b->ev1[i]); }
     if (e != cudaSuccess) { amps_recc_iq_batch_destroy(b); return set_cuda_error(e, "batch streams / events"); }
@@ -747,7 +763,7 @@ extern "C" int amps_recc_iq_batch_destroy(amps_recc_iq_batch *b) {
     if (b->stream) cudaStreamDestroy(b->stream);
     if (b->side) cudaStreamDestroy(b->side);
     if (b->ev_front) cudaEventDestroy(b->ev_front);
-    for (int i = 0; i < 2; ++i) if (b->ev_side[i]) cudaEventDestroy(b->ev_side[i]);
+    for (int i = 0; i < kRxDepth; ++i) if (b->ev_side[i]) cudaEventDestroy(b->ev_side[i]);
     for (int i = 0; i < amps_recc_iq_batch::kEv; ++i) { if (b->ev0[i]) cudaEventDestroy(b->ev0[i]); if (b->ev1[i]) cudaEventDestroy(b->ev1[i]); }
     cudaFree(b->d_stage);
     delete b;
@@ -759,9 +775,9 @@ extern "C" int amps_recc_iq_batch_size(const amps_recc_iq_batch *b) { return b ?
 // one call: channel i gets nsamples[i] new samples at d_iq[i] (device pointers; several channels may share one buffer)
 static int batch_enqueue(amps_recc_iq_batch *b, const void *const *d_iq, const size_t *nsamples, cudaStream_t st) {
     AMPS_NVTX("amps_recc_iq_batch: enqueue");
-    const uint32_t par = (uint32_t)(b->call_no & 1u);
+    const uint32_t par = (uint32_t)(b->call_no % kRxDepth);
     b->last_stream = st;
-    if (b->call_no >= 2) CK(cudaStreamWaitEvent(st, b->ev_side[par], 0));
+    if (b->call_no >= (uint64_t)kRxDepth) CK(cudaStreamWaitEvent(st, b->ev_side[par], 0));
     const uint32_t resident = (uint32_t)rx_front_ctas_per_sm(b->sc16) * (uint32_t)b->sm_count;
     const int evi = (int)(b->ev_count % amps_recc_iq_batch::kEv);
     if (b->timed) CK(cudaEventRecord(b->ev0[evi], st));
@@ -818,7 +834,7 @@ static int batch_enqueue(amps_recc_iq_batch *b, const void *const *d_iq, const s
     CK(cudaEventRecord(b->ev_front, st));
     CK(cudaStreamWaitEvent(sd, b->ev_front, 0));
     for (size_t k = 0; k < caps.size(); ++k) {
-        if (split) { CKL(launch_rx_search(srch[k], (int)srch_grid[k], sd)); b->launches++; }
+        if (split) { CKL(launch_rx_search(srch[k], (int)srch_grid[k], false, sd)); b->launches++; }
         if (mm) { CKL(launch_rx_mm(mms[k], sd)); b->launches += 2; }
         CKL(launch_rx_capture(caps[k], (int)cap_grid[k], sd));
         b->launches++;

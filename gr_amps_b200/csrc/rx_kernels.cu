@@ -966,10 +966,63 @@ uint32_t rx_make_deal(RxDeal &d, uint32_t tiles, uint32_t resident) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// One accepted burst, all threads of the CTA: gather the 3374 half-symbols at the chosen phase (or take the blob amps.recc
+// cut in M&M mode), decode, and stream the finished record into the host-visible ring (posted PCIe writes).  Ends with the
+// record on its way (__threadfence_system + barrier); publishing the count is the caller's business.
+// ---------------------------------------------------------------------------------------------
+__device__ void capture_burst(const float *__restrict__ dring, uint32_t dmask, const Accepted *acc, const uint8_t *blobs,
+                              const unsigned long long *blob_sym_index, uint32_t decim, amps_burst *host_ring, uint32_t ring_len,
+                              unsigned long long rec_base, unsigned int b, unsigned int n_acc, amps_burst *rec, uint8_t *s_valid,
+                              unsigned int *s_errs) {
+    const int t = threadIdx.x, nt = blockDim.x;
+    if (blobs) {
+        for (int s = t; s < kCapture; s += nt) rec->symbols[s] = blobs[(size_t)b * kCapture + s];
+        if (t == 0) {
+            // position bookkeeping is nominal here: the recovered half-symbol index, 10 demod samples per half-symbol
+            const unsigned long long first_sym = blob_sym_index[b];
+            const unsigned long long trig_sym = first_sym >= (unsigned long long)kTrig ? first_sym - kTrig : 0ull;
+            rec->demod_index = trig_sym * (unsigned long long)kOS;
+            rec->sample_index = rec->demod_index * (unsigned long long)decim;
+            rec->corr = 0.0f;
+            rec->run_length = 0;
+            rec->pad[0] = 0; rec->pad[1] = 0;
+        }
+    } else {
+        const Accepted a = acc[b];
+        // the 3374 half-symbols after the trigger, sliced at the chosen sampling phase (recc_impl.cc:124-126)
+        for (int s = t; s < kCapture; s += nt) {
+            const float v = __ldcg(&dring[(a.pos + (unsigned long long)(kOS * (kTrig + s))) & dmask]);
+            rec->symbols[s] = v >= 0.0f ? 1 : 0;
+        }
+        if (t == 0) {
+            rec->demod_index = a.pos;
+            rec->sample_index = a.pos * (unsigned long long)decim;
+            rec->corr = a.corr;
+            rec->run_length = a.run;
+            rec->pad[0] = 0; rec->pad[1] = 0;
+        }
+    }
+    __syncthreads();
+    decode_burst_block(rec->symbols, &rec->decoded, s_valid, s_errs);
+    // (when one call accepts more bursts than the ring holds, only the newest ring_len are written: two CTAs must
+    // never race for the same slot)
+    if (n_acc - b <= ring_len) {
+        const unsigned long long *src = reinterpret_cast<const unsigned long long *>(rec);
+        unsigned long long *dst = reinterpret_cast<unsigned long long *>(&host_ring[(rec_base + b) % ring_len]);
+        for (int w = t; w < (int)(sizeof(amps_burst) / 8); w += nt) dst[w] = src[w];
+    }
+    __threadfence_system();
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
 // stand-alone trigger search + selection on the demod rings, one or many channels per launch: CTAs [cta_first, cta_first +
 // cta_count) of the launch search a contiguous slice each of channel c's groups [g_lo, g_hi); the last of them to finish
 // selects.  Same rules (and the same device routines) as inside rx_front_kernel.
+//   kCapture2 (calls so short that at most two bursts can become capturable): that last CTA also captures them, and the
+// call needs no capture launch at all -- two launches per call, the side stream's share of a small pipelined call halves.
 // ---------------------------------------------------------------------------------------------
+template <bool kCapture2>
 __global__ void __launch_bounds__(256) rx_search_kernel(const __grid_constant__ RxSearchParams p) {
     __shared__ uint32_t s_last;
     __shared__ SearchScratch sc;
@@ -996,12 +1049,30 @@ __global__ void __launch_bounds__(256) rx_search_kernel(const __grid_constant__ 
         __threadfence();
         select_channel(ch.state, ch.cand, ch.cand + kMaxCand, ch.acc + (size_t)ch.par * kMaxAccept, ch.par, ch.total_d, ch.host_pub, s_cand, 64u);
         if (threadIdx.x == 0) ch.state->search_done = 0u;
+        if constexpr (kCapture2) {
+            __shared__ __align__(16) unsigned char rec_raw[sizeof(amps_burst)];
+            __shared__ uint8_t s_valid[40];
+            __shared__ unsigned int s_errs[8];
+            RxState *state = ch.state;
+            const unsigned int n_acc = state->n_acc[ch.par];
+            const unsigned long long rec_base = state->rec_base[ch.par];
+            for (unsigned int b = 0; b < n_acc; ++b)
+                capture_burst(ch.dring, ch.dmask, ch.acc + (size_t)ch.par * kMaxAccept, nullptr, nullptr, ch.decim, ch.host_ring, ch.ring_len,
+                              rec_base, b, n_acc, reinterpret_cast<amps_burst *>(rec_raw), s_valid, s_errs);
+            if (threadIdx.x == 0 && n_acc > 0) {
+                state->pub_overflow = state->cand_overflow;
+                __threadfence_system();
+                ch.host_pub->cand_overflow = state->cand_overflow;
+                ch.host_pub->nrec_total = rec_base + n_acc;
+            }
+        }
     }
 }
 
-cudaError_t launch_rx_search(const RxSearchParams &p, int grid, cudaStream_t st) {
+cudaError_t launch_rx_search(const RxSearchParams &p, int grid, bool capture_too, cudaStream_t st) {
     if (grid <= 0) return cudaSuccess;
-    rx_search_kernel<<<grid, 256, 0, st>>>(p);
+    if (capture_too) rx_search_kernel<true><<<grid, 256, 0, st>>>(p);
+    else rx_search_kernel<false><<<grid, 256, 0, st>>>(p);
     return cudaGetLastError();
 }
 
@@ -1020,49 +1091,11 @@ __global__ void __launch_bounds__(256) rx_capture_kernel(const __grid_constant__
     RxState *state = ch.state;
     const unsigned int n_acc = state->n_acc[ch.par];
     const unsigned long long rec_base = state->rec_base[ch.par];
-    const int t = threadIdx.x, nt = blockDim.x;
     amps_burst *rec = reinterpret_cast<amps_burst *>(rec_raw);
     for (unsigned int b = blockIdx.x - ch.cta_first; b < n_acc; b += ch.cta_count) {
-        if (ch.blobs) {
-            for (int s = t; s < kCapture; s += nt) rec->symbols[s] = ch.blobs[(size_t)b * kCapture + s];
-            if (t == 0) {
-                // position bookkeeping is nominal here: the recovered half-symbol index, 10 demod samples per half-symbol
-                const unsigned long long first_sym = ch.blob_sym_index[b];
-                const unsigned long long trig_sym = first_sym >= (unsigned long long)kTrig ? first_sym - kTrig : 0ull;
-                rec->demod_index = trig_sym * (unsigned long long)kOS;
-                rec->sample_index = rec->demod_index * (unsigned long long)ch.decim;
-                rec->corr = 0.0f;
-                rec->run_length = 0;
-                rec->pad[0] = 0; rec->pad[1] = 0;
-            }
-        } else {
-            const Accepted a = ch.acc[b];
-            // the 3374 half-symbols after the trigger, sliced at the chosen sampling phase (recc_impl.cc:124-126)
-            for (int s = t; s < kCapture; s += nt) {
-                const float v = ch.dring[(a.pos + (unsigned long long)(kOS * (kTrig + s))) & ch.dmask];
-                rec->symbols[s] = v >= 0.0f ? 1 : 0;
-            }
-            if (t == 0) {
-                rec->demod_index = a.pos;
-                rec->sample_index = a.pos * (unsigned long long)ch.decim;
-                rec->corr = a.corr;
-                rec->run_length = a.run;
-                rec->pad[0] = 0; rec->pad[1] = 0;
-            }
-        }
-        __syncthreads();
-        decode_burst_block(rec->symbols, &rec->decoded, s_valid, s_errs);
-        // publish: stream the finished record into the host-visible ring (posted PCIe writes)
-        // (when one call accepts more bursts than the ring holds, only the newest ring_len are written: two CTAs must
-        // never race for the same slot)
-        if (n_acc - b <= ch.ring_len) {
-            const unsigned long long *src = reinterpret_cast<const unsigned long long *>(rec);
-            unsigned long long *dst = reinterpret_cast<unsigned long long *>(&ch.host_ring[(rec_base + b) % ch.ring_len]);
-            for (int w = t; w < (int)(sizeof(amps_burst) / 8); w += nt) dst[w] = src[w];
-        }
-        __threadfence_system();
-        __syncthreads();
-        if (t == 0) {
+        capture_burst(ch.dring, ch.dmask, ch.acc, ch.blobs, ch.blob_sym_index, ch.decim, ch.host_ring, ch.ring_len, rec_base, b, n_acc, rec,
+                      s_valid, s_errs);
+        if (threadIdx.x == 0) {
             const unsigned int prev = atomicAdd(&state->done, 1u);
             if (prev + 1 == n_acc) {                          // last burst of the call: every record is on its way, publish the count
                 state->done = 0;
@@ -1226,7 +1259,7 @@ cudaError_t rx_configure_device() {
     // The side-stream kernels share SMs with the NEXT call's front kernel, whose two CTAs need 199 KB of shared memory per
     // SM.  An SM's L1/shared split is fixed while CTAs are resident: if a kernel that wants a big L1 gets there first, the
     // front CTAs wait until it has left.  Ask for the front kernel's split everywhere.
-    const void *side[] = {(const void *)rx_search_kernel, (const void *)rx_capture_kernel, (const void *)rx_mm_kernel,
+    const void *side[] = {(const void *)rx_search_kernel<false>, (const void *)rx_search_kernel<true>, (const void *)rx_capture_kernel, (const void *)rx_mm_kernel,
                           (const void *)rx_mm_recc_kernel};
     for (const void *f : side) {
         e = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);

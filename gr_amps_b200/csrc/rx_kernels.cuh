@@ -32,6 +32,8 @@ constexpr int kHist      = kWarmTiles * kTile;   // input history carried betwee
 constexpr int kPorchCols = 40;               // columns of v history kept in front of each row (>= (150 + 2R)/R)
 constexpr int kRowLen    = kPorchCols + kTB + 2; // pairs per row (+2: rows land 32 B apart in bank space)
 constexpr int kPass400   = kPassTiles * kTB;     // native 400 kS/s front end: 1536 input samples per pass (no CIC stage)
+constexpr int kRxDepth   = 4;                // calls whose side-stream work (search, capture) may be in flight: the demod ring
+                                             // holds kRxDepth + 1 calls, the accepted-burst lists are kept per call slot
 constexpr int kMaxGrid   = 1024;             // most CTAs a front launch may have (per-channel completion flags)
 constexpr int kMaxBatch  = 64;               // channels one batched launch can carry (kernel parameter space: 32 KB)
 
@@ -45,8 +47,8 @@ static_assert(kUnitOut * (kGroupLag + 1) > 63 + kOS * (kTrig - 1), "group lag to
 struct RxState {             // device-resident stream state of one channel
     unsigned long long resume_at;   // positions below this are inside an already captured burst
     unsigned long long nrec_total;  // bursts published since stream start (monotonic)
-    unsigned long long rec_base[2]; // nrec_total before the bursts accepted by the select of call parity 0/1
-    unsigned int       n_acc[2];    // bursts accepted by that select, captured by the capture kernel
+    unsigned long long rec_base[kRxDepth]; // nrec_total before the bursts accepted by the select of call slot (call number mod kRxDepth)
+    unsigned int       n_acc[kRxDepth];    // bursts accepted by that select, captured by the capture kernel
     unsigned int       ncand;       // candidates on the list (new ones appended by the search, undecided ones kept by select)
     unsigned int       cand_overflow;   // candidates dropped because the list was full (monotonic)
     unsigned int       pub_overflow;    // value of cand_overflow last mirrored to the host
@@ -85,7 +87,7 @@ struct RxChan {
     float2       *ydump;     // optional: complex baseband of this call (units*kUnitOut entries) or nullptr
     RxState      *state;
     Candidate    *cand;      // 2 x kMaxCand: list + the select's sorted scratch
-    Accepted     *acc;       // 2 x kMaxAccept, by call parity
+    Accepted     *acc;       // kRxDepth x kMaxAccept, by call slot
     RxPublished  *host_pub;
     uint32_t     *flags;     // kMaxGrid words, all zero between launches: flags[j] counts the CTAs whose output the boundary
                              // groups of CTA j's segment read and that have published it (the last one searches them)
@@ -96,7 +98,7 @@ struct RxChan {
     uint32_t      nchunk;    // samples in `chunk`
     uint32_t      blk_base;  // absolute 25-sample block index (mod 2^32) of logical sample 0
     uint32_t      fcw25;     // NCO phase step per block (25 * fcw mod 2^32)
-    uint32_t      par;       // call parity: which acc / n_acc / rec_base slot this call's select fills
+    uint32_t      par;       // call slot (call number mod kRxDepth): which acc / n_acc / rec_base entry this call's select fills
     uint32_t      search;    // 0: no trigger search in this launch (M&M timing mode runs its own tail)
     float         in_scale;  // sc16 input: x = (float)int16 * in_scale (one fp32 multiply per component)
     float2        w[kD1];    // NCO phasors inside a block
@@ -173,13 +175,16 @@ struct RxSearchChan {
     const uint32_t *hring;
     RxState        *state;
     Candidate      *cand;
-    Accepted       *acc;        // 2 x kMaxAccept
+    Accepted       *acc;        // kRxDepth x kMaxAccept
     RxPublished    *host_pub;
     unsigned long long g_lo, g_hi;   // groups to search
     unsigned long long total_d;      // demod samples produced so far (what select decides against)
     uint32_t        dmask;
     uint32_t        par;
     uint32_t        cta_first, cta_count;
+    // for the variant that also captures (calls that can make at most two bursts capturable)
+    amps_burst     *host_ring;
+    uint32_t        ring_len, decim;
 };
 struct RxSearchParams {
     uint32_t     nchan;
@@ -212,7 +217,7 @@ cudaError_t launch_rx_front_batch(const RxFrontParamsB &p, int grid, cudaStream_
 cudaError_t launch_rx_front400(const RxFront400Params &p, int grid, cudaStream_t st, bool sc16 = false, bool unit = false);
 // stand-alone trigger search + selection on the demod rings (same rules as inside rx_front_kernel): the tail of the 400 kS/s
 // front end, and of the 10 MS/s one unless AMPS_RX_FUSED_SEARCH asks for the search inside the front kernel
-cudaError_t launch_rx_search(const RxSearchParams &p, int grid, cudaStream_t st);
+cudaError_t launch_rx_search(const RxSearchParams &p, int grid, bool capture_too, cudaStream_t st);
 // capture: CTAs [cta_first, cta_first + cta_count) of channel c walk its accepted bursts (stride cta_count): gather the
 // 3374 half-symbols, decode, and stream the record into host_ring[(rec_base + b) % ring_len] (mapped pinned host memory)
 cudaError_t launch_rx_capture(const RxCaptureParams &p, int grid, cudaStream_t st);
