@@ -798,7 +798,8 @@ static int batch_enqueue(amps_recc_iq_batch *b, const void *const *d_iq, const s
         std::memcpy(p.g, h0->fp.g, sizeof p.g);
         std::memcpy(p.h2, h0->fp.h2, sizeof p.h2);
         p.prof = nullptr;
-        uint32_t n = 0, tiles = 0, cap_ctas = 0, srch_ctas = 0;
+        uint32_t n = 0, tiles = 0, cap_ctas = 0, srch_ctas = 0, eq_tiles = 0;
+        bool all_equal = true;
         RxCaptureParams cp;
         RxSearchParams sp;
         RxMmParams mp;
@@ -810,7 +811,9 @@ static int batch_enqueue(amps_recc_iq_batch *b, const void *const *d_iq, const s
             const uint32_t units = (h->dev_carry + nchunk) / (uint32_t)kUnit;
             if (units == 0) { int rc = chan_append_carry(h, static_cast<const uint8_t *>(d_iq[i]), nchunk, st); if (rc != AMPS_OK) return rc; continue; }
             chan_begin(h, p.ch[n], static_cast<const uint8_t *>(d_iq[i]), nchunk, units, par);
-            tiles += rx_tiles_of(units);
+            const uint32_t ct = rx_tiles_of(units);
+            if (n == 0) eq_tiles = ct; else if (ct != eq_tiles) all_equal = false;
+            tiles += ct;
             p.tile_cum[n + 1] = tiles;
             const uint32_t nc = mm ? mm_capture_ctas((uint64_t)units * kUnitOut) : capture_ctas((uint64_t)units * kUnitOut);
             if (mm) chan_mm(h, mp.ch[n], par);
@@ -822,7 +825,7 @@ static int batch_enqueue(amps_recc_iq_batch *b, const void *const *d_iq, const s
         if (n == 0) continue;
         p.nchan = n;
         cp.nchan = n;
-        const uint32_t grid = rx_make_deal(p.deal, tiles, resident);
+        const uint32_t grid = rx_make_deal(p.deal, tiles, resident, n, all_equal ? eq_tiles : 0u);
         CKL(launch_rx_front_batch(p, (int)grid, st, b->sc16, b->sc16_unit, !split && !mm));
         b->launches++;
         caps.push_back(cp);

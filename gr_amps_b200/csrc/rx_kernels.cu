@@ -590,8 +590,12 @@ __device__ __forceinline__ void finish_pass(const float (&h2)[300], const PassOu
 // ---- how a launch's tiles are dealt: the Tt tiles are split evenly, CTA s owns tiles [Tt*s/grid, Tt*(s+1)/grid) -- its
 // SEGMENTS (one per channel the range touches).  (A pool of late segments for CTAs that finish early was tried on the
 // 2^28-sample batch: the spread between CTAs is not removed by it and the extra warm-up tiles cost 2 %.)
-__device__ __forceinline__ uint32_t deal_lo(const RxDeal &d, uint32_t s) { return (uint32_t)((unsigned long long)d.Tt * s / d.nstat); }
+__device__ __forceinline__ uint32_t deal_lo(const RxDeal &d, uint32_t s) {
+    if (d.P) return (s / d.P) * d.Tc + (uint32_t)((unsigned long long)d.Tc * (s % d.P) / d.P);       // (s == nstat gives Tt)
+    return (uint32_t)((unsigned long long)d.Tt * s / d.nstat);
+}
 __device__ __forceinline__ uint32_t deal_owner(const RxDeal &d, uint32_t tile) {
+    if (d.P) return (tile / d.Tc) * d.P + (uint32_t)((((unsigned long long)(tile % d.Tc) + 1ull) * d.P - 1ull) / d.Tc);
     return (uint32_t)((((unsigned long long)tile + 1ull) * d.nstat - 1ull) / d.Tt);
 }
 
@@ -966,11 +970,16 @@ cudaError_t launch_rx_front_batch(const RxFrontParamsB &p, int grid, cudaStream_
 }
 int rx_front_ctas_per_sm(bool sc16) { return sc16 ? kSc16Ctas : 2; }
 
-uint32_t rx_make_deal(RxDeal &d, uint32_t tiles, uint32_t resident) {
+uint32_t rx_make_deal(RxDeal &d, uint32_t tiles, uint32_t resident, uint32_t nchan, uint32_t equal_tiles) {
     uint32_t grid = resident < (uint32_t)kMaxGrid ? resident : (uint32_t)kMaxGrid;
     if (grid > tiles) grid = tiles;
     if (grid < 1u) grid = 1u;
-    d.Tt = tiles; d.nstat = grid;
+    d.Tt = tiles; d.nstat = grid; d.P = 0; d.Tc = 0;
+    if (nchan > 1u && equal_tiles > 0u && nchan <= grid) {
+        uint32_t P = grid / nchan;                           // whole CTAs per channel
+        if (P > equal_tiles) P = equal_tiles;
+        if (4u * nchan * P >= 3u * grid) { d.P = P; d.Tc = equal_tiles; d.nstat = nchan * P; return d.nstat; }    // >= 3/4 of the CTAs busy
+    }
     return grid;
 }
 

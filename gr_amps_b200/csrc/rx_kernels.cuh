@@ -107,10 +107,15 @@ struct RxChan {
 // how a launch's tiles are dealt to CTAs (see deal_lo() in rx_kernels.cu)
 struct RxDeal {
     uint32_t Tt;             // tiles of the launch
-    uint32_t nstat;          // CTAs of the launch; CTA s owns tiles [Tt*s/nstat, Tt*(s+1)/nstat)
+    uint32_t nstat;          // CTAs of the launch
+    uint32_t P;              // 0: CTA s owns tiles [Tt*s/nstat, Tt*(s+1)/nstat) (a range may cross channels);
+                             // > 0: the channels all have Tc tiles and P CTAs each: CTA s owns part s % P of channel s / P
+    uint32_t Tc;
 };
-// fills a deal for `tiles` tiles on at most `resident` CTAs; returns the grid size
-uint32_t rx_make_deal(RxDeal &d, uint32_t tiles, uint32_t resident);
+// fills a deal for `tiles` tiles on at most `resident` CTAs; returns the grid size.  nchan channels of equal_tiles tiles each
+// (equal_tiles = 0: lengths differ) are given whole CTAs when that keeps most of the machine busy: a CTA that finishes one
+// channel and starts the next pays a second warm-up and a cold restart of its copy ring.
+uint32_t rx_make_deal(RxDeal &d, uint32_t tiles, uint32_t resident, uint32_t nchan = 1, uint32_t equal_tiles = 0);
 
 template <int kMaxChan>
 struct RxFrontParamsT {
