@@ -335,6 +335,15 @@ class ReccIqBatch:
         cnt = (C.c_size_t * k)(*ns)
         check(lib().amps_recc_iq_batch_submit_dev(self.b, ptrs, cnt, C.c_void_p(stream)))
 
+    def prepare(self, dev_ptrs, nsamples):
+        """The two argument arrays of submit_dev built once (a caller that reuses its buffers saves the marshalling)."""
+        k = len(self.handles)
+        ns = [nsamples] * k if isinstance(nsamples, int) else list(nsamples)
+        return (C.c_void_p * k)(*dev_ptrs), (C.c_size_t * k)(*ns)
+
+    def submit_prepared(self, prepared, stream: int = 0):
+        check(lib().amps_recc_iq_batch_submit_dev(self.b, prepared[0], prepared[1], C.c_void_p(stream)))
+
     def work_shared(self, iq: np.ndarray) -> list:
         """One host buffer for every channel; returns [(channel, Burst), ...]."""
         iq = np.ascontiguousarray(iq)

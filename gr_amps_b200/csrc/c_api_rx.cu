@@ -54,7 +54,10 @@ struct amps_recc_iq {
     uint64_t     lost = 0;               // bursts overwritten in the ring before they were collected
     uint32_t     overflow_seen = 0;      // candidate-list overflows already reported to the caller
     cudaStream_t last_stream = nullptr;
-    cudaStream_t side = nullptr;         // capture (and the M&M / 400 kS/s tails) run here, overlapped with the next front kernel
+    cudaStream_t side = nullptr;         // search + selection (and the M&M / 400 kS/s tails) run here, overlapped with the next front kernel
+    cudaStream_t side2 = nullptr;        // ... and the capture here: the search of call k+1 does not wait for the capture of call k
+    cudaEvent_t  ev_sel = nullptr;       // selection of the current call finished (side -> side2)
+    int          cap_par = -1;           // call slot of the last capture launched on side2 (-1: none since the last join)
     cudaEvent_t  ev_front = nullptr;     // front kernel of the current call finished
     cudaEvent_t  ev_side[kRxDepth] = {};            // side-stream work of call k finished (k mod kRxDepth)
     bool         ev_side_valid[kRxDepth] = {};      // ... and whether call k used the side stream at all
@@ -97,8 +100,8 @@ struct amps_recc_iq_batch {
     std::vector<amps_recc_iq *> ch;
     bool         sc16 = false, sc16_unit = false;
     size_t       isz = sizeof(float2);
-    cudaStream_t stream = nullptr, side = nullptr, last_stream = nullptr;
-    cudaEvent_t  ev_front = nullptr, ev_side[kRxDepth] = {};
+    cudaStream_t stream = nullptr, side = nullptr, side2 = nullptr, last_stream = nullptr;
+    cudaEvent_t  ev_front = nullptr, ev_sel = nullptr, ev_side[kRxDepth] = {};
     uint64_t     call_no = 0;
     uint64_t     launches = 0;
     uint8_t     *d_stage = nullptr;      // shared-buffer host path: [carry | new chunk], every channel reads it
@@ -167,7 +170,9 @@ static int rx_alloc(amps_recc_iq *h) {
     std::memset(h->h_pub, 0, sizeof(RxPublished));
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->side2, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&h->ev_front, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_sel, cudaEventDisableTiming));
     for (int i = 0; i < kRxDepth; ++i) CK(cudaEventCreateWithFlags(&h->ev_side[i], cudaEventDisableTiming));
     if (h->flags & AMPS_RX_TIME_KERNELS)
         for (int i = 0; i < amps_recc_iq::kEv; ++i) { CK(cudaEventCreate(&h->ev0[i])); CK(cudaEventCreate(&h->ev1[i])); }
@@ -249,7 +254,9 @@ extern "C" int amps_recc_iq_destroy(amps_recc_iq *h) {
     cudaDeviceSynchronize();
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->side) cudaStreamDestroy(h->side);
+    if (h->side2) cudaStreamDestroy(h->side2);
     if (h->ev_front) cudaEventDestroy(h->ev_front);
+    if (h->ev_sel) cudaEventDestroy(h->ev_sel);
     for (int i = 0; i < kRxDepth; ++i) if (h->ev_side[i]) cudaEventDestroy(h->ev_side[i]);
     for (int i = 0; i < amps_recc_iq::kEv; ++i) { if (h->ev0[i]) cudaEventDestroy(h->ev0[i]); if (h->ev1[i]) cudaEventDestroy(h->ev1[i]); }
     cudaFree(h->d_stage); cudaFree(h->d_tail[0]); cudaFree(h->d_tail[1]); cudaFree(h->d_dring); cudaFree(h->d_hring);
@@ -273,6 +280,7 @@ extern "C" int amps_recc_iq_reset(amps_recc_iq *h) {
     std::memset(h->h_pub, 0, sizeof(RxPublished));
     h->consumed = 0; h->call_no = 0; h->overflow_seen = 0;
     for (int i = 0; i < kRxDepth; ++i) h->ev_side_valid[i] = false;
+    h->cap_par = -1;
     h->tail_cur = 0; h->carry = 0; h->dev_carry = 0; h->samples_in = 0; h->total_d = 0; h->groups_done = 0;
     h->ydump_first = 0; h->ydump_count = 0;
     return AMPS_OK;
@@ -423,8 +431,18 @@ static int rx_enqueue10(amps_recc_iq *h, const uint8_t *d_chunk, uint32_t nchunk
             RxSearchParams sp;
             sp.nchan = 1;
             const uint32_t ns = chan_search(h, sp.ch[0], par, 0);
+            // (a search that captures by itself publishes the record count: the captures still running on side2 go first)
+            if (small && !serial && h->cap_par >= 0) { CK(cudaStreamWaitEvent(sd, h->ev_side[h->cap_par], 0)); h->cap_par = -1; }
             CKL(launch_rx_search(sp, (int)ns, small, sd));
             h->launches++;
+            if (!small && !serial) {
+                // the capture gets a stream of its own: search + selection of consecutive calls are one chain (the candidate
+                // list), the captures another -- a pipelined call costs the longer of the two, not their sum
+                CK(cudaEventRecord(h->ev_sel, sd));
+                sd = h->side2;
+                CK(cudaStreamWaitEvent(sd, h->ev_sel, 0));
+                h->cap_par = (int)par;
+            }
         }
         if (!small) {
             chan_capture(h, cp.ch[0], par, 0, nc);
@@ -536,9 +554,11 @@ static int rx_fetch(amps_recc_iq *h, uint64_t *n_out, bool *overflowed) {
     *overflowed = false;
     if (h->batch) {
         CK(cudaStreamSynchronize(h->batch->side));
+        CK(cudaStreamSynchronize(h->batch->side2));
         CK(cudaStreamSynchronize(h->batch->last_stream));       // (a null handle is the default stream)
     } else {
         CK(cudaStreamSynchronize(h->side));
+        CK(cudaStreamSynchronize(h->side2));
         CK(cudaStreamSynchronize(h->last_stream));
     }
     const uint32_t ov = h->h_pub->cand_overflow;
@@ -745,7 +765,9 @@ extern "C" int amps_recc_iq_batch_create(amps_recc_iq *const *handles, int count
     b->timed = (flags & AMPS_RX_TIME_KERNELS) != 0;
     cudaError_t e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->side, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->side2, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_front, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_sel, cudaEventDisableTiming);
     for (int i = 0; i < kRxDepth && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&b->ev_side[i], cudaEventDisableTiming);
     if (b->timed)
         for (int i = 0; i < amps_recc_iq_batch::kEv && e == cudaSuccess; ++i) { e = cudaEventCreate(&b->ev0[i]); if (e == cudaSuccess) e = cudaEventCreate(&b->ev1[i]); }
@@ -762,7 +784,9 @@ extern "C" int amps_recc_iq_batch_destroy(amps_recc_iq_batch *b) {
     for (amps_recc_iq *h : b->ch) if (h->batch == b) h->batch = nullptr;
     if (b->stream) cudaStreamDestroy(b->stream);
     if (b->side) cudaStreamDestroy(b->side);
+    if (b->side2) cudaStreamDestroy(b->side2);
     if (b->ev_front) cudaEventDestroy(b->ev_front);
+    if (b->ev_sel) cudaEventDestroy(b->ev_sel);
     for (int i = 0; i < kRxDepth; ++i) if (b->ev_side[i]) cudaEventDestroy(b->ev_side[i]);
     for (int i = 0; i < amps_recc_iq_batch::kEv; ++i) { if (b->ev0[i]) cudaEventDestroy(b->ev0[i]); if (b->ev1[i]) cudaEventDestroy(b->ev1[i]); }
     cudaFree(b->d_stage);
@@ -780,7 +804,7 @@ static int batch_enqueue(amps_recc_iq_batch *b, const void *const *d_iq, const s
     if (b->call_no >= (uint64_t)kRxDepth) CK(cudaStreamWaitEvent(st, b->ev_side[par], 0));
     const uint32_t resident = (uint32_t)rx_front_ctas_per_sm(b->sc16) * (uint32_t)b->sm_count;
     const int evi = (int)(b->ev_count % amps_recc_iq_batch::kEv);
-    if (b->timed) CK(cudaEventRecord(b->ev0[evi], st));
+    bool ev0_done = !b->timed;
     cudaStream_t sd = b->side;
     static thread_local RxFrontParamsB p;                  // 24 KB: not on the stack
     size_t i = 0;
@@ -826,6 +850,7 @@ static int batch_enqueue(amps_recc_iq_batch *b, const void *const *d_iq, const s
         p.nchan = n;
         cp.nchan = n;
         const uint32_t grid = rx_make_deal(p.deal, tiles, resident, n, all_equal ? eq_tiles : 0u);
+        if (!ev0_done) { CK(cudaEventRecord(b->ev0[evi], st)); ev0_done = true; }      // (after the host-side set-up)
         CKL(launch_rx_front_batch(p, (int)grid, st, b->sc16, b->sc16_unit, !split && !mm));
         b->launches++;
         caps.push_back(cp);
@@ -833,14 +858,22 @@ static int batch_enqueue(amps_recc_iq_batch *b, const void *const *d_iq, const s
         if (split) { sp.nchan = n; srch.push_back(sp); srch_grid.push_back(srch_ctas); }
         if (mm) { mp.nchan = n; mms.push_back(mp); }
     }
+    if (b->timed && !ev0_done) CK(cudaEventRecord(b->ev0[evi], st));                 // (no channel had a whole unit)
     if (b->timed) { CK(cudaEventRecord(b->ev1[evi], st)); b->ev_count++; }
     CK(cudaEventRecord(b->ev_front, st));
     CK(cudaStreamWaitEvent(sd, b->ev_front, 0));
+    if (b->ch[0]->front_only) caps.clear();               // (AMPS_RX_FRONT_ONLY: a measurement switch, see tools/roofline_sweep.py)
     for (size_t k = 0; k < caps.size(); ++k) {
         if (split) { CKL(launch_rx_search(srch[k], (int)srch_grid[k], false, sd)); b->launches++; }
         if (mm) { CKL(launch_rx_mm(mms[k], sd)); b->launches += 2; }
-        CKL(launch_rx_capture(caps[k], (int)cap_grid[k], sd));
-        b->launches++;
+        if (!split) { CKL(launch_rx_capture(caps[k], (int)cap_grid[k], sd)); b->launches++; }
+    }
+    if (split && !caps.empty()) {
+        // the captures on a stream of their own, behind every selection of this call (see rx_enqueue10)
+        CK(cudaEventRecord(b->ev_sel, sd));
+        sd = b->side2;
+        CK(cudaStreamWaitEvent(sd, b->ev_sel, 0));
+        for (size_t k = 0; k < caps.size(); ++k) { CKL(launch_rx_capture(caps[k], (int)cap_grid[k], sd)); b->launches++; }
     }
     CK(cudaEventRecord(b->ev_side[par], sd));
     b->call_no++;

@@ -250,8 +250,8 @@ __device__ __noinline__ void select_channel(RxState *state, Candidate *cand, Can
         state->n_acc[par] = na;
         state->rec_base[par] = state->nrec_total;
         state->nrec_total += na;
-        if (na == 0 && state->cand_overflow != state->pub_overflow) {     // nothing for the capture kernel to publish
-            state->pub_overflow = state->cand_overflow;
+        if (state->cand_overflow != state->pub_overflow) {     // (rare; the capture of an earlier call may be running on its own
+            state->pub_overflow = state->cand_overflow;        //  stream right now: in this mode only the selection publishes this)
             __threadfence_system();
             host_pub->cand_overflow = state->cand_overflow;
         }
@@ -483,16 +483,24 @@ struct FrontSmem {
     float2   pb[3][2][kTB];               // [tile % 3][P1|P2][block] rotated CIC partial sums (3 buffers: a tile reads its
                                           // own and the previous tile's, the next tile may already be writing)
     uint64_t full[kStages];
-    uint32_t hw[kHwRing];                 // the segment's newest hard decisions (trigger search without a trip to L2)
     uint32_t is_last;                     // this CTA is the last one of the channel to finish
+    uint32_t pad;
+};
+// what only the instance with the trigger search inside needs: it follows FrontSmem in the dynamic shared memory of that
+// instance alone, so that next to two CTAs of the default instance an SM has room for a search AND a capture CTA
+struct FusedSmem {
+    uint32_t hw[kHwRing];                 // the segment's newest hard decisions (trigger search without a trip to L2)
     uint32_t nb;                          // boundaries this CTA contributes to: whose (CTA index), the counter value that
     uint32_t bj[kMaxBound];               // means "everybody else has been here", and whether this CTA was the last to arrive
     uint32_t bneed[kMaxBound];
     uint32_t bmine[kMaxBound];
+    uint32_t pad;
     SearchScratch sc;
 };
+template <typename In, bool kFused>
+constexpr size_t front_smem_bytes() { return sizeof(FrontSmem<In>) + (kFused ? sizeof(FusedSmem) : 0); }
 
-size_t rx_front_smem_bytes() { return sizeof(FrontSmem<float2>); }
+size_t rx_front_smem_bytes() { return front_smem_bytes<float2, false>(); }
 
 __host__ __device__ constexpr int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
@@ -643,9 +651,21 @@ __device__ __forceinline__ void copy_tail(const RxChan &ch, const RxDeal &d, uin
     const In *tl = static_cast<const In *>(ch.tail) + (long)kHist;
     const In *ck = static_cast<const In *>(ch.chunk) - (long)ch.carry;
     In *dst = static_cast<In *>(ch.tail_out);
-    for (uint32_t i = lo + (uint32_t)t; i < hi; i += kTB) {
-        const long L = first + (long)i;
-        dst[i] = L < (long)ch.carry ? tl[L] : ck[L];
+    // (eight loads in flight per thread: with few CTAs on a channel a slice is a dozen rounds of DRAM latency otherwise)
+    constexpr int kB = 8;
+    for (uint32_t i0 = lo + (uint32_t)t; i0 < hi; i0 += kB * kTB) {
+        In v[kB];
+#pragma unroll
+        for (int j = 0; j < kB; ++j) {
+            const uint32_t i = i0 + (uint32_t)(j * kTB);
+            const long L = first + (long)i;
+            if (i < hi) v[j] = L < (long)ch.carry ? __ldg(tl + L) : __ldg(ck + L);
+        }
+#pragma unroll
+        for (int j = 0; j < kB; ++j) {
+            const uint32_t i = i0 + (uint32_t)(j * kTB);
+            if (i < hi) dst[i] = v[j];
+        }
     }
 }
 
@@ -655,6 +675,7 @@ template <typename In, bool kUnitScale, int kMaxChan, bool kFused>
 __device__ __forceinline__ void run_segment(const RxFrontParamsT<kMaxChan> &p, const RxChan &ch, FrontSmem<In> *sm,
                                             uint32_t ta, uint32_t tb, uint32_t &it, int t, const RxDeal &dl, uint32_t cta,
                                             uint32_t cbase, uint32_t cend) {
+    FusedSmem *fs = reinterpret_cast<FusedSmem *>(sm + 1);               // (exists in the kFused instance only)
     const int  ntiles = (int)(tb - ta) + kWarmTiles;
     const long tj0    = (long)ta - kWarmTiles;                          // channel tile index of tile i = 0
     const uint32_t U  = ch.units;
@@ -666,7 +687,7 @@ __device__ __forceinline__ void run_segment(const RxFrontParamsT<kMaxChan> &p, c
     };
     const In *chunk0 = static_cast<const In *>(ch.chunk) - (long)ch.carry;      // logical sample 0 of the chunk (virtual)
     PassOut o;
-    o.dring = ch.dring; o.hring = ch.hring; o.ydump = ch.ydump; o.dmask = ch.dmask; o.hw = (kFused && ch.search) ? sm->hw : nullptr;
+    o.dring = ch.dring; o.hring = ch.hring; o.ydump = ch.ydump; o.dmask = ch.dmask; o.hw = (kFused && ch.search) ? fs->hw : nullptr;
     const uint32_t useg = ((uint32_t)kTileUnits * tb < U ? (uint32_t)kTileUnits * tb : U) - (uint32_t)kTileUnits * ta;   // units of the segment
     const unsigned long long ql0 = (unsigned long long)kUnitOut * kTileUnits * ta;     // first output, relative to the call
     // first group that reads nothing in front of the segment (the groups below it are searched in finish_segment)
@@ -753,8 +774,8 @@ __device__ __forceinline__ void run_segment(const RxFrontParamsT<kMaxChan> &p, c
                 if (g_end > g_next) {                      // (at most 24 groups: one pass)
                     __syncthreads();                       // the pass's decisions are in the ring (and its demod samples in L2)
                     const unsigned long long g = g_next + (unsigned long long)t;
-                    const uint32_t m0 = g < g_end ? group_match_smem(sm->hw, 32ull * g) : 0u;
-                    if (__syncthreads_or(m0 != 0u)) resolve_round(ch.dring, ch.hring, ch.dmask, ch.state, ch.cand, g_next, m0, &sm->sc, sm->hw);
+                    const uint32_t m0 = g < g_end ? group_match_smem(fs->hw, 32ull * g) : 0u;
+                    if (__syncthreads_or(m0 != 0u)) resolve_round(ch.dring, ch.hring, ch.dmask, ch.state, ch.cand, g_next, m0, &fs->sc, fs->hw);
                     g_next = g_end;
                 }
             }
@@ -797,6 +818,7 @@ __device__ __forceinline__ void finish_segment(const RxFrontParamsT<kMaxChan> &p
     const unsigned long long qe = ch.q_base + (unsigned long long)kUnitOut * ((uint32_t)kTileUnits * tb < U ? (uint32_t)kTileUnits * tb : U);
     const unsigned long long total_d = ch.q_base + (unsigned long long)kUnitOut * U;
     if constexpr (!kFused) { RX_PROF(p, 3); RX_PROF(p, 7); return; }      // search and selection are a launch of their own
+    FusedSmem *fs = reinterpret_cast<FusedSmem *>(sm + 1);
     RxState *state = ch.state;
     const uint32_t k1 = deal_owner(dl, cend - 1);             // last segment of the channel
     __syncthreads();                                      // this CTA's demod samples and decisions are visible to all its threads
@@ -811,45 +833,45 @@ __device__ __forceinline__ void finish_segment(const RxFrontParamsT<kMaxChan> &p
                 if (sj.lo == 0u) continue;                // the channel's first segment of the call: nothing in front of it in this launch
                 const uint32_t first = boundary_first(dl, cbase, sj.lo);
                 if (first > seg) break;                   // segment j (and everything behind it) does not read my output
-                sm->bj[n] = j;
-                sm->bneed[n] = j - first;                 // counter value the last arrival sees
+                fs->bj[n] = j;
+                fs->bneed[n] = j - first;                 // counter value the last arrival sees
                 ++n;
             }
-            sm->nb = n;
+            fs->nb = n;
         }
         __syncthreads();
-        const uint32_t nb = sm->nb;
+        const uint32_t nb = fs->nb;
         if ((uint32_t)t < nb) {
-            const uint32_t j = sm->bj[t];
+            const uint32_t j = fs->bj[t];
             const uint32_t prev = atomicAdd(&ch.flags[j], 1u);
-            const bool mine = prev == sm->bneed[t];
+            const bool mine = prev == fs->bneed[t];
             if (mine) ch.flags[j] = 0u;                   // everybody has been here: ready for the next launch
-            sm->bmine[t] = mine ? 1u : 0u;
+            fs->bmine[t] = mine ? 1u : 0u;
         }
         // (the groups that read only this segment's own output were searched pass by pass in run_segment)
         RX_PROF(p, 4);
         if (ta == 0) {
             // ---- the channel's first segment of the call: its front groups read the previous calls' output, which is in place
             const SegGroups g = seg_groups(qs, qe, false);
-            search_groups(ch.dring, ch.hring, ch.dmask, state, ch.cand, g.lo, g.mid, &sm->sc);
+            search_groups(ch.dring, ch.hring, ch.dmask, state, ch.cand, g.lo, g.mid, &fs->sc);
         }
         // ---- the boundaries this CTA was the last to reach
         __syncthreads();
         for (uint32_t i = 0; i < nb; ++i) {
-            if (!sm->bmine[i]) continue;
+            if (!fs->bmine[i]) continue;
             __threadfence();
-            const SegTiles sj = seg_tiles(dl, sm->bj[i], cbase, cend);
+            const SegTiles sj = seg_tiles(dl, fs->bj[i], cbase, cend);
             const unsigned long long js = ch.q_base + (unsigned long long)kUnitOut * kTileUnits * sj.lo;
             const uint32_t ju = (uint32_t)kTileUnits * sj.hi;
             const unsigned long long je = ch.q_base + (unsigned long long)kUnitOut * (ju < U ? ju : U);
             const SegGroups gj = seg_groups(js, je, false);
-            search_groups(ch.dring, ch.hring, ch.dmask, state, ch.cand, gj.lo, gj.mid, &sm->sc);
+            search_groups(ch.dring, ch.hring, ch.dmask, state, ch.cand, gj.lo, gj.mid, &fs->sc);
         }
     }
     __syncthreads();
     RX_PROF(p, 5);
     if (t == 0) {
-        if (ch.search) flush_candidates(state, ch.cand, &sm->sc);
+        if (ch.search) flush_candidates(state, ch.cand, &fs->sc);
         __threadfence();
         const uint32_t n_touch = k1 - deal_owner(dl, cbase) + 1u;
         const unsigned int prev = atomicAdd(&state->front_done, 1u);
@@ -880,7 +902,7 @@ __global__ void __launch_bounds__(kTB, kMinCtas) rx_front_kernel(const __grid_co
     if (t == 0) {
         for (int s = 0; s < kStages; ++s) mbar_init(&sm->full[s], 1);
         mbar_fence_init();
-        sm->sc.nlc = 0u;
+        if constexpr (kFused) reinterpret_cast<FusedSmem *>(sm + 1)->sc.nlc = 0u;
     }
     uint32_t it = 0;
     if constexpr (kMaxChan == 1) {
@@ -957,9 +979,9 @@ constexpr int kSc16Ctas = 3;
 constexpr int kFc32Regs = 2;
 template <int kMaxChan, bool kFused, typename P>
 static cudaError_t launch_front_t(const P &p, int grid, cudaStream_t st, bool sc16, bool unit) {
-    if (sc16 && unit) rx_front_kernel<short2, kSc16Ctas, true, kMaxChan, kFused><<<grid, kTB, sizeof(FrontSmem<short2>), st>>>(p);
-    else if (sc16) rx_front_kernel<short2, kSc16Ctas, false, kMaxChan, kFused><<<grid, kTB, sizeof(FrontSmem<short2>), st>>>(p);
-    else rx_front_kernel<float2, kFc32Regs, false, kMaxChan, kFused><<<grid, kTB, sizeof(FrontSmem<float2>), st>>>(p);
+    if (sc16 && unit) rx_front_kernel<short2, kSc16Ctas, true, kMaxChan, kFused><<<grid, kTB, front_smem_bytes<short2, kFused>(), st>>>(p);
+    else if (sc16) rx_front_kernel<short2, kSc16Ctas, false, kMaxChan, kFused><<<grid, kTB, front_smem_bytes<short2, kFused>(), st>>>(p);
+    else rx_front_kernel<float2, kFc32Regs, false, kMaxChan, kFused><<<grid, kTB, front_smem_bytes<float2, kFused>(), st>>>(p);
     return cudaGetLastError();
 }
 cudaError_t launch_rx_front(const RxFrontParams1 &p, int grid, cudaStream_t st, bool sc16, bool unit, bool fused) {
@@ -1078,9 +1100,7 @@ __global__ void __launch_bounds__(256) rx_search_kernel(const __grid_constant__ 
                 capture_burst(ch.dring, ch.dmask, ch.acc + (size_t)ch.par * kMaxAccept, nullptr, nullptr, ch.decim, ch.host_ring, ch.ring_len,
                               rec_base, b, n_acc, reinterpret_cast<amps_burst *>(rec_raw), s_valid, s_errs);
             if (threadIdx.x == 0 && n_acc > 0) {
-                state->pub_overflow = state->cand_overflow;
                 __threadfence_system();
-                ch.host_pub->cand_overflow = state->cand_overflow;
                 ch.host_pub->nrec_total = rec_base + n_acc;
             }
         }
@@ -1117,9 +1137,9 @@ __global__ void __launch_bounds__(256) rx_capture_kernel(const __grid_constant__
             const unsigned int prev = atomicAdd(&state->done, 1u);
             if (prev + 1 == n_acc) {                          // last burst of the call: every record is on its way, publish the count
                 state->done = 0;
-                state->pub_overflow = state->cand_overflow;
+                if (ch.blobs) state->pub_overflow = state->cand_overflow;      // M&M mode: no selection, amps.recc counts the surplus
                 __threadfence_system();
-                ch.host_pub->cand_overflow = state->cand_overflow;
+                if (ch.blobs) ch.host_pub->cand_overflow = state->cand_overflow;
                 ch.host_pub->nrec_total = rec_base + n_acc;
             }
         }
@@ -1264,9 +1284,9 @@ static cudaError_t front_attrs(K kernel, size_t smem) {
 template <int kMaxChan, bool kFused>
 static cudaError_t front_attrs_all() {
     cudaError_t e;
-    if ((e = front_attrs(rx_front_kernel<float2, kFc32Regs, false, kMaxChan, kFused>, sizeof(FrontSmem<float2>))) != cudaSuccess) return e;
-    if ((e = front_attrs(rx_front_kernel<short2, kSc16Ctas, false, kMaxChan, kFused>, sizeof(FrontSmem<short2>))) != cudaSuccess) return e;
-    return front_attrs(rx_front_kernel<short2, kSc16Ctas, true, kMaxChan, kFused>, sizeof(FrontSmem<short2>));
+    if ((e = front_attrs(rx_front_kernel<float2, kFc32Regs, false, kMaxChan, kFused>, front_smem_bytes<float2, kFused>())) != cudaSuccess) return e;
+    if ((e = front_attrs(rx_front_kernel<short2, kSc16Ctas, false, kMaxChan, kFused>, front_smem_bytes<short2, kFused>())) != cudaSuccess) return e;
+    return front_attrs(rx_front_kernel<short2, kSc16Ctas, true, kMaxChan, kFused>, front_smem_bytes<short2, kFused>());
 }
 cudaError_t rx_configure_device() {
     cudaError_t e;
