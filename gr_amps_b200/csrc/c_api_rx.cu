@@ -63,6 +63,7 @@ struct amps_recc_iq {
     bool         ev_side_valid[kRxDepth] = {};      // ... and whether call k used the side stream at all
     uint64_t     call_no = 0;
     bool         serial = false;         // AMPS_RX_SERIAL=1: no overlap (profiling / A-B measurements)
+    bool         one_side = false;       // AMPS_RX_ONE_SIDE=1: search and capture share one side stream (A/B measurements)
     bool         front_only = false;     // AMPS_RX_FRONT_ONLY=1: no capture (pipeline measurements only: no bursts come out)
     int          grid_cap = 0;           // AMPS_RX_GRID (test hook): cap on the front kernel's grid
     bool         want_prof = false;      // AMPS_RX_PROF=1 (measurement aid): per-CTA time stamps of the last front launch
@@ -208,6 +209,7 @@ extern "C" int amps_recc_iq_create(const amps_recc_iq_params *params, amps_recc_
     h->isz = h->sc16 ? sizeof(short2) : sizeof(float2);
     { const char *e = std::getenv("AMPS_RX_SERIAL"); h->serial = e && e[0] == '1'; }
     { const char *e = std::getenv("AMPS_RX_FRONT_ONLY"); h->front_only = e && e[0] == '1'; }
+    { const char *e = std::getenv("AMPS_RX_ONE_SIDE"); h->one_side = e && e[0] == '1'; }
     { const char *e = std::getenv("AMPS_RX_GRID"); h->grid_cap = e ? std::atoi(e) : 0; }
     { const char *e = std::getenv("AMPS_RX_NOSEARCH"); h->nosearch = e && e[0] == '1'; }
     { const char *e = std::getenv("AMPS_RX_PROF"); h->want_prof = e && e[0] == '1'; }
@@ -435,7 +437,7 @@ static int rx_enqueue10(amps_recc_iq *h, const uint8_t *d_chunk, uint32_t nchunk
             if (small && !serial && h->cap_par >= 0) { CK(cudaStreamWaitEvent(sd, h->ev_side[h->cap_par], 0)); h->cap_par = -1; }
             CKL(launch_rx_search(sp, (int)ns, small, sd));
             h->launches++;
-            if (!small && !serial) {
+            if (!small && !serial && !h->one_side) {
                 // the capture gets a stream of its own: search + selection of consecutive calls are one chain (the candidate
                 // list), the captures another -- a pipelined call costs the longer of the two, not their sum
                 CK(cudaEventRecord(h->ev_sel, sd));
@@ -868,7 +870,9 @@ static int batch_enqueue(amps_recc_iq_batch *b, const void *const *d_iq, const s
         if (mm) { CKL(launch_rx_mm(mms[k], sd)); b->launches += 2; }
         if (!split) { CKL(launch_rx_capture(caps[k], (int)cap_grid[k], sd)); b->launches++; }
     }
-    if (split && !caps.empty()) {
+    if (split && !caps.empty() && b->ch[0]->one_side) {
+        for (size_t k = 0; k < caps.size(); ++k) { CKL(launch_rx_capture(caps[k], (int)cap_grid[k], sd)); b->launches++; }
+    } else if (split && !caps.empty()) {
         // the captures on a stream of their own, behind every selection of this call (see rx_enqueue10)
         CK(cudaEventRecord(b->ev_sel, sd));
         sd = b->side2;

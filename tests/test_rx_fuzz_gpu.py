@@ -117,3 +117,38 @@ def test_random_batches(capi, oracle, seed):
     b.close()
     for h in hs:
         h.close()
+
+
+@pytest.mark.parametrize("collect_between", [False, True])
+def test_mixed_call_sizes_pipelined(capi, oracle, collect_between):
+    """Device-resident calls of very different lengths back to back without a synchronisation in between: calls short enough
+    that the search kernel captures by itself (< 1.7 M samples) alternate with calls whose capture is a launch of its own on
+    its own stream -- the records must come out complete, in stream order and equal to the one-shot oracle's."""
+    torch = pytest.importorskip("torch")
+    xs = []
+    for i, lead in enumerate((20000, 380000, 300000, 40000, 150000, 250000)):
+        c = multi.carrier(0)
+        x, _, _ = synth.config2_period(n_total=N1, snr_db=[None, 30.0, 15.0][i % 3], seed=4100 + i, center=c.center_freq,
+                                       min10="21255588%02d" % i, lead=lead)
+        xs.append(x)
+    x = np.concatenate(xs)
+    _, d = oracle.rx_chain_f32(x)
+    ob = oracle.rx_detect(d)
+    assert len(ob) == 6
+    sizes = [2200000, 64000, 1900000, 300000, 2400000, 1600, 1800000, 2, 2500000, 120000, 1730000, 500000]
+    rx = capi.ReccIq(max_samples=2500000, max_bursts=64)
+    t = torch.from_numpy(x.view(np.float32).copy()).cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    got, pos, k = [], 0, 0
+    while pos < len(x):
+        n = min(sizes[k % len(sizes)], len(x) - pos)
+        rx.submit_dev(t.data_ptr() + 8 * pos, n, st)
+        pos += n
+        k += 1
+        if collect_between and k % 3 == 0:
+            got += rx.collect()
+    got += rx.collect()
+    assert rx.stats()["demod_out"] == len(x) // 50
+    check(got, ob, oracle)
+    assert [g.demod_index for g in got] == sorted(g.demod_index for g in got)
+    rx.close()
