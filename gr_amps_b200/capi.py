@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libamps_b200.so")
+LIB_PATH = os.environ.get("AMPS_B200_LIB") or os.path.join(PKG_DIR, "libamps_b200.so")      # (the override: A/B runs of two builds)
 
 TRIGGER_SYMS = 74
 CAPTURE_SYMS = 3374

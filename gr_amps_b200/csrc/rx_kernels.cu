@@ -652,7 +652,10 @@ __device__ __forceinline__ void copy_tail(const RxChan &ch, const RxDeal &d, uin
     const In *ck = static_cast<const In *>(ch.chunk) - (long)ch.carry;
     In *dst = static_cast<In *>(ch.tail_out);
     // (eight loads in flight per thread: with few CTAs on a channel a slice is a dozen rounds of DRAM latency otherwise)
-    constexpr int kB = 8;
+#ifndef AMPS_TAIL_BATCH
+#define AMPS_TAIL_BATCH 8
+#endif
+    constexpr int kB = AMPS_TAIL_BATCH;
     for (uint32_t i0 = lo + (uint32_t)t; i0 < hi; i0 += kB * kTB) {
         In v[kB];
 #pragma unroll
