@@ -133,7 +133,7 @@ typedef struct amps_recc_iq_params {
                                       bit-identical to feeding amps_recc_iq_work() the converted floats. */
 
 #define AMPS_RX_FUSED_SEARCH  16u  /* 10 MS/s: run the trigger search and the burst selection INSIDE the front kernel (two launches per
-                                      call: front, capture) instead of as a launch of their own on the side stream (three).  Same
+                                      call: front, capture) instead of as a launch of their own on a side stream (three; two for calls under 1.7 M samples).  Same
                                       results bit for bit.  Saves a launch; costs the front kernel its tail (the search of the last
                                       CTAs to finish cannot overlap anything), so the default keeps it outside -- DESIGN.md 4.2 has
                                       the measurements. */
@@ -160,8 +160,11 @@ AMPS_B200_API int amps_recc_iq_work_sc16(amps_recc_iq *h, const int16_t *iq_host
                                          amps_burst_cb cb, void *user);
 
 /* Device-resident variant: d_iq is a device pointer (16-byte aligned) on the handle's device; kernels are
- * enqueued on cuda_stream (a cudaStream_t, NULL = default stream) and the call returns without synchronising:
- * one front launch (filter + demod + trigger search + burst selection) and one capture launch per call.
+ * enqueued and the call returns without synchronising: the front launch (filter + demod) on cuda_stream (a
+ * cudaStream_t, NULL = default stream); the trigger search + burst selection and the capture on two streams of the
+ * handle's own, ordered behind it by events, so that they overlap the front kernels of the next calls (up to four
+ * calls deep; the call after that waits on the device, not on the host).  d_iq may be reused as soon as cuda_stream
+ * has passed the call (its last samples are copied into the handle's history by the front kernel itself).
  * At 10 MS/s nsamples may be any count whose bytes are a multiple of 16 (fc32: even, sc16: multiple of 4):
  * what does not fill a 1600-sample quantum is carried, on the device, into the next call.  At 400 kS/s
  * nsamples must be a multiple of amps_recc_iq_granularity(). */
