@@ -432,6 +432,7 @@ static int rx_enqueue10(amps_recc_iq *h, const uint8_t *d_chunk, uint32_t nchunk
             // trigger search + selection as their own launch, overlapped (like the capture) with the next call's front kernel
             RxSearchParams sp;
             sp.nchan = 1;
+            sp.prof = h->d_prof;
             const uint32_t ns = chan_search(h, sp.ch[0], par, 0);
             // (a search that captures by itself publishes the record count: the captures still running on side2 go first)
             if (small && !serial && h->cap_par >= 0) { CK(cudaStreamWaitEvent(sd, h->ev_side[h->cap_par], 0)); h->cap_par = -1; }

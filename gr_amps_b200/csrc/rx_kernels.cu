@@ -35,12 +35,12 @@ __device__ __forceinline__ unsigned long long global_ns() {
 // ============================================================================================
 // 74 half-symbols: Manchester("10" x 13 + "11100010010"), bit 0 -> (1,0), bit 1 -> (0,1)
 // (lib/recc_impl.cc:51-65,76).
-__device__ __constant__ uint8_t c_trig[kTrig] = {
-    0,1,1,0,0,1,1,0,0,1,1,0,0,1,1,0,0,1,1,0,0,1,1,0,0,1,1,0,0,1,1,0,0,1,1,0,0,1,1,0,0,1,1,0,0,1,1,0,0,1,1,0,
-    0,1,0,1,0,1,1,0,1,0,1,0,0,1,1,0,1,0,0,1,1,0};
-
+//   0,1,1,0 x 13 | 0,1,0,1,0,1,1,0,1,0,1,0,0,1,1,0,1,0,0,1,1,0
 // 74-symbol trigger packed LSB-first (symbol k = bit k)
 __device__ __constant__ uint32_t c_trig_bits[3] = {0x66666666u, 0x56A66666u, 0x00000196u};
+__host__ __device__ constexpr uint32_t trig_bit(int k) {                             // (the same, folded where k is a constant)
+    return ((k < 32 ? 0x66666666u : k < 64 ? 0x56A66666u : 0x00000196u) >> (k & 31)) & 1u;
+}
 
 // The rings are read with ld.global.cg: inside rx_front_kernel the words were written during this very launch, some of them
 // by other SMs, and an L1 line fetched earlier by a co-resident CTA may predate them.
@@ -132,7 +132,7 @@ __device__ __noinline__ void resolve_group(const float *__restrict__ dring, cons
     if (t < 42 && ((M >> t) & 1ull)) {
         float c = 0.0f;
 #pragma unroll
-        for (int k = 0; k < kTrig; ++k) { const float v = sc->d[t + kOS * k]; c = __fadd_rn(c, c_trig[k] ? v : -v); }
+        for (int k = 0; k < kTrig; ++k) { const float v = sc->d[t + kOS * k]; c = __fadd_rn(c, trig_bit(k) ? v : -v); }
         sc->corr[t] = c;
     }
     __syncthreads();
@@ -1070,6 +1070,8 @@ __global__ void __launch_bounds__(256) rx_search_kernel(const __grid_constant__ 
     __shared__ uint32_t s_last;
     __shared__ SearchScratch sc;
     __shared__ Candidate s_cand[64];                   // (small: this CTA must fit on an SM next to two front-kernel CTAs)
+#define S_PROF(k) do { if (p.prof && blockIdx.x == 0 && threadIdx.x == 0) p.prof[9 + (k)] = global_ns(); } while (0)
+    S_PROF(0);
     uint32_t c = 0;
     while (c + 1 < p.nchan && blockIdx.x >= p.ch[c + 1].cta_first) ++c;
     const RxSearchChan &ch = p.ch[c];
@@ -1082,15 +1084,18 @@ __global__ void __launch_bounds__(256) rx_search_kernel(const __grid_constant__ 
     if (hi > ch.g_hi) hi = ch.g_hi;
     search_groups(ch.dring, ch.hring, ch.dmask, ch.state, ch.cand, lo, hi, &sc);
     __syncthreads();
+    S_PROF(1);
     if (threadIdx.x == 0) {
         flush_candidates(ch.state, ch.cand, &sc);
         __threadfence();
         s_last = atomicAdd(&ch.state->search_done, 1u) + 1u == ch.cta_count ? 1u : 0u;
     }
     __syncthreads();
+    S_PROF(2);
     if (s_last) {
         __threadfence();
         select_channel(ch.state, ch.cand, ch.cand + kMaxCand, ch.acc + (size_t)ch.par * kMaxAccept, ch.par, ch.total_d, ch.host_pub, s_cand, 64u);
+        S_PROF(3);
         if (threadIdx.x == 0) ch.state->search_done = 0u;
         if constexpr (kCapture2) {
             __shared__ __align__(16) unsigned char rec_raw[sizeof(amps_burst)];
@@ -1108,6 +1113,8 @@ __global__ void __launch_bounds__(256) rx_search_kernel(const __grid_constant__ 
             }
         }
     }
+    S_PROF(4);
+#undef S_PROF
 }
 
 cudaError_t launch_rx_search(const RxSearchParams &p, int grid, bool capture_too, cudaStream_t st) {

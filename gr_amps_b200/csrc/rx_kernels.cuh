@@ -193,6 +193,7 @@ struct RxSearchChan {
 };
 struct RxSearchParams {
     uint32_t     nchan;
+    unsigned long long *prof = nullptr;    // measurement aid (AMPS_RX_PROF=1): CTA 0 stamps slots 9..15 of the front kernel's first record
     RxSearchChan ch[kMaxBatch];
 };
 // CTAs a channel with `groups` groups to search gets
