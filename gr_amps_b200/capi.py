@@ -97,7 +97,7 @@ EXPORTS = [
     "amps_b200_version", "amps_b200_strerror", "amps_b200_last_error", "amps_b200_device_count", "amps_b200_abi_sizes",
     "amps_recc_iq_create", "amps_recc_iq_destroy", "amps_recc_iq_reset", "amps_recc_iq_work",
     "amps_recc_iq_submit_dev", "amps_recc_iq_work_sc16", "amps_recc_iq_submit_sc16_dev", "amps_recc_iq_collect", "amps_recc_iq_peek", "amps_recc_iq_consume", "amps_recc_iq_poll", "amps_recc_iq_granularity", "amps_recc_iq_read_demod",
-    "amps_recc_iq_read_baseband", "amps_recc_iq_stats", "amps_recc_iq_front_times", "amps_recc_iq_get_taps", "amps_recc_iq_debug_prof",
+    "amps_recc_iq_read_baseband", "amps_recc_iq_stats", "amps_recc_iq_front_times", "amps_recc_iq_get_taps", "amps_recc_iq_debug_prof", "amps_b200_debug_deal",
     "amps_recc_iq_batch_create", "amps_recc_iq_batch_destroy", "amps_recc_iq_batch_size", "amps_recc_iq_batch_submit_dev",
     "amps_recc_iq_batch_work_shared", "amps_recc_iq_batch_front_times", "amps_recc_iq_batch_stats",
     "amps_recc_decode_create", "amps_recc_decode_destroy", "amps_recc_decode_burst", "amps_recc_decode_bursts",

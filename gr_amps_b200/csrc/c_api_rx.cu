@@ -727,6 +727,18 @@ extern "C" int amps_recc_iq_front_times(amps_recc_iq *h, float *ms_out, int cap,
     return event_times(h->ev0, h->ev1, h->ev_count, amps_recc_iq::kEv, ms_out, cap, n_out);
 }
 
+// test aid (pure host arithmetic, no device needed): how `tiles` tiles of `nchan` channels would be dealt to CTAs
+extern "C" int amps_b200_debug_deal(uint32_t tiles, uint32_t resident, uint32_t nchan, uint32_t equal_tiles, uint32_t *grid_out,
+                                    uint32_t *lo_out, uint32_t *owner_out) {
+    if (!grid_out || !lo_out || !owner_out || tiles == 0) return set_error(AMPS_E_INVAL, "null argument or no tiles");
+    RxDeal d;
+    const uint32_t grid = rx_make_deal(d, tiles, resident, nchan, equal_tiles);
+    *grid_out = grid;
+    for (uint32_t s = 0; s <= grid; ++s) lo_out[s] = deal_lo(d, s);
+    for (uint32_t t = 0; t < tiles; ++t) owner_out[t] = deal_owner(d, t);
+    return AMPS_OK;
+}
+
 extern "C" int amps_recc_iq_debug_prof(amps_recc_iq *h, unsigned long long *out, int ctas) {
     if (!h || !out || ctas < 0 || ctas > kMaxGrid) return set_error(AMPS_E_INVAL, "bad argument");
     if (!h->d_prof) return set_error(AMPS_E_STATE, "create the handle with AMPS_RX_PROF=1 in the environment");

@@ -598,14 +598,7 @@ __device__ __forceinline__ void finish_pass(const float (&h2)[300], const PassOu
 // ---- how a launch's tiles are dealt: the Tt tiles are split evenly, CTA s owns tiles [Tt*s/grid, Tt*(s+1)/grid) -- its
 // SEGMENTS (one per channel the range touches).  (A pool of late segments for CTAs that finish early was tried on the
 // 2^28-sample batch: the spread between CTAs is not removed by it and the extra warm-up tiles cost 2 %.)
-__device__ __forceinline__ uint32_t deal_lo(const RxDeal &d, uint32_t s) {
-    if (d.P) return (s / d.P) * d.Tc + (uint32_t)((unsigned long long)d.Tc * (s % d.P) / d.P);       // (s == nstat gives Tt)
-    return (uint32_t)((unsigned long long)d.Tt * s / d.nstat);
-}
-__device__ __forceinline__ uint32_t deal_owner(const RxDeal &d, uint32_t tile) {
-    if (d.P) return (tile / d.Tc) * d.P + (uint32_t)((((unsigned long long)(tile % d.Tc) + 1ull) * d.P - 1ull) / d.Tc);
-    return (uint32_t)((((unsigned long long)tile + 1ull) * d.nstat - 1ull) / d.Tt);
-}
+// (deal_lo() / deal_owner(): rx_kernels.cuh -- the host-side tests walk them too)
 
 // samples [L0, L0 + n) of a channel's logical stream -> shared memory; logical samples below `carry` live in the tail
 // buffer (history + what the previous call could not use), the rest in this call's chunk; a tile may straddle the seam

@@ -117,6 +117,16 @@ struct RxDeal {
 // channel and starts the next pays a second warm-up and a cold restart of its copy ring.
 uint32_t rx_make_deal(RxDeal &d, uint32_t tiles, uint32_t resident, uint32_t nchan = 1, uint32_t equal_tiles = 0);
 
+// first tile of CTA s (s == nstat gives Tt) and the CTA that owns a tile
+__host__ __device__ __forceinline__ uint32_t deal_lo(const RxDeal &d, uint32_t s) {
+    if (d.P) return (s / d.P) * d.Tc + (uint32_t)((unsigned long long)d.Tc * (s % d.P) / d.P);
+    return (uint32_t)((unsigned long long)d.Tt * s / d.nstat);
+}
+__host__ __device__ __forceinline__ uint32_t deal_owner(const RxDeal &d, uint32_t tile) {
+    if (d.P) return (tile / d.Tc) * d.P + (uint32_t)((((unsigned long long)(tile % d.Tc) + 1ull) * d.P - 1ull) / d.Tc);
+    return (uint32_t)((((unsigned long long)tile + 1ull) * d.nstat - 1ull) / d.Tt);
+}
+
 template <int kMaxChan>
 struct RxFrontParamsT {
     float     g[75];         // CIC^3 taps (73 + 2 zeros)

@@ -195,6 +195,11 @@ AMPS_B200_API int amps_recc_iq_get_taps(const amps_recc_iq *h, float *lpf_out, i
 /* Measurement aid (handles created while AMPS_RX_PROF=1 is in the environment): 16 %globaltimer stamps (ns) per CTA of the
  * most recent 10 MS/s front launch -- tools/front_phases.py turns them into a phase breakdown. */
 AMPS_B200_API int amps_recc_iq_debug_prof(amps_recc_iq *h, unsigned long long *out, int ctas);
+/* Test aid, host arithmetic only: the front kernel's dealing of `tiles` 4800-sample tiles (nchan channels; equal_tiles > 0: they
+ * all have that many) to at most `resident` CTAs.  *grid_out CTAs; lo_out[s] = first tile of CTA s for s = 0 .. grid (grid + 1
+ * entries, at most 1025); owner_out[t] = the CTA that owns tile t (tiles entries). */
+AMPS_B200_API int amps_b200_debug_deal(uint32_t tiles, uint32_t resident, uint32_t nchan, uint32_t equal_tiles, uint32_t *grid_out,
+                                       uint32_t *lo_out, uint32_t *owner_out);
 
 /* ------------------------------------------------------------------------------------------
  * Batched calls: K channels (handles) of ONE GPU served by one front launch + one capture launch per call
