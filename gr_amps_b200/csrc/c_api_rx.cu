@@ -399,7 +399,7 @@ static int rx_enqueue10(amps_recc_iq *h, const uint8_t *d_chunk, uint32_t nchunk
     // between one and five tiles per SM a CTA that has its SM to itself gets through its two warm-up tiles and its 2 .. 5 own
     // ones sooner than two CTAs that share the SM get through two warm-up tiles and 1 .. 2 own ones each (measured,
     // tools/grid_probe.py: 1.5 M .. 3.5 M samples 14.5 .. 16.5 us against 15.2 .. 18.0 us; equal at 4.2 M, worse beyond)
-    if (!h->sc16 && tiles > resident && tiles <= 5u * (uint32_t)h->sm_count) resident = (uint32_t)h->sm_count;
+    if (!h->sc16 && h->grid_cap == 0 && tiles > resident && tiles <= 5u * (uint32_t)h->sm_count) resident = (uint32_t)h->sm_count;
     if (h->grid_cap > 0 && resident > (uint32_t)h->grid_cap) resident = (uint32_t)h->grid_cap;
     const uint32_t grid = rx_make_deal(p.deal, tiles, resident);
     const bool timed = (h->flags & AMPS_RX_TIME_KERNELS) != 0;

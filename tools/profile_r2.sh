@@ -17,4 +17,14 @@ AMPS_RX_SERIAL=1 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram_
 # the top kernel, once
 ncu --set full --clock-control none --import-source on -k regex:rx_front_kernel -s 4 -c 1 -f -o gpurun_out/r2_rx_front \
     python tools/rx_pipeline_probe.py 128 3 > gpurun_out/r2_probe.log 2>&1
-ls -la gpurun_out | tail -20
+
+# bench lines (N=1), the reference arm, the forward workload
+python bench.py > gpurun_out/r2_bench_n1.json 2> gpurun_out/r2_bench_a.err
+python bench.py --impl reference > gpurun_out/r2_bench_reference_n1.json 2>> gpurun_out/r2_bench_a.err
+python bench.py --workload fwd > gpurun_out/r2_bench_fwd_n1.json 2>> gpurun_out/r2_bench_a.err
+# where a launch / a call spends its time
+python tools/front_phases.py 16 21 24 28 > gpurun_out/r2_front_phases.jsonl 2>&1
+python tools/call_overheads.py 16 21 23 24 > gpurun_out/r2_call_overheads.jsonl 2>&1
+python tools/search_phases.py 16 40 > gpurun_out/r2_search_phases.jsonl 2>&1
+python tools/search_phases.py 21 8 >> gpurun_out/r2_search_phases.jsonl 2>&1
+python tools/grid_probe.py 1048576,1500000,2097152,3000000,4194304 0,296,148 > gpurun_out/r2_grid_probe_after.jsonl 2>&1   # (0 = the rule, an explicit cap overrides it)
