@@ -63,6 +63,9 @@ struct amps_recc_iq {
     bool         ev_side_valid[kRxDepth] = {};      // ... and whether call k used the side stream at all
     uint64_t     call_no = 0;
     bool         serial = false;         // AMPS_RX_SERIAL=1: no overlap (profiling / A-B measurements)
+    cudaStream_t copy = nullptr;         // host path, big calls: uploads run here, a piece ahead of the kernels on `stream`
+    cudaEvent_t  ev_copy = nullptr;
+    uint32_t     piece = 0;              // samples per uploaded piece (2^24, rounded to the granularity; AMPS_RX_PIECE overrides, 0 = off)
     bool         one_side = false;       // AMPS_RX_ONE_SIDE=1: search and capture share one side stream (A/B measurements)
     bool         front_only = false;     // AMPS_RX_FRONT_ONLY=1: no capture (pipeline measurements only: no bursts come out)
     int          grid_cap = 0;           // AMPS_RX_GRID (test hook): cap on the front kernel's grid
@@ -172,6 +175,8 @@ static int rx_alloc(amps_recc_iq *h) {
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&h->side2, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->ev_front, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->ev_sel, cudaEventDisableTiming));
     for (int i = 0; i < kRxDepth; ++i) CK(cudaEventCreateWithFlags(&h->ev_side[i], cudaEventDisableTiming));
@@ -210,6 +215,7 @@ extern "C" int amps_recc_iq_create(const amps_recc_iq_params *params, amps_recc_
     { const char *e = std::getenv("AMPS_RX_SERIAL"); h->serial = e && e[0] == '1'; }
     { const char *e = std::getenv("AMPS_RX_FRONT_ONLY"); h->front_only = e && e[0] == '1'; }
     { const char *e = std::getenv("AMPS_RX_ONE_SIDE"); h->one_side = e && e[0] == '1'; }
+    { const char *e = std::getenv("AMPS_RX_PIECE"); const long v = e ? std::atol(e) : (1l << 24); h->piece = (uint32_t)(v > 0 ? v : 0); }
     { const char *e = std::getenv("AMPS_RX_GRID"); h->grid_cap = e ? std::atoi(e) : 0; }
     { const char *e = std::getenv("AMPS_RX_NOSEARCH"); h->nosearch = e && e[0] == '1'; }
     { const char *e = std::getenv("AMPS_RX_PROF"); h->want_prof = e && e[0] == '1'; }
@@ -257,6 +263,8 @@ extern "C" int amps_recc_iq_destroy(amps_recc_iq *h) {
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->side) cudaStreamDestroy(h->side);
     if (h->side2) cudaStreamDestroy(h->side2);
+    if (h->copy) cudaStreamDestroy(h->copy);
+    if (h->ev_copy) cudaEventDestroy(h->ev_copy);
     if (h->ev_front) cudaEventDestroy(h->ev_front);
     if (h->ev_sel) cudaEventDestroy(h->ev_sel);
     for (int i = 0; i < kRxDepth; ++i) if (h->ev_side[i]) cudaEventDestroy(h->ev_side[i]);
@@ -640,11 +648,43 @@ static int rx_work(amps_recc_iq *h, const void *iq_host, size_t nsamples, amps_b
     cudaStream_t st = h->stream;
     // the staging buffer of the host path exists from the first host call on (device-resident and batched use never needs it)
     if (!h->d_stage) CK(cudaMalloc(&h->d_stage, ((size_t)h->max_samples + h->gran) * h->isz));
+    h->last_stream = st;
+    const size_t piece = (size_t)(h->piece / h->gran) * h->gran;
+    if (!h->native400 && !h->d_ydump && piece && nsamples >= 2 * piece) {
+        // a big call goes up in pieces on a stream of its own and the kernels of piece i run while piece i+1 is on the link:
+        // what the caller waits for after the last byte has arrived is one piece's kernels, not the whole call's
+        const uint8_t *src = static_cast<const uint8_t *>(iq_host);
+        size_t up = 0, enq = 0;                          // samples uploaded / samples handed to the kernels (staging coordinates)
+        while (up < nsamples) {
+            size_t n = nsamples - up;
+            if (n >= 2 * piece) n = piece;               // (the last piece is between one and two pieces long)
+            CK(cudaMemcpyAsync(h->d_stage + (h->carry + up) * h->isz, src + up * h->isz, n * h->isz, cudaMemcpyHostToDevice, h->copy));
+            CK(cudaEventRecord(h->ev_copy, h->copy));
+            CK(cudaStreamWaitEvent(st, h->ev_copy, 0));
+            up += n;
+            const size_t nq = (h->carry + up - enq) / h->gran;
+            if (nq) {
+                int rc = rx_enqueue10(h, h->d_stage + enq * h->isz, (uint32_t)(nq * h->gran), st, /*in_order=*/true);
+                if (rc != AMPS_OK) return rc;
+                enq += nq * h->gran;
+            }
+        }
+        const size_t left = h->carry + nsamples - enq;
+        if (left) CK(cudaMemcpyAsync(h->d_stage, h->d_stage + enq * h->isz, left * h->isz, cudaMemcpyDeviceToDevice, st));
+        h->carry = left;
+        uint64_t nb = 0;
+        bool ovf = false;
+        int rc = rx_fetch(h, &nb, &ovf);
+        if (rc != AMPS_OK) return rc;
+        if (cb) for (uint64_t i = 0; i < nb; ++i) cb(&h->h_ring[(h->consumed + i) % h->max_records], user);
+        h->consumed += nb;
+        h->bursts += nb;
+        return ovf ? overflow_status(h) : AMPS_OK;
+    }
     if (nsamples)
         CK(cudaMemcpyAsync(h->d_stage + h->carry * h->isz, iq_host, nsamples * h->isz, cudaMemcpyHostToDevice, st));
     const size_t avail = h->carry + nsamples;
     const uint32_t nq = (uint32_t)(avail / h->gran);       // whole processing quanta (units at 10 MS/s, passes at 400 kS/s)
-    h->last_stream = st;
     if (nq) {
         int rc = h->native400 ? rx_enqueue400(h, h->d_stage, nq, st) : rx_enqueue10(h, h->d_stage, nq * h->gran, st, /*in_order=*/true);
         if (rc != AMPS_OK) return rc;

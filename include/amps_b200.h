@@ -150,6 +150,8 @@ AMPS_B200_API int amps_recc_iq_reset(amps_recc_iq *h);          /* back to strea
  * lib/recc_impl.cc:126); the records arrive in a pinned host ring the capture kernel writes into.  Any
  * nsamples >= 0 is accepted; samples that do not fill a processing quantum (amps_recc_iq_granularity():
  * 1600 samples = 32 demodulated samples at 10 MS/s, 1536 at 400 kS/s) are carried to the next call.
+ * A 10 MS/s call of 2^25 samples or more is uploaded in pieces of 2^24 samples on a stream of its own while the
+ * kernels of the piece before run (same results; what is left to wait for after the last byte is one piece's kernels).
  * Returns AMPS_E_OVERFLOW ONCE (after delivering what was captured) when the device-side list of
  * undecided trigger candidates overflowed (> 8192) and candidates had to be dropped; the stream goes on. */
 AMPS_B200_API int amps_recc_iq_work(amps_recc_iq *h, const float *iq_host, size_t nsamples,

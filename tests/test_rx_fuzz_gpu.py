@@ -152,3 +152,34 @@ def test_mixed_call_sizes_pipelined(capi, oracle, collect_between):
     check(got, ob, oracle)
     assert [g.demod_index for g in got] == sorted(g.demod_index for g in got)
     rx.close()
+
+
+@pytest.mark.parametrize("sc16", [False, True])
+def test_host_path_uploads_big_calls_in_pieces(capi, oracle, stream, sc16, monkeypatch):
+    """amps_recc_iq_work on a call of at least two upload pieces (AMPS_RX_PIECE, 2^24 samples by default, 300 000 here): the
+    pieces go up on a copy stream while the kernels of the piece before run -- same stream, same bursts, ragged call lengths."""
+    x, d_orc, ob = stream
+    scale = 1.0 / 8192.0
+    monkeypatch.setenv("AMPS_RX_PIECE", "300000")
+    if sc16:
+        q = np.clip(np.round(x.view(np.float32) / scale), -32768, 32767).astype(np.int16)
+        xq = (q.astype(np.float32) * np.float32(scale)).view(np.complex64)
+        _, d_orc = oracle.rx_chain_f32(xq)
+        ob = oracle.rx_detect(d_orc)
+        rx = capi.ReccIq(max_samples=len(x), sc16=True, sc16_scale=scale)
+        cuts = [0, 2500001 * 2, 2500001 * 2 + 4 * 150001, 2 * len(x)]          # (int16 counts: whole I,Q pairs)
+        got = []
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            got += rx.work(q[a:b])
+    else:
+        rx = capi.ReccIq(max_samples=len(x))
+        cuts = [0, 2500001, 2500001 + 599999, 2500001 + 599999 + 17, len(x)]    # big (8 pieces), just under two pieces, tiny, big
+        got = []
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            got += rx.work(x[a:b])
+    nd = rx.stats()["demod_out"]
+    assert nd == len(x) // 50
+    assert bits_equal_f32(rx.read_demod(nd - 60000, 60000), d_orc[nd - 60000:nd])
+    check(got, ob, oracle)
+    assert rx.stats()["kernel_launches"] > 3 * 8
+    rx.close()
