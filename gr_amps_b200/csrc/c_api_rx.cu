@@ -648,6 +648,11 @@ static int rx_work(amps_recc_iq *h, const void *iq_host, size_t nsamples, amps_b
     cudaStream_t st = h->stream;
     // the staging buffer of the host path exists from the first host call on (device-resident and batched use never needs it)
     if (!h->d_stage) CK(cudaMalloc(&h->d_stage, ((size_t)h->max_samples + h->gran) * h->isz));
+    // a caller that used submit_dev() before and did not collect: this call's kernels run in order on `st`, behind whatever
+    // search / capture work of those calls is still on the side streams
+    for (int i = 0; i < kRxDepth; ++i)
+        if (h->ev_side_valid[i]) { CK(cudaStreamWaitEvent(st, h->ev_side[i], 0)); h->ev_side_valid[i] = false; }
+    h->cap_par = -1;
     h->last_stream = st;
     const size_t piece = (size_t)(h->piece / h->gran) * h->gran;
     if (!h->native400 && !h->d_ydump && piece && nsamples >= 2 * piece) {

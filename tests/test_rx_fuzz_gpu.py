@@ -183,3 +183,26 @@ def test_host_path_uploads_big_calls_in_pieces(capi, oracle, stream, sc16, monke
     check(got, ob, oracle)
     assert rx.stats()["kernel_launches"] > 3 * 8
     rx.close()
+
+
+def test_device_calls_then_host_calls_without_collect(capi, oracle, stream):
+    """submit_dev() calls still in flight on the side streams when the caller switches to amps_recc_iq_work(): the host-path
+    call is ordered behind them (whole units only, so that nothing is pending in the device-side carry)."""
+    torch = pytest.importorskip("torch")
+    x, d_orc, ob = stream
+    rx = capi.ReccIq(max_samples=2400000)
+    t = torch.from_numpy(x.view(np.float32).copy()).cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    pos = 0
+    for n in (1600 * 1400, 1600 * 40, 1600 * 1100):          # one with its own capture launch, two that capture by themselves
+        rx.submit_dev(t.data_ptr() + 8 * pos, n, st)
+        pos += n
+    got = []
+    while pos < len(x):
+        n = min(777777, len(x) - pos)
+        got += rx.work(x[pos:pos + n])
+        pos += n
+    got += rx.collect()
+    assert rx.stats()["demod_out"] == len(x) // 50
+    check(sorted(got, key=lambda g: g.demod_index), ob, oracle)
+    rx.close()
